@@ -1,0 +1,710 @@
+// libb2r.so - C ABI (include/b2r.h) and host orchestration of the B200 rendering path.
+//
+// One frame = one fixed sequence of kernels on one stream, no host synchronisation and no
+// device->host round trip inside it (the reference needs ceil(visible/256) batches with a
+// cudaDeviceSynchronize after every launch, CUDARenderer.cu:237-330):
+//
+//   H2D   per-mesh constants (WVP computed on the host exactly like CUDARenderer.cu:242)
+//   K1    vertex_transform_kernel      IVertex -> pos4 + attr
+//   K2    triangle_setup_kernel        cull / frustum / screen / bbox / bin rect / tile counts
+//   K3    bin_big_kernel<count>        cooperative counting of large rectangles
+//   K4    tile_scan_kernel             exclusive scan of the tile counts
+//   K5    bin_scatter_kernel           ids of small rectangles -> lists
+//   K6    bin_big_kernel<scatter>      ids of large rectangles -> lists
+//   K7/8  bin_sort_kernel(+long)       canonical (ascending id) order per tile
+//   K9    raster_shade_kernel          coverage + depth resolve + deferred shade + ROP write-back
+#include "../../include/b2r.h"
+#include "device_types.cuh"
+#include "geometry_kernels.cuh"
+#include "raster_kernel.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace b2r;
+
+namespace {
+
+thread_local std::string g_createError;
+
+// grow-only device array
+template <typename T>
+struct DeviceVec
+{
+	T* ptr = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n, cudaStream_t s, size_t keep = 0)
+	{
+		if (n <= cap) return cudaSuccess;
+		size_t newCap = std::max(n, cap + cap / 2);
+		T* np = nullptr;
+		cudaError_t e = cudaMalloc((void**)&np, newCap * sizeof(T));
+		if (e != cudaSuccess) return e;
+		if (keep && ptr)
+		{
+			e = cudaMemcpyAsync(np, ptr, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+			if (e != cudaSuccess) { cudaFree(np); return e; }
+		}
+		cudaFree(ptr);
+		ptr = np; cap = newCap;
+		return cudaSuccess;
+	}
+	void release() { cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct HostMesh
+{
+	uint32_t vtxInBase, vtxOutBase, nVertices, idxBase, nTris, primBase;
+	float world[16];
+	int texIds[4];
+};
+
+struct HostTexture { uint32_t* px = nullptr; uint32_t w = 0, h = 0; bool alive = false; };
+
+struct RenderCall
+{
+	float camPos[3], camFwd[3], viewProj[16], clearRGB[3];
+	int cull, sample, vis;
+	bool valid = false;
+};
+
+}
+
+struct b2r_context
+{
+	int device = 0;
+	uint32_t width = 0, height = 0;
+	uint32_t binsX = 0, binsY = 0, binW = kTile, binH = kTile;
+	cudaStream_t ownStream = nullptr, stream = nullptr;
+	std::string error;
+
+	// options
+	int fillTopLeft = 1, ownerRank = 0, ownerCount = 1, debugSurfaces = 0, stageTimers = 0, sortBins = 1;
+
+	// scene
+	std::vector<HostMesh> meshes;
+	std::vector<HostTexture> textures;
+	size_t nVtxIn = 0, nVtxOut = 0, nIdx = 0, nPrims = 0;
+	bool sceneDirty = true, texDirty = true;
+	DeviceVec<float2> dIVertex;        // 7 float2 per vertex
+	DeviceVec<uint32_t> dIndices;
+	DeviceVec<float4> dPos4, dAttr;    // attr: 4 float4 per vertex
+	DeviceVec<TriRecord> dRecords;
+	DeviceVec<TriAux> dAux;
+	DeviceVec<uint2> dRects;
+	DeviceVec<Chunk> dVsChunks, dTriChunks;
+	uint32_t nVsChunks = 0, nTriChunks = 0;
+	DeviceVec<MeshConst> dMeshConst;
+	MeshConst* hMeshConst = nullptr; size_t hMeshConstCap = 0;   // pinned staging
+	DeviceVec<TexDesc> dTexDesc;
+
+	// binning
+	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dBigList, dBinIds;
+	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
+	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles
+	struct HostInfo { unsigned long long frameInfo[4]; uint32_t counters[2]; } *hInfo = nullptr;   // pinned
+
+	// surfaces
+	uint32_t* dFramebuffer = nullptr; int32_t* dDepth = nullptr; float* dZ = nullptr; uint32_t* dWinner = nullptr;
+	uint32_t* boundFramebuffer = nullptr;
+
+	// frame state
+	RenderCall last;
+	bool framePending = false;      // a frame was enqueued and its info not yet validated
+	bool haveFrame = false;
+	cudaEvent_t ev[B2R_NUM_STAGES + 1] = {};
+	bool evRecorded = false;
+	uint64_t kernelsLaunched = 0;
+	int numSMs = 148;
+};
+
+namespace {
+
+int fail(b2r_context* c, int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	if (c) c->error = buf; else g_createError = buf;
+	return code;
+}
+#define CU(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((c), B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+uint32_t nBins(const b2r_context* c) { return c->binsX * c->binsY; }
+
+// projection * Inverse(lookAt) * world on the HOST, element order of Matrix4.h:120-143
+void mulMat4(const float* lm, const float* rm, float* out)
+{
+	for (int r = 0; r < 4; ++r)
+		for (int col = 0; col < 4; ++col)
+			out[col * 4 + r] = lm[0 * 4 + r] * rm[col * 4 + 0] + lm[1 * 4 + r] * rm[col * 4 + 1] +
+			                   lm[2 * 4 + r] * rm[col * 4 + 2] + lm[3 * 4 + r] * rm[col * 4 + 3];
+}
+
+int allocSurfaces(b2r_context* c)
+{
+	const size_t n = (size_t)c->width * c->height;
+	CU(c, cudaMalloc((void**)&c->dFramebuffer, n * 4));
+	CU(c, cudaMalloc((void**)&c->dDepth, n * 4));
+	CU(c, cudaMemset(c->dFramebuffer, 0, n * 4));     // CUDAWindowHelper.h:17-25 zero-initialises
+	CU(c, cudaMemset(c->dDepth, 0, n * 4));
+	return B2R_OK;
+}
+
+int ensureDebugSurfaces(b2r_context* c)
+{
+	const size_t n = (size_t)c->width * c->height;
+	if (!c->dZ) { CU(c, cudaMalloc((void**)&c->dZ, n * 4)); CU(c, cudaMemset(c->dZ, 0, n * 4)); }
+	if (!c->dWinner) { CU(c, cudaMalloc((void**)&c->dWinner, n * 4)); CU(c, cudaMemset(c->dWinner, 0xFF, n * 4)); }
+	return B2R_OK;
+}
+
+int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
+{
+	if (!bx || !by || !bw || !bh) return fail(c, B2R_E_INVALID, "bin grid and bin size must be non-zero");
+	if ((uint64_t)bx * bw < c->width || (uint64_t)by * bh < c->height)
+		return fail(c, B2R_E_INVALID, "bins (%ux%u of %ux%u) must cover the %ux%u screen", bx, by, bw, bh, c->width, c->height);
+	if (bx > 32767 || by > 32767) return fail(c, B2R_E_INVALID, "too many bins");
+	c->binsX = bx; c->binsY = by; c->binW = bw; c->binH = bh;
+	const uint32_t n = bx * by;
+	CU(c, c->dTileCount.reserve(n, c->stream));
+	CU(c, c->dTileOffset.reserve(n, c->stream));
+	CU(c, c->dTileCursor.reserve(n, c->stream));
+	CU(c, c->dLongTiles.reserve(n, c->stream));
+	return B2R_OK;
+}
+
+bool texValid(const b2r_context* c, int id) { return id >= 0 && (size_t)id < c->textures.size() && c->textures[id].alive; }
+
+// chunk tables + stream sizes after the mesh list changed
+int rebuildScene(b2r_context* c)
+{
+	std::vector<Chunk> vs, tri;
+	for (size_t m = 0; m < c->meshes.size(); ++m)
+	{
+		const HostMesh& hm = c->meshes[m];
+		for (uint32_t f = 0; f < hm.nVertices; f += kChunk) vs.push_back(Chunk{ (uint32_t)m, f });
+		for (uint32_t f = 0; f < hm.nTris; f += kChunk) tri.push_back(Chunk{ (uint32_t)m, f });
+	}
+	c->nVsChunks = (uint32_t)vs.size(); c->nTriChunks = (uint32_t)tri.size();
+	CU(c, c->dVsChunks.reserve(std::max<size_t>(vs.size(), 1), c->stream));
+	CU(c, c->dTriChunks.reserve(std::max<size_t>(tri.size(), 1), c->stream));
+	if (!vs.empty()) CU(c, cudaMemcpyAsync(c->dVsChunks.ptr, vs.data(), vs.size() * sizeof(Chunk), cudaMemcpyHostToDevice, c->stream));
+	if (!tri.empty()) CU(c, cudaMemcpyAsync(c->dTriChunks.ptr, tri.data(), tri.size() * sizeof(Chunk), cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));   // vs/tri are host temporaries
+	CU(c, c->dPos4.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
+	CU(c, c->dAttr.reserve(std::max<size_t>(c->nVtxOut, 1) * 4, c->stream));
+	CU(c, c->dRecords.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	CU(c, c->dAux.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	CU(c, c->dRects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	CU(c, c->dBigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	CU(c, c->dMeshConst.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
+	if (c->hMeshConstCap < c->meshes.size())
+	{
+		if (c->hMeshConst) cudaFreeHost(c->hMeshConst);
+		c->hMeshConstCap = std::max<size_t>(c->meshes.size() * 2, 16);
+		CU(c, cudaMallocHost((void**)&c->hMeshConst, c->hMeshConstCap * sizeof(MeshConst)));
+	}
+	// list capacity heuristic; regrown on overflow (see validateFrame)
+	CU(c, c->dBinIds.reserve(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), c->stream));
+	c->sceneDirty = false;
+	return B2R_OK;
+}
+
+int rebuildTextures(b2r_context* c)
+{
+	std::vector<TexDesc> td(std::max<size_t>(c->textures.size(), 1), TexDesc{ nullptr, 0, 0 });
+	for (size_t i = 0; i < c->textures.size(); ++i)
+		if (c->textures[i].alive) td[i] = TexDesc{ c->textures[i].px, c->textures[i].w, c->textures[i].h };
+	CU(c, c->dTexDesc.reserve(td.size(), c->stream));
+	CU(c, cudaMemcpyAsync(c->dTexDesc.ptr, td.data(), td.size() * sizeof(TexDesc), cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	c->texDirty = false;
+	return B2R_OK;
+}
+
+FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
+{
+	FrameParams fp{};
+	for (int i = 0; i < 3; ++i) { fp.camPos[i] = rc.camPos[i]; fp.camFwd[i] = rc.camFwd[i]; fp.clearRGB[i] = rc.clearRGB[i]; }
+	fp.width = c->width; fp.height = c->height;
+	fp.binsX = c->binsX; fp.binsY = c->binsY; fp.binW = c->binW; fp.binH = c->binH;
+	fp.subX = (c->binW + kTile - 1) / kTile; fp.subY = (c->binH + kTile - 1) / kTile;
+	fp.cullMode = (uint32_t)rc.cull; fp.sampleState = (uint32_t)rc.sample; fp.visState = (uint32_t)rc.vis;
+	fp.fillTopLeft = (uint32_t)c->fillTopLeft;
+	fp.ownerRank = (uint32_t)c->ownerRank; fp.ownerCount = (uint32_t)c->ownerCount;
+	fp.debugSurfaces = (uint32_t)c->debugSurfaces;
+	fp.bigRectTiles = 64;
+	return fp;
+}
+
+#define STAGE_EVENT(c, i) do { if ((c)->stageTimers) CU((c), cudaEventRecord((c)->ev[(i)], (c)->stream)); } while (0)
+
+int enqueueFrame(b2r_context* c)
+{
+	const RenderCall& rc = c->last;
+	if (c->sceneDirty) { int r = rebuildScene(c); if (r) return r; }
+	if (c->texDirty) { int r = rebuildTextures(c); if (r) return r; }
+	if (c->debugSurfaces) { int r = ensureDebugSurfaces(c); if (r) return r; }
+	cudaStream_t s = c->stream;
+	const FrameParams fp = makeParams(c, rc);
+	const uint32_t tiles = nBins(c);
+	c->kernelsLaunched = 0;
+
+	// per-mesh constants
+	for (size_t m = 0; m < c->meshes.size(); ++m)
+	{
+		const HostMesh& hm = c->meshes[m];
+		MeshConst& mc = c->hMeshConst[m];
+		mulMat4(rc.viewProj, hm.world, mc.wvp);
+		memcpy(mc.world, hm.world, 64);
+		for (int col = 0; col < 3; ++col) for (int r = 0; r < 3; ++r) mc.rot[col * 3 + r] = hm.world[col * 4 + r];
+		mc.vtxInBase = hm.vtxInBase; mc.vtxOutBase = hm.vtxOutBase; mc.nVertices = hm.nVertices;
+		mc.idxBase = hm.idxBase; mc.nTris = hm.nTris; mc.primBase = hm.primBase;
+		// CUDARenderer.cu:559-571: Norm only with Diff, Spec/Gloss only with Norm
+		const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);
+		mc.tex[0] = d ? hm.texIds[0] : -1;
+		mc.tex[1] = n ? hm.texIds[1] : -1;
+		mc.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
+		mc.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
+		mc.pad = 0;
+	}
+	if (c->stageTimers) CU(c, cudaEventRecord(c->ev[0], s));
+	if (!c->meshes.empty())
+		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, c->hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
+	CU(c, cudaMemsetAsync(c->dTileCount.ptr, 0, tiles * 4, s));
+	CU(c, cudaMemsetAsync(c->dCounters, 0, 8, s));
+
+	if (c->nVsChunks)
+	{
+		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, c->dMeshConst.ptr, c->dIVertex.ptr, c->dPos4.ptr, c->dAttr.ptr, fp);
+		++c->kernelsLaunched;
+	}
+	STAGE_EVENT(c, 1);
+	if (c->nTriChunks)
+	{
+		triangle_setup_kernel<<<c->nTriChunks, kChunk, 0, s>>>(c->dTriChunks.ptr, c->dMeshConst.ptr, c->dIndices.ptr, c->dPos4.ptr,
+			c->dRecords.ptr, c->dAux.ptr, c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, fp);
+		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, fp);
+		c->kernelsLaunched += 2;
+	}
+	STAGE_EVENT(c, 2);
+	tile_scan_kernel<<<1, 1024, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dTileCursor.ptr, tiles,
+		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortSmall, c->dLongTiles.ptr, c->dFrameInfo);
+	++c->kernelsLaunched;
+	STAGE_EVENT(c, 3);
+	if (c->nPrims)
+	{
+		bin_scatter_kernel<<<(uint32_t)((c->nPrims + 255) / 256), 256, 0, s>>>(c->dRects.ptr, (uint32_t)c->nPrims, c->dTileOffset.ptr,
+			c->dTileCursor.ptr, c->dBinIds.ptr, c->dFrameInfo, fp);
+		bin_big_kernel<true><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, nullptr, c->dTileOffset.ptr,
+			c->dTileCursor.ptr, c->dBinIds.ptr, fp);
+		c->kernelsLaunched += 2;
+	}
+	STAGE_EVENT(c, 4);
+	if (c->sortBins && c->nPrims)
+	{
+		bin_sort_kernel<<<tiles, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
+		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLarge * sizeof(uint32_t), s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,
+			c->dBinIds.ptr, c->dFrameInfo);
+		c->kernelsLaunched += 2;
+	}
+	STAGE_EVENT(c, 5);
+	{
+		RasterArgs A{};
+		A.tileCount = c->dTileCount.ptr; A.tileOffset = c->dTileOffset.ptr; A.binIds = c->dBinIds.ptr;
+		A.records = c->dRecords.ptr; A.aux = c->dAux.ptr; A.pos4 = c->dPos4.ptr; A.attr = c->dAttr.ptr;
+		A.meshes = c->dMeshConst.ptr; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
+		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer;
+		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
+		const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
+		if (owned)
+		{
+			const dim3 grid(owned, fp.subX * fp.subY);
+			if (c->fillTopLeft) raster_shade_kernel<true><<<grid, kTile * kTile, 0, s>>>(A, fp);
+			else raster_shade_kernel<false><<<grid, kTile * kTile, 0, s>>>(A, fp);
+			++c->kernelsLaunched;
+		}
+	}
+	STAGE_EVENT(c, 6);
+	c->evRecorded = c->stageTimers != 0;
+	CU(c, cudaMemcpyAsync(c->hInfo->frameInfo, c->dFrameInfo, 32, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaMemcpyAsync(c->hInfo->counters, c->dCounters, 8, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaGetLastError());
+	c->framePending = true;
+	c->haveFrame = true;
+	return B2R_OK;
+}
+
+// wait for the frame; if the bin-list buffer was too small, grow it and run the frame again
+int validateFrame(b2r_context* c)
+{
+	for (int attempt = 0; attempt < 4; ++attempt)
+	{
+		CU(c, cudaStreamSynchronize(c->stream));
+		if (!c->framePending) return B2R_OK;
+		c->framePending = false;
+		if (!c->hInfo->frameInfo[1]) return B2R_OK;
+		const size_t need = (size_t)c->hInfo->frameInfo[0];
+		CU(c, c->dBinIds.reserve(need + need / 4, c->stream));
+		int r = enqueueFrame(c);
+		if (r) return r;
+	}
+	return fail(c, B2R_E_STATE, "bin list capacity could not be satisfied");
+}
+
+}
+
+// =======================================================================================
+extern "C" {
+
+const char* b2r_last_error(const b2r_context* ctx)
+{
+	return ctx ? ctx->error.c_str() : g_createError.c_str();
+}
+
+int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
+{
+	if (!out) return fail(nullptr, B2R_E_INVALID, "out is null");
+	*out = nullptr;
+	if (!width || !height || width > 32767 || height > 32767)
+		return fail(nullptr, B2R_E_INVALID, "resolution %ux%u out of range (bounding boxes are 16-bit, BoundingBox.h:4-10)", width, height);
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+		return fail(nullptr, B2R_E_NO_DEVICE, "no CUDA device: this renderer has no CPU fallback");
+	if (device < 0 || device >= count) return fail(nullptr, B2R_E_INVALID, "device %d out of range (%d devices)", device, count);
+	b2r_context* c = new (std::nothrow) b2r_context;
+	if (!c) return fail(nullptr, B2R_E_INVALID, "out of host memory");
+	c->device = device; c->width = width; c->height = height;
+	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
+	CUC(cudaSetDevice(device));
+	CUC(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device));
+	CUC(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+	c->stream = c->ownStream;
+	for (auto& e : c->ev) CUC(cudaEventCreate(&e));
+	CUC(cudaMalloc((void**)&c->dCounters, 8));
+	CUC(cudaMalloc((void**)&c->dFrameInfo, 32));
+	CUC(cudaMemset(c->dFrameInfo, 0, 32));
+	CUC(cudaMallocHost((void**)&c->hInfo, sizeof(*c->hInfo)));
+	memset(c->hInfo, 0, sizeof(*c->hInfo));
+	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortLarge * sizeof(uint32_t))));
+#undef CUC
+	int r = allocSurfaces(c);
+	if (r) return bail(r);
+	r = setBins(c, (width + kTile - 1) / kTile, (height + kTile - 1) / kTile, kTile, kTile);
+	if (r) return bail(r);
+	*out = c;
+	return B2R_OK;
+}
+
+void b2r_destroy(b2r_context* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
+	c->dIVertex.release(); c->dIndices.release(); c->dPos4.release(); c->dAttr.release();
+	c->dRecords.release(); c->dAux.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
+	c->dMeshConst.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
+	c->dTileCursor.release(); c->dLongTiles.release(); c->dBigList.release(); c->dBinIds.release();
+	cudaFree(c->dCounters); cudaFree(c->dFrameInfo);
+	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
+	if (c->hMeshConst) cudaFreeHost(c->hMeshConst);
+	if (c->hInfo) cudaFreeHost(c->hInfo);
+	for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+	if (c->ownStream) cudaStreamDestroy(c->ownStream);
+	delete c;
+}
+
+int b2r_setup_bins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh, uint32_t /*queue_max_size*/)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	return setBins(c, bx, by, bw, bh);
+}
+
+int b2r_texture_create_rgba8(b2r_context* c, const uint32_t* pixels, uint32_t w, uint32_t h, int* outId)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!pixels || !w || !h || !outId) return fail(c, B2R_E_INVALID, "texture arguments invalid");
+	CU(c, cudaSetDevice(c->device));
+	HostTexture t; t.w = w; t.h = h; t.alive = true;
+	CU(c, cudaMalloc((void**)&t.px, (size_t)w * h * 4));
+	cudaError_t e = cudaMemcpy(t.px, pixels, (size_t)w * h * 4, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cudaFree(t.px); return fail(c, B2R_E_CUDA, "texture upload failed: %s", cudaGetErrorString(e)); }
+	c->textures.push_back(t);
+	c->texDirty = true;
+	*outId = (int)c->textures.size() - 1;
+	return B2R_OK;
+}
+
+int b2r_texture_destroy(b2r_context* c, int id)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!texValid(c, id)) return fail(c, B2R_E_INVALID, "texture id %d is not alive", id);
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	cudaFree(c->textures[id].px);
+	c->textures[id] = HostTexture{};
+	c->texDirty = true;
+	return B2R_OK;
+}
+
+static int addMesh(b2r_context* c, HostMesh hm, const float world[16], const int tex[4], int* outId)
+{
+	memcpy(hm.world, world, 64);
+	for (int i = 0; i < 4; ++i) hm.texIds[i] = tex ? tex[i] : -1;
+	hm.vtxOutBase = (uint32_t)c->nVtxOut; hm.primBase = (uint32_t)c->nPrims;
+	if (c->nVtxOut + hm.nVertices > 0xFFFFFFF0ull || c->nPrims + hm.nTris > 0xFFFFFFF0ull)
+		return fail(c, B2R_E_INVALID, "scene exceeds 2^32 vertices or primitives");
+	c->nVtxOut += hm.nVertices; c->nPrims += hm.nTris;
+	c->meshes.push_back(hm);
+	c->sceneDirty = true;
+	if (outId) *outId = (int)c->meshes.size() - 1;
+	return B2R_OK;
+}
+
+int b2r_mesh_upload(b2r_context* c, const void* ivertex56, uint32_t nV, const uint32_t* indices, uint32_t nI, int topology,
+                    const float world[16], const int tex[4], int* outId)
+{
+	if (!c) return B2R_E_INVALID;
+	if (topology != B2R_TOPOLOGY_TRIANGLE_LIST)
+		return fail(c, B2R_E_UNSUPPORTED, "only TriangleList is supported (TriangleStrip is broken on the reference GPU path, CUDARenderer.cu:733-753)");
+	if (!world || (nV && !ivertex56) || (nI && !indices)) return fail(c, B2R_E_INVALID, "null mesh argument");
+	for (uint32_t i = 0; i < nI - nI % 3; ++i)
+		if (indices[i] >= nV) return fail(c, B2R_E_INVALID, "index %u = %u out of range (%u vertices)", i, indices[i], nV);
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	CU(c, c->dIVertex.reserve((c->nVtxIn + nV) * 7 + 1, c->stream, c->nVtxIn * 7));
+	CU(c, c->dIndices.reserve(c->nIdx + nI + 1, c->stream, c->nIdx));
+	if (nV) CU(c, cudaMemcpy(c->dIVertex.ptr + c->nVtxIn * 7, ivertex56, (size_t)nV * 56, cudaMemcpyHostToDevice));
+	if (nI) CU(c, cudaMemcpy(c->dIndices.ptr + c->nIdx, indices, (size_t)nI * 4, cudaMemcpyHostToDevice));
+	HostMesh hm{};
+	hm.vtxInBase = (uint32_t)c->nVtxIn; hm.nVertices = nV; hm.idxBase = (uint32_t)c->nIdx; hm.nTris = nI / 3;
+	c->nVtxIn += nV; c->nIdx += nI;
+	return addMesh(c, hm, world, tex, outId);
+}
+
+int b2r_mesh_instance(b2r_context* c, int src, const float world[16], const int tex[4], int* outId)
+{
+	if (!c) return B2R_E_INVALID;
+	if (src < 0 || (size_t)src >= c->meshes.size() || !world) return fail(c, B2R_E_INVALID, "bad source mesh id %d", src);
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	HostMesh hm = c->meshes[src];
+	return addMesh(c, hm, world, tex ? tex : c->meshes[src].texIds, outId);
+}
+
+int b2r_mesh_set_world(b2r_context* c, int id, const float world[16])
+{
+	if (!c) return B2R_E_INVALID;
+	if (id < 0 || (size_t)id >= c->meshes.size() || !world) return fail(c, B2R_E_INVALID, "bad mesh id %d", id);
+	memcpy(c->meshes[id].world, world, 64);
+	return B2R_OK;
+}
+
+int b2r_mesh_clear_all(b2r_context* c)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	c->meshes.clear();
+	c->nVtxIn = c->nVtxOut = c->nIdx = c->nPrims = 0;
+	c->sceneDirty = true;
+	return B2R_OK;
+}
+
+int b2r_set_option(b2r_context* c, int option, int value)
+{
+	if (!c) return B2R_E_INVALID;
+	switch (option)
+	{
+	case B2R_OPT_FILL_RULE_TOP_LEFT: c->fillTopLeft = value ? 1 : 0; break;
+	case B2R_OPT_TILE_OWNER_RANK: if (value < 0) return fail(c, B2R_E_INVALID, "rank < 0"); c->ownerRank = value; break;
+	case B2R_OPT_TILE_OWNER_COUNT: if (value < 1) return fail(c, B2R_E_INVALID, "count < 1"); c->ownerCount = value; break;
+	case B2R_OPT_DEBUG_SURFACES: c->debugSurfaces = value ? 1 : 0; break;
+	case B2R_OPT_STAGE_TIMERS: c->stageTimers = value ? 1 : 0; break;
+	case B2R_OPT_SORT_BINS: c->sortBins = value ? 1 : 0; break;
+	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
+	}
+	if (c->ownerRank >= c->ownerCount) { /* tolerated while the pair is being set; checked at render */ }
+	return B2R_OK;
+}
+
+int b2r_render(b2r_context* c, const float camPos[3], const float camFwd[3], const float viewProj[16],
+               int cull, int sample, int vis, const float clearRGB[3])
+{
+	if (!c) return B2R_E_INVALID;
+	if (!camPos || !camFwd || !viewProj) return fail(c, B2R_E_INVALID, "null camera argument");
+	if (cull < 0 || cull > 2 || sample < 0 || sample > 1 || vis < 0 || vis > 2) return fail(c, B2R_E_INVALID, "bad render state");
+	if (c->ownerRank >= c->ownerCount) return fail(c, B2R_E_INVALID, "tile owner rank %d >= count %d", c->ownerRank, c->ownerCount);
+	CU(c, cudaSetDevice(c->device));
+	if (c->framePending)
+	{
+		// the previous frame's pinned info block is about to be overwritten: settle it first
+		int r = validateFrame(c); if (r) return r;
+	}
+	RenderCall& rc = c->last;
+	memcpy(rc.camPos, camPos, 12); memcpy(rc.camFwd, camFwd, 12); memcpy(rc.viewProj, viewProj, 64);
+	static const float defClear[3] = { 0.25f, 0.25f, 0.25f };   // CUDARenderer.h:135
+	memcpy(rc.clearRGB, clearRGB ? clearRGB : defClear, 12);
+	rc.cull = cull; rc.sample = sample; rc.vis = vis; rc.valid = true;
+	return enqueueFrame(c);
+}
+
+int b2r_sync(b2r_context* c)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	return validateFrame(c);
+}
+
+static int readSurface(b2r_context* c, const void* src, void* out, const char* what)
+{
+	if (!out) return fail(c, B2R_E_INVALID, "null output");
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "%s: nothing rendered yet", what);
+	if (!src) return fail(c, B2R_E_STATE, "%s: surface not enabled (B2R_OPT_DEBUG_SURFACES)", what);
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	CU(c, cudaMemcpyAsync(out, src, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return B2R_OK;
+}
+
+int b2r_read_framebuffer(b2r_context* c, uint32_t* out)
+{
+	if (!c) return B2R_E_INVALID;
+	return readSurface(c, c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer, out, "read_framebuffer");
+}
+int b2r_read_depth(b2r_context* c, int32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dDepth, out, "read_depth"); }
+int b2r_read_z(b2r_context* c, float* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dZ, out, "read_z"); }
+int b2r_read_winner(b2r_context* c, uint32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dWinner, out, "read_winner"); }
+
+int b2r_read_overtex(b2r_context* c, int id, float* out18)
+{
+	if (!c) return B2R_E_INVALID;
+	if (id < 0 || (size_t)id >= c->meshes.size() || !out18) return fail(c, B2R_E_INVALID, "bad mesh id %d", id);
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "read_overtex: nothing rendered yet");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	const HostMesh& hm = c->meshes[id];
+	std::vector<float4> pos(hm.nVertices), attr((size_t)hm.nVertices * 4);
+	if (hm.nVertices)
+	{
+		CU(c, cudaMemcpy(pos.data(), c->dPos4.ptr + hm.vtxOutBase, (size_t)hm.nVertices * 16, cudaMemcpyDeviceToHost));
+		CU(c, cudaMemcpy(attr.data(), c->dAttr.ptr + (size_t)hm.vtxOutBase * 4, (size_t)hm.nVertices * 64, cudaMemcpyDeviceToHost));
+	}
+	for (uint32_t v = 0; v < hm.nVertices; ++v)
+	{
+		float* o = out18 + (size_t)v * 18;
+		const float* a = reinterpret_cast<const float*>(&attr[(size_t)v * 4]);
+		o[0] = pos[v].x; o[1] = pos[v].y; o[2] = pos[v].z; o[3] = pos[v].w;
+		memcpy(o + 4, a, 14 * sizeof(float));     // uv2 n3 tan3 vd3 c3
+	}
+	return B2R_OK;
+}
+
+int b2r_read_visible(b2r_context* c, int id, uint8_t* out)
+{
+	if (!c) return B2R_E_INVALID;
+	if (id < 0 || (size_t)id >= c->meshes.size() || !out) return fail(c, B2R_E_INVALID, "bad mesh id %d", id);
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "read_visible: nothing rendered yet");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	const HostMesh& hm = c->meshes[id];
+	std::vector<uint2> rc(hm.nTris);
+	if (hm.nTris) CU(c, cudaMemcpy(rc.data(), c->dRects.ptr + hm.primBase, (size_t)hm.nTris * 8, cudaMemcpyDeviceToHost));
+	for (uint32_t t = 0; t < hm.nTris; ++t) out[t] = ((rc[t].x & 0xFFFFu) == 0xFFFFu) ? 0 : 1;
+	return B2R_OK;
+}
+
+int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t idsCap, uint64_t* total)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "read_bins: nothing rendered yet");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	const uint64_t pairs = c->hInfo->frameInfo[0];
+	if (total) *total = pairs;
+	const uint32_t n = nBins(c);
+	if (counts) CU(c, cudaMemcpy(counts, c->dTileCount.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	if (offsets) CU(c, cudaMemcpy(offsets, c->dTileOffset.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	if (ids)
+	{
+		if (idsCap < pairs) return fail(c, B2R_E_INVALID, "ids capacity %llu < %llu pairs", (unsigned long long)idsCap, (unsigned long long)pairs);
+		if (pairs) CU(c, cudaMemcpy(ids, c->dBinIds.ptr, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+	}
+	return B2R_OK;
+}
+
+int b2r_get_stats(b2r_context* c, uint32_t* totalTris, uint32_t* visibleTris)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	if (totalTris) *totalTris = (uint32_t)c->nPrims;
+	if (visibleTris) *visibleTris = c->haveFrame ? c->hInfo->counters[0] : 0;
+	return B2R_OK;
+}
+
+int b2r_get_stage_ms(b2r_context* c, float* out, int n)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!out || n < 1) return fail(c, B2R_E_INVALID, "bad output");
+	if (!c->evRecorded) return fail(c, B2R_E_STATE, "stage timers were not enabled for the last frame (B2R_OPT_STAGE_TIMERS)");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	float ms[B2R_NUM_STAGES] = {};
+	for (int i = 0; i < 6; ++i) CU(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+	CU(c, cudaEventElapsedTime(&ms[B2R_STAGE_TOTAL], c->ev[0], c->ev[6]));
+	for (int i = 0; i < n && i < B2R_NUM_STAGES; ++i) out[i] = ms[i];
+	return B2R_OK;
+}
+
+int b2r_get_counters(b2r_context* c, uint64_t* out, int n)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!out || n < 1) return fail(c, B2R_E_INVALID, "bad output");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	const uint32_t tiles = nBins(c);
+	const uint64_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - c->ownerRank + c->ownerCount - 1) / c->ownerCount : 0;
+	const uint64_t v[6] = { c->hInfo->frameInfo[0], c->kernelsLaunched, owned, tiles, c->hInfo->frameInfo[2], c->hInfo->counters[1] };
+	for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+	return B2R_OK;
+}
+
+int b2r_set_stream(b2r_context* c, void* stream)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	c->stream = stream ? (cudaStream_t)stream : c->ownStream;
+	return B2R_OK;
+}
+
+int b2r_device_surfaces(b2r_context* c, void** framebuffer, void** depth)
+{
+	if (!c) return B2R_E_INVALID;
+	if (framebuffer) *framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer;
+	if (depth) *depth = c->dDepth;
+	return B2R_OK;
+}
+
+int b2r_bind_framebuffer(b2r_context* c, void* devicePtr)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	c->boundFramebuffer = (uint32_t*)devicePtr;
+	return B2R_OK;
+}
+
+}

@@ -1,0 +1,378 @@
+// Geometry front end: vertex transform, triangle setup + cull, tile binning
+// (count -> scan -> scatter -> sort).  Replaces VS_Kernel, TA_Kernel, TB_Kernel and
+// CUDAAtomicQueue of the reference (CUDARenderer.cu:673-796, 903-988; CUDAAtomicQueue.cuh).
+#pragma once
+#include "device_types.cuh"
+
+namespace b2r {
+
+// a*b + c*d + e*f the way the reference's device code evaluates it (SASS: FMUL c*d, FFMA a*b, FFMA e*f)
+__device__ __forceinline__ float sum3(float a, float b, float c, float d, float e, float f)
+{
+	return fmaf(e, f, fmaf(a, b, c * d));
+}
+// a*b - c*d  (SASS: FMUL c*d, FFMA a*b - t)
+__device__ __forceinline__ float diff2(float a, float b, float c, float d)
+{
+	return fmaf(a, b, -(c * d));
+}
+// Matrix4 * point (w = 1), row r of a data[col][row] matrix: Matrix4.h:158-166
+__device__ __forceinline__ float mulRow4(const float* m, int r, float x, float y, float z)
+{
+	return sum3(m[0 + r], x, m[4 + r], y, m[8 + r], z) + m[12 + r];
+}
+__device__ __forceinline__ float mulRow3(const float* m, int r, float x, float y, float z)
+{
+	return sum3(m[0 + r], x, m[3 + r], y, m[6 + r], z);
+}
+// Vector.h:42-56 Normalize: v * (1 / sqrt(dot)), zero vector when the length is 0
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z)
+{
+	const float m = __fsqrt_rn(sum3(x, x, y, y, z, z));
+	if (m == 0.f) { x = 0.f; y = 0.f; z = 0.f; return; }
+	const float inv = __frcp_rn(m);
+	x = x * inv; y = y * inv; z = z * inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// vertex transform: one CTA per chunk of 256 vertices of one mesh.
+// Input records (56 B AoS) are staged through shared memory with coalesced 8-byte loads;
+// outputs are a 16 B position stream and a 64 B attribute stream.
+// Follows GetNDCVertex, CUDAROPs.cu:99-118.
+__global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
+	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
+	const float2* __restrict__ ivertex, float4* __restrict__ pos4, float4* __restrict__ attr, FrameParams fp)
+{
+	__shared__ float2 sIn[kChunk * 7];
+	__shared__ float sMat[41];
+	const Chunk ch = chunks[blockIdx.x];
+	const MeshConst& mc = meshes[ch.mesh];
+	const uint32_t n = min((uint32_t)kChunk, mc.nVertices - ch.first);
+	const float2* src = ivertex + (size_t)(mc.vtxInBase + ch.first) * 7;
+	for (uint32_t i = threadIdx.x; i < n * 7; i += kChunk)
+		sIn[i] = __ldg(src + i);
+	if (threadIdx.x < 16) sMat[threadIdx.x] = mc.wvp[threadIdx.x];
+	else if (threadIdx.x < 32) sMat[threadIdx.x] = mc.world[threadIdx.x - 16];
+	else if (threadIdx.x < 41) sMat[threadIdx.x] = mc.rot[threadIdx.x - 32];
+	__syncthreads();
+	if (threadIdx.x >= n) return;
+
+	const float* v = reinterpret_cast<const float*>(sIn) + threadIdx.x * 14;
+	const float px = v[0], py = v[1], pz = v[2];
+	const float* wvp = sMat; const float* world = sMat + 16; const float* rot = sMat + 32;
+
+	const float cx = mulRow4(wvp, 0, px, py, pz);
+	const float cy = mulRow4(wvp, 1, px, py, pz);
+	const float cz = mulRow4(wvp, 2, px, py, pz);
+	const float cw = mulRow4(wvp, 3, px, py, pz);
+	float4 p;
+	p.x = __fdiv_rn(cx, cw); p.y = __fdiv_rn(cy, cw); p.z = __fdiv_rn(cz, cw); p.w = cw;
+
+	const float nx = mulRow3(rot, 0, v[5], v[6], v[7]);
+	const float ny = mulRow3(rot, 1, v[5], v[6], v[7]);
+	const float nz = mulRow3(rot, 2, v[5], v[6], v[7]);
+	const float tx = mulRow3(rot, 0, v[8], v[9], v[10]);
+	const float ty = mulRow3(rot, 1, v[8], v[9], v[10]);
+	const float tz = mulRow3(rot, 2, v[8], v[9], v[10]);
+	float vx = mulRow4(world, 0, px, py, pz) - fp.camPos[0];
+	float vy = mulRow4(world, 1, px, py, pz) - fp.camPos[1];
+	float vz = mulRow4(world, 2, px, py, pz) - fp.camPos[2];
+	normalize3(vx, vy, vz);
+
+	const size_t o = (size_t)mc.vtxOutBase + ch.first + threadIdx.x;
+	pos4[o] = p;
+	float4* a = attr + o * 4;
+	a[0] = make_float4(v[3], v[4], nx, ny);
+	a[1] = make_float4(nz, tx, ty, tz);
+	a[2] = make_float4(vx, vy, vz, v[11]);
+	a[3] = make_float4(v[12], v[13], 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float min3ref(float a, float b, float c) { float m = a; if (b < m) m = b; if (c < m) m = c; return m; }
+__device__ __forceinline__ float max3ref(float a, float b, float c) { float m = a; if (b > m) m = b; if (c > m) m = c; return m; }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { const int c = v < lo ? lo : v; return c > hi ? hi : c; }
+// (short)f -+ 1 then ClampFast to [0, limit] as shorts: CUDAROPs.cu:184-192
+__device__ __forceinline__ int bboxCoord(float f, int delta, int limit)
+{
+	const int t = __float2int_rz(f) + delta;          // cvt.rzi.s32.f32, saturating, NaN -> 0
+	const int s = (int)(short)(t & 0xFFFF);           // wraps exactly like the 16-bit store
+	return clampi(s, 0, (int)(short)limit);
+}
+__device__ __forceinline__ bool tileOwned(const FrameParams& fp, uint32_t tile)
+{
+	return fp.ownerCount <= 1 || (tile % fp.ownerCount) == fp.ownerRank;
+}
+
+// triangle setup: one CTA per chunk of 256 triangles of one mesh.
+// cull (CUDARenderer.cu:760-777), frustum reject (CUDAROPs.cu:147-178), screen mapping (:88-97),
+// inflated bbox (:180-200), bin rectangle (CUDARenderer.cu:935-942), per-tile counts.
+__global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
+	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
+	const uint32_t* __restrict__ indices, const float4* __restrict__ pos4,
+	TriRecord* __restrict__ records, TriAux* __restrict__ aux, uint2* __restrict__ rects,
+	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig*/,
+	FrameParams fp)
+{
+	const Chunk ch = chunks[blockIdx.x];
+	const MeshConst& mc = meshes[ch.mesh];
+	const uint32_t local = ch.first + threadIdx.x;
+	bool visible = false;
+	uint32_t prim = 0;
+	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+	if (local < mc.nTris)
+	{
+		prim = mc.primBase + local;
+		const uint32_t* ip = indices + (size_t)mc.idxBase + (size_t)local * 3;
+		const uint32_t i0 = mc.vtxOutBase + __ldg(ip), i1 = mc.vtxOutBase + __ldg(ip + 1), i2 = mc.vtxOutBase + __ldg(ip + 2);
+		const float4 p0 = __ldg(pos4 + i0), p1 = __ldg(pos4 + i1), p2 = __ldg(pos4 + i2);
+		visible = true;
+		if (fp.cullMode != 2u)
+		{
+			const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+			const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+			float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
+			normalize3(nx, ny, nz);
+			// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
+			const float d = (fp.cullMode == 0u)
+				? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
+				: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
+			if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
+		}
+		if (visible)
+		{
+			const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
+			const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
+			const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
+			visible = !(xOut || yOut || zOut);
+		}
+		if (visible)
+		{
+			const float W = (float)fp.width, H = (float)fp.height;
+			TriRecord r;
+			r.x0 = ((p0.x + 1.f) * 0.5f) * W; r.y0 = ((1.f - p0.y) * 0.5f) * H;
+			r.x1 = ((p1.x + 1.f) * 0.5f) * W; r.y1 = ((1.f - p1.y) * 0.5f) * H;
+			r.x2 = ((p2.x + 1.f) * 0.5f) * W; r.y2 = ((1.f - p2.y) * 0.5f) * H;
+			r.z0 = p0.z; r.z1 = p1.z; r.z2 = p2.z;
+			r.area = fabsf(diff2(r.x0 - r.x1, r.y0 - r.y2, r.y0 - r.y1, r.x0 - r.x2));
+			const int xMin = bboxCoord(min3ref(r.x0, r.x1, r.x2), -1, (int)fp.width);
+			const int yMin = bboxCoord(min3ref(r.y0, r.y1, r.y2), -1, (int)fp.height);
+			const int xMax = bboxCoord(max3ref(r.x0, r.x1, r.x2), +1, (int)fp.width);
+			const int yMax = bboxCoord(max3ref(r.y0, r.y1, r.y2), +1, (int)fp.height);
+			r.bbX = (uint32_t)xMin | ((uint32_t)xMax << 16);
+			r.bbY = (uint32_t)yMin | ((uint32_t)yMax << 16);
+			records[prim] = r;
+			TriAux a; a.v0 = i0; a.v1 = i1; a.v2 = i2; a.mesh = ch.mesh;
+			aux[prim] = a;
+			bx0 = clampi(xMin / (int)fp.binW, 0, (int)fp.binsX);
+			by0 = clampi(yMin / (int)fp.binH, 0, (int)fp.binsY);
+			bx1 = clampi(xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
+			by1 = clampi(yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
+		}
+		// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
+		// from a visible primitive whose rectangle happens to be empty
+		rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16))
+		                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
+	}
+	// statistics: one atomic per CTA
+	const int nVis = __syncthreads_count(visible);
+	if (threadIdx.x == 0 && nVis) atomicAdd(&counters[0], (uint32_t)nVis);
+
+	if (visible && bx0 <= bx1 && by0 <= by1)
+	{
+		const uint32_t nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
+		if (nTiles > fp.bigRectTiles)
+		{
+			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively by bin_big_kernel
+		}
+		else
+		{
+			for (int ty = by0; ty <= by1; ++ty)
+				for (int tx = bx0; tx <= bx1; ++tx)
+				{
+					const uint32_t tile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
+					if (tileOwned(fp, tile)) atomicAdd(&tileCount[tile], 1u);
+				}
+		}
+	}
+}
+
+// cooperative binning of triangles with large rectangles (full-screen quads ...): one CTA per
+// big triangle, threads stride over its tiles.  SCATTER=false counts, true writes the ids.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) bin_big_kernel(
+	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, const uint2* __restrict__ rects,
+	uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
+	uint32_t* __restrict__ binIds, FrameParams fp)
+{
+	const uint32_t nBig = counters[1];
+	for (uint32_t b = blockIdx.x; b < nBig; b += gridDim.x)
+	{
+		const uint32_t prim = bigList[b];
+		const uint2 rc = rects[prim];
+		const int bx0 = rc.x & 0xFFFF, bx1 = rc.x >> 16, by0 = rc.y & 0xFFFF, by1 = rc.y >> 16;
+		const int w = bx1 - bx0 + 1, n = w * (by1 - by0 + 1);
+		for (int i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			const uint32_t tile = (uint32_t)(bx0 + i % w) + (uint32_t)(by0 + i / w) * fp.binsX;
+			if (!tileOwned(fp, tile)) continue;
+			if (SCATTER)
+				binIds[tileOffset[tile] + atomicAdd(&tileCursor[tile], 1u)] = prim;
+			else
+				atomicAdd(&tileCount[tile], 1u);
+		}
+	}
+}
+
+// exclusive scan of the per-tile counts (single CTA; the tile grid is at most a few 100k entries).
+// Also clears the cursors and publishes the pair total / overflow flag.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(
+	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
+	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold, uint32_t* __restrict__ longTiles,
+	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles*/)
+{
+	__shared__ unsigned long long sWarp[32];
+	__shared__ unsigned long long sCarry;
+	__shared__ uint32_t sLong;
+	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; }
+	__syncthreads();
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (uint32_t base = 0; base < nTiles; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const unsigned long long v = (i < nTiles) ? tileCount[i] : 0ull;
+		unsigned long long incl = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+			if (lane >= (uint32_t)d) incl += t;
+		}
+		if (lane == 31) sWarp[warp] = incl;
+		__syncthreads();
+		if (warp == 0)
+		{
+			unsigned long long w = sWarp[lane];
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, w, d);
+				if (lane >= (uint32_t)d) w += t;
+			}
+			sWarp[lane] = w;
+		}
+		__syncthreads();
+		const unsigned long long carry = sCarry;
+		const unsigned long long excl = carry + (warp ? sWarp[warp - 1] : 0ull) + incl - v;
+		if (i < nTiles)
+		{
+			tileOffset[i] = (uint32_t)excl;
+			tileCursor[i] = 0u;
+			if (v > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i;
+		}
+		__syncthreads();
+		if (threadIdx.x == 1023) sCarry = carry + sWarp[31];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		frameInfo[0] = sCarry;
+		frameInfo[1] = (sCarry > capacity) ? 1ull : 0ull;
+		frameInfo[2] = 0ull;
+		frameInfo[3] = sLong;
+	}
+}
+
+// scatter of the small rectangles: one thread per primitive, re-reading the 8 B rectangle.
+__global__ void __launch_bounds__(256) bin_scatter_kernel(
+	const uint2* __restrict__ rects, uint32_t nPrims, const uint32_t* __restrict__ tileOffset,
+	uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ binIds,
+	const unsigned long long* __restrict__ frameInfo, FrameParams fp)
+{
+	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
+	const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+	if (prim >= nPrims) return;
+	const uint2 rc = rects[prim];
+	const int bx0 = rc.x & 0xFFFF, bx1 = rc.x >> 16, by0 = rc.y & 0xFFFF, by1 = rc.y >> 16;
+	if (bx0 > bx1 || by0 > by1) return;
+	if ((uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1) > fp.bigRectTiles) return;
+	for (int ty = by0; ty <= by1; ++ty)
+		for (int tx = bx0; tx <= bx1; ++tx)
+		{
+			const uint32_t tile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
+			if (tileOwned(fp, tile))
+				binIds[tileOffset[tile] + atomicAdd(&tileCursor[tile], 1u)] = prim;
+		}
+}
+
+// per-tile sort of the id lists (ascending primitive id = submission order): makes the lists
+// bit-reproducible regardless of the order the scatter atomics were served.
+//  tier 1: every tile, lists up to kSortSmall entries, static shared memory
+//  tier 2: the tiles tile_scan_kernel put on the long-list worklist, up to kSortLarge entries
+//          in dynamic shared memory (one CTA per SM)
+//  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
+//  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
+constexpr int kSortSmall = 4096;
+constexpr int kSortLarge = 49152;
+
+__device__ __forceinline__ void sortTileList(uint32_t* __restrict__ list, uint32_t n, uint32_t* sKeys)
+{
+	// already sorted? (common: consecutive primitives of one CTA land in order)
+	int unsorted = 0;
+	for (uint32_t i = threadIdx.x; i + 1 < n; i += blockDim.x)
+		unsorted |= (list[i] > list[i + 1]);
+	if (!__syncthreads_or(unsorted)) return;
+	uint32_t m = 1; while (m < n) m <<= 1;
+	for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sKeys[i] = (i < n) ? list[i] : 0xFFFFFFFFu;
+	__syncthreads();
+	for (uint32_t k = 2; k <= m; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+			{
+				const uint32_t p = i ^ j;
+				if (p > i)
+				{
+					const uint32_t a = sKeys[i], b = sKeys[p];
+					const bool up = ((i & k) == 0);
+					if ((a > b) == up) { sKeys[i] = b; sKeys[p] = a; }
+				}
+			}
+			__syncthreads();
+		}
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) list[i] = sKeys[i];
+}
+
+__global__ void __launch_bounds__(256) bin_sort_kernel(
+	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
+	const unsigned long long* __restrict__ frameInfo)
+{
+	__shared__ uint32_t sKeys[kSortSmall];
+	if (frameInfo[1]) return;
+	const uint32_t n = tileCount[blockIdx.x];
+	if (n < 2 || n > (uint32_t)kSortSmall) return;
+	sortTileList(binIds + tileOffset[blockIdx.x], n, sKeys);
+}
+
+__global__ void __launch_bounds__(1024) bin_sort_long_kernel(
+	const uint32_t* __restrict__ longTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
+	uint32_t* __restrict__ binIds, unsigned long long* __restrict__ frameInfo)
+{
+	extern __shared__ uint32_t sKeysDyn[];
+	if (frameInfo[1]) return;
+	const uint32_t nLong = (uint32_t)frameInfo[3];
+	for (uint32_t w = blockIdx.x; w < nLong; w += gridDim.x)
+	{
+		const uint32_t tile = longTiles[w];
+		const uint32_t n = tileCount[tile];
+		if (n > (uint32_t)kSortLarge)
+		{
+			if (threadIdx.x == 0) atomicAdd(&frameInfo[2], 1ull);
+			continue;
+		}
+		sortTileList(binIds + tileOffset[tile], n, sKeysDyn);
+		__syncthreads();
+	}
+}
+
+}

@@ -1,0 +1,338 @@
+// Per-tile raster + deferred shade + ROP write-back in ONE kernel.
+// Replaces RA_PerTileKernel, RasterizePixelAtomic, PerformDepthTestAtomic, the 152 B/pixel
+// fragment buffer, the three CLEAR_* kernels and PS_Kernel of the reference
+// (CUDARenderer.cu:598-643, 833-897, 1039-1129; CUDAROPs.cu:231-251, 329-470).
+//
+// One CTA = one 16x16 pixel tile, one thread = one pixel.  The tile's depth/winner state
+// never leaves the SM: a 64-bit key (z_int << 32 | primitive id) per pixel lives in a
+// register for triangles that are rasterised pixel-parallel and in shared memory for small
+// triangles that are rasterised triangle-parallel (atomicMin).  Because the resolve is a
+// min over (depth, primitive id) it is independent of the order in which triangles are
+// visited: equal depths go to the lower primitive id, i.e. to the first-submitted triangle
+// (the sequential meaning of the reference's "first to take the lock wins").
+// After the last triangle each pixel is shaded once (like the reference's deferred
+// PS_Kernel) and colour + depth are written with one coalesced store per row segment.
+#pragma once
+#include "device_types.cuh"
+#include "geometry_kernels.cuh"
+
+namespace b2r {
+
+struct RasterArgs
+{
+	const uint32_t* tileCount;
+	const uint32_t* tileOffset;
+	const uint32_t* binIds;
+	const TriRecord* records;
+	const TriAux* aux;
+	const float4* pos4;
+	const float4* attr;
+	const MeshConst* meshes;
+	const TexDesc* textures;
+	const unsigned long long* frameInfo;
+	uint32_t* framebuffer;
+	int32_t* depth;
+	float* zSurface;        // debug surfaces (may be null)
+	uint32_t* winnerSurface;
+};
+
+// expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
+struct __align__(16) TriShared
+{
+	float x0, y0, x1, y1;
+	float x2, y2, z0, z1;
+	float z2, area, eAx, eAy;     // eA = v1 - v0
+	float eBx, eBy, eCx, eCy;     // eB = v2 - v1, eC = v0 - v2
+};
+
+struct Bary { float b0, b1, b2, z; };
+
+__device__ __forceinline__ bool topLeftEdge(float ex, float ey) { return ey > 0.f || (ey == 0.f && ex < 0.f); }
+
+// IsPixelInTriangle + weights + depth of RasterizePixelAtomic (CUDAROPs.cu:128-145, 333-345, 386).
+// Returns false if the fragment is not produced.  zi = cvt.rzi.s32.f32(z * 2^31).
+template <bool TOPLEFT>
+__device__ __forceinline__ bool fragmentTest(const TriShared& t, float fx, float fy, Bary& out, int& zi)
+{
+	const float w2 = diff2(fx - t.x0, t.eAy, fy - t.y0, t.eAx);
+	const float w0 = diff2(fx - t.x1, t.eBy, fy - t.y1, t.eBx);
+	const float w1 = diff2(fx - t.x2, t.eCy, fy - t.y2, t.eCx);
+	if (!(w0 >= 0.f && w1 >= 0.f && w2 >= 0.f)) return false;
+	if (TOPLEFT)
+	{
+		if ((w2 == 0.f && !topLeftEdge(t.eAx, t.eAy)) || (w0 == 0.f && !topLeftEdge(t.eBx, t.eBy)) ||
+			(w1 == 0.f && !topLeftEdge(t.eCx, t.eCy)))
+			return false;
+	}
+	out.b0 = __fdiv_rn(w0, t.area); out.b1 = __fdiv_rn(w1, t.area); out.b2 = __fdiv_rn(w2, t.area);
+	out.z = sum3(out.b0, t.z0, out.b1, t.z1, out.b2, t.z2);
+	if (out.z < 0.f || out.z > 1.f) return false;
+	zi = __float2int_rz(out.z * 2147483648.f);
+	// a saturated INT_MAX never passes `zf < (float)INT_MAX` against the cleared buffer (CUDAROPs.cu:242)
+	return zi != 0x7FFFFFFF;
+}
+
+__device__ __forceinline__ void expandRecord(const TriRecord& r, TriShared& t)
+{
+	t.x0 = r.x0; t.y0 = r.y0; t.x1 = r.x1; t.y1 = r.y1; t.x2 = r.x2; t.y2 = r.y2;
+	t.z0 = r.z0; t.z1 = r.z1; t.z2 = r.z2; t.area = r.area;
+	t.eAx = r.x1 - r.x0; t.eAy = r.y1 - r.y0;
+	t.eBx = r.x2 - r.x1; t.eBy = r.y2 - r.y1;
+	t.eCx = r.x0 - r.x2; t.eCy = r.y0 - r.y2;
+}
+
+// ---- texture sampling (CUDATextureSampler.cuh:80-191) -------------------------------------
+struct RGB { float r, g, b; };
+
+__device__ __forceinline__ bool texelCoords(const TexDesc& t, float u, float v, int& x, int& y)
+{
+	x = __float2int_rz(fmaf(u, (float)t.w, 0.5f));
+	y = __float2int_rz(fmaf(v, (float)t.h, 0.5f));
+	return !(x < 0 || y < 0 || (uint32_t)x >= t.w || (uint32_t)y >= t.h);
+}
+__device__ __forceinline__ RGB samplePoint(const TexDesc& t, float u, float v)
+{
+	int x, y;
+	if (!texelCoords(t, u, v, x, y)) return RGB{ 1.f, 0.f, 1.f };
+	const uint32_t s = __ldg(t.px + (size_t)x + (size_t)y * t.w);
+	return RGB{ __fdiv_rn((float)(s & 0xFFu), 255.f), __fdiv_rn((float)((s >> 8) & 0xFFu), 255.f), __fdiv_rn((float)((s >> 16) & 0xFFu), 255.f) };
+}
+__device__ __forceinline__ RGB sampleLinear(const TexDesc& t, float u, float v)
+{
+	int x, y;
+	if (!texelCoords(t, u, v, x, y)) return RGB{ 1.f, 0.f, 1.f };
+	const int texSize = (int)(t.w * t.h);
+	const int o = x + y * (int)t.w;
+	int n0 = o - 1;          if (n0 < 0) n0 = o;
+	int n1 = o + 1;          if (n1 >= texSize) n1 = o;
+	int n2 = o + (int)t.w;   if (n2 >= texSize) n2 = o;
+	int n3 = o - (int)t.w;   if (n3 < 0) n3 = o;
+	const uint32_t s0 = __ldg(t.px + n0), s1 = __ldg(t.px + n1), s2 = __ldg(t.px + n2), s3 = __ldg(t.px + n3), sc = __ldg(t.px + o);
+	// all partial sums are exact in fp32 (multiples of 1/8 below 2^11), so the order is free
+	const float r = (float)((s0 & 0xFFu) + (s1 & 0xFFu) + (s2 & 0xFFu) + (s3 & 0xFFu)) * 0.125f + (float)(sc & 0xFFu) * 0.5f;
+	const float g = (float)(((s0 >> 8) & 0xFFu) + ((s1 >> 8) & 0xFFu) + ((s2 >> 8) & 0xFFu) + ((s3 >> 8) & 0xFFu)) * 0.125f + (float)((sc >> 8) & 0xFFu) * 0.5f;
+	const float b = (float)(((s0 >> 16) & 0xFFu) + ((s1 >> 16) & 0xFFu) + ((s2 >> 16) & 0xFFu) + ((s3 >> 16) & 0xFFu)) * 0.125f + (float)((sc >> 16) & 0xFFu) * 0.5f;
+	const float rev = __frcp_rn(255.f);
+	return RGB{ r * rev, g * rev, b * rev };
+}
+__device__ __forceinline__ RGB sampleTex(const TexDesc& t, float u, float v, uint32_t sampleState)
+{
+	return sampleState == 1u ? sampleLinear(t, u, v) : samplePoint(t, u, v);
+}
+
+// RGBRaw.h:23-32: truncating pack to 0x00RRGGBB
+__device__ __forceinline__ uint32_t packColour(float r, float g, float b)
+{
+	const uint32_t b0 = __float2uint_rz(b * 255.f) & 0xFFu;
+	const uint32_t b1 = __float2uint_rz(g * 255.f) & 0xFFu;
+	const uint32_t b2 = __float2uint_rz(r * 255.f) & 0xFFu;
+	return b0 | (b1 << 8) | (b2 << 16);
+}
+
+// attribute interpolation S(a) = w0*(a0*iw0) + w1*(a1*iw1) + w2*(a2*iw2), CUDAROPs.cu:50-84
+struct Interp
+{
+	float b0, b1, b2, iw0, iw1, iw2;
+	__device__ __forceinline__ float operator()(float a0, float a1, float a2) const
+	{
+		return sum3(b0, a0 * iw0, b1, a1 * iw1, b2, a2 * iw2);
+	}
+};
+
+// ShadePixelSafe, CUDAROPs.cu:411-470, with the contraction pattern of the reference build
+__device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& mc, uint32_t sampleState,
+	float u, float v, float nx, float ny, float nz, float tx, float ty, float tz, float vx, float vy, float vz)
+{
+	const RGB D = sampleTex(A.textures[mc.tex[0]], u, v, sampleState);
+	if (mc.tex[1] < 0) return D;
+	const RGB Ns = sampleTex(A.textures[mc.tex[1]], u, v, sampleState);
+	const float cx = diff2(ty, nz, tz, ny), cy = diff2(tz, nx, tx, nz), cz = diff2(tx, ny, ty, nx);   // Cross(tan, n); binormal = -C
+	const float fx = fmaf(Ns.r, 2.f, -1.f), fy = fmaf(Ns.g, 2.f, -1.f), fz = fmaf(Ns.b, 2.f, -1.f);
+	const float Nx = fmaf(fz, nx, fmaf(tx, fx, -(cx * fy)));
+	const float Ny = fmaf(fz, ny, fmaf(ty, fx, -(cy * fy)));
+	const float Nz = fmaf(fz, nz, fmaf(tz, fx, -(cz * fy)));
+	const float L = 0.577f;
+	const float nxL = Nx * L;
+	float oa = fmaf(Nz, L, fmaf(Ny, L, -nxL));       // Dot(-N, lightDirection); ClampFast(oa,0,oa) is the identity
+	oa = __fdiv_rn(oa, 3.14159274101257324f);
+	oa = oa * 7.0f;
+	RGB c{ D.r * oa, D.g * oa, D.b * oa };
+	if (mc.tex[2] < 0 || mc.tex[3] < 0) return c;
+	const RGB S = sampleTex(A.textures[mc.tex[2]], u, v, sampleState);
+	const RGB G = sampleTex(A.textures[mc.tex[3]], u, v, sampleState);
+	float dotLN = fmaf(Nz, -L, fmaf(Ny, -L, nxL));
+	dotLN = dotLN + dotLN;
+	const float Rx = fmaf(Nx, dotLN, -L), Ry = fmaf(Ny, dotLN, L), Rz = fmaf(Nz, dotLN, L);
+	float angle = fmaf(Rz, vz, fmaf(Rx, vx, vy * Ry));
+	angle = (angle < 0.f) ? 0.f : angle;
+	angle = (angle > 1.f) ? 1.f : angle;
+	angle = powf(angle, G.r * 25.f);
+	c.r = fmaf(angle, S.r, c.r + 0.05f);
+	c.g = fmaf(angle, S.g, c.g + 0.05f);
+	c.b = fmaf(angle, S.b, c.b + 0.05f);
+	const float gb = (c.g < c.b) ? c.b : c.g;
+	const float mx = (c.r < gb) ? gb : c.r;
+	if (mx > 1.f)
+	{
+		const float rev = __frcp_rn(mx);
+		c.r *= rev; c.g *= rev; c.b *= rev;
+	}
+	return c;
+}
+
+constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
+constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are rasterised by one thread
+
+template <bool TOPLEFT>
+__global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs A, FrameParams fp)
+{
+	__shared__ TriShared sTri[kListChunk];
+	__shared__ uint32_t sPrim[kListChunk];
+	__shared__ uint32_t sBig[kListChunk];
+	__shared__ unsigned long long sKey[kTile * kTile];
+	__shared__ uint32_t sNumBig;
+
+	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
+	const uint32_t bin = fp.ownerRank + blockIdx.x * fp.ownerCount;
+	const uint32_t binX = bin % fp.binsX, binY = bin / fp.binsX;
+	const uint32_t subX = blockIdx.y % fp.subX, subY = blockIdx.y / fp.subX;
+	const int tid = threadIdx.x;
+	const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
+	// extent of this CTA's pixel block inside the bin and the screen
+	const int ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
+	const int ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
+	const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
+	const bool live = px < ex && py < ey;
+	const float fx = (float)px, fy = (float)py;
+
+	unsigned long long best = kEmptyKey;
+	sKey[tid] = kEmptyKey;
+	const uint32_t n = A.tileCount[bin];
+	const uint32_t* list = A.binIds + A.tileOffset[bin];
+
+	for (uint32_t base = 0; base < n; base += kListChunk)
+	{
+		if (tid == 0) sNumBig = 0;
+		__syncthreads();
+		const uint32_t m = min((uint32_t)kListChunk, n - base);
+		if ((uint32_t)tid < m)
+		{
+			const uint32_t prim = __ldg(list + base + tid);
+			const TriRecord r = A.records[prim];
+			TriShared t;
+			expandRecord(r, t);
+			sTri[tid] = t;
+			sPrim[tid] = prim;
+			// candidate pixels = inflated bbox (CUDAROPs.cu:180-200) clipped to this CTA's block;
+			// the bbox is conservative for the edge test, so this equals testing the whole bin
+			const int x0 = max((int)(r.bbX & 0xFFFFu), ox), x1 = min((int)(r.bbX >> 16), ex);
+			const int y0 = max((int)(r.bbY & 0xFFFFu), oy), y1 = min((int)(r.bbY >> 16), ey);
+			const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
+			if (area > kSmallArea)
+				sBig[atomicAdd(&sNumBig, 1u)] = (uint32_t)tid;
+			else if (area > 0)
+			{
+				// triangle-parallel path: this thread walks the few candidate pixels
+				for (int y = y0; y < y1; ++y)
+					for (int x = x0; x < x1; ++x)
+					{
+						Bary bc; int zi;
+						if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+						{
+							const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
+							atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
+						}
+					}
+			}
+		}
+		__syncthreads();
+		// pixel-parallel path: every thread tests its own pixel against each large triangle
+		const uint32_t nBig = sNumBig;
+		for (uint32_t j = 0; j < nBig; ++j)
+		{
+			const uint32_t slot = sBig[j];
+			const TriShared& t = sTri[slot];
+			Bary bc; int zi;
+			if (live && fragmentTest<TOPLEFT>(t, fx, fy, bc, zi))
+			{
+				const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | sPrim[slot];
+				best = min(best, key);
+			}
+		}
+		__syncthreads();
+	}
+	best = min(best, sKey[tid]);
+	if (!live) return;
+
+	// ---- deferred shade of the winner (PS_Kernel, CUDARenderer.cu:833-897) + ROP write-back
+	const size_t pix = (size_t)px + (size_t)py * fp.width;
+	uint32_t colour;
+	int depthOut = 0x7FFFFFFF;
+	float zOut = 0.f;
+	uint32_t prim = kNoPrim;
+	if (best == kEmptyKey)
+	{
+		// untouched fragment: zero-cleared PixelShade whose colour32 is the clear colour
+		if (fp.visState == 0u) colour = packColour(fp.clearRGB[0], fp.clearRGB[1], fp.clearRGB[2]);
+		else colour = 0u;   // Depth: (0-.985)/.015*255 < 0 -> 0 ; Normal: n = 0
+	}
+	else
+	{
+		prim = (uint32_t)best;
+		depthOut = (int)(uint32_t)(best >> 32);
+		TriShared t;
+		expandRecord(A.records[prim], t);
+		Bary bc; int zi;
+		fragmentTest<false>(t, fx, fy, bc, zi);      // same arithmetic as the coverage pass
+		zOut = bc.z;
+		const TriAux ax = A.aux[prim];
+		const MeshConst& mc = A.meshes[ax.mesh];
+		if (fp.visState == 1u)
+		{
+			const float r = __fdiv_rn(bc.z - 0.985f, 1.f - 0.985f);   // Remap, MathUtilities.h:175-178
+			colour = (__float2uint_rz(r * 255.f) & 0xFFu) << 16;
+		}
+		else
+		{
+			Interp S;
+			S.b0 = bc.b0; S.b1 = bc.b1; S.b2 = bc.b2;
+			S.iw0 = __frcp_rn(__ldg(&A.pos4[ax.v0].w)); S.iw1 = __frcp_rn(__ldg(&A.pos4[ax.v1].w)); S.iw2 = __frcp_rn(__ldg(&A.pos4[ax.v2].w));
+			const float4* a0 = A.attr + (size_t)ax.v0 * 4; const float4* a1 = A.attr + (size_t)ax.v1 * 4; const float4* a2 = A.attr + (size_t)ax.v2 * 4;
+			const bool textured = (fp.visState == 0u) && mc.tex[0] >= 0;
+			if (fp.visState == 0u && !textured)
+			{
+				// vertex colour, NOT multiplied by wInterpolated (CUDAROPs.cu:379)
+				const float4 c0a = __ldg(a0 + 2), c0b = __ldg(a0 + 3), c1a = __ldg(a1 + 2), c1b = __ldg(a1 + 3), c2a = __ldg(a2 + 2), c2b = __ldg(a2 + 3);
+				colour = packColour(S(c0a.w, c1a.w, c2a.w), S(c0b.x, c1b.x, c2b.x), S(c0b.y, c1b.y, c2b.y));
+			}
+			else
+			{
+				const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
+				const float4 p0 = __ldg(a0), p1 = __ldg(a1), p2 = __ldg(a2);               // uv, n.x, n.y
+				const float4 q0 = __ldg(a0 + 1), q1 = __ldg(a1 + 1), q2 = __ldg(a2 + 1);   // n.z, tan
+				const float nx = S(p0.z, p1.z, p2.z) * wInterp, ny = S(p0.w, p1.w, p2.w) * wInterp, nz = S(q0.x, q1.x, q2.x) * wInterp;
+				if (fp.visState == 2u)
+					colour = packColour(nx, ny, nz);
+				else
+				{
+					const float u = S(p0.x, p1.x, p2.x) * wInterp, v = S(p0.y, p1.y, p2.y) * wInterp;
+					const float tx = S(q0.y, q1.y, q2.y), ty = S(q0.z, q1.z, q2.z), tz = S(q0.w, q1.w, q2.w);   // no wInterp (CUDAROPs.cu:372)
+					const float4 r0 = __ldg(a0 + 2), r1 = __ldg(a1 + 2), r2 = __ldg(a2 + 2);
+					float vx = S(r0.x, r1.x, r2.x), vy = S(r0.y, r1.y, r2.y), vz = S(r0.z, r1.z, r2.z);
+					normalize3(vx, vy, vz);
+					const RGB c = shadePixel(A, mc, fp.sampleState, u, v, nx, ny, nz, tx, ty, tz, vx, vy, vz);
+					colour = packColour(c.r, c.g, c.b);
+				}
+			}
+		}
+	}
+	A.framebuffer[pix] = colour;
+	A.depth[pix] = depthOut;
+	if (fp.debugSurfaces)
+	{
+		A.zSurface[pix] = zOut;
+		A.winnerSurface[pix] = prim;
+	}
+}
+
+}

@@ -1,0 +1,162 @@
+/*
+ * b2r.h - C ABI of the B200-native per-frame rendering path (libb2r.so).
+ *
+ * The reference (kdedeurw/Custom-GPGPU-Rasterizer) has no plugin / FFI interface: its
+ * renderer is a C++ class inside one executable.  This header is the boundary a
+ * maintainer of the reference binds instead of its CUDA translation units: each entry
+ * point names the reference interface it replaces (paths relative to
+ * CustomCUDARasterizer/).  The C++ veneer in custom_gpgpu_rasterizer_b200/csrc/host/ keeps the
+ * reference's own class surface (CUDARenderer, SceneManager, SceneGraph, Mesh, ObjParser,
+ * Camera, CUDATextureManager ...) and is implemented on top of these calls only.
+ *
+ * Conventions
+ *   - every call returns B2R_OK (0) or a negative B2R_E_* code; b2r_last_error() gives text.
+ *   - one context = one CUDA device + one stream.  A context is thread-compatible
+ *     (no internal locking; do not call into one context from two threads at once).
+ *   - matrices are 16 floats in the reference's FMatrix4 memory layout, data[col][row]
+ *     (Matrix4.h:17): element (row r, col c) is m[c*4 + r].
+ *   - host arrays passed in stay owned by the caller; device copies are owned by the context.
+ *   - there is no CPU fallback: without a CUDA device b2r_create fails.
+ */
+#ifndef B2R_H
+#define B2R_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2r_context b2r_context;
+
+enum
+{
+	B2R_OK = 0,
+	B2R_E_INVALID = -1,     /* bad argument */
+	B2R_E_CUDA = -2,        /* CUDA runtime error (text in b2r_last_error) */
+	B2R_E_NO_DEVICE = -3,   /* no usable CUDA device */
+	B2R_E_UNSUPPORTED = -4, /* e.g. TriangleStrip (broken on the reference GPU path, CUDARenderer.cu:733-753) */
+	B2R_E_STATE = -5        /* call order violated (e.g. read before any render) */
+};
+
+/* CullingMode.h, SampleState.h, VisualisationState.h, PrimitiveTopology.h - same numeric values */
+enum { B2R_CULL_BACKFACE = 0, B2R_CULL_FRONTFACE = 1, B2R_CULL_NONE = 2 };
+enum { B2R_SAMPLE_POINT = 0, B2R_SAMPLE_LINEAR = 1 };
+enum { B2R_VIS_PBR = 0, B2R_VIS_DEPTH = 1, B2R_VIS_NORMAL = 2 };
+enum { B2R_TOPOLOGY_TRIANGLE_LIST = 0, B2R_TOPOLOGY_TRIANGLE_STRIP = 1 };
+
+/* options for b2r_set_option */
+enum
+{
+	/* coverage rule for fragments lying EXACTLY on an edge (edge function == 0):
+	 * 1 (default) = top-left rule, 0 = the reference's rule "all three >= 0" (CUDAROPs.cu:144). */
+	B2R_OPT_FILL_RULE_TOP_LEFT = 1,
+	/* sort-first sharding: this context rasterises only tiles t with t % B2R_OPT_TILE_OWNER_COUNT
+	 * == B2R_OPT_TILE_OWNER_RANK (t = tx + ty*tiles_x).  Defaults 0 / 1 (owns every tile). */
+	B2R_OPT_TILE_OWNER_RANK = 2,
+	B2R_OPT_TILE_OWNER_COUNT = 3,
+	/* also write the parity surfaces float z / winning primitive id per pixel (costs 8 B/px). Default 0. */
+	B2R_OPT_DEBUG_SURFACES = 4,
+	/* record cudaEvents between stages so b2r_get_stage_ms works. Default 0. */
+	B2R_OPT_STAGE_TIMERS = 5,
+	/* sort every tile list by primitive id after the scatter (deterministic lists). Default 1. */
+	B2R_OPT_SORT_BINS = 6
+};
+
+/* stage indices for b2r_get_stage_ms */
+enum
+{
+	B2R_STAGE_VERTEX = 0, B2R_STAGE_SETUP = 1, B2R_STAGE_BIN_SCAN = 2, B2R_STAGE_BIN_SCATTER = 3,
+	B2R_STAGE_BIN_SORT = 4, B2R_STAGE_RASTER_SHADE = 5, B2R_STAGE_TOTAL = 6, B2R_NUM_STAGES = 7
+};
+
+/* error text of the last failing call on this context (NULL context: last b2r_create failure) */
+const char* b2r_last_error(const b2r_context* ctx);
+
+/* CUDARenderer::CUDARenderer(const WindowHelper&) + AllocateCUDADeviceBuffers
+ * (CUDARenderer.cu:34-46, 414-475; CUDAWindowHelper.h:9-31).  Bins default to 16x16 tiles. */
+int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out);
+/* CUDARenderer::~CUDARenderer / FreeCUDADeviceBuffers (CUDARenderer.cu:49-53, 515-525) */
+void b2r_destroy(b2r_context* ctx);
+
+/* CUDARenderer::SetupBins(numBins, binDim, binQueueMaxSize) (CUDARenderer.cu:200-204).
+ * queue_max_size is accepted for source compatibility and ignored: bin lists are exact-sized
+ * (count -> scan -> scatter), so the reference's 256-triangle batching disappears. */
+int b2r_setup_bins(b2r_context* ctx, uint32_t num_bins_x, uint32_t num_bins_y,
+                   uint32_t bin_w, uint32_t bin_h, uint32_t queue_max_size);
+
+/* CUDATexture::Create (CUDATexture.cpp:24-72) minus the PNG decode: pixels are RGBA8,
+ * byte 0 = R (SDL_image order; RGBRaw.h:34-38), tightly packed w*h words.
+ * Ids are dense insertion indices like CUDATextureManager::AddCUDATexture (CUDATextureManager.cpp:29-37). */
+int b2r_texture_create_rgba8(b2r_context* ctx, const uint32_t* pixels, uint32_t w, uint32_t h, int* out_tex_id);
+/* CUDATexture::Destroy (CUDATexture.cpp:74-82); the id is not reused */
+int b2r_texture_destroy(b2r_context* ctx, int tex_id);
+
+/* CUDAMesh::CUDAMesh + Allocate (CUDAMesh.cpp:4-20, 42-59) and CUDARenderer::UpdateCUDAMeshTextures
+ * (CUDARenderer.cu:543-573).  ivertex56 = n_vertices records of {p3, uv2, n3, tan3, c3} floats
+ * (Vertex.h:113-145).  world = the matrix the reference's CUDAMesh would hold (the veneer applies
+ * the double translation of CUDAMesh.cpp:16-18).  tex_ids = {diffuse, normal, specular, gloss}, -1 = none.
+ * Meshes are drawn in upload order (CUDARenderer.cu:237). */
+int b2r_mesh_upload(b2r_context* ctx, const void* ivertex56, uint32_t n_vertices,
+                    const uint32_t* indices, uint32_t n_indices, int topology,
+                    const float world[16], const int tex_ids[4], int* out_mesh_id);
+/* same vertex/index buffers as src_mesh_id under another world matrix / texture set
+ * (instancing instead of N copies) */
+int b2r_mesh_instance(b2r_context* ctx, int src_mesh_id, const float world[16], const int tex_ids[4], int* out_mesh_id);
+/* per-frame world refresh (the reference snapshots it at LoadScene, CUDAMesh.cpp:16) */
+int b2r_mesh_set_world(b2r_context* ctx, int mesh_id, const float world[16]);
+/* CUDARenderer::FreeAllCUDAMeshBuffers (CUDARenderer.cu:489-496) */
+int b2r_mesh_clear_all(b2r_context* ctx);
+
+int b2r_set_option(b2r_context* ctx, int option, int value);
+
+/* CUDARenderer::EnterValidRenderingState/Clear + Render (CUDARenderer.cu:374-381, 1626-1659, 207-354).
+ * cam_pos / cam_fwd = Camera::GetPosition/GetForward, view_proj = projection * Inverse(lookAt)
+ * (CUDARenderer.cu:215-219).  clear_rgb as CUDARenderer::Clear's colour (default .25,.25,.25,
+ * CUDARenderer.h:135).  Asynchronous: work is enqueued on the context's stream. */
+int b2r_render(b2r_context* ctx, const float cam_pos[3], const float cam_fwd[3], const float view_proj[16],
+               int cull_mode, int sample_state, int vis_state, const float clear_rgb[3]);
+/* the cudaDeviceSynchronize that ends CUDARenderer::Render (CUDARenderer.cu:339) */
+int b2r_sync(b2r_context* ctx);
+
+/* CUDARenderer::Present's device->host copy (CUDARenderer.cu:386-388): width*height words 0x00RRGGBB.
+ * Synchronous.  Full-speed if `out` is pinned memory. */
+int b2r_read_framebuffer(b2r_context* ctx, uint32_t* out);
+/* depth buffer as the reference keeps it (int z*2^31, INT_MAX = empty; CUDAROPs.cu:386, CUDARenderer.cu:1640) */
+int b2r_read_depth(b2r_context* ctx, int32_t* out);
+/* parity surfaces (need B2R_OPT_DEBUG_SURFACES=1 before the render): PixelShade.zInterpolated
+ * (0 where empty, like the zero-cleared fragment buffer) and the winning global primitive id
+ * (0xFFFFFFFF where empty) */
+int b2r_read_z(b2r_context* ctx, float* out);
+int b2r_read_winner(b2r_context* ctx, uint32_t* out);
+/* OVertex buffer of one mesh, 18 floats per vertex {p4, uv2, n3, tan3, vd3, c3} (Vertex.h:280-327) */
+int b2r_read_overtex(b2r_context* ctx, int mesh_id, float* out18);
+/* per-primitive visibility of one mesh after cull + frustum reject (the set TA_Kernel appends,
+ * CUDARenderer.cu:702-796), one byte per triangle */
+int b2r_read_visible(b2r_context* ctx, int mesh_id, uint8_t* out);
+/* bin lists of the last frame: counts[num_bins], exclusive offsets[num_bins], and the
+ * concatenated global primitive ids (mesh order, then triangle index).  Pass ids = NULL to query
+ * sizes; *total receives the number of (triangle, bin) pairs. */
+int b2r_read_bins(b2r_context* ctx, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t ids_capacity, uint64_t* total);
+
+/* CUDARenderer::GetTotalNumTriangles / GetTotalNumVisibleTriangles (CUDARenderer.h:63-64) */
+int b2r_get_stats(b2r_context* ctx, uint32_t* total_tris, uint32_t* visible_tris);
+/* device time of each stage of the last frame (replaces the BENCHMARK macro, CUDARenderer.cu:223-353) */
+int b2r_get_stage_ms(b2r_context* ctx, float* out_ms, int n);
+/* counters of the last frame: [0] (triangle,bin) pairs, [1] kernels launched by b2r_render,
+ * [2] tiles rasterised by this context, [3] number of bins */
+int b2r_get_counters(b2r_context* ctx, uint64_t* out, int n);
+
+/* interop for harnesses that own device memory / streams (PyTorch, NCCL):
+ * run on a caller-provided cudaStream_t (NULL = the context's own stream) */
+int b2r_set_stream(b2r_context* ctx, void* cuda_stream);
+/* device pointers of the colour (uint32) and depth (int32) surfaces */
+int b2r_device_surfaces(b2r_context* ctx, void** framebuffer, void** depth);
+/* redirect the ROP write-back of later frames into caller-provided device memory
+ * (e.g. a peer GPU's framebuffer mapped over NVLink); NULL restores the internal surface */
+int b2r_bind_framebuffer(b2r_context* ctx, void* device_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

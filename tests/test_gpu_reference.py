@@ -1,0 +1,118 @@
+"""-m gpu: pins the oracle AND the product against the reference itself.
+
+oracle/_ref/ref_render is the UNMODIFIED reference CUDA renderer (built from /root/reference by
+oracle/build_ref.sh, with our headless driver).  It only runs on a GPU box.  Each test runs it on a
+scene dump and compares every surface with the CPU oracle (faithful mode: reference fill rule,
+integer-division launch grids) and with the CUDA path.
+
+The reference resolves equal-depth fragments and the order of visible triangles by races, so
+pixels where the oracle saw a depth tie or an exact-edge fragment are the only ones allowed to
+differ (BASELINE.json: "only on shared triangle edges").
+"""
+import numpy as np
+import pytest
+
+import oracle_lib
+import parity
+from custom_gpgpu_rasterizer_b200 import scenes
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not parity.have_ref(), reason="oracle/_ref/ref_render not built")]
+
+SCENES = {
+    "soup_vertex_colour": lambda: scenes.random_triangles_scene(640, 480, 400, seed=11, cull=2),
+    "soup_backface_3_meshes": lambda: scenes.random_triangles_scene(640, 480, 600, seed=12, cull=0, n_meshes=3),
+    "soup_frontface": lambda: scenes.random_triangles_scene(640, 480, 300, seed=13, cull=1, n_meshes=2),
+    "soup_textured_point": lambda: scenes.random_triangles_scene(640, 480, 300, seed=14, cull=2, textured=True, n_meshes=3),
+    "soup_textured_linear": lambda: scenes.random_triangles_scene(640, 480, 300, seed=15, cull=2, textured=True, n_meshes=3, sample=1),
+    "soup_depth_vis": lambda: scenes.random_triangles_scene(640, 480, 200, seed=16, cull=2, vis=1),
+    "soup_normal_vis": lambda: scenes.random_triangles_scene(640, 480, 200, seed=17, cull=2, vis=2),
+    "spheres_small": lambda: scenes.sphere_grid_scene(960, 544, nx=6, ny=4, stacks=41, slices=60, cam_z=14.0),
+    "spheres_tiny_tris": lambda: scenes.sphere_grid_scene(640, 480, nx=8, ny=5, stacks=81, slices=100, cam_z=22.0),
+    "fill_quads_linear": lambda: scenes.fill_quads_scene(640, 480, layers=8, tex_size=256, sample=1),
+    "shared_edges": lambda: scenes.shared_edge_scene(),
+}
+
+
+def _ref_bins_as_sets(scene, ref):
+    """{bin: sorted rows of (mesh, idx0, idx1, idx2)} from the reference's per-batch queue dumps."""
+    rows = []
+    for mi, m in enumerate(ref["meshes"]):
+        p = m["bin_pairs"]
+        if p.size:
+            rows.append(np.concatenate([p[:, :1], np.full((p.shape[0], 1), mi, np.uint32), p[:, 1:]], 1))
+    return parity.sort_rows(np.concatenate(rows, 0)) if rows else np.zeros((0, 5), np.uint32)
+
+
+def _ids_as_rows(scene, counts, ids):
+    bases = scene.prim_bases()
+    bin_of = np.repeat(np.arange(len(counts), dtype=np.uint32), counts)
+    mesh_of = np.searchsorted(np.asarray(bases[1:] + [1 << 62]), ids, side="right").astype(np.uint32)
+    rows = np.zeros((ids.size, 5), np.uint32)
+    rows[:, 0] = bin_of
+    rows[:, 1] = mesh_of
+    for mi, m in enumerate(scene.meshes):
+        sel = mesh_of == mi
+        rows[sel, 2:] = m.indices.reshape(-1, 3)[ids[sel] - bases[mi]]
+    return parity.sort_rows(rows)
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_oracle_matches_reference(name):
+    sc = SCENES[name]()
+    ref = parity.run_ref(sc, "stages")
+    o = oracle_lib.render(sc, fill_rule=0, model_holes=True)
+
+    # host side: camera matrices
+    for k in ("view_proj", "view", "proj", "cam_pos", "cam_fwd"):
+        assert np.array_equal(parity.bits(ref[k]), parity.bits(o[k])), f"{k}: oracle differs from the reference"
+    assert ref["total_tris"] == o["total_tris"]
+    assert ref["visible_tris"] == o["visible_tris"], "number of visible triangles differs"
+    for mi, m in enumerate(sc.meshes):
+        # VS_Kernel output, bit for bit
+        assert np.array_equal(parity.bits(ref["meshes"][mi]["overtex"]), parity.bits(o["meshes"][mi]["overtex"])), f"mesh {mi}: OVertex buffer differs"
+        # TA_Kernel output as a set (the reference appends in atomicAdd order)
+        want = parity.sort_rows(parity.triples_of(sc, mi, np.nonzero(o["meshes"][mi]["visible"])[0]))
+        got = parity.sort_rows(ref["meshes"][mi]["visible_triples"])
+        assert np.array_equal(want, got), f"mesh {mi}: visible triangle set differs"
+    # TB_Kernel output: per-bin sets, bit-exact after sorting
+    assert np.array_equal(_ref_bins_as_sets(sc, ref), _ids_as_rows(sc, o["bin_counts"], o["bin_ids"])), "bin sets differ"
+
+    covered_ref = ref["depth"] != 0x7FFFFFFF
+    covered_orc = o["depth"] != 0x7FFFFFFF
+    h_clear = 32 * (sc.height // 32)          # rows the reference's Clear actually resets (CUDARenderer.cu:1642)
+    allowed = parity.dilate(o["edge_mask"] != 0, 0)
+    assert np.array_equal(covered_ref[:h_clear] | allowed[:h_clear], covered_orc[:h_clear] | allowed[:h_clear]), "coverage differs away from exact edges"
+    same_cov = covered_ref & covered_orc & ~allowed
+    parity.assert_depth_parity(ref["z"], o["z"], same_cov, name)
+    exact_depth = float((ref["depth"][same_cov] == o["depth"][same_cov]).mean()) if same_cov.any() else 1.0
+    assert exact_depth == 1.0, f"integer depth differs away from ties: exact fraction {exact_depth}"
+    rep = parity.assert_colour_parity(ref["framebuffer"], o["framebuffer"], allowed, name)
+    print(f"[{name}] oracle vs reference: {rep}, exact depth {exact_depth}")
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_product_matches_reference(name):
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    sc = SCENES[name]()
+    ref = parity.run_ref(sc, "render")
+    o = oracle_lib.render(sc, fill_rule=0, model_holes=True)       # only for the edge/tie mask
+    r = Renderer(sc.width, sc.height)
+    try:
+        r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+        r.load_scene(sc)
+        r.render_scene(sc)
+        total, visible = r.stats()
+        assert (total, visible) == (ref["total_tris"], ref["visible_tris"])
+        fb, z, depth = r.framebuffer(), r.z(), r.depth()
+        h_ok = min(32 * (sc.height // 32), 16 * (sc.height // 16))   # rows the reference both clears and shades
+        allowed = o["edge_mask"] != 0
+        covered_ref = ref["depth"] != 0x7FFFFFFF
+        covered = depth != 0x7FFFFFFF
+        assert np.array_equal((covered_ref | allowed)[:h_ok], (covered | allowed)[:h_ok]), "coverage differs away from exact edges"
+        same = (covered_ref & covered & ~allowed)[:h_ok]
+        parity.assert_depth_parity(ref["z"][:h_ok], z[:h_ok], same, name)
+        rep = parity.assert_colour_parity(ref["framebuffer"][:h_ok], fb[:h_ok], allowed[:h_ok], name)
+        print(f"[{name}] product vs reference: {rep}")
+    finally:
+        r.close()
