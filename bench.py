@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Headline benchmark of the B200 rendering path (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload spheres10m|fill64]
+
+One "step" = one frame of the workload through the per-frame hot path.  At N=1 the workload is the
+configuration BASELINE.json's metric is quoted on: the 10 000 000-triangle sphere grid at 3840x2160
+(config 3).  N>1 launches one rank per GPU (torchrun); the frame is sharded sort-first (each rank owns an
+interleaved set of 16x16 tiles, transforms and bins the full mesh, rasterises only its tiles, and the
+framebuffer is gathered to rank 0 over NCCL/NVLink).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from custom_gpgpu_rasterizer_b200 import scenes  # noqa: E402  (numpy only)
+
+WIDTH, HEIGHT = 3840, 2160
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_scene(workload: str):
+    if workload == "spheres10m":
+        return scenes.sphere_grid_scene(WIDTH, HEIGHT)                      # BASELINE config 3
+    if workload == "spheres_small":                                        # quick functional check
+        return scenes.sphere_grid_scene(WIDTH, HEIGHT, nx=5, ny=5)
+    if workload == "fill64":
+        return scenes.fill_quads_scene(WIDTH, HEIGHT, layers=64, sample=1)  # BASELINE config 4
+    raise SystemExit(f"unknown workload {workload}")
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, n in enumerate(names):
+                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_arm(scene, steps: int, warmup: int):
+    """The reference's CPU software path (ERenderer restatement, oracle/liborc_erenderer.so), 1 thread."""
+    lib_path = os.path.join(ROOT, "oracle", "liborc_erenderer.so")
+    if not os.path.exists(lib_path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liborc_erenderer.so"])
+    L = C.CDLL(lib_path)
+    L.ere_load.restype = C.c_void_p
+    L.ere_load.argtypes = [C.c_char_p, C.c_uint64]
+    L.ere_render.restype = C.c_double
+    L.ere_render.argtypes = [C.c_void_p] + [C.c_uint32] * 4
+    L.ere_free.argtypes = [C.c_void_p]
+    blob = scene.to_blob()
+    S = L.ere_load(blob, len(blob))
+    times = []
+    for i in range(warmup + steps):
+        t = L.ere_render(S, 0, 0xFFFFFFFF, 0, 0xFFFFFFFF)
+        if i >= warmup:
+            times.append(t)
+    L.ere_free(S)
+    return float(np.mean(times)), times
+
+
+def run_reference(args, scene):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded: the full frame costs ~1 s on one core, so a handful of frames stays within minutes
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    mean_s, _ = cpu_reference_arm(scene, steps, warmup)
+    fps = 1.0 / mean_s
+    line = {
+        "impl": "reference", "metric": "frames/s at 4K (device-timed for the GPU arm; host steady_clock for this arm)",
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean_s * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mtris_per_s": scene.n_tris / mean_s / 1e6,
+        "config": workload_config(args.workload, scene),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": f"full frame of the workload, {steps} frames after {warmup} warm-up; ERenderer.cpp restated (the in-tree file is stale and cannot compile); single-threaded like the reference",
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, scene):
+    return {"workload": {"spheres10m": "BASELINE config 3: 25x25 UV-sphere grid, 10 000 000 triangles / 5 176 250 vertices, 3840x2160, 16x16 tiles (240x135), back-face culling, vertex colours",
+                         "fill64": "BASELINE config 4: 64 stacked full-screen textured quads, 3840x2160, linear sampling, no culling",
+                         "spheres_small": "5x5 spheres (400 000 triangles), 3840x2160"}[name],
+            "triangles": scene.n_tris, "vertices": scene.n_vertices, "resolution": f"{scene.width}x{scene.height}",
+            "l2_policy": "inputs larger than L2 (vertex+index streams 410 MB, intermediates ~1 GB per frame)" if name == "spheres10m" else "working set is L2-resident by nature of the workload (textures + 128 triangles); framebuffer write-back 66 MB per frame"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def algorithmic_bytes(scene, visible, pairs, frags, covered_px):
+    """SURVEY.md section 8d / BASELINE.md section 3 contract figures."""
+    V, T, Tv, P, N = scene.n_vertices, scene.n_tris, visible, pairs, scene.bins_x * scene.bins_y
+    px = scene.width * scene.height
+    return {
+        "vertex": V * 128,
+        "setup": T * 60 + Tv * 12,
+        "binning": Tv * 120 + P * 4 + N * 16,
+        # fill/ROP: F*4 (depth read) + Fp*8 (depth+colour write) + W*H*8 (write-back) + list consumption P*(4+48)
+        "raster_shade": frags * 4 + covered_px * 8 + px * 8 + P * 52,
+    }
+
+
+def run_b200(args, scene):
+    import torch
+    import torch.distributed as dist
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    r = Renderer(scene.width, scene.height, device=local)
+    r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
+    r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
+    t0 = time.perf_counter()
+    r.load_scene(scene)
+    load_s = time.perf_counter() - t0
+    stream = torch.cuda.Stream(device=dev)
+    r.set_stream(stream.cuda_stream)
+    from custom_gpgpu_rasterizer_b200.renderer import host_camera
+    cam = host_camera(scene.cam_pos, scene.fov_deg, scene.width, scene.height, scene.near, scene.far)
+
+    gather = None
+    if world > 1:
+        from custom_gpgpu_rasterizer_b200.multi_gpu import SortFirstGather
+        gather = SortFirstGather(r, scene, rank, world, stream)
+
+    def frame():
+        r.render(cam, scene.cull, scene.sample, scene.vis, sync=False)
+        if gather is not None:
+            gather.run()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also grows the bin-list buffer if needed)
+    for _ in range(max(args.warmup, 3)):
+        frame()
+    r.sync()
+    barrier()
+
+    # ---- timed region: device time of K frames, max over ranks
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.steps):
+                frame()
+            e1.record(stream)
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    counters = r.counters()
+    launches_per_frame = counters["kernels_launched"] + (gather.launches_per_frame if gather else 0)
+
+    # ---- end to end through the public API: per-frame constants H2D + render + framebuffer D2H to pinned host memory
+    pinned = torch.empty((scene.height, scene.width), dtype=torch.int32, pin_memory=True)
+    host_fb = pinned.numpy().view(np.uint32)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame()
+        if rank == 0:
+            r.framebuffer(out=host_fb)       # Present(): device->host copy of the gathered frame
+        else:
+            r.sync()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+
+    # ---- per-stage device times over K more frames (CUDA events recorded between the stages on the same stream)
+    r.set_option(_lib.OPT_STAGE_TIMERS, 1)
+    r.stage_ms_mean(reset=True)
+    for _ in range(args.steps):
+        frame()
+    r.sync()
+    stages, n_timed = r.stage_ms_mean(reset=True)
+    r.set_option(_lib.OPT_STAGE_TIMERS, 0)
+
+    # ---- workload counters for the roofline (instrumented frame, outside every timed region)
+    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
+    frame()
+    r.sync()
+    c2 = r.counters()
+    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 0)
+    total_tris, visible = r.stats()
+    depth = r.depth()
+    covered_px = int((depth != 0x7FFFFFFF).sum())
+    barrier()
+
+    if rank != 0:
+        r.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fps = args.steps / (total_ms / 1e3)
+    peak, peak_src = load_peaks()
+    ab = algorithmic_bytes(scene, visible, counters["pairs"], c2["fragments"], covered_px)
+    stage_of = {"vertex": "vertex", "setup": "setup", "binning": None, "raster_shade": "raster_shade"}
+    per_stage = {}
+    for k, b in ab.items():
+        t = stages["bin_scan"] + stages["bin_scatter"] + stages["bin_sort"] if k == "binning" else stages[stage_of[k]]
+        if k == "setup":
+            pass
+        per_stage[k] = {"ms": t, "algorithmic_bytes": b, "gbs": (b / 1e9) / (t / 1e3) if t > 0 else None,
+                        "frac_of_hbm_peak": ((b / 1e9) / (t / 1e3)) / peak if t > 0 else None}
+    dominant = max(per_stage, key=lambda k: per_stage[k]["ms"])
+    roof = per_stage[dominant]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dominant)
+    except Exception:
+        pass
+
+    line = {
+        "metric": "frames/s at 4K (device-timed)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, NCCL gather to rank 0")),
+        "mtris_per_s": scene.n_tris * fps / 1e6,
+        "visible_triangles": visible, "tile_pairs": counters["pairs"], "fragments": c2["fragments"], "covered_pixels": covered_px,
+        "stages_ms": stages, "stages": per_stage,
+        "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
+                     "traffic": traffic, "peak_source": peak_src,
+                     "note": "achieved = algorithmic bytes of SURVEY section 8d / stage time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},
+        "e2e": {"value": args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": len(scene.meshes) * 208,
+                "d2h_bytes_per_step": scene.width * scene.height * 4,
+                "note": "b2r_render + b2r_read_framebuffer into pinned host memory every frame (RenderAuto = Render + Present), wall clock"},
+        "gpu_launches": launches_per_frame * args.steps,
+        "gpu_launches_per_step": launches_per_frame,
+        "load_scene_s": load_s,
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        mean_s, _ = cpu_reference_arm(scene, 3, 1)
+        line["cpu_baseline"] = {"value": 1.0 / mean_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                                "sample": "the full frame of this workload, 3 frames after 1 warm-up, ERenderer restatement (oracle/erenderer_oracle.cpp), single-threaded like the reference",
+                                "mtris_per_s": scene.n_tris / mean_s / 1e6, "host_cores_available": os.cpu_count()}
+    if world == 1 and args.workload == "spheres10m" and not args.no_fill:
+        line["fill_test"] = fill_test(r.__class__, _lib, torch, dev, args, peak)
+    r.close()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def fill_test(Renderer, _lib, torch, dev, args, peak):
+    """BASELINE config 4 on the same GPU: fill/ROP-equivalent bandwidth (north_star: >= 50 % of the HBM roofline)."""
+    from custom_gpgpu_rasterizer_b200.renderer import host_camera
+    sc = make_scene("fill64")
+    r = Renderer(sc.width, sc.height, device=dev.index)
+    r.load_scene(sc)
+    stream = torch.cuda.Stream(device=dev)
+    r.set_stream(stream.cuda_stream)
+    cam = host_camera(sc.cam_pos, sc.fov_deg, sc.width, sc.height, sc.near, sc.far)
+    for _ in range(3):
+        r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+    r.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    r.set_option(_lib.OPT_STAGE_TIMERS, 1)
+    r.stage_ms_mean(reset=True)
+    for _ in range(args.steps):
+        r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+    r.sync()
+    stages, _ = r.stage_ms_mean(reset=True)
+    r.set_option(_lib.OPT_STAGE_TIMERS, 0)
+    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
+    r.render(cam, sc.cull, sc.sample, sc.vis, sync=True)
+    frags = r.counters()["fragments"]
+    r.close()
+    px = sc.width * sc.height
+    rop_bytes = frags * 4 + frags * 8 + px * 8          # back-to-front: every fragment passes depth (F = Fp)
+    t = stages["raster_shade"]
+    return {"workload": "BASELINE config 4: 64 stacked full-screen textured quads, 3840x2160, linear sampling",
+            "frames_per_s": 1e3 / ms, "ms_per_frame": ms, "fragments": frags, "gfragments_per_s": frags / (t / 1e3) / 1e9,
+            "raster_shade_ms": t, "rop_equivalent_bytes": rop_bytes, "rop_equivalent_gbs": (rop_bytes / 1e9) / (t / 1e3),
+            "frac_of_hbm_peak": (rop_bytes / 1e9) / (t / 1e3) / peak, "physical_write_back_bytes": px * 8, "stages_ms": stages}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fill", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return
+    scene = make_scene(args.workload)
+    if args.impl == "reference":
+        run_reference(args, scene)
+    else:
+        run_b200(args, scene)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,7 @@ SAMPLE_POINT, SAMPLE_LINEAR = 0, 1
 VIS_PBR, VIS_DEPTH, VIS_NORMAL = 0, 1, 2
 TOPOLOGY_TRIANGLE_LIST, TOPOLOGY_TRIANGLE_STRIP = 0, 1
 OPT_FILL_RULE_TOP_LEFT, OPT_TILE_OWNER_RANK, OPT_TILE_OWNER_COUNT = 1, 2, 3
-OPT_DEBUG_SURFACES, OPT_STAGE_TIMERS, OPT_SORT_BINS = 4, 5, 6
+OPT_DEBUG_SURFACES, OPT_STAGE_TIMERS, OPT_SORT_BINS, OPT_COUNT_FRAGMENTS = 4, 5, 6, 7
 STAGE_NAMES = ("vertex", "setup", "bin_scan", "bin_scatter", "bin_sort", "raster_shade", "total")
 NUM_STAGES = 7
 
@@ -57,6 +57,7 @@ ABI = {
     "b2r_read_bins": (_i32, [_vp, _vp, _vp, _vp, _u64, _u64p]),
     "b2r_get_stats": (_i32, [_vp, _u32p, _u32p]),
     "b2r_get_stage_ms": (_i32, [_vp, _fp, _i32]),
+    "b2r_get_stage_ms_mean": (_i32, [_vp, _fp, _i32, _u64p, _i32]),
     "b2r_get_counters": (_i32, [_vp, _u64p, _i32]),
     "b2r_set_stream": (_i32, [_vp, _vp]),
     "b2r_device_surfaces": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),

@@ -30,6 +30,8 @@ using namespace b2r;
 
 namespace {
 
+constexpr int kRing = 4;
+constexpr int kInfoWords = 6;
 thread_local std::string g_createError;
 
 // grow-only device array
@@ -101,14 +103,32 @@ struct b2r_context
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
 	DeviceVec<MeshConst> dMeshConst;
-	MeshConst* hMeshConst = nullptr; size_t hMeshConstCap = 0;   // pinned staging
 	DeviceVec<TexDesc> dTexDesc;
 
 	// binning
 	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dBigList, dBinIds;
 	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
-	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles
-	struct HostInfo { unsigned long long frameInfo[4]; uint32_t counters[2]; } *hInfo = nullptr;   // pinned
+	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
+	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };
+
+	// frames in flight: each enqueued frame owns one slot of pinned host memory + events, so the
+	// host can run ahead of the device by kRing frames without a synchronisation
+	struct Slot
+	{
+		HostInfo* hInfo = nullptr;                 // pinned
+		MeshConst* hMeshConst = nullptr;           // pinned staging of the per-mesh constants
+		size_t hMeshConstCap = 0;
+		cudaEvent_t done = nullptr;
+		cudaEvent_t ev[B2R_NUM_STAGES] = {};
+		bool pending = false, timed = false;
+	} slots[kRing];
+	uint64_t seq = 0;
+	HostInfo lastInfo{};                           // info of the newest harvested frame
+	size_t overflowNeed = 0;
+	double stageAccum[B2R_NUM_STAGES] = {};
+	float stageLast[B2R_NUM_STAGES] = {};
+	uint64_t stageFrames = 0;
+	bool haveStageTimes = false;
 
 	// surfaces
 	uint32_t* dFramebuffer = nullptr; int32_t* dDepth = nullptr; float* dZ = nullptr; uint32_t* dWinner = nullptr;
@@ -116,10 +136,8 @@ struct b2r_context
 
 	// frame state
 	RenderCall last;
-	bool framePending = false;      // a frame was enqueued and its info not yet validated
 	bool haveFrame = false;
-	cudaEvent_t ev[B2R_NUM_STAGES + 1] = {};
-	bool evRecorded = false;
+	int countFragments = 0;
 	uint64_t kernelsLaunched = 0;
 	int numSMs = 148;
 };
@@ -204,12 +222,6 @@ int rebuildScene(b2r_context* c)
 	CU(c, c->dRects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dBigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dMeshConst.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
-	if (c->hMeshConstCap < c->meshes.size())
-	{
-		if (c->hMeshConst) cudaFreeHost(c->hMeshConst);
-		c->hMeshConstCap = std::max<size_t>(c->meshes.size() * 2, 16);
-		CU(c, cudaMallocHost((void**)&c->hMeshConst, c->hMeshConstCap * sizeof(MeshConst)));
-	}
 	// list capacity heuristic; regrown on overflow (see validateFrame)
 	CU(c, c->dBinIds.reserve(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), c->stream));
 	c->sceneDirty = false;
@@ -243,7 +255,32 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	return fp;
 }
 
-#define STAGE_EVENT(c, i) do { if ((c)->stageTimers) CU((c), cudaEventRecord((c)->ev[(i)], (c)->stream)); } while (0)
+#define STAGE_EVENT(c, slot, i) do { if ((slot).timed) CU((c), cudaEventRecord((slot).ev[(i)], (c)->stream)); } while (0)
+
+// book-keeping of a finished frame: capacity overflow, stage times, counters
+int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
+{
+	slot.pending = false;
+	c->lastInfo = *slot.hInfo;
+	if (slot.hInfo->frameInfo[1])
+		c->overflowNeed = std::max(c->overflowNeed, (size_t)slot.hInfo->frameInfo[0]);
+	if (slot.timed)
+	{
+		float total = 0.f;
+		for (int i = 0; i < 6; ++i)
+		{
+			float ms = 0.f;
+			CU(c, cudaEventElapsedTime(&ms, slot.ev[i], slot.ev[i + 1]));
+			c->stageLast[i] = ms; c->stageAccum[i] += ms; total += ms;
+		}
+		float ms = 0.f;
+		CU(c, cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[6]));
+		c->stageLast[B2R_STAGE_TOTAL] = ms; c->stageAccum[B2R_STAGE_TOTAL] += ms;
+		++c->stageFrames;
+		c->haveStageTimes = true;
+	}
+	return B2R_OK;
+}
 
 int enqueueFrame(b2r_context* c)
 {
@@ -256,11 +293,25 @@ int enqueueFrame(b2r_context* c)
 	const uint32_t tiles = nBins(c);
 	c->kernelsLaunched = 0;
 
+	b2r_context::Slot& slot = c->slots[c->seq % kRing];
+	if (slot.pending)
+	{
+		CU(c, cudaEventSynchronize(slot.done));
+		int r = harvestSlot(c, slot); if (r) return r;
+	}
+	if (slot.hMeshConstCap < c->meshes.size())
+	{
+		if (slot.hMeshConst) cudaFreeHost(slot.hMeshConst);
+		slot.hMeshConstCap = std::max<size_t>(c->meshes.size() * 2, 16);
+		CU(c, cudaMallocHost((void**)&slot.hMeshConst, slot.hMeshConstCap * sizeof(MeshConst)));
+	}
+	slot.timed = c->stageTimers != 0;
+
 	// per-mesh constants
 	for (size_t m = 0; m < c->meshes.size(); ++m)
 	{
 		const HostMesh& hm = c->meshes[m];
-		MeshConst& mc = c->hMeshConst[m];
+		MeshConst& mc = slot.hMeshConst[m];
 		mulMat4(rc.viewProj, hm.world, mc.wvp);
 		memcpy(mc.world, hm.world, 64);
 		for (int col = 0; col < 3; ++col) for (int r = 0; r < 3; ++r) mc.rot[col * 3 + r] = hm.world[col * 4 + r];
@@ -274,18 +325,19 @@ int enqueueFrame(b2r_context* c)
 		mc.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
 		mc.pad = 0;
 	}
-	if (c->stageTimers) CU(c, cudaEventRecord(c->ev[0], s));
+	STAGE_EVENT(c, slot, 0);
 	if (!c->meshes.empty())
-		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, c->hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
+		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, slot.hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
 	CU(c, cudaMemsetAsync(c->dTileCount.ptr, 0, tiles * 4, s));
 	CU(c, cudaMemsetAsync(c->dCounters, 0, 8, s));
+	CU(c, cudaMemsetAsync(c->dFrameInfo, 0, kInfoWords * 8, s));
 
 	if (c->nVsChunks)
 	{
 		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, c->dMeshConst.ptr, c->dIVertex.ptr, c->dPos4.ptr, c->dAttr.ptr, fp);
 		++c->kernelsLaunched;
 	}
-	STAGE_EVENT(c, 1);
+	STAGE_EVENT(c, slot, 1);
 	if (c->nTriChunks)
 	{
 		triangle_setup_kernel<<<c->nTriChunks, kChunk, 0, s>>>(c->dTriChunks.ptr, c->dMeshConst.ptr, c->dIndices.ptr, c->dPos4.ptr,
@@ -293,11 +345,11 @@ int enqueueFrame(b2r_context* c)
 		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, fp);
 		c->kernelsLaunched += 2;
 	}
-	STAGE_EVENT(c, 2);
+	STAGE_EVENT(c, slot, 2);
 	tile_scan_kernel<<<1, 1024, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dTileCursor.ptr, tiles,
 		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortSmall, c->dLongTiles.ptr, c->dFrameInfo);
 	++c->kernelsLaunched;
-	STAGE_EVENT(c, 3);
+	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
 	{
 		bin_scatter_kernel<<<(uint32_t)((c->nPrims + 255) / 256), 256, 0, s>>>(c->dRects.ptr, (uint32_t)c->nPrims, c->dTileOffset.ptr,
@@ -306,7 +358,7 @@ int enqueueFrame(b2r_context* c)
 			c->dTileCursor.ptr, c->dBinIds.ptr, fp);
 		c->kernelsLaunched += 2;
 	}
-	STAGE_EVENT(c, 4);
+	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
 		bin_sort_kernel<<<tiles, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
@@ -314,7 +366,7 @@ int enqueueFrame(b2r_context* c)
 			c->dBinIds.ptr, c->dFrameInfo);
 		c->kernelsLaunched += 2;
 	}
-	STAGE_EVENT(c, 5);
+	STAGE_EVENT(c, slot, 5);
 	{
 		RasterArgs A{};
 		A.tileCount = c->dTileCount.ptr; A.tileOffset = c->dTileOffset.ptr; A.binIds = c->dBinIds.ptr;
@@ -326,31 +378,43 @@ int enqueueFrame(b2r_context* c)
 		if (owned)
 		{
 			const dim3 grid(owned, fp.subX * fp.subY);
-			if (c->fillTopLeft) raster_shade_kernel<true><<<grid, kTile * kTile, 0, s>>>(A, fp);
-			else raster_shade_kernel<false><<<grid, kTile * kTile, 0, s>>>(A, fp);
+			const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0);
+			switch (variant)
+			{
+			case 0: raster_shade_kernel<false, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 1: raster_shade_kernel<true, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 2: raster_shade_kernel<false, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			default: raster_shade_kernel<true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			}
 			++c->kernelsLaunched;
 		}
 	}
-	STAGE_EVENT(c, 6);
-	c->evRecorded = c->stageTimers != 0;
-	CU(c, cudaMemcpyAsync(c->hInfo->frameInfo, c->dFrameInfo, 32, cudaMemcpyDeviceToHost, s));
-	CU(c, cudaMemcpyAsync(c->hInfo->counters, c->dCounters, 8, cudaMemcpyDeviceToHost, s));
+	STAGE_EVENT(c, slot, 6);
+	CU(c, cudaMemcpyAsync(slot.hInfo->frameInfo, c->dFrameInfo, kInfoWords * 8, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaMemcpyAsync(slot.hInfo->counters, c->dCounters, 8, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
-	c->framePending = true;
+	slot.pending = true;
+	++c->seq;
 	c->haveFrame = true;
 	return B2R_OK;
 }
 
-// wait for the frame; if the bin-list buffer was too small, grow it and run the frame again
+// wait for every frame in flight; if the bin-list buffer was too small for any of them, grow it
+// and run the newest frame again (older frames were overwritten anyway)
 int validateFrame(b2r_context* c)
 {
 	for (int attempt = 0; attempt < 4; ++attempt)
 	{
 		CU(c, cudaStreamSynchronize(c->stream));
-		if (!c->framePending) return B2R_OK;
-		c->framePending = false;
-		if (!c->hInfo->frameInfo[1]) return B2R_OK;
-		const size_t need = (size_t)c->hInfo->frameInfo[0];
+		for (uint64_t k = 0; k < kRing; ++k)
+		{
+			b2r_context::Slot& slot = c->slots[(c->seq + k) % kRing];     // oldest first
+			if (slot.pending) { int r = harvestSlot(c, slot); if (r) return r; }
+		}
+		if (!c->overflowNeed) return B2R_OK;
+		const size_t need = c->overflowNeed;
+		c->overflowNeed = 0;
 		CU(c, c->dBinIds.reserve(need + need / 4, c->stream));
 		int r = enqueueFrame(c);
 		if (r) return r;
@@ -387,12 +451,16 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	CUC(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device));
 	CUC(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	c->stream = c->ownStream;
-	for (auto& e : c->ev) CUC(cudaEventCreate(&e));
+	for (auto& slot : c->slots)
+	{
+		CUC(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+		for (auto& e : slot.ev) CUC(cudaEventCreate(&e));
+		CUC(cudaMallocHost((void**)&slot.hInfo, sizeof(b2r_context::HostInfo)));
+		memset(slot.hInfo, 0, sizeof(b2r_context::HostInfo));
+	}
 	CUC(cudaMalloc((void**)&c->dCounters, 8));
-	CUC(cudaMalloc((void**)&c->dFrameInfo, 32));
-	CUC(cudaMemset(c->dFrameInfo, 0, 32));
-	CUC(cudaMallocHost((void**)&c->hInfo, sizeof(*c->hInfo)));
-	memset(c->hInfo, 0, sizeof(*c->hInfo));
+	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8));
+	CUC(cudaMemset(c->dFrameInfo, 0, kInfoWords * 8));
 	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortLarge * sizeof(uint32_t))));
 #undef CUC
 	int r = allocSurfaces(c);
@@ -415,9 +483,13 @@ void b2r_destroy(b2r_context* c)
 	c->dTileCursor.release(); c->dLongTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dCounters); cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
-	if (c->hMeshConst) cudaFreeHost(c->hMeshConst);
-	if (c->hInfo) cudaFreeHost(c->hInfo);
-	for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+	for (auto& slot : c->slots)
+	{
+		if (slot.hMeshConst) cudaFreeHost(slot.hMeshConst);
+		if (slot.hInfo) cudaFreeHost(slot.hInfo);
+		if (slot.done) cudaEventDestroy(slot.done);
+		for (auto& e : slot.ev) if (e) cudaEventDestroy(e);
+	}
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
 }
@@ -532,6 +604,7 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_DEBUG_SURFACES: c->debugSurfaces = value ? 1 : 0; break;
 	case B2R_OPT_STAGE_TIMERS: c->stageTimers = value ? 1 : 0; break;
 	case B2R_OPT_SORT_BINS: c->sortBins = value ? 1 : 0; break;
+	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
 	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
 	}
 	if (c->ownerRank >= c->ownerCount) { /* tolerated while the pair is being set; checked at render */ }
@@ -546,11 +619,6 @@ int b2r_render(b2r_context* c, const float camPos[3], const float camFwd[3], con
 	if (cull < 0 || cull > 2 || sample < 0 || sample > 1 || vis < 0 || vis > 2) return fail(c, B2R_E_INVALID, "bad render state");
 	if (c->ownerRank >= c->ownerCount) return fail(c, B2R_E_INVALID, "tile owner rank %d >= count %d", c->ownerRank, c->ownerCount);
 	CU(c, cudaSetDevice(c->device));
-	if (c->framePending)
-	{
-		// the previous frame's pinned info block is about to be overwritten: settle it first
-		int r = validateFrame(c); if (r) return r;
-	}
 	RenderCall& rc = c->last;
 	memcpy(rc.camPos, camPos, 12); memcpy(rc.camFwd, camFwd, 12); memcpy(rc.viewProj, viewProj, 64);
 	static const float defClear[3] = { 0.25f, 0.25f, 0.25f };   // CUDARenderer.h:135
@@ -631,7 +699,7 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	if (!c->haveFrame) return fail(c, B2R_E_STATE, "read_bins: nothing rendered yet");
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
-	const uint64_t pairs = c->hInfo->frameInfo[0];
+	const uint64_t pairs = c->lastInfo.frameInfo[0];
 	if (total) *total = pairs;
 	const uint32_t n = nBins(c);
 	if (counts) CU(c, cudaMemcpy(counts, c->dTileCount.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -650,7 +718,7 @@ int b2r_get_stats(b2r_context* c, uint32_t* totalTris, uint32_t* visibleTris)
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
 	if (totalTris) *totalTris = (uint32_t)c->nPrims;
-	if (visibleTris) *visibleTris = c->haveFrame ? c->hInfo->counters[0] : 0;
+	if (visibleTris) *visibleTris = c->haveFrame ? c->lastInfo.counters[0] : 0;
 	return B2R_OK;
 }
 
@@ -658,13 +726,22 @@ int b2r_get_stage_ms(b2r_context* c, float* out, int n)
 {
 	if (!c) return B2R_E_INVALID;
 	if (!out || n < 1) return fail(c, B2R_E_INVALID, "bad output");
-	if (!c->evRecorded) return fail(c, B2R_E_STATE, "stage timers were not enabled for the last frame (B2R_OPT_STAGE_TIMERS)");
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
-	float ms[B2R_NUM_STAGES] = {};
-	for (int i = 0; i < 6; ++i) CU(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
-	CU(c, cudaEventElapsedTime(&ms[B2R_STAGE_TOTAL], c->ev[0], c->ev[6]));
-	for (int i = 0; i < n && i < B2R_NUM_STAGES; ++i) out[i] = ms[i];
+	if (!c->haveStageTimes) return fail(c, B2R_E_STATE, "no frame was rendered with B2R_OPT_STAGE_TIMERS enabled");
+	for (int i = 0; i < n && i < B2R_NUM_STAGES; ++i) out[i] = c->stageLast[i];
+	return B2R_OK;
+}
+
+int b2r_get_stage_ms_mean(b2r_context* c, float* out, int n, uint64_t* frames, int reset)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!out || n < 1) return fail(c, B2R_E_INVALID, "bad output");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	for (int i = 0; i < n && i < B2R_NUM_STAGES; ++i) out[i] = c->stageFrames ? (float)(c->stageAccum[i] / (double)c->stageFrames) : 0.f;
+	if (frames) *frames = c->stageFrames;
+	if (reset) { for (auto& a : c->stageAccum) a = 0.0; c->stageFrames = 0; }
 	return B2R_OK;
 }
 
@@ -676,8 +753,8 @@ int b2r_get_counters(b2r_context* c, uint64_t* out, int n)
 	int r = validateFrame(c); if (r) return r;
 	const uint32_t tiles = nBins(c);
 	const uint64_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - c->ownerRank + c->ownerCount - 1) / c->ownerCount : 0;
-	const uint64_t v[6] = { c->hInfo->frameInfo[0], c->kernelsLaunched, owned, tiles, c->hInfo->frameInfo[2], c->hInfo->counters[1] };
-	for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+	const uint64_t v[7] = { c->lastInfo.frameInfo[0], c->kernelsLaunched, owned, tiles, c->lastInfo.frameInfo[2], c->lastInfo.counters[1], c->lastInfo.frameInfo[4] };
+	for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
 	return B2R_OK;
 }
 

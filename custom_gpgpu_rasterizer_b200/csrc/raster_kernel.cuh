@@ -29,7 +29,7 @@ struct RasterArgs
 	const float4* attr;
 	const MeshConst* meshes;
 	const TexDesc* textures;
-	const unsigned long long* frameInfo;
+	unsigned long long* frameInfo;
 	uint32_t* framebuffer;
 	int32_t* depth;
 	float* zSurface;        // debug surfaces (may be null)
@@ -183,7 +183,7 @@ __device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& 
 constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
 constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are rasterised by one thread
 
-template <bool TOPLEFT>
+template <bool TOPLEFT, bool COUNT>
 __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
 	__shared__ TriShared sTri[kListChunk];
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 	const float fx = (float)px, fy = (float)py;
 
 	unsigned long long best = kEmptyKey;
+	uint32_t nFrags = 0;      // fragments that pass the inside + z-range tests (COUNT builds only)
 	sKey[tid] = kEmptyKey;
 	const uint32_t n = A.tileCount[bin];
 	const uint32_t* list = A.binIds + A.tileOffset[bin];
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 						{
 							const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
 							atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
+							if (COUNT) ++nFrags;
 						}
 					}
 			}
@@ -257,11 +259,20 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 			{
 				const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | sPrim[slot];
 				best = min(best, key);
+				if (COUNT) ++nFrags;
 			}
 		}
 		__syncthreads();
 	}
 	best = min(best, sKey[tid]);
+	if (COUNT)
+	{
+		const int total = __syncthreads_count(0) + 0;   // barrier
+		(void)total;
+		unsigned int v = nFrags;
+		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+		if ((tid & 31) == 0 && v) atomicAdd(&A.frameInfo[4], (unsigned long long)v);
+	}
 	if (!live) return;
 
 	// ---- deferred shade of the winner (PS_Kernel, CUDARenderer.cu:833-897) + ROP write-back

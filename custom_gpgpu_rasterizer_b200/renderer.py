@@ -210,10 +210,16 @@ class Renderer:
         self._check(lib.b2r_get_stage_ms(self._ctx, out, _lib.NUM_STAGES))
         return dict(zip(_lib.STAGE_NAMES, [float(x) for x in out]))
 
+    def stage_ms_mean(self, reset: bool = True):
+        out = (C.c_float * _lib.NUM_STAGES)()
+        frames = C.c_uint64(0)
+        self._check(lib.b2r_get_stage_ms_mean(self._ctx, out, _lib.NUM_STAGES, C.byref(frames), int(reset)))
+        return dict(zip(_lib.STAGE_NAMES, [float(x) for x in out])), frames.value
+
     def counters(self) -> Dict[str, int]:
-        out = (C.c_uint64 * 6)()
-        self._check(lib.b2r_get_counters(self._ctx, out, 6))
-        keys = ("pairs", "kernels_launched", "tiles_owned", "num_bins", "unsorted_tiles", "big_triangles")
+        out = (C.c_uint64 * 7)()
+        self._check(lib.b2r_get_counters(self._ctx, out, 7))
+        keys = ("pairs", "kernels_launched", "tiles_owned", "num_bins", "unsorted_tiles", "big_triangles", "fragments")
         return dict(zip(keys, [int(x) for x in out]))
 
     def set_stream(self, stream_ptr: int):

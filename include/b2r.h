@@ -60,7 +60,10 @@ enum
 	/* record cudaEvents between stages so b2r_get_stage_ms works. Default 0. */
 	B2R_OPT_STAGE_TIMERS = 5,
 	/* sort every tile list by primitive id after the scatter (deterministic lists). Default 1. */
-	B2R_OPT_SORT_BINS = 6
+	B2R_OPT_SORT_BINS = 6,
+	/* count the fragments that pass the inside and z-range tests (the F of the fill/ROP roofline
+	 * contract) into counter [6]; an instrumented variant of the raster kernel. Default 0. */
+	B2R_OPT_COUNT_FRAGMENTS = 7
 };
 
 /* stage indices for b2r_get_stage_ms */
@@ -141,10 +144,14 @@ int b2r_read_bins(b2r_context* ctx, uint32_t* counts, uint32_t* offsets, uint32_
 
 /* CUDARenderer::GetTotalNumTriangles / GetTotalNumVisibleTriangles (CUDARenderer.h:63-64) */
 int b2r_get_stats(b2r_context* ctx, uint32_t* total_tris, uint32_t* visible_tris);
-/* device time of each stage of the last frame (replaces the BENCHMARK macro, CUDARenderer.cu:223-353) */
+/* device time of each stage of the last frame rendered with B2R_OPT_STAGE_TIMERS
+ * (replaces the BENCHMARK macro, CUDARenderer.cu:223-353) */
 int b2r_get_stage_ms(b2r_context* ctx, float* out_ms, int n);
+/* mean stage times over all timed frames since the last reset; *frames = how many */
+int b2r_get_stage_ms_mean(b2r_context* ctx, float* out_ms, int n, uint64_t* frames, int reset);
 /* counters of the last frame: [0] (triangle,bin) pairs, [1] kernels launched by b2r_render,
- * [2] tiles rasterised by this context, [3] number of bins */
+ * [2] tiles rasterised by this context, [3] number of bins, [4] tile lists left unsorted (longer
+ * than the sorter handles), [5] triangles binned cooperatively, [6] fragments (B2R_OPT_COUNT_FRAGMENTS) */
 int b2r_get_counters(b2r_context* ctx, uint64_t* out, int n);
 
 /* interop for harnesses that own device memory / streams (PyTorch, NCCL):

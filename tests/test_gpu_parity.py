@@ -44,7 +44,7 @@ def _compare(scene, fill_rule):
         counts, offsets, ids = r.bin_lists()
         assert np.array_equal(counts, o["bin_counts"]), "bin counts differ"
         assert np.array_equal(offsets, np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32))
-        mine = parity.bin_sets(counts, ids) if hasattr(parity, "bin_sets") else oracle_lib.bin_sets(counts, ids)
+        mine = oracle_lib.bin_sets(counts, ids)
         ref = oracle_lib.bin_sets(o["bin_counts"], o["bin_ids"])
         for b, (a, c) in enumerate(zip(mine, ref)):
             assert np.array_equal(a, c), f"bin {b}: triangle set differs"
@@ -162,14 +162,17 @@ def test_frame_is_deterministic_and_repeatable():
 
 
 def test_list_capacity_regrow():
-    """More (triangle, tile) pairs than the initial list capacity: the frame is re-run transparently."""
-    sc = scenes.fill_quads_scene(1920, 1088, layers=300, tex_size=256, sample=0)   # 600 tris x 8160 tiles = 4.9 M pairs
+    """More (triangle, tile) pairs than the initial list capacity (4 Mi entries): the frame is re-run transparently."""
+    sc = scenes.fill_quads_scene(3840, 2160, layers=80, tex_size=256, sample=0)   # 160 tris x 32 400 tiles = 5.2 M pairs
     r, _ = _render_product(sc, debug=False)
     try:
         c = r.counters()
-        assert c["pairs"] == 600 * 8160 - 0 or c["pairs"] > (1 << 22)
+        assert c["pairs"] == 160 * 32400 and c["pairs"] > (1 << 22)
+        assert c["big_triangles"] == 160
         fb = r.framebuffer()
         assert (fb != 0x003F3F3F).all()
+        counts, _, ids = r.bin_lists()
+        assert np.all(counts == 160) and ids.size == c["pairs"]
     finally:
         r.close()
 
