@@ -95,3 +95,7 @@ class B2RError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"b2r error {code}: {message}")
         self.code = code
+
+# test hook: hoisted division of the raster kernel vs __fdiv_rn
+lib.b2r_selftest_division.restype = _i32
+lib.b2r_selftest_division.argtypes = [_i32, _u64, _u32, _u64p]

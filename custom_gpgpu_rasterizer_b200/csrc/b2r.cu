@@ -106,7 +106,7 @@ struct b2r_context
 	DeviceVec<TexDesc> dTexDesc;
 
 	// binning
-	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dBigList, dBinIds;
+	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dBigList, dBinIds;
 	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
 	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };
@@ -194,6 +194,9 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 	CU(c, c->dTileOffset.reserve(n, c->stream));
 	CU(c, c->dTileCursor.reserve(n, c->stream));
 	CU(c, c->dLongTiles.reserve(n, c->stream));
+	CU(c, c->dMidTiles.reserve(n, c->stream));
+	// tile_scan_kernel reads the counts with 16-byte loads
+	CU(c, c->dTileCount.reserve((size_t)n + 4, c->stream));
 	return B2R_OK;
 }
 
@@ -206,8 +209,10 @@ int rebuildScene(b2r_context* c)
 	for (size_t m = 0; m < c->meshes.size(); ++m)
 	{
 		const HostMesh& hm = c->meshes[m];
-		for (uint32_t f = 0; f < hm.nVertices; f += kChunk) vs.push_back(Chunk{ (uint32_t)m, f });
-		for (uint32_t f = 0; f < hm.nTris; f += kChunk) tri.push_back(Chunk{ (uint32_t)m, f });
+		for (uint32_t f = 0; f < hm.nVertices; f += kChunk)
+			vs.push_back(Chunk{ (uint32_t)m, std::min<uint32_t>(kChunk, hm.nVertices - f), hm.vtxInBase + f, hm.vtxOutBase + f, 0u, 0u });
+		for (uint32_t f = 0; f < hm.nTris; f += kChunk)
+			tri.push_back(Chunk{ (uint32_t)m, std::min<uint32_t>(kChunk, hm.nTris - f), hm.idxBase + 3u * f, hm.vtxOutBase, hm.primBase + f, 0u });
 	}
 	c->nVsChunks = (uint32_t)vs.size(); c->nTriChunks = (uint32_t)tri.size();
 	CU(c, c->dVsChunks.reserve(std::max<size_t>(vs.size(), 1), c->stream));
@@ -329,7 +334,7 @@ int enqueueFrame(b2r_context* c)
 	if (!c->meshes.empty())
 		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, slot.hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
 	CU(c, cudaMemsetAsync(c->dTileCount.ptr, 0, tiles * 4, s));
-	CU(c, cudaMemsetAsync(c->dCounters, 0, 8, s));
+	CU(c, cudaMemsetAsync(c->dCounters, 0, kCounterWords * 4, s));
 	CU(c, cudaMemsetAsync(c->dFrameInfo, 0, kInfoWords * 8, s));
 
 	if (c->nVsChunks)
@@ -340,14 +345,14 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 1);
 	if (c->nTriChunks)
 	{
-		triangle_setup_kernel<<<c->nTriChunks, kChunk, 0, s>>>(c->dTriChunks.ptr, c->dMeshConst.ptr, c->dIndices.ptr, c->dPos4.ptr,
+		triangle_setup_kernel<<<c->nTriChunks, kChunk, 0, s>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dPos4.ptr,
 			c->dRecords.ptr, c->dAux.ptr, c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, fp);
-		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, fp);
+		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, c->dFrameInfo, fp);
 		c->kernelsLaunched += 2;
 	}
 	STAGE_EVENT(c, slot, 2);
 	tile_scan_kernel<<<1, 1024, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dTileCursor.ptr, tiles,
-		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortSmall, c->dLongTiles.ptr, c->dFrameInfo);
+		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortWarp, (uint32_t)kSortSmall, c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
 	++c->kernelsLaunched;
 	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
@@ -355,16 +360,17 @@ int enqueueFrame(b2r_context* c)
 		bin_scatter_kernel<<<(uint32_t)((c->nPrims + 255) / 256), 256, 0, s>>>(c->dRects.ptr, (uint32_t)c->nPrims, c->dTileOffset.ptr,
 			c->dTileCursor.ptr, c->dBinIds.ptr, c->dFrameInfo, fp);
 		bin_big_kernel<true><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, nullptr, c->dTileOffset.ptr,
-			c->dTileCursor.ptr, c->dBinIds.ptr, fp);
+			c->dTileCursor.ptr, c->dBinIds.ptr, c->dFrameInfo, fp);
 		c->kernelsLaunched += 2;
 	}
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		bin_sort_kernel<<<tiles, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
+		bin_sort_warp_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, tiles, c->dFrameInfo);
+		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
 		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLarge * sizeof(uint32_t), s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,
 			c->dBinIds.ptr, c->dFrameInfo);
-		c->kernelsLaunched += 2;
+		c->kernelsLaunched += 3;
 	}
 	STAGE_EVENT(c, slot, 5);
 	{
@@ -424,8 +430,50 @@ int validateFrame(b2r_context* c)
 
 }
 
+// ---- self test: the hoisted division of raster_kernel.cuh against __fdiv_rn ------------------
+__device__ __forceinline__ uint32_t hash32(uint32_t x)
+{
+	x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+	return x;
+}
+__global__ void division_selftest_kernel(unsigned long long nPairs, uint32_t seed, unsigned long long* mismatches)
+{
+	unsigned long long bad = 0;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nPairs; i += (unsigned long long)gridDim.x * blockDim.x)
+	{
+		const uint32_t h0 = hash32((uint32_t)i ^ seed), h1 = hash32(h0 + (uint32_t)(i >> 32) + 0x9E3779B9u), h2 = hash32(h1 ^ 0x85EBCA6Bu);
+		// divisor: any normal float with exponent in [-95, 95]
+		const uint32_t eb = 127u - 95u + (h0 % 191u);
+		const float b = __uint_as_float((eb << 23) | (h1 & 0x7FFFFFu));
+		// dividend: in one third of the cases b*u with u in (0, 1.0001] (edge function inside a triangle), otherwise any float >= 2^-95
+		float a;
+		if ((h2 & 3u) == 0u) a = b * (1.0001f * (float)((h2 >> 8) + 1u) * (1.f / 16777216.f));
+		else if ((h2 & 3u) == 1u) a = b * __uint_as_float(((127u - (h2 >> 8) % 64u) << 23) | (h0 & 0x7FFFFFu));
+		else a = __uint_as_float(((127u - 95u + (h2 >> 8) % 191u) << 23) | (h2 & 0x7FFFFFu));
+		if (!(a >= kDivLo) || !(b >= kDivLo && b <= kDivHi)) continue;
+		const float q = divByArea(a, b, refinedReciprocal(b));
+		if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+
 // =======================================================================================
 extern "C" {
+
+// test hook (not part of include/b2r.h): bit-compares the raster kernel's hoisted division with
+// __fdiv_rn on nPairs pseudo-random operand pairs; returns the number of mismatches
+int b2r_selftest_division(int device, unsigned long long nPairs, uint32_t seed, unsigned long long* mismatches)
+{
+	if (!mismatches) return B2R_E_INVALID;
+	if (cudaSetDevice(device) != cudaSuccess) return B2R_E_NO_DEVICE;
+	unsigned long long* d = nullptr;
+	if (cudaMalloc((void**)&d, 8) != cudaSuccess) return B2R_E_CUDA;
+	cudaMemset(d, 0, 8);
+	division_selftest_kernel<<<148 * 8, 256>>>(nPairs, seed, d);
+	cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return e == cudaSuccess ? B2R_OK : B2R_E_CUDA;
+}
 
 const char* b2r_last_error(const b2r_context* ctx)
 {
@@ -458,7 +506,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 		CUC(cudaMallocHost((void**)&slot.hInfo, sizeof(b2r_context::HostInfo)));
 		memset(slot.hInfo, 0, sizeof(b2r_context::HostInfo));
 	}
-	CUC(cudaMalloc((void**)&c->dCounters, 8));
+	CUC(cudaMalloc((void**)&c->dCounters, kCounterWords * 4));
 	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8));
 	CUC(cudaMemset(c->dFrameInfo, 0, kInfoWords * 8));
 	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortLarge * sizeof(uint32_t))));
@@ -480,7 +528,7 @@ void b2r_destroy(b2r_context* c)
 	c->dIVertex.release(); c->dIndices.release(); c->dPos4.release(); c->dAttr.release();
 	c->dRecords.release(); c->dAux.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
 	c->dMeshConst.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
-	c->dTileCursor.release(); c->dLongTiles.release(); c->dBigList.release(); c->dBinIds.release();
+	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dCounters); cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
 	for (auto& slot : c->slots)

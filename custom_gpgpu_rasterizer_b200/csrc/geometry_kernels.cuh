@@ -47,10 +47,10 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	__shared__ float sMat[41];
 	const Chunk ch = chunks[blockIdx.x];
 	const MeshConst& mc = meshes[ch.mesh];
-	const uint32_t n = min((uint32_t)kChunk, mc.nVertices - ch.first);
-	const float2* src = ivertex + (size_t)(mc.vtxInBase + ch.first) * 7;
+	const uint32_t n = ch.count;
+	const float2* src = ivertex + (size_t)ch.inStart * 7;
 	for (uint32_t i = threadIdx.x; i < n * 7; i += kChunk)
-		sIn[i] = __ldg(src + i);
+		sIn[i] = __ldcs(src + i);                  // read once: streaming
 	if (threadIdx.x < 16) sMat[threadIdx.x] = mc.wvp[threadIdx.x];
 	else if (threadIdx.x < 32) sMat[threadIdx.x] = mc.world[threadIdx.x - 16];
 	else if (threadIdx.x < 41) sMat[threadIdx.x] = mc.rot[threadIdx.x - 32];
@@ -79,13 +79,13 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	float vz = mulRow4(world, 2, px, py, pz) - fp.camPos[2];
 	normalize3(vx, vy, vz);
 
-	const size_t o = (size_t)mc.vtxOutBase + ch.first + threadIdx.x;
-	pos4[o] = p;
-	float4* a = attr + o * 4;
-	a[0] = make_float4(v[3], v[4], nx, ny);
-	a[1] = make_float4(nz, tx, ty, tz);
-	a[2] = make_float4(vx, vy, vz, v[11]);
-	a[3] = make_float4(v[12], v[13], 0.f, 0.f);
+	const size_t o = (size_t)ch.outStart + threadIdx.x;
+	pos4[o] = p;                                   // re-read by triangle setup: normal L2 policy
+	float4* a = attr + o * 4;                      // only the winners' attributes are read back: streaming stores
+	__stcs(a + 0, make_float4(v[3], v[4], nx, ny));
+	__stcs(a + 1, make_float4(nz, tx, ty, tz));
+	__stcs(a + 2, make_float4(vx, vy, vz, v[11]));
+	__stcs(a + 3, make_float4(v[12], v[13], 0.f, 0.f));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -104,27 +104,54 @@ __device__ __forceinline__ bool tileOwned(const FrameParams& fp, uint32_t tile)
 	return fp.ownerCount <= 1 || (tile % fp.ownerCount) == fp.ownerRank;
 }
 
+
+// Warp-aggregated per-tile counter update: the lanes of a warp that address the same tile in the
+// same step are combined into ONE atomic (consecutive triangles of a mesh usually land in the
+// same few tiles).  Every lane of the warp must call this the same number of times (`steps` =
+// warp-wide maximum of nTiles); lanes with k >= nTiles pass tile = kNoTile.
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+// counters[]: [0] visible triangles (summed by tile_scan_kernel), [1] big triangles,
+// [kVisBase + 32*s] partial visible counts, one 128-byte line per slot
+constexpr uint32_t kVisSlots = 64, kVisBase = 32, kCounterWords = kVisBase + kVisSlots * 32;
+template <bool RETURN>
+__device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t tile)
+{
+	const unsigned peers = __match_any_sync(0xFFFFFFFFu, tile);
+	const int leader = __ffs(peers) - 1;
+	const unsigned lane = threadIdx.x & 31u;
+	uint32_t base = 0;
+	if (tile != kNoTile && (int)lane == leader)
+	{
+		if (RETURN) base = atomicAdd(&counters[tile], (uint32_t)__popc(peers));
+		else atomicAdd(&counters[tile], (uint32_t)__popc(peers));
+	}
+	if (RETURN)
+	{
+		base = __shfl_sync(0xFFFFFFFFu, base, leader);
+		return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+	}
+	return 0;
+}
+
 // triangle setup: one CTA per chunk of 256 triangles of one mesh.
 // cull (CUDARenderer.cu:760-777), frustum reject (CUDAROPs.cu:147-178), screen mapping (:88-97),
 // inflated bbox (:180-200), bin rectangle (CUDARenderer.cu:935-942), per-tile counts.
 __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
-	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
+	const Chunk* __restrict__ chunks,
 	const uint32_t* __restrict__ indices, const float4* __restrict__ pos4,
 	TriRecord* __restrict__ records, TriAux* __restrict__ aux, uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig*/,
 	FrameParams fp)
 {
 	const Chunk ch = chunks[blockIdx.x];
-	const MeshConst& mc = meshes[ch.mesh];
-	const uint32_t local = ch.first + threadIdx.x;
 	bool visible = false;
 	uint32_t prim = 0;
 	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
-	if (local < mc.nTris)
+	if (threadIdx.x < ch.count)
 	{
-		prim = mc.primBase + local;
-		const uint32_t* ip = indices + (size_t)mc.idxBase + (size_t)local * 3;
-		const uint32_t i0 = mc.vtxOutBase + __ldg(ip), i1 = mc.vtxOutBase + __ldg(ip + 1), i2 = mc.vtxOutBase + __ldg(ip + 2);
+		prim = ch.primStart + threadIdx.x;
+		const uint32_t* ip = indices + (size_t)ch.inStart + (size_t)threadIdx.x * 3;
+		const uint32_t i0 = ch.outStart + __ldg(ip), i1 = ch.outStart + __ldg(ip + 1), i2 = ch.outStart + __ldg(ip + 2);
 		const float4 p0 = __ldg(pos4 + i0), p1 = __ldg(pos4 + i1), p2 = __ldg(pos4 + i2);
 		visible = true;
 		if (fp.cullMode != 2u)
@@ -174,26 +201,36 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 		rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16))
 		                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
 	}
-	// statistics: one atomic per CTA
-	const int nVis = __syncthreads_count(visible);
-	if (threadIdx.x == 0 && nVis) atomicAdd(&counters[0], (uint32_t)nVis);
+	// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+	{
+		const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
+		if ((threadIdx.x & 31) == 0 && vis)
+			atomicAdd(&counters[kVisBase + ((blockIdx.x * 8 + (threadIdx.x >> 5)) % kVisSlots) * 32], (uint32_t)__popc(vis));
+	}
 
+	// per-tile counts, warp-aggregated
+	uint32_t nTiles = 0;
+	int w = 1;
 	if (visible && bx0 <= bx1 && by0 <= by1)
 	{
-		const uint32_t nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
+		w = bx1 - bx0 + 1;
+		nTiles = (uint32_t)w * (uint32_t)(by1 - by0 + 1);
 		if (nTiles > fp.bigRectTiles)
 		{
 			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively by bin_big_kernel
+			nTiles = 0;
 		}
-		else
+	}
+	const uint32_t steps = __reduce_max_sync(0xFFFFFFFFu, nTiles);
+	for (uint32_t k = 0; k < steps; ++k)
+	{
+		uint32_t tile = kNoTile;
+		if (k < nTiles)
 		{
-			for (int ty = by0; ty <= by1; ++ty)
-				for (int tx = bx0; tx <= bx1; ++tx)
-				{
-					const uint32_t tile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
-					if (tileOwned(fp, tile)) atomicAdd(&tileCount[tile], 1u);
-				}
+			tile = (uint32_t)(bx0 + (int)(k % (uint32_t)w)) + (uint32_t)(by0 + (int)(k / (uint32_t)w)) * fp.binsX;
+			if (!tileOwned(fp, tile)) tile = kNoTile;
 		}
+		warpTileAdd<false>(tileCount, tile);
 	}
 }
 
@@ -203,8 +240,9 @@ template <bool SCATTER>
 __global__ void __launch_bounds__(256) bin_big_kernel(
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, const uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t* __restrict__ binIds, FrameParams fp)
+	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo, FrameParams fp)
 {
+	if (SCATTER && frameInfo[1]) return;   // list capacity overflow: the host regrows and re-runs the frame
 	const uint32_t nBig = counters[1];
 	for (uint32_t b = blockIdx.x; b < nBig; b += gridDim.x)
 	{
@@ -225,23 +263,49 @@ __global__ void __launch_bounds__(256) bin_big_kernel(
 }
 
 // exclusive scan of the per-tile counts (single CTA; the tile grid is at most a few 100k entries).
-// Also clears the cursors and publishes the pair total / overflow flag.
+// Every thread owns 32 consecutive tiles (one 128-byte line), so a 4K frame (32 400 tiles) is one
+// pass.  Also clears the cursors, publishes the pair total / overflow flag and builds the two
+// work lists of the list sorter (tiles whose list is too long for the warp-level sort).
+constexpr uint32_t kScanPerThread = 32;
 __global__ void __launch_bounds__(1024) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold, uint32_t* __restrict__ longTiles,
-	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles*/)
+	uint32_t nTiles, unsigned long long capacity, uint32_t midThreshold, uint32_t longThreshold,
+	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
+	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles*/)
 {
+	if (threadIdx.x < 32)
+	{
+		uint32_t v = counters[kVisBase + threadIdx.x * 32] + counters[kVisBase + (threadIdx.x + 32) * 32];
+		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+		if (threadIdx.x == 0) counters[0] = v;
+	}
 	__shared__ unsigned long long sWarp[32];
 	__shared__ unsigned long long sCarry;
-	__shared__ uint32_t sLong;
-	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; }
+	__shared__ uint32_t sLong, sMid;
+	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; sMid = 0; }
 	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (uint32_t base = 0; base < nTiles; base += 1024)
+	for (uint32_t base = 0; base < nTiles; base += 1024 * kScanPerThread)
 	{
-		const uint32_t i = base + threadIdx.x;
-		const unsigned long long v = (i < nTiles) ? tileCount[i] : 0ull;
-		unsigned long long incl = v;
+		const uint32_t first = base + threadIdx.x * kScanPerThread;
+		uint32_t v[kScanPerThread];
+		unsigned long long sum = 0;
+		#pragma unroll
+		for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
+		{
+			uint4 t = make_uint4(0, 0, 0, 0);
+			const uint32_t i = first + q * 4;
+			if (i + 3 < nTiles) t = *reinterpret_cast<const uint4*>(tileCount + i);
+			else
+			{
+				if (i < nTiles) t.x = tileCount[i];
+				if (i + 1 < nTiles) t.y = tileCount[i + 1];
+				if (i + 2 < nTiles) t.z = tileCount[i + 2];
+			}
+			v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+			sum += (unsigned long long)t.x + t.y + t.z + t.w;
+		}
+		unsigned long long incl = sum;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1)
 		{
@@ -263,12 +327,19 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 		}
 		__syncthreads();
 		const unsigned long long carry = sCarry;
-		const unsigned long long excl = carry + (warp ? sWarp[warp - 1] : 0ull) + incl - v;
-		if (i < nTiles)
+		unsigned long long run = carry + (warp ? sWarp[warp - 1] : 0ull) + incl - sum;
+		#pragma unroll
+		for (uint32_t q = 0; q < kScanPerThread; ++q)
 		{
-			tileOffset[i] = (uint32_t)excl;
-			tileCursor[i] = 0u;
-			if (v > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i;
+			const uint32_t i = first + q;
+			if (i < nTiles)
+			{
+				tileOffset[i] = (uint32_t)run;
+				tileCursor[i] = 0u;
+				if (v[q] > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i;
+				else if (v[q] > midThreshold) midTiles[atomicAdd(&sMid, 1u)] = i;
+			}
+			run += v[q];
 		}
 		__syncthreads();
 		if (threadIdx.x == 1023) sCarry = carry + sWarp[31];
@@ -280,10 +351,12 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 		frameInfo[1] = (sCarry > capacity) ? 1ull : 0ull;
 		frameInfo[2] = 0ull;
 		frameInfo[3] = sLong;
+		frameInfo[5] = sMid;
 	}
 }
 
-// scatter of the small rectangles: one thread per primitive, re-reading the 8 B rectangle.
+// scatter of the small rectangles: one thread per primitive, re-reading the 8 B rectangle; the
+// slot inside the tile's list comes from a warp-aggregated atomic on the tile cursor.
 __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	const uint2* __restrict__ rects, uint32_t nPrims, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ binIds,
@@ -291,33 +364,114 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 {
 	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
 	const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
-	if (prim >= nPrims) return;
-	const uint2 rc = rects[prim];
-	const int bx0 = rc.x & 0xFFFF, bx1 = rc.x >> 16, by0 = rc.y & 0xFFFF, by1 = rc.y >> 16;
-	if (bx0 > bx1 || by0 > by1) return;
-	if ((uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1) > fp.bigRectTiles) return;
-	for (int ty = by0; ty <= by1; ++ty)
-		for (int tx = bx0; tx <= bx1; ++tx)
+	uint32_t nTiles = 0;
+	int bx0 = 0, by0 = 0, w = 1;
+	if (prim < nPrims)
+	{
+		const uint2 rc = __ldg(rects + prim);
+		bx0 = rc.x & 0xFFFF; by0 = rc.y & 0xFFFF;
+		const int bx1 = rc.x >> 16, by1 = rc.y >> 16;
+		if (bx0 <= bx1 && by0 <= by1)
 		{
-			const uint32_t tile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
-			if (tileOwned(fp, tile))
-				binIds[tileOffset[tile] + atomicAdd(&tileCursor[tile], 1u)] = prim;
+			w = bx1 - bx0 + 1;
+			nTiles = (uint32_t)w * (uint32_t)(by1 - by0 + 1);
+			if (nTiles > fp.bigRectTiles) nTiles = 0;   // bin_big_kernel
 		}
+	}
+	const uint32_t steps = __reduce_max_sync(0xFFFFFFFFu, nTiles);
+	for (uint32_t k = 0; k < steps; ++k)
+	{
+		uint32_t tile = kNoTile;
+		if (k < nTiles)
+		{
+			tile = (uint32_t)(bx0 + (int)(k % (uint32_t)w)) + (uint32_t)(by0 + (int)(k / (uint32_t)w)) * fp.binsX;
+			if (!tileOwned(fp, tile)) tile = kNoTile;
+		}
+		const uint32_t slot = warpTileAdd<true>(tileCursor, tile);
+		if (tile != kNoTile) binIds[__ldg(tileOffset + tile) + slot] = prim;
+	}
 }
 
 // per-tile sort of the id lists (ascending primitive id = submission order): makes the lists
 // bit-reproducible regardless of the order the scatter atomics were served.
-//  tier 1: every tile, lists up to kSortSmall entries, static shared memory
-//  tier 2: the tiles tile_scan_kernel put on the long-list worklist, up to kSortLarge entries
-//          in dynamic shared memory (one CTA per SM)
+//  tier 1: one WARP per tile, lists up to 256 entries: bitonic network on 8 keys per lane in
+//          registers, cross-lane steps with shuffles, no shared memory, no block barrier
+//  tier 2: the tiles tile_scan_kernel put on the "mid" work list (257 .. kSortSmall entries), one
+//          CTA per tile, keys in static shared memory
+//  tier 3: the "long" work list (up to kSortLarge entries) in dynamic shared memory, one CTA per SM
 //  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
+constexpr int kSortWarp = 256;
 constexpr int kSortSmall = 4096;
 constexpr int kSortLarge = 49152;
 
+__global__ void __launch_bounds__(256) bin_sort_warp_kernel(
+	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
+	uint32_t nTiles, const unsigned long long* __restrict__ frameInfo)
+{
+	if (frameInfo[1]) return;
+	const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+	if (tile >= nTiles) return;
+	const uint32_t n = tileCount[tile];
+	if (n < 2 || n > (uint32_t)kSortWarp) return;
+	const uint32_t lane = threadIdx.x & 31;
+	uint32_t* list = binIds + tileOffset[tile];
+	// virtual element index v = i*32 + lane (coalesced); padding keys sort to the end
+	uint32_t a[8];
+	#pragma unroll
+	for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; a[i] = (v < n) ? list[v] : 0xFFFFFFFFu; }
+	// already sorted? (v, v+1) neighbours: lane+1 of the same i, or lane 0 of i+1
+	bool unsorted = false;
+	#pragma unroll
+	for (int i = 0; i < 8; ++i)
+	{
+		uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, a[i], 1);
+		const uint32_t wrap = __shfl_sync(0xFFFFFFFFu, (i < 7) ? a[(i + 1) & 7] : 0xFFFFFFFFu, 0);
+		if (lane == 31) nxt = wrap;
+		unsorted |= a[i] > nxt;
+	}
+	if (!__any_sync(0xFFFFFFFFu, unsorted)) return;
+	#pragma unroll
+	for (uint32_t k = 2; k <= 256; k <<= 1)
+	{
+		#pragma unroll
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			if (j >= 32)
+			{
+				const int ji = j >> 5;
+				#pragma unroll
+				for (int i = 0; i < 8; ++i)
+				{
+					const int p = i ^ ji;
+					if (p > i)
+					{
+						const bool up = (((uint32_t)i * 32u) & k) == 0;     // k >= 64 here: direction depends on i only
+						const uint32_t x = a[i], y = a[p];
+						if ((x > y) == up) { a[i] = y; a[p] = x; }
+					}
+				}
+			}
+			else
+			{
+				#pragma unroll
+				for (int i = 0; i < 8; ++i)
+				{
+					const uint32_t v = (uint32_t)i * 32u + lane;
+					const bool up = (v & k) == 0;
+					const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, a[i], j);
+					const bool lower = (lane & j) == 0;
+					a[i] = (lower == up) ? min(a[i], y) : max(a[i], y);
+				}
+			}
+		}
+	}
+	#pragma unroll
+	for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; if (v < n) list[v] = a[i]; }
+}
+
 __device__ __forceinline__ void sortTileList(uint32_t* __restrict__ list, uint32_t n, uint32_t* sKeys)
 {
-	// already sorted? (common: consecutive primitives of one CTA land in order)
 	int unsorted = 0;
 	for (uint32_t i = threadIdx.x; i + 1 < n; i += blockDim.x)
 		unsorted |= (list[i] > list[i + 1]);
@@ -343,15 +497,19 @@ __device__ __forceinline__ void sortTileList(uint32_t* __restrict__ list, uint32
 	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) list[i] = sKeys[i];
 }
 
-__global__ void __launch_bounds__(256) bin_sort_kernel(
-	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
-	const unsigned long long* __restrict__ frameInfo)
+__global__ void __launch_bounds__(256) bin_sort_mid_kernel(
+	const uint32_t* __restrict__ midTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
+	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
 {
 	__shared__ uint32_t sKeys[kSortSmall];
 	if (frameInfo[1]) return;
-	const uint32_t n = tileCount[blockIdx.x];
-	if (n < 2 || n > (uint32_t)kSortSmall) return;
-	sortTileList(binIds + tileOffset[blockIdx.x], n, sKeys);
+	const uint32_t nMid = (uint32_t)frameInfo[5];
+	for (uint32_t w = blockIdx.x; w < nMid; w += gridDim.x)
+	{
+		const uint32_t tile = midTiles[w];
+		sortTileList(binIds + tileOffset[tile], tileCount[tile], sKeys);
+		__syncthreads();
+	}
 }
 
 __global__ void __launch_bounds__(1024) bin_sort_long_kernel(

@@ -41,13 +41,38 @@ struct __align__(16) TriShared
 {
 	float x0, y0, x1, y1;
 	float x2, y2, z0, z1;
-	float z2, area, eAx, eAy;     // eA = v1 - v0
+	float z2, rcpArea, eAx, eAy;  // eA = v1 - v0; rcpArea = refined reciprocal of |area| (see divByArea)
 	float eBx, eBy, eCx, eCy;     // eB = v2 - v1, eC = v0 - v2
+	float area;                   // |Cross(v0-v1, v0-v2)|, CUDAROPs.cu:336
+	uint32_t prim;
+	int zLow;                     // conservative lower bound of any fragment's integer depth
+	uint32_t fastDiv;             // 1 when |area| is in the range where the hoisted division is exact
 };
 
 struct Bary { float b0, b1, b2, z; };
 
 __device__ __forceinline__ bool topLeftEdge(float ex, float ey) { return ey > 0.f || (ey == 0.f && ex < 0.f); }
+
+// IEEE division w / area with the reciprocal hoisted out of the pixel loop.
+// div.rn.f32 on sm_100a is: r = MUFU.RCP(b); r' = fma(r, fma(-b, r, 1), r); q = fma(a, r', 0);
+// q' = fma(r', fma(-b, q, a), q), plus an FCHK range test that diverts zero / denormal / huge
+// operands to a slow path.  r' depends on the divisor only, so it is computed once per triangle;
+// the quotient sequence below is then instruction-for-instruction the fast path of div.rn.
+// Operands outside a conservative exponent window take __fdiv_rn (tests/test_gpu_units.py checks
+// bit-equality against __fdiv_rn on 2^32 random operand pairs).
+__device__ __forceinline__ float refinedReciprocal(float b)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+	return fmaf(r, fmaf(-b, r, 1.f), r);
+}
+__device__ __forceinline__ float divByArea(float a, float area, float rcp)
+{
+	const float q = fmaf(a, rcp, 0.f);
+	return fmaf(rcp, fmaf(-area, q, a), q);
+}
+constexpr float kDivLo = 2.5243549e-29f;   // 2^-95
+constexpr float kDivHi = 3.9614081e+28f;   // 2^95
 
 // IsPixelInTriangle + weights + depth of RasterizePixelAtomic (CUDAROPs.cu:128-145, 333-345, 386).
 // Returns false if the fragment is not produced.  zi = cvt.rzi.s32.f32(z * 2^31).
@@ -58,13 +83,22 @@ __device__ __forceinline__ bool fragmentTest(const TriShared& t, float fx, float
 	const float w0 = diff2(fx - t.x1, t.eBy, fy - t.y1, t.eBx);
 	const float w1 = diff2(fx - t.x2, t.eCy, fy - t.y2, t.eCx);
 	if (!(w0 >= 0.f && w1 >= 0.f && w2 >= 0.f)) return false;
-	if (TOPLEFT)
+	const float wMin = fminf(fminf(w0, w1), w2);
+	if (t.fastDiv && wMin >= kDivLo)
 	{
-		if ((w2 == 0.f && !topLeftEdge(t.eAx, t.eAy)) || (w0 == 0.f && !topLeftEdge(t.eBx, t.eBy)) ||
-			(w1 == 0.f && !topLeftEdge(t.eCx, t.eCy)))
-			return false;
+		out.b0 = divByArea(w0, t.area, t.rcpArea); out.b1 = divByArea(w1, t.area, t.rcpArea); out.b2 = divByArea(w2, t.area, t.rcpArea);
 	}
-	out.b0 = __fdiv_rn(w0, t.area); out.b1 = __fdiv_rn(w1, t.area); out.b2 = __fdiv_rn(w2, t.area);
+	else
+	{
+		// exact-edge fragments (some weight is 0) and degenerate operands: rare, fully general path
+		if (TOPLEFT)
+		{
+			if ((w2 == 0.f && !topLeftEdge(t.eAx, t.eAy)) || (w0 == 0.f && !topLeftEdge(t.eBx, t.eBy)) ||
+				(w1 == 0.f && !topLeftEdge(t.eCx, t.eCy)))
+				return false;
+		}
+		out.b0 = __fdiv_rn(w0, t.area); out.b1 = __fdiv_rn(w1, t.area); out.b2 = __fdiv_rn(w2, t.area);
+	}
 	out.z = sum3(out.b0, t.z0, out.b1, t.z1, out.b2, t.z2);
 	if (out.z < 0.f || out.z > 1.f) return false;
 	zi = __float2int_rz(out.z * 2147483648.f);
@@ -72,13 +106,21 @@ __device__ __forceinline__ bool fragmentTest(const TriShared& t, float fx, float
 	return zi != 0x7FFFFFFF;
 }
 
-__device__ __forceinline__ void expandRecord(const TriRecord& r, TriShared& t)
+__device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, TriShared& t)
 {
 	t.x0 = r.x0; t.y0 = r.y0; t.x1 = r.x1; t.y1 = r.y1; t.x2 = r.x2; t.y2 = r.y2;
 	t.z0 = r.z0; t.z1 = r.z1; t.z2 = r.z2; t.area = r.area;
 	t.eAx = r.x1 - r.x0; t.eAy = r.y1 - r.y0;
 	t.eBx = r.x2 - r.x1; t.eBy = r.y2 - r.y1;
 	t.eCx = r.x0 - r.x2; t.eCy = r.y0 - r.y2;
+	t.prim = prim;
+	t.fastDiv = (r.area >= kDivLo && r.area <= kDivHi) ? 1u : 0u;
+	t.rcpArea = refinedReciprocal(r.area);
+	// weights are in [0, 1 + few ulp] and sum to 1 +- few ulp, so z >= min(z_i) - small; anything
+	// non-finite or negative falls back to "no bound"
+	const float zMin = fminf(fminf(r.z0, r.z1), r.z2);
+	const float zb = zMin * 0.999999f - 1e-9f;
+	t.zLow = (zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
 }
 
 // ---- texture sampling (CUDATextureSampler.cuh:80-191) -------------------------------------
@@ -184,12 +226,10 @@ constexpr int kListChunk = 256;       // bin-list entries staged per iteration (
 constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are rasterised by one thread
 
 template <bool TOPLEFT, bool COUNT>
-__global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs A, FrameParams fp)
+__global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
-	__shared__ TriShared sTri[kListChunk];
-	__shared__ uint32_t sPrim[kListChunk];
-	__shared__ uint32_t sBig[kListChunk];
-	__shared__ unsigned long long sKey[kTile * kTile];
+	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
+	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
 	__shared__ uint32_t sNumBig;
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
@@ -204,9 +244,12 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 	const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
 	const bool live = px < ex && py < ey;
 	const float fx = (float)px, fy = (float)py;
+	// rows covered by this warp (two 16-pixel rows): triangles whose bbox misses them are skipped warp-wide
+	const int warpY0 = oy + ((tid >> 5) << 1), warpY1 = warpY0 + 2;
 
-	unsigned long long best = kEmptyKey;
-	uint32_t nFrags = 0;      // fragments that pass the inside + z-range tests (COUNT builds only)
+	int bestZ = 0x7FFFFFFF;          // register copy of this pixel's depth/winner for the pixel-parallel path
+	uint32_t bestPrim = kNoPrim;
+	uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
 	sKey[tid] = kEmptyKey;
 	const uint32_t n = A.tileCount[bin];
 	const uint32_t* list = A.binIds + A.tileOffset[bin];
@@ -220,31 +263,37 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 		{
 			const uint32_t prim = __ldg(list + base + tid);
 			const TriRecord r = A.records[prim];
-			TriShared t;
-			expandRecord(r, t);
-			sTri[tid] = t;
-			sPrim[tid] = prim;
 			// candidate pixels = inflated bbox (CUDAROPs.cu:180-200) clipped to this CTA's block;
 			// the bbox is conservative for the edge test, so this equals testing the whole bin
 			const int x0 = max((int)(r.bbX & 0xFFFFu), ox), x1 = min((int)(r.bbX >> 16), ex);
 			const int y0 = max((int)(r.bbY & 0xFFFFu), oy), y1 = min((int)(r.bbY >> 16), ey);
 			const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
-			if (area > kSmallArea)
-				sBig[atomicAdd(&sNumBig, 1u)] = (uint32_t)tid;
-			else if (area > 0)
+			if (area > 0)
 			{
-				// triangle-parallel path: this thread walks the few candidate pixels
-				for (int y = y0; y < y1; ++y)
-					for (int x = x0; x < x1; ++x)
-					{
-						Bary bc; int zi;
-						if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+				TriShared t;
+				expandRecord(r, prim, t);
+				if (area > kSmallArea)
+				{
+					// pixel-parallel: bbox rows are kept in zLow's neighbours for the warp-level reject
+					TriShared& dst = sBig[atomicAdd(&sNumBig, 1u)];
+					dst = t;
+					dst.fastDiv |= ((uint32_t)y0 << 8) | ((uint32_t)y1 << 20);   // y extent (12 bits each) above the flag
+				}
+				else
+				{
+					// triangle-parallel: this thread walks the few candidate pixels
+					for (int y = y0; y < y1; ++y)
+						for (int x = x0; x < x1; ++x)
 						{
-							const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
-							atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
-							if (COUNT) ++nFrags;
+							Bary bc; int zi;
+							if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+							{
+								const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
+								atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
+								if (COUNT) ++nFrags;
+							}
 						}
-					}
+				}
 			}
 		}
 		__syncthreads();
@@ -252,23 +301,24 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 		const uint32_t nBig = sNumBig;
 		for (uint32_t j = 0; j < nBig; ++j)
 		{
-			const uint32_t slot = sBig[j];
-			const TriShared& t = sTri[slot];
+			TriShared t = sBig[j];
+			const int ty0 = (int)((t.fastDiv >> 8) & 0xFFFu), ty1 = (int)(t.fastDiv >> 20);
+			if (ty1 <= warpY0 || ty0 >= warpY1) continue;          // warp-uniform
+			if (!COUNT && t.zLow > bestZ) continue;                // cannot win this pixel (per lane)
+			t.fastDiv &= 1u;
 			Bary bc; int zi;
 			if (live && fragmentTest<TOPLEFT>(t, fx, fy, bc, zi))
 			{
-				const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | sPrim[slot];
-				best = min(best, key);
 				if (COUNT) ++nFrags;
+				if (zi < bestZ || (zi == bestZ && t.prim < bestPrim)) { bestZ = zi; bestPrim = t.prim; }
 			}
 		}
 		__syncthreads();
 	}
+	unsigned long long best = (bestPrim == kNoPrim) ? kEmptyKey : (((unsigned long long)(uint32_t)bestZ << 32) | bestPrim);
 	best = min(best, sKey[tid]);
 	if (COUNT)
 	{
-		const int total = __syncthreads_count(0) + 0;   // barrier
-		(void)total;
 		unsigned int v = nFrags;
 		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
 		if ((tid & 31) == 0 && v) atomicAdd(&A.frameInfo[4], (unsigned long long)v);
@@ -292,7 +342,7 @@ __global__ void __launch_bounds__(kTile * kTile) raster_shade_kernel(RasterArgs 
 		prim = (uint32_t)best;
 		depthOut = (int)(uint32_t)(best >> 32);
 		TriShared t;
-		expandRecord(A.records[prim], t);
+		expandRecord(A.records[prim], prim, t);
 		Bary bc; int zi;
 		fragmentTest<false>(t, fx, fy, bc, zi);      // same arithmetic as the coverage pass
 		zOut = bc.z;
