@@ -368,7 +368,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		bin_sort_warp_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, tiles, c->dFrameInfo);
 		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
-		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLarge * sizeof(uint32_t), s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,
+		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,
 			c->dBinIds.ptr, c->dFrameInfo);
 		c->kernelsLaunched += 3;
 	}
@@ -445,12 +445,13 @@ __global__ void division_selftest_kernel(unsigned long long nPairs, uint32_t see
 		// divisor: any normal float with exponent in [-95, 95]
 		const uint32_t eb = 127u - 95u + (h0 % 191u);
 		const float b = __uint_as_float((eb << 23) | (h1 & 0x7FFFFFu));
-		// dividend: in one third of the cases b*u with u in (0, 1.0001] (edge function inside a triangle), otherwise any float >= 2^-95
+		// dividend: the domain the raster kernel uses the hoisted path on: a in [b*2^-64, 4b], a >= 2^-95
 		float a;
-		if ((h2 & 3u) == 0u) a = b * (1.0001f * (float)((h2 >> 8) + 1u) * (1.f / 16777216.f));
-		else if ((h2 & 3u) == 1u) a = b * __uint_as_float(((127u - (h2 >> 8) % 64u) << 23) | (h0 & 0x7FFFFFu));
-		else a = __uint_as_float(((127u - 95u + (h2 >> 8) % 191u) << 23) | (h2 & 0x7FFFFFu));
-		if (!(a >= kDivLo) || !(b >= kDivLo && b <= kDivHi)) continue;
+		if ((h2 & 3u) == 0u) a = b * (1.0001f * (float)((h2 >> 8) + 1u) * (1.f / 16777216.f));            // u uniform in (0, 1.0001]
+		else if ((h2 & 3u) == 1u) a = b * __uint_as_float(((127u - (h2 >> 8) % 64u) << 23) | (h0 & 0x7FFFFFu));   // u = 2^-k * m, k < 64
+		else if ((h2 & 3u) == 2u) a = b * __uint_as_float(((127u + (h2 >> 8) % 2u) << 23) | (h2 & 0x7FFFFFu));    // u in [1, 4)
+		else a = __uint_as_float(__float_as_uint(b) - (h2 >> 8) % 4096u);                                  // a within a few thousand ulp below b
+		if (!(a >= fmaxf(kDivLo, b * 5.42101086e-20f)) || !(b >= kDivLo && b <= kDivHi)) continue;
 		const float q = divByArea(a, b, refinedReciprocal(b));
 		if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
 	}
@@ -509,7 +510,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	CUC(cudaMalloc((void**)&c->dCounters, kCounterWords * 4));
 	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8));
 	CUC(cudaMemset(c->dFrameInfo, 0, kInfoWords * 8));
-	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortLarge * sizeof(uint32_t))));
+	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortLongSmem));
 #undef CUC
 	int r = allocSurfaces(c);
 	if (r) return bail(r);

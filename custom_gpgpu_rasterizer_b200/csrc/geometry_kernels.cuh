@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
 constexpr int kSortWarp = 256;
 constexpr int kSortSmall = 4096;
-constexpr int kSortLarge = 49152;
+constexpr int kSortLarge = 40960;
+constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(256) bin_sort_warp_kernel(
 	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
@@ -470,44 +471,111 @@ __global__ void __launch_bounds__(256) bin_sort_warp_kernel(
 	for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; if (v < n) list[v] = a[i]; }
 }
 
-__device__ __forceinline__ void sortTileList(uint32_t* __restrict__ list, uint32_t n, uint32_t* sKeys)
+// Block-level stable LSD radix sort (8-bit digits) of one tile list.  Keys are distinct primitive
+// ids; only the bits that vary inside the list (id - min id) are sorted, so a list whose ids span
+// less than 65 536 takes two passes.  Stability comes from a fixed ownership order: warp w owns a
+// contiguous segment, walks it 32 keys at a time, and lanes rank themselves among the lanes with
+// the same digit (__match_any_sync); per-(warp, digit) counters in shared memory are then scanned
+// digit-major / warp-minor.  bufA/bufB are ping-pong buffers (bufB may be the global list itself).
+template <int WARPS>
+__device__ __forceinline__ void radixSortTileList(uint32_t* __restrict__ list, uint32_t n, uint32_t* bufA, uint32_t* bufB,
+	uint32_t* whist /*[WARPS*256]*/, uint32_t* sRed /*[2*WARPS + 2]*/)
 {
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// load + min / max + sortedness
+	uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 	int unsorted = 0;
-	for (uint32_t i = threadIdx.x; i + 1 < n; i += blockDim.x)
-		unsorted |= (list[i] > list[i + 1]);
+	for (uint32_t i = tid; i < n; i += WARPS * 32)
+	{
+		const uint32_t k = list[i];
+		bufA[i] = k;
+		kmin = min(kmin, k); kmax = max(kmax, k);
+		if (i + 1 < n) unsorted |= (k > list[i + 1]);
+	}
 	if (!__syncthreads_or(unsorted)) return;
-	uint32_t m = 1; while (m < n) m <<= 1;
-	for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sKeys[i] = (i < n) ? list[i] : 0xFFFFFFFFu;
+	kmin = __reduce_min_sync(0xFFFFFFFFu, kmin); kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+	if (lane == 0) { sRed[warp] = kmin; sRed[WARPS + warp] = kmax; }
 	__syncthreads();
-	for (uint32_t k = 2; k <= m; k <<= 1)
-		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+	if (tid == 0)
+	{
+		uint32_t a = sRed[0], b = sRed[WARPS];
+		for (int w = 1; w < WARPS; ++w) { a = min(a, sRed[w]); b = max(b, sRed[WARPS + w]); }
+		sRed[2 * WARPS] = a; sRed[2 * WARPS + 1] = b;
+	}
+	__syncthreads();
+	kmin = sRed[2 * WARPS];
+	const uint32_t range = sRed[2 * WARPS + 1] - kmin;
+	const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
+	// warp w owns [segBegin, segEnd): contiguous, a multiple of 32 long
+	const uint32_t seg = ((n + WARPS - 1) / WARPS + 31u) & ~31u;
+	const uint32_t segBegin = min(warp * seg, n), segEnd = min(segBegin + seg, n);
+	uint32_t* src = bufA; uint32_t* dst = bufB;
+	for (int p = 0; p < passes; ++p)
+	{
+		const int shift = 8 * p;
+		for (uint32_t i = tid; i < WARPS * 256; i += WARPS * 32) whist[i] = 0;
+		__syncthreads();
+		// sweep 1: per-(warp, digit) counts
+		for (uint32_t b = segBegin; b < segEnd; b += 32)
 		{
-			for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
-			{
-				const uint32_t p = i ^ j;
-				if (p > i)
-				{
-					const uint32_t a = sKeys[i], b = sKeys[p];
-					const bool up = ((i & k) == 0);
-					if ((a > b) == up) { sKeys[i] = b; sKeys[p] = a; }
-				}
-			}
-			__syncthreads();
+			const uint32_t i = b + lane;
+			const bool valid = i < segEnd;
+			const uint32_t d = valid ? (((src[i] - kmin) >> shift) & 255u) : (256u + lane);
+			const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+			if (valid && (int)lane == __ffs(peers) - 1) whist[warp * 256 + d] += (uint32_t)__popc(peers);
+			__syncwarp();
 		}
-	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) list[i] = sKeys[i];
+		__syncthreads();
+		// exclusive scan, digit-major / warp-minor: thread d < 256 owns digit d
+		uint32_t total = 0;
+		if (tid < 256)
+		{
+			for (int w = 0; w < WARPS; ++w) { const uint32_t c = whist[w * 256 + tid]; whist[w * 256 + tid] = total; total += c; }
+		}
+		uint32_t incl = total;
+		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= (uint32_t)dd) incl += t; }
+		if (tid < 256 && lane == 31) sRed[warp] = incl;
+		__syncthreads();
+		if (tid < 256)
+		{
+			uint32_t base = incl - total;
+			for (uint32_t w = 0; w < warp; ++w) base += sRed[w];
+			for (int w = 0; w < WARPS; ++w) whist[w * 256 + tid] += base;
+		}
+		__syncthreads();
+		// sweep 2: rank + scatter (same order as sweep 1 => stable)
+		for (uint32_t b = segBegin; b < segEnd; b += 32)
+		{
+			const uint32_t i = b + lane;
+			const bool valid = i < segEnd;
+			const uint32_t k = valid ? src[i] : 0u;
+			const uint32_t d = valid ? (((k - kmin) >> shift) & 255u) : (256u + lane);
+			const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+			const int leader = __ffs(peers) - 1;
+			uint32_t base = 0;
+			if (valid && (int)lane == leader) { base = whist[warp * 256 + d]; whist[warp * 256 + d] = base + (uint32_t)__popc(peers); }
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (valid) dst[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = k;
+			__syncwarp();
+		}
+		__syncthreads();
+		uint32_t* t = src; src = dst; dst = t;
+	}
+	if (src != list)
+		for (uint32_t i = tid; i < n; i += WARPS * 32) list[i] = src[i];
 }
 
 __global__ void __launch_bounds__(256) bin_sort_mid_kernel(
 	const uint32_t* __restrict__ midTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
 {
-	__shared__ uint32_t sKeys[kSortSmall];
+	__shared__ uint32_t sA[kSortSmall], sB[kSortSmall], sHist[8 * 256], sRed[2 * 8 + 2];
 	if (frameInfo[1]) return;
 	const uint32_t nMid = (uint32_t)frameInfo[5];
 	for (uint32_t w = blockIdx.x; w < nMid; w += gridDim.x)
 	{
 		const uint32_t tile = midTiles[w];
-		sortTileList(binIds + tileOffset[tile], tileCount[tile], sKeys);
+		radixSortTileList<8>(binIds + tileOffset[tile], tileCount[tile], sA, sB, sHist, sRed);
 		__syncthreads();
 	}
 }
@@ -516,7 +584,7 @@ __global__ void __launch_bounds__(1024) bin_sort_long_kernel(
 	const uint32_t* __restrict__ longTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ binIds, unsigned long long* __restrict__ frameInfo)
 {
-	extern __shared__ uint32_t sKeysDyn[];
+	extern __shared__ uint32_t sDyn[];      // [kSortLarge] keys + [32*256] counters + reductions
 	if (frameInfo[1]) return;
 	const uint32_t nLong = (uint32_t)frameInfo[3];
 	for (uint32_t w = blockIdx.x; w < nLong; w += gridDim.x)
@@ -528,7 +596,8 @@ __global__ void __launch_bounds__(1024) bin_sort_long_kernel(
 			if (threadIdx.x == 0) atomicAdd(&frameInfo[2], 1ull);
 			continue;
 		}
-		sortTileList(binIds + tileOffset[tile], n, sKeysDyn);
+		uint32_t* list = binIds + tileOffset[tile];
+		radixSortTileList<32>(list, n, sDyn, list, sDyn + kSortLarge, sDyn + kSortLarge + 32 * 256);
 		__syncthreads();
 	}
 }

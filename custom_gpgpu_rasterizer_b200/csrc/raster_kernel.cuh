@@ -46,7 +46,8 @@ struct __align__(16) TriShared
 	float area;                   // |Cross(v0-v1, v0-v2)|, CUDAROPs.cu:336
 	uint32_t prim;
 	int zLow;                     // conservative lower bound of any fragment's integer depth
-	uint32_t fastDiv;             // 1 when |area| is in the range where the hoisted division is exact
+	uint32_t yExtent;             // pixel-parallel path: bbox rows y0 | y1 << 16 for the warp-level reject
+	float divLo;                  // weights >= divLo take the hoisted division; +inf disables it for this triangle
 };
 
 struct Bary { float b0, b1, b2, z; };
@@ -84,7 +85,7 @@ __device__ __forceinline__ bool fragmentTest(const TriShared& t, float fx, float
 	const float w1 = diff2(fx - t.x2, t.eCy, fy - t.y2, t.eCx);
 	if (!(w0 >= 0.f && w1 >= 0.f && w2 >= 0.f)) return false;
 	const float wMin = fminf(fminf(w0, w1), w2);
-	if (t.fastDiv && wMin >= kDivLo)
+	if (wMin >= t.divLo)
 	{
 		out.b0 = divByArea(w0, t.area, t.rcpArea); out.b1 = divByArea(w1, t.area, t.rcpArea); out.b2 = divByArea(w2, t.area, t.rcpArea);
 	}
@@ -114,7 +115,9 @@ __device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, 
 	t.eBx = r.x2 - r.x1; t.eBy = r.y2 - r.y1;
 	t.eCx = r.x0 - r.x2; t.eCy = r.y0 - r.y2;
 	t.prim = prim;
-	t.fastDiv = (r.area >= kDivLo && r.area <= kDivHi) ? 1u : 0u;
+	// hoisted division only for quotients in [2^-64, ~1] with a sane divisor; everything else uses __fdiv_rn
+	t.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
+	t.yExtent = 0;
 	t.rcpArea = refinedReciprocal(r.area);
 	// weights are in [0, 1 + few ulp] and sum to 1 +- few ulp, so z >= min(z_i) - small; anything
 	// non-finite or negative falls back to "no bound"
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 					// pixel-parallel: bbox rows are kept in zLow's neighbours for the warp-level reject
 					TriShared& dst = sBig[atomicAdd(&sNumBig, 1u)];
 					dst = t;
-					dst.fastDiv |= ((uint32_t)y0 << 8) | ((uint32_t)y1 << 20);   // y extent (12 bits each) above the flag
+					dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
 				}
 				else
 				{
@@ -302,10 +305,9 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 		for (uint32_t j = 0; j < nBig; ++j)
 		{
 			TriShared t = sBig[j];
-			const int ty0 = (int)((t.fastDiv >> 8) & 0xFFFu), ty1 = (int)(t.fastDiv >> 20);
+			const int ty0 = (int)(t.yExtent & 0xFFFFu), ty1 = (int)(t.yExtent >> 16);
 			if (ty1 <= warpY0 || ty0 >= warpY1) continue;          // warp-uniform
 			if (!COUNT && t.zLow > bestZ) continue;                // cannot win this pixel (per lane)
-			t.fastDiv &= 1u;
 			Bary bc; int zi;
 			if (live && fragmentTest<TOPLEFT>(t, fx, fy, bc, zi))
 			{
