@@ -31,7 +31,7 @@ using namespace b2r;
 namespace {
 
 constexpr int kRing = 4;
-constexpr int kInfoWords = 6;
+constexpr int kInfoWords = 8;
 thread_local std::string g_createError;
 
 // grow-only device array
@@ -96,9 +96,9 @@ struct b2r_context
 	bool sceneDirty = true, texDirty = true;
 	DeviceVec<float2> dIVertex;        // 7 float2 per vertex
 	DeviceVec<uint32_t> dIndices;
-	DeviceVec<float4> dPos4, dAttr;    // attr: 4 float4 per vertex
+	DeviceVec<float4> dPosIn, dPos4;   // positions in (x,y,z,1) / transformed (ndc.xyz, clip.w)
+	DeviceVec<float> dOvertexScratch;
 	DeviceVec<TriRecord> dRecords;
-	DeviceVec<TriAux> dAux;
 	DeviceVec<uint2> dRects;
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
@@ -106,7 +106,7 @@ struct b2r_context
 	DeviceVec<TexDesc> dTexDesc;
 
 	// binning
-	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dBigList, dBinIds;
+	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dWarpTiles, dBigList, dBinIds;
 	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
 	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };
@@ -195,6 +195,7 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 	CU(c, c->dTileCursor.reserve(n, c->stream));
 	CU(c, c->dLongTiles.reserve(n, c->stream));
 	CU(c, c->dMidTiles.reserve(n, c->stream));
+	CU(c, c->dWarpTiles.reserve(n, c->stream));
 	// tile_scan_kernel reads the counts with 16-byte loads
 	CU(c, c->dTileCount.reserve((size_t)n + 4, c->stream));
 	return B2R_OK;
@@ -221,9 +222,7 @@ int rebuildScene(b2r_context* c)
 	if (!tri.empty()) CU(c, cudaMemcpyAsync(c->dTriChunks.ptr, tri.data(), tri.size() * sizeof(Chunk), cudaMemcpyHostToDevice, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));   // vs/tri are host temporaries
 	CU(c, c->dPos4.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
-	CU(c, c->dAttr.reserve(std::max<size_t>(c->nVtxOut, 1) * 4, c->stream));
 	CU(c, c->dRecords.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
-	CU(c, c->dAux.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dRects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dBigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dMeshConst.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
@@ -257,6 +256,7 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.ownerRank = (uint32_t)c->ownerRank; fp.ownerCount = (uint32_t)c->ownerCount;
 	fp.debugSurfaces = (uint32_t)c->debugSurfaces;
 	fp.bigRectTiles = 64;
+	fp.nMeshes = (uint32_t)c->meshes.size();
 	return fp;
 }
 
@@ -339,20 +339,21 @@ int enqueueFrame(b2r_context* c)
 
 	if (c->nVsChunks)
 	{
-		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, c->dMeshConst.ptr, c->dIVertex.ptr, c->dPos4.ptr, c->dAttr.ptr, fp);
+		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, c->dMeshConst.ptr, c->dPosIn.ptr, c->dPos4.ptr);
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 1);
 	if (c->nTriChunks)
 	{
 		triangle_setup_kernel<<<c->nTriChunks, kChunk, 0, s>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dPos4.ptr,
-			c->dRecords.ptr, c->dAux.ptr, c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, fp);
+			c->dRecords.ptr, c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, fp);
 		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, c->dFrameInfo, fp);
 		c->kernelsLaunched += 2;
 	}
 	STAGE_EVENT(c, slot, 2);
 	tile_scan_kernel<<<1, 1024, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dTileCursor.ptr, tiles,
-		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortWarp, (uint32_t)kSortSmall, c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
+		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortWarp, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
+		c->dWarpTiles.ptr, c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
 	++c->kernelsLaunched;
 	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
@@ -367,16 +368,17 @@ int enqueueFrame(b2r_context* c)
 	if (c->sortBins && c->nPrims)
 	{
 		bin_sort_warp_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, tiles, c->dFrameInfo);
+		bin_sort_warp_radix_kernel<<<c->numSMs * 6, 128, 0, s>>>(c->dWarpTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
 		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
 		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,
 			c->dBinIds.ptr, c->dFrameInfo);
-		c->kernelsLaunched += 3;
+		c->kernelsLaunched += 4;
 	}
 	STAGE_EVENT(c, slot, 5);
 	{
 		RasterArgs A{};
 		A.tileCount = c->dTileCount.ptr; A.tileOffset = c->dTileOffset.ptr; A.binIds = c->dBinIds.ptr;
-		A.records = c->dRecords.ptr; A.aux = c->dAux.ptr; A.pos4 = c->dPos4.ptr; A.attr = c->dAttr.ptr;
+		A.records = c->dRecords.ptr; A.pos4 = c->dPos4.ptr; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
 		A.meshes = c->dMeshConst.ptr; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
 		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer;
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
@@ -526,10 +528,10 @@ void b2r_destroy(b2r_context* c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
-	c->dIVertex.release(); c->dIndices.release(); c->dPos4.release(); c->dAttr.release();
-	c->dRecords.release(); c->dAux.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
+	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); c->dPos4.release(); c->dOvertexScratch.release();
+	c->dRecords.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
 	c->dMeshConst.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
-	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dBigList.release(); c->dBinIds.release();
+	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dWarpTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dCounters); cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
 	for (auto& slot : c->slots)
@@ -605,7 +607,13 @@ int b2r_mesh_upload(b2r_context* c, const void* ivertex56, uint32_t nV, const ui
 	int r = validateFrame(c); if (r) return r;
 	CU(c, c->dIVertex.reserve((c->nVtxIn + nV) * 7 + 1, c->stream, c->nVtxIn * 7));
 	CU(c, c->dIndices.reserve(c->nIdx + nI + 1, c->stream, c->nIdx));
-	if (nV) CU(c, cudaMemcpy(c->dIVertex.ptr + c->nVtxIn * 7, ivertex56, (size_t)nV * 56, cudaMemcpyHostToDevice));
+	CU(c, c->dPosIn.reserve(c->nVtxIn + nV + 1, c->stream, c->nVtxIn));
+	if (nV)
+	{
+		CU(c, cudaMemcpy(c->dIVertex.ptr + c->nVtxIn * 7, ivertex56, (size_t)nV * 56, cudaMemcpyHostToDevice));
+		split_positions_kernel<<<(nV + 255) / 256, 256, 0, c->stream>>>(c->dIVertex.ptr, c->dPosIn.ptr, (uint32_t)c->nVtxIn, nV);
+		CU(c, cudaGetLastError());
+	}
 	if (nI) CU(c, cudaMemcpy(c->dIndices.ptr + c->nIdx, indices, (size_t)nI * 4, cudaMemcpyHostToDevice));
 	HostMesh hm{};
 	hm.vtxInBase = (uint32_t)c->nVtxIn; hm.nVertices = nV; hm.idxBase = (uint32_t)c->nIdx; hm.nTris = nI / 3;
@@ -712,19 +720,13 @@ int b2r_read_overtex(b2r_context* c, int id, float* out18)
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
 	const HostMesh& hm = c->meshes[id];
-	std::vector<float4> pos(hm.nVertices), attr((size_t)hm.nVertices * 4);
-	if (hm.nVertices)
-	{
-		CU(c, cudaMemcpy(pos.data(), c->dPos4.ptr + hm.vtxOutBase, (size_t)hm.nVertices * 16, cudaMemcpyDeviceToHost));
-		CU(c, cudaMemcpy(attr.data(), c->dAttr.ptr + (size_t)hm.vtxOutBase * 4, (size_t)hm.nVertices * 64, cudaMemcpyDeviceToHost));
-	}
-	for (uint32_t v = 0; v < hm.nVertices; ++v)
-	{
-		float* o = out18 + (size_t)v * 18;
-		const float* a = reinterpret_cast<const float*>(&attr[(size_t)v * 4]);
-		o[0] = pos[v].x; o[1] = pos[v].y; o[2] = pos[v].z; o[3] = pos[v].w;
-		memcpy(o + 4, a, 14 * sizeof(float));     // uv2 n3 tan3 vd3 c3
-	}
+	if (!hm.nVertices) return B2R_OK;
+	CU(c, c->dOvertexScratch.reserve((size_t)hm.nVertices * 18, c->stream));
+	const FrameParams fp = makeParams(c, c->last);
+	overtex_kernel<<<(hm.nVertices + 255) / 256, 256, 0, c->stream>>>(c->dMeshConst.ptr, (uint32_t)id, c->dIVertex.ptr, c->dPos4.ptr, c->dOvertexScratch.ptr, fp);
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(out18, c->dOvertexScratch.ptr, (size_t)hm.nVertices * 18 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
 	return B2R_OK;
 }
 

@@ -35,57 +35,75 @@ __device__ __forceinline__ void normalize3(float& x, float& y, float& z)
 }
 
 // ---------------------------------------------------------------------------------------
-// vertex transform: one CTA per chunk of 256 vertices of one mesh.
-// Input records (56 B AoS) are staged through shared memory with coalesced 8-byte loads;
-// outputs are a 16 B position stream and a 64 B attribute stream.
-// Follows GetNDCVertex, CUDAROPs.cu:99-118.
+// upload-time: pull the positions out of the 56 B AoS records into a 16 B stream, so the per-frame
+// transform reads 16 B per vertex instead of dragging the whole record through the memory system
+__global__ void __launch_bounds__(256) split_positions_kernel(const float2* __restrict__ ivertex, float4* __restrict__ posIn, uint32_t first, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float2* rec = ivertex + (size_t)(first + i) * 7;
+	const float2 a = __ldg(rec), b = __ldg(rec + 1);
+	posIn[first + i] = make_float4(a.x, a.y, b.x, 1.f);
+}
+
+// vertex transform: one CTA per chunk of 256 vertices of one mesh; 16 B in, 16 B out, coalesced.
+// clip = WVP * (p, 1); ndc = clip.xyz / clip.w (IEEE); w kept.  GetNDCVertex, CUDAROPs.cu:99-107.
 __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
-	const float2* __restrict__ ivertex, float4* __restrict__ pos4, float4* __restrict__ attr, FrameParams fp)
+	const float4* __restrict__ posIn, float4* __restrict__ pos4)
 {
-	__shared__ float2 sIn[kChunk * 7];
-	__shared__ float sMat[41];
+	__shared__ float sMat[16];
 	const Chunk ch = chunks[blockIdx.x];
-	const MeshConst& mc = meshes[ch.mesh];
-	const uint32_t n = ch.count;
-	const float2* src = ivertex + (size_t)ch.inStart * 7;
-	for (uint32_t i = threadIdx.x; i < n * 7; i += kChunk)
-		sIn[i] = __ldcs(src + i);                  // read once: streaming
-	if (threadIdx.x < 16) sMat[threadIdx.x] = mc.wvp[threadIdx.x];
-	else if (threadIdx.x < 32) sMat[threadIdx.x] = mc.world[threadIdx.x - 16];
-	else if (threadIdx.x < 41) sMat[threadIdx.x] = mc.rot[threadIdx.x - 32];
+	if (threadIdx.x < 16) sMat[threadIdx.x] = meshes[ch.mesh].wvp[threadIdx.x];
+	float4 in = make_float4(0.f, 0.f, 0.f, 1.f);
+	if (threadIdx.x < ch.count) in = __ldcs(posIn + (size_t)ch.inStart + threadIdx.x);
 	__syncthreads();
-	if (threadIdx.x >= n) return;
-
-	const float* v = reinterpret_cast<const float*>(sIn) + threadIdx.x * 14;
-	const float px = v[0], py = v[1], pz = v[2];
-	const float* wvp = sMat; const float* world = sMat + 16; const float* rot = sMat + 32;
-
-	const float cx = mulRow4(wvp, 0, px, py, pz);
-	const float cy = mulRow4(wvp, 1, px, py, pz);
-	const float cz = mulRow4(wvp, 2, px, py, pz);
-	const float cw = mulRow4(wvp, 3, px, py, pz);
+	if (threadIdx.x >= ch.count) return;
+	const float cx = mulRow4(sMat, 0, in.x, in.y, in.z);
+	const float cy = mulRow4(sMat, 1, in.x, in.y, in.z);
+	const float cz = mulRow4(sMat, 2, in.x, in.y, in.z);
+	const float cw = mulRow4(sMat, 3, in.x, in.y, in.z);
 	float4 p;
 	p.x = __fdiv_rn(cx, cw); p.y = __fdiv_rn(cy, cw); p.z = __fdiv_rn(cz, cw); p.w = cw;
+	pos4[(size_t)ch.outStart + threadIdx.x] = p;
+}
 
-	const float nx = mulRow3(rot, 0, v[5], v[6], v[7]);
-	const float ny = mulRow3(rot, 1, v[5], v[6], v[7]);
-	const float nz = mulRow3(rot, 2, v[5], v[6], v[7]);
-	const float tx = mulRow3(rot, 0, v[8], v[9], v[10]);
-	const float ty = mulRow3(rot, 1, v[8], v[9], v[10]);
-	const float tz = mulRow3(rot, 2, v[8], v[9], v[10]);
-	float vx = mulRow4(world, 0, px, py, pz) - fp.camPos[0];
-	float vy = mulRow4(world, 1, px, py, pz) - fp.camPos[1];
-	float vz = mulRow4(world, 2, px, py, pz) - fp.camPos[2];
+// the attribute half of GetNDCVertex (CUDAROPs.cu:108-115) for ONE vertex record
+struct VertexAttrs { float uv[2], n[3], tan[3], vd[3], c[3]; };
+__device__ __forceinline__ void transformAttributes(const float* v /*14 floats of the IVertex*/, const MeshConst& mc, const float* camPos, VertexAttrs& o)
+{
+	o.uv[0] = v[3]; o.uv[1] = v[4];
+	o.n[0] = mulRow3(mc.rot, 0, v[5], v[6], v[7]); o.n[1] = mulRow3(mc.rot, 1, v[5], v[6], v[7]); o.n[2] = mulRow3(mc.rot, 2, v[5], v[6], v[7]);
+	o.tan[0] = mulRow3(mc.rot, 0, v[8], v[9], v[10]); o.tan[1] = mulRow3(mc.rot, 1, v[8], v[9], v[10]); o.tan[2] = mulRow3(mc.rot, 2, v[8], v[9], v[10]);
+	float vx = mulRow4(mc.world, 0, v[0], v[1], v[2]) - camPos[0];
+	float vy = mulRow4(mc.world, 1, v[0], v[1], v[2]) - camPos[1];
+	float vz = mulRow4(mc.world, 2, v[0], v[1], v[2]) - camPos[2];
 	normalize3(vx, vy, vz);
+	o.vd[0] = vx; o.vd[1] = vy; o.vd[2] = vz;
+	o.c[0] = v[11]; o.c[1] = v[12]; o.c[2] = v[13];
+}
 
-	const size_t o = (size_t)ch.outStart + threadIdx.x;
-	pos4[o] = p;                                   // re-read by triangle setup: normal L2 policy
-	float4* a = attr + o * 4;                      // only the winners' attributes are read back: streaming stores
-	__stcs(a + 0, make_float4(v[3], v[4], nx, ny));
-	__stcs(a + 1, make_float4(nz, tx, ty, tz));
-	__stcs(a + 2, make_float4(vx, vy, vz, v[11]));
-	__stcs(a + 3, make_float4(v[12], v[13], 0.f, 0.f));
+// parity surface: the full 72 B OVertex records of one mesh, produced on demand (b2r_read_overtex)
+__global__ void __launch_bounds__(256) overtex_kernel(const MeshConst* __restrict__ meshes, uint32_t mesh,
+	const float2* __restrict__ ivertex, const float4* __restrict__ pos4, float* __restrict__ out18, FrameParams fp)
+{
+	const MeshConst& mc = meshes[mesh];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= mc.nVertices) return;
+	float v[14];
+	const float2* rec = ivertex + (size_t)(mc.vtxInBase + i) * 7;
+	#pragma unroll
+	for (int k = 0; k < 7; ++k) { const float2 t = __ldg(rec + k); v[2 * k] = t.x; v[2 * k + 1] = t.y; }
+	VertexAttrs a;
+	transformAttributes(v, mc, fp.camPos, a);
+	const float4 p = pos4[mc.vtxOutBase + i];
+	float* o = out18 + (size_t)i * 18;
+	o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.w;
+	o[4] = a.uv[0]; o[5] = a.uv[1];
+	o[6] = a.n[0]; o[7] = a.n[1]; o[8] = a.n[2];
+	o[9] = a.tan[0]; o[10] = a.tan[1]; o[11] = a.tan[2];
+	o[12] = a.vd[0]; o[13] = a.vd[1]; o[14] = a.vd[2];
+	o[15] = a.c[0]; o[16] = a.c[1]; o[17] = a.c[2];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -139,7 +157,7 @@ __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t til
 __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 	const Chunk* __restrict__ chunks,
 	const uint32_t* __restrict__ indices, const float4* __restrict__ pos4,
-	TriRecord* __restrict__ records, TriAux* __restrict__ aux, uint2* __restrict__ rects,
+	TriRecord* __restrict__ records, uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig*/,
 	FrameParams fp)
 {
@@ -182,15 +200,38 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 			r.x2 = ((p2.x + 1.f) * 0.5f) * W; r.y2 = ((1.f - p2.y) * 0.5f) * H;
 			r.z0 = p0.z; r.z1 = p1.z; r.z2 = p2.z;
 			r.area = fabsf(diff2(r.x0 - r.x1, r.y0 - r.y2, r.y0 - r.y1, r.x0 - r.x2));
-			const int xMin = bboxCoord(min3ref(r.x0, r.x1, r.x2), -1, (int)fp.width);
-			const int yMin = bboxCoord(min3ref(r.y0, r.y1, r.y2), -1, (int)fp.height);
-			const int xMax = bboxCoord(max3ref(r.x0, r.x1, r.x2), +1, (int)fp.width);
-			const int yMax = bboxCoord(max3ref(r.y0, r.y1, r.y2), +1, (int)fp.height);
-			r.bbX = (uint32_t)xMin | ((uint32_t)xMax << 16);
-			r.bbY = (uint32_t)yMin | ((uint32_t)yMax << 16);
+			// the reference's inflated 16-bit bbox (CUDAROPs.cu:180-200) decides the BINS ...
+			const float minx = min3ref(r.x0, r.x1, r.x2), maxx = max3ref(r.x0, r.x1, r.x2);
+			const float miny = min3ref(r.y0, r.y1, r.y2), maxy = max3ref(r.y0, r.y1, r.y2);
+			const int xMin = bboxCoord(minx, -1, (int)fp.width);
+			const int yMin = bboxCoord(miny, -1, (int)fp.height);
+			const int xMax = bboxCoord(maxx, +1, (int)fp.width);
+			const int yMax = bboxCoord(maxy, +1, (int)fp.height);
+			// ... while the raster kernel only needs a superset of the pixels whose three edge
+			// functions can be >= 0.  A covered pixel has non-negative barycentrics, so it lies inside
+			// the float bounds of the triangle up to the rounding error of the edge functions: a pixel
+			// eps outside the bounds carries a negative weight of at least area*eps/extent, against an
+			// evaluation error below 2^-21 * D^2 (D = pixel-to-vertex distances).  eps below keeps a
+			// 8x safety factor on that error plus the rounding of the coordinates themselves; thin or
+			// degenerate triangles (area -> 0) widen to the whole screen, i.e. to the reference's
+			// "every pixel of the bin" (CUDARenderer.cu:1116-1127).
+			const float extx = maxx - minx, exty = maxy - miny;
+			const float D = extx + exty + 2.f;
+			const float maxAbs = fmaxf(fmaxf(fabsf(minx), fabsf(maxx)), fmaxf(fabsf(miny), fabsf(maxy)));
+			const float k = 3.814697265625e-6f * D * D / r.area;
+			const float epsx = 0.015625f + maxAbs * 1.52587890625e-5f + k * extx;
+			const float epsy = 0.015625f + maxAbs * 1.52587890625e-5f + k * exty;
+			int cx0 = 0, cx1 = (int)fp.width, cy0 = 0, cy1 = (int)fp.height;
+			if (epsx < 1.0e6f && epsy < 1.0e6f && maxAbs < 1.0e9f)      // false for NaN / inf
+			{
+				cx0 = clampi(__float2int_ru(minx - epsx), 0, (int)fp.width);
+				cx1 = clampi(__float2int_rd(maxx + epsx) + 1, 0, (int)fp.width);
+				cy0 = clampi(__float2int_ru(miny - epsy), 0, (int)fp.height);
+				cy1 = clampi(__float2int_rd(maxy + epsy) + 1, 0, (int)fp.height);
+			}
+			r.cbX = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
+			r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
 			records[prim] = r;
-			TriAux a; a.v0 = i0; a.v1 = i1; a.v2 = i2; a.mesh = ch.mesh;
-			aux[prim] = a;
 			bx0 = clampi(xMin / (int)fp.binW, 0, (int)fp.binsX);
 			by0 = clampi(yMin / (int)fp.binH, 0, (int)fp.binsY);
 			bx1 = clampi(xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
@@ -269,9 +310,9 @@ __global__ void __launch_bounds__(256) bin_big_kernel(
 constexpr uint32_t kScanPerThread = 32;
 __global__ void __launch_bounds__(1024) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t nTiles, unsigned long long capacity, uint32_t midThreshold, uint32_t longThreshold,
-	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
-	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles*/)
+	uint32_t nTiles, unsigned long long capacity, uint32_t warpThreshold, uint32_t midThreshold, uint32_t longThreshold,
+	uint32_t* __restrict__ warpTiles, uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
+	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles,[6]=warp-radix tiles*/)
 {
 	if (threadIdx.x < 32)
 	{
@@ -281,8 +322,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 	}
 	__shared__ unsigned long long sWarp[32];
 	__shared__ unsigned long long sCarry;
-	__shared__ uint32_t sLong, sMid;
-	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; sMid = 0; }
+	__shared__ uint32_t sLong, sMid, sWarpList;
+	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; sMid = 0; sWarpList = 0; }
 	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (uint32_t base = 0; base < nTiles; base += 1024 * kScanPerThread)
@@ -329,17 +370,36 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 		const unsigned long long carry = sCarry;
 		unsigned long long run = carry + (warp ? sWarp[warp - 1] : 0ull) + incl - sum;
 		#pragma unroll
-		for (uint32_t q = 0; q < kScanPerThread; ++q)
+		for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
 		{
-			const uint32_t i = first + q;
-			if (i < nTiles)
+			const uint32_t i = first + q * 4;
+			uint4 o;
+			o.x = (uint32_t)run; run += v[q * 4];
+			o.y = (uint32_t)run; run += v[q * 4 + 1];
+			o.z = (uint32_t)run; run += v[q * 4 + 2];
+			o.w = (uint32_t)run; run += v[q * 4 + 3];
+			if (i + 3 < nTiles)
 			{
-				tileOffset[i] = (uint32_t)run;
-				tileCursor[i] = 0u;
-				if (v[q] > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i;
-				else if (v[q] > midThreshold) midTiles[atomicAdd(&sMid, 1u)] = i;
+				*reinterpret_cast<uint4*>(tileOffset + i) = o;
+				*reinterpret_cast<uint4*>(tileCursor + i) = make_uint4(0, 0, 0, 0);
 			}
-			run += v[q];
+			else
+			{
+				if (i < nTiles) { tileOffset[i] = o.x; tileCursor[i] = 0; }
+				if (i + 1 < nTiles) { tileOffset[i + 1] = o.y; tileCursor[i + 1] = 0; }
+				if (i + 2 < nTiles) { tileOffset[i + 2] = o.z; tileCursor[i + 2] = 0; }
+			}
+			#pragma unroll
+			for (uint32_t e = 0; e < 4; ++e)
+			{
+				const uint32_t c = v[q * 4 + e];
+				if (i + e < nTiles && c > warpThreshold)
+				{
+					if (c > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i + e;
+					else if (c > midThreshold) midTiles[atomicAdd(&sMid, 1u)] = i + e;
+					else warpTiles[atomicAdd(&sWarpList, 1u)] = i + e;
+				}
+			}
 		}
 		__syncthreads();
 		if (threadIdx.x == 1023) sCarry = carry + sWarp[31];
@@ -352,6 +412,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 		frameInfo[2] = 0ull;
 		frameInfo[3] = sLong;
 		frameInfo[5] = sMid;
+		frameInfo[6] = sWarpList;
 	}
 }
 
@@ -401,8 +462,9 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 //  tier 3: the "long" work list (up to kSortLarge entries) in dynamic shared memory, one CTA per SM
 //  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
-constexpr int kSortWarp = 256;
-constexpr int kSortSmall = 4096;
+constexpr int kSortWarp = 256;       // <= : register bitonic, one warp
+constexpr int kSortWarpRadix = 1024; // <= : shared-memory radix, one warp, no block barriers
+constexpr int kSortSmall = 4096;     // <= : shared-memory radix, one CTA
 constexpr int kSortLarge = 40960;
 constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
 
@@ -469,6 +531,85 @@ __global__ void __launch_bounds__(256) bin_sort_warp_kernel(
 	}
 	#pragma unroll
 	for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; if (v < n) list[v] = a[i]; }
+}
+
+// Warp-level stable LSD radix sort of one tile list (257 .. kSortWarpRadix entries): same scheme as the
+// block version below with a single warp, so every step is ordered by __syncwarp only.
+__global__ void __launch_bounds__(128) bin_sort_warp_radix_kernel(
+	const uint32_t* __restrict__ warpTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
+	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
+{
+	__shared__ uint32_t sKeys[4][2][kSortWarpRadix];
+	__shared__ uint32_t sHist[4][256];
+	if (frameInfo[1]) return;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t nWork = (uint32_t)frameInfo[6];
+	uint32_t* hist = sHist[warp];
+	for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4)
+	{
+		const uint32_t tile = warpTiles[w];
+		const uint32_t n = tileCount[tile];
+		uint32_t* list = binIds + tileOffset[tile];
+		uint32_t* src = sKeys[warp][0]; uint32_t* dst = sKeys[warp][1];
+		uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+		bool unsorted = false;
+		for (uint32_t i = lane; i < n; i += 32)
+		{
+			const uint32_t k = list[i];
+			src[i] = k;
+			kmin = min(kmin, k); kmax = max(kmax, k);
+			if (i + 1 < n) unsorted |= (k > list[i + 1]);
+		}
+		if (!__any_sync(0xFFFFFFFFu, unsorted)) continue;
+		kmin = __reduce_min_sync(0xFFFFFFFFu, kmin); kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+		const uint32_t range = kmax - kmin;
+		const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
+		__syncwarp();
+		for (int p = 0; p < passes; ++p)
+		{
+			const int shift = 8 * p;
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = 0;
+			__syncwarp();
+			for (uint32_t b = 0; b < n; b += 32)
+			{
+				const uint32_t i = b + lane;
+				const bool valid = i < n;
+				const uint32_t d = valid ? (((src[i] - kmin) >> shift) & 255u) : (256u + lane);
+				const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+				if (valid && (int)lane == __ffs(peers) - 1) hist[d] += (uint32_t)__popc(peers);
+				__syncwarp();
+			}
+			// exclusive scan of the 256 counters: 8 consecutive digits per lane
+			uint32_t c[8], sum = 0;
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; sum += c[q]; }
+			uint32_t incl = sum;
+			#pragma unroll
+			for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= (uint32_t)dd) incl += t; }
+			uint32_t run = incl - sum;
+			#pragma unroll
+			for (int q = 0; q < 8; ++q) { hist[lane * 8 + q] = run; run += c[q]; }
+			__syncwarp();
+			for (uint32_t b = 0; b < n; b += 32)
+			{
+				const uint32_t i = b + lane;
+				const bool valid = i < n;
+				const uint32_t k = valid ? src[i] : 0u;
+				const uint32_t d = valid ? (((k - kmin) >> shift) & 255u) : (256u + lane);
+				const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+				const int leader = __ffs(peers) - 1;
+				uint32_t base = 0;
+				if (valid && (int)lane == leader) { base = hist[d]; hist[d] = base + (uint32_t)__popc(peers); }
+				base = __shfl_sync(0xFFFFFFFFu, base, leader);
+				if (valid) dst[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = k;
+				__syncwarp();
+			}
+			uint32_t* t = src; src = dst; dst = t;
+		}
+		for (uint32_t i = lane; i < n; i += 32) list[i] = src[i];
+		__syncwarp();
+	}
 }
 
 // Block-level stable LSD radix sort (8-bit digits) of one tile list.  Keys are distinct primitive

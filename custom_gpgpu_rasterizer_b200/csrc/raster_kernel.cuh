@@ -24,9 +24,9 @@ struct RasterArgs
 	const uint32_t* tileOffset;
 	const uint32_t* binIds;
 	const TriRecord* records;
-	const TriAux* aux;
 	const float4* pos4;
-	const float4* attr;
+	const float2* ivertex;      // resident IVertex records (7 float2 each)
+	const uint32_t* indices;
 	const MeshConst* meshes;
 	const TexDesc* textures;
 	unsigned long long* frameInfo;
@@ -266,10 +266,11 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 		{
 			const uint32_t prim = __ldg(list + base + tid);
 			const TriRecord r = A.records[prim];
-			// candidate pixels = inflated bbox (CUDAROPs.cu:180-200) clipped to this CTA's block;
-			// the bbox is conservative for the edge test, so this equals testing the whole bin
-			const int x0 = max((int)(r.bbX & 0xFFFFu), ox), x1 = min((int)(r.bbX >> 16), ex);
-			const int y0 = max((int)(r.bbY & 0xFFFFu), oy), y1 = min((int)(r.bbY >> 16), ey);
+			// candidate pixels = the record's conservative box clipped to this CTA's block; the box
+			// contains every pixel whose edge functions can all be >= 0, so this equals the
+			// reference's test of every pixel of the bin (CUDARenderer.cu:1116-1127)
+			const int x0 = max((int)(r.cbX & 0xFFFFu), ox), x1 = min((int)(r.cbX >> 16), ex);
+			const int y0 = max((int)(r.cbY & 0xFFFFu), oy), y1 = min((int)(r.cbY >> 16), ey);
 			const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
 			if (area > 0)
 			{
@@ -348,8 +349,10 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 		Bary bc; int zi;
 		fragmentTest<false>(t, fx, fy, bc, zi);      // same arithmetic as the coverage pass
 		zOut = bc.z;
-		const TriAux ax = A.aux[prim];
-		const MeshConst& mc = A.meshes[ax.mesh];
+		// which mesh: primitive ids are mesh-major (binary search over the per-mesh bases)
+		uint32_t lo = 0, hi = fp.nMeshes;
+		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (A.meshes[mid].primBase <= prim) lo = mid; else hi = mid; }
+		const MeshConst& mc = A.meshes[lo];
 		if (fp.visState == 1u)
 		{
 			const float r = __fdiv_rn(bc.z - 0.985f, 1.f - 0.985f);   // Remap, MathUtilities.h:175-178
@@ -357,33 +360,47 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 		}
 		else
 		{
+			const uint32_t* ip = A.indices + (size_t)mc.idxBase + (size_t)(prim - mc.primBase) * 3;
+			const uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 			Interp S;
 			S.b0 = bc.b0; S.b1 = bc.b1; S.b2 = bc.b2;
-			S.iw0 = __frcp_rn(__ldg(&A.pos4[ax.v0].w)); S.iw1 = __frcp_rn(__ldg(&A.pos4[ax.v1].w)); S.iw2 = __frcp_rn(__ldg(&A.pos4[ax.v2].w));
-			const float4* a0 = A.attr + (size_t)ax.v0 * 4; const float4* a1 = A.attr + (size_t)ax.v1 * 4; const float4* a2 = A.attr + (size_t)ax.v2 * 4;
+			S.iw0 = __frcp_rn(__ldg(&A.pos4[mc.vtxOutBase + i0].w)); S.iw1 = __frcp_rn(__ldg(&A.pos4[mc.vtxOutBase + i1].w)); S.iw2 = __frcp_rn(__ldg(&A.pos4[mc.vtxOutBase + i2].w));
+			const float2* r0 = A.ivertex + (size_t)(mc.vtxInBase + i0) * 7;
+			const float2* r1 = A.ivertex + (size_t)(mc.vtxInBase + i1) * 7;
+			const float2* r2 = A.ivertex + (size_t)(mc.vtxInBase + i2) * 7;
 			const bool textured = (fp.visState == 0u) && mc.tex[0] >= 0;
 			if (fp.visState == 0u && !textured)
 			{
-				// vertex colour, NOT multiplied by wInterpolated (CUDAROPs.cu:379)
-				const float4 c0a = __ldg(a0 + 2), c0b = __ldg(a0 + 3), c1a = __ldg(a1 + 2), c1b = __ldg(a1 + 3), c2a = __ldg(a2 + 2), c2b = __ldg(a2 + 3);
-				colour = packColour(S(c0a.w, c1a.w, c2a.w), S(c0b.x, c1b.x, c2b.x), S(c0b.y, c1b.y, c2b.y));
+				// vertex colour (IVertex floats 11..13, copied unchanged by GetNDCVertex), NOT multiplied
+				// by wInterpolated (CUDAROPs.cu:379)
+				const float2 a0 = __ldg(r0 + 5), b0 = __ldg(r0 + 6), a1 = __ldg(r1 + 5), b1 = __ldg(r1 + 6), a2 = __ldg(r2 + 5), b2 = __ldg(r2 + 6);
+				colour = packColour(S(a0.y, a1.y, a2.y), S(b0.x, b1.x, b2.x), S(b0.y, b1.y, b2.y));
 			}
 			else
 			{
+				// transform the three vertices' attributes now (the reference did it for every vertex in VS_Kernel)
+				float v[14];
+				VertexAttrs t0, t1, t2;
+				#pragma unroll
+				for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r0 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+				transformAttributes(v, mc, fp.camPos, t0);
+				#pragma unroll
+				for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r1 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+				transformAttributes(v, mc, fp.camPos, t1);
+				#pragma unroll
+				for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r2 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+				transformAttributes(v, mc, fp.camPos, t2);
 				const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
-				const float4 p0 = __ldg(a0), p1 = __ldg(a1), p2 = __ldg(a2);               // uv, n.x, n.y
-				const float4 q0 = __ldg(a0 + 1), q1 = __ldg(a1 + 1), q2 = __ldg(a2 + 1);   // n.z, tan
-				const float nx = S(p0.z, p1.z, p2.z) * wInterp, ny = S(p0.w, p1.w, p2.w) * wInterp, nz = S(q0.x, q1.x, q2.x) * wInterp;
+				const float nx = S(t0.n[0], t1.n[0], t2.n[0]) * wInterp, ny = S(t0.n[1], t1.n[1], t2.n[1]) * wInterp, nz = S(t0.n[2], t1.n[2], t2.n[2]) * wInterp;
 				if (fp.visState == 2u)
 					colour = packColour(nx, ny, nz);
 				else
 				{
-					const float u = S(p0.x, p1.x, p2.x) * wInterp, v = S(p0.y, p1.y, p2.y) * wInterp;
-					const float tx = S(q0.y, q1.y, q2.y), ty = S(q0.z, q1.z, q2.z), tz = S(q0.w, q1.w, q2.w);   // no wInterp (CUDAROPs.cu:372)
-					const float4 r0 = __ldg(a0 + 2), r1 = __ldg(a1 + 2), r2 = __ldg(a2 + 2);
-					float vx = S(r0.x, r1.x, r2.x), vy = S(r0.y, r1.y, r2.y), vz = S(r0.z, r1.z, r2.z);
+					const float u = S(t0.uv[0], t1.uv[0], t2.uv[0]) * wInterp, vv = S(t0.uv[1], t1.uv[1], t2.uv[1]) * wInterp;
+					const float tx = S(t0.tan[0], t1.tan[0], t2.tan[0]), ty = S(t0.tan[1], t1.tan[1], t2.tan[1]), tz = S(t0.tan[2], t1.tan[2], t2.tan[2]);   // no wInterp (CUDAROPs.cu:372)
+					float vx = S(t0.vd[0], t1.vd[0], t2.vd[0]), vy = S(t0.vd[1], t1.vd[1], t2.vd[1]), vz = S(t0.vd[2], t1.vd[2], t2.vd[2]);
 					normalize3(vx, vy, vz);
-					const RGB c = shadePixel(A, mc, fp.sampleState, u, v, nx, ny, nz, tx, ty, tz, vx, vy, vz);
+					const RGB c = shadePixel(A, mc, fp.sampleState, u, vv, nx, ny, nz, tx, ty, tz, vx, vy, vz);
 					colour = packColour(c.r, c.g, c.b);
 				}
 			}

@@ -194,3 +194,23 @@ def shared_edge_scene(width: int = 256, height: int = 256) -> Scene:
             v00, v01, v10, v11 = r * (n + 1) + c, r * (n + 1) + c + 1, (r + 1) * (n + 1) + c, (r + 1) * (n + 1) + c + 1
             idx += [v00, v10, v11, v00, v11, v01]
     return Scene(width, height, [MeshData(verts, np.asarray(idx, np.uint32))], [], cull=0, cam_pos=(0.0, 0.0, 0.0), name="shared_edges")
+
+
+def sliver_scene(width: int = 640, height: int = 480, n_tris: int = 1500, seed: int = 3) -> Scene:
+    """Needle-thin, tiny and huge triangles: stresses the conservative candidate-pixel boxes of the raster kernel."""
+    rng = np.random.default_rng(seed)
+    centre = np.stack([rng.uniform(-4.5, 4.5, n_tris), rng.uniform(-2.5, 2.5, n_tris), rng.uniform(-4.0, 1.0, n_tris)], -1)
+    ang = rng.uniform(0, 2 * np.pi, n_tris)
+    length = 10.0 ** rng.uniform(-2.5, 1.3, n_tris)          # 0.003 .. 20 world units
+    thick = length * 10.0 ** rng.uniform(-5.0, -0.3, n_tris)  # aspect ratios up to 1e5
+    d = np.stack([np.cos(ang), np.sin(ang), np.zeros(n_tris)], -1)
+    nrm = np.stack([-np.sin(ang), np.cos(ang), np.zeros(n_tris)], -1)
+    v0 = centre - d * length[:, None] * 0.5
+    v1 = centre + d * length[:, None] * 0.5 + rng.normal(0, 0.02, (n_tris, 3)) * np.array([0, 0, 1.0])
+    v2 = centre + nrm * thick[:, None] + d * (rng.uniform(-0.5, 0.5, n_tris) * length)[:, None]
+    tri = np.stack([v0, v1, v2], 1)
+    a, b = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    ccw = (a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]) > 0
+    tri[~ccw] = tri[~ccw][:, [0, 2, 1]]
+    verts = make_vertices(tri.reshape(-1, 3), col=rng.uniform(0.2, 1.0, (n_tris * 3, 3)))
+    return Scene(width, height, [MeshData(verts, np.arange(n_tris * 3, dtype=np.uint32))], [], cull=2, cam_pos=(0.0, 0.0, 5.0), name=f"slivers_{n_tris}_{seed}")

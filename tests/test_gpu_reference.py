@@ -30,6 +30,8 @@ SCENES = {
     "spheres_tiny_tris": lambda: scenes.sphere_grid_scene(640, 480, nx=8, ny=5, stacks=81, slices=100, cam_z=22.0),
     "fill_quads_linear": lambda: scenes.fill_quads_scene(640, 480, layers=8, tex_size=256, sample=1),
     "shared_edges": lambda: scenes.shared_edge_scene(),
+    "slivers": lambda: scenes.sliver_scene(640, 480, 1500, seed=3),
+    "slivers_4k": lambda: scenes.sliver_scene(3840, 2160, 600, seed=4),
 }
 
 
