@@ -352,8 +352,8 @@ int enqueueFrame(b2r_context* c)
 	}
 	STAGE_EVENT(c, slot, 2);
 	tile_scan_kernel<<<1, 1024, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dTileCursor.ptr, tiles,
-		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortWarp, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
-		c->dWarpTiles.ptr, c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
+		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
+		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
 	++c->kernelsLaunched;
 	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
@@ -367,7 +367,7 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		bin_sort_warp_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, tiles, c->dFrameInfo);
+		bin_sort_runs_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, tiles, c->dWarpTiles.ptr, c->dFrameInfo);
 		bin_sort_warp_radix_kernel<<<c->numSMs * 6, 128, 0, s>>>(c->dWarpTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
 		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
 		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,

@@ -151,6 +151,64 @@ __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t til
 	return 0;
 }
 
+// Warp-level binning of up to 32 small rectangles (one per lane, rectangle = inclusive tile range,
+// nTiles = 0 for lanes without one).  Consecutive primitives overlap the same few tiles, so the warp
+// walks the UNION of its rectangles tile by tile: for each tile the lanes whose rectangle contains it
+// are found with one ballot and served by ONE atomic.  SCATTER: the lanes' ids are written in lane
+// order, so every (warp, tile) pair contributes exactly one ascending run of primitive ids, and runs
+// of different warps cover disjoint id ranges - the property bin_sort_runs_kernel relies on.
+// Warps whose union is large (incoherent geometry) fall back to per-lane iteration.
+constexpr uint32_t kUnionTilesMax = 64;
+template <bool SCATTER>
+__device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, int by0, int by1, uint32_t prim,
+	uint32_t* __restrict__ counters /*tileCount or tileCursor*/, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
+	const FrameParams& fp)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned have = __ballot_sync(0xFFFFFFFFu, nTiles > 0);
+	if (!have) return;
+	const int ux0 = __reduce_min_sync(0xFFFFFFFFu, nTiles ? bx0 : 0x7FFF), ux1 = __reduce_max_sync(0xFFFFFFFFu, nTiles ? bx1 : -1);
+	const int uy0 = __reduce_min_sync(0xFFFFFFFFu, nTiles ? by0 : 0x7FFF), uy1 = __reduce_max_sync(0xFFFFFFFFu, nTiles ? by1 : -1);
+	const uint32_t uw = (uint32_t)(ux1 - ux0 + 1), uArea = uw * (uint32_t)(uy1 - uy0 + 1);
+	if (uArea <= kUnionTilesMax)
+	{
+		for (uint32_t u = 0; u < uArea; ++u)
+		{
+			const int tx = ux0 + (int)(u % uw), ty = uy0 + (int)(u / uw);
+			const uint32_t tile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
+			const bool in = nTiles && tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1;
+			const unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
+			if (!mask || !tileOwned(fp, tile)) continue;          // warp-uniform
+			const int leader = __ffs(mask) - 1;
+			if (SCATTER)
+			{
+				uint32_t base = 0;
+				if ((int)lane == leader) base = atomicAdd(&counters[tile], (uint32_t)__popc(mask));
+				base = __shfl_sync(0xFFFFFFFFu, base, leader);
+				if (in) binIds[__ldg(tileOffset + tile) + base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = prim;
+			}
+			else if ((int)lane == leader)
+				atomicAdd(&counters[tile], (uint32_t)__popc(mask));
+		}
+	}
+	else
+	{
+		const int w = bx1 - bx0 + 1;
+		const uint32_t steps = __reduce_max_sync(0xFFFFFFFFu, nTiles);
+		for (uint32_t k = 0; k < steps; ++k)
+		{
+			uint32_t tile = kNoTile;
+			if (k < nTiles)
+			{
+				tile = (uint32_t)(bx0 + (int)(k % (uint32_t)w)) + (uint32_t)(by0 + (int)(k / (uint32_t)w)) * fp.binsX;
+				if (!tileOwned(fp, tile)) tile = kNoTile;
+			}
+			const uint32_t slot = warpTileAdd<SCATTER>(counters, tile);
+			if (SCATTER && tile != kNoTile) binIds[__ldg(tileOffset + tile) + slot] = prim;
+		}
+	}
+}
+
 // triangle setup: one CTA per chunk of 256 triangles of one mesh.
 // cull (CUDARenderer.cu:760-777), frustum reject (CUDAROPs.cu:147-178), screen mapping (:88-97),
 // inflated bbox (:180-200), bin rectangle (CUDARenderer.cu:935-942), per-tile counts.
@@ -262,17 +320,8 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 			nTiles = 0;
 		}
 	}
-	const uint32_t steps = __reduce_max_sync(0xFFFFFFFFu, nTiles);
-	for (uint32_t k = 0; k < steps; ++k)
-	{
-		uint32_t tile = kNoTile;
-		if (k < nTiles)
-		{
-			tile = (uint32_t)(bx0 + (int)(k % (uint32_t)w)) + (uint32_t)(by0 + (int)(k / (uint32_t)w)) * fp.binsX;
-			if (!tileOwned(fp, tile)) tile = kNoTile;
-		}
-		warpTileAdd<false>(tileCount, tile);
-	}
+	(void)w;
+	warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
 }
 
 // cooperative binning of triangles with large rectangles (full-screen quads ...): one CTA per
@@ -310,9 +359,9 @@ __global__ void __launch_bounds__(256) bin_big_kernel(
 constexpr uint32_t kScanPerThread = 32;
 __global__ void __launch_bounds__(1024) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t nTiles, unsigned long long capacity, uint32_t warpThreshold, uint32_t midThreshold, uint32_t longThreshold,
-	uint32_t* __restrict__ warpTiles, uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
-	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles,[6]=warp-radix tiles*/)
+	uint32_t nTiles, unsigned long long capacity, uint32_t midThreshold, uint32_t longThreshold,
+	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
+	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles; [6] is the run sorter's fallback count*/)
 {
 	if (threadIdx.x < 32)
 	{
@@ -322,8 +371,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 	}
 	__shared__ unsigned long long sWarp[32];
 	__shared__ unsigned long long sCarry;
-	__shared__ uint32_t sLong, sMid, sWarpList;
-	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; sMid = 0; sWarpList = 0; }
+	__shared__ uint32_t sLong, sMid;
+	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; sMid = 0; }
 	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (uint32_t base = 0; base < nTiles; base += 1024 * kScanPerThread)
@@ -393,11 +442,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 			for (uint32_t e = 0; e < 4; ++e)
 			{
 				const uint32_t c = v[q * 4 + e];
-				if (i + e < nTiles && c > warpThreshold)
+				if (i + e < nTiles && c > midThreshold)
 				{
 					if (c > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i + e;
-					else if (c > midThreshold) midTiles[atomicAdd(&sMid, 1u)] = i + e;
-					else warpTiles[atomicAdd(&sWarpList, 1u)] = i + e;
+					else midTiles[atomicAdd(&sMid, 1u)] = i + e;
 				}
 			}
 		}
@@ -412,7 +460,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 		frameInfo[2] = 0ull;
 		frameInfo[3] = sLong;
 		frameInfo[5] = sMid;
-		frameInfo[6] = sWarpList;
 	}
 }
 
@@ -426,12 +473,12 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
 	const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t nTiles = 0;
-	int bx0 = 0, by0 = 0, w = 1;
+	int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1, w = 1;
 	if (prim < nPrims)
 	{
 		const uint2 rc = __ldg(rects + prim);
 		bx0 = rc.x & 0xFFFF; by0 = rc.y & 0xFFFF;
-		const int bx1 = rc.x >> 16, by1 = rc.y >> 16;
+		bx1 = rc.x >> 16; by1 = rc.y >> 16;
 		if (bx0 <= bx1 && by0 <= by1)
 		{
 			w = bx1 - bx0 + 1;
@@ -439,26 +486,18 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 			if (nTiles > fp.bigRectTiles) nTiles = 0;   // bin_big_kernel
 		}
 	}
-	const uint32_t steps = __reduce_max_sync(0xFFFFFFFFu, nTiles);
-	for (uint32_t k = 0; k < steps; ++k)
-	{
-		uint32_t tile = kNoTile;
-		if (k < nTiles)
-		{
-			tile = (uint32_t)(bx0 + (int)(k % (uint32_t)w)) + (uint32_t)(by0 + (int)(k / (uint32_t)w)) * fp.binsX;
-			if (!tileOwned(fp, tile)) tile = kNoTile;
-		}
-		const uint32_t slot = warpTileAdd<true>(tileCursor, tile);
-		if (tile != kNoTile) binIds[__ldg(tileOffset + tile) + slot] = prim;
-	}
+	(void)w;
+	warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp);
 }
 
 // per-tile sort of the id lists (ascending primitive id = submission order): makes the lists
 // bit-reproducible regardless of the order the scatter atomics were served.
-//  tier 1: one WARP per tile, lists up to 256 entries: bitonic network on 8 keys per lane in
-//          registers, cross-lane steps with shuffles, no shared memory, no block barrier
-//  tier 2: the tiles tile_scan_kernel put on the "mid" work list (257 .. kSortSmall entries), one
-//          CTA per tile, keys in static shared memory
+//  tier 1: one WARP per tile, lists up to kSortWarpRadix entries.  warpBinRects() writes one ascending
+//          run per (warp, tile) and the runs of different warps cover disjoint id ranges, so the list
+//          is sorted by ORDERING THE RUNS by their first key and moving them (bin_sort_runs_kernel).
+//          Tiles where that does not hold (interleaved runs) go to a warp-level radix sort.
+//  tier 2: the tiles tile_scan_kernel put on the "mid" work list (up to kSortSmall entries), one
+//          CTA per tile, block radix sort in static shared memory
 //  tier 3: the "long" work list (up to kSortLarge entries) in dynamic shared memory, one CTA per SM
 //  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
@@ -468,69 +507,100 @@ constexpr int kSortSmall = 4096;     // <= : shared-memory radix, one CTA
 constexpr int kSortLarge = 40960;
 constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
 
-__global__ void __launch_bounds__(256) bin_sort_warp_kernel(
+constexpr int kMaxRuns = 128;
+__global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
-	uint32_t nTiles, const unsigned long long* __restrict__ frameInfo)
+	uint32_t nTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)
 {
+	__shared__ uint32_t sK[8][kSortWarpRadix];
+	__shared__ uint16_t sStart[8][kMaxRuns + 1], sOrder[8][kMaxRuns], sOut[8][kMaxRuns];
 	if (frameInfo[1]) return;
-	const uint32_t tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t tile = blockIdx.x * 8 + warp;
 	if (tile >= nTiles) return;
 	const uint32_t n = tileCount[tile];
-	if (n < 2 || n > (uint32_t)kSortWarp) return;
-	const uint32_t lane = threadIdx.x & 31;
+	if (n < 2 || n > (uint32_t)kSortWarpRadix) return;
 	uint32_t* list = binIds + tileOffset[tile];
-	// virtual element index v = i*32 + lane (coalesced); padding keys sort to the end
-	uint32_t a[8];
-	#pragma unroll
-	for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; a[i] = (v < n) ? list[v] : 0xFFFFFFFFu; }
-	// already sorted? (v, v+1) neighbours: lane+1 of the same i, or lane 0 of i+1
-	bool unsorted = false;
-	#pragma unroll
-	for (int i = 0; i < 8; ++i)
+	uint32_t* K = sK[warp];
+	uint16_t* S = sStart[warp];
+	const unsigned ltMask = (1u << lane) - 1u;
+	// 1. stage the keys, find the ascending runs (a run starts where the previous key is larger)
+	uint32_t runs = 0, carry = 0;
+	for (uint32_t b = 0; b < n; b += 32)
 	{
-		uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, a[i], 1);
-		const uint32_t wrap = __shfl_sync(0xFFFFFFFFu, (i < 7) ? a[(i + 1) & 7] : 0xFFFFFFFFu, 0);
-		if (lane == 31) nxt = wrap;
-		unsorted |= a[i] > nxt;
-	}
-	if (!__any_sync(0xFFFFFFFFu, unsorted)) return;
-	#pragma unroll
-	for (uint32_t k = 2; k <= 256; k <<= 1)
-	{
-		#pragma unroll
-		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		const uint32_t i = b + lane;
+		const uint32_t k = (i < n) ? list[i] : 0xFFFFFFFFu;
+		if (i < n) K[i] = k;
+		uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k, 1);
+		if (lane == 0) prev = carry;
+		const bool start = (i < n) && (i == 0 || prev > k);
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
+		if (start)
 		{
-			if (j >= 32)
-			{
-				const int ji = j >> 5;
-				#pragma unroll
-				for (int i = 0; i < 8; ++i)
-				{
-					const int p = i ^ ji;
-					if (p > i)
-					{
-						const bool up = (((uint32_t)i * 32u) & k) == 0;     // k >= 64 here: direction depends on i only
-						const uint32_t x = a[i], y = a[p];
-						if ((x > y) == up) { a[i] = y; a[p] = x; }
-					}
-				}
-			}
-			else
-			{
-				#pragma unroll
-				for (int i = 0; i < 8; ++i)
-				{
-					const uint32_t v = (uint32_t)i * 32u + lane;
-					const bool up = (v & k) == 0;
-					const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, a[i], j);
-					const bool lower = (lane & j) == 0;
-					a[i] = (lower == up) ? min(a[i], y) : max(a[i], y);
-				}
-			}
+			const uint32_t r = runs + (uint32_t)__popc(m & ltMask);
+			if (r < (uint32_t)kMaxRuns) S[r] = (uint16_t)i;
 		}
+		runs += (uint32_t)__popc(m);
+		carry = __shfl_sync(0xFFFFFFFFu, k, 31);
 	}
-	#pragma unroll
-	for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; if (v < n) list[v] = a[i]; }
+	if (runs == 1) return;                                   // already in canonical order
+	bool fallback = runs > (uint32_t)kMaxRuns;
+	if (!fallback)
+	{
+		if (lane == 0) S[runs] = (uint16_t)n;
+		__syncwarp();
+		// 2. order the runs by their first key (keys are distinct primitive ids)
+		for (uint32_t r = lane; r < runs; r += 32)
+		{
+			const uint32_t head = K[S[r]];
+			uint32_t rank = 0;
+			for (uint32_t q = 0; q < runs; ++q) rank += (K[S[q]] < head) ? 1u : 0u;
+			sOrder[warp][rank] = (uint16_t)r;
+		}
+		__syncwarp();
+		// 3. output position of every run = prefix of the run lengths in that order; the runs must
+		//    cover disjoint id ranges (last key of a run < first key of the next one)
+		uint32_t running = 0;
+		bool bad = false;
+		for (uint32_t b = 0; b < runs; b += 32)
+		{
+			const uint32_t kk = b + lane;
+			uint32_t len = 0, r = 0;
+			if (kk < runs)
+			{
+				r = sOrder[warp][kk];
+				len = (uint32_t)S[r + 1] - (uint32_t)S[r];
+				if (kk + 1 < runs) bad |= K[S[r + 1] - 1] > K[S[sOrder[warp][kk + 1]]];
+			}
+			uint32_t incl = len;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+			if (kk < runs) sOut[warp][r] = (uint16_t)(running + incl - len);
+			running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+		}
+		fallback = __any_sync(0xFFFFFFFFu, bad);
+	}
+	if (fallback)
+	{
+		// interleaved runs (cooperatively binned big triangles, incoherent warps): radix-sort this tile instead
+		if (lane == 0) fallbackTiles[atomicAdd(&frameInfo[6], 1ull)] = tile;
+		return;
+	}
+	__syncwarp();
+	// 4. move every key to its run's output position
+	uint32_t before = 0;
+	for (uint32_t b = 0; b < n; b += 32)
+	{
+		const uint32_t i = b + lane;
+		const bool start = (i < n) && (i == 0 || K[i - 1] > K[i]);
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
+		if (i < n)
+		{
+			const uint32_t r = before + (uint32_t)__popc(m & (ltMask | (1u << lane))) - 1u;
+			list[(uint32_t)sOut[warp][r] + (i - (uint32_t)S[r])] = K[i];
+		}
+		before += (uint32_t)__popc(m);
+	}
 }
 
 // Warp-level stable LSD radix sort of one tile list (257 .. kSortWarpRadix entries): same scheme as the

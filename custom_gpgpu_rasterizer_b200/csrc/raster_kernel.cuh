@@ -376,6 +376,15 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 				const float2 a0 = __ldg(r0 + 5), b0 = __ldg(r0 + 6), a1 = __ldg(r1 + 5), b1 = __ldg(r1 + 6), a2 = __ldg(r2 + 5), b2 = __ldg(r2 + 6);
 				colour = packColour(S(a0.y, a1.y, a2.y), S(b0.x, b1.x, b2.x), S(b0.y, b1.y, b2.y));
 			}
+			else if (fp.visState == 0u && mc.tex[1] < 0)
+			{
+				// diffuse map only: ShadePixelSafe returns the diffuse sample (CUDAROPs.cu:465-468); only uv is needed
+				const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
+				const float2 a0 = __ldg(r0 + 1), b0 = __ldg(r0 + 2), a1 = __ldg(r1 + 1), b1 = __ldg(r1 + 2), a2 = __ldg(r2 + 1), b2 = __ldg(r2 + 2);
+				const float u = S(a0.y, a1.y, a2.y) * wInterp, vv = S(b0.x, b1.x, b2.x) * wInterp;
+				const RGB c = sampleTex(A.textures[mc.tex[0]], u, vv, fp.sampleState);
+				colour = packColour(c.r, c.g, c.b);
+			}
 			else
 			{
 				// transform the three vertices' attributes now (the reference did it for every vertex in VS_Kernel)
