@@ -804,8 +804,8 @@ int b2r_get_counters(b2r_context* c, uint64_t* out, int n)
 	int r = validateFrame(c); if (r) return r;
 	const uint32_t tiles = nBins(c);
 	const uint64_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - c->ownerRank + c->ownerCount - 1) / c->ownerCount : 0;
-	const uint64_t v[7] = { c->lastInfo.frameInfo[0], c->kernelsLaunched, owned, tiles, c->lastInfo.frameInfo[2], c->lastInfo.counters[1], c->lastInfo.frameInfo[4] };
-	for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+	const uint64_t v[8] = { c->lastInfo.frameInfo[0], c->kernelsLaunched, owned, tiles, c->lastInfo.frameInfo[2], c->lastInfo.counters[1], c->lastInfo.frameInfo[4], c->lastInfo.frameInfo[6] };
+	for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
 	return B2R_OK;
 }
 

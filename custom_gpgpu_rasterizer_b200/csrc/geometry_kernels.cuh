@@ -507,7 +507,47 @@ constexpr int kSortSmall = 4096;     // <= : shared-memory radix, one CTA
 constexpr int kSortLarge = 40960;
 constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
 
-constexpr int kMaxRuns = 128;
+// register bitonic network over 256 keys held 8 per lane, virtual index v = i*32 + lane
+__device__ __forceinline__ void warpBitonic256(uint32_t (&a)[8], uint32_t lane)
+{
+	#pragma unroll
+	for (uint32_t k = 2; k <= 256; k <<= 1)
+	{
+		#pragma unroll
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			if (j >= 32)
+			{
+				const int ji = j >> 5;
+				#pragma unroll
+				for (int i = 0; i < 8; ++i)
+				{
+					const int p = i ^ ji;
+					if (p > i)
+					{
+						const bool up = (((uint32_t)i * 32u) & k) == 0;     // k >= 64 here: direction depends on i only
+						const uint32_t x = a[i], y = a[p];
+						if ((x > y) == up) { a[i] = y; a[p] = x; }
+					}
+				}
+			}
+			else
+			{
+				#pragma unroll
+				for (int i = 0; i < 8; ++i)
+				{
+					const uint32_t v = (uint32_t)i * 32u + lane;
+					const bool up = (v & k) == 0;
+					const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, a[i], j);
+					const bool lower = (lane & j) == 0;
+					a[i] = (lower == up) ? min(a[i], y) : max(a[i], y);
+				}
+			}
+		}
+	}
+}
+
+constexpr int kMaxRuns = 64;
 __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
 	uint32_t nTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)
@@ -524,8 +564,11 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	uint32_t* K = sK[warp];
 	uint16_t* S = sStart[warp];
 	const unsigned ltMask = (1u << lane) - 1u;
-	// 1. stage the keys, find the ascending runs (a run starts where the previous key is larger)
+	// 1. stage the keys and find the runs.  A run = the ids one scatter warp wrote: it ends where the
+	//    next key is smaller or belongs to another 32-aligned id group (warpBinRects: one ascending run
+	//    per warp and tile, and a warp's ids are one aligned group of 32)
 	uint32_t runs = 0, carry = 0;
+	bool descent = false;
 	for (uint32_t b = 0; b < n; b += 32)
 	{
 		const uint32_t i = b + lane;
@@ -533,7 +576,8 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 		if (i < n) K[i] = k;
 		uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k, 1);
 		if (lane == 0) prev = carry;
-		const bool start = (i < n) && (i == 0 || prev > k);
+		const bool start = (i < n) && (i == 0 || prev > k || (prev >> 5) != (k >> 5));
+		descent |= (i < n) && i > 0 && prev > k;
 		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
 		if (start)
 		{
@@ -543,7 +587,19 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 		runs += (uint32_t)__popc(m);
 		carry = __shfl_sync(0xFFFFFFFFu, k, 31);
 	}
-	if (runs == 1) return;                                   // already in canonical order
+	if (!__any_sync(0xFFFFFFFFu, descent)) return;           // already in canonical order
+	__syncwarp();
+	if (n <= 256 && runs > 24)
+	{
+		// short list made of many short runs (e.g. cooperatively binned big triangles): sort the keys directly
+		uint32_t a[8];
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; a[i] = (v < n) ? K[v] : 0xFFFFFFFFu; }
+		warpBitonic256(a, lane);
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; if (v < n) list[v] = a[i]; }
+		return;
+	}
 	bool fallback = runs > (uint32_t)kMaxRuns;
 	if (!fallback)
 	{
@@ -582,7 +638,7 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	}
 	if (fallback)
 	{
-		// interleaved runs (cooperatively binned big triangles, incoherent warps): radix-sort this tile instead
+		// interleaved or too many runs (incoherent warps, big triangles in a long list): radix-sort this tile instead
 		if (lane == 0) fallbackTiles[atomicAdd(&frameInfo[6], 1ull)] = tile;
 		return;
 	}
@@ -592,7 +648,7 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	for (uint32_t b = 0; b < n; b += 32)
 	{
 		const uint32_t i = b + lane;
-		const bool start = (i < n) && (i == 0 || K[i - 1] > K[i]);
+		const bool start = (i < n) && (i == 0 || K[i - 1] > K[i] || (K[i - 1] >> 5) != (K[i] >> 5));
 		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
 		if (i < n)
 		{

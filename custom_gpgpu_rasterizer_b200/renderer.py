@@ -217,9 +217,9 @@ class Renderer:
         return dict(zip(_lib.STAGE_NAMES, [float(x) for x in out])), frames.value
 
     def counters(self) -> Dict[str, int]:
-        out = (C.c_uint64 * 7)()
-        self._check(lib.b2r_get_counters(self._ctx, out, 7))
-        keys = ("pairs", "kernels_launched", "tiles_owned", "num_bins", "unsorted_tiles", "big_triangles", "fragments")
+        out = (C.c_uint64 * 8)()
+        self._check(lib.b2r_get_counters(self._ctx, out, 8))
+        keys = ("pairs", "kernels_launched", "tiles_owned", "num_bins", "unsorted_tiles", "big_triangles", "fragments", "sort_fallback_tiles")
         return dict(zip(keys, [int(x) for x in out]))
 
     def set_stream(self, stream_ptr: int):
