@@ -188,7 +188,7 @@ def run_b200(args, scene):
     gather = None
     if world > 1:
         from custom_gpgpu_rasterizer_b200.multi_gpu import SortFirstGather
-        gather = SortFirstGather(r, scene, rank, world, stream)
+        gather = SortFirstGather(r, scene, rank, world, stream, mode=args.gather)
 
     def frame():
         r.render(cam, scene.cull, scene.sample, scene.vis, sync=False)
@@ -262,6 +262,8 @@ def run_b200(args, scene):
     barrier()
 
     if rank != 0:
+        if gather is not None:
+            gather.close()
         r.close()
         if world > 1:
             dist.destroy_process_group()
@@ -291,7 +293,7 @@ def run_b200(args, scene):
         "metric": "frames/s at 4K (device-timed)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, NCCL gather to rank 0")),
+        "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + ("NCCL gather of packed tiles to rank 0" if args.gather == "nccl" else "peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)"))),
         "mtris_per_s": scene.n_tris * fps / 1e6,
         "visible_triangles": visible, "tile_pairs": counters["pairs"], "fragments": c2["fragments"], "covered_pixels": covered_px,
         "stages_ms": stages, "stages": per_stage,
@@ -367,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small"])
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="sort-first composition: NCCL gather of packed tiles, or peer-to-peer ROP write-back over NVLink")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
     args = ap.parse_args()

@@ -27,7 +27,7 @@ SAMPLE_POINT, SAMPLE_LINEAR = 0, 1
 VIS_PBR, VIS_DEPTH, VIS_NORMAL = 0, 1, 2
 TOPOLOGY_TRIANGLE_LIST, TOPOLOGY_TRIANGLE_STRIP = 0, 1
 OPT_FILL_RULE_TOP_LEFT, OPT_TILE_OWNER_RANK, OPT_TILE_OWNER_COUNT = 1, 2, 3
-OPT_DEBUG_SURFACES, OPT_STAGE_TIMERS, OPT_SORT_BINS, OPT_COUNT_FRAGMENTS = 4, 5, 6, 7
+OPT_DEBUG_SURFACES, OPT_STAGE_TIMERS, OPT_SORT_BINS, OPT_COUNT_FRAGMENTS, OPT_PACKED_OUTPUT = 4, 5, 6, 7, 8
 STAGE_NAMES = ("vertex", "setup", "bin_scan", "bin_scatter", "bin_sort", "raster_shade", "total")
 NUM_STAGES = 7
 
@@ -62,6 +62,11 @@ ABI = {
     "b2r_set_stream": (_i32, [_vp, _vp]),
     "b2r_device_surfaces": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "b2r_bind_framebuffer": (_i32, [_vp, _vp]),
+    "b2r_packed_size": (_i32, [_vp, _i32, _i32, _u64p]),
+    "b2r_unpack_tiles": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "b2r_ipc_export": (_i32, [_vp, _vp, _vp]),
+    "b2r_ipc_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    "b2r_ipc_close": (_i32, [_vp, _vp]),
 }
 for _name, (_res, _args) in ABI.items():
     _fn = getattr(lib, _name)

@@ -87,7 +87,7 @@ struct b2r_context
 	std::string error;
 
 	// options
-	int fillTopLeft = 1, ownerRank = 0, ownerCount = 1, debugSurfaces = 0, stageTimers = 0, sortBins = 1;
+	int fillTopLeft = 1, ownerRank = 0, ownerCount = 1, debugSurfaces = 0, stageTimers = 0, sortBins = 1, packedOutput = 0;
 
 	// scene
 	std::vector<HostMesh> meshes;
@@ -257,6 +257,7 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.debugSurfaces = (uint32_t)c->debugSurfaces;
 	fp.bigRectTiles = 64;
 	fp.nMeshes = (uint32_t)c->meshes.size();
+	fp.packedOutput = (uint32_t)c->packedOutput;
 	return fp;
 }
 
@@ -662,6 +663,7 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_STAGE_TIMERS: c->stageTimers = value ? 1 : 0; break;
 	case B2R_OPT_SORT_BINS: c->sortBins = value ? 1 : 0; break;
 	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
+	case B2R_OPT_PACKED_OUTPUT: c->packedOutput = value ? 1 : 0; break;
 	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
 	}
 	if (c->ownerRank >= c->ownerCount) { /* tolerated while the pair is being set; checked at render */ }
@@ -826,11 +828,67 @@ int b2r_device_surfaces(b2r_context* c, void** framebuffer, void** depth)
 	return B2R_OK;
 }
 
-int b2r_bind_framebuffer(b2r_context* c, void* devicePtr)
+static uint32_t ownedTiles(uint32_t tiles, uint32_t rank, uint32_t count)
+{
+	return tiles > rank ? (tiles - rank + count - 1) / count : 0;
+}
+
+int b2r_packed_size(b2r_context* c, int rank, int count, uint64_t* pixels)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!pixels || count < 1 || rank < 0 || rank >= count) return fail(c, B2R_E_INVALID, "bad rank/count");
+	const FrameParams fp = makeParams(c, c->last);
+	*pixels = (uint64_t)ownedTiles(nBins(c), (uint32_t)rank, (uint32_t)count) * fp.subX * fp.subY * kTile * kTile;
+	return B2R_OK;
+}
+
+int b2r_unpack_tiles(b2r_context* c, const void* packed, int rank, int count, void* dstFramebuffer)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!packed || count < 1 || rank < 0 || rank >= count) return fail(c, B2R_E_INVALID, "bad unpack arguments");
+	CU(c, cudaSetDevice(c->device));
+	const FrameParams fp = makeParams(c, c->last);
+	const uint32_t owned = ownedTiles(nBins(c), (uint32_t)rank, (uint32_t)count);
+	if (!owned) return B2R_OK;
+	uint32_t* dst = dstFramebuffer ? (uint32_t*)dstFramebuffer : c->dFramebuffer;
+	unpack_tiles_kernel<<<dim3(owned, fp.subX * fp.subY), kTile * kTile, 0, c->stream>>>((const uint32_t*)packed, dst, (uint32_t)rank, (uint32_t)count, fp);
+	CU(c, cudaGetLastError());
+	return B2R_OK;
+}
+
+int b2r_ipc_export(b2r_context* c, void* devicePtr, void* handle64)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!handle64) return fail(c, B2R_E_INVALID, "null handle");
+	CU(c, cudaSetDevice(c->device));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, devicePtr ? devicePtr : (void*)c->dFramebuffer));
+	return B2R_OK;
+}
+
+int b2r_ipc_open(b2r_context* c, const void* handle64, void** devicePtr)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!handle64 || !devicePtr) return fail(c, B2R_E_INVALID, "null handle");
+	CU(c, cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+	CU(c, cudaIpcOpenMemHandle(devicePtr, h, cudaIpcMemLazyEnablePeerAccess));
+	return B2R_OK;
+}
+
+int b2r_ipc_close(b2r_context* c, void* devicePtr)
 {
 	if (!c) return B2R_E_INVALID;
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
+	CU(c, cudaIpcCloseMemHandle(devicePtr));
+	return B2R_OK;
+}
+
+int b2r_bind_framebuffer(b2r_context* c, void* devicePtr)
+{
+	if (!c) return B2R_E_INVALID;
+	// takes effect for frames enqueued from now on; frames already in flight keep their target
 	c->boundFramebuffer = (uint32_t*)devicePtr;
 	return B2R_OK;
 }

@@ -415,13 +415,34 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 			}
 		}
 	}
-	A.framebuffer[pix] = colour;
+	// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
+	// gathered with one contiguous NCCL transfer / written straight into a peer's memory
+	if (fp.packedOutput) A.framebuffer[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * (kTile * kTile) + tid] = colour;
+	else A.framebuffer[pix] = colour;
 	A.depth[pix] = depthOut;
 	if (fp.debugSurfaces)
 	{
 		A.zSurface[pix] = zOut;
 		A.winnerSurface[pix] = prim;
 	}
+}
+
+
+// sort-first composition on the gathering rank: scatter one rank's packed tile-major colours back
+// into the row-major framebuffer (tile owner = tile index mod count)
+__global__ void __launch_bounds__(kTile * kTile) unpack_tiles_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ framebuffer,
+	uint32_t rank, uint32_t count, FrameParams fp)
+{
+	const uint32_t bin = rank + blockIdx.x * count;
+	const uint32_t binX = bin % fp.binsX, binY = bin / fp.binsX;
+	const uint32_t subX = blockIdx.y % fp.subX, subY = blockIdx.y / fp.subX;
+	const int tid = threadIdx.x;
+	const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
+	const int ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
+	const int ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
+	const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
+	if (px < ex && py < ey)
+		framebuffer[(size_t)px + (size_t)py * fp.width] = packed[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * (kTile * kTile) + tid];
 }
 
 }

@@ -63,7 +63,10 @@ enum
 	B2R_OPT_SORT_BINS = 6,
 	/* count the fragments that pass the inside and z-range tests (the F of the fill/ROP roofline
 	 * contract) into counter [6]; an instrumented variant of the raster kernel. Default 0. */
-	B2R_OPT_COUNT_FRAGMENTS = 7
+	B2R_OPT_COUNT_FRAGMENTS = 7,
+	/* sort-first: write the colours of the owned tiles tile-major (owned tile k, sub-tile s at
+	 * (k*S + s)*256 pixels) instead of row-major, so one rank's share is one contiguous buffer. Default 0. */
+	B2R_OPT_PACKED_OUTPUT = 8
 };
 
 /* stage indices for b2r_get_stage_ms */
@@ -162,6 +165,19 @@ int b2r_device_surfaces(b2r_context* ctx, void** framebuffer, void** depth);
 /* redirect the ROP write-back of later frames into caller-provided device memory
  * (e.g. a peer GPU's framebuffer mapped over NVLink); NULL restores the internal surface */
 int b2r_bind_framebuffer(b2r_context* ctx, void* device_ptr);
+
+
+/* ---- multi-GPU (sort-first) helpers; the reference is single-GPU (main.cpp:397-399), nothing replaced ----
+ * pixels of the packed buffer a rank with this ownership writes under B2R_OPT_PACKED_OUTPUT */
+int b2r_packed_size(b2r_context* ctx, int rank, int count, uint64_t* pixels);
+/* on the gathering rank: scatter one rank's packed colours into a row-major framebuffer
+ * (dst_framebuffer = NULL: this context's own surface); runs on the context's stream */
+int b2r_unpack_tiles(b2r_context* ctx, const void* packed_device, int rank, int count, void* dst_framebuffer);
+/* CUDA IPC so that ranks in other processes can write their tiles straight into the gathering
+ * rank's memory over NVLink (device_ptr = NULL exports this context's framebuffer); handle = 64 bytes */
+int b2r_ipc_export(b2r_context* ctx, void* device_ptr, void* handle64);
+int b2r_ipc_open(b2r_context* ctx, const void* handle64, void** device_ptr);
+int b2r_ipc_close(b2r_context* ctx, void* device_ptr);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,78 @@
+"""CPU (gloo, world_size 2) tests of the sort-first host logic: tile ownership, the packed tile-major
+layout (numpy models of B2R_OPT_PACKED_OUTPUT / b2r_unpack_tiles) and the gather plumbing."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from custom_gpgpu_rasterizer_b200 import multi_gpu as mg  # noqa: E402
+
+
+def test_ownership_partitions_all_bins():
+    for n_bins, world in [(32400, 8), (8160, 3), (7, 4), (1, 2)]:
+        seen = np.concatenate([mg.owned_bins(n_bins, r, world) for r in range(world)])
+        assert np.array_equal(np.sort(seen), np.arange(n_bins))
+        sizes = [len(mg.owned_bins(n_bins, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("w,h,bw,bh", [(64, 48, 16, 16), (70, 37, 16, 16), (160, 96, 80, 48)])
+def test_pack_unpack_roundtrip(w, h, bw, bh):
+    bins_x, bins_y = (w + bw - 1) // bw, (h + bh - 1) // bh
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 1 << 32, (h, w), dtype=np.uint64).astype(np.uint32)
+    world = 3
+    out = np.zeros_like(img)
+    for r in range(world):
+        packed = mg.pack_reference(img, r, world, bins_x, bins_y, bw, bh)
+        sub = ((bw + 15) // 16) * ((bh + 15) // 16)
+        assert packed.size == mg.packed_pixels(bins_x * bins_y, r, world, sub)
+        mg.unpack_reference(packed, out, r, world, bins_x, bins_y, bw, bh)
+    assert np.array_equal(out, img)
+
+
+def _worker(rank, world, port, w, h, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bins_x, bins_y = (w + 15) // 16, (h + 15) // 16
+        rng = np.random.default_rng(7)
+        full = rng.integers(0, 1 << 31, (h, w), dtype=np.int64).astype(np.int32)   # the frame every rank would agree on
+        n_bins = bins_x * bins_y
+        max_px = max(mg.packed_pixels(n_bins, k, world) for k in range(world))
+        local = np.zeros(max_px, np.int32)
+        mine = mg.pack_reference(full, rank, world, bins_x, bins_y)
+        local[: mine.size] = mine
+        bufs = mg.gather_packed(torch.from_numpy(local), rank, world, dst=0)
+        if rank == 0:
+            out = np.zeros_like(full)
+            for k in range(world):
+                mg.unpack_reference(bufs[k].numpy(), out, k, world, bins_x, bins_y)
+            q.put(bool(np.array_equal(out, full)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_gather_composes_full_frame():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 100, 70, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
