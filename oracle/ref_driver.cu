@@ -57,14 +57,25 @@ template <typename T> void WriteN(FILE* f, const T* src, size_t n) { fwrite(src,
 
 int Fail(const char* msg) { fprintf(stderr, "ref_render: %s\n", msg); return 2; }
 
-int Parse(const char* objPath, int invertY, const char* outPath)
+int Parse(const char* objPath, int invertY, const char* outPath, bool useVectorOverload)
 {
 	ObjParser parser{};
 	if (!parser.OpenFile(objPath))
 		return Fail("cannot open obj");
 	parser.SetInvertYAxis(invertY != 0);
 	IVertex* pV{}; unsigned nV{}; unsigned* pI{}; unsigned nI{}; short vertexType{};
-	parser.ReadFromObjFile(pV, nV, pI, nI, vertexType);
+	if (useVectorOverload)
+	{
+		// ObjParser.cpp:100-108 / 381-548: the std::vector overload (the raw-pointer one sizes its buffer by the
+		// face count and overruns it for meshes with more unique vertices than faces, e.g. vehicle.obj)
+		std::vector<IVertex> v; std::vector<unsigned int> idx;
+		parser.ReadFromObjFile(v, idx, vertexType);
+		nV = (unsigned)v.size(); nI = (unsigned)idx.size();
+		pV = new IVertex[nV]; pI = new unsigned[nI];
+		memcpy((void*)pV, v.data(), sizeof(IVertex) * nV); memcpy(pI, idx.data(), 4 * (size_t)nI);
+	}
+	else
+		parser.ReadFromObjFile(pV, nV, pI, nI, vertexType);
 	FILE* f = fopen(outPath, "wb");
 	if (!f) return Fail("cannot open output");
 	const unsigned hdr[4] = { 0x50523242u /*B2RP*/, nV, nI, (unsigned)(unsigned short)vertexType };
@@ -80,8 +91,8 @@ int Parse(const char* objPath, int invertY, const char* outPath)
 
 int main(int argc, char** argv)
 {
-	if (argc >= 5 && std::string(argv[1]) == "parse")
-		return Parse(argv[2], atoi(argv[3]), argv[4]);
+	if (argc >= 5 && (std::string(argv[1]) == "parse" || std::string(argv[1]) == "parsev"))
+		return Parse(argv[2], atoi(argv[3]), argv[4], std::string(argv[1]) == "parsev");
 	if (argc < 4)
 		return Fail("usage: ref_render render|stages scene.b2rs out.b2ro | parse file.obj invertY out.bin");
 	const bool stages = std::string(argv[1]) == "stages";

@@ -1,0 +1,148 @@
+"""CPU: the C-ABI library loads and exports everything include/b2r.h declares (no compute without a GPU),
+and the host-side veneer (Camera, Mesh world matrix, ObjParser, PNG decode) reproduces the reference:
+camera/world matrices against the oracle's restatement, ObjParser against buffers produced by the
+reference's own parser (tests/golden/objparser_reference.npz, tools/make_golden.py parser)."""
+import ctypes as C
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_cases
+import oracle_lib
+import parity
+from custom_gpgpu_rasterizer_b200 import _lib, scenes
+from custom_gpgpu_rasterizer_b200.renderer import Renderer, B2RError, decode_png, host_camera, host_mesh_world, parse_obj
+from custom_gpgpu_rasterizer_b200.scenefile import Scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    declared = set(re.findall(r"\b(b2r_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"{name} declared in include/b2r.h but not exported by libb2r.so"
+    assert declared == set(_lib.ABI), f"ctypes table out of sync: {declared ^ set(_lib.ABI)}"
+
+
+def test_no_cpu_fallback():
+    if _has_gpu():
+        pytest.skip("this check is for machines without a CUDA device")
+    with pytest.raises(B2RError) as e:
+        Renderer(64, 64)
+    assert e.value.code == _lib.B2R_E_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_create_rejects_bad_resolution():
+    ctx = C.c_void_p()
+    assert _lib.lib.b2r_create(0, 0, 10, C.byref(ctx)) == _lib.B2R_E_INVALID
+    assert _lib.lib.b2r_create(0, 40000, 10, C.byref(ctx)) == _lib.B2R_E_INVALID
+    assert b"16-bit" in _lib.lib.b2r_last_error(None)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(pos=(0, 1, 5), fov=45.0, w=640, h=480, near=0.1, far=100.0, pitch=0.0, yaw=0.0),          # main.cpp:422
+    dict(pos=(0, 5, 65), fov=45.0, w=1920, h=1080, near=0.1, far=100.0, pitch=0.0, yaw=0.0),       # main.cpp:421
+    dict(pos=(0, 0, 68), fov=45.0, w=3840, h=2160, near=0.1, far=100.0, pitch=0.0, yaw=0.0),       # config 3
+    dict(pos=(0, 250, 700), fov=45.0, w=1920, h=1080, near=1.0, far=2000.0, pitch=-19.654, yaw=123.4),   # config 5 style
+    dict(pos=(3, -2, 9), fov=70.0, w=333, h=217, near=0.5, far=50.0, pitch=12.5, yaw=-40.0),
+])
+def test_camera_matches_oracle_restatement(cfg):
+    cam = host_camera(cfg["pos"], cfg["fov"], cfg["w"], cfg["h"], cfg["near"], cfg["far"], cfg["pitch"], cfg["yaw"])
+    sc = Scene(cfg["w"] - cfg["w"] % 16 or 16, cfg["h"] - cfg["h"] % 16 or 16, cam_pos=cfg["pos"], fov_deg=cfg["fov"], near=cfg["near"], far=cfg["far"],
+               pitch_deg=cfg["pitch"], yaw_deg=cfg["yaw"])
+    sc.width, sc.height = cfg["w"], cfg["h"]
+    o = oracle_lib.render(sc)
+    for k in ("view_proj", "view", "proj", "cam_pos", "cam_fwd"):
+        assert np.array_equal(parity.bits(cam[k]), parity.bits(o[k])), k
+    # projection structure of Camera.cpp:97-108: m(3,3) stays 1 -> w_clip = -z_view + 1
+    proj = cam["proj"].reshape(4, 4).T
+    assert proj[3, 3] == 1.0 and proj[3, 2] == -1.0
+
+
+def test_mesh_world_is_translated_twice_like_cudamesh():
+    w = host_mesh_world((3.0, -2.0, 7.5)).reshape(4, 4).T
+    assert np.array_equal(w[:3, 3], np.float32([6.0, -4.0, 15.0]))       # Mesh.cpp:29 + CUDAMesh.cpp:16-18
+    wv = host_mesh_world((3.0, -2.0, 7.5), vector_ctor=True).reshape(4, 4).T
+    assert np.array_equal(wv[:3, 3], np.float32([12.0, -8.0, 30.0]))    # copying ctor translates twice (Mesh.cpp:4-13), CUDAMesh doubles it again
+    sc = Scene(64, 64, [scenes.MeshData(scenes.make_vertices([(0, 0, 0), (1, 0, 0), (0, 1, 0)]), np.arange(3), position=(3.0, -2.0, 7.5))])
+    assert np.array_equal(oracle_lib.render(sc)["meshes"][0]["world"], host_mesh_world((3.0, -2.0, 7.5)))
+
+
+def _same_buffers(v, i, gv, gi):
+    assert v.shape == gv.shape and i.shape == gi.shape, (v.shape, gv.shape, i.shape, gi.shape)
+    assert np.array_equal(i, gi), "index buffer differs"
+    assert np.array_equal(v.view(np.uint32), gv.view(np.uint32)), f"vertex buffer differs at rows {np.nonzero((v.view(np.uint32) != gv.view(np.uint32)).any(1))[0][:8]}"
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases.obj_cases()))
+@pytest.mark.parametrize("flavour", ["pointer", "vector"])
+def test_objparser_matches_reference_parser(name, flavour):
+    g = np.load(os.path.join(GOLD, "objparser_reference.npz"))
+    text, invert = golden_cases.obj_cases()[name]
+    key = name if flavour == "pointer" else name + "_vec"
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "mesh.obj")
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        v, i, vt = parse_obj(p, invert, pointer_flavour=(flavour == "pointer"))
+    assert vt == int(g[key + "_t"][0])
+    _same_buffers(v, i, g[key + "_v"], g[key + "_i"])
+
+
+@pytest.mark.parametrize("name,invert,flavour", [("vehicle", True, "vector"), ("tuktuk", True, "vector"), ("lowpoly_bunny", False, "pointer")])
+def test_objparser_on_the_reference_meshes(name, invert, flavour):
+    """The reference's bundled meshes (read from /root/reference when it is mounted) against the stored output of the
+    reference parser: 12 965 vertices / 34 914 indices for vehicle.obj."""
+    path = f"/root/reference/CustomCUDARasterizer/Resources/{name}.obj"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    g = np.load(os.path.join(GOLD, "objparser_reference.npz"))
+    v, i, vt = parse_obj(path, invert, pointer_flavour=(flavour == "pointer"))
+    assert vt == int(g[f"res_{name}_t"][0])
+    _same_buffers(v, i, g[f"res_{name}_v"], g[f"res_{name}_i"])
+
+
+def test_objparser_rejects_other_extensions():
+    with pytest.raises(FileNotFoundError):
+        parse_obj("/tmp/nothing.ply", True)
+
+
+def test_png_decoder_matches_pil():
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    with tempfile.TemporaryDirectory() as td:
+        for mode, ch in (("RGBA", 4), ("RGB", 3)):
+            arr = rng.integers(0, 256, (37, 53, ch), dtype=np.uint8)
+            p = os.path.join(td, f"t_{mode}.png")
+            Image.fromarray(arr, mode).save(p)
+            px = decode_png(p)
+            want = arr[..., 0].astype(np.uint32) | (arr[..., 1].astype(np.uint32) << 8) | (arr[..., 2].astype(np.uint32) << 16)
+            want |= (arr[..., 3].astype(np.uint32) << 24) if ch == 4 else np.uint32(255 << 24)
+            assert np.array_equal(px, want)
+
+
+def test_scene_blob_layout_is_stable():
+    sc = scenes.random_triangles_scene(64, 48, 5, seed=1, textured=True)
+    blob = sc.to_blob()
+    assert blob[:4] == b"B2RS" and len(blob) == 92 + sum(8 + t.size * 4 for t in sc.textures) + sum(40 + m.vertices.nbytes + m.indices.nbytes for m in sc.meshes)
+
+
+def test_synthetic_workloads_have_the_documented_shape():
+    pos, nrm, uv, tris = scenes.uv_sphere(81, 100)
+    assert pos.shape[0] == 8282 and tris.shape[0] == 16000
+    sc = scenes.fill_quads_scene(3840, 2160, layers=64)
+    assert sc.n_tris == 128 and sc.n_vertices == 256               # config 4
