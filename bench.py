@@ -24,6 +24,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 from custom_gpgpu_rasterizer_b200 import scenes  # noqa: E402  (numpy only)
 
@@ -241,6 +244,33 @@ def run_b200(args, scene):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
 
+    # ---- view-parallel mode (N > 1): every rank renders complete, independent frames - no data-path collective
+    view_parallel = None
+    if world > 1:
+        gather.close()
+        r.bind_framebuffer(None)
+        r.set_option(_lib.OPT_PACKED_OUTPUT, 0)
+        r.set_option(_lib.OPT_TILE_OWNER_COUNT, 1)
+        r.set_option(_lib.OPT_TILE_OWNER_RANK, 0)
+        for _ in range(3):
+            r.render(cam, scene.cull, scene.sample, scene.vis, sync=False)
+        r.sync()
+        barrier()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            v0.record(stream)
+            for _ in range(args.steps):
+                r.render(cam, scene.cull, scene.sample, scene.vis, sync=False)
+            v1.record(stream)
+        barrier()
+        vms = torch.tensor([v0.elapsed_time(v1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(vms, op=dist.ReduceOp.MAX)
+        view_parallel = {"value": world * args.steps / (float(vms.item()) / 1e3), "unit": "frames/s", "scaling": "weak",
+                         "note": "independent views: every rank renders whole frames of the same scene, no communication; max over ranks"}
+        r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
+        r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
+        gather = None
+
     # ---- per-stage device times over K more frames (CUDA events recorded between the stages on the same stream)
     r.set_option(_lib.OPT_STAGE_TIMERS, 1)
     r.stage_ms_mean(reset=True)
@@ -308,6 +338,8 @@ def run_b200(args, scene):
         "load_scene_s": load_s,
         "clocks": clocks.summary(),
     }
+    if view_parallel is not None:
+        line["view_parallel"] = view_parallel
     if world == 1 and not args.no_cpu_baseline:
         mean_s, _ = cpu_reference_arm(scene, 3, 1)
         line["cpu_baseline"] = {"value": 1.0 / mean_s, "unit": "frames/s", "cores": 1, "kind": "port",
