@@ -387,13 +387,20 @@ int enqueueFrame(b2r_context* c)
 		if (owned)
 		{
 			const dim3 grid(owned, fp.subX * fp.subY);
-			const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0);
+			// light variant when the frame cannot reach the texture / visualiser paths
+			bool anyDiffuse = rc.vis != 0;
+			for (const HostMesh& hm : c->meshes) anyDiffuse |= texValid(c, hm.texIds[0]);
+			const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (anyDiffuse ? 4 : 0);
 			switch (variant)
 			{
-			case 0: raster_shade_kernel<false, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 1: raster_shade_kernel<true, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 2: raster_shade_kernel<false, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			default: raster_shade_kernel<true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 0: raster_shade_kernel<false, false, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 1: raster_shade_kernel<true, false, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 2: raster_shade_kernel<false, true, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 3: raster_shade_kernel<true, true, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 4: raster_shade_kernel<false, false, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 5: raster_shade_kernel<true, false, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 6: raster_shade_kernel<false, true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			default: raster_shade_kernel<true, true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
 			}
 			++c->kernelsLaunched;
 		}

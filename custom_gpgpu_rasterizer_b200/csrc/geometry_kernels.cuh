@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 			}
 			r.cbX = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
 			r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
+			// per-triangle constants of the raster kernel's fragment test, computed here where ALU is free:
+			// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn) ...
+			r.rcpArea = refinedReciprocal(r.area);
+			r.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
+			// ... and a conservative lower bound of the integer depth: weights are in [0, 1 + few ulp] and
+			// sum to 1 +- few ulp, so z >= min(z_i) - small; anything non-finite or negative means "no bound"
+			const float zb = fminf(fminf(r.z0, r.z1), r.z2) * 0.999999f - 1e-9f;
+			r.zLow = (zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
+			r.pad = 0;
 			records[prim] = r;
 			bx0 = clampi(xMin / (int)fp.binW, 0, (int)fp.binsX);
 			by0 = clampi(yMin / (int)fp.binH, 0, (int)fp.binsY);

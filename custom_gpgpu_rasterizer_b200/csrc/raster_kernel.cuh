@@ -54,27 +54,6 @@ struct Bary { float b0, b1, b2, z; };
 
 __device__ __forceinline__ bool topLeftEdge(float ex, float ey) { return ey > 0.f || (ey == 0.f && ex < 0.f); }
 
-// IEEE division w / area with the reciprocal hoisted out of the pixel loop.
-// div.rn.f32 on sm_100a is: r = MUFU.RCP(b); r' = fma(r, fma(-b, r, 1), r); q = fma(a, r', 0);
-// q' = fma(r', fma(-b, q, a), q), plus an FCHK range test that diverts zero / denormal / huge
-// operands to a slow path.  r' depends on the divisor only, so it is computed once per triangle;
-// the quotient sequence below is then instruction-for-instruction the fast path of div.rn.
-// Operands outside a conservative exponent window take __fdiv_rn (tests/test_gpu_units.py checks
-// bit-equality against __fdiv_rn on 2^32 random operand pairs).
-__device__ __forceinline__ float refinedReciprocal(float b)
-{
-	float r;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-	return fmaf(r, fmaf(-b, r, 1.f), r);
-}
-__device__ __forceinline__ float divByArea(float a, float area, float rcp)
-{
-	const float q = fmaf(a, rcp, 0.f);
-	return fmaf(rcp, fmaf(-area, q, a), q);
-}
-constexpr float kDivLo = 2.5243549e-29f;   // 2^-95
-constexpr float kDivHi = 3.9614081e+28f;   // 2^95
-
 // IsPixelInTriangle + weights + depth of RasterizePixelAtomic (CUDAROPs.cu:128-145, 333-345, 386).
 // Returns false if the fragment is not produced.  zi = cvt.rzi.s32.f32(z * 2^31).
 template <bool TOPLEFT>
@@ -115,15 +94,8 @@ __device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, 
 	t.eBx = r.x2 - r.x1; t.eBy = r.y2 - r.y1;
 	t.eCx = r.x0 - r.x2; t.eCy = r.y0 - r.y2;
 	t.prim = prim;
-	// hoisted division only for quotients in [2^-64, ~1] with a sane divisor; everything else uses __fdiv_rn
-	t.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
+	t.divLo = r.divLo; t.rcpArea = r.rcpArea; t.zLow = r.zLow;
 	t.yExtent = 0;
-	t.rcpArea = refinedReciprocal(r.area);
-	// weights are in [0, 1 + few ulp] and sum to 1 +- few ulp, so z >= min(z_i) - small; anything
-	// non-finite or negative falls back to "no bound"
-	const float zMin = fminf(fminf(r.z0, r.z1), r.z2);
-	const float zb = zMin * 0.999999f - 1e-9f;
-	t.zLow = (zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
 }
 
 // ---- texture sampling (CUDATextureSampler.cuh:80-191) -------------------------------------
@@ -228,8 +200,11 @@ __device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& 
 constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
 constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are rasterised by one thread
 
-template <bool TOPLEFT, bool COUNT>
-__global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterArgs A, FrameParams fp)
+// TEXTURED = false is the light variant for frames in which no mesh has a diffuse map and the
+// visualisation is PBR (vertex colours only): the texture/normal-mapping path is compiled out, which
+// frees enough registers for 6 resident CTAs per SM instead of 4.
+template <bool TOPLEFT, bool COUNT, bool TEXTURED>
+__global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
 	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
@@ -368,8 +343,8 @@ __global__ void __launch_bounds__(kTile * kTile, 4) raster_shade_kernel(RasterAr
 			const float2* r0 = A.ivertex + (size_t)(mc.vtxInBase + i0) * 7;
 			const float2* r1 = A.ivertex + (size_t)(mc.vtxInBase + i1) * 7;
 			const float2* r2 = A.ivertex + (size_t)(mc.vtxInBase + i2) * 7;
-			const bool textured = (fp.visState == 0u) && mc.tex[0] >= 0;
-			if (fp.visState == 0u && !textured)
+			const bool textured = TEXTURED && (fp.visState == 0u) && mc.tex[0] >= 0;
+			if (!TEXTURED || (fp.visState == 0u && !textured))
 			{
 				// vertex colour (IVertex floats 11..13, copied unchanged by GetNDCVertex), NOT multiplied
 				// by wInterpolated (CUDAROPs.cu:379)
