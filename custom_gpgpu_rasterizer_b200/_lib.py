@@ -49,6 +49,8 @@ ABI = {
     "b2r_render": (_i32, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _fp]),
     "b2r_sync": (_i32, [_vp]),
     "b2r_read_framebuffer": (_i32, [_vp, _vp]),
+    "b2r_present_async": (_i32, [_vp, _vp]),
+    "b2r_present_wait": (_i32, [_vp]),
     "b2r_read_depth": (_i32, [_vp, _vp]),
     "b2r_read_z": (_i32, [_vp, _vp]),
     "b2r_read_winner": (_i32, [_vp, _vp]),

@@ -133,6 +133,14 @@ struct b2r_context
 	// surfaces
 	uint32_t* dFramebuffer = nullptr; int32_t* dDepth = nullptr; float* dZ = nullptr; uint32_t* dWinner = nullptr;
 	uint32_t* boundFramebuffer = nullptr;
+	// pipelined Present: two colour surfaces; while one is copied to the host on copyStream the next
+	// frame renders into the other
+	uint32_t* dColour[2] = { nullptr, nullptr };
+	int colourIdx = 0;                 // surface the NEXT frame renders into
+	int lastColourIdx = 0;             // surface the newest enqueued frame rendered into
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t frameDone = nullptr, copyDone[2] = { nullptr, nullptr };
+	bool copyPending[2] = { false, false };
 
 	// frame state
 	RenderCall last;
@@ -170,6 +178,7 @@ int allocSurfaces(b2r_context* c)
 	CU(c, cudaMalloc((void**)&c->dFramebuffer, n * 4));
 	CU(c, cudaMalloc((void**)&c->dDepth, n * 4));
 	CU(c, cudaMemset(c->dFramebuffer, 0, n * 4));     // CUDAWindowHelper.h:17-25 zero-initialises
+	c->dColour[0] = c->dFramebuffer;
 	CU(c, cudaMemset(c->dDepth, 0, n * 4));
 	return B2R_OK;
 }
@@ -381,7 +390,14 @@ int enqueueFrame(b2r_context* c)
 		A.tileCount = c->dTileCount.ptr; A.tileOffset = c->dTileOffset.ptr; A.binIds = c->dBinIds.ptr;
 		A.records = c->dRecords.ptr; A.pos4 = c->dPos4.ptr; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
 		A.meshes = c->dMeshConst.ptr; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
-		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer;
+		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
+		{
+			// this surface is still being copied to the host by an earlier b2r_present_async
+			CU(c, cudaStreamWaitEvent(s, c->copyDone[c->colourIdx], 0));
+			c->copyPending[c->colourIdx] = false;
+		}
+		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->colourIdx];
+		c->lastColourIdx = c->colourIdx;
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
 		const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
 		if (owned)
@@ -542,6 +558,10 @@ void b2r_destroy(b2r_context* c)
 	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dWarpTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dCounters); cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
+	if (c->dColour[1]) cudaFree(c->dColour[1]);
+	if (c->copyStream) cudaStreamDestroy(c->copyStream);
+	if (c->frameDone) cudaEventDestroy(c->frameDone);
+	for (auto& e : c->copyDone) if (e) cudaEventDestroy(e);
 	for (auto& slot : c->slots)
 	{
 		if (slot.hMeshConst) cudaFreeHost(slot.hMeshConst);
@@ -715,8 +735,43 @@ static int readSurface(b2r_context* c, const void* src, void* out, const char* w
 int b2r_read_framebuffer(b2r_context* c, uint32_t* out)
 {
 	if (!c) return B2R_E_INVALID;
-	return readSurface(c, c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer, out, "read_framebuffer");
+	return readSurface(c, c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->lastColourIdx], out, "read_framebuffer");
 }
+int b2r_present_async(b2r_context* c, uint32_t* hostPixels)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!hostPixels) return fail(c, B2R_E_INVALID, "null output");
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "present_async: nothing rendered yet");
+	if (c->boundFramebuffer) return fail(c, B2R_E_STATE, "present_async: the colour surface is bound to caller memory");
+	CU(c, cudaSetDevice(c->device));
+	const size_t bytes = (size_t)c->width * c->height * 4;
+	if (!c->copyStream)
+	{
+		CU(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+		CU(c, cudaEventCreateWithFlags(&c->frameDone, cudaEventDisableTiming));
+		for (auto& e : c->copyDone) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		CU(c, cudaMalloc((void**)&c->dColour[1], bytes));
+		CU(c, cudaMemset(c->dColour[1], 0, bytes));
+	}
+	const int idx = c->lastColourIdx;
+	CU(c, cudaEventRecord(c->frameDone, c->stream));
+	CU(c, cudaStreamWaitEvent(c->copyStream, c->frameDone, 0));
+	CU(c, cudaMemcpyAsync(hostPixels, c->dColour[idx], bytes, cudaMemcpyDeviceToHost, c->copyStream));
+	CU(c, cudaEventRecord(c->copyDone[idx], c->copyStream));
+	c->copyPending[idx] = true;
+	c->colourIdx = idx ^ 1;          // the next frame renders into the other surface
+	return B2R_OK;
+}
+
+int b2r_present_wait(b2r_context* c)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	if (c->copyStream) CU(c, cudaStreamSynchronize(c->copyStream));
+	c->copyPending[0] = c->copyPending[1] = false;
+	return validateFrame(c);
+}
+
 int b2r_read_depth(b2r_context* c, int32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dDepth, out, "read_depth"); }
 int b2r_read_z(b2r_context* c, float* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dZ, out, "read_z"); }
 int b2r_read_winner(b2r_context* c, uint32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dWinner, out, "read_winner"); }
@@ -830,7 +885,7 @@ int b2r_set_stream(b2r_context* c, void* stream)
 int b2r_device_surfaces(b2r_context* c, void** framebuffer, void** depth)
 {
 	if (!c) return B2R_E_INVALID;
-	if (framebuffer) *framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dFramebuffer;
+	if (framebuffer) *framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->lastColourIdx];
 	if (depth) *depth = c->dDepth;
 	return B2R_OK;
 }
@@ -857,7 +912,7 @@ int b2r_unpack_tiles(b2r_context* c, const void* packed, int rank, int count, vo
 	const FrameParams fp = makeParams(c, c->last);
 	const uint32_t owned = ownedTiles(nBins(c), (uint32_t)rank, (uint32_t)count);
 	if (!owned) return B2R_OK;
-	uint32_t* dst = dstFramebuffer ? (uint32_t*)dstFramebuffer : c->dFramebuffer;
+	uint32_t* dst = dstFramebuffer ? (uint32_t*)dstFramebuffer : c->dColour[c->lastColourIdx];
 	unpack_tiles_kernel<<<dim3(owned, fp.subX * fp.subY), kTile * kTile, 0, c->stream>>>((const uint32_t*)packed, dst, (uint32_t)rank, (uint32_t)count, fp);
 	CU(c, cudaGetLastError());
 	return B2R_OK;

@@ -172,6 +172,13 @@ class Renderer:
     def framebuffer(self, out=None) -> np.ndarray:
         return self._surface(lib.b2r_read_framebuffer, np.uint32, out)
 
+    def present_async(self, out: np.ndarray):
+        """Pipelined Present: start copying the newest frame into `out` (pinned), do not wait."""
+        self._check(lib.b2r_present_async(self._ctx, out.ctypes.data))
+
+    def present_wait(self):
+        self._check(lib.b2r_present_wait(self._ctx))
+
     def depth(self) -> np.ndarray:
         return self._surface(lib.b2r_read_depth, np.int32)
 

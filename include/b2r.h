@@ -128,6 +128,12 @@ int b2r_sync(b2r_context* ctx);
 /* CUDARenderer::Present's device->host copy (CUDARenderer.cu:386-388): width*height words 0x00RRGGBB.
  * Synchronous.  Full-speed if `out` is pinned memory. */
 int b2r_read_framebuffer(b2r_context* ctx, uint32_t* out);
+/* Present without the stall: the colour surface of the newest frame is copied to
+ * `host_pixels` (pinned memory) on a second stream; the call returns immediately and the next frame
+ * renders into the other of two colour surfaces, so the copy overlaps the next b2r_render.
+ * b2r_present_wait blocks until every outstanding copy has landed (and the frames are complete). */
+int b2r_present_async(b2r_context* ctx, uint32_t* host_pixels);
+int b2r_present_wait(b2r_context* ctx);
 /* depth buffer as the reference keeps it (int z*2^31, INT_MAX = empty; CUDAROPs.cu:386, CUDARenderer.cu:1640) */
 int b2r_read_depth(b2r_context* ctx, int32_t* out);
 /* parity surfaces (need B2R_OPT_DEBUG_SURFACES=1 before the render): PixelShade.zInterpolated

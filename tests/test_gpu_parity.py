@@ -198,3 +198,26 @@ def test_api_errors():
             r.setup_bins(2, 2, 16, 16)      # does not cover 64x64
     finally:
         r.close()
+
+
+def test_pipelined_present_returns_each_frame():
+    """b2r_present_async: frame i's copy overlaps frame i+1's rendering (two colour surfaces) and still delivers frame i."""
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer, host_camera
+    sc = scenes.random_triangles_scene(640, 480, 300, seed=71, cull=2, textured=True, n_meshes=2)
+    cams = [host_camera((x, 0.3 * x, 5.0), sc.fov_deg, sc.width, sc.height, sc.near, sc.far) for x in (0.0, 0.7, -1.1, 0.4, 2.0)]
+    with Renderer(sc.width, sc.height) as r:
+        r.load_scene(sc)
+        want = []
+        for cam in cams:
+            r.render(cam, sc.cull, sc.sample, sc.vis)
+            want.append(r.framebuffer().copy())
+        bufs = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+        for cam, b in zip(cams, bufs):
+            r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+            r.present_async(b)
+        r.present_wait()
+        for i, (b, w) in enumerate(zip(bufs, want)):
+            assert np.array_equal(b, w), f"frame {i} differs"
+        assert not np.array_equal(want[0], want[1])
+        # the synchronous read-back still returns the newest frame
+        assert np.array_equal(r.framebuffer(), want[-1])
