@@ -98,7 +98,7 @@ struct b2r_context
 	DeviceVec<uint32_t> dIndices;
 	DeviceVec<float4> dPosIn, dPos4;   // positions in (x,y,z,1) / transformed (ndc.xyz, clip.w)
 	DeviceVec<float> dOvertexScratch;
-	DeviceVec<TriRecord> dRecords;
+	DeviceVec<uint4> dTriRefs;         // static {v0, v1, v2, mesh} per primitive, rebuilt when the mesh list changes
 	DeviceVec<uint2> dRects;
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
@@ -109,7 +109,7 @@ struct b2r_context
 	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dWarpTiles, dBigList, dBinIds;
 	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
 	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
-	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };
+	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };   // device layout: dFrameInfo, then dCounters
 
 	// frames in flight: each enqueued frame owns one slot of pinned host memory + events, so the
 	// host can run ahead of the device by kRing frames without a synchronisation
@@ -230,8 +230,14 @@ int rebuildScene(b2r_context* c)
 	if (!vs.empty()) CU(c, cudaMemcpyAsync(c->dVsChunks.ptr, vs.data(), vs.size() * sizeof(Chunk), cudaMemcpyHostToDevice, c->stream));
 	if (!tri.empty()) CU(c, cudaMemcpyAsync(c->dTriChunks.ptr, tri.data(), tri.size() * sizeof(Chunk), cudaMemcpyHostToDevice, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));   // vs/tri are host temporaries
+	CU(c, c->dTriRefs.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	if (c->nTriChunks)
+	{
+		build_trirefs_kernel<<<c->nTriChunks, kChunk, 0, c->stream>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dTriRefs.ptr);
+		CU(c, cudaGetLastError());
+	}
 	CU(c, c->dPos4.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
-	CU(c, c->dRecords.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	CU(c, c->dTriRefs.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dRects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dBigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dMeshConst.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
@@ -343,9 +349,10 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 0);
 	if (!c->meshes.empty())
 		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, slot.hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
-	CU(c, cudaMemsetAsync(c->dTileCount.ptr, 0, tiles * 4, s));
-	CU(c, cudaMemsetAsync(c->dCounters, 0, kCounterWords * 4, s));
-	CU(c, cudaMemsetAsync(c->dFrameInfo, 0, kInfoWords * 8, s));
+	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
+	// queue behind the previous frame's 33 MB Present copy
+	frame_clear_kernel<<<(tiles + 4095) / 4096, 256, 0, s>>>(c->dTileCount.ptr, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords);
+	++c->kernelsLaunched;
 
 	if (c->nVsChunks)
 	{
@@ -355,8 +362,8 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 1);
 	if (c->nTriChunks)
 	{
-		triangle_setup_kernel<<<c->nTriChunks, kChunk, 0, s>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dPos4.ptr,
-			c->dRecords.ptr, c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, fp);
+		triangle_setup_kernel<<<(uint32_t)((c->nPrims + kChunk - 1) / kChunk), kChunk, 0, s>>>(c->dTriRefs.ptr, c->dPos4.ptr,
+			c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, 0u, (uint32_t)c->nPrims, fp);
 		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, c->dFrameInfo, fp);
 		c->kernelsLaunched += 2;
 	}
@@ -388,7 +395,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = c->dTileCount.ptr; A.tileOffset = c->dTileOffset.ptr; A.binIds = c->dBinIds.ptr;
-		A.records = c->dRecords.ptr; A.pos4 = c->dPos4.ptr; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = c->dPos4.ptr; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
 		A.meshes = c->dMeshConst.ptr; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -422,8 +429,8 @@ int enqueueFrame(b2r_context* c)
 		}
 	}
 	STAGE_EVENT(c, slot, 6);
-	CU(c, cudaMemcpyAsync(slot.hInfo->frameInfo, c->dFrameInfo, kInfoWords * 8, cudaMemcpyDeviceToHost, s));
-	CU(c, cudaMemcpyAsync(slot.hInfo->counters, c->dCounters, 8, cudaMemcpyDeviceToHost, s));
+	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
+	CU(c, cudaMemcpyAsync(slot.hInfo, c->dFrameInfo, sizeof(b2r_context::HostInfo), cudaMemcpyDeviceToHost, s));
 	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
 	slot.pending = true;
@@ -533,9 +540,9 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 		CUC(cudaMallocHost((void**)&slot.hInfo, sizeof(b2r_context::HostInfo)));
 		memset(slot.hInfo, 0, sizeof(b2r_context::HostInfo));
 	}
-	CUC(cudaMalloc((void**)&c->dCounters, kCounterWords * 4));
-	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8));
-	CUC(cudaMemset(c->dFrameInfo, 0, kInfoWords * 8));
+	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8 + kCounterWords * 4));
+	CUC(cudaMemset(c->dFrameInfo, 0, kInfoWords * 8 + kCounterWords * 4));
+	c->dCounters = reinterpret_cast<uint32_t*>(c->dFrameInfo + kInfoWords);
 	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortLongSmem));
 #undef CUC
 	int r = allocSurfaces(c);
@@ -553,10 +560,10 @@ void b2r_destroy(b2r_context* c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); c->dPos4.release(); c->dOvertexScratch.release();
-	c->dRecords.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
+	c->dTriRefs.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
 	c->dMeshConst.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
 	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dWarpTiles.release(); c->dBigList.release(); c->dBinIds.release();
-	cudaFree(c->dCounters); cudaFree(c->dFrameInfo);
+	cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
 	if (c->dColour[1]) cudaFree(c->dColour[1]);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);

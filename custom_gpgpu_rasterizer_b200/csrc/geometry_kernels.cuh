@@ -151,6 +151,20 @@ __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t til
 	return 0;
 }
 
+// start of frame: zero the tile counts (tileCount is padded to a multiple of 4 words) and the counters
+__global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__ tileCount, uint32_t nTiles,
+	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords)
+{
+	const uint32_t q = (nTiles + 3) / 4;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < q; i += gridDim.x * blockDim.x)
+		reinterpret_cast<uint4*>(tileCount)[i] = make_uint4(0, 0, 0, 0);
+	if (blockIdx.x == 0)
+	{
+		for (uint32_t i = threadIdx.x; i < kCounterWords; i += blockDim.x) counters[i] = 0;
+		if (threadIdx.x < infoWords) frameInfo[threadIdx.x] = 0;
+	}
+}
+
 // Warp-level binning of up to 32 small rectangles (one per lane, rectangle = inclusive tile range,
 // nTiles = 0 for lanes without one).  Consecutive primitives overlap the same few tiles, so the warp
 // walks the UNION of its rectangles tile by tile: for each tile the lanes whose rectangle contains it
@@ -209,26 +223,88 @@ __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, 
 	}
 }
 
-// triangle setup: one CTA per chunk of 256 triangles of one mesh.
+// scene-load time: the static per-primitive reference {v0, v1, v2, mesh} with GLOBAL indices into the
+// transformed-vertex stream (mesh.vtxOutBase + index).  It never changes between frames, so the frame
+// itself writes nothing per primitive except the 8-byte bin rectangle: the raster kernel rebuilds the
+// screen-space triangle of a list entry from this reference and the three transformed positions.
+__global__ void __launch_bounds__(kChunk) build_trirefs_kernel(const Chunk* __restrict__ chunks, const uint32_t* __restrict__ indices,
+	uint4* __restrict__ triRefs)
+{
+	const Chunk ch = chunks[blockIdx.x];
+	if (threadIdx.x >= ch.count) return;
+	const uint32_t* ip = indices + (size_t)ch.inStart + (size_t)threadIdx.x * 3;
+	triRefs[ch.primStart + threadIdx.x] = make_uint4(ch.outStart + __ldg(ip), ch.outStart + __ldg(ip + 1), ch.outStart + __ldg(ip + 2), ch.mesh);
+}
+
+// screen mapping of the three NDC vertices (CUDAROPs.cu:88-97) and the float bounds
+struct ScreenBounds { float minx, maxx, miny, maxy; };
+__device__ __forceinline__ ScreenBounds screenMap(const float4& p0, const float4& p1, const float4& p2, const FrameParams& fp, TriRecord& r)
+{
+	const float W = (float)fp.width, H = (float)fp.height;
+	r.x0 = ((p0.x + 1.f) * 0.5f) * W; r.y0 = ((1.f - p0.y) * 0.5f) * H;
+	r.x1 = ((p1.x + 1.f) * 0.5f) * W; r.y1 = ((1.f - p1.y) * 0.5f) * H;
+	r.x2 = ((p2.x + 1.f) * 0.5f) * W; r.y2 = ((1.f - p2.y) * 0.5f) * H;
+	r.z0 = p0.z; r.z1 = p1.z; r.z2 = p2.z;
+	ScreenBounds b;
+	b.minx = min3ref(r.x0, r.x1, r.x2); b.maxx = max3ref(r.x0, r.x1, r.x2);
+	b.miny = min3ref(r.y0, r.y1, r.y2); b.maxy = max3ref(r.y0, r.y1, r.y2);
+	return b;
+}
+
+// the per-triangle constants of the raster kernel's fragment test (area, candidate box, hoisted
+// reciprocal, conservative depth bound).  Evaluated by the raster kernel for every list entry.
+__device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const FrameParams& fp, TriRecord& r)
+{
+	r.area = fabsf(diff2(r.x0 - r.x1, r.y0 - r.y2, r.y0 - r.y1, r.x0 - r.x2));
+	// The reference's inflated 16-bit bbox (CUDAROPs.cu:180-200) decides the BINS, while the raster kernel
+	// only needs a superset of the pixels whose three edge functions can be >= 0.  A covered pixel has
+	// non-negative barycentrics, so it lies inside the float bounds of the triangle up to the rounding
+	// error of the edge functions: a pixel eps outside the bounds carries a negative weight of at least
+	// area*eps/extent, against an evaluation error below 2^-21 * D^2 (D = pixel-to-vertex distances).
+	// eps below keeps a 8x safety factor on that error plus the rounding of the coordinates themselves;
+	// thin or degenerate triangles (area -> 0) widen to the whole screen, i.e. to the reference's
+	// "every pixel of the bin" (CUDARenderer.cu:1116-1127).
+	const float extx = b.maxx - b.minx, exty = b.maxy - b.miny;
+	const float D = extx + exty + 2.f;
+	const float maxAbs = fmaxf(fmaxf(fabsf(b.minx), fabsf(b.maxx)), fmaxf(fabsf(b.miny), fabsf(b.maxy)));
+	const float k = 3.814697265625e-6f * D * D / r.area;
+	const float epsx = 0.015625f + maxAbs * 1.52587890625e-5f + k * extx;
+	const float epsy = 0.015625f + maxAbs * 1.52587890625e-5f + k * exty;
+	int cx0 = 0, cx1 = (int)fp.width, cy0 = 0, cy1 = (int)fp.height;
+	if (epsx < 1.0e6f && epsy < 1.0e6f && maxAbs < 1.0e9f)      // false for NaN / inf
+	{
+		cx0 = clampi(__float2int_ru(b.minx - epsx), 0, (int)fp.width);
+		cx1 = clampi(__float2int_rd(b.maxx + epsx) + 1, 0, (int)fp.width);
+		cy0 = clampi(__float2int_ru(b.miny - epsy), 0, (int)fp.height);
+		cy1 = clampi(__float2int_rd(b.maxy + epsy) + 1, 0, (int)fp.height);
+	}
+	r.cbX = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
+	r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
+	// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn) ...
+	r.rcpArea = refinedReciprocal(r.area);
+	r.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
+	// ... and a conservative lower bound of the integer depth: weights are in [0, 1 + few ulp] and
+	// sum to 1 +- few ulp, so z >= min(z_i) - small; anything non-finite or negative means "no bound"
+	const float zb = fminf(fminf(r.z0, r.z1), r.z2) * 0.999999f - 1e-9f;
+	r.zLow = (zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
+	r.pad = 0;
+}
+
+// triangle setup: one thread per primitive of [primLo, primHi).
 // cull (CUDARenderer.cu:760-777), frustum reject (CUDAROPs.cu:147-178), screen mapping (:88-97),
 // inflated bbox (:180-200), bin rectangle (CUDARenderer.cu:935-942), per-tile counts.
 __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
-	const Chunk* __restrict__ chunks,
-	const uint32_t* __restrict__ indices, const float4* __restrict__ pos4,
-	TriRecord* __restrict__ records, uint2* __restrict__ rects,
+	const uint4* __restrict__ triRefs, const float4* __restrict__ pos4, uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig*/,
-	FrameParams fp)
+	uint32_t primLo, uint32_t primHi, FrameParams fp)
 {
-	const Chunk ch = chunks[blockIdx.x];
 	bool visible = false;
-	uint32_t prim = 0;
+	const uint32_t prim = primLo + blockIdx.x * kChunk + threadIdx.x;
 	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
-	if (threadIdx.x < ch.count)
+	if (prim < primHi)
 	{
-		prim = ch.primStart + threadIdx.x;
-		const uint32_t* ip = indices + (size_t)ch.inStart + (size_t)threadIdx.x * 3;
-		const uint32_t i0 = ch.outStart + __ldg(ip), i1 = ch.outStart + __ldg(ip + 1), i2 = ch.outStart + __ldg(ip + 2);
-		const float4 p0 = __ldg(pos4 + i0), p1 = __ldg(pos4 + i1), p2 = __ldg(pos4 + i2);
+		const uint4 tr = __ldcs(triRefs + prim);
+		const float4 p0 = __ldg(pos4 + tr.x), p1 = __ldg(pos4 + tr.y), p2 = __ldg(pos4 + tr.z);
 		visible = true;
 		if (fp.cullMode != 2u)
 		{
@@ -251,54 +327,12 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 		}
 		if (visible)
 		{
-			const float W = (float)fp.width, H = (float)fp.height;
 			TriRecord r;
-			r.x0 = ((p0.x + 1.f) * 0.5f) * W; r.y0 = ((1.f - p0.y) * 0.5f) * H;
-			r.x1 = ((p1.x + 1.f) * 0.5f) * W; r.y1 = ((1.f - p1.y) * 0.5f) * H;
-			r.x2 = ((p2.x + 1.f) * 0.5f) * W; r.y2 = ((1.f - p2.y) * 0.5f) * H;
-			r.z0 = p0.z; r.z1 = p1.z; r.z2 = p2.z;
-			r.area = fabsf(diff2(r.x0 - r.x1, r.y0 - r.y2, r.y0 - r.y1, r.x0 - r.x2));
-			// the reference's inflated 16-bit bbox (CUDAROPs.cu:180-200) decides the BINS ...
-			const float minx = min3ref(r.x0, r.x1, r.x2), maxx = max3ref(r.x0, r.x1, r.x2);
-			const float miny = min3ref(r.y0, r.y1, r.y2), maxy = max3ref(r.y0, r.y1, r.y2);
-			const int xMin = bboxCoord(minx, -1, (int)fp.width);
-			const int yMin = bboxCoord(miny, -1, (int)fp.height);
-			const int xMax = bboxCoord(maxx, +1, (int)fp.width);
-			const int yMax = bboxCoord(maxy, +1, (int)fp.height);
-			// ... while the raster kernel only needs a superset of the pixels whose three edge
-			// functions can be >= 0.  A covered pixel has non-negative barycentrics, so it lies inside
-			// the float bounds of the triangle up to the rounding error of the edge functions: a pixel
-			// eps outside the bounds carries a negative weight of at least area*eps/extent, against an
-			// evaluation error below 2^-21 * D^2 (D = pixel-to-vertex distances).  eps below keeps a
-			// 8x safety factor on that error plus the rounding of the coordinates themselves; thin or
-			// degenerate triangles (area -> 0) widen to the whole screen, i.e. to the reference's
-			// "every pixel of the bin" (CUDARenderer.cu:1116-1127).
-			const float extx = maxx - minx, exty = maxy - miny;
-			const float D = extx + exty + 2.f;
-			const float maxAbs = fmaxf(fmaxf(fabsf(minx), fabsf(maxx)), fmaxf(fabsf(miny), fabsf(maxy)));
-			const float k = 3.814697265625e-6f * D * D / r.area;
-			const float epsx = 0.015625f + maxAbs * 1.52587890625e-5f + k * extx;
-			const float epsy = 0.015625f + maxAbs * 1.52587890625e-5f + k * exty;
-			int cx0 = 0, cx1 = (int)fp.width, cy0 = 0, cy1 = (int)fp.height;
-			if (epsx < 1.0e6f && epsy < 1.0e6f && maxAbs < 1.0e9f)      // false for NaN / inf
-			{
-				cx0 = clampi(__float2int_ru(minx - epsx), 0, (int)fp.width);
-				cx1 = clampi(__float2int_rd(maxx + epsx) + 1, 0, (int)fp.width);
-				cy0 = clampi(__float2int_ru(miny - epsy), 0, (int)fp.height);
-				cy1 = clampi(__float2int_rd(maxy + epsy) + 1, 0, (int)fp.height);
-			}
-			r.cbX = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
-			r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
-			// per-triangle constants of the raster kernel's fragment test, computed here where ALU is free:
-			// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn) ...
-			r.rcpArea = refinedReciprocal(r.area);
-			r.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
-			// ... and a conservative lower bound of the integer depth: weights are in [0, 1 + few ulp] and
-			// sum to 1 +- few ulp, so z >= min(z_i) - small; anything non-finite or negative means "no bound"
-			const float zb = fminf(fminf(r.z0, r.z1), r.z2) * 0.999999f - 1e-9f;
-			r.zLow = (zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
-			r.pad = 0;
-			records[prim] = r;
+			const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
+			const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
+			const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
+			const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
+			const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
 			bx0 = clampi(xMin / (int)fp.binW, 0, (int)fp.binsX);
 			by0 = clampi(yMin / (int)fp.binH, 0, (int)fp.binsY);
 			bx1 = clampi(xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
@@ -318,18 +352,15 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 
 	// per-tile counts, warp-aggregated
 	uint32_t nTiles = 0;
-	int w = 1;
 	if (visible && bx0 <= bx1 && by0 <= by1)
 	{
-		w = bx1 - bx0 + 1;
-		nTiles = (uint32_t)w * (uint32_t)(by1 - by0 + 1);
+		nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
 		if (nTiles > fp.bigRectTiles)
 		{
 			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively by bin_big_kernel
 			nTiles = 0;
 		}
 	}
-	(void)w;
 	warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
 }
 

@@ -23,7 +23,7 @@ struct RasterArgs
 	const uint32_t* tileCount;
 	const uint32_t* tileOffset;
 	const uint32_t* binIds;
-	const TriRecord* records;
+	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
 	const float2* ivertex;      // resident IVertex records (7 float2 each)
 	const uint32_t* indices;
@@ -240,7 +240,12 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		if ((uint32_t)tid < m)
 		{
 			const uint32_t prim = __ldg(list + base + tid);
-			const TriRecord r = A.records[prim];
+			// rebuild the screen-space triangle from the static reference + the transformed positions
+			// (same code, hence the same bits, wherever a triangle is expanded)
+			const uint4 tr = __ldg(A.triRefs + prim);
+			const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
+			TriRecord r;
+			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
 			// candidate pixels = the record's conservative box clipped to this CTA's block; the box
 			// contains every pixel whose edge functions can all be >= 0, so this equals the
 			// reference's test of every pixel of the bin (CUDARenderer.cu:1116-1127)
@@ -319,15 +324,18 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	{
 		prim = (uint32_t)best;
 		depthOut = (int)(uint32_t)(best >> 32);
+		const uint4 tr = __ldg(A.triRefs + prim);
+		const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
 		TriShared t;
-		expandRecord(A.records[prim], prim, t);
+		{
+			TriRecord r;
+			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
+			expandRecord(r, prim, t);
+		}
 		Bary bc; int zi;
 		fragmentTest<false>(t, fx, fy, bc, zi);      // same arithmetic as the coverage pass
 		zOut = bc.z;
-		// which mesh: primitive ids are mesh-major (binary search over the per-mesh bases)
-		uint32_t lo = 0, hi = fp.nMeshes;
-		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (A.meshes[mid].primBase <= prim) lo = mid; else hi = mid; }
-		const MeshConst& mc = A.meshes[lo];
+		const MeshConst& mc = A.meshes[tr.w];
 		if (fp.visState == 1u)
 		{
 			const float r = __fdiv_rn(bc.z - 0.985f, 1.f - 0.985f);   // Remap, MathUtilities.h:175-178
@@ -335,14 +343,13 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		}
 		else
 		{
-			const uint32_t* ip = A.indices + (size_t)mc.idxBase + (size_t)(prim - mc.primBase) * 3;
-			const uint32_t i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 			Interp S;
 			S.b0 = bc.b0; S.b1 = bc.b1; S.b2 = bc.b2;
-			S.iw0 = __frcp_rn(__ldg(&A.pos4[mc.vtxOutBase + i0].w)); S.iw1 = __frcp_rn(__ldg(&A.pos4[mc.vtxOutBase + i1].w)); S.iw2 = __frcp_rn(__ldg(&A.pos4[mc.vtxOutBase + i2].w));
-			const float2* r0 = A.ivertex + (size_t)(mc.vtxInBase + i0) * 7;
-			const float2* r1 = A.ivertex + (size_t)(mc.vtxInBase + i1) * 7;
-			const float2* r2 = A.ivertex + (size_t)(mc.vtxInBase + i2) * 7;
+			S.iw0 = __frcp_rn(p0.w); S.iw1 = __frcp_rn(p1.w); S.iw2 = __frcp_rn(p2.w);
+			const uint32_t inDelta = mc.vtxInBase - mc.vtxOutBase;     // transformed-stream index -> IVertex record (mod 2^32)
+			const float2* r0 = A.ivertex + (size_t)(tr.x + inDelta) * 7;
+			const float2* r1 = A.ivertex + (size_t)(tr.y + inDelta) * 7;
+			const float2* r2 = A.ivertex + (size_t)(tr.z + inDelta) * 7;
 			const bool textured = TEXTURED && (fp.visState == 0u) && mc.tex[0] >= 0;
 			if (!TEXTURED || (fp.visState == 0u && !textured))
 			{
