@@ -178,8 +178,10 @@ def run_b200(args, scene):
     dev = torch.device("cuda", local)
 
     r = Renderer(scene.width, scene.height, device=local)
-    r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
-    r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
+    sharded = world > 1 and args.gather == "sharded"
+    if not sharded:
+        r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
+        r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
     t0 = time.perf_counter()
     r.load_scene(scene)
     load_s = time.perf_counter() - t0
@@ -190,8 +192,8 @@ def run_b200(args, scene):
 
     gather = None
     if world > 1:
-        from custom_gpgpu_rasterizer_b200.multi_gpu import SortFirstGather
-        gather = SortFirstGather(r, scene, rank, world, stream, mode=args.gather)
+        from custom_gpgpu_rasterizer_b200.multi_gpu import ShardedSortFirst, SortFirstGather
+        gather = ShardedSortFirst(r, rank, world) if sharded else SortFirstGather(r, scene, rank, world, stream, mode=args.gather)
 
     def frame():
         r.render(cam, scene.cull, scene.sample, scene.vis, sync=False)
@@ -236,11 +238,11 @@ def run_b200(args, scene):
         if rank == 0:
             # Present(): device->host copy of the (gathered) frame into pinned memory; pipelined - the copy of
             # frame i overlaps the rendering of frame i+1 (two colour surfaces, two host buffers)
-            if world == 1:
+            if world == 1 or sharded:
                 r.present_async(host_fb[i & 1])
             else:
                 r.framebuffer(out=host_fb[i & 1])
-    if rank == 0 and world == 1:
+    if rank == 0 and (world == 1 or sharded):
         r.present_wait()
     else:
         r.sync()
@@ -251,9 +253,36 @@ def run_b200(args, scene):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
 
+    # ---- per-stage device times over K more frames (CUDA events recorded between the stages on the same stream)
+    r.set_option(_lib.OPT_STAGE_TIMERS, 1)
+    r.stage_ms_mean(reset=True)
+    for _ in range(args.steps):
+        frame()
+    r.sync()
+    stages, n_timed = r.stage_ms_mean(reset=True)
+    r.set_option(_lib.OPT_STAGE_TIMERS, 0)
+
+    # ---- workload counters for the roofline (instrumented frame, outside every timed region)
+    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
+    frame()
+    r.sync()
+    c2 = r.counters()
+    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 0)
+    total_tris, visible = r.stats()
+    pairs, frags = counters["pairs"], c2["fragments"]
+    if world > 1:
+        # every rank counted its own tiles (and, with the sharded front end, its own primitives)
+        agg = torch.tensor([pairs, frags, visible if sharded else 0], device=dev, dtype=torch.int64)
+        dist.all_reduce(agg)
+        pairs, frags = int(agg[0].item()), int(agg[1].item())
+        if sharded:
+            visible = int(agg[2].item())
+    barrier()
+
     # ---- view-parallel mode (N > 1): every rank renders complete, independent frames - no data-path collective
     view_parallel = None
     if world > 1:
+        r.sync()
         gather.close()
         r.bind_framebuffer(None)
         r.set_option(_lib.OPT_PACKED_OUTPUT, 0)
@@ -274,26 +303,7 @@ def run_b200(args, scene):
         dist.all_reduce(vms, op=dist.ReduceOp.MAX)
         view_parallel = {"value": world * args.steps / (float(vms.item()) / 1e3), "unit": "frames/s", "scaling": "weak",
                          "note": "independent views: every rank renders whole frames of the same scene, no communication; max over ranks"}
-        r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
-        r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
         gather = None
-
-    # ---- per-stage device times over K more frames (CUDA events recorded between the stages on the same stream)
-    r.set_option(_lib.OPT_STAGE_TIMERS, 1)
-    r.stage_ms_mean(reset=True)
-    for _ in range(args.steps):
-        frame()
-    r.sync()
-    stages, n_timed = r.stage_ms_mean(reset=True)
-    r.set_option(_lib.OPT_STAGE_TIMERS, 0)
-
-    # ---- workload counters for the roofline (instrumented frame, outside every timed region)
-    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
-    frame()
-    r.sync()
-    c2 = r.counters()
-    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 0)
-    total_tris, visible = r.stats()
     depth = r.depth()
     covered_px = int((depth != 0x7FFFFFFF).sum())
     barrier()
@@ -308,7 +318,7 @@ def run_b200(args, scene):
 
     fps = args.steps / (total_ms / 1e3)
     peak, peak_src = load_peaks()
-    ab = algorithmic_bytes(scene, visible, counters["pairs"], c2["fragments"], covered_px)
+    ab = algorithmic_bytes(scene, visible, pairs, frags, covered_px)
     stage_of = {"vertex": "vertex", "setup": "setup", "binning": None, "raster_shade": "raster_shade"}
     per_stage = {}
     for k, b in ab.items():
@@ -330,9 +340,9 @@ def run_b200(args, scene):
         "metric": "frames/s at 4K (device-timed)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + ("NCCL gather of packed tiles to rank 0" if args.gather == "nccl" else "peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)"))),
+        "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up/bins/sorts primitive slice r, owners read the peers' lists over NVLink, colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather])),
         "mtris_per_s": scene.n_tris * fps / 1e6,
-        "visible_triangles": visible, "tile_pairs": counters["pairs"], "fragments": c2["fragments"], "covered_pixels": covered_px,
+        "visible_triangles": visible, "tile_pairs": pairs, "fragments": frags, "covered_pixels": covered_px,
         "stages_ms": stages, "stages": per_stage,
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
                      "traffic": traffic, "peak_source": peak_src,
@@ -408,7 +418,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small"])
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="sort-first composition: NCCL gather of packed tiles, or peer-to-peer ROP write-back over NVLink")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
     args = ap.parse_args()

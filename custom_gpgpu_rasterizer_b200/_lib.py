@@ -69,6 +69,9 @@ ABI = {
     "b2r_ipc_export": (_i32, [_vp, _vp, _vp]),
     "b2r_ipc_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
     "b2r_ipc_close": (_i32, [_vp, _vp]),
+    "b2r_shard_prepare": (_i32, [_vp, _i32, _i32, _u64, _vp, _vp]),
+    "b2r_shard_bind": (_i32, [_vp, _vp, _vp]),
+    "b2r_shard_release": (_i32, [_vp]),
 }
 for _name, (_res, _args) in ABI.items():
     _fn = getattr(lib, _name)

@@ -142,6 +142,25 @@ struct b2r_context
 	cudaEvent_t frameDone = nullptr, copyDone[2] = { nullptr, nullptr };
 	bool copyPending[2] = { false, false };
 
+	// sharded front end (b2r_shard_*): double-buffered bin lists + flag words in one IPC-exported arena,
+	// rank 0's two colour surfaces in another; peers' arenas / rank 0's surfaces mapped over NVLink
+	struct Shard
+	{
+		bool prepared = false, bound = false;
+		int n = 1, self = 0;
+		uint8_t* arena = nullptr;
+		size_t tilesPad = 0, listCap = 0, setBytes = 0;
+		uint8_t* peerArena[kMaxRanks] = {};
+		uint32_t* colourBase = nullptr;        // rank 0: own 2-surface allocation; others: the mapping of it
+		bool colourIsPeer = false;
+		uint32_t frame = 0;                    // frames rendered since the bind (same on every rank)
+		uint32_t* tileCount(uint8_t* base, int set) const { return reinterpret_cast<uint32_t*>(base + 256 + (size_t)set * setBytes); }
+		uint32_t* tileOffset(uint8_t* base, int set) const { return tileCount(base, set) + tilesPad; }
+		uint32_t* binIds(uint8_t* base, int set) const { return tileCount(base, set) + 2 * tilesPad; }
+	} shard;
+	// bin buffers of the newest frame (the DeviceVecs, or one set of the shard arena)
+	uint32_t* curTileCount = nullptr; uint32_t* curTileOffset = nullptr; uint32_t* curBinIds = nullptr;
+
 	// frame state
 	RenderCall last;
 	bool haveFrame = false;
@@ -175,10 +194,11 @@ void mulMat4(const float* lm, const float* rm, float* out)
 int allocSurfaces(b2r_context* c)
 {
 	const size_t n = (size_t)c->width * c->height;
-	CU(c, cudaMalloc((void**)&c->dFramebuffer, n * 4));
+	// two colour surfaces in ONE allocation (pipelined Present; one IPC handle for the sharded mode)
+	CU(c, cudaMalloc((void**)&c->dFramebuffer, 2 * n * 4));
 	CU(c, cudaMalloc((void**)&c->dDepth, n * 4));
-	CU(c, cudaMemset(c->dFramebuffer, 0, n * 4));     // CUDAWindowHelper.h:17-25 zero-initialises
-	c->dColour[0] = c->dFramebuffer;
+	CU(c, cudaMemset(c->dFramebuffer, 0, 2 * n * 4));     // CUDAWindowHelper.h:17-25 zero-initialises
+	c->dColour[0] = c->dFramebuffer; c->dColour[1] = c->dFramebuffer + n;
 	CU(c, cudaMemset(c->dDepth, 0, n * 4));
 	return B2R_OK;
 }
@@ -207,6 +227,7 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 	CU(c, c->dWarpTiles.reserve(n, c->stream));
 	// tile_scan_kernel reads the counts with 16-byte loads
 	CU(c, c->dTileCount.reserve((size_t)n + 4, c->stream));
+	CU(c, c->dTileOffset.reserve((size_t)n + 4, c->stream));    // [n] = overflow marker for peer ranks
 	return B2R_OK;
 }
 
@@ -273,6 +294,7 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.bigRectTiles = 64;
 	fp.nMeshes = (uint32_t)c->meshes.size();
 	fp.packedOutput = (uint32_t)c->packedOutput;
+	fp.shardGeometry = c->shard.bound ? 1u : 0u;
 	return fp;
 }
 
@@ -285,6 +307,8 @@ int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
 	c->lastInfo = *slot.hInfo;
 	if (slot.hInfo->frameInfo[1])
 		c->overflowNeed = std::max(c->overflowNeed, (size_t)slot.hInfo->frameInfo[0]);
+	if (slot.hInfo->frameInfo[7])
+		return fail(c, B2R_E_STATE, "sharded front end: a peer rank did not reach the frame barrier within 4 s");
 	if (slot.timed)
 	{
 		float total = 0.f;
@@ -313,6 +337,24 @@ int enqueueFrame(b2r_context* c)
 	const FrameParams fp = makeParams(c, rc);
 	const uint32_t tiles = nBins(c);
 	c->kernelsLaunched = 0;
+
+	// bin buffers and primitive slice of this frame
+	const b2r_context::Shard& sh = c->shard;
+	const int set = (int)(sh.frame & 1u);
+	uint32_t* tileCount = sh.bound ? sh.tileCount(sh.arena, set) : c->dTileCount.ptr;
+	uint32_t* tileOffset = sh.bound ? sh.tileOffset(sh.arena, set) : c->dTileOffset.ptr;
+	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, set) : c->dBinIds.ptr;
+	const size_t listCap = sh.bound ? sh.listCap : c->dBinIds.cap;
+	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds;
+	uint32_t primLo = 0, primHi = (uint32_t)c->nPrims;
+	if (sh.bound)
+	{
+		// contiguous slices of whole 256-primitive blocks, so that the concatenation of the ranks' lists in
+		// rank order is the ascending list a single GPU builds
+		const uint64_t blocks = (c->nPrims + kChunk - 1) / kChunk;
+		primLo = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)sh.self / (uint64_t)sh.n * kChunk);
+		primHi = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)(sh.self + 1) / (uint64_t)sh.n * kChunk);
+	}
 
 	b2r_context::Slot& slot = c->slots[c->seq % kRing];
 	if (slot.pending)
@@ -351,7 +393,7 @@ int enqueueFrame(b2r_context* c)
 		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, slot.hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
 	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
 	// queue behind the previous frame's 33 MB Present copy
-	frame_clear_kernel<<<(tiles + 4095) / 4096, 256, 0, s>>>(c->dTileCount.ptr, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords);
+	frame_clear_kernel<<<(tiles + 4095) / 4096, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords);
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks)
@@ -362,41 +404,50 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 1);
 	if (c->nTriChunks)
 	{
-		triangle_setup_kernel<<<(uint32_t)((c->nPrims + kChunk - 1) / kChunk), kChunk, 0, s>>>(c->dTriRefs.ptr, c->dPos4.ptr,
-			c->dRects.ptr, c->dTileCount.ptr, c->dBigList.ptr, c->dCounters, 0u, (uint32_t)c->nPrims, fp);
-		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, c->dTileCount.ptr, nullptr, nullptr, nullptr, c->dFrameInfo, fp);
-		c->kernelsLaunched += 2;
+		if (primHi > primLo)
+		{
+			triangle_setup_kernel<<<(primHi - primLo + kChunk - 1) / kChunk, kChunk, 0, s>>>(c->dTriRefs.ptr, c->dPos4.ptr,
+				c->dRects.ptr, tileCount, c->dBigList.ptr, c->dCounters, primLo, primHi, fp);
+			++c->kernelsLaunched;
+		}
+		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, tileCount, nullptr, nullptr, nullptr, c->dFrameInfo, fp);
+		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 2);
-	tile_scan_kernel<<<1, 1024, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dTileCursor.ptr, tiles,
-		(unsigned long long)c->dBinIds.cap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
+	tile_scan_kernel<<<1, 1024, 0, s>>>(tileCount, tileOffset, c->dTileCursor.ptr, tiles,
+		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
 		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
 	++c->kernelsLaunched;
 	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
 	{
-		bin_scatter_kernel<<<(uint32_t)((c->nPrims + 255) / 256), 256, 0, s>>>(c->dRects.ptr, (uint32_t)c->nPrims, c->dTileOffset.ptr,
-			c->dTileCursor.ptr, c->dBinIds.ptr, c->dFrameInfo, fp);
-		bin_big_kernel<true><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, nullptr, c->dTileOffset.ptr,
-			c->dTileCursor.ptr, c->dBinIds.ptr, c->dFrameInfo, fp);
-		c->kernelsLaunched += 2;
+		if (primHi > primLo)
+		{
+			bin_scatter_kernel<<<(primHi - primLo + 255) / 256, 256, 0, s>>>(c->dRects.ptr, primLo, primHi, tileOffset,
+				c->dTileCursor.ptr, binIds, c->dFrameInfo, fp);
+			++c->kernelsLaunched;
+		}
+		bin_big_kernel<true><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, nullptr, tileOffset,
+			c->dTileCursor.ptr, binIds, c->dFrameInfo, fp);
+		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		bin_sort_runs_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, tiles, c->dWarpTiles.ptr, c->dFrameInfo);
-		bin_sort_warp_radix_kernel<<<c->numSMs * 6, 128, 0, s>>>(c->dWarpTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
-		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr, c->dBinIds.ptr, c->dFrameInfo);
-		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, c->dTileCount.ptr, c->dTileOffset.ptr,
-			c->dBinIds.ptr, c->dFrameInfo);
+		bin_sort_runs_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(tileCount, tileOffset, binIds, tiles, c->dWarpTiles.ptr, c->dFrameInfo);
+		bin_sort_warp_radix_kernel<<<c->numSMs * 6, 128, 0, s>>>(c->dWarpTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo);
+		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo);
+		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, tileCount, tileOffset,
+			binIds, c->dFrameInfo);
 		c->kernelsLaunched += 4;
 	}
 	STAGE_EVENT(c, slot, 5);
 	{
 		RasterArgs A{};
-		A.tileCount = c->dTileCount.ptr; A.tileOffset = c->dTileOffset.ptr; A.binIds = c->dBinIds.ptr;
+		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = c->dPos4.ptr; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
 		A.meshes = c->dMeshConst.ptr; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
+		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
 			// this surface is still being copied to the host by an earlier b2r_present_async
@@ -405,6 +456,21 @@ int enqueueFrame(b2r_context* c)
 		}
 		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->colourIdx];
 		c->lastColourIdx = c->colourIdx;
+		PeerFlags pf{};
+		if (sh.bound)
+		{
+			for (int p = 0; p < sh.n; ++p)
+			{
+				uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
+				A.shard.tileCount[p] = sh.tileCount(base, set); A.shard.tileOffset[p] = sh.tileOffset(base, set); A.shard.binIds[p] = sh.binIds(base, set);
+				pf.flags[p] = reinterpret_cast<uint32_t*>(base);
+			}
+			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
+			// "lists ready": nobody reads a peer's lists before that peer has sorted them.  (Rank 0 arrives only
+			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
+			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo);
+			++c->kernelsLaunched;
+		}
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
 		const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
 		if (owned)
@@ -426,6 +492,13 @@ int enqueueFrame(b2r_context* c)
 			default: raster_shade_kernel<true, true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
 			}
 			++c->kernelsLaunched;
+		}
+		if (sh.bound)
+		{
+			// "colours landed": every rank tells rank 0 that its tiles are in rank 0's surface; only rank 0 waits
+			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame + 1u, 0u, sh.self == 0 ? 1u : 0u, c->dFrameInfo);
+			++c->kernelsLaunched;
+			++c->shard.frame;
 		}
 	}
 	STAGE_EVENT(c, slot, 6);
@@ -452,6 +525,13 @@ int validateFrame(b2r_context* c)
 			if (slot.pending) { int r = harvestSlot(c, slot); if (r) return r; }
 		}
 		if (!c->overflowNeed) return B2R_OK;
+		if (c->shard.bound)
+		{
+			const size_t need = c->overflowNeed;
+			c->overflowNeed = 0;
+			return fail(c, B2R_E_STATE, "sharded front end: this rank's bin lists need %zu entries but the shared arena holds %zu; "
+				"b2r_shard_release and b2r_shard_prepare with a larger list_capacity on every rank", need, c->shard.listCap);
+		}
 		const size_t need = c->overflowNeed;
 		c->overflowNeed = 0;
 		CU(c, c->dBinIds.reserve(need + need / 4, c->stream));
@@ -461,6 +541,16 @@ int validateFrame(b2r_context* c)
 	return fail(c, B2R_E_STATE, "bin list capacity could not be satisfied");
 }
 
+}
+
+static void releaseShard(b2r_context* c)
+{
+	b2r_context::Shard& sh = c->shard;
+	for (int p = 0; p < kMaxRanks; ++p)
+		if (sh.peerArena[p]) { cudaIpcCloseMemHandle(sh.peerArena[p]); sh.peerArena[p] = nullptr; }
+	if (sh.colourIsPeer && sh.colourBase) cudaIpcCloseMemHandle(sh.colourBase);
+	if (sh.arena) cudaFree(sh.arena);
+	sh = b2r_context::Shard{};
 }
 
 // ---- self test: the hoisted division of raster_kernel.cuh against __fdiv_rn ------------------
@@ -565,7 +655,7 @@ void b2r_destroy(b2r_context* c)
 	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dWarpTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
-	if (c->dColour[1]) cudaFree(c->dColour[1]);
+	releaseShard(c);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->frameDone) cudaEventDestroy(c->frameDone);
 	for (auto& e : c->copyDone) if (e) cudaEventDestroy(e);
@@ -757,8 +847,6 @@ int b2r_present_async(b2r_context* c, uint32_t* hostPixels)
 		CU(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
 		CU(c, cudaEventCreateWithFlags(&c->frameDone, cudaEventDisableTiming));
 		for (auto& e : c->copyDone) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-		CU(c, cudaMalloc((void**)&c->dColour[1], bytes));
-		CU(c, cudaMemset(c->dColour[1], 0, bytes));
 	}
 	const int idx = c->lastColourIdx;
 	CU(c, cudaEventRecord(c->frameDone, c->stream));
@@ -766,7 +854,7 @@ int b2r_present_async(b2r_context* c, uint32_t* hostPixels)
 	CU(c, cudaMemcpyAsync(hostPixels, c->dColour[idx], bytes, cudaMemcpyDeviceToHost, c->copyStream));
 	CU(c, cudaEventRecord(c->copyDone[idx], c->copyStream));
 	c->copyPending[idx] = true;
-	c->colourIdx = idx ^ 1;          // the next frame renders into the other surface
+	if (!c->shard.bound) c->colourIdx = idx ^ 1;          // the next frame renders into the other surface (sharded: frame parity)
 	return B2R_OK;
 }
 
@@ -824,12 +912,12 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	const uint64_t pairs = c->lastInfo.frameInfo[0];
 	if (total) *total = pairs;
 	const uint32_t n = nBins(c);
-	if (counts) CU(c, cudaMemcpy(counts, c->dTileCount.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
-	if (offsets) CU(c, cudaMemcpy(offsets, c->dTileOffset.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	if (counts) CU(c, cudaMemcpy(counts, c->curTileCount, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	if (offsets) CU(c, cudaMemcpy(offsets, c->curTileOffset, (size_t)n * 4, cudaMemcpyDeviceToHost));
 	if (ids)
 	{
 		if (idsCap < pairs) return fail(c, B2R_E_INVALID, "ids capacity %llu < %llu pairs", (unsigned long long)idsCap, (unsigned long long)pairs);
-		if (pairs) CU(c, cudaMemcpy(ids, c->dBinIds.ptr, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+		if (pairs) CU(c, cudaMemcpy(ids, c->curBinIds, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
 	}
 	return B2R_OK;
 }
@@ -952,6 +1040,69 @@ int b2r_ipc_close(b2r_context* c, void* devicePtr)
 	int r = validateFrame(c); if (r) return r;
 	CU(c, cudaIpcCloseMemHandle(devicePtr));
 	return B2R_OK;
+}
+
+int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity, void* arenaHandle64, void* colourHandle64)
+{
+	if (!c) return B2R_E_INVALID;
+	if (count < 2 || count > kMaxRanks || rank < 0 || rank >= count || !arenaHandle64 || !colourHandle64)
+		return fail(c, B2R_E_INVALID, "shard_prepare: need 2..%d ranks, 0 <= rank < count and two handle buffers", kMaxRanks);
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	if (c->shard.prepared) return fail(c, B2R_E_STATE, "shard_prepare: already prepared (b2r_shard_release first)");
+	if (c->boundFramebuffer || c->packedOutput) return fail(c, B2R_E_STATE, "shard_prepare: incompatible with a bound framebuffer / packed output");
+	if (c->sceneDirty) { r = rebuildScene(c); if (r) return r; }
+	b2r_context::Shard& sh = c->shard;
+	sh.n = count; sh.self = rank;
+	const size_t tiles = nBins(c);
+	sh.tilesPad = (tiles + 4 + 63) & ~(size_t)63;
+	const size_t def = std::max<size_t>((size_t)1 << 22, (c->nPrims + count - 1) / count * 4);
+	sh.listCap = ((listCapacity ? (size_t)listCapacity : def) + 63) & ~(size_t)63;
+	sh.setBytes = (2 * sh.tilesPad + sh.listCap) * 4;
+	const size_t bytes = 256 + 2 * sh.setBytes;
+	CU(c, cudaMalloc((void**)&sh.arena, bytes));
+	CU(c, cudaMemset(sh.arena, 0, bytes));
+	memset(arenaHandle64, 0, 64); memset(colourHandle64, 0, 64);
+	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)arenaHandle64, sh.arena));
+	if (rank == 0) CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)colourHandle64, c->dFramebuffer));
+	c->ownerRank = rank; c->ownerCount = count;
+	sh.prepared = true;
+	return B2R_OK;
+}
+
+int b2r_shard_bind(b2r_context* c, const void* arenaHandles, const void* colourHandleRank0)
+{
+	if (!c) return B2R_E_INVALID;
+	b2r_context::Shard& sh = c->shard;
+	if (!sh.prepared || sh.bound) return fail(c, B2R_E_STATE, "shard_bind: call b2r_shard_prepare first (once)");
+	if (!arenaHandles || !colourHandleRank0) return fail(c, B2R_E_INVALID, "shard_bind: null handles");
+	CU(c, cudaSetDevice(c->device));
+	for (int p = 0; p < sh.n; ++p)
+	{
+		if (p == sh.self) continue;
+		cudaIpcMemHandle_t h; memcpy(&h, (const uint8_t*)arenaHandles + (size_t)p * 64, 64);
+		CU(c, cudaIpcOpenMemHandle((void**)&sh.peerArena[p], h, cudaIpcMemLazyEnablePeerAccess));
+	}
+	if (sh.self == 0) { sh.colourBase = c->dFramebuffer; sh.colourIsPeer = false; }
+	else
+	{
+		cudaIpcMemHandle_t h; memcpy(&h, colourHandleRank0, 64);
+		CU(c, cudaIpcOpenMemHandle((void**)&sh.colourBase, h, cudaIpcMemLazyEnablePeerAccess));
+		sh.colourIsPeer = true;
+	}
+	sh.frame = 0;
+	sh.bound = true;
+	return B2R_OK;
+}
+
+int b2r_shard_release(b2r_context* c)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c);
+	releaseShard(c);
+	c->colourIdx = 0;
+	return r;
 }
 
 int b2r_bind_framebuffer(b2r_context* c, void* devicePtr)

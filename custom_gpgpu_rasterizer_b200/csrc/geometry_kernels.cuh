@@ -119,7 +119,7 @@ __device__ __forceinline__ int bboxCoord(float f, int delta, int limit)
 }
 __device__ __forceinline__ bool tileOwned(const FrameParams& fp, uint32_t tile)
 {
-	return fp.ownerCount <= 1 || (tile % fp.ownerCount) == fp.ownerRank;
+	return fp.ownerCount <= 1 || fp.shardGeometry || (tile % fp.ownerCount) == fp.ownerRank;
 }
 
 
@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 	{
 		frameInfo[0] = sCarry;
 		frameInfo[1] = (sCarry > capacity) ? 1ull : 0ull;
+		tileOffset[nTiles] = (sCarry > capacity) ? 0xFFFFFFFFu : 0u;    // what a peer rank reads (sharded front end)
 		frameInfo[2] = 0ull;
 		frameInfo[3] = sLong;
 		frameInfo[5] = sMid;
@@ -506,15 +507,15 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(
 // scatter of the small rectangles: one thread per primitive, re-reading the 8 B rectangle; the
 // slot inside the tile's list comes from a warp-aggregated atomic on the tile cursor.
 __global__ void __launch_bounds__(256) bin_scatter_kernel(
-	const uint2* __restrict__ rects, uint32_t nPrims, const uint32_t* __restrict__ tileOffset,
+	const uint2* __restrict__ rects, uint32_t primLo, uint32_t primHi, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ binIds,
 	const unsigned long long* __restrict__ frameInfo, FrameParams fp)
 {
 	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
-	const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t prim = primLo + blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t nTiles = 0;
 	int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1, w = 1;
-	if (prim < nPrims)
+	if (prim < primHi)
 	{
 		const uint2 rc = __ldg(rects + prim);
 		bx0 = rc.x & 0xFFFF; by0 = rc.y & 0xFFFF;
@@ -528,6 +529,37 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	}
 	(void)w;
 	warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp);
+}
+
+// Cross-GPU ordering point of the sharded front end (one warp).  Every rank stores `epoch` into its slot of
+// the peers' flag words over NVLink (signalAll) or of rank 0's only, then (wait) spins until all ranks'
+// slots in its OWN flag words have reached the epoch.  The preceding kernels of the stream have completed,
+// so their writes (bin lists; colours stored into rank 0's surface) are visible before the flag.  A peer
+// that never arrives raises frameInfo[7] after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch,
+	uint32_t signalAll, uint32_t wait, unsigned long long* __restrict__ frameInfo)
+{
+	const uint32_t lane = threadIdx.x;
+	__threadfence_system();
+	if (lane < n && (signalAll || lane == 0u))
+		*reinterpret_cast<volatile uint32_t*>(pf.flags[lane] + slotBase + self) = epoch;
+	if (wait && lane < n)
+	{
+		const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(pf.flags[self] + slotBase + lane);
+		const unsigned long long t0 = globalTimerNs();
+		while ((int)(*f - epoch) < 0)
+		{
+			if (globalTimerNs() - t0 > 4000000000ull) { frameInfo[7] = 1ull; break; }
+			__nanosleep(64);
+		}
+	}
+	__threadfence_system();
 }
 
 // per-tile sort of the id lists (ascending primitive id = submission order): makes the lists

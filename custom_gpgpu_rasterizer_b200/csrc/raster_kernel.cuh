@@ -34,6 +34,7 @@ struct RasterArgs
 	int32_t* depth;
 	float* zSurface;        // debug surfaces (may be null)
 	uint32_t* winnerSurface;
+	ShardTable shard;       // sharded front end only: the per-rank lists (fp.shardGeometry)
 };
 
 // expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
@@ -229,8 +230,40 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	uint32_t bestPrim = kNoPrim;
 	uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
 	sKey[tid] = kEmptyKey;
-	const uint32_t n = A.tileCount[bin];
-	const uint32_t* list = A.binIds + A.tileOffset[bin];
+	uint32_t n;
+	const uint32_t* list = nullptr;
+	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
+	if (fp.shardGeometry)
+	{
+		// the tile's list is the concatenation, in rank order, of the lists the ranks built from their
+		// (ascending, disjoint) primitive ranges: read all heads at once, one lane per rank
+		if (tid < 32)
+		{
+			uint32_t cnt = 0, off = 0, bad = 0;
+			if ((uint32_t)tid < fp.ownerCount)
+			{
+				cnt = __ldg(A.shard.tileCount[tid] + bin);
+				off = __ldg(A.shard.tileOffset[tid] + bin);
+				bad = __ldg(A.shard.tileOffset[tid] + fp.binsX * fp.binsY) == 0xFFFFFFFFu;
+			}
+			uint32_t incl = cnt;
+			#pragma unroll
+			for (int d = 1; d < kMaxRanks; d <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+				if (tid >= d) incl += t;
+			}
+			if (__any_sync(0xFFFFFFFFu, bad)) incl = 0;       // a peer overflowed its list buffer: the host re-runs the frame
+			if (tid < kMaxRanks) { sSegEnd[tid] = incl; sSegOff[tid] = off; }
+		}
+		__syncthreads();
+		n = sSegEnd[fp.ownerCount - 1];
+	}
+	else
+	{
+		n = A.tileCount[bin];
+		list = A.binIds + A.tileOffset[bin];
+	}
 
 	for (uint32_t base = 0; base < n; base += kListChunk)
 	{
@@ -239,7 +272,16 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		const uint32_t m = min((uint32_t)kListChunk, n - base);
 		if ((uint32_t)tid < m)
 		{
-			const uint32_t prim = __ldg(list + base + tid);
+			uint32_t prim;
+			if (fp.shardGeometry)
+			{
+				const uint32_t e = base + tid;
+				uint32_t seg = 0;
+				while (e >= sSegEnd[seg]) ++seg;
+				prim = __ldg(A.shard.binIds[seg] + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u)));
+			}
+			else
+				prim = __ldg(list + base + tid);
 			// rebuild the screen-space triangle from the static reference + the transformed positions
 			// (same code, hence the same bits, wherever a triangle is expanded)
 			const uint4 tr = __ldg(A.triRefs + prim);

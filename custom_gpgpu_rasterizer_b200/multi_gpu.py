@@ -12,6 +12,11 @@ each rank's share of the final colours, W*H*4*(world-1)/world bytes per frame:
   so the transfer overlaps the rasterisation tile by tile and no collective moves pixel data -
   only a 4-byte all-reduce per frame orders "everybody has written" before rank 0 unpacks.
 
+* class ShardedSortFirst (b2r_shard_*): the geometry front end is divided as well - rank r sets up, bins
+  and sorts the r-th contiguous slice of the primitives into the lists of ALL tiles; a tile's owner walks
+  the ranks' lists in rank order over NVLink and every rank stores its colours straight into rank 0's
+  surface.  No collective on the data path: two flag barriers per frame inside b2r_render.
+
 The pure index helpers below are shared with the CPU (gloo) tests.
 """
 from __future__ import annotations
@@ -83,6 +88,46 @@ def gather_packed(local, rank: int, world: int, dst: int = 0):
     bufs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
     dist.gather(local, bufs, dst=dst)
     return bufs
+
+
+def prim_slice(n_prims: int, rank: int, world: int, block: int = 256):
+    """[lo, hi) of the primitives rank `rank` sets up and bins in the sharded front end (whole 256-blocks)."""
+    blocks = (n_prims + block - 1) // block
+    lo = min(n_prims, blocks * rank // world * block)
+    hi = min(n_prims, blocks * (rank + 1) // world * block)
+    return lo, hi
+
+
+class ShardedSortFirst:
+    """Sharded front end: exchange the CUDA-IPC handles once; afterwards every Renderer.render() on every
+    rank is one frame of the distributed pipeline and the composed image lives on rank 0."""
+
+    launches_per_frame = 0      # the barrier kernels are counted by b2r_render itself
+
+    def __init__(self, renderer, rank: int, world: int, list_capacity: int = 0):
+        import torch.distributed as dist
+        from . import _lib
+        self.dist, self._lib, self.r, self.rank, self.world = dist, _lib, renderer, rank, world
+        arena, colour = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+        renderer._check(_lib.lib.b2r_shard_prepare(renderer.handle, rank, world, list_capacity, arena, colour))
+        handles: List[Optional[tuple]] = [None] * world
+        dist.all_gather_object(handles, (bytes(arena), bytes(colour)))
+        all_arenas = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(h[0] for h in handles))
+        colour0 = (C.c_ubyte * 64).from_buffer_copy(handles[0][1])
+        renderer._check(_lib.lib.b2r_shard_bind(renderer.handle, all_arenas, colour0))
+        dist.barrier()            # every mapping exists before anybody renders
+        self.bound = True
+
+    def run(self):
+        pass
+
+    def close(self):
+        if self.bound:
+            self.r.sync()
+            self.dist.barrier()   # nobody still reads this rank's arena
+            self.r._check(self._lib.lib.b2r_shard_release(self.r.handle))
+            self.dist.barrier()
+            self.bound = False
 
 
 class SortFirstGather:

@@ -14,7 +14,7 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "sharded"])
 def test_sort_first_two_ranks_matches_single_gpu(mode):
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")

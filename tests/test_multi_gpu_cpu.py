@@ -76,3 +76,66 @@ def test_gloo_gather_composes_full_frame():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_prim_slices_partition_the_primitives():
+    for n in (0, 1, 255, 256, 257, 10_000_000, 1_234_567):
+        for world in (2, 3, 4, 8):
+            cuts = [mg.prim_slice(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            for a, b in zip(cuts, cuts[1:]):
+                assert a[1] == b[0] and a[0] <= a[1]
+            assert all(lo % 256 == 0 for lo, _ in cuts)
+
+
+def _bin_slice(rects, lo, hi, bins_x, n_bins):
+    """numpy model of one rank's front end: ascending per-tile lists of the primitives [lo, hi)."""
+    lists = [[] for _ in range(n_bins)]
+    for prim in range(lo, hi):
+        x0, x1, y0, y1 = rects[prim]
+        for ty in range(y0, y1 + 1):
+            for tx in range(x0, x1 + 1):
+                lists[tx + ty * bins_x].append(prim)
+    return lists
+
+
+def _sharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bins_x, bins_y, n = 12, 9, 3000
+        rng = np.random.default_rng(11)
+        x0 = rng.integers(0, bins_x, n); y0 = rng.integers(0, bins_y, n)
+        rects = np.stack([x0, np.minimum(x0 + rng.integers(0, 3, n), bins_x - 1), y0, np.minimum(y0 + rng.integers(0, 3, n), bins_y - 1)], 1)
+        lo, hi = mg.prim_slice(n, rank, world)
+        mine = _bin_slice(rects, lo, hi, bins_x, bins_x * bins_y)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        # the owner of a tile walks the ranks' lists in rank order: must be the single-GPU ascending list
+        single = _bin_slice(rects, 0, n, bins_x, bins_x * bins_y)
+        ok = True
+        for t in mg.owned_bins(bins_x * bins_y, rank, world):
+            cat = [p for k in range(world) for p in everyone[k][t]]
+            ok &= cat == single[t]
+        q.put(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_sharded_front_end_lists_concatenate_in_rank_order():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True and q.get(timeout=10) is True

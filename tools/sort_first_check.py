@@ -1,5 +1,5 @@
 """torchrun helper: sort-first composition over N ranks must reproduce the single-GPU frame bit for bit.
-usage: python -m torch.distributed.run --nproc-per-node N tools/sort_first_check.py [nccl|p2p]"""
+usage: python -m torch.distributed.run --nproc-per-node N tools/sort_first_check.py [nccl|p2p|sharded]"""
 import os
 import sys
 
@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 from custom_gpgpu_rasterizer_b200 import _lib, scenes
-from custom_gpgpu_rasterizer_b200.multi_gpu import SortFirstGather
+from custom_gpgpu_rasterizer_b200.multi_gpu import ShardedSortFirst, SortFirstGather
 from custom_gpgpu_rasterizer_b200.renderer import Renderer, host_camera
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
@@ -18,32 +18,53 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for sc in (scenes.random_triangles_scene(1000, 600, 500, seed=41, cull=2, textured=True, n_meshes=2),
-           scenes.sphere_grid_scene(1920, 1080, nx=8, ny=5, stacks=41, slices=60, cam_z=20.0)):
+test_scenes = [scenes.random_triangles_scene(1000, 600, 500, seed=41, cull=2, textured=True, n_meshes=2),
+               scenes.sphere_grid_scene(1920, 1080, nx=8, ny=5, stacks=41, slices=60, cam_z=20.0)]
+if mode == "sharded":
+    test_scenes.append(scenes.fill_quads_scene(1280, 720, layers=6))     # big rectangles: cooperative binner
+for sc in test_scenes:
     r = Renderer(sc.width, sc.height, device=local)
-    r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
-    r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
     r.load_scene(sc)
     stream = torch.cuda.Stream()
     r.set_stream(stream.cuda_stream)
     cam = host_camera(sc.cam_pos, sc.fov_deg, sc.width, sc.height, sc.near, sc.far)
-    g = SortFirstGather(r, sc, rank, world, stream, mode=mode)
-    for _ in range(3):                      # several frames: exercises the double buffering
+    if mode == "sharded":
+        g = ShardedSortFirst(r, rank, world)
+    else:
+        r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
+        r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
+        g = SortFirstGather(r, sc, rank, world, stream, mode=mode)
+    for _ in range(5):                      # several frames: exercises the double buffering
         r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
         g.run()
     r.sync()
     dist.barrier()
     torch.cuda.synchronize()
+    lists = None
+    if mode == "sharded":
+        # the per-tile concatenation of the ranks' lists, in rank order, must be the single-GPU list
+        counts, offsets, ids = r.bin_lists()
+        lists = [None] * world
+        dist.all_gather_object(lists, (counts, offsets, ids))
     if rank == 0:
         got = r.framebuffer()
         full = Renderer(sc.width, sc.height, device=local)
         full.load_scene(sc)
         full.render(cam, sc.cull, sc.sample, sc.vis)
         want = full.framebuffer()
-        full.close()
         same = bool(np.array_equal(got, want))
         print(f"sort-first[{mode}] world={world} {sc.name}: {'identical' if same else 'DIFFERENT (%d px)' % int((got != want).sum())}")
         ok &= same
+        if lists is not None:
+            c1, o1, i1 = full.bin_lists()
+            csum = sum(l[0].astype(np.int64) for l in lists)
+            same_l = bool(np.array_equal(csum, c1.astype(np.int64)))
+            for t in np.flatnonzero(c1)[:: max(1, int(np.count_nonzero(c1)) // 500)]:
+                cat = np.concatenate([l[2][l[1][t]: l[1][t] + l[0][t]] for l in lists])
+                same_l &= bool(np.array_equal(cat, i1[o1[t]: o1[t] + c1[t]]))
+            print(f"sort-first[{mode}] world={world} {sc.name} bin lists: {'identical' if same_l else 'DIFFERENT'}")
+            ok &= same_l
+        full.close()
     dist.barrier()
     g.close()
     r.close()
