@@ -261,6 +261,10 @@ def run_b200(args, scene):
     r.sync()
     stages, n_timed = r.stage_ms_mean(reset=True)
     r.set_option(_lib.OPT_STAGE_TIMERS, 0)
+    stages_per_rank = None
+    if world > 1:
+        stages_per_rank = [None] * world
+        dist.all_gather_object(stages_per_rank, {k: round(v, 4) for k, v in stages.items()})
 
     # ---- workload counters for the roofline (instrumented frame, outside every timed region)
     r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
@@ -357,6 +361,7 @@ def run_b200(args, scene):
     }
     if view_parallel is not None:
         line["view_parallel"] = view_parallel
+        line["stages_ms_per_rank"] = stages_per_rank
     if world == 1 and not args.no_cpu_baseline:
         mean_s, _ = cpu_reference_arm(scene, 3, 1)
         line["cpu_baseline"] = {"value": 1.0 / mean_s, "unit": "frames/s", "cores": 1, "kind": "port",
@@ -418,7 +423,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small"])
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
+    ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
     args = ap.parse_args()

@@ -31,7 +31,7 @@ using namespace b2r;
 namespace {
 
 constexpr int kRing = 4;
-constexpr int kInfoWords = 8;
+constexpr int kInfoWords = 16;
 thread_local std::string g_createError;
 
 // grow-only device array
@@ -119,8 +119,8 @@ struct b2r_context
 		MeshConst* hMeshConst = nullptr;           // pinned staging of the per-mesh constants
 		size_t hMeshConstCap = 0;
 		cudaEvent_t done = nullptr;
-		cudaEvent_t ev[B2R_NUM_STAGES] = {};
-		bool pending = false, timed = false;
+		cudaEvent_t ev[10] = {};                    // 0..6 stage boundaries; sharded: 7 after pull, 8 after barrier A, 9 after raster
+		bool pending = false, timed = false, exchanged = false;
 	} slots[kRing];
 	uint64_t seq = 0;
 	HostInfo lastInfo{};                           // info of the newest harvested frame
@@ -151,12 +151,17 @@ struct b2r_context
 		uint8_t* arena = nullptr;
 		size_t tilesPad = 0, listCap = 0, setBytes = 0;
 		uint8_t* peerArena[kMaxRanks] = {};
+		uint32_t* mergedCount = nullptr; uint32_t* mergedOffset = nullptr; uint32_t* mergedIds = nullptr;   // local, owned tiles only
+		size_t mergedCap = 0;
 		uint32_t* colourBase = nullptr;        // rank 0: own 2-surface allocation; others: the mapping of it
 		bool colourIsPeer = false;
 		uint32_t frame = 0;                    // frames rendered since the bind (same on every rank)
+		// arena: 256 B of flag words, then per set {tileCount, tileOffset, inbox count[n], inbox offset[n], binIds}
 		uint32_t* tileCount(uint8_t* base, int set) const { return reinterpret_cast<uint32_t*>(base + 256 + (size_t)set * setBytes); }
 		uint32_t* tileOffset(uint8_t* base, int set) const { return tileCount(base, set) + tilesPad; }
-		uint32_t* binIds(uint8_t* base, int set) const { return tileCount(base, set) + 2 * tilesPad; }
+		uint32_t* inboxCount(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + src) * tilesPad; }
+		uint32_t* inboxOffset(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + n + src) * tilesPad; }
+		uint32_t* binIds(uint8_t* base, int set) const { return tileCount(base, set) + (size_t)(2 + 2 * n) * tilesPad; }
 	} shard;
 	// bin buffers of the newest frame (the DeviceVecs, or one set of the shard arena)
 	uint32_t* curTileCount = nullptr; uint32_t* curTileOffset = nullptr; uint32_t* curBinIds = nullptr;
@@ -321,6 +326,20 @@ int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
 		float ms = 0.f;
 		CU(c, cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[6]));
 		c->stageLast[B2R_STAGE_TOTAL] = ms; c->stageAccum[B2R_STAGE_TOTAL] += ms;
+		float pull = 0.f, wait = 0.f;
+		if (slot.exchanged)
+		{
+			float waitA = 0.f, raster = 0.f, waitB = 0.f;
+			CU(c, cudaEventElapsedTime(&waitA, slot.ev[5], slot.ev[8]));
+			CU(c, cudaEventElapsedTime(&pull, slot.ev[8], slot.ev[7]));
+			CU(c, cudaEventElapsedTime(&raster, slot.ev[7], slot.ev[9]));
+			CU(c, cudaEventElapsedTime(&waitB, slot.ev[9], slot.ev[6]));
+			wait = waitA + waitB;
+			c->stageAccum[B2R_STAGE_RASTER_SHADE] += raster - c->stageLast[B2R_STAGE_RASTER_SHADE];
+			c->stageLast[B2R_STAGE_RASTER_SHADE] = raster;
+		}
+		c->stageLast[B2R_STAGE_EXCHANGE] = pull; c->stageAccum[B2R_STAGE_EXCHANGE] += pull;
+		c->stageLast[B2R_STAGE_PEER_WAIT] = wait; c->stageAccum[B2R_STAGE_PEER_WAIT] += wait;
 		++c->stageFrames;
 		c->haveStageTimes = true;
 	}
@@ -369,6 +388,7 @@ int enqueueFrame(b2r_context* c)
 		CU(c, cudaMallocHost((void**)&slot.hMeshConst, slot.hMeshConstCap * sizeof(MeshConst)));
 	}
 	slot.timed = c->stageTimers != 0;
+	slot.exchanged = slot.timed && c->shard.bound;
 
 	// per-mesh constants
 	for (size_t m = 0; m < c->meshes.size(); ++m)
@@ -418,6 +438,18 @@ int enqueueFrame(b2r_context* c)
 		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
 		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
 	++c->kernelsLaunched;
+	if (sh.bound)
+	{
+		// the heads of this rank's lists go to the tiles' owners now, so the transfer hides behind scatter + sort
+		ShardInbox inbox{};
+		for (int p = 0; p < sh.n; ++p)
+		{
+			uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
+			inbox.tileCount[p] = sh.inboxCount(base, set, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, set, sh.self);
+		}
+		shard_push_heads_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n);
+		++c->kernelsLaunched;
+	}
 	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
 	{
@@ -457,12 +489,14 @@ int enqueueFrame(b2r_context* c)
 		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->colourIdx];
 		c->lastColourIdx = c->colourIdx;
 		PeerFlags pf{};
+		const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
 		if (sh.bound)
 		{
+			ShardTable T{};
 			for (int p = 0; p < sh.n; ++p)
 			{
 				uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
-				A.shard.tileCount[p] = sh.tileCount(base, set); A.shard.tileOffset[p] = sh.tileOffset(base, set); A.shard.binIds[p] = sh.binIds(base, set);
+				T.tileCount[p] = sh.inboxCount(sh.arena, set, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, set, p); T.binIds[p] = sh.binIds(base, set);
 				pf.flags[p] = reinterpret_cast<uint32_t*>(base);
 			}
 			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
@@ -470,9 +504,17 @@ int enqueueFrame(b2r_context* c)
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
 			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo);
 			++c->kernelsLaunched;
+			STAGE_EVENT(c, slot, 8);
+			if (owned)
+			{
+				shard_pull_kernel<<<(owned + 7) / 8, 256, 0, s>>>(T, owned, sh.mergedCount, sh.mergedOffset, sh.mergedIds, (unsigned long long)sh.mergedCap,
+					c->dFrameInfo, fp);
+				++c->kernelsLaunched;
+			}
+			A.tileCount = sh.mergedCount; A.tileOffset = sh.mergedOffset; A.binIds = sh.mergedIds;
+			STAGE_EVENT(c, slot, 7);
 		}
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
-		const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
 		if (owned)
 		{
 			const dim3 grid(owned, fp.subX * fp.subY);
@@ -495,6 +537,7 @@ int enqueueFrame(b2r_context* c)
 		}
 		if (sh.bound)
 		{
+			STAGE_EVENT(c, slot, 9);
 			// "colours landed": every rank tells rank 0 that its tiles are in rank 0's surface; only rank 0 waits
 			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame + 1u, 0u, sh.self == 0 ? 1u : 0u, c->dFrameInfo);
 			++c->kernelsLaunched;
@@ -550,6 +593,7 @@ static void releaseShard(b2r_context* c)
 		if (sh.peerArena[p]) { cudaIpcCloseMemHandle(sh.peerArena[p]); sh.peerArena[p] = nullptr; }
 	if (sh.colourIsPeer && sh.colourBase) cudaIpcCloseMemHandle(sh.colourBase);
 	if (sh.arena) cudaFree(sh.arena);
+	if (sh.mergedCount) cudaFree(sh.mergedCount);
 	sh = b2r_context::Shard{};
 }
 
@@ -1058,10 +1102,14 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	sh.tilesPad = (tiles + 4 + 63) & ~(size_t)63;
 	const size_t def = std::max<size_t>((size_t)1 << 22, (c->nPrims + count - 1) / count * 4);
 	sh.listCap = ((listCapacity ? (size_t)listCapacity : def) + 63) & ~(size_t)63;
-	sh.setBytes = (2 * sh.tilesPad + sh.listCap) * 4;
+	sh.setBytes = ((size_t)(2 + 2 * count) * sh.tilesPad + sh.listCap) * 4;
 	const size_t bytes = 256 + 2 * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));
 	CU(c, cudaMemset(sh.arena, 0, bytes));
+	// local merged lists of the owned tiles, addressed like a single GPU's list buffer (offset = sum of the ranks' offsets)
+	sh.mergedCap = std::min<size_t>(sh.listCap * (size_t)count, 0xFFFFFFF0ull);
+	CU(c, cudaMalloc((void**)&sh.mergedCount, 2 * sh.tilesPad * 4 + sh.mergedCap * 4));
+	sh.mergedOffset = sh.mergedCount + sh.tilesPad; sh.mergedIds = sh.mergedCount + 2 * sh.tilesPad;
 	memset(arenaHandle64, 0, 64); memset(colourHandle64, 0, 64);
 	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)arenaHandle64, sh.arena));
 	if (rank == 0) CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)colourHandle64, c->dFramebuffer));

@@ -34,7 +34,6 @@ struct RasterArgs
 	int32_t* depth;
 	float* zSurface;        // debug surfaces (may be null)
 	uint32_t* winnerSurface;
-	ShardTable shard;       // sharded front end only: the per-rank lists (fp.shardGeometry)
 };
 
 // expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
@@ -212,7 +211,8 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	__shared__ uint32_t sNumBig;
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
-	const uint32_t bin = fp.ownerRank + blockIdx.x * fp.ownerCount;
+	const uint32_t ownedIdx = blockIdx.x;
+	const uint32_t bin = fp.ownerRank + ownedIdx * fp.ownerCount;
 	const uint32_t binX = bin % fp.binsX, binY = bin / fp.binsX;
 	const uint32_t subX = blockIdx.y % fp.subX, subY = blockIdx.y / fp.subX;
 	const int tid = threadIdx.x;
@@ -230,40 +230,8 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	uint32_t bestPrim = kNoPrim;
 	uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
 	sKey[tid] = kEmptyKey;
-	uint32_t n;
-	const uint32_t* list = nullptr;
-	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
-	if (fp.shardGeometry)
-	{
-		// the tile's list is the concatenation, in rank order, of the lists the ranks built from their
-		// (ascending, disjoint) primitive ranges: read all heads at once, one lane per rank
-		if (tid < 32)
-		{
-			uint32_t cnt = 0, off = 0, bad = 0;
-			if ((uint32_t)tid < fp.ownerCount)
-			{
-				cnt = __ldg(A.shard.tileCount[tid] + bin);
-				off = __ldg(A.shard.tileOffset[tid] + bin);
-				bad = __ldg(A.shard.tileOffset[tid] + fp.binsX * fp.binsY) == 0xFFFFFFFFu;
-			}
-			uint32_t incl = cnt;
-			#pragma unroll
-			for (int d = 1; d < kMaxRanks; d <<= 1)
-			{
-				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-				if (tid >= d) incl += t;
-			}
-			if (__any_sync(0xFFFFFFFFu, bad)) incl = 0;       // a peer overflowed its list buffer: the host re-runs the frame
-			if (tid < kMaxRanks) { sSegEnd[tid] = incl; sSegOff[tid] = off; }
-		}
-		__syncthreads();
-		n = sSegEnd[fp.ownerCount - 1];
-	}
-	else
-	{
-		n = A.tileCount[bin];
-		list = A.binIds + A.tileOffset[bin];
-	}
+	const uint32_t n = A.tileCount[bin];
+	const uint32_t* list = A.binIds + A.tileOffset[bin];
 
 	for (uint32_t base = 0; base < n; base += kListChunk)
 	{
@@ -272,16 +240,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		const uint32_t m = min((uint32_t)kListChunk, n - base);
 		if ((uint32_t)tid < m)
 		{
-			uint32_t prim;
-			if (fp.shardGeometry)
-			{
-				const uint32_t e = base + tid;
-				uint32_t seg = 0;
-				while (e >= sSegEnd[seg]) ++seg;
-				prim = __ldg(A.shard.binIds[seg] + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u)));
-			}
-			else
-				prim = __ldg(list + base + tid);
+			const uint32_t prim = __ldg(list + base + tid);
 			// rebuild the screen-space triangle from the static reference + the transformed positions
 			// (same code, hence the same bits, wherever a triangle is expanded)
 			const uint4 tr = __ldg(A.triRefs + prim);
@@ -441,7 +400,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	}
 	// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
 	// gathered with one contiguous NCCL transfer / written straight into a peer's memory
-	if (fp.packedOutput) A.framebuffer[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * (kTile * kTile) + tid] = colour;
+	if (fp.packedOutput) A.framebuffer[((size_t)ownedIdx * gridDim.y + blockIdx.y) * (kTile * kTile) + tid] = colour;
 	else A.framebuffer[pix] = colour;
 	A.depth[pix] = depthOut;
 	if (fp.debugSurfaces)
@@ -451,6 +410,102 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	}
 }
 
+
+// Sharded front end: bring the lists of one owned tile together.  Rank p built the ascending list of ITS
+// primitive slice for every tile; the slices are contiguous and ordered by rank, so the tile's full list is
+// the concatenation in rank order.  Every rank pushed the heads (count, offset) of its lists into the
+// owners' inboxes right after its scan (shard_push_heads_kernel), so here one WARP per owned tile reads the
+// n heads from local memory and copies the segments - the peers' over NVLink, one hop - into the local
+// merged buffer; the raster kernel then runs on local memory exactly as on a single GPU.  No scan is needed
+// for the merged offsets: every rank's offset[t] is the exclusive prefix of its own counts, so their SUM is
+// the exclusive prefix of the summed counts.
+__global__ void __launch_bounds__(256) shard_push_heads_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
+	uint32_t nTiles, ShardInbox inbox, uint32_t nRanks)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < nTiles)
+	{
+		const uint32_t owner = t % nRanks;
+		inbox.tileCount[owner][t] = tileCount[t];
+		inbox.tileOffset[owner][t] = tileOffset[t];
+	}
+	if (t < nRanks) inbox.tileOffset[t][nTiles] = tileOffset[nTiles];      // overflow marker, to everybody
+}
+
+__global__ void __launch_bounds__(256) shard_pull_kernel(ShardTable T, uint32_t nOwned, uint32_t* __restrict__ mergedCount, uint32_t* __restrict__ mergedOffset,
+	uint32_t* __restrict__ mergedIds, unsigned long long mergedCap, unsigned long long* __restrict__ frameInfo, FrameParams fp)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (k >= nOwned) return;
+	const uint32_t bin = fp.ownerRank + k * fp.ownerCount;
+	uint32_t cnt = 0, off = 0, bad = 0;
+	if (lane < fp.ownerCount)
+	{
+		cnt = __ldg(T.tileCount[lane] + bin);
+		off = __ldg(T.tileOffset[lane] + bin);
+		bad = __ldg(T.tileOffset[lane] + fp.binsX * fp.binsY) == 0xFFFFFFFFu;   // that rank's list buffer overflowed
+	}
+	// the segments are fetched as ALIGNED 16-byte vectors (a few ids of the neighbouring lists ride along and
+	// are dropped): NVLink needs many bytes in flight per thread to reach its bandwidth
+	const uint32_t vecLo = off >> 2, vecs = cnt ? ((off + cnt + 3) >> 2) - vecLo : 0u;
+	uint32_t incl = cnt, vIncl = vecs;
+	unsigned long long base = off;
+	#pragma unroll
+	for (int d = 1; d < kMaxRanks; d <<= 1)
+	{
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d), tv = __shfl_up_sync(0xFFFFFFFFu, vIncl, d);
+		if (lane >= (uint32_t)d) { incl += t; vIncl += tv; }
+	}
+	#pragma unroll
+	for (int d = kMaxRanks / 2; d > 0; d >>= 1) base += __shfl_down_sync(0xFFFFFFFFu, base, d);
+	base = __shfl_sync(0xFFFFFFFFu, base, 0);
+	uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, kMaxRanks - 1);
+	uint32_t totalVecs = __shfl_sync(0xFFFFFFFFu, vIncl, kMaxRanks - 1);
+	const bool overflow = __any_sync(0xFFFFFFFFu, bad) || base + total > mergedCap;
+	if (overflow) { total = 0; totalVecs = 0; if (lane == 0) frameInfo[1] = 1ull; }
+	if (lane == 0)
+	{
+		mergedCount[bin] = total;
+		mergedOffset[bin] = overflow ? 0u : (uint32_t)base;
+	}
+	uint32_t* dst = mergedIds + (uint32_t)base;
+	constexpr int kUnroll = 2;
+	for (uint32_t v0 = 0; v0 < totalVecs; v0 += 32 * kUnroll)
+	{
+		uint4 val[kUnroll];
+		uint32_t first[kUnroll], lo[kUnroll], hi[kUnroll];     // merged position of val.x, and the valid window
+		#pragma unroll
+		for (int u = 0; u < kUnroll; ++u)
+		{
+			const uint32_t v = v0 + (uint32_t)u * 32u + lane;
+			uint32_t seg = 0;
+			for (uint32_t s = 0; s + 1 < fp.ownerCount; ++s)
+				if (v >= __shfl_sync(0xFFFFFFFFu, vIncl, s)) seg = s + 1;
+			const uint32_t sVEnd = __shfl_sync(0xFFFFFFFFu, vIncl, seg), sVecs = __shfl_sync(0xFFFFFFFFu, vecs, seg), sVecLo = __shfl_sync(0xFFFFFFFFu, vecLo, seg);
+			const uint32_t sEnd = __shfl_sync(0xFFFFFFFFu, incl, seg), sCnt = __shfl_sync(0xFFFFFFFFu, cnt, seg), sOff = __shfl_sync(0xFFFFFFFFu, off, seg);
+			val[u] = make_uint4(0, 0, 0, 0); first[u] = 0; lo[u] = 0; hi[u] = 0;      // empty window: nothing stored
+			if (v < totalVecs)
+			{
+				const uint32_t vec = sVecLo + (v - (sVEnd - sVecs));                 // 16-byte vector index in the source buffer
+				val[u] = __ldg(reinterpret_cast<const uint4*>(T.binIds[seg]) + vec);
+				lo[u] = sEnd - sCnt; hi[u] = sEnd;                                   // merged range of this segment
+				first[u] = lo[u] + (vec << 2) - sOff;                                // may wrap below lo: compared modulo 2^32 below
+			}
+		}
+		#pragma unroll
+		for (int u = 0; u < kUnroll; ++u)
+		{
+			const uint32_t w[4] = { val[u].x, val[u].y, val[u].z, val[u].w };
+			#pragma unroll
+			for (uint32_t q = 0; q < 4; ++q)
+			{
+				const uint32_t pos = first[u] + q;
+				if (pos - lo[u] < hi[u] - lo[u]) dst[pos] = w[q];
+			}
+		}
+	}
+}
 
 // sort-first composition on the gathering rank: scatter one rank's packed tile-major colours back
 // into the row-major framebuffer (tile owner = tile index mod count)

@@ -73,7 +73,10 @@ enum
 enum
 {
 	B2R_STAGE_VERTEX = 0, B2R_STAGE_SETUP = 1, B2R_STAGE_BIN_SCAN = 2, B2R_STAGE_BIN_SCATTER = 3,
-	B2R_STAGE_BIN_SORT = 4, B2R_STAGE_RASTER_SHADE = 5, B2R_STAGE_TOTAL = 6, B2R_NUM_STAGES = 7
+	B2R_STAGE_BIN_SORT = 4, B2R_STAGE_RASTER_SHADE = 5, B2R_STAGE_TOTAL = 6,
+	/* sharded front end only (0 otherwise): EXCHANGE = pulling the peers' lists over NVLink,
+	 * PEER_WAIT = time inside the two flag barriers (waiting for the slowest rank's lists / colours) */
+	B2R_STAGE_EXCHANGE = 7, B2R_STAGE_PEER_WAIT = 8, B2R_NUM_STAGES = 9
 };
 
 /* error text of the last failing call on this context (NULL context: last b2r_create failure) */
