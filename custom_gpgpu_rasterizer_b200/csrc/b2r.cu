@@ -151,17 +151,16 @@ struct b2r_context
 		uint8_t* arena = nullptr;
 		size_t tilesPad = 0, listCap = 0, setBytes = 0;
 		uint8_t* peerArena[kMaxRanks] = {};
-		uint32_t* mergedCount = nullptr; uint32_t* mergedOffset = nullptr; uint32_t* mergedIds = nullptr;   // local, owned tiles only
-		size_t mergedCap = 0;
 		uint32_t* colourBase = nullptr;        // rank 0: own 2-surface allocation; others: the mapping of it
 		bool colourIsPeer = false;
 		uint32_t frame = 0;                    // frames rendered since the bind (same on every rank)
-		// arena: 256 B of flag words, then per set {tileCount, tileOffset, inbox count[n], inbox offset[n], binIds}
+		// arena: 256 B of flag words, then per set {tileCount, tileOffset, inbox count[n], inbox offset[n], binIds, region[n]}
 		uint32_t* tileCount(uint8_t* base, int set) const { return reinterpret_cast<uint32_t*>(base + 256 + (size_t)set * setBytes); }
 		uint32_t* tileOffset(uint8_t* base, int set) const { return tileCount(base, set) + tilesPad; }
 		uint32_t* inboxCount(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + src) * tilesPad; }
 		uint32_t* inboxOffset(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + n + src) * tilesPad; }
 		uint32_t* binIds(uint8_t* base, int set) const { return tileCount(base, set) + (size_t)(2 + 2 * n) * tilesPad; }
+		uint32_t* region(uint8_t* base, int set, int src) const { return binIds(base, set) + (size_t)(1 + src) * listCap; }   // lists pushed by rank src
 	} shard;
 	// bin buffers of the newest frame (the DeviceVecs, or one set of the shard arena)
 	uint32_t* curTileCount = nullptr; uint32_t* curTileOffset = nullptr; uint32_t* curBinIds = nullptr;
@@ -413,7 +412,8 @@ int enqueueFrame(b2r_context* c)
 		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, slot.hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
 	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
 	// queue behind the previous frame's 33 MB Present copy
-	frame_clear_kernel<<<(tiles + 4095) / 4096, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords);
+	frame_clear_kernel<<<(tiles + 4095) / 4096, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
+		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta));
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks)
@@ -434,7 +434,7 @@ int enqueueFrame(b2r_context* c)
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 2);
-	tile_scan_kernel<<<1, 1024, 0, s>>>(tileCount, tileOffset, c->dTileCursor.ptr, tiles,
+	tile_scan_kernel<<<(tiles + kScanPerCta - 1) / kScanPerCta, kScanThreads, 0, s>>>(tileCount, tileOffset, c->dTileCursor.ptr, tiles,
 		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
 		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
 	++c->kernelsLaunched;
@@ -473,6 +473,14 @@ int enqueueFrame(b2r_context* c)
 			binIds, c->dFrameInfo);
 		c->kernelsLaunched += 4;
 	}
+	if (sh.bound && c->nPrims)
+	{
+		// mirror the sorted lists into their owners' memory (posted stores; landed by the time of the barrier)
+		ShardRegions R{};
+		for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], set, sh.self);
+		shard_push_lists_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, c->dFrameInfo);
+		++c->kernelsLaunched;
+	}
 	STAGE_EVENT(c, slot, 5);
 	{
 		RasterArgs A{};
@@ -496,7 +504,8 @@ int enqueueFrame(b2r_context* c)
 			for (int p = 0; p < sh.n; ++p)
 			{
 				uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
-				T.tileCount[p] = sh.inboxCount(sh.arena, set, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, set, p); T.binIds[p] = sh.binIds(base, set);
+				T.tileCount[p] = sh.inboxCount(sh.arena, set, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, set, p);
+				T.binIds[p] = (p == sh.self) ? sh.binIds(sh.arena, set) : sh.region(sh.arena, set, p);
 				pf.flags[p] = reinterpret_cast<uint32_t*>(base);
 			}
 			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
@@ -505,13 +514,7 @@ int enqueueFrame(b2r_context* c)
 			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo);
 			++c->kernelsLaunched;
 			STAGE_EVENT(c, slot, 8);
-			if (owned)
-			{
-				shard_pull_kernel<<<(owned + 7) / 8, 256, 0, s>>>(T, owned, sh.mergedCount, sh.mergedOffset, sh.mergedIds, (unsigned long long)sh.mergedCap,
-					c->dFrameInfo, fp);
-				++c->kernelsLaunched;
-			}
-			A.tileCount = sh.mergedCount; A.tileOffset = sh.mergedOffset; A.binIds = sh.mergedIds;
+			A.shard = T;
 			STAGE_EVENT(c, slot, 7);
 		}
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
@@ -593,7 +596,6 @@ static void releaseShard(b2r_context* c)
 		if (sh.peerArena[p]) { cudaIpcCloseMemHandle(sh.peerArena[p]); sh.peerArena[p] = nullptr; }
 	if (sh.colourIsPeer && sh.colourBase) cudaIpcCloseMemHandle(sh.colourBase);
 	if (sh.arena) cudaFree(sh.arena);
-	if (sh.mergedCount) cudaFree(sh.mergedCount);
 	sh = b2r_context::Shard{};
 }
 
@@ -1102,14 +1104,10 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	sh.tilesPad = (tiles + 4 + 63) & ~(size_t)63;
 	const size_t def = std::max<size_t>((size_t)1 << 22, (c->nPrims + count - 1) / count * 4);
 	sh.listCap = ((listCapacity ? (size_t)listCapacity : def) + 63) & ~(size_t)63;
-	sh.setBytes = ((size_t)(2 + 2 * count) * sh.tilesPad + sh.listCap) * 4;
+	sh.setBytes = ((size_t)(2 + 2 * count) * sh.tilesPad + sh.listCap * (size_t)(1 + count)) * 4;
 	const size_t bytes = 256 + 2 * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));
 	CU(c, cudaMemset(sh.arena, 0, bytes));
-	// local merged lists of the owned tiles, addressed like a single GPU's list buffer (offset = sum of the ranks' offsets)
-	sh.mergedCap = std::min<size_t>(sh.listCap * (size_t)count, 0xFFFFFFF0ull);
-	CU(c, cudaMalloc((void**)&sh.mergedCount, 2 * sh.tilesPad * 4 + sh.mergedCap * 4));
-	sh.mergedOffset = sh.mergedCount + sh.tilesPad; sh.mergedIds = sh.mergedCount + 2 * sh.tilesPad;
 	memset(arenaHandle64, 0, 64); memset(colourHandle64, 0, 64);
 	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)arenaHandle64, sh.arena));
 	if (rank == 0) CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)colourHandle64, c->dFramebuffer));

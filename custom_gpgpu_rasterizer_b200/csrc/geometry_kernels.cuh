@@ -129,8 +129,9 @@ __device__ __forceinline__ bool tileOwned(const FrameParams& fp, uint32_t tile)
 // warp-wide maximum of nTiles); lanes with k >= nTiles pass tile = kNoTile.
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 // counters[]: [0] visible triangles (summed by tile_scan_kernel), [1] big triangles,
-// [kVisBase + 32*s] partial visible counts, one 128-byte line per slot
-constexpr uint32_t kVisSlots = 64, kVisBase = 32, kCounterWords = kVisBase + kVisSlots * 32;
+// [kVisBase + 32*s] partial visible counts, one 128-byte line per slot,
+// [kScanBase ...] the 64-bit slice sums of the chained tile scan
+constexpr uint32_t kVisSlots = 64, kVisBase = 32, kScanBase = kVisBase + kVisSlots * 32 /* 8-byte aligned */, kScanMaxCtas = 2048 /* 2048 x 2048 tiles = a 32767^2 screen */, kCounterWords = kScanBase + 2 * kScanMaxCtas;
 template <bool RETURN>
 __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t tile)
 {
@@ -153,14 +154,14 @@ __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t til
 
 // start of frame: zero the tile counts (tileCount is padded to a multiple of 4 words) and the counters
 __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__ tileCount, uint32_t nTiles,
-	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords)
+	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords)
 {
 	const uint32_t q = (nTiles + 3) / 4;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < q; i += gridDim.x * blockDim.x)
 		reinterpret_cast<uint4*>(tileCount)[i] = make_uint4(0, 0, 0, 0);
 	if (blockIdx.x == 0)
 	{
-		for (uint32_t i = threadIdx.x; i < kCounterWords; i += blockDim.x) counters[i] = 0;
+		for (uint32_t i = threadIdx.x; i < counterWords; i += blockDim.x) counters[i] = 0;
 		if (threadIdx.x < infoWords) frameInfo[threadIdx.x] = 0;
 	}
 }
@@ -392,115 +393,125 @@ __global__ void __launch_bounds__(256) bin_big_kernel(
 	}
 }
 
-// exclusive scan of the per-tile counts (single CTA; the tile grid is at most a few 100k entries).
-// Every thread owns 32 consecutive tiles (one 128-byte line), so a 4K frame (32 400 tiles) is one
-// pass.  Also clears the cursors, publishes the pair total / overflow flag and builds the two
-// work lists of the list sorter (tiles whose list is too long for the warp-level sort).
-constexpr uint32_t kScanPerThread = 32;
-__global__ void __launch_bounds__(1024) tile_scan_kernel(
+// exclusive scan of the per-tile counts: a chained scan over a handful of co-resident CTAs (2048 tiles
+// each; a 4K frame is 16 CTAs).  Every CTA publishes the sum of its slice, adds up the published sums of
+// its predecessors (they are all resident, so spinning is safe) and scans its slice locally.  Also clears
+// the cursors, publishes the pair total / overflow flag and builds the two work lists of the list sorter
+// (tiles whose list is too long for the warp-level sort).
+constexpr uint32_t kScanThreads = 256, kScanPerThread = 8, kScanPerCta = kScanThreads * kScanPerThread;
+__global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
 	uint32_t nTiles, unsigned long long capacity, uint32_t midThreshold, uint32_t longThreshold,
 	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
 	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles; [6] is the run sorter's fallback count*/)
 {
-	if (threadIdx.x < 32)
+	// published slice sums: bit 63 = ready (frame_clear_kernel zeroes them)
+	volatile unsigned long long* partial = reinterpret_cast<volatile unsigned long long*>(counters + kScanBase);
+	if (blockIdx.x == 0 && threadIdx.x < 32)
 	{
 		uint32_t v = counters[kVisBase + threadIdx.x * 32] + counters[kVisBase + (threadIdx.x + 32) * 32];
 		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
 		if (threadIdx.x == 0) counters[0] = v;
 	}
-	__shared__ unsigned long long sWarp[32];
-	__shared__ unsigned long long sCarry;
-	__shared__ uint32_t sLong, sMid;
-	if (threadIdx.x == 0) { sCarry = 0; sLong = 0; sMid = 0; }
-	__syncthreads();
+	__shared__ unsigned long long sWarp[kScanThreads / 32];
+	__shared__ unsigned long long sPrefix;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (uint32_t base = 0; base < nTiles; base += 1024 * kScanPerThread)
+	const uint32_t first = blockIdx.x * kScanPerCta + threadIdx.x * kScanPerThread;
+	uint32_t v[kScanPerThread];
+	unsigned long long sum = 0;
+	#pragma unroll
+	for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
 	{
-		const uint32_t first = base + threadIdx.x * kScanPerThread;
-		uint32_t v[kScanPerThread];
-		unsigned long long sum = 0;
-		#pragma unroll
-		for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
+		uint4 t = make_uint4(0, 0, 0, 0);
+		const uint32_t i = first + q * 4;
+		if (i + 3 < nTiles) t = *reinterpret_cast<const uint4*>(tileCount + i);
+		else
 		{
-			uint4 t = make_uint4(0, 0, 0, 0);
-			const uint32_t i = first + q * 4;
-			if (i + 3 < nTiles) t = *reinterpret_cast<const uint4*>(tileCount + i);
-			else
-			{
-				if (i < nTiles) t.x = tileCount[i];
-				if (i + 1 < nTiles) t.y = tileCount[i + 1];
-				if (i + 2 < nTiles) t.z = tileCount[i + 2];
-			}
-			v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-			sum += (unsigned long long)t.x + t.y + t.z + t.w;
+			if (i < nTiles) t.x = tileCount[i];
+			if (i + 1 < nTiles) t.y = tileCount[i + 1];
+			if (i + 2 < nTiles) t.z = tileCount[i + 2];
 		}
-		unsigned long long incl = sum;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-			if (lane >= (uint32_t)d) incl += t;
-		}
-		if (lane == 31) sWarp[warp] = incl;
-		__syncthreads();
-		if (warp == 0)
-		{
-			unsigned long long w = sWarp[lane];
-			#pragma unroll
-			for (int d = 1; d < 32; d <<= 1)
-			{
-				const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, w, d);
-				if (lane >= (uint32_t)d) w += t;
-			}
-			sWarp[lane] = w;
-		}
-		__syncthreads();
-		const unsigned long long carry = sCarry;
-		unsigned long long run = carry + (warp ? sWarp[warp - 1] : 0ull) + incl - sum;
-		#pragma unroll
-		for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
-		{
-			const uint32_t i = first + q * 4;
-			uint4 o;
-			o.x = (uint32_t)run; run += v[q * 4];
-			o.y = (uint32_t)run; run += v[q * 4 + 1];
-			o.z = (uint32_t)run; run += v[q * 4 + 2];
-			o.w = (uint32_t)run; run += v[q * 4 + 3];
-			if (i + 3 < nTiles)
-			{
-				*reinterpret_cast<uint4*>(tileOffset + i) = o;
-				*reinterpret_cast<uint4*>(tileCursor + i) = make_uint4(0, 0, 0, 0);
-			}
-			else
-			{
-				if (i < nTiles) { tileOffset[i] = o.x; tileCursor[i] = 0; }
-				if (i + 1 < nTiles) { tileOffset[i + 1] = o.y; tileCursor[i + 1] = 0; }
-				if (i + 2 < nTiles) { tileOffset[i + 2] = o.z; tileCursor[i + 2] = 0; }
-			}
-			#pragma unroll
-			for (uint32_t e = 0; e < 4; ++e)
-			{
-				const uint32_t c = v[q * 4 + e];
-				if (i + e < nTiles && c > midThreshold)
-				{
-					if (c > longThreshold) longTiles[atomicAdd(&sLong, 1u)] = i + e;
-					else midTiles[atomicAdd(&sMid, 1u)] = i + e;
-				}
-			}
-		}
-		__syncthreads();
-		if (threadIdx.x == 1023) sCarry = carry + sWarp[31];
-		__syncthreads();
+		v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+		sum += (unsigned long long)t.x + t.y + t.z + t.w;
 	}
-	if (threadIdx.x == 0)
+	unsigned long long incl = sum;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
 	{
-		frameInfo[0] = sCarry;
-		frameInfo[1] = (sCarry > capacity) ? 1ull : 0ull;
-		tileOffset[nTiles] = (sCarry > capacity) ? 0xFFFFFFFFu : 0u;    // what a peer rank reads (sharded front end)
-		frameInfo[2] = 0ull;
-		frameInfo[3] = sLong;
-		frameInfo[5] = sMid;
+		const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= (uint32_t)d) incl += t;
+	}
+	if (lane == 31) sWarp[warp] = incl;
+	__syncthreads();
+	if (warp == 0)
+	{
+		// block total -> publish; then the sum of the predecessors' totals
+		unsigned long long w = lane < kScanThreads / 32 ? sWarp[lane] : 0ull;
+		#pragma unroll
+		for (int d = 1; d < (int)(kScanThreads / 32); d <<= 1)
+		{
+			const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, w, d);
+			if (lane >= (uint32_t)d) w += t;
+		}
+		if (lane < kScanThreads / 32) sWarp[lane] = w;
+		const unsigned long long blockTotal = __shfl_sync(0xFFFFFFFFu, w, kScanThreads / 32 - 1);
+		if (lane == 0)
+		{
+			__threadfence();
+			partial[blockIdx.x] = blockTotal | (1ull << 63);
+		}
+		unsigned long long before = 0;
+		for (uint32_t j = lane; j < blockIdx.x; j += 32)
+		{
+			unsigned long long p;
+			while (!((p = partial[j]) >> 63)) { }
+			before += p & ~(1ull << 63);
+		}
+		for (int d = 16; d > 0; d >>= 1) before += __shfl_down_sync(0xFFFFFFFFu, before, d);
+		if (lane == 0)
+		{
+			sPrefix = before;
+			if (blockIdx.x == gridDim.x - 1)
+			{
+				const unsigned long long pairs = before + blockTotal;
+				frameInfo[0] = pairs;
+				frameInfo[1] = (pairs > capacity) ? 1ull : 0ull;
+				tileOffset[nTiles] = (pairs > capacity) ? 0xFFFFFFFFu : 0u;    // what a peer rank reads (sharded front end)
+			}
+		}
+	}
+	__syncthreads();
+	unsigned long long run = sPrefix + (warp ? sWarp[warp - 1] : 0ull) + incl - sum;
+	#pragma unroll
+	for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
+	{
+		const uint32_t i = first + q * 4;
+		uint4 o;
+		o.x = (uint32_t)run; run += v[q * 4];
+		o.y = (uint32_t)run; run += v[q * 4 + 1];
+		o.z = (uint32_t)run; run += v[q * 4 + 2];
+		o.w = (uint32_t)run; run += v[q * 4 + 3];
+		if (i + 3 < nTiles)
+		{
+			*reinterpret_cast<uint4*>(tileOffset + i) = o;
+			*reinterpret_cast<uint4*>(tileCursor + i) = make_uint4(0, 0, 0, 0);
+		}
+		else
+		{
+			if (i < nTiles) { tileOffset[i] = o.x; tileCursor[i] = 0; }
+			if (i + 1 < nTiles) { tileOffset[i + 1] = o.y; tileCursor[i + 1] = 0; }
+			if (i + 2 < nTiles) { tileOffset[i + 2] = o.z; tileCursor[i + 2] = 0; }
+		}
+		#pragma unroll
+		for (uint32_t e = 0; e < 4; ++e)
+		{
+			const uint32_t c = v[q * 4 + e];
+			if (i + e < nTiles && c > midThreshold)
+			{
+				if (c > longThreshold) longTiles[atomicAdd(&frameInfo[3], 1ull)] = i + e;
+				else midTiles[atomicAdd(&frameInfo[5], 1ull)] = i + e;
+			}
+		}
 	}
 }
 

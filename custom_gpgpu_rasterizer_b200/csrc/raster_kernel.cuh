@@ -34,6 +34,7 @@ struct RasterArgs
 	int32_t* depth;
 	float* zSurface;        // debug surfaces (may be null)
 	uint32_t* winnerSurface;
+	ShardTable shard;       // sharded front end only (fp.shardGeometry): the per-rank lists of this rank's tiles, all in local memory
 };
 
 // expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
@@ -230,8 +231,46 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	uint32_t bestPrim = kNoPrim;
 	uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
 	sKey[tid] = kEmptyKey;
-	const uint32_t n = A.tileCount[bin];
-	const uint32_t* list = A.binIds + A.tileOffset[bin];
+	uint32_t n;
+	const uint32_t* list = nullptr;
+	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
+	if (fp.shardGeometry)
+	{
+		// Sharded front end.  Rank p built the ascending list of ITS primitive slice for every tile and pushed
+		// the heads (after its scan) and the sorted ids (after its sort) of the tiles owned here into this
+		// rank's memory.  The slices are contiguous and ordered by rank, so the tile's list is the
+		// concatenation of the n segments in rank order: read the n heads at once, one lane per rank.
+		if (tid < 32)
+		{
+			uint32_t cnt = 0, off = 0, bad = 0;
+			if ((uint32_t)tid < fp.ownerCount)
+			{
+				cnt = __ldg(A.shard.tileCount[tid] + bin);
+				off = __ldg(A.shard.tileOffset[tid] + bin);
+				bad = __ldg(A.shard.tileOffset[tid] + fp.binsX * fp.binsY) == 0xFFFFFFFFu;   // that rank's list buffer overflowed
+			}
+			uint32_t incl = cnt;
+			#pragma unroll
+			for (int d = 1; d < kMaxRanks; d <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+				if (tid >= d) incl += t;
+			}
+			if (__any_sync(0xFFFFFFFFu, bad))
+			{
+				incl = 0;                                  // void frame: the host reports the undersized list capacity
+				if (tid == 0) A.frameInfo[1] = 1ull;
+			}
+			if (tid < kMaxRanks) { sSegEnd[tid] = incl; sSegOff[tid] = off; }
+		}
+		__syncthreads();
+		n = sSegEnd[fp.ownerCount - 1];
+	}
+	else
+	{
+		n = A.tileCount[bin];
+		list = A.binIds + A.tileOffset[bin];
+	}
 
 	for (uint32_t base = 0; base < n; base += kListChunk)
 	{
@@ -240,7 +279,16 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		const uint32_t m = min((uint32_t)kListChunk, n - base);
 		if ((uint32_t)tid < m)
 		{
-			const uint32_t prim = __ldg(list + base + tid);
+			uint32_t prim;
+			if (fp.shardGeometry)
+			{
+				const uint32_t e = base + tid;
+				uint32_t seg = 0;
+				while (e >= sSegEnd[seg]) ++seg;
+				prim = __ldg(A.shard.binIds[seg] + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u)));
+			}
+			else
+				prim = __ldg(list + base + tid);
 			// rebuild the screen-space triangle from the static reference + the transformed positions
 			// (same code, hence the same bits, wherever a triangle is expanded)
 			const uint4 tr = __ldg(A.triRefs + prim);
@@ -411,14 +459,8 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 }
 
 
-// Sharded front end: bring the lists of one owned tile together.  Rank p built the ascending list of ITS
-// primitive slice for every tile; the slices are contiguous and ordered by rank, so the tile's full list is
-// the concatenation in rank order.  Every rank pushed the heads (count, offset) of its lists into the
-// owners' inboxes right after its scan (shard_push_heads_kernel), so here one WARP per owned tile reads the
-// n heads from local memory and copies the segments - the peers' over NVLink, one hop - into the local
-// merged buffer; the raster kernel then runs on local memory exactly as on a single GPU.  No scan is needed
-// for the merged offsets: every rank's offset[t] is the exclusive prefix of its own counts, so their SUM is
-// the exclusive prefix of the summed counts.
+// Sharded front end, exchange step 1: right after its scan every rank stores the heads (count, offset) of its
+// lists into the inbox of each tile's owner, so the transfer hides behind scatter + sort.
 __global__ void __launch_bounds__(256) shard_push_heads_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t nTiles, ShardInbox inbox, uint32_t nRanks)
 {
@@ -432,79 +474,24 @@ __global__ void __launch_bounds__(256) shard_push_heads_kernel(const uint32_t* _
 	if (t < nRanks) inbox.tileOffset[t][nTiles] = tileOffset[nTiles];      // overflow marker, to everybody
 }
 
-__global__ void __launch_bounds__(256) shard_pull_kernel(ShardTable T, uint32_t nOwned, uint32_t* __restrict__ mergedCount, uint32_t* __restrict__ mergedOffset,
-	uint32_t* __restrict__ mergedIds, unsigned long long mergedCap, unsigned long long* __restrict__ frameInfo, FrameParams fp)
+// after the sort: mirror the list of every tile into its owner's memory, at the SAME offset inside the region
+// reserved there for this rank, so no rank needs another rank's offsets.  Posted NVLink stores of aligned
+// 16-byte vectors; the few ids of the neighbouring lists that ride along belong to tiles t-1 / t+1, which
+// have other owners, so nobody reads them there.
+__global__ void __launch_bounds__(256) shard_push_lists_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
+	const uint32_t* __restrict__ binIds, uint32_t nTiles, ShardRegions R, uint32_t nRanks, uint32_t self,
+	const unsigned long long* __restrict__ frameInfo)
 {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if (k >= nOwned) return;
-	const uint32_t bin = fp.ownerRank + k * fp.ownerCount;
-	uint32_t cnt = 0, off = 0, bad = 0;
-	if (lane < fp.ownerCount)
-	{
-		cnt = __ldg(T.tileCount[lane] + bin);
-		off = __ldg(T.tileOffset[lane] + bin);
-		bad = __ldg(T.tileOffset[lane] + fp.binsX * fp.binsY) == 0xFFFFFFFFu;   // that rank's list buffer overflowed
-	}
-	// the segments are fetched as ALIGNED 16-byte vectors (a few ids of the neighbouring lists ride along and
-	// are dropped): NVLink needs many bytes in flight per thread to reach its bandwidth
-	const uint32_t vecLo = off >> 2, vecs = cnt ? ((off + cnt + 3) >> 2) - vecLo : 0u;
-	uint32_t incl = cnt, vIncl = vecs;
-	unsigned long long base = off;
-	#pragma unroll
-	for (int d = 1; d < kMaxRanks; d <<= 1)
-	{
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d), tv = __shfl_up_sync(0xFFFFFFFFu, vIncl, d);
-		if (lane >= (uint32_t)d) { incl += t; vIncl += tv; }
-	}
-	#pragma unroll
-	for (int d = kMaxRanks / 2; d > 0; d >>= 1) base += __shfl_down_sync(0xFFFFFFFFu, base, d);
-	base = __shfl_sync(0xFFFFFFFFu, base, 0);
-	uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, kMaxRanks - 1);
-	uint32_t totalVecs = __shfl_sync(0xFFFFFFFFu, vIncl, kMaxRanks - 1);
-	const bool overflow = __any_sync(0xFFFFFFFFu, bad) || base + total > mergedCap;
-	if (overflow) { total = 0; totalVecs = 0; if (lane == 0) frameInfo[1] = 1ull; }
-	if (lane == 0)
-	{
-		mergedCount[bin] = total;
-		mergedOffset[bin] = overflow ? 0u : (uint32_t)base;
-	}
-	uint32_t* dst = mergedIds + (uint32_t)base;
-	constexpr int kUnroll = 2;
-	for (uint32_t v0 = 0; v0 < totalVecs; v0 += 32 * kUnroll)
-	{
-		uint4 val[kUnroll];
-		uint32_t first[kUnroll], lo[kUnroll], hi[kUnroll];     // merged position of val.x, and the valid window
-		#pragma unroll
-		for (int u = 0; u < kUnroll; ++u)
-		{
-			const uint32_t v = v0 + (uint32_t)u * 32u + lane;
-			uint32_t seg = 0;
-			for (uint32_t s = 0; s + 1 < fp.ownerCount; ++s)
-				if (v >= __shfl_sync(0xFFFFFFFFu, vIncl, s)) seg = s + 1;
-			const uint32_t sVEnd = __shfl_sync(0xFFFFFFFFu, vIncl, seg), sVecs = __shfl_sync(0xFFFFFFFFu, vecs, seg), sVecLo = __shfl_sync(0xFFFFFFFFu, vecLo, seg);
-			const uint32_t sEnd = __shfl_sync(0xFFFFFFFFu, incl, seg), sCnt = __shfl_sync(0xFFFFFFFFu, cnt, seg), sOff = __shfl_sync(0xFFFFFFFFu, off, seg);
-			val[u] = make_uint4(0, 0, 0, 0); first[u] = 0; lo[u] = 0; hi[u] = 0;      // empty window: nothing stored
-			if (v < totalVecs)
-			{
-				const uint32_t vec = sVecLo + (v - (sVEnd - sVecs));                 // 16-byte vector index in the source buffer
-				val[u] = __ldg(reinterpret_cast<const uint4*>(T.binIds[seg]) + vec);
-				lo[u] = sEnd - sCnt; hi[u] = sEnd;                                   // merged range of this segment
-				first[u] = lo[u] + (vec << 2) - sOff;                                // may wrap below lo: compared modulo 2^32 below
-			}
-		}
-		#pragma unroll
-		for (int u = 0; u < kUnroll; ++u)
-		{
-			const uint32_t w[4] = { val[u].x, val[u].y, val[u].z, val[u].w };
-			#pragma unroll
-			for (uint32_t q = 0; q < 4; ++q)
-			{
-				const uint32_t pos = first[u] + q;
-				if (pos - lo[u] < hi[u] - lo[u]) dst[pos] = w[q];
-			}
-		}
-	}
+	if (frameInfo[1]) return;
+	const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+	if (t >= nTiles) return;
+	const uint32_t owner = t % nRanks;
+	if (owner == self) return;
+	const uint32_t cnt = __ldg(tileCount + t), off = __ldg(tileOffset + t);
+	if (!cnt) return;
+	const uint4* src = reinterpret_cast<const uint4*>(binIds);
+	uint4* dst = reinterpret_cast<uint4*>(R.region[owner]);
+	for (uint32_t v = (off >> 2) + lane, vEnd = (off + cnt + 3) >> 2; v < vEnd; v += 32) dst[v] = src[v];
 }
 
 // sort-first composition on the gathering rank: scatter one rank's packed tile-major colours back

@@ -10,3 +10,6 @@ for lo, hi in [(1, 32), (33, 256), (257, 1024), (1025, 4096), (4097, 40960), (40
     m = (counts >= lo) & (counts <= hi)
     print(f"{lo:>6}..{hi:<10} tiles {m.sum():>6} entries {counts[m].sum():>9}")
 print(r.counters())
+top = np.sort(counts)[::-1][:24]
+print("longest lists", top.tolist())
+print("tiles > 1024:", int((counts > 1024).sum()), " > 2048:", int((counts > 2048).sum()))
