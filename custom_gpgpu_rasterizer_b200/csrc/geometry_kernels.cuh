@@ -915,18 +915,121 @@ __device__ __forceinline__ void radixSortTileList(uint32_t* __restrict__ list, u
 		for (uint32_t i = tid; i < n; i += WARPS * 32) list[i] = src[i];
 }
 
+// exclusive scan of one value per thread over a 256-thread CTA; *total receives the block sum
+__device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* sWarp /*[9]*/, uint32_t* total)
+{
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+	__syncthreads();                       // sWarp may still be read from a previous call
+	if (lane == 31) sWarp[warp] = incl;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t run = 0;
+		for (int w = 0; w < 8; ++w) { const uint32_t c = sWarp[w]; sWarp[w] = run; run += c; }
+		sWarp[8] = run;
+	}
+	__syncthreads();
+	*total = sWarp[8];
+	return sWarp[warp] + incl - v;
+}
+
+// tier 2 (kSortWarpRadix < n <= kSortSmall): one CTA per tile.  Same idea as bin_sort_runs_kernel at CTA
+// scale: the list consists of at most kMidRuns ascending runs (one per (warp, tile) pair of the scatter)
+// that cover disjoint id ranges, so ordering the RUN HEADS and moving whole runs sorts the list; if the
+// runs interleave or there are too many of them the CTA falls back to the radix sort.
+constexpr int kMidRuns = 512, kMidPerThread = kSortSmall / 256;
 __global__ void __launch_bounds__(256) bin_sort_mid_kernel(
 	const uint32_t* __restrict__ midTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
 {
 	__shared__ uint32_t sA[kSortSmall], sB[kSortSmall], sHist[8 * 256], sRed[2 * 8 + 2];
+	__shared__ uint32_t sHead[kMidRuns], sWarpScan[9];
+	__shared__ uint16_t sStart[kMidRuns + 1], sOrder[kMidRuns], sOut[kMidRuns];
 	if (frameInfo[1]) return;
 	const uint32_t nMid = (uint32_t)frameInfo[5];
+	const uint32_t tid = threadIdx.x;
 	for (uint32_t w = blockIdx.x; w < nMid; w += gridDim.x)
 	{
 		const uint32_t tile = midTiles[w];
-		radixSortTileList<8>(binIds + tileOffset[tile], tileCount[tile], sA, sB, sHist, sRed);
+		const uint32_t n = tileCount[tile];
+		uint32_t* list = binIds + tileOffset[tile];
 		__syncthreads();
+		for (uint32_t i = tid; i < n; i += 256) sA[i] = list[i];
+		__syncthreads();
+		// 1. run starts of this thread's kMidPerThread consecutive entries
+		const uint32_t first = tid * kMidPerThread;
+		uint32_t flags = 0;
+		int descent = 0;
+		#pragma unroll
+		for (uint32_t k = 0; k < (uint32_t)kMidPerThread; ++k)
+		{
+			const uint32_t i = first + k;
+			if (i < n)
+			{
+				const uint32_t cur = sA[i], prev = i ? sA[i - 1] : 0u;
+				if (i == 0 || prev > cur || (prev >> 5) != (cur >> 5)) flags |= 1u << k;
+				descent |= (i > 0 && prev > cur);
+			}
+		}
+		if (!__syncthreads_or(descent)) continue;          // already in canonical order
+		uint32_t runs = 0;
+		const uint32_t runBase = blockExclusiveScan256((uint32_t)__popc(flags), sWarpScan, &runs);
+		bool fallback = runs > (uint32_t)kMidRuns;
+		if (!fallback)
+		{
+			for (uint32_t k = 0, r = runBase; k < (uint32_t)kMidPerThread; ++k)
+				if (flags & (1u << k)) { sStart[r] = (uint16_t)(first + k); sHead[r] = sA[first + k]; ++r; }
+			if (tid == 0) sStart[runs] = (uint16_t)n;
+			__syncthreads();
+			// 2. order the runs by their first key (keys are distinct primitive ids)
+			for (uint32_t r = tid; r < runs; r += 256)
+			{
+				const uint32_t head = sHead[r];
+				uint32_t rank = 0;
+				for (uint32_t q = 0; q < runs; ++q) rank += (sHead[q] < head) ? 1u : 0u;
+				sOrder[rank] = (uint16_t)r;
+			}
+			__syncthreads();
+			// 3. output position of every run = prefix of the run lengths in that order (two runs per thread);
+			//    the runs must cover disjoint id ranges (last key of a run < first key of the next one)
+			uint32_t len0 = 0, len1 = 0, r0 = 0, r1 = 0;
+			int bad = 0;
+			const uint32_t k0 = 2 * tid, k1 = 2 * tid + 1;
+			if (k0 < runs)
+			{
+				r0 = sOrder[k0]; len0 = (uint32_t)sStart[r0 + 1] - (uint32_t)sStart[r0];
+				if (k0 + 1 < runs) bad |= sA[sStart[r0 + 1] - 1] > sHead[sOrder[k0 + 1]];
+			}
+			if (k1 < runs)
+			{
+				r1 = sOrder[k1]; len1 = (uint32_t)sStart[r1 + 1] - (uint32_t)sStart[r1];
+				if (k1 + 1 < runs) bad |= sA[sStart[r1 + 1] - 1] > sHead[sOrder[k1 + 1]];
+			}
+			uint32_t total = 0;
+			const uint32_t pos = blockExclusiveScan256(len0 + len1, sWarpScan, &total);
+			if (k0 < runs) sOut[r0] = (uint16_t)pos;
+			if (k1 < runs) sOut[r1] = (uint16_t)(pos + len0);
+			fallback = __syncthreads_or(bad) != 0;
+		}
+		if (fallback)
+		{
+			radixSortTileList<8>(list, n, sA, sB, sHist, sRed);
+			continue;
+		}
+		// 4. move every key to its run's output position
+		#pragma unroll
+		for (uint32_t k = 0; k < (uint32_t)kMidPerThread; ++k)
+		{
+			const uint32_t i = first + k;
+			if (i < n)
+			{
+				const uint32_t r = runBase + (uint32_t)__popc(flags & ((2u << k) - 1u)) - 1u;
+				list[(uint32_t)sOut[r] + (i - (uint32_t)sStart[r])] = sA[i];
+			}
+		}
 	}
 }
 
