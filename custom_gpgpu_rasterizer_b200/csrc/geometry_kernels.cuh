@@ -187,23 +187,36 @@ __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, 
 	const uint32_t uw = (uint32_t)(ux1 - ux0 + 1), uArea = uw * (uint32_t)(uy1 - uy0 + 1);
 	if (uArea <= kUnionTilesMax)
 	{
-		for (uint32_t u = 0; u < uArea; ++u)
+		// 32 union tiles at a time: lane u keeps the ballot of tile u, then ALL tiles' atomics are issued by one
+		// instruction (one round trip to L2 instead of one per tile), then the ids are written tile by tile
+		for (uint32_t u0 = 0; u0 < uArea; u0 += 32)
 		{
-			const int tx = ux0 + (int)(u % uw), ty = uy0 + (int)(u / uw);
-			const uint32_t tile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
-			const bool in = nTiles && tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1;
-			const unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
-			if (!mask || !tileOwned(fp, tile)) continue;          // warp-uniform
-			const int leader = __ffs(mask) - 1;
+			const uint32_t uEnd = min(uArea - u0, 32u);
+			uint32_t myMask = 0, myTile = 0;
+			for (uint32_t u = 0; u < uEnd; ++u)
+			{
+				const int tx = ux0 + (int)((u0 + u) % uw), ty = uy0 + (int)((u0 + u) / uw);
+				const bool in = nTiles && tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1;
+				const unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
+				if (lane == u)
+				{
+					myTile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
+					myMask = tileOwned(fp, myTile) ? mask : 0u;
+				}
+			}
 			if (SCATTER)
 			{
-				uint32_t base = 0;
-				if ((int)lane == leader) base = atomicAdd(&counters[tile], (uint32_t)__popc(mask));
-				base = __shfl_sync(0xFFFFFFFFu, base, leader);
-				if (in) binIds[__ldg(tileOffset + tile) + base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = prim;
+				uint32_t myBase = 0;
+				if (myMask) myBase = __ldg(tileOffset + myTile) + atomicAdd(&counters[myTile], (uint32_t)__popc(myMask));
+				for (uint32_t u = 0; u < uEnd; ++u)
+				{
+					const unsigned mask = __shfl_sync(0xFFFFFFFFu, myMask, u);
+					const uint32_t base = __shfl_sync(0xFFFFFFFFu, myBase, u);
+					if ((mask >> lane) & 1u) binIds[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = prim;
+				}
 			}
-			else if ((int)lane == leader)
-				atomicAdd(&counters[tile], (uint32_t)__popc(mask));
+			else if (myMask)
+				atomicAdd(&counters[myTile], (uint32_t)__popc(myMask));
 		}
 	}
 	else

@@ -13,3 +13,36 @@ def test_hoisted_division_is_bit_exact():
         bad = C.c_uint64(123)
         assert lib.b2r_selftest_division(0, 1 << 30, seed, C.byref(bad)) == 0
         assert bad.value == 0, f"{bad.value} of 2^30 quotients differ from div.rn (seed {seed})"
+
+
+@pytest.mark.parametrize("res,grid,tess", [((640, 360), (3, 2), (101, 150)), ((320, 180), (1, 1), (201, 300)), ((1920, 1080), (6, 4), (61, 90))])
+def test_list_sort_tiers_give_canonical_lists(res, grid, tess):
+    """Every sorter tier (warp run ordering, warp radix, CTA run ordering / radix, long radix) must turn the
+    scatter-order lists into ascending primitive ids without changing their content."""
+    import numpy as np
+    from custom_gpgpu_rasterizer_b200 import _lib, scenes
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    sc = scenes.sphere_grid_scene(res[0], res[1], nx=grid[0], ny=grid[1], stacks=tess[0], slices=tess[1], cam_z=6.0 * max(grid))
+    r = Renderer(sc.width, sc.height)
+    r.load_scene(sc)
+    r.set_option(_lib.OPT_SORT_BINS, 0)
+    r.render_scene(sc)
+    c0, o0, i0 = r.bin_lists()
+    fb0 = r.framebuffer().copy()
+    r.set_option(_lib.OPT_SORT_BINS, 1)
+    r.render_scene(sc)
+    c1, o1, i1 = r.bin_lists()
+    unsorted_tiles = r.counters()["unsorted_tiles"]
+    assert np.array_equal(c0, c1) and np.array_equal(o0, o1)
+    assert np.array_equal(r.framebuffer(), fb0), "the image must not depend on the list order"
+    tiers = {"warp": 0, "mid": 0, "long": 0, "beyond": 0}
+    for t in np.flatnonzero(c1):
+        seg = i1[o1[t]: o1[t] + c1[t]]
+        n = int(c1[t])
+        tiers["warp" if n <= 1024 else "mid" if n <= 4096 else "long" if n <= 40960 else "beyond"] += 1
+        if n <= 40960:
+            assert np.all(seg[1:] > seg[:-1]), f"tile {t} ({n} entries) is not in ascending primitive order"
+        assert np.array_equal(np.sort(seg), np.sort(i0[o0[t]: o0[t] + c0[t]])), f"tile {t}: content changed by the sort"
+    assert unsorted_tiles == tiers["beyond"]
+    assert tiers["mid"] + tiers["long"] > 0, f"scene does not exercise the CTA-level sorters: {tiers}"
+    r.close()
