@@ -7,11 +7,10 @@
 //   H2D   per-mesh constants (WVP computed on the host exactly like CUDARenderer.cu:242)
 //   K1    vertex_transform_kernel      IVertex -> pos4 + attr
 //   K2    triangle_setup_kernel        cull / frustum / screen / bbox / bin rect / tile counts
-//   K3    bin_big_kernel<count>        cooperative counting of large rectangles
-//   K4    tile_scan_kernel             exclusive scan of the tile counts
-//   K5    bin_scatter_kernel           ids of small rectangles -> lists
-//   K6    bin_big_kernel<scatter>      ids of large rectangles -> lists
-//   K7/8  bin_sort_kernel(+long)       canonical (ascending id) order per tile
+//   K3    bin_big_count_kernel         cooperative counting of large rectangles
+//   K4    tile_scan_kernel             exclusive scan of the tile counts (chained over a few CTAs)
+//   K5    bin_scatter_kernel           ids -> lists (small rectangles per primitive, large ones cooperatively)
+//   K6-8  bin_sort_{runs,mid,long}     canonical (ascending id) order per tile
 //   K9    raster_shade_kernel          coverage + depth resolve + deferred shade + ROP write-back
 #include "../../include/b2r.h"
 #include "device_types.cuh"
@@ -408,12 +407,14 @@ int enqueueFrame(b2r_context* c)
 		mc.pad = 0;
 	}
 	STAGE_EVENT(c, slot, 0);
-	if (!c->meshes.empty())
-		CU(c, cudaMemcpyAsync(c->dMeshConst.ptr, slot.hMeshConst, c->meshes.size() * sizeof(MeshConst), cudaMemcpyHostToDevice, s));
 	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
 	// queue behind the previous frame's 33 MB Present copy
-	frame_clear_kernel<<<(tiles + 4095) / 4096, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
-		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta));
+	static_assert(sizeof(MeshConst) % 16 == 0, "MeshConst is moved as 16-byte vectors");
+	const uint32_t nConstVec = (uint32_t)(c->meshes.size() * sizeof(MeshConst) / 16);
+	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (nConstVec + 255) / 256), (uint32_t)c->numSMs * 4);
+	frame_clear_kernel<<<clearCtas, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
+		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
+		reinterpret_cast<const uint4*>(slot.hMeshConst), reinterpret_cast<uint4*>(c->dMeshConst.ptr), nConstVec);
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks)
@@ -430,7 +431,7 @@ int enqueueFrame(b2r_context* c)
 				c->dRects.ptr, tileCount, c->dBigList.ptr, c->dCounters, primLo, primHi, fp);
 			++c->kernelsLaunched;
 		}
-		bin_big_kernel<false><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, tileCount, nullptr, nullptr, nullptr, c->dFrameInfo, fp);
+		bin_big_count_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, tileCount, fp);
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 2);
@@ -453,25 +454,22 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 3);
 	if (c->nPrims)
 	{
-		if (primHi > primLo)
 		{
-			bin_scatter_kernel<<<(primHi - primLo + 255) / 256, 256, 0, s>>>(c->dRects.ptr, primLo, primHi, tileOffset,
-				c->dTileCursor.ptr, binIds, c->dFrameInfo, fp);
+			// per-primitive CTAs, followed by the CTAs that scatter the cooperatively binned (big) triangles
+			const uint32_t primBlocks = (primHi - primLo + 255) / 256;
+			bin_scatter_kernel<<<primBlocks + (uint32_t)c->numSMs * 2, 256, 0, s>>>(c->dRects.ptr, primLo, primHi, tileOffset,
+				c->dTileCursor.ptr, binIds, c->dBigList.ptr, c->dCounters, primBlocks, c->dFrameInfo, fp);
 			++c->kernelsLaunched;
 		}
-		bin_big_kernel<true><<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, nullptr, tileOffset,
-			c->dTileCursor.ptr, binIds, c->dFrameInfo, fp);
-		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		bin_sort_runs_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(tileCount, tileOffset, binIds, tiles, c->dWarpTiles.ptr, c->dFrameInfo);
-		bin_sort_warp_radix_kernel<<<c->numSMs * 6, 128, 0, s>>>(c->dWarpTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo);
+		bin_sort_runs_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(tileCount, tileOffset, binIds, tiles, c->dMidTiles.ptr, c->dFrameInfo);
 		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo);
 		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, tileCount, tileOffset,
 			binIds, c->dFrameInfo);
-		c->kernelsLaunched += 4;
+		c->kernelsLaunched += 3;
 	}
 	if (sh.bound && c->nPrims)
 	{
@@ -549,7 +547,8 @@ int enqueueFrame(b2r_context* c)
 	}
 	STAGE_EVENT(c, slot, 6);
 	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
-	CU(c, cudaMemcpyAsync(slot.hInfo, c->dFrameInfo, sizeof(b2r_context::HostInfo), cudaMemcpyDeviceToHost, s));
+	publish_info_kernel<<<1, 32, 0, s>>>(c->dFrameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8));
+	++c->kernelsLaunched;
 	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
 	slot.pending = true;

@@ -152,18 +152,30 @@ __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t til
 	return 0;
 }
 
-// start of frame: zero the tile counts (tileCount is padded to a multiple of 4 words) and the counters
+// start of frame: zero the tile counts (tileCount is padded to a multiple of 4 words) and the counters, and
+// fetch the per-mesh constants straight from the pinned host staging buffer (zero-copy read over PCIe).
+// Together with publish_info_kernel this keeps the frame off the copy engines, which belong to Present:
+// a cudaMemcpyAsync here can be queued behind the previous frame's 33 MB framebuffer copy.
 __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__ tileCount, uint32_t nTiles,
-	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords)
+	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords,
+	const uint4* __restrict__ hostConstants, uint4* __restrict__ constants, uint32_t nConstVec)
 {
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	for (uint32_t i = gtid; i < nConstVec; i += gsize) constants[i] = hostConstants[i];
 	const uint32_t q = (nTiles + 3) / 4;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < q; i += gridDim.x * blockDim.x)
+	for (uint32_t i = gtid; i < q; i += gsize)
 		reinterpret_cast<uint4*>(tileCount)[i] = make_uint4(0, 0, 0, 0);
 	if (blockIdx.x == 0)
 	{
 		for (uint32_t i = threadIdx.x; i < counterWords; i += blockDim.x) counters[i] = 0;
 		if (threadIdx.x < infoWords) frameInfo[threadIdx.x] = 0;
 	}
+}
+// end of frame: the frame's counters go to the pinned host slot (zero-copy write)
+__global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words)
+{
+	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];
+	__threadfence_system();
 }
 
 // Warp-level binning of up to 32 small rectangles (one per lane, rectangle = inclusive tile range,
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 		nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
 		if (nTiles > fp.bigRectTiles)
 		{
-			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively by bin_big_kernel
+			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
 			nTiles = 0;
 		}
 	}
@@ -379,16 +391,16 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 }
 
 // cooperative binning of triangles with large rectangles (full-screen quads ...): one CTA per
-// big triangle, threads stride over its tiles.  SCATTER=false counts, true writes the ids.
+// big triangle, threads stride over its tiles.  SCATTER=false counts (bin_big_count_kernel), true writes
+// the ids (extra CTAs of bin_scatter_kernel).
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) bin_big_kernel(
+__device__ __forceinline__ void binBigBody(uint32_t cta, uint32_t nCtas,
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, const uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo, FrameParams fp)
+	uint32_t* __restrict__ binIds, const FrameParams& fp)
 {
-	if (SCATTER && frameInfo[1]) return;   // list capacity overflow: the host regrows and re-runs the frame
 	const uint32_t nBig = counters[1];
-	for (uint32_t b = blockIdx.x; b < nBig; b += gridDim.x)
+	for (uint32_t b = cta; b < nBig; b += nCtas)
 	{
 		const uint32_t prim = bigList[b];
 		const uint2 rc = rects[prim];
@@ -404,6 +416,14 @@ __global__ void __launch_bounds__(256) bin_big_kernel(
 				atomicAdd(&tileCount[tile], 1u);
 		}
 	}
+}
+
+// counting pass of the big triangles (their scatter pass rides in bin_scatter_kernel's grid)
+__global__ void __launch_bounds__(256) bin_big_count_kernel(
+	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, const uint2* __restrict__ rects,
+	uint32_t* __restrict__ tileCount, FrameParams fp)
+{
+	binBigBody<false>(blockIdx.x, gridDim.x, bigList, counters, rects, tileCount, nullptr, nullptr, nullptr, fp);
 }
 
 // exclusive scan of the per-tile counts: a chained scan over a handful of co-resident CTAs (2048 tiles
@@ -533,9 +553,16 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	const uint2* __restrict__ rects, uint32_t primLo, uint32_t primHi, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ binIds,
+	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, uint32_t primBlocks,
 	const unsigned long long* __restrict__ frameInfo, FrameParams fp)
 {
 	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
+	if (blockIdx.x >= primBlocks)
+	{
+		// the CTAs behind the per-primitive part scatter the cooperatively binned (big) triangles
+		binBigBody<true>(blockIdx.x - primBlocks, gridDim.x - primBlocks, bigList, counters, rects, nullptr, tileOffset, tileCursor, binIds, fp);
+		return;
+	}
 	const uint32_t prim = primLo + blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t nTiles = 0;
 	int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1, w = 1;
@@ -548,7 +575,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 		{
 			w = bx1 - bx0 + 1;
 			nTiles = (uint32_t)w * (uint32_t)(by1 - by0 + 1);
-			if (nTiles > fp.bigRectTiles) nTiles = 0;   // bin_big_kernel
+			if (nTiles > fp.bigRectTiles) nTiles = 0;   // binBigBody
 		}
 	}
 	(void)w;
@@ -591,9 +618,9 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t
 //  tier 1: one WARP per tile, lists up to kSortWarpRadix entries.  warpBinRects() writes one ascending
 //          run per (warp, tile) and the runs of different warps cover disjoint id ranges, so the list
 //          is sorted by ORDERING THE RUNS by their first key and moving them (bin_sort_runs_kernel).
-//          Tiles where that does not hold (interleaved runs) go to a warp-level radix sort.
+//          Tiles where that does not hold (interleaved or too many runs) are appended to the mid list.
 //  tier 2: the tiles tile_scan_kernel put on the "mid" work list (up to kSortSmall entries), one
-//          CTA per tile, block radix sort in static shared memory
+//          CTA per tile: run ordering at CTA scale, block radix sort in static shared memory as fallback
 //  tier 3: the "long" work list (up to kSortLarge entries) in dynamic shared memory, one CTA per SM
 //  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
@@ -665,11 +692,15 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	//    per warp and tile, and a warp's ids are one aligned group of 32)
 	uint32_t runs = 0, carry = 0;
 	bool descent = false;
+	// stage the list in shared memory first: the loads are independent, so they are all in flight together
+	// (the run detection below is a serial chain over the 32-entry batches)
+	#pragma unroll 4
+	for (uint32_t i = lane; i < n; i += 32) K[i] = list[i];
+	__syncwarp();
 	for (uint32_t b = 0; b < n; b += 32)
 	{
 		const uint32_t i = b + lane;
-		const uint32_t k = (i < n) ? list[i] : 0xFFFFFFFFu;
-		if (i < n) K[i] = k;
+		const uint32_t k = (i < n) ? K[i] : 0xFFFFFFFFu;
 		uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k, 1);
 		if (lane == 0) prev = carry;
 		const bool start = (i < n) && (i == 0 || prev > k || (prev >> 5) != (k >> 5));
@@ -735,7 +766,7 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	if (fallback)
 	{
 		// interleaved or too many runs (incoherent warps, big triangles in a long list): radix-sort this tile instead
-		if (lane == 0) fallbackTiles[atomicAdd(&frameInfo[6], 1ull)] = tile;
+		if (lane == 0) { fallbackTiles[atomicAdd(&frameInfo[5], 1ull)] = tile; atomicAdd(&frameInfo[6], 1ull); }
 		return;
 	}
 	__syncwarp();
@@ -752,85 +783,6 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 			list[(uint32_t)sOut[warp][r] + (i - (uint32_t)S[r])] = K[i];
 		}
 		before += (uint32_t)__popc(m);
-	}
-}
-
-// Warp-level stable LSD radix sort of one tile list (257 .. kSortWarpRadix entries): same scheme as the
-// block version below with a single warp, so every step is ordered by __syncwarp only.
-__global__ void __launch_bounds__(128) bin_sort_warp_radix_kernel(
-	const uint32_t* __restrict__ warpTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
-	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
-{
-	__shared__ uint32_t sKeys[4][2][kSortWarpRadix];
-	__shared__ uint32_t sHist[4][256];
-	if (frameInfo[1]) return;
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t nWork = (uint32_t)frameInfo[6];
-	uint32_t* hist = sHist[warp];
-	for (uint32_t w = blockIdx.x * 4 + warp; w < nWork; w += gridDim.x * 4)
-	{
-		const uint32_t tile = warpTiles[w];
-		const uint32_t n = tileCount[tile];
-		uint32_t* list = binIds + tileOffset[tile];
-		uint32_t* src = sKeys[warp][0]; uint32_t* dst = sKeys[warp][1];
-		uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-		bool unsorted = false;
-		for (uint32_t i = lane; i < n; i += 32)
-		{
-			const uint32_t k = list[i];
-			src[i] = k;
-			kmin = min(kmin, k); kmax = max(kmax, k);
-			if (i + 1 < n) unsorted |= (k > list[i + 1]);
-		}
-		if (!__any_sync(0xFFFFFFFFu, unsorted)) continue;
-		kmin = __reduce_min_sync(0xFFFFFFFFu, kmin); kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
-		const uint32_t range = kmax - kmin;
-		const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
-		__syncwarp();
-		for (int p = 0; p < passes; ++p)
-		{
-			const int shift = 8 * p;
-			#pragma unroll
-			for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = 0;
-			__syncwarp();
-			for (uint32_t b = 0; b < n; b += 32)
-			{
-				const uint32_t i = b + lane;
-				const bool valid = i < n;
-				const uint32_t d = valid ? (((src[i] - kmin) >> shift) & 255u) : (256u + lane);
-				const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
-				if (valid && (int)lane == __ffs(peers) - 1) hist[d] += (uint32_t)__popc(peers);
-				__syncwarp();
-			}
-			// exclusive scan of the 256 counters: 8 consecutive digits per lane
-			uint32_t c[8], sum = 0;
-			#pragma unroll
-			for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; sum += c[q]; }
-			uint32_t incl = sum;
-			#pragma unroll
-			for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= (uint32_t)dd) incl += t; }
-			uint32_t run = incl - sum;
-			#pragma unroll
-			for (int q = 0; q < 8; ++q) { hist[lane * 8 + q] = run; run += c[q]; }
-			__syncwarp();
-			for (uint32_t b = 0; b < n; b += 32)
-			{
-				const uint32_t i = b + lane;
-				const bool valid = i < n;
-				const uint32_t k = valid ? src[i] : 0u;
-				const uint32_t d = valid ? (((k - kmin) >> shift) & 255u) : (256u + lane);
-				const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
-				const int leader = __ffs(peers) - 1;
-				uint32_t base = 0;
-				if (valid && (int)lane == leader) { base = hist[d]; hist[d] = base + (uint32_t)__popc(peers); }
-				base = __shfl_sync(0xFFFFFFFFu, base, leader);
-				if (valid) dst[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = k;
-				__syncwarp();
-			}
-			uint32_t* t = src; src = dst; dst = t;
-		}
-		for (uint32_t i = lane; i < n; i += 32) list[i] = src[i];
-		__syncwarp();
 	}
 }
 
