@@ -192,21 +192,26 @@ int b2r_ipc_close(b2r_context* ctx, void* device_ptr);
 /* ---- sharded front end (sort-first with the geometry work divided as well) ----
  * With plain tile ownership every rank still sets up and bins the whole mesh.  In the sharded mode rank r
  * sets up / bins / sorts only the r-th contiguous slice of the primitives - into the lists of ALL tiles -
- * and the raster kernel of a tile's owner walks the ranks' lists of that tile in rank order, reading the
- * peers' lists over NVLink (CUDA IPC mappings).  What crosses the link per frame is 4 bytes per
- * (triangle, tile) pair plus the colours, which every rank stores straight into rank 0's surface.
- * Two flag barriers per frame (one small kernel each) order "lists ready" and "colours landed"; the bin
- * lists and rank 0's colour surface are double-buffered so that no other synchronisation is needed.
+ * and then stores (posted NVLink writes into CUDA-IPC-mapped peer memory) the heads and the sorted ids of
+ * every tile's list into a region reserved for it in the memory of the tile's owner.  The owner's raster
+ * kernel walks the ranks' segments in rank order from local memory; because the slices are contiguous and
+ * ascending, that concatenation is exactly the list a single GPU builds.  Every rank stores its colours
+ * straight into rank 0's surface.  What crosses the link per frame is 4 bytes per (triangle, tile) pair
+ * plus the colours; there is no collective.  Two flag barriers per frame (one small kernel each) order
+ * "lists ready" and "colours landed"; the bin lists and rank 0's colour surface are double-buffered by
+ * frame parity so that no other synchronisation is needed.
  *
- * Protocol (same scene loaded on every rank; one context per process/GPU):
+ * Protocol (same scene loaded on every rank; one context per process/GPU; 2..8 ranks):
  *   1. every rank: b2r_shard_prepare(ctx, rank, count, list_capacity, arena_handle, colour_handle)
  *      list_capacity = entries of one rank's bin-list buffer (0 = default), identical on every rank
  *   2. all-gather the 64-byte arena handles; broadcast rank 0's colour handle
  *   3. every rank: b2r_shard_bind(ctx, handles[count][64], colour_handle_of_rank_0); host barrier
  *   4. every rank calls b2r_render with the same arguments the same number of times; the composed frame is
- *      in rank 0's surface (b2r_read_framebuffer / b2r_present_async on rank 0)
+ *      in rank 0's surface (b2r_read_framebuffer / b2r_present_async on rank 0).  b2r_read_bins returns the
+ *      calling rank's own segment lists.
  *   5. host barrier; b2r_shard_release on every rank
- * An undersized list_capacity is reported by b2r_sync (B2R_E_STATE) and the frame is void on every rank. */
+ * An undersized list_capacity is reported by b2r_sync (B2R_E_STATE) and the frame is void on every rank;
+ * a peer that does not reach a barrier within 4 s is reported the same way instead of hanging the GPU. */
 int b2r_shard_prepare(b2r_context* ctx, int rank, int count, uint64_t list_capacity, void* arena_handle64, void* colour_handle64);
 int b2r_shard_bind(b2r_context* ctx, const void* arena_handles, const void* colour_handle_rank0);
 int b2r_shard_release(b2r_context* ctx);
