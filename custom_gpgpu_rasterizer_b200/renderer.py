@@ -141,9 +141,14 @@ class Renderer:
         self.setup_bins(scene.bins_x, scene.bins_y, scene.bin_w, scene.bin_h, scene.queue_cap)
         self.clear_meshes()
         tex_map = [self.add_texture(t) for t in scene.textures]
+        uploaded = {}       # meshes sharing the very same vertex / index memory become instances (b2r_mesh_instance)
         for m in scene.meshes:
             tex = [tex_map[t] if 0 <= t < len(tex_map) else -1 for t in m.tex_ids]
-            self.add_mesh(m.vertices, m.indices, host_mesh_world(m.position), tex, m.topology)
+            key = (m.vertices.ctypes.data, m.vertices.shape[0], m.indices.ctypes.data, m.indices.size, m.topology)
+            if key in uploaded:
+                self.add_instance(uploaded[key], host_mesh_world(m.position), tex)
+            else:
+                uploaded[key] = self.add_mesh(m.vertices, m.indices, host_mesh_world(m.position), tex, m.topology)
 
     # -- frame
     def render(self, cam: Dict[str, np.ndarray], cull: int = 0, sample: int = 0, vis: int = 0, clear_rgb=None, sync: bool = True):

@@ -27,7 +27,10 @@ if [ ! -d "$REF" ]; then
   exit 0
 fi
 
-mkdir -p "$SRC" "$OBJ"
+mkdir -p "$SRC" "$OBJ" "$OUT/resources"
+# the bundled meshes and textures of BASELINE configs 1/2/5 (data, not sources): git-ignored with the rest of
+# oracle/_ref, but they travel to the GPU box so the parity tests can render the reference's own scenes
+cp "$REF"/Resources/*.obj "$REF"/Resources/*.png "$OUT/resources"/
 cp "$REF"/*.h "$REF"/*.cpp "$REF"/*.cu "$REF"/*.cuh "$SRC"/
 
 # -- patch 1: GCC's <cmath> has no std::powf (RGBColor.h:126-128)

@@ -17,7 +17,13 @@ COLOUR_MAX_FRACTION = 1e-3 # at most 0.1 % of pixels may differ by more, and onl
 
 
 def bits(a: np.ndarray) -> np.ndarray:
-    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+    """Bit patterns of float32 data for exact comparison.  NaNs are canonicalised: the value class is part
+    of the contract, the payload is not (x86 produces 0xFFC00000, the GPU 0x7FFFFFFF for the same operation;
+    the bundled vehicle mesh carries NaN tangents from the reference parser's degenerate-uv triangles)."""
+    f = np.ascontiguousarray(a, np.float32)
+    u = f.view(np.uint32).copy()
+    u[np.isnan(f)] = 0x7FC00000
+    return u
 
 
 def channels(fb: np.ndarray) -> np.ndarray:

@@ -8,6 +8,7 @@ stronger property wherever it holds: bit-exact vertices, visibility, bins, depth
 import numpy as np
 import pytest
 
+import asset_scenes
 import oracle_lib
 import parity
 from custom_gpgpu_rasterizer_b200 import scenes
@@ -84,6 +85,18 @@ SCENES = {
     "slivers": lambda: scenes.sliver_scene(640, 480, 1500, seed=3),
     "slivers_4k": lambda: scenes.sliver_scene(3840, 2160, 600, seed=4),
 }
+
+# the reference's own bundled scenes (BASELINE configs 2 and 5; config 1 is the same mesh at 640x480); present when
+# oracle/build_ref.sh has copied the assets next to the built reference renderer
+if asset_scenes.have_assets():
+    SCENES.update({
+        "vehicle_480p_point": lambda: asset_scenes.vehicle_scene(640, 480, sample=0),
+        "vehicle_1080p_point": lambda: asset_scenes.vehicle_scene(1920, 1080, sample=0),
+        "vehicle_1080p_linear": lambda: asset_scenes.vehicle_scene(1920, 1080, sample=1),
+        "vehicle_1080p_normal_vis": lambda: asset_scenes.vehicle_scene(1920, 1080, vis=2),
+        "vehicles172_view0": lambda: asset_scenes.vehicle_views_scene(0),
+        "vehicles172_view389": lambda: asset_scenes.vehicle_views_scene(389),
+    })
 
 
 @pytest.mark.parametrize("name", sorted(SCENES))

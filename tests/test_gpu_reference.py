@@ -12,6 +12,7 @@ differ (BASELINE.json: "only on shared triangle edges").
 import numpy as np
 import pytest
 
+import asset_scenes
 import oracle_lib
 import parity
 from custom_gpgpu_rasterizer_b200 import scenes
@@ -33,6 +34,21 @@ SCENES = {
     "slivers": lambda: scenes.sliver_scene(640, 480, 1500, seed=3),
     "slivers_4k": lambda: scenes.sliver_scene(3840, 2160, 600, seed=4),
 }
+
+# the reference's own bundled scenes (BASELINE configs 1, 2 and 5); present when oracle/build_ref.sh has copied the
+# assets next to the built reference renderer.  The reference's raster kernel has no screen-bounds guard
+# (CUDARenderer.cu:1053-1067), so it can only be run where 16x16 bins tile the screen exactly: 1080 rows do not
+# (68 x 16 = 1088), hence 1280x720 here; the 1920x1080 configuration itself is covered product-vs-oracle in
+# tests/test_gpu_parity.py.
+if asset_scenes.have_assets():
+    SCENES.update({
+        "vehicle_480p_point": lambda: asset_scenes.vehicle_scene(640, 480, sample=0),
+        "vehicle_480p_linear": lambda: asset_scenes.vehicle_scene(640, 480, sample=1),
+        "vehicle_720p_point": lambda: asset_scenes.vehicle_scene(1280, 720, sample=0),
+        "vehicle_720p_normal_vis": lambda: asset_scenes.vehicle_scene(1280, 720, vis=2),
+        "vehicles172_720p_view0": lambda: asset_scenes.vehicle_views_scene(0, width=1280, height=720),
+        "vehicles172_720p_view389": lambda: asset_scenes.vehicle_views_scene(389, width=1280, height=720),
+    })
 
 
 def _ref_bins_as_sets(scene, ref):
