@@ -228,6 +228,15 @@ def run_b200(args, scene):
     counters = r.counters()
     launches_per_frame = counters["kernels_launched"] + (gather.launches_per_frame if gather else 0)
 
+    # ---- host cost of enqueueing one frame (ring of 4 frames in flight: the first three calls after a sync never block)
+    r.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        frame()
+    host_enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
+    r.sync()
+
     # ---- end to end through the public API: per-frame constants H2D + render + framebuffer D2H to pinned host memory
     pinned = [torch.empty((scene.height, scene.width), dtype=torch.int32, pin_memory=True) for _ in range(2)]
     host_fb = [p.numpy().view(np.uint32) for p in pinned]
@@ -351,11 +360,12 @@ def run_b200(args, scene):
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
                      "traffic": traffic, "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of SURVEY section 8d / stage time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},
-        "e2e": {"value": args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": len(scene.meshes) * 208,
+        "e2e": {"value": args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 64,
                 "d2h_bytes_per_step": scene.width * scene.height * 4,
-                "note": "per frame: per-mesh constants H2D + b2r_render + device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), wall clock over all frames incl. the final wait"},
+                "note": "per frame: view-projection matrix from the host (zero-copy read; per-mesh constants are built on the device) + b2r_render + device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), wall clock over all frames incl. the final wait"},
         "gpu_launches": launches_per_frame * args.steps,
         "gpu_launches_per_step": launches_per_frame,
+        "host_enqueue_ms_per_frame": host_enqueue_ms,
         "load_scene_s": load_s,
         "clocks": clocks.summary(),
     }

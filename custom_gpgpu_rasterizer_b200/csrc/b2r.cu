@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -95,13 +96,23 @@ struct b2r_context
 	bool sceneDirty = true, texDirty = true;
 	DeviceVec<float2> dIVertex;        // 7 float2 per vertex
 	DeviceVec<uint32_t> dIndices;
-	DeviceVec<float4> dPosIn, dPos4;   // positions in (x,y,z,1) / transformed (ndc.xyz, clip.w)
+	DeviceVec<float4> dPosIn;          // positions in (x,y,z,1)
+	// transformed positions (ndc.xyz, clip.w) and per-mesh constants, double-buffered by frame parity: the vertex
+	// stage of frame f+1 runs on its own stream while frame f is still binning / rasterising
+	DeviceVec<float4> dPos4[2];
+	int geoIdx = 0;                    // parity of the newest enqueued frame
+	cudaStream_t vtxStream = nullptr;
+	cudaEvent_t vtxDone[2] = { nullptr, nullptr }, rasterDone[2] = { nullptr, nullptr }, forkEv = nullptr;
+	bool rasterPending[2] = { false, false }, vtxNeedsFork = true;
+	int overlapVertex = 1;
 	DeviceVec<float> dOvertexScratch;
 	DeviceVec<uint4> dTriRefs;         // static {v0, v1, v2, mesh} per primitive, rebuilt when the mesh list changes
 	DeviceVec<uint2> dRects;
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
-	DeviceVec<MeshConst> dMeshConst;
+	DeviceVec<MeshConst> dMeshConst[2];
+	DeviceVec<MeshStatic> dMeshStatic;
+	bool meshStaticDirty = true, anyDiffuse = false;
 	DeviceVec<TexDesc> dTexDesc;
 
 	// binning
@@ -115,8 +126,9 @@ struct b2r_context
 	struct Slot
 	{
 		HostInfo* hInfo = nullptr;                 // pinned
-		MeshConst* hMeshConst = nullptr;           // pinned staging of the per-mesh constants
-		size_t hMeshConstCap = 0;
+		float* hViewProj = nullptr;                // pinned: the frame's view-projection matrix (read zero-copy by the device)
+		MeshStatic* hStatic = nullptr;             // pinned staging of the camera-independent per-mesh constants
+		size_t hStaticCap = 0;
 		cudaEvent_t done = nullptr;
 		cudaEvent_t ev[10] = {};                    // 0..6 stage boundaries; sharded: 7 after pull, 8 after barrier A, 9 after raster
 		bool pending = false, timed = false, exchanged = false;
@@ -185,15 +197,6 @@ int fail(b2r_context* c, int code, const char* fmt, ...)
 
 uint32_t nBins(const b2r_context* c) { return c->binsX * c->binsY; }
 
-// projection * Inverse(lookAt) * world on the HOST, element order of Matrix4.h:120-143
-void mulMat4(const float* lm, const float* rm, float* out)
-{
-	for (int r = 0; r < 4; ++r)
-		for (int col = 0; col < 4; ++col)
-			out[col * 4 + r] = lm[0 * 4 + r] * rm[col * 4 + 0] + lm[1 * 4 + r] * rm[col * 4 + 1] +
-			                   lm[2 * 4 + r] * rm[col * 4 + 2] + lm[3 * 4 + r] * rm[col * 4 + 3];
-}
-
 int allocSurfaces(b2r_context* c)
 {
 	const size_t n = (size_t)c->width * c->height;
@@ -260,11 +263,11 @@ int rebuildScene(b2r_context* c)
 		build_trirefs_kernel<<<c->nTriChunks, kChunk, 0, c->stream>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dTriRefs.ptr);
 		CU(c, cudaGetLastError());
 	}
-	CU(c, c->dPos4.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
+	for (auto& v : c->dPos4) CU(c, v.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
 	CU(c, c->dTriRefs.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dRects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, c->dBigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
-	CU(c, c->dMeshConst.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
+	for (auto& v : c->dMeshConst) CU(c, v.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
 	// list capacity heuristic; regrown on overflow (see validateFrame)
 	CU(c, c->dBinIds.reserve(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), c->stream));
 	c->sceneDirty = false;
@@ -379,47 +382,80 @@ int enqueueFrame(b2r_context* c)
 		CU(c, cudaEventSynchronize(slot.done));
 		int r = harvestSlot(c, slot); if (r) return r;
 	}
-	if (slot.hMeshConstCap < c->meshes.size())
-	{
-		if (slot.hMeshConst) cudaFreeHost(slot.hMeshConst);
-		slot.hMeshConstCap = std::max<size_t>(c->meshes.size() * 2, 16);
-		CU(c, cudaMallocHost((void**)&slot.hMeshConst, slot.hMeshConstCap * sizeof(MeshConst)));
-	}
 	slot.timed = c->stageTimers != 0;
 	slot.exchanged = slot.timed && c->shard.bound;
-
-	// per-mesh constants
-	for (size_t m = 0; m < c->meshes.size(); ++m)
+	memcpy(slot.hViewProj, rc.viewProj, 64);
+	if (c->meshStaticDirty)
 	{
-		const HostMesh& hm = c->meshes[m];
-		MeshConst& mc = slot.hMeshConst[m];
-		mulMat4(rc.viewProj, hm.world, mc.wvp);
-		memcpy(mc.world, hm.world, 64);
-		for (int col = 0; col < 3; ++col) for (int r = 0; r < 3; ++r) mc.rot[col * 3 + r] = hm.world[col * 4 + r];
-		mc.vtxInBase = hm.vtxInBase; mc.vtxOutBase = hm.vtxOutBase; mc.nVertices = hm.nVertices;
-		mc.idxBase = hm.idxBase; mc.nTris = hm.nTris; mc.primBase = hm.primBase;
-		// CUDARenderer.cu:559-571: Norm only with Diff, Spec/Gloss only with Norm
-		const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);
-		mc.tex[0] = d ? hm.texIds[0] : -1;
-		mc.tex[1] = n ? hm.texIds[1] : -1;
-		mc.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
-		mc.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
-		mc.pad = 0;
+		// camera-independent per-mesh constants: only when the mesh list, a world matrix or the texture set changed
+		if (slot.hStaticCap < c->meshes.size())
+		{
+			if (slot.hStatic) cudaFreeHost(slot.hStatic);
+			slot.hStaticCap = std::max<size_t>(c->meshes.size() * 2, 16);
+			CU(c, cudaMallocHost((void**)&slot.hStatic, slot.hStaticCap * sizeof(MeshStatic)));
+		}
+		c->anyDiffuse = false;
+		for (size_t m = 0; m < c->meshes.size(); ++m)
+		{
+			const HostMesh& hm = c->meshes[m];
+			MeshStatic& ms = slot.hStatic[m];
+			memcpy(ms.world, hm.world, 64);
+			ms.vtxInBase = hm.vtxInBase; ms.vtxOutBase = hm.vtxOutBase; ms.nVertices = hm.nVertices;
+			ms.idxBase = hm.idxBase; ms.nTris = hm.nTris; ms.primBase = hm.primBase;
+			// CUDARenderer.cu:559-571: Norm only with Diff, Spec/Gloss only with Norm
+			const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);
+			ms.tex[0] = d ? hm.texIds[0] : -1;
+			ms.tex[1] = n ? hm.texIds[1] : -1;
+			ms.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
+			ms.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
+			ms.pad[0] = ms.pad[1] = 0;
+			c->anyDiffuse |= d;
+		}
+		CU(c, c->dMeshStatic.reserve(std::max<size_t>(c->meshes.size(), 1), s));
+		if (!c->meshes.empty())
+			CU(c, cudaMemcpyAsync(c->dMeshStatic.ptr, slot.hStatic, c->meshes.size() * sizeof(MeshStatic), cudaMemcpyHostToDevice, s));
+		c->vtxNeedsFork = true;       // the vertex stream must see this copy
+		c->meshStaticDirty = false;
 	}
 	STAGE_EVENT(c, slot, 0);
+	const uint32_t nMeshes = (uint32_t)c->meshes.size();
+	const int g = (int)(c->seq & 1u);
+	c->geoIdx = g;
+	float4* pos4 = c->dPos4[g].ptr;
+	MeshConst* meshConst = c->dMeshConst[g].ptr;
+	// The vertex stage depends on nothing of the previous frame, so (unless the stages are being timed) it runs on
+	// its own stream: vertex(f+1) overlaps binning / raster of frame f.  It re-uses the buffers of frame f-1, hence
+	// the wait for that frame's raster; after an idle point it is ordered behind whatever the caller enqueued.
+	const bool overlap = c->overlapVertex && !slot.timed && c->nVsChunks;
+	if (overlap)
+	{
+		cudaStream_t v = c->vtxStream;
+		if (c->vtxNeedsFork)
+		{
+			CU(c, cudaEventRecord(c->forkEv, s));
+			CU(c, cudaStreamWaitEvent(v, c->forkEv, 0));
+			c->vtxNeedsFork = false;
+		}
+		if (c->rasterPending[g]) CU(c, cudaStreamWaitEvent(v, c->rasterDone[g], 0));
+		build_constants_kernel<<<std::max<uint32_t>(1u, std::min<uint32_t>((nMeshes + 63) / 64, (uint32_t)c->numSMs * 4)), 64, 0, v>>>(
+			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes);
+		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, v>>>(c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4);
+		c->kernelsLaunched += 2;
+		CU(c, cudaEventRecord(c->vtxDone[g], v));
+		CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
+	}
 	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
 	// queue behind the previous frame's 33 MB Present copy
-	static_assert(sizeof(MeshConst) % 16 == 0, "MeshConst is moved as 16-byte vectors");
-	const uint32_t nConstVec = (uint32_t)(c->meshes.size() * sizeof(MeshConst) / 16);
-	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (nConstVec + 255) / 256), (uint32_t)c->numSMs * 4);
+	const uint32_t clearMeshes = overlap ? 0u : nMeshes;
+	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (clearMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
 	frame_clear_kernel<<<clearCtas, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
 		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
-		reinterpret_cast<const uint4*>(slot.hMeshConst), reinterpret_cast<uint4*>(c->dMeshConst.ptr), nConstVec);
+		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes);
 	++c->kernelsLaunched;
 
-	if (c->nVsChunks)
+	if (c->nVsChunks && !overlap)
 	{
-		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, c->dMeshConst.ptr, c->dPosIn.ptr, c->dPos4.ptr);
+		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4);
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 1);
@@ -427,7 +463,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		if (primHi > primLo)
 		{
-			triangle_setup_kernel<<<(primHi - primLo + kChunk - 1) / kChunk, kChunk, 0, s>>>(c->dTriRefs.ptr, c->dPos4.ptr,
+			triangle_setup_kernel<<<(primHi - primLo + kChunk - 1) / kChunk, kChunk, 0, s>>>(c->dTriRefs.ptr, pos4,
 				c->dRects.ptr, tileCount, c->dBigList.ptr, c->dCounters, primLo, primHi, fp);
 			++c->kernelsLaunched;
 		}
@@ -483,8 +519,8 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = c->dPos4.ptr; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
-		A.meshes = c->dMeshConst.ptr; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -520,8 +556,7 @@ int enqueueFrame(b2r_context* c)
 		{
 			const dim3 grid(owned, fp.subX * fp.subY);
 			// light variant when the frame cannot reach the texture / visualiser paths
-			bool anyDiffuse = rc.vis != 0;
-			for (const HostMesh& hm : c->meshes) anyDiffuse |= texValid(c, hm.texIds[0]);
+			const bool anyDiffuse = rc.vis != 0 || c->anyDiffuse;
 			const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (anyDiffuse ? 4 : 0);
 			switch (variant)
 			{
@@ -536,6 +571,9 @@ int enqueueFrame(b2r_context* c)
 			}
 			++c->kernelsLaunched;
 		}
+		// the vertex stage of frame f+2 may overwrite pos4 / constants of this parity once this raster is done
+		CU(c, cudaEventRecord(c->rasterDone[g], s));
+		c->rasterPending[g] = true;
 		if (sh.bound)
 		{
 			STAGE_EVENT(c, slot, 9);
@@ -563,7 +601,8 @@ int validateFrame(b2r_context* c)
 {
 	for (int attempt = 0; attempt < 4; ++attempt)
 	{
-		CU(c, cudaStreamSynchronize(c->stream));
+		CU(c, cudaStreamSynchronize(c->stream));      // the vertex stream is joined into it every frame
+		c->vtxNeedsFork = true; c->rasterPending[0] = c->rasterPending[1] = false;
 		for (uint64_t k = 0; k < kRing; ++k)
 		{
 			b2r_context::Slot& slot = c->slots[(c->seq + k) % kRing];     // oldest first
@@ -662,17 +701,26 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	b2r_context* c = new (std::nothrow) b2r_context;
 	if (!c) return fail(nullptr, B2R_E_INVALID, "out of host memory");
 	c->device = device; c->width = width; c->height = height;
+	if (const char* e = getenv("B2R_OVERLAP_VERTEX")) c->overlapVertex = atoi(e) != 0;      // debugging aid; see B2R_OPT_OVERLAP_VERTEX
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));
 	CUC(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device));
 	CUC(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	c->stream = c->ownStream;
+	CUC(cudaStreamCreateWithFlags(&c->vtxStream, cudaStreamNonBlocking));
+	CUC(cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming));
+	for (int i = 0; i < 2; ++i)
+	{
+		CUC(cudaEventCreateWithFlags(&c->vtxDone[i], cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&c->rasterDone[i], cudaEventDisableTiming));
+	}
 	for (auto& slot : c->slots)
 	{
 		CUC(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
 		for (auto& e : slot.ev) CUC(cudaEventCreate(&e));
 		CUC(cudaMallocHost((void**)&slot.hInfo, sizeof(b2r_context::HostInfo)));
+		CUC(cudaMallocHost((void**)&slot.hViewProj, 64));
 		memset(slot.hInfo, 0, sizeof(b2r_context::HostInfo));
 	}
 	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8 + kCounterWords * 4));
@@ -693,10 +741,13 @@ void b2r_destroy(b2r_context* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->vtxStream) { cudaStreamSynchronize(c->vtxStream); cudaStreamDestroy(c->vtxStream); }
+	if (c->forkEv) cudaEventDestroy(c->forkEv);
+	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
-	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); c->dPos4.release(); c->dOvertexScratch.release();
+	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
 	c->dTriRefs.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
-	c->dMeshConst.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
+	for (auto& v : c->dMeshConst) v.release(); c->dMeshStatic.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
 	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dWarpTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
@@ -706,7 +757,8 @@ void b2r_destroy(b2r_context* c)
 	for (auto& e : c->copyDone) if (e) cudaEventDestroy(e);
 	for (auto& slot : c->slots)
 	{
-		if (slot.hMeshConst) cudaFreeHost(slot.hMeshConst);
+		if (slot.hStatic) cudaFreeHost(slot.hStatic);
+		if (slot.hViewProj) cudaFreeHost(slot.hViewProj);
 		if (slot.hInfo) cudaFreeHost(slot.hInfo);
 		if (slot.done) cudaEventDestroy(slot.done);
 		for (auto& e : slot.ev) if (e) cudaEventDestroy(e);
@@ -730,10 +782,11 @@ int b2r_texture_create_rgba8(b2r_context* c, const uint32_t* pixels, uint32_t w,
 	CU(c, cudaSetDevice(c->device));
 	HostTexture t; t.w = w; t.h = h; t.alive = true;
 	CU(c, cudaMalloc((void**)&t.px, (size_t)w * h * 4));
-	cudaError_t e = cudaMemcpy(t.px, pixels, (size_t)w * h * 4, cudaMemcpyHostToDevice);
+	cudaError_t e = cudaMemcpyAsync(t.px, pixels, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	if (e != cudaSuccess) { cudaFree(t.px); return fail(c, B2R_E_CUDA, "texture upload failed: %s", cudaGetErrorString(e)); }
 	c->textures.push_back(t);
-	c->texDirty = true;
+	c->texDirty = true; c->meshStaticDirty = true;
 	*outId = (int)c->textures.size() - 1;
 	return B2R_OK;
 }
@@ -746,7 +799,7 @@ int b2r_texture_destroy(b2r_context* c, int id)
 	int r = validateFrame(c); if (r) return r;
 	cudaFree(c->textures[id].px);
 	c->textures[id] = HostTexture{};
-	c->texDirty = true;
+	c->texDirty = true; c->meshStaticDirty = true;
 	return B2R_OK;
 }
 
@@ -759,7 +812,7 @@ static int addMesh(b2r_context* c, HostMesh hm, const float world[16], const int
 		return fail(c, B2R_E_INVALID, "scene exceeds 2^32 vertices or primitives");
 	c->nVtxOut += hm.nVertices; c->nPrims += hm.nTris;
 	c->meshes.push_back(hm);
-	c->sceneDirty = true;
+	c->sceneDirty = true; c->meshStaticDirty = true;
 	if (outId) *outId = (int)c->meshes.size() - 1;
 	return B2R_OK;
 }
@@ -780,11 +833,14 @@ int b2r_mesh_upload(b2r_context* c, const void* ivertex56, uint32_t nV, const ui
 	CU(c, c->dPosIn.reserve(c->nVtxIn + nV + 1, c->stream, c->nVtxIn));
 	if (nV)
 	{
-		CU(c, cudaMemcpy(c->dIVertex.ptr + c->nVtxIn * 7, ivertex56, (size_t)nV * 56, cudaMemcpyHostToDevice));
+		// on the context's stream: a plain cudaMemcpy from pageable memory may return before its DMA has landed and
+		// is ordered only against the legacy default stream, not against this (non-blocking) stream
+		CU(c, cudaMemcpyAsync(c->dIVertex.ptr + c->nVtxIn * 7, ivertex56, (size_t)nV * 56, cudaMemcpyHostToDevice, c->stream));
 		split_positions_kernel<<<(nV + 255) / 256, 256, 0, c->stream>>>(c->dIVertex.ptr, c->dPosIn.ptr, (uint32_t)c->nVtxIn, nV);
 		CU(c, cudaGetLastError());
 	}
-	if (nI) CU(c, cudaMemcpy(c->dIndices.ptr + c->nIdx, indices, (size_t)nI * 4, cudaMemcpyHostToDevice));
+	if (nI) CU(c, cudaMemcpyAsync(c->dIndices.ptr + c->nIdx, indices, (size_t)nI * 4, cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));       // the caller keeps ownership of the host arrays
 	HostMesh hm{};
 	hm.vtxInBase = (uint32_t)c->nVtxIn; hm.nVertices = nV; hm.idxBase = (uint32_t)c->nIdx; hm.nTris = nI / 3;
 	c->nVtxIn += nV; c->nIdx += nI;
@@ -806,6 +862,7 @@ int b2r_mesh_set_world(b2r_context* c, int id, const float world[16])
 	if (!c) return B2R_E_INVALID;
 	if (id < 0 || (size_t)id >= c->meshes.size() || !world) return fail(c, B2R_E_INVALID, "bad mesh id %d", id);
 	memcpy(c->meshes[id].world, world, 64);
+	c->meshStaticDirty = true;
 	return B2R_OK;
 }
 
@@ -816,7 +873,7 @@ int b2r_mesh_clear_all(b2r_context* c)
 	int r = validateFrame(c); if (r) return r;
 	c->meshes.clear();
 	c->nVtxIn = c->nVtxOut = c->nIdx = c->nPrims = 0;
-	c->sceneDirty = true;
+	c->sceneDirty = true; c->meshStaticDirty = true;
 	return B2R_OK;
 }
 
@@ -833,6 +890,7 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_SORT_BINS: c->sortBins = value ? 1 : 0; break;
 	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
 	case B2R_OPT_PACKED_OUTPUT: c->packedOutput = value ? 1 : 0; break;
+	case B2R_OPT_OVERLAP_VERTEX: c->overlapVertex = value ? 1 : 0; break;
 	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
 	}
 	if (c->ownerRank >= c->ownerCount) { /* tolerated while the pair is being set; checked at render */ }
@@ -927,7 +985,7 @@ int b2r_read_overtex(b2r_context* c, int id, float* out18)
 	if (!hm.nVertices) return B2R_OK;
 	CU(c, c->dOvertexScratch.reserve((size_t)hm.nVertices * 18, c->stream));
 	const FrameParams fp = makeParams(c, c->last);
-	overtex_kernel<<<(hm.nVertices + 255) / 256, 256, 0, c->stream>>>(c->dMeshConst.ptr, (uint32_t)id, c->dIVertex.ptr, c->dPos4.ptr, c->dOvertexScratch.ptr, fp);
+	overtex_kernel<<<(hm.nVertices + 255) / 256, 256, 0, c->stream>>>(c->dMeshConst[c->geoIdx].ptr, (uint32_t)id, c->dIVertex.ptr, c->dPos4[c->geoIdx].ptr, c->dOvertexScratch.ptr, fp);
 	CU(c, cudaGetLastError());
 	CU(c, cudaMemcpyAsync(out18, c->dOvertexScratch.ptr, (size_t)hm.nVertices * 18 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));

@@ -152,16 +152,49 @@ __device__ __forceinline__ uint32_t warpTileAdd(uint32_t* counters, uint32_t til
 	return 0;
 }
 
+// Per-mesh constants of a frame, built on the device: WVP = viewProj * world in the element order of
+// Matrix4.h:120-143 (what the reference computes on the host, CUDARenderer.cu:242; unfused multiplies and adds,
+// left to right - this translation unit is compiled with -fmad=false, so the bits equal a host evaluation),
+// rot = (FMatrix3)world.  viewProj is read straight from the frame's pinned host slot (zero-copy): the host's
+// per-frame work and the PCIe traffic do not depend on the number of meshes.
+__device__ __forceinline__ void buildMeshConst(const float* __restrict__ vp, const MeshStatic& ms, MeshConst& mc)
+{
+	#pragma unroll
+	for (int col = 0; col < 4; ++col)
+		#pragma unroll
+		for (int r = 0; r < 4; ++r)
+			mc.wvp[col * 4 + r] = vp[0 * 4 + r] * ms.world[col * 4 + 0] + vp[1 * 4 + r] * ms.world[col * 4 + 1] +
+			                      vp[2 * 4 + r] * ms.world[col * 4 + 2] + vp[3 * 4 + r] * ms.world[col * 4 + 3];
+	#pragma unroll
+	for (int i = 0; i < 16; ++i) mc.world[i] = ms.world[i];
+	#pragma unroll
+	for (int col = 0; col < 3; ++col)
+		#pragma unroll
+		for (int r = 0; r < 3; ++r) mc.rot[col * 3 + r] = ms.world[col * 4 + r];
+	mc.vtxInBase = ms.vtxInBase; mc.vtxOutBase = ms.vtxOutBase; mc.nVertices = ms.nVertices;
+	mc.idxBase = ms.idxBase; mc.nTris = ms.nTris; mc.primBase = ms.primBase;
+	mc.tex[0] = ms.tex[0]; mc.tex[1] = ms.tex[1]; mc.tex[2] = ms.tex[2]; mc.tex[3] = ms.tex[3];
+	mc.pad = 0;
+}
+__device__ __forceinline__ void buildMeshConsts(uint32_t gtid, uint32_t gsize, const float* __restrict__ hostViewProj,
+	const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes)
+{
+	if (gtid >= nMeshes) return;
+	float vp[16];
+	#pragma unroll
+	for (int i = 0; i < 16; ++i) vp[i] = hostViewProj[i];
+	for (uint32_t m = gtid; m < nMeshes; m += gsize) buildMeshConst(vp, meshStatic[m], meshConst[m]);
+}
+
 // start of frame: zero the tile counts (tileCount is padded to a multiple of 4 words) and the counters, and
-// fetch the per-mesh constants straight from the pinned host staging buffer (zero-copy read over PCIe).
-// Together with publish_info_kernel this keeps the frame off the copy engines, which belong to Present:
-// a cudaMemcpyAsync here can be queued behind the previous frame's 33 MB framebuffer copy.
+// build the per-mesh constants.  Together with publish_info_kernel this keeps the frame off the copy engines,
+// which belong to Present: a cudaMemcpyAsync here can be queued behind the previous frame's 33 MB framebuffer copy.
 __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__ tileCount, uint32_t nTiles,
 	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords,
-	const uint4* __restrict__ hostConstants, uint4* __restrict__ constants, uint32_t nConstVec)
+	const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes)
 {
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-	for (uint32_t i = gtid; i < nConstVec; i += gsize) constants[i] = hostConstants[i];
+	buildMeshConsts(gtid, gsize, hostViewProj, meshStatic, meshConst, nMeshes);
 	const uint32_t q = (nTiles + 3) / 4;
 	for (uint32_t i = gtid; i < q; i += gsize)
 		reinterpret_cast<uint4*>(tileCount)[i] = make_uint4(0, 0, 0, 0);
@@ -170,6 +203,12 @@ __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__
 		for (uint32_t i = threadIdx.x; i < counterWords; i += blockDim.x) counters[i] = 0;
 		if (threadIdx.x < infoWords) frameInfo[threadIdx.x] = 0;
 	}
+}
+// the constants alone, for frames whose vertex stage runs ahead on its own stream
+__global__ void __launch_bounds__(64) build_constants_kernel(const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic,
+	MeshConst* __restrict__ meshConst, uint32_t nMeshes)
+{
+	buildMeshConsts(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, hostViewProj, meshStatic, meshConst, nMeshes);
 }
 // end of frame: the frame's counters go to the pinned host slot (zero-copy write)
 __global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words)

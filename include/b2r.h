@@ -66,7 +66,11 @@ enum
 	B2R_OPT_COUNT_FRAGMENTS = 7,
 	/* sort-first: write the colours of the owned tiles tile-major (owned tile k, sub-tile s at
 	 * (k*S + s)*256 pixels) instead of row-major, so one rank's share is one contiguous buffer. Default 0. */
-	B2R_OPT_PACKED_OUTPUT = 8
+	B2R_OPT_PACKED_OUTPUT = 8,
+	/* run the vertex stage of a frame on a second stream so that it overlaps binning / raster of the previous
+	 * frame when frames are enqueued back to back (transformed positions and per-mesh constants are
+	 * double-buffered).  Ignored while B2R_OPT_STAGE_TIMERS is on.  Default 1. */
+	B2R_OPT_OVERLAP_VERTEX = 10
 };
 
 /* stage indices for b2r_get_stage_ms */
