@@ -332,7 +332,10 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	const float extx = b.maxx - b.minx, exty = b.maxy - b.miny;
 	const float D = extx + exty + 2.f;
 	const float maxAbs = fmaxf(fmaxf(fabsf(b.minx), fabsf(b.maxx)), fmaxf(fabsf(b.miny), fabsf(b.maxy)));
-	const float k = 3.814697265625e-6f * D * D / r.area;
+	// hoisted reciprocal first: it also serves the margin (times 1 + 2^-20, so the product is an upper bound of
+	// D*D/area; a zero / non-finite area makes eps non-finite and selects the whole-screen box below)
+	r.rcpArea = refinedReciprocal(r.area);
+	const float k = 3.814697265625e-6f * D * D * (r.rcpArea * 1.00000095367431640625f);
 	const float epsx = 0.015625f + maxAbs * 1.52587890625e-5f + k * extx;
 	const float epsy = 0.015625f + maxAbs * 1.52587890625e-5f + k * exty;
 	int cx0 = 0, cx1 = (int)fp.width, cy0 = 0, cy1 = (int)fp.height;
@@ -346,7 +349,6 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	r.cbX = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
 	r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
 	// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn) ...
-	r.rcpArea = refinedReciprocal(r.area);
 	r.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
 	// ... and a conservative lower bound of the integer depth: weights are in [0, 1 + few ulp] and
 	// sum to 1 +- few ulp, so z >= min(z_i) - small; anything non-finite or negative means "no bound"
