@@ -293,6 +293,8 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.width = c->width; fp.height = c->height;
 	fp.binsX = c->binsX; fp.binsY = c->binsY; fp.binW = c->binW; fp.binH = c->binH;
 	fp.subX = (c->binW + kTile - 1) / kTile; fp.subY = (c->binH + kTile - 1) / kTile;
+	auto log2OrMinus1 = [](uint32_t v) { int s = 0; while ((1u << s) < v) ++s; return (1u << s) == v ? s : -1; };
+	fp.binShiftX = log2OrMinus1(c->binW); fp.binShiftY = log2OrMinus1(c->binH);
 	fp.cullMode = (uint32_t)rc.cull; fp.sampleState = (uint32_t)rc.sample; fp.visState = (uint32_t)rc.vis;
 	fp.fillTopLeft = (uint32_t)c->fillTopLeft;
 	fp.ownerRank = (uint32_t)c->ownerRank; fp.ownerCount = (uint32_t)c->ownerCount;

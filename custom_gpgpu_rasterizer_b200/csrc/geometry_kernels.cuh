@@ -240,13 +240,13 @@ __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, 
 	{
 		// 32 union tiles at a time: lane u keeps the ballot of tile u, then ALL tiles' atomics are issued by one
 		// instruction (one round trip to L2 instead of one per tile), then the ids are written tile by tile
+		int tx = ux0, ty = uy0;        // row-major walk over the union, carried across the 32-tile chunks (no div / mod)
 		for (uint32_t u0 = 0; u0 < uArea; u0 += 32)
 		{
 			const uint32_t uEnd = min(uArea - u0, 32u);
 			uint32_t myMask = 0, myTile = 0;
 			for (uint32_t u = 0; u < uEnd; ++u)
 			{
-				const int tx = ux0 + (int)((u0 + u) % uw), ty = uy0 + (int)((u0 + u) / uw);
 				const bool in = nTiles && tx >= bx0 && tx <= bx1 && ty >= by0 && ty <= by1;
 				const unsigned mask = __ballot_sync(0xFFFFFFFFu, in);
 				if (lane == u)
@@ -254,6 +254,7 @@ __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, 
 					myTile = (uint32_t)tx + (uint32_t)ty * fp.binsX;
 					myMask = tileOwned(fp, myTile) ? mask : 0u;
 				}
+				if (++tx > ux1) { tx = ux0; ++ty; }
 			}
 			if (SCATTER)
 			{
@@ -400,10 +401,12 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 			const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
 			const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
 			const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
-			bx0 = clampi(xMin / (int)fp.binW, 0, (int)fp.binsX);
-			by0 = clampi(yMin / (int)fp.binH, 0, (int)fp.binsY);
-			bx1 = clampi(xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
-			by1 = clampi(yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
+			// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
+			const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+			bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
+			by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
+			bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
+			by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
 		}
 		// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
 		// from a visible primitive whose rectangle happens to be empty
