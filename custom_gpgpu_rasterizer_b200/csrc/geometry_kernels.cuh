@@ -213,8 +213,7 @@ __global__ void __launch_bounds__(64) build_constants_kernel(const float* __rest
 // end of frame: the frame's counters go to the pinned host slot (zero-copy write)
 __global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words)
 {
-	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];
-	__threadfence_system();
+	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];      // visible to the host once the frame's `done` event has completed
 }
 
 // Warp-level binning of up to 32 small rectangles (one per lane, rectangle = inclusive tile range,
