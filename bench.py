@@ -146,7 +146,7 @@ def workload_config(name, scene):
                          "fill64": "BASELINE config 4: 64 stacked full-screen textured quads, 3840x2160, linear sampling, no culling",
                          "spheres_small": "5x5 spheres (400 000 triangles), 3840x2160"}[name],
             "triangles": scene.n_tris, "vertices": scene.n_vertices, "resolution": f"{scene.width}x{scene.height}",
-            "l2_policy": "inputs larger than L2 (vertex+index streams 410 MB, intermediates ~1 GB per frame)" if name == "spheres10m" else "working set is L2-resident by nature of the workload (textures + 128 triangles); framebuffer write-back 66 MB per frame"}
+            "l2_policy": "inputs larger than L2 (static position / triangle-reference / vertex streams 530 MB; ~0.9 GB of DRAM traffic per frame)" if name == "spheres10m" else "working set is L2-resident by nature of the workload (textures + 128 triangles); framebuffer write-back 66 MB per frame"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm

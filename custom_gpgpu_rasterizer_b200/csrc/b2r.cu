@@ -116,7 +116,7 @@ struct b2r_context
 	DeviceVec<TexDesc> dTexDesc;
 
 	// binning
-	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dWarpTiles, dBigList, dBinIds;
+	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dBigList, dBinIds;
 	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
 	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };   // device layout: dFrameInfo, then dCounters
@@ -230,7 +230,6 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 	CU(c, c->dTileCursor.reserve(n, c->stream));
 	CU(c, c->dLongTiles.reserve(n, c->stream));
 	CU(c, c->dMidTiles.reserve(n, c->stream));
-	CU(c, c->dWarpTiles.reserve(n, c->stream));
 	// tile_scan_kernel reads the counts with 16-byte loads
 	CU(c, c->dTileCount.reserve((size_t)n + 4, c->stream));
 	CU(c, c->dTileOffset.reserve((size_t)n + 4, c->stream));    // [n] = overflow marker for peer ranks
@@ -521,7 +520,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr; A.indices = c->dIndices.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
@@ -750,7 +749,7 @@ void b2r_destroy(b2r_context* c)
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
 	c->dTriRefs.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
 	for (auto& v : c->dMeshConst) v.release(); c->dMeshStatic.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
-	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dWarpTiles.release(); c->dBigList.release(); c->dBinIds.release();
+	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dBigList.release(); c->dBinIds.release();
 	cudaFree(c->dFrameInfo);
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
 	releaseShard(c);

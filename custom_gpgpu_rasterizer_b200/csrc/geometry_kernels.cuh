@@ -667,10 +667,9 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t
 //  tier 3: the "long" work list (up to kSortLarge entries) in dynamic shared memory, one CTA per SM
 //  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
-constexpr int kSortWarp = 256;       // <= : register bitonic, one warp
-constexpr int kSortWarpRadix = 1024; // <= : shared-memory radix, one warp, no block barriers
-constexpr int kSortSmall = 4096;     // <= : shared-memory radix, one CTA
-constexpr int kSortLarge = 40960;
+constexpr int kSortWarpRadix = 1024; // <= : tier 1, one warp per tile (run ordering in shared memory)
+constexpr int kSortSmall = 4096;     // <= : tier 2, one CTA per tile
+constexpr int kSortLarge = 40960;    // <= : tier 3, one CTA per SM, dynamic shared memory
 constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
 
 // register bitonic network over 256 keys held 8 per lane, virtual index v = i*32 + lane

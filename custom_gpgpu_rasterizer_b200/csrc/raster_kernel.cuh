@@ -26,7 +26,6 @@ struct RasterArgs
 	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
 	const float2* ivertex;      // resident IVertex records (7 float2 each)
-	const uint32_t* indices;
 	const MeshConst* meshes;
 	const TexDesc* textures;
 	unsigned long long* frameInfo;
