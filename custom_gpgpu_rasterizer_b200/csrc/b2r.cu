@@ -104,7 +104,7 @@ struct b2r_context
 	cudaStream_t vtxStream = nullptr;
 	cudaEvent_t vtxDone[2] = { nullptr, nullptr }, rasterDone[2] = { nullptr, nullptr }, forkEv = nullptr;
 	bool rasterPending[2] = { false, false }, vtxNeedsFork = true;
-	int overlapVertex = 1;
+	int overlapVertex = 1, usePdl = 1;
 	DeviceVec<float> dOvertexScratch;
 	DeviceVec<uint4> dTriRefs;         // static {v0, v1, v2, mesh} per primitive, rebuilt when the mesh list changes
 	DeviceVec<uint2> dRects;
@@ -305,6 +305,19 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	return fp;
 }
 
+// kernel launch with the programmatic-dependent-launch attribute (see pdlPrologue in device_types.cuh)
+template <typename... P, typename... A>
+cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args)
+{
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+	cudaLaunchAttribute attr{};
+	attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr.val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = &attr; cfg.numAttrs = c->usePdl ? 1u : 0u;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
 #define STAGE_EVENT(c, slot, i) do { if ((slot).timed) CU((c), cudaEventRecord((slot).ev[(i)], (c)->stream)); } while (0)
 
 // book-keeping of a finished frame: capacity overflow, stage times, counters
@@ -438,9 +451,9 @@ int enqueueFrame(b2r_context* c)
 			c->vtxNeedsFork = false;
 		}
 		if (c->rasterPending[g]) CU(c, cudaStreamWaitEvent(v, c->rasterDone[g], 0));
-		build_constants_kernel<<<std::max<uint32_t>(1u, std::min<uint32_t>((nMeshes + 63) / 64, (uint32_t)c->numSMs * 4)), 64, 0, v>>>(
-			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes);
-		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, v>>>(c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4);
+		CU(c, launchFrameKernel(c, build_constants_kernel, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((nMeshes + 63) / 64, (uint32_t)c->numSMs * 4))), dim3(64), 0, v, 
+			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
+		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, v, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
 		c->kernelsLaunched += 2;
 		CU(c, cudaEventRecord(c->vtxDone[g], v));
 		CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
@@ -449,14 +462,14 @@ int enqueueFrame(b2r_context* c)
 	// queue behind the previous frame's 33 MB Present copy
 	const uint32_t clearMeshes = overlap ? 0u : nMeshes;
 	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (clearMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
-	frame_clear_kernel<<<clearCtas, 256, 0, s>>>(tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
+	CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(clearCtas), dim3(256), 0, s, tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
 		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
-		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes);
+		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes));
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks && !overlap)
 	{
-		vertex_transform_kernel<<<c->nVsChunks, kChunk, 0, s>>>(c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4);
+		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, s, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 1);
@@ -464,17 +477,17 @@ int enqueueFrame(b2r_context* c)
 	{
 		if (primHi > primLo)
 		{
-			triangle_setup_kernel<<<(primHi - primLo + kChunk - 1) / kChunk, kChunk, 0, s>>>(c->dTriRefs.ptr, pos4,
-				c->dRects.ptr, tileCount, c->dBigList.ptr, c->dCounters, primLo, primHi, fp);
+			CU(c, launchFrameKernel(c, triangle_setup_kernel, dim3((primHi - primLo + kChunk - 1) / kChunk), dim3(kChunk), 0, s, c->dTriRefs.ptr, pos4,
+				c->dRects.ptr, tileCount, c->dBigList.ptr, c->dCounters, primLo, primHi, fp));
 			++c->kernelsLaunched;
 		}
-		bin_big_count_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dBigList.ptr, c->dCounters, c->dRects.ptr, tileCount, fp);
+		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, s, c->dBigList.ptr, c->dCounters, c->dRects.ptr, tileCount, fp));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 2);
-	tile_scan_kernel<<<(tiles + kScanPerCta - 1) / kScanPerCta, kScanThreads, 0, s>>>(tileCount, tileOffset, c->dTileCursor.ptr, tiles,
+	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, s, tileCount, tileOffset, c->dTileCursor.ptr, tiles,
 		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
-		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo);
+		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo));
 	++c->kernelsLaunched;
 	if (sh.bound)
 	{
@@ -485,7 +498,7 @@ int enqueueFrame(b2r_context* c)
 			uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
 			inbox.tileCount[p] = sh.inboxCount(base, set, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, set, sh.self);
 		}
-		shard_push_heads_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n);
+		CU(c, launchFrameKernel(c, shard_push_heads_kernel, dim3((tiles + 255) / 256), dim3(256), 0, s, tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 3);
@@ -494,18 +507,18 @@ int enqueueFrame(b2r_context* c)
 		{
 			// per-primitive CTAs, followed by the CTAs that scatter the cooperatively binned (big) triangles
 			const uint32_t primBlocks = (primHi - primLo + 255) / 256;
-			bin_scatter_kernel<<<primBlocks + (uint32_t)c->numSMs * 2, 256, 0, s>>>(c->dRects.ptr, primLo, primHi, tileOffset,
-				c->dTileCursor.ptr, binIds, c->dBigList.ptr, c->dCounters, primBlocks, c->dFrameInfo, fp);
+			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, s, c->dRects.ptr, primLo, primHi, tileOffset,
+				c->dTileCursor.ptr, binIds, c->dBigList.ptr, c->dCounters, primBlocks, c->dFrameInfo, fp));
 			++c->kernelsLaunched;
 		}
 	}
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		bin_sort_runs_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(tileCount, tileOffset, binIds, tiles, c->dMidTiles.ptr, c->dFrameInfo);
-		bin_sort_mid_kernel<<<c->numSMs * 4, 256, 0, s>>>(c->dMidTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo);
-		bin_sort_long_kernel<<<c->numSMs, 1024, kSortLongSmem, s>>>(c->dLongTiles.ptr, tileCount, tileOffset,
-			binIds, c->dFrameInfo);
+		CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, tileCount, tileOffset, binIds, tiles, c->dMidTiles.ptr, c->dFrameInfo));
+		CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, s, c->dMidTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo));
+		CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, s, c->dLongTiles.ptr, tileCount, tileOffset,
+			binIds, c->dFrameInfo));
 		c->kernelsLaunched += 3;
 	}
 	if (sh.bound && c->nPrims)
@@ -513,7 +526,7 @@ int enqueueFrame(b2r_context* c)
 		// mirror the sorted lists into their owners' memory (posted stores; landed by the time of the barrier)
 		ShardRegions R{};
 		for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], set, sh.self);
-		shard_push_lists_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, c->dFrameInfo);
+		CU(c, launchFrameKernel(c, shard_push_lists_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, c->dFrameInfo));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 5);
@@ -546,7 +559,7 @@ int enqueueFrame(b2r_context* c)
 			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
 			// "lists ready": nobody reads a peer's lists before that peer has sorted them.  (Rank 0 arrives only
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
-			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo);
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo));
 			++c->kernelsLaunched;
 			STAGE_EVENT(c, slot, 8);
 			A.shard = T;
@@ -561,14 +574,14 @@ int enqueueFrame(b2r_context* c)
 			const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (anyDiffuse ? 4 : 0);
 			switch (variant)
 			{
-			case 0: raster_shade_kernel<false, false, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 1: raster_shade_kernel<true, false, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 2: raster_shade_kernel<false, true, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 3: raster_shade_kernel<true, true, false><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 4: raster_shade_kernel<false, false, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 5: raster_shade_kernel<true, false, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			case 6: raster_shade_kernel<false, true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
-			default: raster_shade_kernel<true, true, true><<<grid, kTile * kTile, 0, s>>>(A, fp); break;
+			case 0: CU(c, launchFrameKernel(c, raster_shade_kernel<false, false, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			case 1: CU(c, launchFrameKernel(c, raster_shade_kernel<true, false, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			case 2: CU(c, launchFrameKernel(c, raster_shade_kernel<false, true, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			case 3: CU(c, launchFrameKernel(c, raster_shade_kernel<true, true, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			case 4: CU(c, launchFrameKernel(c, raster_shade_kernel<false, false, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			case 5: CU(c, launchFrameKernel(c, raster_shade_kernel<true, false, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			case 6: CU(c, launchFrameKernel(c, raster_shade_kernel<false, true, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
+			default: CU(c, launchFrameKernel(c, raster_shade_kernel<true, true, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
 			}
 			++c->kernelsLaunched;
 		}
@@ -579,14 +592,14 @@ int enqueueFrame(b2r_context* c)
 		{
 			STAGE_EVENT(c, slot, 9);
 			// "colours landed": every rank tells rank 0 that its tiles are in rank 0's surface; only rank 0 waits
-			peer_barrier_kernel<<<1, 32, 0, s>>>(pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame + 1u, 0u, sh.self == 0 ? 1u : 0u, c->dFrameInfo);
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame + 1u, 0u, sh.self == 0 ? 1u : 0u, c->dFrameInfo));
 			++c->kernelsLaunched;
 			++c->shard.frame;
 		}
 	}
 	STAGE_EVENT(c, slot, 6);
 	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
-	publish_info_kernel<<<1, 32, 0, s>>>(c->dFrameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8));
+	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, s, c->dFrameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8)));
 	++c->kernelsLaunched;
 	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
@@ -702,7 +715,8 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	b2r_context* c = new (std::nothrow) b2r_context;
 	if (!c) return fail(nullptr, B2R_E_INVALID, "out of host memory");
 	c->device = device; c->width = width; c->height = height;
-	if (const char* e = getenv("B2R_OVERLAP_VERTEX")) c->overlapVertex = atoi(e) != 0;      // debugging aid; see B2R_OPT_OVERLAP_VERTEX
+	if (const char* e = getenv("B2R_OVERLAP_VERTEX")) c->overlapVertex = atoi(e) != 0;
+	if (const char* e = getenv("B2R_PDL")) c->usePdl = atoi(e) != 0;                           // debugging aid: programmatic dependent launch      // debugging aid; see B2R_OPT_OVERLAP_VERTEX
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
 	const float4* __restrict__ posIn, float4* __restrict__ pos4)
 {
+	pdlPrologue();
 	__shared__ float sMat[16];
 	const Chunk ch = chunks[blockIdx.x];
 	if (threadIdx.x < 16) sMat[threadIdx.x] = meshes[ch.mesh].wvp[threadIdx.x];
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__
 	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords,
 	const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes)
 {
+	pdlPrologue();
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	buildMeshConsts(gtid, gsize, hostViewProj, meshStatic, meshConst, nMeshes);
 	const uint32_t q = (nTiles + 3) / 4;
@@ -208,11 +210,13 @@ __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__
 __global__ void __launch_bounds__(64) build_constants_kernel(const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic,
 	MeshConst* __restrict__ meshConst, uint32_t nMeshes)
 {
+	pdlPrologue();
 	buildMeshConsts(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, hostViewProj, meshStatic, meshConst, nMeshes);
 }
 // end of frame: the frame's counters go to the pinned host slot (zero-copy write)
 __global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words)
 {
+	pdlPrologue();
 	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];      // visible to the host once the frame's `done` event has completed
 }
 
@@ -365,6 +369,7 @@ __global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
 	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig*/,
 	uint32_t primLo, uint32_t primHi, FrameParams fp)
 {
+	pdlPrologue();
 	bool visible = false;
 	const uint32_t prim = primLo + blockIdx.x * kChunk + threadIdx.x;
 	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(256) bin_big_count_kernel(
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, const uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, FrameParams fp)
 {
+	pdlPrologue();
 	binBigBody<false>(blockIdx.x, gridDim.x, bigList, counters, rects, tileCount, nullptr, nullptr, nullptr, fp);
 }
 
@@ -481,6 +487,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
 	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles; [6] is the run sorter's fallback count*/)
 {
+	pdlPrologue();
 	// published slice sums: bit 63 = ready (frame_clear_kernel zeroes them)
 	volatile unsigned long long* partial = reinterpret_cast<volatile unsigned long long*>(counters + kScanBase);
 	if (blockIdx.x == 0 && threadIdx.x < 32)
@@ -599,6 +606,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, uint32_t primBlocks,
 	const unsigned long long* __restrict__ frameInfo, FrameParams fp)
 {
+	pdlPrologue();
 	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
 	if (blockIdx.x >= primBlocks)
 	{
@@ -639,6 +647,7 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch,
 	uint32_t signalAll, uint32_t wait, unsigned long long* __restrict__ frameInfo)
 {
+	pdlPrologue();
 	const uint32_t lane = threadIdx.x;
 	__threadfence_system();
 	if (lane < n && (signalAll || lane == 0u))
@@ -717,6 +726,7 @@ __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
 	uint32_t nTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)
 {
+	pdlPrologue();
 	__shared__ uint32_t sK[8][kSortWarpRadix];
 	__shared__ uint16_t sStart[8][kMaxRuns + 1], sOrder[8][kMaxRuns], sOut[8][kMaxRuns];
 	if (frameInfo[1]) return;
@@ -952,6 +962,7 @@ __global__ void __launch_bounds__(256) bin_sort_mid_kernel(
 	const uint32_t* __restrict__ midTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
 {
+	pdlPrologue();
 	__shared__ uint32_t sA[kSortSmall], sB[kSortSmall], sHist[8 * 256], sRed[2 * 8 + 2];
 	__shared__ uint32_t sHead[kMidRuns], sWarpScan[9];
 	__shared__ uint16_t sStart[kMidRuns + 1], sOrder[kMidRuns], sOut[kMidRuns];
@@ -1044,6 +1055,7 @@ __global__ void __launch_bounds__(1024) bin_sort_long_kernel(
 	const uint32_t* __restrict__ longTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ binIds, unsigned long long* __restrict__ frameInfo)
 {
+	pdlPrologue();
 	extern __shared__ uint32_t sDyn[];      // [kSortLarge] keys + [32*256] counters + reductions
 	if (frameInfo[1]) return;
 	const uint32_t nLong = (uint32_t)frameInfo[3];

@@ -206,6 +206,7 @@ constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are raste
 template <bool TOPLEFT, bool COUNT, bool TEXTURED>
 __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
+	pdlPrologue();
 	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
 	__shared__ uint32_t sNumBig;
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 __global__ void __launch_bounds__(256) shard_push_heads_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
 	uint32_t nTiles, ShardInbox inbox, uint32_t nRanks)
 {
+	pdlPrologue();
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t < nTiles)
 	{
@@ -481,6 +483,7 @@ __global__ void __launch_bounds__(256) shard_push_lists_kernel(const uint32_t* _
 	const uint32_t* __restrict__ binIds, uint32_t nTiles, ShardRegions R, uint32_t nRanks, uint32_t self,
 	const unsigned long long* __restrict__ frameInfo)
 {
+	pdlPrologue();
 	if (frameInfo[1]) return;
 	const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
 	if (t >= nTiles) return;
