@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	pdlPrologue();
 	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
-	__shared__ uint32_t sNumBig;
+	__shared__ uint32_t sNumBig[2];                    // big-triangle count of the current / the next list chunk
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
 	const uint32_t ownedIdx = blockIdx.x;
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 	uint32_t bestPrim = kNoPrim;
 	uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
 	sKey[tid] = kEmptyKey;
+	if (tid < 2) sNumBig[tid] = 0;
 	uint32_t n;
 	const uint32_t* list = nullptr;
 	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
@@ -272,10 +273,12 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		list = A.binIds + A.tileOffset[bin];
 	}
 
-	for (uint32_t base = 0; base < n; base += kListChunk)
+	// two barriers per chunk of the list (one for a list of up to 256 entries): the counter of the NEXT chunk is
+	// reset while the current one is being filled, and the trailing barrier only protects sBig from the next chunk
+	if (n && !fp.shardGeometry) __syncthreads();       // sKey / counters initialised (the sharded path has synchronised above)
+	for (uint32_t base = 0, it = 0; base < n; base += kListChunk, ++it)
 	{
-		if (tid == 0) sNumBig = 0;
-		__syncthreads();
+		if (tid == 0) sNumBig[(it + 1u) & 1u] = 0;
 		const uint32_t m = min((uint32_t)kListChunk, n - base);
 		if ((uint32_t)tid < m)
 		{
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 				if (area > kSmallArea)
 				{
 					// pixel-parallel: bbox rows are kept in zLow's neighbours for the warp-level reject
-					TriShared& dst = sBig[atomicAdd(&sNumBig, 1u)];
+					TriShared& dst = sBig[atomicAdd(&sNumBig[it & 1u], 1u)];
 					dst = t;
 					dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
 				}
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 		}
 		__syncthreads();
 		// pixel-parallel path: every thread tests its own pixel against each large triangle
-		const uint32_t nBig = sNumBig;
+		const uint32_t nBig = sNumBig[it & 1u];
 		for (uint32_t j = 0; j < nBig; ++j)
 		{
 			TriShared t = sBig[j];
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_
 				if (zi < bestZ || (zi == bestZ && t.prim < bestPrim)) { bestZ = zi; bestPrim = t.prim; }
 			}
 		}
-		__syncthreads();
+		if (base + kListChunk < n) __syncthreads();
 	}
 	unsigned long long best = (bestPrim == kNoPrim) ? kEmptyKey : (((unsigned long long)(uint32_t)bestZ << 32) | bestPrim);
 	best = min(best, sKey[tid]);
