@@ -165,6 +165,8 @@ struct b2r_context
 		uint32_t* colourBase = nullptr;        // rank 0: own 2-surface allocation; others: the mapping of it
 		bool colourIsPeer = false;
 		uint32_t frame = 0;                    // frames rendered since the bind (same on every rank)
+		uint32_t waitedFrame = 0;              // rank 0: frames whose "colours landed" flags have been waited for
+		unsigned long long* hTimeout = nullptr; // pinned: raised by a colour wait that ran into its time-out
 		// arena: 256 B of flag words, then per set {tileCount, tileOffset, inbox count[n], inbox offset[n], binIds, region[n]}
 		uint32_t* tileCount(uint8_t* base, int set) const { return reinterpret_cast<uint32_t*>(base + 256 + (size_t)set * setBytes); }
 		uint32_t* tileOffset(uint8_t* base, int set) const { return tileCount(base, set) + tilesPad; }
@@ -559,7 +561,7 @@ int enqueueFrame(b2r_context* c)
 			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
 			// "lists ready": nobody reads a peer's lists before that peer has sorted them.  (Rank 0 arrives only
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
-			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo));
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo + 7));
 			++c->kernelsLaunched;
 			STAGE_EVENT(c, slot, 8);
 			A.shard = T;
@@ -591,15 +593,18 @@ int enqueueFrame(b2r_context* c)
 		if (sh.bound)
 		{
 			STAGE_EVENT(c, slot, 9);
-			// "colours landed": every rank tells rank 0 that its tiles are in rank 0's surface; only rank 0 waits
-			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame + 1u, 0u, sh.self == 0 ? 1u : 0u, c->dFrameInfo));
-			++c->kernelsLaunched;
 			++c->shard.frame;
 		}
 	}
+	// "colours landed": publish_info_kernel tells rank 0 that this rank's tiles of the frame are in rank 0's surface;
+	// rank 0 waits for the flags only when it reads or presents the frame (enqueueColourWait)
+	uint32_t* landedFlag = nullptr;
+	if (sh.bound)
+		landedFlag = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]) + 8 + sh.self;
 	STAGE_EVENT(c, slot, 6);
 	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
-	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, s, c->dFrameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8)));
+	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, s, c->dFrameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8),
+		landedFlag, c->shard.frame));
 	++c->kernelsLaunched;
 	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
@@ -609,13 +614,32 @@ int enqueueFrame(b2r_context* c)
 	return B2R_OK;
 }
 
+// sharded front end, rank 0: before the newest frame is read or presented, wait until every rank's colours of
+// it have landed in this rank's surface (flag words 8..15 of the arena, stored by the ranks' publish_info_kernel)
+int enqueueColourWait(b2r_context* c)
+{
+	b2r_context::Shard& sh = c->shard;
+	if (!sh.bound || sh.self != 0 || sh.waitedFrame == sh.frame) return B2R_OK;
+	PeerFlags pf{};
+	for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(p == sh.self ? sh.arena : sh.peerArena[p]);
+	CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, c->stream, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame, 0u, 1u, sh.hTimeout));
+	sh.waitedFrame = sh.frame;
+	return B2R_OK;
+}
+
 // wait for every frame in flight; if the bin-list buffer was too small for any of them, grow it
 // and run the newest frame again (older frames were overwritten anyway)
 int validateFrame(b2r_context* c)
 {
 	for (int attempt = 0; attempt < 4; ++attempt)
 	{
+		{ int r = enqueueColourWait(c); if (r) return r; }
 		CU(c, cudaStreamSynchronize(c->stream));      // the vertex stream is joined into it every frame
+		if (c->shard.hTimeout && *c->shard.hTimeout)
+		{
+			*c->shard.hTimeout = 0;
+			return fail(c, B2R_E_STATE, "sharded front end: a peer rank's colours did not arrive within 4 s");
+		}
 		c->vtxNeedsFork = true; c->rasterPending[0] = c->rasterPending[1] = false;
 		for (uint64_t k = 0; k < kRing; ++k)
 		{
@@ -648,6 +672,7 @@ static void releaseShard(b2r_context* c)
 		if (sh.peerArena[p]) { cudaIpcCloseMemHandle(sh.peerArena[p]); sh.peerArena[p] = nullptr; }
 	if (sh.colourIsPeer && sh.colourBase) cudaIpcCloseMemHandle(sh.colourBase);
 	if (sh.arena) cudaFree(sh.arena);
+	if (sh.hTimeout) cudaFreeHost(sh.hTimeout);
 	sh = b2r_context::Shard{};
 }
 
@@ -967,6 +992,7 @@ int b2r_present_async(b2r_context* c, uint32_t* hostPixels)
 		for (auto& e : c->copyDone) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	}
 	const int idx = c->lastColourIdx;
+	{ int r = enqueueColourWait(c); if (r) return r; }
 	CU(c, cudaEventRecord(c->frameDone, c->stream));
 	CU(c, cudaStreamWaitEvent(c->copyStream, c->frameDone, 0));
 	CU(c, cudaMemcpyAsync(hostPixels, c->dColour[idx], bytes, cudaMemcpyDeviceToHost, c->copyStream));
@@ -1180,6 +1206,8 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	const size_t bytes = 256 + 2 * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));
 	CU(c, cudaMemset(sh.arena, 0, bytes));
+	CU(c, cudaMallocHost((void**)&sh.hTimeout, 8));
+	*sh.hTimeout = 0;
 	memset(arenaHandle64, 0, 64); memset(colourHandle64, 0, 64);
 	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)arenaHandle64, sh.arena));
 	if (rank == 0) CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)colourHandle64, c->dFramebuffer));

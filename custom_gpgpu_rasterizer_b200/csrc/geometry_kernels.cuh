@@ -213,11 +213,19 @@ __global__ void __launch_bounds__(64) build_constants_kernel(const float* __rest
 	pdlPrologue();
 	buildMeshConsts(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, hostViewProj, meshStatic, meshConst, nMeshes);
 }
-// end of frame: the frame's counters go to the pinned host slot (zero-copy write)
-__global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words)
+// end of frame: the frame's counters go to the pinned host slot (zero-copy write).  Sharded front end: the same
+// kernel tells rank 0 that this rank's colours of the frame are in rank 0's surface (the raster kernel before it
+// in the stream has completed, so its NVLink stores have landed).
+__global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words,
+	uint32_t* landedFlag, uint32_t epoch)
 {
 	pdlPrologue();
 	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];      // visible to the host once the frame's `done` event has completed
+	if (landedFlag && threadIdx.x == 0)
+	{
+		__threadfence_system();
+		*reinterpret_cast<volatile uint32_t*>(landedFlag) = epoch;
+	}
 }
 
 // Warp-level binning of up to 32 small rectangles (one per lane, rectangle = inclusive tile range,
@@ -634,8 +642,9 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 }
 
 // Cross-GPU ordering point of the sharded front end (one warp).  Every rank stores `epoch` into its slot of
-// the peers' flag words over NVLink (signalAll) or of rank 0's only, then (wait) spins until all ranks'
-// slots in its OWN flag words have reached the epoch.  The preceding kernels of the stream have completed,
+// the peers' flag words over NVLink (signal), then (wait) spins until all ranks' slots in its OWN flag words
+// have reached the epoch.  "Lists ready" (slots 0..7) does both inside every frame; "colours landed" (slots
+// 8..15) is signalled by publish_info_kernel and waited for by rank 0 only when it reads or presents the frame.  The preceding kernels of the stream have completed,
 // so their writes (bin lists; colours stored into rank 0's surface) are visible before the flag.  A peer
 // that never arrives raises frameInfo[7] after ~4 s instead of hanging the GPU.
 __device__ __forceinline__ unsigned long long globalTimerNs()
@@ -645,12 +654,12 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
 	return t;
 }
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch,
-	uint32_t signalAll, uint32_t wait, unsigned long long* __restrict__ frameInfo)
+	uint32_t signal, uint32_t wait, unsigned long long* timeoutFlag /*device frameInfo[7] or a pinned host word*/)
 {
 	pdlPrologue();
 	const uint32_t lane = threadIdx.x;
 	__threadfence_system();
-	if (lane < n && (signalAll || lane == 0u))
+	if (signal && lane < n)
 		*reinterpret_cast<volatile uint32_t*>(pf.flags[lane] + slotBase + self) = epoch;
 	if (wait && lane < n)
 	{
@@ -658,7 +667,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t
 		const unsigned long long t0 = globalTimerNs();
 		while ((int)(*f - epoch) < 0)
 		{
-			if (globalTimerNs() - t0 > 4000000000ull) { frameInfo[7] = 1ull; break; }
+			if (globalTimerNs() - t0 > 4000000000ull) { *timeoutFlag = 1ull; break; }
 			__nanosleep(64);
 		}
 	}
