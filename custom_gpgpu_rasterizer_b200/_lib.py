@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIBRARY") or os.path.join(_HERE, "csrc", "libb2r.so")     # B2R_LIBRARY: A/B builds of the same ABI
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

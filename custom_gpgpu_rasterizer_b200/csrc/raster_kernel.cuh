@@ -204,7 +204,13 @@ constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are raste
 // visualisation is PBR (vertex colours only): the texture/normal-mapping path is compiled out, which
 // frees enough registers for 6 resident CTAs per SM instead of 4.
 template <bool TOPLEFT, bool COUNT, bool TEXTURED>
-__global__ void __launch_bounds__(kTile * kTile, TEXTURED ? 4 : 6) raster_shade_kernel(RasterArgs A, FrameParams fp)
+#ifndef B2R_RASTER_LIGHT_CTAS
+#define B2R_RASTER_LIGHT_CTAS 6
+#endif
+#ifndef B2R_RASTER_FULL_CTAS
+#define B2R_RASTER_FULL_CTAS 4
+#endif
+__global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS : B2R_RASTER_LIGHT_CTAS) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
 	pdlPrologue();
 	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
