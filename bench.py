@@ -24,9 +24,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line: this image exports NCCL_DEBUG=VERSION, which makes NCCL print its version
+# banner to stdout (so does WARN); drop those levels, and send an explicitly requested INFO/TRACE log to stderr
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 from custom_gpgpu_rasterizer_b200 import scenes  # noqa: E402  (numpy only)
 
@@ -50,6 +52,96 @@ def make_scene(workload: str):
     if workload == "fill64":
         return scenes.fill_quads_scene(WIDTH, HEIGHT, layers=64, sample=1)  # BASELINE config 4
     raise SystemExit(f"unknown workload {workload}")
+
+
+# ------------------------------------------------------------------------------------ BASELINE config 5 (optional workload)
+def make_views_scene():
+    """172 instances of the reference's bundled vehicle mesh (the REFERENCE parser's output, committed as a golden
+    vector in tests/golden/objparser_reference.npz; textures are synthetic 1024^2 maps) on a 14x13 lattice, and the
+    1024 cameras of SURVEY section 8d: Camera(pos, 45), Pitch(-19.654), Yaw(360 i / 1024), pos = 743.3 * forward."""
+    from custom_gpgpu_rasterizer_b200.renderer import host_camera
+    from custom_gpgpu_rasterizer_b200.scenefile import MeshData, Scene
+    g = np.load(os.path.join(ROOT, "tests", "golden", "objparser_reference.npz"))
+    v, i = g["res_vehicle_v"], g["res_vehicle_i"]
+    tex = [scenes.checker_texture(1024, 1), scenes.normal_texture(1024, 2), scenes.noise_texture(1024, 3), scenes.noise_texture(1024, 4)]
+    meshes = [MeshData(v, i, ((k % 14 - 6.5) * 45.0, 0.0, (k // 14 - 6.0) * 45.0), (0, 1, 2, 3)) for k in range(172)]
+    sc = Scene(1920, 1080, meshes=meshes, textures=tex, cull=0, sample=0, vis=0, fov_deg=45.0, near=1.0, far=2000.0, name="vehicles172_views1024")
+    cams = []
+    for k in range(1024):
+        pitch, yaw = -19.654, 360.0 * k / 1024
+        fwd = host_camera((0.0, 0.0, 0.0), 45.0, sc.width, sc.height, 1.0, 2000.0, pitch, yaw)["cam_fwd"]
+        pos = tuple(float(np.float32(743.3) * f) for f in fwd)
+        cams.append(host_camera(pos, 45.0, sc.width, sc.height, 1.0, 2000.0, pitch, yaw))
+    return sc, cams
+
+
+def run_views(args):
+    """View-parallel batch: view i is rendered by rank i mod N, no communication; K views per rank are timed."""
+    import torch
+    import torch.distributed as dist
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sc, cams = make_views_scene()
+    r = Renderer(sc.width, sc.height, device=local)
+    r.load_scene(sc)
+    stream = torch.cuda.Stream(device=dev)
+    r.set_stream(stream.cuda_stream)
+    mine = [cams[(rank + k * world) % len(cams)] for k in range(max(args.warmup, 3) + args.steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for cam in mine[: max(args.warmup, 3)]:
+        r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+    r.sync()
+    timed = mine[max(args.warmup, 3):]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for cam in timed:
+                r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+            e1.record(stream)
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    launches = r.counters()["kernels_launched"]
+    pinned = [torch.empty((sc.height, sc.width), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    host_fb = [p.numpy().view(np.uint32) for p in pinned]
+    barrier()
+    t0 = time.perf_counter()
+    for k, cam in enumerate(timed):
+        r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+        r.present_async(host_fb[k & 1])
+    r.present_wait()
+    barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    total, visible = r.stats()
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    t = float(ms.item()) / 1e3
+    print(json.dumps({
+        "metric": "views/s (BASELINE config 5, device-timed)", "value": world * args.steps / t, "unit": "views/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 5: 172 instances of the bundled vehicle mesh (2 001 736 triangles, one vertex buffer + 172 world matrices), "
+                               "1920x1080, 1024 cameras on a ring, PBR shading with four 1024^2 maps, view-parallel (view i -> rank i mod N, no communication)",
+                   "triangles": total, "visible_triangles_last_view": visible, "resolution": "1920x1080", "parallelism": f"view-parallel, {world} rank(s)"},
+        "mtris_per_s": total * world * args.steps / t / 1e6,
+        "e2e": {"value": world * args.steps / float(e2e.item()), "unit": "views/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": sc.width * sc.height * 4},
+        "gpu_launches": launches * args.steps, "clocks": clocks.summary()}), flush=True)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -432,13 +524,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small"])
+    ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small", "views172"])
     ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.workload == "views172":
+        if args.impl == "reference":
+            raise SystemExit("the reference arm is defined on the default workload")
+        return run_views(args)
     scene = make_scene(args.workload)
     if args.impl == "reference":
         run_reference(args, scene)
