@@ -336,11 +336,13 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	// The reference's inflated 16-bit bbox (CUDAROPs.cu:180-200) decides the BINS, while the raster kernel
 	// only needs a superset of the pixels whose three edge functions can be >= 0.  A covered pixel has
 	// non-negative barycentrics, so it lies inside the float bounds of the triangle up to the rounding
-	// error of the edge functions: a pixel eps outside the bounds carries a negative weight of at least
-	// area*eps/extent, against an evaluation error below 2^-21 * D^2 (D = pixel-to-vertex distances).
-	// eps below keeps a 8x safety factor on that error plus the rounding of the coordinates themselves;
-	// thin or degenerate triangles (area -> 0) widen to the whole screen, i.e. to the reference's
-	// "every pixel of the bin" (CUDARenderer.cu:1116-1127).
+	// error of the edge functions: a pixel delta outside the bounds has a true edge value of at most
+	// -area*delta/(2*extent), against an fp32 evaluation error below 2^-20 * (delta + ext) * ext.  For
+	// area > 2^-17 * D^2 (D = extents + 2) that limits delta to 2^-18 * D^2 * extent / area, which is the eps
+	// below (plus the rounding of the coordinates themselves).  Needle and degenerate triangles (smaller area:
+	// every pixel near the supporting LINE can evaluate to three non-negative edge functions, at any distance)
+	// and non-finite ones get the whole screen, i.e. the reference's "every pixel of the bin"
+	// (CUDARenderer.cu:1116-1127).
 	const float extx = b.maxx - b.minx, exty = b.maxy - b.miny;
 	const float D = extx + exty + 2.f;
 	const float maxAbs = fmaxf(fmaxf(fabsf(b.minx), fabsf(b.maxx)), fmaxf(fabsf(b.miny), fabsf(b.maxy)));
@@ -351,7 +353,8 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	const float epsx = 0.015625f + maxAbs * 1.52587890625e-5f + k * extx;
 	const float epsy = 0.015625f + maxAbs * 1.52587890625e-5f + k * exty;
 	int cx0 = 0, cx1 = (int)fp.width, cy0 = 0, cy1 = (int)fp.height;
-	if (epsx < 1.0e6f && epsy < 1.0e6f && maxAbs < 1.0e9f)      // false for NaN / inf
+	const bool wellConditioned = epsx < 1.0e6f && epsy < 1.0e6f && maxAbs < 1.0e9f && r.area > 7.62939453125e-6f * D * D;   // false for NaN / inf
+	if (wellConditioned)
 	{
 		cx0 = clampi(__float2int_ru(b.minx - epsx), 0, (int)fp.width);
 		cx1 = clampi(__float2int_rd(b.maxx + epsx) + 1, 0, (int)fp.width);
@@ -362,10 +365,13 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
 	// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn) ...
 	r.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
-	// ... and a conservative lower bound of the integer depth: weights are in [0, 1 + few ulp] and
-	// sum to 1 +- few ulp, so z >= min(z_i) - small; anything non-finite or negative means "no bound"
-	const float zb = fminf(fminf(r.z0, r.z1), r.z2) * 0.999999f - 1e-9f;
-	r.zLow = (zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
+	// ... and a conservative lower bound of the integer depth.  The computed weights of a produced fragment are
+	// >= 0 and, for a well-conditioned triangle, sum to 1 within k (= 2^-18 D^2 / area < 1/2, the relative error
+	// of the edge functions and of the area), so z >= min(z_i) * (1 - k) for min(z_i) > 0.  A needle / degenerate
+	// triangle has arbitrary (even NaN: 0/0) weights, so its fragments can have any depth - including the
+	// integer 0 that cvt.rzi makes of NaN - and gets no bound; so does anything non-finite or negative.
+	const float zb = fminf(fminf(r.z0, r.z1), r.z2) * (1.f - k) * 0.999999f - 1e-9f;
+	r.zLow = (wellConditioned && zb > 0.f && zb < 1.f) ? __float2int_rz(zb * 2147483648.f) : 0;
 	r.pad = 0;
 }
 

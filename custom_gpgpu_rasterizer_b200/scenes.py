@@ -178,6 +178,36 @@ def random_triangles_scene(width: int, height: int, n_tris: int, seed: int, cull
                  name=f"soup_{n_tris}_{seed}_{width}x{height}")
 
 
+def hostile_scene(width: int = 640, height: int = 480, n_tris: int = 600, seed: int = 21, textured: bool = False) -> Scene:
+    """Inputs the reference handles without clipping or validation: triangles that cross the camera plane
+    (w <= 0 on some vertices, NDC flying off to +-inf), vertices exactly on it, huge and tiny coordinates,
+    NaN / inf positions, normals and uvs, fully degenerate triangles.  Every stage has to treat them like
+    the reference does (saturating / NaN->0 float->int conversions, comparisons that are false for NaN)."""
+    rng = np.random.default_rng(seed)
+    nt = n_tris
+    centre = np.stack([rng.uniform(-5, 5, nt), rng.uniform(-3, 3, nt), rng.uniform(-8.0, 9.0, nt)], -1)   # camera at z = 5
+    tri = centre[:, None, :] + rng.normal(0.0, 2.0, (nt, 3, 3))
+    k = nt // 12
+    tri[0 * k:1 * k, :, 2] = 6.0                                   # w_clip = -z_view + 1 = 0 exactly (Camera.cpp:103-107)
+    tri[1 * k:2 * k] *= 1.0e6                                      # huge
+    tri[2 * k:3 * k] = centre[2 * k:3 * k, None, :] + rng.normal(0, 1e-6, (k, 3, 3))   # sub-ulp-ish slivers
+    tri[3 * k:4 * k, 1] = tri[3 * k:4 * k, 0]                      # two equal vertices
+    tri[4 * k:5 * k, 2] = tri[4 * k:5 * k, 0]; tri[4 * k:5 * k, 1] = tri[4 * k:5 * k, 0]   # a point
+    tri[5 * k:5 * k + 8, 0, 0] = np.nan
+    tri[5 * k + 8:5 * k + 16, 1, 1] = np.inf
+    tri[5 * k + 16:5 * k + 24, 2, 2] = -np.inf
+    pos = tri.reshape(-1, 3)
+    nrm = rng.normal(0, 1, (nt * 3, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    tan = rng.normal(0, 1, (nt * 3, 3))
+    nrm[::97] = np.nan; tan[::89] = 0.0
+    uv = rng.uniform(-0.3, 1.3, (nt * 3, 2)); uv[::101] = np.nan; uv[::103] = 1.0e9
+    col = rng.uniform(0.0, 1.5, (nt * 3, 3)); col[::107] = -1.0; col[::109] = np.nan
+    verts = make_vertices(pos, uv=uv, n=nrm, tan=tan, col=col)
+    textures = [checker_texture(256, seed), normal_texture(256, seed + 1), noise_texture(256, seed + 2), noise_texture(256, seed + 3)] if textured else []
+    mesh = MeshData(verts, np.arange(nt * 3, dtype=np.uint32), tex_ids=(0, 1, 2, 3) if textured else (-1, -1, -1, -1))
+    return Scene(width, height, [mesh], textures, cull=2, cam_pos=(0.0, 0.0, 5.0), name=f"hostile_{n_tris}_{seed}_{width}x{height}")
+
+
 def shared_edge_scene(width: int = 256, height: int = 256) -> Scene:
     """A tessellated quad whose interior edges pass exactly through pixel positions (tests the fill rule)."""
     n = 8

@@ -487,21 +487,30 @@ void RasterMesh(OrcFrame& F, int meshIdx, int fillRule)
 		T.area = fabsf(d_Cross2(V2{ T.x0 - T.x1, T.y0 - T.y1 }, V2{ T.x0 - T.x2, T.y0 - T.y2 }));
 		T.iw0 = 1.f / T.v0->p[3]; T.iw1 = 1.f / T.v1->p[3]; T.iw2 = 1.f / T.v2->p[3];
 
-		// every pixel of every overlapped bin is tested in the reference (no bbox intersection,
-		// CUDARenderer.cu:1116-1127); coverage is decided by the edge test alone, so the
-		// scan is narrowed to a conservative float bound when the coordinates are sane.
+		// Every pixel of every overlapped bin is tested in the reference (no bbox intersection,
+		// CUDARenderer.cu:1116-1127) and coverage is decided by the edge test alone.  The scan below is the same
+		// full-bin scan, narrowed ONLY for well-conditioned triangles: a pixel delta outside the float bounds has
+		// a true edge value <= -area*delta/(2*extent) while the fp32 evaluation error is below 2^-20*(delta+ext)*ext,
+		// so with area > 2^-10*D^2 (D = extents + 2) nothing farther than 1 + ext/256 pixels outside the bounds can
+		// pass.  Degenerate and needle triangles (zero or tiny area: every pixel on the supporting line has all
+		// three edge functions == 0 or rounding-sized) get the full scan, like in the reference.
 		int X0 = bx0 * (int)F.h.binW, X1 = bx1 * (int)F.h.binW + covX;
 		int Y0 = by0 * (int)F.h.binH, Y1 = by1 * (int)F.h.binH + covY;
 		X1 = std::min(X1, (int)F.h.width); Y1 = std::min(Y1, (int)F.h.height);
 		const float mnx = Min3(T.x0, T.x1, T.x2), mxx = Max3(T.x0, T.x1, T.x2);
 		const float mny = Min3(T.y0, T.y1, T.y2), mxy = Max3(T.y0, T.y1, T.y2);
-		if (std::isfinite(mnx) && std::isfinite(mxx) && std::isfinite(mny) && std::isfinite(mxy))
+		if (std::isfinite(mnx) && std::isfinite(mxx) && std::isfinite(mny) && std::isfinite(mxy) && std::isfinite(T.area) &&
+			std::fabs(mnx) < 1.0e7f && std::fabs(mxx) < 1.0e7f && std::fabs(mny) < 1.0e7f && std::fabs(mxy) < 1.0e7f)
 		{
-			const double lo = -1.0e9, hi = 1.0e9;
-			X0 = std::max(X0, (int)std::floor(std::min(std::max((double)mnx, lo), hi)) - 1);
-			X1 = std::min(X1, (int)std::floor(std::min(std::max((double)mxx, lo), hi)) + 2);
-			Y0 = std::max(Y0, (int)std::floor(std::min(std::max((double)mny, lo), hi)) - 1);
-			Y1 = std::min(Y1, (int)std::floor(std::min(std::max((double)mxy, lo), hi)) + 2);
+			const double ext = std::max((double)mxx - mnx, (double)mxy - mny), D = ((double)mxx - mnx) + ((double)mxy - mny) + 2.0;
+			if ((double)T.area > D * D / 1024.0)
+			{
+				const int margin = 1 + (int)std::ceil(ext / 256.0);
+				X0 = std::max(X0, (int)std::floor((double)mnx) - margin);
+				X1 = std::min(X1, (int)std::floor((double)mxx) + 1 + margin);
+				Y0 = std::max(Y0, (int)std::floor((double)mny) - margin);
+				Y1 = std::min(Y1, (int)std::floor((double)mxy) + 1 + margin);
+			}
 		}
 		for (int y = Y0; y < Y1; ++y)
 		{

@@ -51,7 +51,10 @@ def assert_colour_parity(a, b, allowed_mask=None, what=""):
 
 def assert_depth_parity(z_a, z_b, covered, what=""):
     za, zb = z_a[covered].astype(np.float64), z_b[covered].astype(np.float64)
-    rel = np.abs(za - zb) / np.maximum(np.abs(zb), 1e-30)
+    with np.errstate(invalid="ignore", over="ignore"):
+        rel = np.abs(za - zb) / np.maximum(np.abs(zb), 1e-30)
+    # non-finite depths (degenerate triangles: 0/0 weights) must agree in kind; equal infinities are equal
+    rel = np.where(np.isnan(za) & np.isnan(zb), 0.0, np.where(za == zb, 0.0, np.where(np.isnan(rel), np.inf, rel)))
     assert rel.size == 0 or rel.max() <= DEPTH_RTOL, f"{what}: depth differs by {rel.max():.3e} relative (limit {DEPTH_RTOL})"
     return float(rel.max()) if rel.size else 0.0
 

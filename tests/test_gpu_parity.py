@@ -82,6 +82,8 @@ SCENES = {
     "fill_quads_linear": lambda: scenes.fill_quads_scene(640, 368, layers=8, tex_size=256, sample=1),
     "fill_quads_point": lambda: scenes.fill_quads_scene(640, 368, layers=8, tex_size=256, sample=0),
     "shared_edges": lambda: scenes.shared_edge_scene(),
+    "hostile_inputs": lambda: scenes.hostile_scene(640, 480, 600, seed=21),
+    "hostile_inputs_textured": lambda: scenes.hostile_scene(640, 480, 360, seed=22, textured=True),
     "slivers": lambda: scenes.sliver_scene(640, 480, 1500, seed=3),
     "slivers_4k": lambda: scenes.sliver_scene(3840, 2160, 600, seed=4),
 }
