@@ -107,6 +107,19 @@ def test_product_matches_oracle(name, fill_rule):
     _compare(SCENES[name](), fill_rule)
 
 
+@pytest.mark.parametrize("seed", [31, 32, 33, 34, 35, 36])
+def test_hostile_fuzz(seed):
+    """More seeds of the hostile-input soup at ragged resolutions, other cull modes and large bins."""
+    res = [(640, 480), (333, 217), (800, 450), (1280, 720), (256, 256), (517, 389)][seed - 31]
+    sc = scenes.hostile_scene(res[0], res[1], 500, seed=seed, textured=(seed % 2 == 0))
+    sc.cull = seed % 3
+    if seed % 2:
+        sc.bin_w = sc.bin_h = 80
+        sc.bins_x, sc.bins_y = (sc.width + 79) // 80, (sc.height + 79) // 80
+    for fill_rule in (1, 0):
+        _compare(sc, fill_rule)
+
+
 def test_empty_scene_is_clear_colour():
     from custom_gpgpu_rasterizer_b200.scenefile import Scene
     sc = Scene(320, 200)
