@@ -22,6 +22,7 @@ test_scenes = [scenes.random_triangles_scene(1000, 600, 500, seed=41, cull=2, te
                scenes.sphere_grid_scene(1920, 1080, nx=8, ny=5, stacks=41, slices=60, cam_z=20.0)]
 if mode == "sharded":
     test_scenes.append(scenes.fill_quads_scene(1280, 720, layers=6))     # big rectangles: cooperative binner
+    test_scenes.append(scenes.hostile_scene(640, 480, 600, seed=21))     # degenerate / non-finite triangles
 for sc in test_scenes:
     r = Renderer(sc.width, sc.height, device=local)
     r.load_scene(sc)
