@@ -211,6 +211,31 @@ def cpu_reference_arm(scene, steps: int, warmup: int):
     return float(np.mean(times)), times
 
 
+def reference_cuda_arm(scene, frames: int, timeout_s: int):
+    """The reference's own CUDA renderer (oracle/_ref/ref_render = the unmodified reference sources compiled for sm_100a, headless),
+    timed on GPU 0 of this box on the same scene: wall clock of its RenderAuto, which synchronises the device inside every frame.
+    A reported baseline next to the CPU one; returns None when the binary is absent or the run fails / exceeds its time-out."""
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_render not built"}
+    with tempfile.TemporaryDirectory() as td:
+        sp = os.path.join(td, "scene.b2rs")
+        with open(sp, "wb") as f:
+            f.write(scene.to_blob())
+        try:
+            res = subprocess.run([exe, "time", sp, str(frames)], capture_output=True, text=True, timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": f"ref_render did not finish 1 + {frames} frames within {timeout_s} s"}
+    if res.returncode != 0:
+        return {"unavailable": f"ref_render exit code {res.returncode}: {res.stderr.strip()[-200:]}"}
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    return {"value": 1e3 / out["ms_per_frame"], "unit": "frames/s", "ms_per_frame": out["ms_per_frame"], "frames": out["frames"],
+            "visible_triangles": out["visible_triangles"], "kind": "reference",
+            "sample": f"the full frame of this workload, {out['frames']} frame(s) after 1 warm-up, through the reference's CUDARenderer::RenderAuto "
+                      "(unmodified sources built by oracle/build_ref.sh), wall clock; 256-triangle batches with a device synchronisation after every launch"}
+
+
 def run_reference(args, scene):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -230,6 +255,8 @@ def run_reference(args, scene):
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.ref_cuda:
+        line["reference_cuda_path"] = reference_cuda_arm(scene, args.ref_cuda, args.ref_cuda_timeout)
     print(json.dumps(line), flush=True)
 
 
@@ -528,6 +555,8 @@ def main():
     ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
+    ap.add_argument("--ref-cuda", type=int, default=0, metavar="FRAMES", help="--impl reference only: also time the reference's own CUDA renderer (oracle/_ref/ref_render) on GPU 0 for this many frames")
+    ap.add_argument("--ref-cuda-timeout", type=int, default=240)
     args = ap.parse_args()
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
         return

@@ -29,6 +29,7 @@ TOPOLOGY_TRIANGLE_LIST, TOPOLOGY_TRIANGLE_STRIP = 0, 1
 OPT_FILL_RULE_TOP_LEFT, OPT_TILE_OWNER_RANK, OPT_TILE_OWNER_COUNT = 1, 2, 3
 OPT_DEBUG_SURFACES, OPT_STAGE_TIMERS, OPT_SORT_BINS, OPT_COUNT_FRAGMENTS, OPT_PACKED_OUTPUT = 4, 5, 6, 7, 8
 OPT_OVERLAP_VERTEX = 10
+OPT_OVERLAP_FRONT = 11
 STAGE_NAMES = ("vertex", "setup", "bin_scan", "bin_scatter", "bin_sort", "raster_shade", "total", "exchange", "peer_wait")
 NUM_STAGES = 9
 

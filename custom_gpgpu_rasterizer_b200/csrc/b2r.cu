@@ -107,7 +107,6 @@ struct b2r_context
 	int overlapVertex = 1, usePdl = 1;
 	DeviceVec<float> dOvertexScratch;
 	DeviceVec<uint4> dTriRefs;         // static {v0, v1, v2, mesh} per primitive, rebuilt when the mesh list changes
-	DeviceVec<uint2> dRects;
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
 	DeviceVec<MeshConst> dMeshConst[2];
@@ -116,10 +115,20 @@ struct b2r_context
 	DeviceVec<TexDesc> dTexDesc;
 
 	// binning
-	DeviceVec<uint32_t> dTileCount, dTileOffset, dTileCursor, dLongTiles, dMidTiles, dBigList, dBinIds;
-	uint32_t* dCounters = nullptr;                 // [0] visible, [1] nBig
-	unsigned long long* dFrameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
-	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };   // device layout: dFrameInfo, then dCounters
+	// Everything the geometry front end (setup -> bin -> sort) writes for one frame.  Two sets: with
+	// B2R_OPT_OVERLAP_FRONT the front end of frame f+1 runs on the second stream while frame f is still being
+	// rasterised from the other set (set = frame parity, like pos4 / the per-mesh constants); otherwise only set 0
+	// is ever allocated.
+	struct BinSet
+	{
+		DeviceVec<uint2> rects;
+		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, midTiles, bigList, binIds;
+		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
+		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
+	} bins[2];
+	int overlapFront = 0;              // B2R_OPT_OVERLAP_FRONT
+	bool lastPipelined = false;        // the newest enqueued frame ran its front end on the second stream
+	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };   // device layout: frameInfo, then counters
 
 	// frames in flight: each enqueued frame owns one slot of pinned host memory + events, so the
 	// host can run ahead of the device by kRing frames without a synchronisation
@@ -177,6 +186,7 @@ struct b2r_context
 	} shard;
 	// bin buffers of the newest frame (the DeviceVecs, or one set of the shard arena)
 	uint32_t* curTileCount = nullptr; uint32_t* curTileOffset = nullptr; uint32_t* curBinIds = nullptr;
+	const uint2* curRects = nullptr;
 
 	// frame state
 	RenderCall last;
@@ -219,6 +229,31 @@ int ensureDebugSurfaces(b2r_context* c)
 	return B2R_OK;
 }
 
+// (Re)size one set of front-end buffers for the current bin grid and scene.  Grow-only and a no-op when nothing
+// changed, so enqueueFrame calls it for the set a frame is about to use (the second set exists only once a
+// pipelined frame has been enqueued).  Growing frees the old allocation, which synchronises the device.
+int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
+{
+	const size_t n = nBins(c);
+	if (!B.frameInfo)
+	{
+		CU(c, cudaMalloc((void**)&B.frameInfo, kInfoWords * 8 + kCounterWords * 4));
+		CU(c, cudaMemset(B.frameInfo, 0, kInfoWords * 8 + kCounterWords * 4));
+		B.counters = reinterpret_cast<uint32_t*>(B.frameInfo + kInfoWords);
+	}
+	// tile_scan_kernel reads the counts with 16-byte loads; tileOffset[n] = overflow marker for peer ranks
+	CU(c, B.tileCount.reserve(n + 4, c->stream));
+	CU(c, B.tileOffset.reserve(n + 4, c->stream));
+	CU(c, B.tileCursor.reserve(n, c->stream));
+	CU(c, B.longTiles.reserve(n, c->stream));
+	CU(c, B.midTiles.reserve(n, c->stream));
+	CU(c, B.rects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	CU(c, B.bigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
+	// list capacity heuristic; regrown on overflow (see validateFrame), and kept equal across the sets
+	CU(c, B.binIds.reserve(std::max<size_t>(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), std::max(c->bins[0].binIds.cap, c->bins[1].binIds.cap)), c->stream));
+	return B2R_OK;
+}
+
 int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 {
 	if (!bx || !by || !bw || !bh) return fail(c, B2R_E_INVALID, "bin grid and bin size must be non-zero");
@@ -226,16 +261,7 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 		return fail(c, B2R_E_INVALID, "bins (%ux%u of %ux%u) must cover the %ux%u screen", bx, by, bw, bh, c->width, c->height);
 	if (bx > 32767 || by > 32767) return fail(c, B2R_E_INVALID, "too many bins");
 	c->binsX = bx; c->binsY = by; c->binW = bw; c->binH = bh;
-	const uint32_t n = bx * by;
-	CU(c, c->dTileCount.reserve(n, c->stream));
-	CU(c, c->dTileOffset.reserve(n, c->stream));
-	CU(c, c->dTileCursor.reserve(n, c->stream));
-	CU(c, c->dLongTiles.reserve(n, c->stream));
-	CU(c, c->dMidTiles.reserve(n, c->stream));
-	// tile_scan_kernel reads the counts with 16-byte loads
-	CU(c, c->dTileCount.reserve((size_t)n + 4, c->stream));
-	CU(c, c->dTileOffset.reserve((size_t)n + 4, c->stream));    // [n] = overflow marker for peer ranks
-	return B2R_OK;
+	return reserveBinSet(c, c->bins[0]);
 }
 
 bool texValid(const b2r_context* c, int id) { return id >= 0 && (size_t)id < c->textures.size() && c->textures[id].alive; }
@@ -265,12 +291,9 @@ int rebuildScene(b2r_context* c)
 		CU(c, cudaGetLastError());
 	}
 	for (auto& v : c->dPos4) CU(c, v.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
-	CU(c, c->dTriRefs.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
-	CU(c, c->dRects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
-	CU(c, c->dBigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	for (auto& v : c->dMeshConst) CU(c, v.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
-	// list capacity heuristic; regrown on overflow (see validateFrame)
-	CU(c, c->dBinIds.reserve(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), c->stream));
+	for (auto& B : c->bins)
+		if (B.frameInfo) { int r = reserveBinSet(c, B); if (r) return r; }
 	c->sceneDirty = false;
 	return B2R_OK;
 }
@@ -374,14 +397,29 @@ int enqueueFrame(b2r_context* c)
 	const uint32_t tiles = nBins(c);
 	c->kernelsLaunched = 0;
 
+	// Pipelined front end (B2R_OPT_OVERLAP_FRONT): the whole geometry front end of this frame (constants, vertex,
+	// setup, binning, sort) goes to the second stream and works on the bin set of the frame's parity, so it
+	// overlaps the raster kernel of the previous frame, which reads the other set.  Not while the stages are being
+	// timed and not with the sharded front end (its sets live in the peer-visible arena).
+	const bool pipelined = c->overlapFront && c->overlapVertex && !c->stageTimers && c->nVsChunks && !c->shard.bound;
+	if (pipelined != c->lastPipelined)
+	{
+		// frames of the other kind used set 0 / the main stream regardless of parity: order this frame's front end
+		// behind everything enqueued so far
+		c->vtxNeedsFork = true;
+		c->lastPipelined = pipelined;
+	}
+	b2r_context::BinSet& B = c->bins[pipelined ? (int)(c->seq & 1u) : 0];
+	{ int r = reserveBinSet(c, B); if (r) return r; }
+
 	// bin buffers and primitive slice of this frame
 	const b2r_context::Shard& sh = c->shard;
 	const int set = (int)(sh.frame & 1u);
-	uint32_t* tileCount = sh.bound ? sh.tileCount(sh.arena, set) : c->dTileCount.ptr;
-	uint32_t* tileOffset = sh.bound ? sh.tileOffset(sh.arena, set) : c->dTileOffset.ptr;
-	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, set) : c->dBinIds.ptr;
-	const size_t listCap = sh.bound ? sh.listCap : c->dBinIds.cap;
-	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds;
+	uint32_t* tileCount = sh.bound ? sh.tileCount(sh.arena, set) : B.tileCount.ptr;
+	uint32_t* tileOffset = sh.bound ? sh.tileOffset(sh.arena, set) : B.tileOffset.ptr;
+	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, set) : B.binIds.ptr;
+	const size_t listCap = sh.bound ? sh.listCap : B.binIds.cap;
+	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds; c->curRects = B.rects.ptr;
 	uint32_t primLo = 0, primHi = (uint32_t)c->nPrims;
 	if (sh.bound)
 	{
@@ -457,21 +495,26 @@ int enqueueFrame(b2r_context* c)
 			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
 		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, v, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
 		c->kernelsLaunched += 2;
-		CU(c, cudaEventRecord(c->vtxDone[g], v));
-		CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
+		if (!pipelined)
+		{
+			CU(c, cudaEventRecord(c->vtxDone[g], v));
+			CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
+		}
 	}
+	// stream of the front end: the second stream when pipelined (joined into the main stream before the raster)
+	cudaStream_t fs = pipelined ? c->vtxStream : s;
 	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
 	// queue behind the previous frame's 33 MB Present copy
 	const uint32_t clearMeshes = overlap ? 0u : nMeshes;
 	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (clearMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
-	CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(clearCtas), dim3(256), 0, s, tileCount, tiles, c->dCounters, c->dFrameInfo, (uint32_t)kInfoWords,
+	CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(clearCtas), dim3(256), 0, fs, tileCount, tiles, B.counters, B.frameInfo, (uint32_t)kInfoWords,
 		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
 		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes));
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks && !overlap)
 	{
-		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, s, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
+		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, fs, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 1);
@@ -479,17 +522,17 @@ int enqueueFrame(b2r_context* c)
 	{
 		if (primHi > primLo)
 		{
-			CU(c, launchFrameKernel(c, triangle_setup_kernel, dim3((primHi - primLo + kChunk - 1) / kChunk), dim3(kChunk), 0, s, c->dTriRefs.ptr, pos4,
-				c->dRects.ptr, tileCount, c->dBigList.ptr, c->dCounters, primLo, primHi, fp));
+			CU(c, launchFrameKernel(c, triangle_setup_kernel, dim3((primHi - primLo + kChunk - 1) / kChunk), dim3(kChunk), 0, fs, c->dTriRefs.ptr, pos4,
+				B.rects.ptr, tileCount, B.bigList.ptr, B.counters, primLo, primHi, fp));
 			++c->kernelsLaunched;
 		}
-		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, s, c->dBigList.ptr, c->dCounters, c->dRects.ptr, tileCount, fp));
+		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, fs, B.bigList.ptr, B.counters, B.rects.ptr, tileCount, fp));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 2);
-	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, s, tileCount, tileOffset, c->dTileCursor.ptr, tiles,
+	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, fs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
 		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
-		c->dMidTiles.ptr, c->dLongTiles.ptr, c->dCounters, c->dFrameInfo));
+		B.midTiles.ptr, B.longTiles.ptr, B.counters, B.frameInfo));
 	++c->kernelsLaunched;
 	if (sh.bound)
 	{
@@ -500,7 +543,7 @@ int enqueueFrame(b2r_context* c)
 			uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
 			inbox.tileCount[p] = sh.inboxCount(base, set, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, set, sh.self);
 		}
-		CU(c, launchFrameKernel(c, shard_push_heads_kernel, dim3((tiles + 255) / 256), dim3(256), 0, s, tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n));
+		CU(c, launchFrameKernel(c, shard_push_heads_kernel, dim3((tiles + 255) / 256), dim3(256), 0, fs, tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 3);
@@ -509,18 +552,18 @@ int enqueueFrame(b2r_context* c)
 		{
 			// per-primitive CTAs, followed by the CTAs that scatter the cooperatively binned (big) triangles
 			const uint32_t primBlocks = (primHi - primLo + 255) / 256;
-			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, s, c->dRects.ptr, primLo, primHi, tileOffset,
-				c->dTileCursor.ptr, binIds, c->dBigList.ptr, c->dCounters, primBlocks, c->dFrameInfo, fp));
+			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, fs, B.rects.ptr, primLo, primHi, tileOffset,
+				B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp));
 			++c->kernelsLaunched;
 		}
 	}
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, tileCount, tileOffset, binIds, tiles, c->dMidTiles.ptr, c->dFrameInfo));
-		CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, s, c->dMidTiles.ptr, tileCount, tileOffset, binIds, c->dFrameInfo));
-		CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, s, c->dLongTiles.ptr, tileCount, tileOffset,
-			binIds, c->dFrameInfo));
+		CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, fs, tileCount, tileOffset, binIds, tiles, B.midTiles.ptr, B.frameInfo));
+		CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, fs, B.midTiles.ptr, tileCount, tileOffset, binIds, B.frameInfo));
+		CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, fs, B.longTiles.ptr, tileCount, tileOffset,
+			binIds, B.frameInfo));
 		c->kernelsLaunched += 3;
 	}
 	if (sh.bound && c->nPrims)
@@ -528,15 +571,21 @@ int enqueueFrame(b2r_context* c)
 		// mirror the sorted lists into their owners' memory (posted stores; landed by the time of the barrier)
 		ShardRegions R{};
 		for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], set, sh.self);
-		CU(c, launchFrameKernel(c, shard_push_lists_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, c->dFrameInfo));
+		CU(c, launchFrameKernel(c, shard_push_lists_kernel, dim3((tiles + 7) / 8), dim3(256), 0, fs, tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, B.frameInfo));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 5);
+	if (pipelined)
+	{
+		// join: the raster of this frame (main stream) starts when its lists are sorted
+		CU(c, cudaEventRecord(c->vtxDone[g], fs));
+		CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
+	}
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
-		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = c->dFrameInfo;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -561,7 +610,7 @@ int enqueueFrame(b2r_context* c)
 			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
 			// "lists ready": nobody reads a peer's lists before that peer has sorted them.  (Rank 0 arrives only
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
-			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, c->dFrameInfo + 7));
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7));
 			++c->kernelsLaunched;
 			STAGE_EVENT(c, slot, 8);
 			A.shard = T;
@@ -588,8 +637,13 @@ int enqueueFrame(b2r_context* c)
 			++c->kernelsLaunched;
 		}
 		// the vertex stage of frame f+2 may overwrite pos4 / constants of this parity once this raster is done
-		CU(c, cudaEventRecord(c->rasterDone[g], s));
-		c->rasterPending[g] = true;
+		// (pipelined: the whole front end of frame f+2 re-uses this bin set, whose counters publish_info_kernel
+		// still reads - the event is recorded after it, below)
+		if (!pipelined)
+		{
+			CU(c, cudaEventRecord(c->rasterDone[g], s));
+			c->rasterPending[g] = true;
+		}
 		if (sh.bound)
 		{
 			STAGE_EVENT(c, slot, 9);
@@ -603,9 +657,14 @@ int enqueueFrame(b2r_context* c)
 		landedFlag = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]) + 8 + sh.self;
 	STAGE_EVENT(c, slot, 6);
 	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
-	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, s, c->dFrameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8),
+	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, s, B.frameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8),
 		landedFlag, c->shard.frame));
 	++c->kernelsLaunched;
+	if (pipelined)
+	{
+		CU(c, cudaEventRecord(c->rasterDone[g], s));
+		c->rasterPending[g] = true;
+	}
 	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
 	slot.pending = true;
@@ -656,7 +715,8 @@ int validateFrame(b2r_context* c)
 		}
 		const size_t need = c->overflowNeed;
 		c->overflowNeed = 0;
-		CU(c, c->dBinIds.reserve(need + need / 4, c->stream));
+		for (auto& B : c->bins)
+			if (B.frameInfo) CU(c, B.binIds.reserve(need + need / 4, c->stream));
 		int r = enqueueFrame(c);
 		if (r) return r;
 	}
@@ -741,14 +801,23 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	if (!c) return fail(nullptr, B2R_E_INVALID, "out of host memory");
 	c->device = device; c->width = width; c->height = height;
 	if (const char* e = getenv("B2R_OVERLAP_VERTEX")) c->overlapVertex = atoi(e) != 0;
-	if (const char* e = getenv("B2R_PDL")) c->usePdl = atoi(e) != 0;                           // debugging aid: programmatic dependent launch      // debugging aid; see B2R_OPT_OVERLAP_VERTEX
+	if (const char* e = getenv("B2R_PDL")) c->usePdl = atoi(e) != 0;                           // debugging aid: programmatic dependent launch
+	if (const char* e = getenv("B2R_OVERLAP_FRONT")) c->overlapFront = atoi(e) != 0;           // see B2R_OPT_OVERLAP_FRONT
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));
 	CUC(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, device));
 	CUC(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	c->stream = c->ownStream;
-	CUC(cudaStreamCreateWithFlags(&c->vtxStream, cudaStreamNonBlocking));
+	{
+		// B2R_FRONT_PRIORITY=1: the second stream (vertex stage / pipelined front end) gets the highest priority, so its
+		// short kernels are dispatched ahead of the remaining CTAs of the long raster grid they overlap with
+		int prLeast = 0, prGreatest = 0;
+		CUC(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+		const char* e = getenv("B2R_FRONT_PRIORITY");
+		const bool high = e ? atoi(e) != 0 : false;
+		CUC(cudaStreamCreateWithPriority(&c->vtxStream, cudaStreamNonBlocking, high ? prGreatest : prLeast));
+	}
 	CUC(cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming));
 	for (int i = 0; i < 2; ++i)
 	{
@@ -763,9 +832,6 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 		CUC(cudaMallocHost((void**)&slot.hViewProj, 64));
 		memset(slot.hInfo, 0, sizeof(b2r_context::HostInfo));
 	}
-	CUC(cudaMalloc((void**)&c->dFrameInfo, kInfoWords * 8 + kCounterWords * 4));
-	CUC(cudaMemset(c->dFrameInfo, 0, kInfoWords * 8 + kCounterWords * 4));
-	c->dCounters = reinterpret_cast<uint32_t*>(c->dFrameInfo + kInfoWords);
 	CUC(cudaFuncSetAttribute(bin_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortLongSmem));
 #undef CUC
 	int r = allocSurfaces(c);
@@ -786,10 +852,14 @@ void b2r_destroy(b2r_context* c)
 	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
-	c->dTriRefs.release(); c->dRects.release(); c->dVsChunks.release(); c->dTriChunks.release();
-	for (auto& v : c->dMeshConst) v.release(); c->dMeshStatic.release(); c->dTexDesc.release(); c->dTileCount.release(); c->dTileOffset.release();
-	c->dTileCursor.release(); c->dLongTiles.release(); c->dMidTiles.release(); c->dBigList.release(); c->dBinIds.release();
-	cudaFree(c->dFrameInfo);
+	c->dTriRefs.release(); c->dVsChunks.release(); c->dTriChunks.release();
+	for (auto& v : c->dMeshConst) v.release(); c->dMeshStatic.release(); c->dTexDesc.release();
+	for (auto& B : c->bins)
+	{
+		B.rects.release(); B.tileCount.release(); B.tileOffset.release(); B.tileCursor.release(); B.longTiles.release();
+		B.midTiles.release(); B.bigList.release(); B.binIds.release();
+		cudaFree(B.frameInfo);
+	}
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
 	releaseShard(c);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
@@ -931,6 +1001,7 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
 	case B2R_OPT_PACKED_OUTPUT: c->packedOutput = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_VERTEX: c->overlapVertex = value ? 1 : 0; break;
+	case B2R_OPT_OVERLAP_FRONT: c->overlapFront = value ? 1 : 0; break;
 	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
 	}
 	if (c->ownerRank >= c->ownerCount) { /* tolerated while the pair is being set; checked at render */ }
@@ -1042,7 +1113,7 @@ int b2r_read_visible(b2r_context* c, int id, uint8_t* out)
 	int r = validateFrame(c); if (r) return r;
 	const HostMesh& hm = c->meshes[id];
 	std::vector<uint2> rc(hm.nTris);
-	if (hm.nTris) CU(c, cudaMemcpy(rc.data(), c->dRects.ptr + hm.primBase, (size_t)hm.nTris * 8, cudaMemcpyDeviceToHost));
+	if (hm.nTris) CU(c, cudaMemcpy(rc.data(), c->curRects + hm.primBase, (size_t)hm.nTris * 8, cudaMemcpyDeviceToHost));
 	for (uint32_t t = 0; t < hm.nTris; ++t) out[t] = ((rc[t].x & 0xFFFFu) == 0xFFFFu) ? 0 : 1;
 	return B2R_OK;
 }

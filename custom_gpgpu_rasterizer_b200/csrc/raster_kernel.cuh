@@ -198,7 +198,10 @@ __device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& 
 }
 
 constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
-constexpr int kSmallArea = 48;        // bbox-in-tile areas up to this are rasterised by one thread
+#ifndef B2R_SMALL_AREA
+#define B2R_SMALL_AREA 48
+#endif
+constexpr int kSmallArea = B2R_SMALL_AREA;   // bbox-in-tile areas up to this are rasterised by one thread
 
 // TEXTURED = false is the light variant for frames in which no mesh has a diffuse map and the
 // visualisation is PBR (vertex colours only): the texture/normal-mapping path is compiled out, which

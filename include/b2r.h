@@ -70,7 +70,13 @@ enum
 	/* run the vertex stage of a frame on a second stream so that it overlaps binning / raster of the previous
 	 * frame when frames are enqueued back to back (transformed positions and per-mesh constants are
 	 * double-buffered).  Ignored while B2R_OPT_STAGE_TIMERS is on.  Default 1. */
-	B2R_OPT_OVERLAP_VERTEX = 10
+	B2R_OPT_OVERLAP_VERTEX = 10,
+	/* pipeline whole frames: run the complete geometry front end of a frame (constants, vertex, setup, binning,
+	 * sort) on the second stream, so that it overlaps the raster kernel of the PREVIOUS frame when frames are
+	 * enqueued back to back; every buffer the front end writes is double-buffered by frame parity.  Results are
+	 * unchanged.  Needs B2R_OPT_OVERLAP_VERTEX; ignored while B2R_OPT_STAGE_TIMERS is on and with the sharded
+	 * front end (b2r_shard_*). */
+	B2R_OPT_OVERLAP_FRONT = 11
 };
 
 /* stage indices for b2r_get_stage_ms */

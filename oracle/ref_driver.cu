@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -94,8 +95,9 @@ int main(int argc, char** argv)
 	if (argc >= 5 && (std::string(argv[1]) == "parse" || std::string(argv[1]) == "parsev"))
 		return Parse(argv[2], atoi(argv[3]), argv[4], std::string(argv[1]) == "parsev");
 	if (argc < 4)
-		return Fail("usage: ref_render render|stages scene.b2rs out.b2ro | parse file.obj invertY out.bin");
+		return Fail("usage: ref_render render|stages scene.b2rs out.b2ro | time scene.b2rs frames | parse file.obj invertY out.bin");
 	const bool stages = std::string(argv[1]) == "stages";
+	const bool timing = std::string(argv[1]) == "time";
 
 	FILE* fin = fopen(argv[2], "rb");
 	if (!fin) return Fail("cannot open scene");
@@ -171,6 +173,26 @@ int main(int argc, char** argv)
 	std::vector<std::vector<unsigned>> visTriples(h.nMeshes);   // idx0,idx1,idx2 per visible triangle
 	std::vector<std::vector<unsigned>> binPairs(h.nMeshes);     // bin,idx0,idx1,idx2 per queue entry
 
+	if (timing)
+	{
+		// wall clock of the reference's own frame call (RenderAuto = clear + Render + Present, CUDARenderer.cu:357-371),
+		// one warm-up frame, then argv[3] frames; the reference synchronises the device inside every frame
+		const int frames = atoi(argv[3]) > 0 ? atoi(argv[3]) : 1;
+		pRenderer->RenderAuto(sm, tm, &camera);
+		cudaDeviceSynchronize();
+		const auto t0 = std::chrono::steady_clock::now();
+		for (int f = 0; f < frames; ++f) pRenderer->RenderAuto(sm, tm, &camera);
+		const cudaError_t terr = cudaDeviceSynchronize();
+		const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		if (terr != cudaSuccess)
+		{
+			fprintf(stderr, "ref_render: CUDA error while timing: %s\n", cudaGetErrorString(terr));
+			return 3;
+		}
+		printf("{\"frames\": %d, \"ms_per_frame\": %.6f, \"triangles\": %u, \"visible_triangles\": %u}\n", frames, sec * 1e3 / frames,
+			pRenderer->GetTotalNumTriangles(), pRenderer->GetTotalNumVisibleTriangles());
+		return 0;
+	}
 	if (!stages)
 	{
 		pRenderer->RenderAuto(sm, tm, &camera);

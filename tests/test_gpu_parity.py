@@ -249,3 +249,40 @@ def test_pipelined_present_returns_each_frame():
         assert not np.array_equal(want[0], want[1])
         # the synchronous read-back still returns the newest frame
         assert np.array_equal(r.framebuffer(), want[-1])
+
+
+def test_pipelined_front_end_matches_serial_frames():
+    """B2R_OPT_OVERLAP_FRONT: the geometry front end of frame f+1 runs on the second stream, on the other bin set, while
+    frame f is rasterised.  Every frame of a back-to-back sequence with a moving camera (and mode switches in between:
+    stage timers force serial frames) must equal the frame rendered on its own."""
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer, host_camera
+    sc = scenes.sphere_grid_scene(1280, 720, nx=6, ny=4, stacks=61, slices=80, cam_z=14.0)
+    cams = [host_camera((0.15 * k - 1.0, 0.1 * (k % 3), 14.0 - 0.3 * k), sc.fov_deg, sc.width, sc.height, sc.near, sc.far) for k in range(12)]
+    with Renderer(sc.width, sc.height) as r:
+        r.load_scene(sc)
+        r.set_option(_lib.OPT_OVERLAP_FRONT, 0)
+        want, want_ids = [], []
+        for cam in cams:
+            r.render(cam, sc.cull, sc.sample, sc.vis)
+            want.append(r.framebuffer().copy())
+            want_ids.append(r.bin_lists()[2].copy())
+        assert not np.array_equal(want[0], want[1])
+        r.set_option(_lib.OPT_OVERLAP_FRONT, 1)
+        for rounds in range(2):
+            bufs = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+            for k, (cam, b) in enumerate(zip(cams, bufs)):
+                if rounds == 1:
+                    r.set_option(_lib.OPT_STAGE_TIMERS, int(k in (3, 4, 8)))     # serial frames in between
+                r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+                r.present_async(b)
+            r.present_wait()
+            for i, (b, w) in enumerate(zip(bufs, want)):
+                assert np.array_equal(b, w), f"round {rounds}: frame {i} differs"
+            assert np.array_equal(r.bin_lists()[2], want_ids[-1])
+            assert np.array_equal(r.framebuffer(), want[-1])
+        # synchronous frames alternate between the two bin sets; surfaces and lists follow the newest frame
+        r.set_option(_lib.OPT_STAGE_TIMERS, 0)
+        for k in (5, 2, 9):
+            r.render(cams[k], sc.cull, sc.sample, sc.vis)
+            assert np.array_equal(r.framebuffer(), want[k]) and np.array_equal(r.bin_lists()[2], want_ids[k])
