@@ -16,6 +16,7 @@ el "A base";           $B > $O/ab_base.json 2> $O/ab_base.err
 el "A pipe";           B2R_OVERLAP_FRONT=1 $B > $O/ab_pipe.json 2> $O/ab_pipe.err
 el "A pipe prio";      B2R_OVERLAP_FRONT=1 B2R_FRONT_PRIORITY=1 $B > $O/ab_pipe_prio.json 2> $O/ab_pipe_prio.err
 el "A prio";           B2R_FRONT_PRIORITY=1 $B > $O/ab_prio.json 2> $O/ab_prio.err
+el "A pipe prio nopdl"; B2R_OVERLAP_FRONT=1 B2R_FRONT_PRIORITY=1 B2R_PDL=0 $B > $O/ab_pipe_prio_nopdl.json 2> $O/ab_pipe_prio_nopdl.err
 el "reference arm + reference CUDA path"; timeout 420 python bench.py --impl reference --steps 3 --warmup 1 --ref-cuda 2 --ref-cuda-timeout 300 > $O/bench_reference.json 2> $O/bench_reference.err
 el "A small24";        B2R_LIBRARY=$PWD/build/variants/libb2r_small24.so $B > $O/ab_small24.json 2> $O/ab_small24.err
 el "A small96";        B2R_LIBRARY=$PWD/build/variants/libb2r_small96.so $B > $O/ab_small96.json 2> $O/ab_small96.err
