@@ -38,6 +38,14 @@ def test_every_declared_symbol_is_exported():
     assert declared == set(_lib.ABI), f"ctypes table out of sync: {declared ^ set(_lib.ABI)}"
 
 
+def test_option_constants_match_the_header():
+    hdr = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    opts = dict(re.findall(r"^\s*(B2R_OPT_[A-Z_]+) = (\d+),?$", hdr, re.M))
+    assert len(opts) >= 10
+    for name, value in opts.items():
+        assert getattr(_lib, name[len("B2R_"):]) == int(value), name
+
+
 def test_no_cpu_fallback():
     if _has_gpu():
         pytest.skip("this check is for machines without a CUDA device")
