@@ -122,7 +122,7 @@ struct b2r_context
 	struct BinSet
 	{
 		DeviceVec<uint2> rects;
-		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, midTiles, bigList, binIds;
+		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, midTiles, smallTiles, bigList, binIds;
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[2];
@@ -247,6 +247,7 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	CU(c, B.tileCursor.reserve(n, c->stream));
 	CU(c, B.longTiles.reserve(n, c->stream));
 	CU(c, B.midTiles.reserve(n, c->stream));
+	CU(c, B.smallTiles.reserve(n, c->stream));
 	CU(c, B.rects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, B.bigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	// list capacity heuristic; regrown on overflow (see validateFrame), and kept equal across the sets
@@ -317,6 +318,8 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.width = c->width; fp.height = c->height;
 	fp.binsX = c->binsX; fp.binsY = c->binsY; fp.binW = c->binW; fp.binH = c->binH;
 	fp.subX = (c->binW + kTile - 1) / kTile; fp.subY = (c->binH + kTile - 1) / kTile;
+	fp.binsXMagic = fp.binsX > 1 ? (uint32_t)(0x100000000ull / fp.binsX) : 0u;
+	fp.subXMagic = fp.subX > 1 ? (uint32_t)(0x100000000ull / fp.subX) : 0u;
 	auto log2OrMinus1 = [](uint32_t v) { int s = 0; while ((1u << s) < v) ++s; return (1u << s) == v ? s : -1; };
 	fp.binShiftX = log2OrMinus1(c->binW); fp.binShiftY = log2OrMinus1(c->binH);
 	fp.cullMode = (uint32_t)rc.cull; fp.sampleState = (uint32_t)rc.sample; fp.visState = (uint32_t)rc.vis;
@@ -532,7 +535,7 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 2);
 	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, fs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
 		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
-		B.midTiles.ptr, B.longTiles.ptr, B.counters, B.frameInfo));
+		B.midTiles.ptr, B.longTiles.ptr, B.smallTiles.ptr, B.counters, B.frameInfo));
 	++c->kernelsLaunched;
 	if (sh.bound)
 	{
@@ -551,7 +554,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		{
 			// per-primitive CTAs, followed by the CTAs that scatter the cooperatively binned (big) triangles
-			const uint32_t primBlocks = (primHi - primLo + 255) / 256;
+			const uint32_t primBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
 			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, fs, B.rects.ptr, primLo, primHi, tileOffset,
 				B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp));
 			++c->kernelsLaunched;
@@ -560,7 +563,7 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, fs, tileCount, tileOffset, binIds, tiles, B.midTiles.ptr, B.frameInfo));
+		CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, fs, tileCount, tileOffset, binIds, B.smallTiles.ptr, B.midTiles.ptr, B.frameInfo));
 		CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, fs, B.midTiles.ptr, tileCount, tileOffset, binIds, B.frameInfo));
 		CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, fs, B.longTiles.ptr, tileCount, tileOffset,
 			binIds, B.frameInfo));
@@ -857,7 +860,7 @@ void b2r_destroy(b2r_context* c)
 	for (auto& B : c->bins)
 	{
 		B.rects.release(); B.tileCount.release(); B.tileOffset.release(); B.tileCursor.release(); B.longTiles.release();
-		B.midTiles.release(); B.bigList.release(); B.binIds.release();
+		B.midTiles.release(); B.smallTiles.release(); B.bigList.release(); B.binIds.release();
 		cudaFree(B.frameInfo);
 	}
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);

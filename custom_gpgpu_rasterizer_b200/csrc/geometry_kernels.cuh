@@ -498,8 +498,8 @@ constexpr uint32_t kScanThreads = 256, kScanPerThread = 8, kScanPerCta = kScanTh
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
 	uint32_t nTiles, unsigned long long capacity, uint32_t midThreshold, uint32_t longThreshold,
-	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ counters,
-	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles; [6] is the run sorter's fallback count*/)
+	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ smallTiles, uint32_t* __restrict__ counters,
+	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles,[8]=small tiles; [6] is the run sorter's fallback count*/)
 {
 	pdlPrologue();
 	// published slice sums: bit 63 = ready (frame_clear_kernel zeroes them)
@@ -610,8 +610,34 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 			}
 		}
 	}
+	// work list of the warp-level sorter: the tiles with 2..midThreshold entries, compacted (most tiles of a frame
+	// are empty or hold a single id, and a sorter warp that finds nothing to do still pins its CTA's shared memory).
+	// One atomic per warp; inside a warp the tiles stay in ascending order.
+	{
+		uint32_t mine = 0;
+		#pragma unroll
+		for (uint32_t e = 0; e < kScanPerThread; ++e) mine += (first + e < nTiles && v[e] >= 2u && v[e] <= midThreshold) ? 1u : 0u;
+		uint32_t inclS = mine;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inclS, d);
+			if (lane >= (uint32_t)d) inclS += t;
+		}
+		const uint32_t warpTotal = __shfl_sync(0xFFFFFFFFu, inclS, 31);
+		uint32_t base = 0;
+		if (lane == 0 && warpTotal) base = (uint32_t)atomicAdd(&frameInfo[8], (unsigned long long)warpTotal);
+		base = __shfl_sync(0xFFFFFFFFu, base, 0) + inclS - mine;
+		#pragma unroll
+		for (uint32_t e = 0; e < kScanPerThread; ++e)
+			if (first + e < nTiles && v[e] >= 2u && v[e] <= midThreshold) smallTiles[base++] = first + e;
+	}
 }
 
+#ifndef B2R_SCATTER_PER_THREAD
+#define B2R_SCATTER_PER_THREAD 2
+#endif
+constexpr int kScatterPerThread = B2R_SCATTER_PER_THREAD;
 // scatter of the small rectangles: one thread per primitive, re-reading the 8 B rectangle; the
 // slot inside the tile's list comes from a warp-aggregated atomic on the tile cursor.
 __global__ void __launch_bounds__(256) bin_scatter_kernel(
@@ -628,23 +654,29 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 		binBigBody<true>(blockIdx.x - primBlocks, gridDim.x - primBlocks, bigList, counters, rects, nullptr, tileOffset, tileCursor, binIds, fp);
 		return;
 	}
-	const uint32_t prim = primLo + blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t nTiles = 0;
-	int bx0 = 0, by0 = 0, bx1 = -1, by1 = -1, w = 1;
-	if (prim < primHi)
+	// kScatterPerThread primitives per thread (a CTA covers kScatterPerThread * 256 consecutive ids): the rectangle
+	// loads are issued together, so their latency is paid once; each warpBinRects call still sees one aligned
+	// group of 32 consecutive ids, which is all the run sorter assumes
+	uint2 rc[kScatterPerThread];
+	#pragma unroll
+	for (int k = 0; k < kScatterPerThread; ++k)
 	{
-		const uint2 rc = __ldg(rects + prim);
-		bx0 = rc.x & 0xFFFF; by0 = rc.y & 0xFFFF;
-		bx1 = rc.x >> 16; by1 = rc.y >> 16;
+		const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
+		rc[k] = (prim < primHi) ? __ldg(rects + prim) : make_uint2(0x0000FFFFu, 0x0000FFFFu);
+	}
+	#pragma unroll
+	for (int k = 0; k < kScatterPerThread; ++k)
+	{
+		const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
+		uint32_t nTiles = 0;
+		const int bx0 = rc[k].x & 0xFFFF, by0 = rc[k].y & 0xFFFF, bx1 = rc[k].x >> 16, by1 = rc[k].y >> 16;
 		if (bx0 <= bx1 && by0 <= by1)
 		{
-			w = bx1 - bx0 + 1;
-			nTiles = (uint32_t)w * (uint32_t)(by1 - by0 + 1);
+			nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
 			if (nTiles > fp.bigRectTiles) nTiles = 0;   // binBigBody
 		}
+		warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp);
 	}
-	(void)w;
-	warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp);
 }
 
 // Cross-GPU ordering point of the sharded front end (one warp).  Every rank stores `epoch` into its slot of
@@ -739,15 +771,17 @@ __device__ __forceinline__ void warpBitonic256(uint32_t (&a)[8], uint32_t lane)
 constexpr int kMaxRuns = 64;
 __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
-	uint32_t nTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)
+	const uint32_t* __restrict__ smallTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
 	__shared__ uint32_t sK[8][kSortWarpRadix];
 	__shared__ uint16_t sStart[8][kMaxRuns + 1], sOrder[8][kMaxRuns], sOut[8][kMaxRuns];
 	if (frameInfo[1]) return;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t tile = blockIdx.x * 8 + warp;
-	if (tile >= nTiles) return;
+	// the grid covers the worst case (every tile on the list); the CTAs behind the list's end leave at once
+	const uint32_t entry = blockIdx.x * 8 + warp;
+	if (entry >= (uint32_t)frameInfo[8]) return;
+	const uint32_t tile = __ldg(smallTiles + entry);
 	const uint32_t n = tileCount[tile];
 	if (n < 2 || n > (uint32_t)kSortWarpRadix) return;
 	uint32_t* list = binIds + tileOffset[tile];

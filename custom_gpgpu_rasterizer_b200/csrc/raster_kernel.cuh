@@ -223,8 +223,9 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
 	const uint32_t ownedIdx = blockIdx.x;
 	const uint32_t bin = fp.ownerRank + ownedIdx * fp.ownerCount;
-	const uint32_t binX = bin % fp.binsX, binY = bin / fp.binsX;
-	const uint32_t subX = blockIdx.y % fp.subX, subY = blockIdx.y / fp.subX;
+	uint32_t binX, subX;
+	const uint32_t binY = divMagic(bin, fp.binsX, fp.binsXMagic, binX);
+	const uint32_t subY = divMagic(blockIdx.y, fp.subX, fp.subXMagic, subX);
 	const int tid = threadIdx.x;
 	const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
 	// extent of this CTA's pixel block inside the bin and the screen
