@@ -197,6 +197,9 @@ __device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& 
 	return c;
 }
 
+#ifndef B2R_RASTER_PREFETCH
+#define B2R_RASTER_PREFETCH 0
+#endif
 constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
 #ifndef B2R_SMALL_AREA
 #define B2R_SMALL_AREA 48
@@ -283,68 +286,38 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS
 		list = A.binIds + A.tileOffset[bin];
 	}
 
-	// two barriers per chunk of the list (one for a list of up to 256 entries): the counter of the NEXT chunk is
-	// reset while the current one is being filled, and the trailing barrier only protects sBig from the next chunk
-	if (n && !fp.shardGeometry) __syncthreads();       // sKey / counters initialised (the sharded path has synchronised above)
-	for (uint32_t base = 0, it = 0; base < n; base += kListChunk, ++it)
+	// One list entry -> screen-space triangle + its candidate box inside this CTA's block.  Returns the number of
+	// candidate pixels (0: nothing to do).
+	auto expandEntry = [&](uint32_t prim, TriShared& t, int& x0, int& x1, int& y0, int& y1) -> int
 	{
-		if (tid == 0) sNumBig[(it + 1u) & 1u] = 0;
-		const uint32_t m = min((uint32_t)kListChunk, n - base);
-		if ((uint32_t)tid < m)
+		// rebuild the screen-space triangle from the static reference + the transformed positions
+		// (same code, hence the same bits, wherever a triangle is expanded)
+		const uint4 tr = __ldg(A.triRefs + prim);
+		const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
+		TriRecord r;
+		rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
+		// candidate pixels = the record's conservative box clipped to this CTA's block; the box
+		// contains every pixel whose edge functions can all be >= 0, so this equals the
+		// reference's test of every pixel of the bin (CUDARenderer.cu:1116-1127)
+		x0 = max((int)(r.cbX & 0xFFFFu), ox); x1 = min((int)(r.cbX >> 16), ex);
+		y0 = max((int)(r.cbY & 0xFFFFu), oy); y1 = min((int)(r.cbY >> 16), ey);
+		const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
+		if (area > 0) expandRecord(r, prim, t);
+		return area;
+	};
+	auto listEntry = [&](uint32_t e) -> uint32_t
+	{
+		if (fp.shardGeometry)
 		{
-			uint32_t prim;
-			if (fp.shardGeometry)
-			{
-				const uint32_t e = base + tid;
-				uint32_t seg = 0;
-				while (e >= sSegEnd[seg]) ++seg;
-				prim = __ldg(A.shard.binIds[seg] + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u)));
-			}
-			else
-				prim = __ldg(list + base + tid);
-			// rebuild the screen-space triangle from the static reference + the transformed positions
-			// (same code, hence the same bits, wherever a triangle is expanded)
-			const uint4 tr = __ldg(A.triRefs + prim);
-			const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
-			TriRecord r;
-			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
-			// candidate pixels = the record's conservative box clipped to this CTA's block; the box
-			// contains every pixel whose edge functions can all be >= 0, so this equals the
-			// reference's test of every pixel of the bin (CUDARenderer.cu:1116-1127)
-			const int x0 = max((int)(r.cbX & 0xFFFFu), ox), x1 = min((int)(r.cbX >> 16), ex);
-			const int y0 = max((int)(r.cbY & 0xFFFFu), oy), y1 = min((int)(r.cbY >> 16), ey);
-			const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
-			if (area > 0)
-			{
-				TriShared t;
-				expandRecord(r, prim, t);
-				if (area > kSmallArea)
-				{
-					// pixel-parallel: bbox rows are kept in zLow's neighbours for the warp-level reject
-					TriShared& dst = sBig[atomicAdd(&sNumBig[it & 1u], 1u)];
-					dst = t;
-					dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
-				}
-				else
-				{
-					// triangle-parallel: this thread walks the few candidate pixels
-					for (int y = y0; y < y1; ++y)
-						for (int x = x0; x < x1; ++x)
-						{
-							Bary bc; int zi;
-							if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
-							{
-								const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
-								atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
-								if (COUNT) ++nFrags;
-							}
-						}
-				}
-			}
+			uint32_t seg = 0;
+			while (e >= sSegEnd[seg]) ++seg;
+			return __ldg(A.shard.binIds[seg] + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u)));
 		}
-		__syncthreads();
-		// pixel-parallel path: every thread tests its own pixel against each large triangle
-		const uint32_t nBig = sNumBig[it & 1u];
+		return __ldg(list + e);
+	};
+	// pixel-parallel path: every thread tests its own pixel against the large triangles staged in sBig
+	auto pixelParallel = [&](uint32_t nBig)
+	{
 		for (uint32_t j = 0; j < nBig; ++j)
 		{
 			TriShared t = sBig[j];
@@ -358,7 +331,99 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS
 				if (zi < bestZ || (zi == bestZ && t.prim < bestPrim)) { bestZ = zi; bestPrim = t.prim; }
 			}
 		}
-		if (base + kListChunk < n) __syncthreads();
+	};
+
+	if (n && !fp.shardGeometry) __syncthreads();       // sKey / counters initialised (the sharded path has synchronised above)
+	// Sweep 1, no barriers: every thread walks its entries of all chunks of the list.  Small triangles are resolved
+	// right away (triangle-parallel, atomicMin into sKey); large ones are only collected in sBig - up to kListChunk of
+	// them for the WHOLE list - and rasterised pixel-parallel after the sweep.  The warps of the CTA therefore drift
+	// apart over a long list instead of meeting at two barriers per chunk, and their memory round trips
+	// (id -> vertex reference -> positions) overlap each other's arithmetic.
+#if B2R_RASTER_PREFETCH
+	uint32_t primAhead = 0;
+	if (!fp.shardGeometry && (uint32_t)tid < n) primAhead = __ldg(list + tid);
+#endif
+	for (uint32_t base = 0; base < n; base += kListChunk)
+	{
+#if B2R_RASTER_PREFETCH
+		// the id of the next chunk's entry is loaded one chunk ahead, its vertex reference pulled into L2 afterwards
+		const uint32_t primNow = primAhead;
+		const bool haveNext = !fp.shardGeometry && base + kListChunk + (uint32_t)tid < n;
+		if (haveNext) primAhead = __ldg(list + base + kListChunk + tid);
+#endif
+		if (base + (uint32_t)tid < n)
+		{
+#if B2R_RASTER_PREFETCH
+			const uint32_t prim = fp.shardGeometry ? listEntry(base + tid) : primNow;
+#else
+			const uint32_t prim = listEntry(base + tid);
+#endif
+			TriShared t;
+			int x0, x1, y0, y1;
+			const int area = expandEntry(prim, t, x0, x1, y0, y1);
+			if (area > kSmallArea)
+			{
+				const uint32_t slot = atomicAdd(&sNumBig[0], 1u);
+				if (slot < (uint32_t)kListChunk)
+				{
+					TriShared& dst = sBig[slot];
+					dst = t;
+					dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);      // bbox rows for the warp-level reject
+				}
+			}
+			else if (area > 0)
+			{
+				// triangle-parallel: this thread walks the few candidate pixels
+				for (int y = y0; y < y1; ++y)
+					for (int x = x0; x < x1; ++x)
+					{
+						Bary bc; int zi;
+						if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+						{
+							const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
+							atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
+							if (COUNT) ++nFrags;
+						}
+					}
+			}
+		}
+#if B2R_RASTER_PREFETCH
+		if (haveNext) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.triRefs + primAhead));
+#endif
+	}
+	if (n)
+	{
+		__syncthreads();
+		const uint32_t nBigTotal = sNumBig[0];
+		if (nBigTotal <= (uint32_t)kListChunk)
+			pixelParallel(nBigTotal);
+		else
+		{
+			// Sweep 2 (more large triangles than sBig holds): chunk by chunk, large triangles only - the small ones
+			// are done.  Two barriers per chunk: the counter of the NEXT chunk is reset while the current one is being
+			// filled, and the trailing barrier protects sBig from the next chunk.
+			__syncthreads();                               // everybody has read the total
+			if (tid < 2) sNumBig[tid] = 0;
+			__syncthreads();
+			for (uint32_t base = 0, it = 0; base < n; base += kListChunk, ++it)
+			{
+				if (tid == 0) sNumBig[(it + 1u) & 1u] = 0;
+				if (base + (uint32_t)tid < n)
+				{
+					TriShared t;
+					int x0, x1, y0, y1;
+					if (expandEntry(listEntry(base + tid), t, x0, x1, y0, y1) > kSmallArea)
+					{
+						TriShared& dst = sBig[atomicAdd(&sNumBig[it & 1u], 1u)];
+						dst = t;
+						dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
+					}
+				}
+				__syncthreads();
+				pixelParallel(sNumBig[it & 1u]);
+				if (base + kListChunk < n) __syncthreads();
+			}
+		}
 	}
 	unsigned long long best = (bestPrim == kNoPrim) ? kEmptyKey : (((unsigned long long)(uint32_t)bestZ << 32) | bestPrim);
 	best = min(best, sKey[tid]);
