@@ -347,6 +347,27 @@ def run_b200(args, scene):
     counters = r.counters()
     launches_per_frame = counters["kernels_launched"] + (gather.launches_per_frame if gather else 0)
 
+    # ---- the same frames without the in-frame list sort (B2R_OPT_SORT_BINS = 0): the image does not depend on the list
+    #      order (order-independent depth resolve) and b2r_read_bins canonicalises on demand; auxiliary number, the
+    #      headline keeps the sort inside the frame
+    unsorted_fps = None
+    if world == 1:
+        r.set_option(_lib.OPT_SORT_BINS, 0)
+        for _ in range(3):
+            frame()
+        r.sync()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            u0.record(stream)
+            for _ in range(args.steps):
+                frame()
+            u1.record(stream)
+        torch.cuda.synchronize()
+        unsorted_fps = args.steps / (u0.elapsed_time(u1) / 1e3)
+        r.set_option(_lib.OPT_SORT_BINS, 1)
+        frame()
+        r.sync()
+
     # ---- host cost of enqueueing one frame (ring of 4 frames in flight: the first three calls after a sync never block)
     r.sync()
     barrier()
@@ -475,6 +496,7 @@ def run_b200(args, scene):
         "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up/bins/sorts primitive slice r, owners read the peers' lists over NVLink, colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather])),
         "mtris_per_s": scene.n_tris * fps / 1e6,
         "visible_triangles": visible, "tile_pairs": pairs, "fragments": frags, "covered_pixels": covered_px,
+        "list_sorter": {"tiles_sent_to_the_cta_sorter_by_the_warp_sorter": counters["sort_fallback_tiles"], "tiles_beyond_the_sorter": counters["unsorted_tiles"]},
         "stages_ms": stages, "stages": per_stage,
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
                      "traffic": traffic, "peak_source": peak_src,
@@ -488,6 +510,9 @@ def run_b200(args, scene):
         "load_scene_s": load_s,
         "clocks": clocks.summary(),
     }
+    if unsorted_fps is not None:
+        line["without_in_frame_list_sort"] = {"value": unsorted_fps, "unit": "frames/s",
+                                              "note": "B2R_OPT_SORT_BINS=0: same framebuffer bit for bit; tile lists stay in scatter order and are canonicalised when read (b2r_read_bins)"}
     if view_parallel is not None:
         line["view_parallel"] = view_parallel
         line["stages_ms_per_rank"] = stages_per_rank

@@ -187,6 +187,8 @@ struct b2r_context
 	// bin buffers of the newest frame (the DeviceVecs, or one set of the shard arena)
 	uint32_t* curTileCount = nullptr; uint32_t* curTileOffset = nullptr; uint32_t* curBinIds = nullptr;
 	const uint2* curRects = nullptr;
+	BinSet* curSet = nullptr;          // set of the newest frame
+	bool curSorted = true;             // its lists are in canonical order (sorted in-frame, or on the first b2r_read_bins)
 
 	// frame state
 	RenderCall last;
@@ -389,6 +391,18 @@ int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
 	return B2R_OK;
 }
 
+// canonical (ascending primitive id) order of every tile list: the three tiers of the list sorter, working off the
+// work lists tile_scan_kernel built in the set's buffers
+int enqueueListSort(b2r_context* c, b2r_context::BinSet& B, uint32_t* tileCount, uint32_t* tileOffset, uint32_t* binIds, cudaStream_t s)
+{
+	const uint32_t tiles = nBins(c);
+	CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, tileCount, tileOffset, binIds, B.smallTiles.ptr, B.midTiles.ptr, B.frameInfo));
+	CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, s, B.midTiles.ptr, tileCount, tileOffset, binIds, B.frameInfo));
+	CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, s, B.longTiles.ptr, tileCount, tileOffset,
+		binIds, B.frameInfo));
+	return B2R_OK;
+}
+
 int enqueueFrame(b2r_context* c)
 {
 	const RenderCall& rc = c->last;
@@ -423,6 +437,7 @@ int enqueueFrame(b2r_context* c)
 	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, set) : B.binIds.ptr;
 	const size_t listCap = sh.bound ? sh.listCap : B.binIds.cap;
 	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds; c->curRects = B.rects.ptr;
+	c->curSet = &B; c->curSorted = c->sortBins != 0;
 	uint32_t primLo = 0, primHi = (uint32_t)c->nPrims;
 	if (sh.bound)
 	{
@@ -563,10 +578,7 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, fs, tileCount, tileOffset, binIds, B.smallTiles.ptr, B.midTiles.ptr, B.frameInfo));
-		CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, fs, B.midTiles.ptr, tileCount, tileOffset, binIds, B.frameInfo));
-		CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, fs, B.longTiles.ptr, tileCount, tileOffset,
-			binIds, B.frameInfo));
+		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs); if (r) return r;
 		c->kernelsLaunched += 3;
 	}
 	if (sh.bound && c->nPrims)
@@ -1130,6 +1142,16 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	const uint64_t pairs = c->lastInfo.frameInfo[0];
 	if (total) *total = pairs;
 	const uint32_t n = nBins(c);
+	if (ids && !c->curSorted && c->curSet && c->nPrims && !c->lastInfo.frameInfo[1])
+	{
+		// B2R_OPT_SORT_BINS = 0: the frame left the lists in scatter order (the image does not depend on it);
+		// whoever looks at them gets the canonical order - sort the newest frame's lists now, in place
+		r = enqueueListSort(c, *c->curSet, c->curTileCount, c->curTileOffset, c->curBinIds, c->stream); if (r) return r;
+		CU(c, cudaStreamSynchronize(c->stream));
+		// counters of the sorter (tiles beyond its reach, fallbacks) as after an in-frame sort
+		CU(c, cudaMemcpy(c->lastInfo.frameInfo, c->curSet->frameInfo, sizeof(c->lastInfo.frameInfo), cudaMemcpyDeviceToHost));
+		c->curSorted = true;
+	}
 	if (counts) CU(c, cudaMemcpy(counts, c->curTileCount, (size_t)n * 4, cudaMemcpyDeviceToHost));
 	if (offsets) CU(c, cudaMemcpy(offsets, c->curTileOffset, (size_t)n * 4, cudaMemcpyDeviceToHost));
 	if (ids)

@@ -768,7 +768,10 @@ __device__ __forceinline__ void warpBitonic256(uint32_t (&a)[8], uint32_t lane)
 	}
 }
 
-constexpr int kMaxRuns = 64;
+#ifndef B2R_SORT_MAX_RUNS
+#define B2R_SORT_MAX_RUNS 64
+#endif
+constexpr int kMaxRuns = B2R_SORT_MAX_RUNS;   // more runs than this: the tile goes to the CTA-level sorter
 __global__ void __launch_bounds__(256) bin_sort_runs_kernel(
 	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
 	const uint32_t* __restrict__ smallTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)

@@ -198,7 +198,7 @@ __device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& 
 }
 
 #ifndef B2R_RASTER_PREFETCH
-#define B2R_RASTER_PREFETCH 0
+#define B2R_RASTER_PREFETCH 1
 #endif
 constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
 #ifndef B2R_SMALL_AREA

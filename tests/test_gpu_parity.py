@@ -76,6 +76,9 @@ SCENES = {
     "soup_textured_linear": lambda: scenes.random_triangles_scene(640, 480, 300, seed=15, cull=2, textured=True, n_meshes=3, sample=1),
     "soup_depth_vis": lambda: scenes.random_triangles_scene(320, 240, 200, seed=16, cull=2, vis=1),
     "soup_normal_vis": lambda: scenes.random_triangles_scene(320, 240, 200, seed=17, cull=2, vis=2),
+    # hundreds of tile-covering triangles per tile: more than the raster kernel collects for one pixel-parallel pass
+    "soup_many_large": lambda: scenes.random_triangles_scene(320, 240, 1200, seed=19, cull=2, size=8.0),
+    "soup_many_large_textured": lambda: scenes.random_triangles_scene(320, 240, 900, seed=20, cull=2, size=8.0, textured=True, n_meshes=2),
     "soup_ragged_resolution": lambda: scenes.random_triangles_scene(333, 217, 250, seed=18, cull=2, textured=True),
     "spheres_small": lambda: scenes.sphere_grid_scene(960, 544, nx=6, ny=4, stacks=41, slices=60, cam_z=14.0),
     "spheres_tiny_tris": lambda: scenes.sphere_grid_scene(640, 368, nx=8, ny=5, stacks=81, slices=100, cam_z=22.0),

@@ -42,6 +42,8 @@ def test_list_sort_tiers_give_canonical_lists(res, grid, tess):
         tiers["warp" if n <= 1024 else "mid" if n <= 4096 else "long" if n <= 40960 else "beyond"] += 1
         if n <= 40960:
             assert np.all(seg[1:] > seg[:-1]), f"tile {t} ({n} entries) is not in ascending primitive order"
+            # B2R_OPT_SORT_BINS = 0 leaves the frame's lists in scatter order, but whoever reads them gets the canonical order
+            assert np.array_equal(i0[o0[t]: o0[t] + c0[t]], seg), f"tile {t}: lists read back without the in-frame sort are not canonical"
         assert np.array_equal(np.sort(seg), np.sort(i0[o0[t]: o0[t] + c0[t]])), f"tile {t}: content changed by the sort"
     assert unsorted_tiles == tiers["beyond"]
     assert tiers["mid"] + tiers["long"] > 0, f"scene does not exercise the CTA-level sorters: {tiers}"

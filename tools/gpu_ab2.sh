@@ -12,7 +12,7 @@ for f in $O/*.json; do echo "$f: $(python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); s=d["stages_ms"]
-    print(round(d["value"],1), "fps | " + " ".join(f"{k} {v*1e3:.1f}" for k,v in s.items() if v))
+    print(round(d["value"],1), "fps | " + " ".join(f"{k} {v*1e3:.1f}" for k,v in s.items() if v), "| unsorted", round(d.get("without_in_frame_list_sort",{}).get("value",0),1), d.get("list_sorter"))
 except Exception as e: print("FAILED", e)
 PY
 )"; done | tee $O/summary.txt
