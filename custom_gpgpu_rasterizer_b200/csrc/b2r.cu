@@ -126,7 +126,10 @@ struct b2r_context
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[2];
-	int overlapFront = 0;              // B2R_OPT_OVERLAP_FRONT
+	int overlapFront = 1;              // B2R_OPT_OVERLAP_FRONT
+	int overlapFrontSharded = 0;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=1, experimental)
+	cudaEvent_t listsReady[2] = { nullptr, nullptr };   // sharded + pipelined: the "lists ready" barrier of a frame has completed
+	bool listsReadyPending[2] = { false, false };
 	bool lastPipelined = false;        // the newest enqueued frame ran its front end on the second stream
 	struct HostInfo { unsigned long long frameInfo[kInfoWords]; uint32_t counters[2]; };   // device layout: frameInfo, then counters
 
@@ -418,7 +421,7 @@ int enqueueFrame(b2r_context* c)
 	// setup, binning, sort) goes to the second stream and works on the bin set of the frame's parity, so it
 	// overlaps the raster kernel of the previous frame, which reads the other set.  Not while the stages are being
 	// timed and not with the sharded front end (its sets live in the peer-visible arena).
-	const bool pipelined = c->overlapFront && c->overlapVertex && !c->stageTimers && c->nVsChunks && !c->shard.bound;
+	const bool pipelined = c->overlapFront && c->overlapVertex && !c->stageTimers && c->nVsChunks && (!c->shard.bound || c->overlapFrontSharded);
 	if (pipelined != c->lastPipelined)
 	{
 		// frames of the other kind used set 0 / the main stream regardless of parity: order this frame's front end
@@ -509,6 +512,10 @@ int enqueueFrame(b2r_context* c)
 			c->vtxNeedsFork = false;
 		}
 		if (c->rasterPending[g]) CU(c, cudaStreamWaitEvent(v, c->rasterDone[g], 0));
+		// Sharded + pipelined: this front end stores list heads / lists into the peers' set of this parity, which their
+		// raster kernels of frame f-2 read.  A peer has finished that raster before it arrives at the "lists ready"
+		// barrier of frame f-1 (stream order), so once OUR barrier of frame f-1 has completed every peer's set is free.
+		if (pipelined && c->shard.bound && c->listsReadyPending[g ^ 1]) CU(c, cudaStreamWaitEvent(v, c->listsReady[g ^ 1], 0));
 		CU(c, launchFrameKernel(c, build_constants_kernel, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((nMeshes + 63) / 64, (uint32_t)c->numSMs * 4))), dim3(64), 0, v, 
 			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
 		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, v, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
@@ -627,6 +634,8 @@ int enqueueFrame(b2r_context* c)
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
 			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7));
 			++c->kernelsLaunched;
+			CU(c, cudaEventRecord(c->listsReady[g], s));
+			c->listsReadyPending[g] = true;
 			STAGE_EVENT(c, slot, 8);
 			A.shard = T;
 			STAGE_EVENT(c, slot, 7);
@@ -714,7 +723,7 @@ int validateFrame(b2r_context* c)
 			*c->shard.hTimeout = 0;
 			return fail(c, B2R_E_STATE, "sharded front end: a peer rank's colours did not arrive within 4 s");
 		}
-		c->vtxNeedsFork = true; c->rasterPending[0] = c->rasterPending[1] = false;
+		c->vtxNeedsFork = true; c->rasterPending[0] = c->rasterPending[1] = false; c->listsReadyPending[0] = c->listsReadyPending[1] = false;
 		for (uint64_t k = 0; k < kRing; ++k)
 		{
 			b2r_context::Slot& slot = c->slots[(c->seq + k) % kRing];     // oldest first
@@ -818,6 +827,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	if (const char* e = getenv("B2R_OVERLAP_VERTEX")) c->overlapVertex = atoi(e) != 0;
 	if (const char* e = getenv("B2R_PDL")) c->usePdl = atoi(e) != 0;                           // debugging aid: programmatic dependent launch
 	if (const char* e = getenv("B2R_OVERLAP_FRONT")) c->overlapFront = atoi(e) != 0;           // see B2R_OPT_OVERLAP_FRONT
+	if (const char* e = getenv("B2R_OVERLAP_FRONT_SHARDED")) c->overlapFrontSharded = atoi(e) != 0;
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));
@@ -838,6 +848,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	{
 		CUC(cudaEventCreateWithFlags(&c->vtxDone[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&c->rasterDone[i], cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&c->listsReady[i], cudaEventDisableTiming));
 	}
 	for (auto& slot : c->slots)
 	{
@@ -864,7 +875,7 @@ void b2r_destroy(b2r_context* c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->vtxStream) { cudaStreamSynchronize(c->vtxStream); cudaStreamDestroy(c->vtxStream); }
 	if (c->forkEv) cudaEventDestroy(c->forkEv);
-	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); }
+	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
 	c->dTriRefs.release(); c->dVsChunks.release(); c->dTriChunks.release();

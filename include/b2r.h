@@ -75,7 +75,7 @@ enum
 	 * sort) on the second stream, so that it overlaps the raster kernel of the PREVIOUS frame when frames are
 	 * enqueued back to back; every buffer the front end writes is double-buffered by frame parity.  Results are
 	 * unchanged.  Needs B2R_OPT_OVERLAP_VERTEX; ignored while B2R_OPT_STAGE_TIMERS is on and with the sharded
-	 * front end (b2r_shard_*). */
+	 * front end (b2r_shard_*).  Default 1. */
 	B2R_OPT_OVERLAP_FRONT = 11
 };
 

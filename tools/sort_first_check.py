@@ -67,6 +67,33 @@ for sc in test_scenes:
             ok &= same_l
         full.close()
     dist.barrier()
+    if mode == "sharded":
+        # frames in flight with a MOVING camera (every frame differs): each composed frame, presented by rank 0 while
+        # the next ones are being rendered, must equal the single-GPU frame of the same camera - catches a stage of
+        # one frame reading buffers another frame's stage has already recycled
+        cams = [host_camera((sc.cam_pos[0] + 0.11 * k, sc.cam_pos[1] - 0.07 * k, sc.cam_pos[2] + 0.05 * k), sc.fov_deg, sc.width, sc.height, sc.near, sc.far)
+                for k in range(10)]
+        bufs = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+        for cam_k, b in zip(cams, bufs):
+            r.render(cam_k, sc.cull, sc.sample, sc.vis, sync=False)
+            if rank == 0:
+                r.present_async(b)
+        if rank == 0:
+            r.present_wait()
+        else:
+            r.sync()
+        dist.barrier()
+        if rank == 0:
+            full = Renderer(sc.width, sc.height, device=local)
+            full.load_scene(sc)
+            bad = 0
+            for cam_k, b in zip(cams, bufs):
+                full.render(cam_k, sc.cull, sc.sample, sc.vis)
+                bad += 0 if np.array_equal(b, full.framebuffer()) else 1
+            full.close()
+            print(f"sort-first[{mode}] world={world} {sc.name} moving camera, {len(cams)} frames in flight: {'identical' if bad == 0 else 'DIFFERENT (%d frames)' % bad}")
+            ok &= bad == 0
+        dist.barrier()
     g.close()
     r.close()
 dist.destroy_process_group()
