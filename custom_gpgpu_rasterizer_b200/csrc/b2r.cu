@@ -101,8 +101,9 @@ struct b2r_context
 	// stage of frame f+1 runs on its own stream while frame f is still binning / rasterising
 	DeviceVec<float4> dPos4[2];
 	int geoIdx = 0;                    // parity of the newest enqueued frame
-	cudaStream_t vtxStream = nullptr;
-	cudaEvent_t vtxDone[2] = { nullptr, nullptr }, rasterDone[2] = { nullptr, nullptr }, forkEv = nullptr;
+	cudaStream_t vtxStream = nullptr;  // vertex stage (constants + transform)
+	cudaStream_t frontStream = nullptr; // pipelined frames: setup, binning and sort
+	cudaEvent_t vtxDone[2] = { nullptr, nullptr }, frontDone[2] = { nullptr, nullptr }, rasterDone[2] = { nullptr, nullptr }, forkEv = nullptr;
 	bool rasterPending[2] = { false, false }, vtxNeedsFork = true;
 	int overlapVertex = 1, usePdl = 1;
 	DeviceVec<float> dOvertexScratch;
@@ -509,25 +510,30 @@ int enqueueFrame(b2r_context* c)
 		{
 			CU(c, cudaEventRecord(c->forkEv, s));
 			CU(c, cudaStreamWaitEvent(v, c->forkEv, 0));
+			CU(c, cudaStreamWaitEvent(c->frontStream, c->forkEv, 0));
 			c->vtxNeedsFork = false;
 		}
 		if (c->rasterPending[g]) CU(c, cudaStreamWaitEvent(v, c->rasterDone[g], 0));
-		// Sharded + pipelined: this front end stores list heads / lists into the peers' set of this parity, which their
-		// raster kernels of frame f-2 read.  A peer has finished that raster before it arrives at the "lists ready"
-		// barrier of frame f-1 (stream order), so once OUR barrier of frame f-1 has completed every peer's set is free.
-		if (pipelined && c->shard.bound && c->listsReadyPending[g ^ 1]) CU(c, cudaStreamWaitEvent(v, c->listsReady[g ^ 1], 0));
 		CU(c, launchFrameKernel(c, build_constants_kernel, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((nMeshes + 63) / 64, (uint32_t)c->numSMs * 4))), dim3(64), 0, v, 
 			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
 		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, v, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
 		c->kernelsLaunched += 2;
-		if (!pipelined)
-		{
-			CU(c, cudaEventRecord(c->vtxDone[g], v));
-			CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
-		}
+		CU(c, cudaEventRecord(c->vtxDone[g], v));
 	}
-	// stream of the front end: the second stream when pipelined (joined into the main stream before the raster)
-	cudaStream_t fs = pipelined ? c->vtxStream : s;
+	// Stream of the front end (setup, binning, sort): the main stream, or - pipelined - a stream of its own, joined
+	// into the main stream before the raster.  Three frames are then in flight: vertex(f+2) | front end(f+1) |
+	// raster(f), each stage waiting only for what it reads or recycles.
+	cudaStream_t fs = pipelined ? c->frontStream : s;
+	if (overlap) CU(c, cudaStreamWaitEvent(fs, c->vtxDone[g], 0));
+	if (pipelined)
+	{
+		// this front end recycles the bin set of frame f-2 (read by that frame's raster and publish kernels) ...
+		if (c->rasterPending[g]) CU(c, cudaStreamWaitEvent(fs, c->rasterDone[g], 0));
+		// ... and, sharded, stores list heads / lists into the peers' set of this parity, which their raster kernels
+		// of frame f-2 read.  A peer has finished that raster before it arrives at the "lists ready" barrier of
+		// frame f-1 (stream order), so once OUR barrier of frame f-1 has completed every peer's set is free.
+		if (c->shard.bound && c->listsReadyPending[g ^ 1]) CU(c, cudaStreamWaitEvent(fs, c->listsReady[g ^ 1], 0));
+	}
 	// one small kernel instead of three memsets: memsets may be served by a copy engine, where they would
 	// queue behind the previous frame's 33 MB Present copy
 	const uint32_t clearMeshes = overlap ? 0u : nMeshes;
@@ -600,8 +606,8 @@ int enqueueFrame(b2r_context* c)
 	if (pipelined)
 	{
 		// join: the raster of this frame (main stream) starts when its lists are sorted
-		CU(c, cudaEventRecord(c->vtxDone[g], fs));
-		CU(c, cudaStreamWaitEvent(s, c->vtxDone[g], 0));
+		CU(c, cudaEventRecord(c->frontDone[g], fs));
+		CU(c, cudaStreamWaitEvent(s, c->frontDone[g], 0));
 	}
 	{
 		RasterArgs A{};
@@ -842,11 +848,13 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 		const char* e = getenv("B2R_FRONT_PRIORITY");
 		const bool high = e ? atoi(e) != 0 : false;
 		CUC(cudaStreamCreateWithPriority(&c->vtxStream, cudaStreamNonBlocking, high ? prGreatest : prLeast));
+		CUC(cudaStreamCreateWithPriority(&c->frontStream, cudaStreamNonBlocking, high ? prGreatest : prLeast));
 	}
 	CUC(cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming));
 	for (int i = 0; i < 2; ++i)
 	{
 		CUC(cudaEventCreateWithFlags(&c->vtxDone[i], cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&c->frontDone[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&c->rasterDone[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&c->listsReady[i], cudaEventDisableTiming));
 	}
@@ -874,8 +882,9 @@ void b2r_destroy(b2r_context* c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->vtxStream) { cudaStreamSynchronize(c->vtxStream); cudaStreamDestroy(c->vtxStream); }
+	if (c->frontStream) { cudaStreamSynchronize(c->frontStream); cudaStreamDestroy(c->frontStream); }
 	if (c->forkEv) cudaEventDestroy(c->forkEv);
-	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
+	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->frontDone[i]) cudaEventDestroy(c->frontDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
 	c->dTriRefs.release(); c->dVsChunks.release(); c->dTriChunks.release();

@@ -6,7 +6,7 @@ python -c "import torch" 2>/dev/null
 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_units.py tests/test_gpu_veneer.py -m gpu -q -x -n 4 > $O/pytest.log 2>&1; echo "exit $?" >> $O/pytest.log
 B="timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-fill"
 $B > $O/main.json 2> $O/main.err
-B2R_OVERLAP_FRONT=1 $B > $O/main_pipe.json 2> $O/main_pipe.err
+B2R_OVERLAP_FRONT=0 $B > $O/main_serial.json 2> $O/main_serial.err
 for v in build/variants/*.so; do n=$(basename $v .so); B2R_LIBRARY=$PWD/$v $B > $O/$n.json 2> $O/$n.err; done
 for f in $O/*.json; do echo "$f: $(python - "$f" <<'PY'
 import json,sys
