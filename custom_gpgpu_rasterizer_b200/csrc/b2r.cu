@@ -128,7 +128,7 @@ struct b2r_context
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[2];
 	int overlapFront = 1;              // B2R_OPT_OVERLAP_FRONT
-	int overlapFrontSharded = 0;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=1, experimental)
+	int overlapFrontSharded = 1;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=0 switches it off)
 	cudaEvent_t listsReady[2] = { nullptr, nullptr };   // sharded + pipelined: the "lists ready" barrier of a frame has completed
 	bool listsReadyPending[2] = { false, false };
 	bool lastPipelined = false;        // the newest enqueued frame ran its front end on the second stream

@@ -74,8 +74,9 @@ enum
 	/* pipeline whole frames: run the complete geometry front end of a frame (constants, vertex, setup, binning,
 	 * sort) on the second stream, so that it overlaps the raster kernel of the PREVIOUS frame when frames are
 	 * enqueued back to back; every buffer the front end writes is double-buffered by frame parity.  Results are
-	 * unchanged.  Needs B2R_OPT_OVERLAP_VERTEX; ignored while B2R_OPT_STAGE_TIMERS is on and with the sharded
-	 * front end (b2r_shard_*).  Default 1. */
+	 * unchanged.  Needs B2R_OPT_OVERLAP_VERTEX; ignored while B2R_OPT_STAGE_TIMERS is on.  With the sharded front
+	 * end (b2r_shard_*) a frame's front end additionally waits for the previous frame's "lists ready" barrier
+	 * before it stores into the peers' list sets.  Default 1. */
 	B2R_OPT_OVERLAP_FRONT = 11
 };
 
