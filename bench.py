@@ -229,7 +229,10 @@ def reference_cuda_arm(scene, frames: int, timeout_s: int):
             return {"unavailable": f"ref_render did not finish 1 + {frames} frames within {timeout_s} s"}
     if res.returncode != 0:
         return {"unavailable": f"ref_render exit code {res.returncode}: {res.stderr.strip()[-200:]}"}
-    out = json.loads(res.stdout.strip().splitlines()[-1])
+    try:
+        out = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception:
+        return {"unavailable": "ref_render printed no timing line"}
     return {"value": 1e3 / out["ms_per_frame"], "unit": "frames/s", "ms_per_frame": out["ms_per_frame"], "frames": out["frames"],
             "visible_triangles": out["visible_triangles"], "kind": "reference",
             "sample": f"the full frame of this workload, {out['frames']} frame(s) after 1 warm-up, through the reference's CUDARenderer::RenderAuto "
@@ -580,7 +583,7 @@ def main():
     ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
-    ap.add_argument("--ref-cuda", type=int, default=0, metavar="FRAMES", help="--impl reference only: also time the reference's own CUDA renderer (oracle/_ref/ref_render) on GPU 0 for this many frames")
+    ap.add_argument("--ref-cuda", type=int, default=2, metavar="FRAMES", help="--impl reference only: also time the reference's own CUDA renderer (oracle/_ref/ref_render) on GPU 0 for this many frames (0 = skip)")
     ap.add_argument("--ref-cuda-timeout", type=int, default=240)
     args = ap.parse_args()
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
