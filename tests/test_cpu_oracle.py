@@ -136,3 +136,34 @@ def test_erenderer_port_agrees_with_gpu_path_on_coverage():
     o = oracle_lib.render(sc)
     cov_cpu, cov_gpu = fb != 0x40404040, o["winner"] != 0xFFFFFFFF
     assert (cov_cpu != cov_gpu).mean() < 0.002       # same inside test; differences only from fused vs unfused edge functions
+
+
+def test_fullsize_helpers_on_a_small_grid_with_the_oracle_as_product():
+    """tests/fullsize.py (the -m gpu checks at BASELINE's full sizes) exercised on CPU: a 5 x 5 grid of the config-3 spheres at the
+    same on-screen size, and an 8-layer config 4, with the oracle's whole-scene frame standing in for the product's."""
+    import fullsize
+    from custom_gpgpu_rasterizer_b200 import scenes
+    full = scenes.sphere_grid_scene(768, 432, nx=5, ny=5, cam_z=68.0 / 5)
+    nv, nt = full.n_vertices // 25, full.n_tris // 25
+    F = oracle_lib.render(full, fill_rule=1)
+    fullsize.check_frame_invariants(F["framebuffer"], F["depth"], F["winner"])
+    compared = fullsize.check_sphere_regions(full, F["framebuffer"], F["depth"], F["winner"], [0, 4, 12, 20, 24, 7], nv, nt, fill_rule=1)
+    assert compared > 6 * 3000
+    counts = F["bin_counts"]
+    offsets = np.concatenate([[0], np.cumsum(counts.astype(np.int64))[:-1]]).astype(np.uint32)
+    # the oracle's lists hold the same sets; bring them into the product's canonical order first
+    ids = np.concatenate([np.sort(s) for s in oracle_lib.bin_sets(counts, F["bin_ids"])] or [np.zeros(0, np.uint32)])
+    fullsize.check_lists(counts, offsets, ids, int(counts.sum()))
+    with pytest.raises(AssertionError):
+        bad = ids.copy(); bad[[5, 6]] = bad[[6, 5]]
+        fullsize.check_lists(counts, offsets, bad, int(counts.sum()))
+    with pytest.raises(AssertionError):
+        wrong = F["framebuffer"].copy(); wrong[F["winner"] != fullsize.NONE] ^= 1
+        fullsize.check_sphere_regions(full, wrong, F["depth"], F["winner"], [12], nv, nt, fill_rule=1)
+    quads = scenes.fill_quads_scene(320, 180, layers=8, tex_size=64, sample=1)
+    Q = oracle_lib.render(quads, fill_rule=1)
+    o = oracle_lib.render(fullsize.nearest_layer_scene(quads, 8), fill_rule=1)
+    cov = o["winner"] != fullsize.NONE           # where the nearest layer produces a fragment it wins (rounding may cost it a border row)
+    assert cov.mean() > 0.98
+    assert np.array_equal(Q["framebuffer"][cov], o["framebuffer"][cov]) and np.array_equal(Q["depth"][cov], o["depth"][cov])
+    assert np.array_equal(Q["winner"][cov].astype(np.int64), o["winner"][cov].astype(np.int64) + 14)

@@ -1,0 +1,73 @@
+"""-m gpu: parity at BASELINE.json's full sizes (configs 3 and 4 at 3840x2160), through the C ABI.  See tests/fullsize.py
+for the properties used (locality of a pixel, depth order).  The file name sorts behind the other -m gpu files on purpose:
+these two tests hold the largest allocations of the suite (2 x 250 MB of bin sets for 10 M triangles).  Written after the
+round's GPU budget was spent: the helpers are exercised on CPU (tests/test_cpu_oracle.py), the product calls are the ones
+tests/test_gpu_parity.py makes."""
+import numpy as np
+import pytest
+
+import fullsize
+import oracle_lib
+from custom_gpgpu_rasterizer_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config3_10m_triangles_4k_matches_oracle_per_sphere():
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    sc = scenes.sphere_grid_scene(3840, 2160)                     # BASELINE config 3
+    nv, nt = 8282, 16000
+    assert sc.n_tris == 625 * nt and sc.n_vertices == 625 * nv
+    with Renderer(sc.width, sc.height) as r:
+        r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+        r.load_scene(sc)
+        r.render_scene(sc)
+        fb, depth, winner = r.framebuffer().copy(), r.depth().copy(), r.winner().copy()
+        total, visible = r.stats()
+        assert total == 10_000_000 and 0 < visible < total
+        fullsize.check_frame_invariants(fb, depth, winner)
+        counts, offsets, ids = r.bin_lists()
+        fullsize.check_lists(counts, offsets, ids, r.counters()["pairs"])
+        # corners, edge centres, the centre and a few others of the 25 x 25 grid
+        sids = [0, 24, 600, 624, 12, 300, 324, 612, 312, 137, 401, 538]
+        compared = fullsize.check_sphere_regions(sc, fb, depth, winner, sids, nv, nt, fill_rule=1)
+        assert compared > 12 * 4000
+        # every covered pixel belongs to the sphere whose rectangle it lies in: winners map to 625 disjoint id ranges
+        won = winner[winner != fullsize.NONE]
+        assert won.max() < total and np.unique(won // nt).size == 625
+        # the frame does not depend on how it is scheduled: serial frames, no in-frame list sort, several frames in flight
+        r.set_option(_lib.OPT_OVERLAP_FRONT, 0)
+        r.render_scene(sc)
+        assert np.array_equal(r.framebuffer(), fb) and np.array_equal(r.depth(), depth)
+        r.set_option(_lib.OPT_OVERLAP_FRONT, 1)
+        r.set_option(_lib.OPT_SORT_BINS, 0)
+        for _ in range(4):
+            r.render_scene(sc, sync=False)
+        assert np.array_equal(r.framebuffer(), fb) and np.array_equal(r.depth(), depth)
+        counts2, offsets2, ids2 = r.bin_lists()                     # canonicalised on read
+        assert np.array_equal(counts2, counts) and np.array_equal(ids2, ids)
+
+
+def test_config4_64_layers_4k_equals_nearest_layer():
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    layers = 64
+    sc = scenes.fill_quads_scene(3840, 2160, layers=layers, sample=1)     # BASELINE config 4, linear sampling
+    o = oracle_lib.render(fullsize.nearest_layer_scene(sc, layers), fill_rule=1)
+    with Renderer(sc.width, sc.height) as r:
+        r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+        r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
+        r.load_scene(sc)
+        r.render_scene(sc)
+        fb, depth, winner = r.framebuffer(), r.depth(), r.winner()
+        c = r.counters()
+    assert (winner != fullsize.NONE).all()
+    cov = o["winner"] != fullsize.NONE           # where the nearest layer produces a fragment it wins; at 4K that is every pixel
+    assert cov.all()
+    assert np.array_equal(winner[cov].astype(np.int64), o["winner"][cov].astype(np.int64) + 2 * (layers - 1)), "the nearest layer must win every pixel it covers"
+    assert np.array_equal(depth[cov], o["depth"][cov]), "integer depth differs from the oracle's nearest layer"
+    assert np.array_equal(fb[cov], o["framebuffer"][cov]), "colours differ from the oracle's nearest layer"
+    assert c["pairs"] == 2 * layers * 240 * 135 and c["big_triangles"] == 2 * layers
+    # every layer covers the screen (a few pixels of the shared diagonal go to one triangle only): F is within 0.1 % of 64 W H
+    assert 0.999 * layers * sc.width * sc.height <= c["fragments"] <= layers * sc.width * sc.height
