@@ -30,6 +30,8 @@ OPT_FILL_RULE_TOP_LEFT, OPT_TILE_OWNER_RANK, OPT_TILE_OWNER_COUNT = 1, 2, 3
 OPT_DEBUG_SURFACES, OPT_STAGE_TIMERS, OPT_SORT_BINS, OPT_COUNT_FRAGMENTS, OPT_PACKED_OUTPUT = 4, 5, 6, 7, 8
 OPT_OVERLAP_VERTEX = 10
 OPT_OVERLAP_FRONT = 11
+OPT_FRAME_RING = 12
+OPT_SHARD_SLICED_VERTEX = 13
 STAGE_NAMES = ("vertex", "setup", "bin_scan", "bin_scatter", "bin_sort", "raster_shade", "total", "exchange", "peer_wait")
 NUM_STAGES = 9
 
@@ -48,6 +50,7 @@ ABI = {
     "b2r_mesh_set_world": (_i32, [_vp, _i32, _fp]),
     "b2r_mesh_clear_all": (_i32, [_vp]),
     "b2r_set_option": (_i32, [_vp, _i32, _i32]),
+    "b2r_get_option": (_i32, [_vp, _i32, C.POINTER(C.c_int)]),
     "b2r_render": (_i32, [_vp, _fp, _fp, _fp, _i32, _i32, _i32, _fp]),
     "b2r_sync": (_i32, [_vp]),
     "b2r_read_framebuffer": (_i32, [_vp, _vp]),

@@ -31,6 +31,7 @@ using namespace b2r;
 namespace {
 
 constexpr int kRing = 4;
+constexpr int kMaxFrameRing = 4;      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
 constexpr int kInfoWords = 16;
 thread_local std::string g_createError;
 
@@ -99,8 +100,9 @@ struct b2r_context
 	DeviceVec<float4> dPosIn;          // positions in (x,y,z,1)
 	// transformed positions (ndc.xyz, clip.w) and per-mesh constants, double-buffered by frame parity: the vertex
 	// stage of frame f+1 runs on its own stream while frame f is still binning / rasterising
-	DeviceVec<float4> dPos4[2];
-	int geoIdx = 0;                    // parity of the newest enqueued frame
+	DeviceVec<float4> dPos4[kMaxFrameRing];
+	int geoIdx = 0;                    // parity (frame ring: ring slot) of the newest enqueued frame
+	std::vector<uint32_t> vsChunkStart; // host copy of the vertex chunks' first transformed-vertex index (ascending)
 	cudaStream_t vtxStream = nullptr;  // vertex stage (constants + transform)
 	cudaStream_t frontStream = nullptr; // pipelined frames: setup, binning and sort
 	cudaEvent_t vtxDone[2] = { nullptr, nullptr }, frontDone[2] = { nullptr, nullptr }, rasterDone[2] = { nullptr, nullptr }, forkEv = nullptr;
@@ -110,7 +112,7 @@ struct b2r_context
 	DeviceVec<uint4> dTriRefs;         // static {v0, v1, v2, mesh} per primitive, rebuilt when the mesh list changes
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
-	DeviceVec<MeshConst> dMeshConst[2];
+	DeviceVec<MeshConst> dMeshConst[kMaxFrameRing];
 	DeviceVec<MeshStatic> dMeshStatic;
 	bool meshStaticDirty = true, anyDiffuse = false;
 	DeviceVec<TexDesc> dTexDesc;
@@ -126,8 +128,19 @@ struct b2r_context
 		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, midTiles, smallTiles, bigList, binIds;
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
-	} bins[2];
+	} bins[kMaxFrameRing];
 	int overlapFront = 1;              // B2R_OPT_OVERLAP_FRONT
+	// Frame ring (B2R_OPT_FRAME_RING = D >= 2, default off): frame f runs from its constants to its raster on ring
+	// stream f % D with its own copy of everything a frame writes, so up to D geometry front ends are in flight;
+	// only the raster kernels are chained in frame order (enqueueFrameRing)
+	int ringDepth = 0;
+	cudaStream_t ringStream[kMaxFrameRing] = {};
+	cudaEvent_t ringDone[kMaxFrameRing] = {};     // raster + publish of the newest frame of that ring slot
+	bool ringNeedsFork[kMaxFrameRing] = {};
+	int ringPrev = -1;                 // ring slot of the previous frame while it may still be in flight
+	uint32_t* dRangeScratch = nullptr;
+	int slicedVertex = 0;              // sharded front end: transform only the vertices of this rank's primitive slice;
+	                                   // the raster kernel transforms the vertices of its list entries itself (B2R_SHARD_SLICED_VERTEX)
 	int overlapFrontSharded = 1;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=0 switches it off)
 	cudaEvent_t listsReady[2] = { nullptr, nullptr };   // sharded + pipelined: the "lists ready" barrier of a frame has completed
 	bool listsReadyPending[2] = { false, false };
@@ -172,6 +185,9 @@ struct b2r_context
 	{
 		bool prepared = false, bound = false;
 		int n = 1, self = 0;
+		int nSets = 2;                         // list sets in the arena: 2 (frame parity) or the depth of the frame ring
+		bool rangeValid = false;               // sliced vertex stage: vertex chunks [chunkLo, chunkHi) cover this rank's primitive slice
+		uint32_t chunkLo = 0, chunkHi = 0;
 		uint8_t* arena = nullptr;
 		size_t tilesPad = 0, listCap = 0, setBytes = 0;
 		uint8_t* peerArena[kMaxRanks] = {};
@@ -257,7 +273,9 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	CU(c, B.rects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, B.bigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	// list capacity heuristic; regrown on overflow (see validateFrame), and kept equal across the sets
-	CU(c, B.binIds.reserve(std::max<size_t>(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), std::max(c->bins[0].binIds.cap, c->bins[1].binIds.cap)), c->stream));
+	size_t listCap = std::max<size_t>((size_t)1 << 22, c->nPrims * 3);
+	for (const auto& other : c->bins) listCap = std::max(listCap, other.binIds.cap);
+	CU(c, B.binIds.reserve(listCap, c->stream));
 	return B2R_OK;
 }
 
@@ -286,6 +304,9 @@ int rebuildScene(b2r_context* c)
 			tri.push_back(Chunk{ (uint32_t)m, std::min<uint32_t>(kChunk, hm.nTris - f), hm.idxBase + 3u * f, hm.vtxOutBase, hm.primBase + f, 0u });
 	}
 	c->nVsChunks = (uint32_t)vs.size(); c->nTriChunks = (uint32_t)tri.size();
+	c->vsChunkStart.resize(vs.size());
+	for (size_t i = 0; i < vs.size(); ++i) c->vsChunkStart[i] = vs[i].outStart;
+	c->shard.rangeValid = false;
 	CU(c, c->dVsChunks.reserve(std::max<size_t>(vs.size(), 1), c->stream));
 	CU(c, c->dTriChunks.reserve(std::max<size_t>(tri.size(), 1), c->stream));
 	if (!vs.empty()) CU(c, cudaMemcpyAsync(c->dVsChunks.ptr, vs.data(), vs.size() * sizeof(Chunk), cudaMemcpyHostToDevice, c->stream));
@@ -297,8 +318,11 @@ int rebuildScene(b2r_context* c)
 		build_trirefs_kernel<<<c->nTriChunks, kChunk, 0, c->stream>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dTriRefs.ptr);
 		CU(c, cudaGetLastError());
 	}
-	for (auto& v : c->dPos4) CU(c, v.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
-	for (auto& v : c->dMeshConst) CU(c, v.reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
+	for (int i = 0; i < std::max(2, c->ringDepth); ++i)
+	{
+		CU(c, c->dPos4[i].reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
+		CU(c, c->dMeshConst[i].reserve(std::max<size_t>(c->meshes.size(), 1), c->stream));
+	}
 	for (auto& B : c->bins)
 		if (B.frameInfo) { int r = reserveBinSet(c, B); if (r) return r; }
 	c->sceneDirty = false;
@@ -350,6 +374,28 @@ cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 g
 	attr.val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = &attr; cfg.numAttrs = c->usePdl ? 1u : 0u;
 	return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
+// the raster kernel instantiation of a frame: fill rule, fragment counter, light variant (the frame cannot reach the
+// texture / visualiser paths), positions transformed on the fly (sharded front end with a sliced vertex stage)
+cudaError_t launchRaster(const b2r_context* c, dim3 grid, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool onTheFly)
+{
+	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (onTheFly ? 8 : 0);
+	const dim3 block(kTile * kTile);
+#define B2R_RASTER_CASE(v, tl, cnt, tex, otf) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, otf>, grid, block, 0, s, A, fp);
+	switch (variant)
+	{
+	B2R_RASTER_CASE(0, false, false, false, false) B2R_RASTER_CASE(1, true, false, false, false)
+	B2R_RASTER_CASE(2, false, true, false, false)  B2R_RASTER_CASE(3, true, true, false, false)
+	B2R_RASTER_CASE(4, false, false, true, false)  B2R_RASTER_CASE(5, true, false, true, false)
+	B2R_RASTER_CASE(6, false, true, true, false)   B2R_RASTER_CASE(7, true, true, true, false)
+	B2R_RASTER_CASE(8, false, false, false, true)  B2R_RASTER_CASE(9, true, false, false, true)
+	B2R_RASTER_CASE(10, false, true, false, true)  B2R_RASTER_CASE(11, true, true, false, true)
+	B2R_RASTER_CASE(12, false, false, true, true)  B2R_RASTER_CASE(13, true, false, true, true)
+	B2R_RASTER_CASE(14, false, true, true, true)
+	default: return launchFrameKernel(c, raster_shade_kernel<true, true, true, true>, grid, block, 0, s, A, fp);
+	}
+#undef B2R_RASTER_CASE
 }
 
 #define STAGE_EVENT(c, slot, i) do { if ((slot).timed) CU((c), cudaEventRecord((slot).ev[(i)], (c)->stream)); } while (0)
@@ -407,8 +453,11 @@ int enqueueListSort(b2r_context* c, b2r_context::BinSet& B, uint32_t* tileCount,
 	return B2R_OK;
 }
 
+int enqueueFrameRing(b2r_context* c);
+
 int enqueueFrame(b2r_context* c)
 {
+	if (c->ringDepth) return enqueueFrameRing(c);
 	const RenderCall& rc = c->last;
 	if (c->sceneDirty) { int r = rebuildScene(c); if (r) return r; }
 	if (c->texDirty) { int r = rebuildTextures(c); if (r) return r; }
@@ -612,7 +661,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
@@ -638,7 +687,7 @@ int enqueueFrame(b2r_context* c)
 			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
 			// "lists ready": nobody reads a peer's lists before that peer has sorted them.  (Rank 0 arrives only
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
-			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7));
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7, 1u));
 			++c->kernelsLaunched;
 			CU(c, cudaEventRecord(c->listsReady[g], s));
 			c->listsReadyPending[g] = true;
@@ -651,19 +700,7 @@ int enqueueFrame(b2r_context* c)
 		{
 			const dim3 grid(owned, fp.subX * fp.subY);
 			// light variant when the frame cannot reach the texture / visualiser paths
-			const bool anyDiffuse = rc.vis != 0 || c->anyDiffuse;
-			const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (anyDiffuse ? 4 : 0);
-			switch (variant)
-			{
-			case 0: CU(c, launchFrameKernel(c, raster_shade_kernel<false, false, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			case 1: CU(c, launchFrameKernel(c, raster_shade_kernel<true, false, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			case 2: CU(c, launchFrameKernel(c, raster_shade_kernel<false, true, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			case 3: CU(c, launchFrameKernel(c, raster_shade_kernel<true, true, false>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			case 4: CU(c, launchFrameKernel(c, raster_shade_kernel<false, false, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			case 5: CU(c, launchFrameKernel(c, raster_shade_kernel<true, false, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			case 6: CU(c, launchFrameKernel(c, raster_shade_kernel<false, true, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			default: CU(c, launchFrameKernel(c, raster_shade_kernel<true, true, true>, grid, dim3(kTile * kTile), 0, s, A, fp)); break;
-			}
+			CU(c, launchRaster(c, grid, s, A, fp, rc.vis != 0 || c->anyDiffuse, false));
 			++c->kernelsLaunched;
 		}
 		// the vertex stage of frame f+2 may overwrite pos4 / constants of this parity once this raster is done
@@ -688,7 +725,7 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 6);
 	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
 	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, s, B.frameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8),
-		landedFlag, c->shard.frame));
+		landedFlag, c->shard.frame, PeerFlags{}, 0u, 0u));
 	++c->kernelsLaunched;
 	if (pipelined)
 	{
@@ -696,6 +733,286 @@ int enqueueFrame(b2r_context* c)
 		c->rasterPending[g] = true;
 	}
 	CU(c, cudaEventRecord(slot.done, s));
+	CU(c, cudaGetLastError());
+	slot.pending = true;
+	++c->seq;
+	c->haveFrame = true;
+	return B2R_OK;
+}
+
+// Frame ring (B2R_OPT_FRAME_RING = D): the alternative to the three-stage pipeline of enqueueFrame.  Frame f runs
+// from its constants to its publish kernel on ring stream f % D and owns ring slot f % D of everything a frame
+// writes (transformed positions, per-mesh constants, bin set and - sharded - the list set in the arenas), so
+//   * re-use of a slot is ordered by the stream itself (frame f follows frame f-D on the same stream);
+//   * the geometry front ends of up to D consecutive frames are in flight at once, which is what a rank of the
+//     sharded front end needs: its front end is a chain of short, latency-bound kernels (1/n of the primitives)
+//     that cannot fill the GPU, and in the three-stage pipeline the front end of frame f+1 has to wait for the
+//     cross-GPU barrier of frame f;
+//   * only the raster kernels are chained in frame order (event of the previous frame): they share the depth and
+//     colour surfaces, and the "colours landed" / "frame done" epochs must rise monotonically.
+// Cross-GPU re-use of a list set: rank A's front end of frame f stores list heads and lists into set f % D of every
+// peer, which the peer's raster kernel of frame f-D reads.  Every rank therefore announces "frame done" to all
+// ranks from its publish kernel (flag words 16..23), and A waits for all peers' announcements of frame f-D right
+// before its first store into peer memory (normally long satisfied: D-1 frames lie in between).
+// With B2R_OPT_STAGE_TIMERS a frame waits for its predecessor at its START, so the stage times are those of
+// serial frames (all stages of a frame are on one stream here).
+int enqueueFrameRing(b2r_context* c)
+{
+	const RenderCall& rc = c->last;
+	if (c->sceneDirty) { int r = rebuildScene(c); if (r) return r; }
+	if (c->texDirty) { int r = rebuildTextures(c); if (r) return r; }
+	if (c->debugSurfaces) { int r = ensureDebugSurfaces(c); if (r) return r; }
+	cudaStream_t s = c->stream;
+	const FrameParams fp = makeParams(c, rc);
+	const uint32_t tiles = nBins(c);
+	c->kernelsLaunched = 0;
+	b2r_context::Shard& sh = c->shard;
+	const int D = c->ringDepth;
+	if (sh.bound && sh.nSets != D) return fail(c, B2R_E_STATE, "frame ring of depth %d but the shared arena holds %d list sets", D, sh.nSets);
+	// ring slot: the same on every rank of a sharded group (all ranks render the same frames after the bind)
+	const uint32_t frameNo = sh.bound ? sh.frame : (uint32_t)c->seq;
+	const int k = (int)(frameNo % (uint32_t)D);
+	cudaStream_t rs = c->ringStream[k];
+	b2r_context::BinSet& B = c->bins[k];
+	{ int r = reserveBinSet(c, B); if (r) return r; }
+	c->lastPipelined = false;
+
+	uint32_t* tileCount = sh.bound ? sh.tileCount(sh.arena, k) : B.tileCount.ptr;
+	uint32_t* tileOffset = sh.bound ? sh.tileOffset(sh.arena, k) : B.tileOffset.ptr;
+	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, k) : B.binIds.ptr;
+	const size_t listCap = sh.bound ? sh.listCap : B.binIds.cap;
+	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds; c->curRects = B.rects.ptr;
+	c->curSet = &B; c->curSorted = c->sortBins != 0;
+	uint32_t primLo = 0, primHi = (uint32_t)c->nPrims;
+	if (sh.bound)
+	{
+		const uint64_t blocks = (c->nPrims + kChunk - 1) / kChunk;
+		primLo = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)sh.self / (uint64_t)sh.n * kChunk);
+		primHi = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)(sh.self + 1) / (uint64_t)sh.n * kChunk);
+	}
+	// sliced vertex stage (sharded only): this rank transforms the vertex chunks its primitive slice refers to, and
+	// its raster kernel transforms the vertices of its list entries itself (OTF instantiations)
+	const bool sliced = sh.bound && c->slicedVertex;
+	if (sliced && !sh.rangeValid)
+	{
+		sh.chunkLo = sh.chunkHi = 0;
+		if (primHi > primLo && c->nVsChunks)
+		{
+			uint32_t range[2] = { 0xFFFFFFFFu, 0u };
+			if (!c->dRangeScratch) CU(c, cudaMalloc((void**)&c->dRangeScratch, 8));
+			uint32_t* dRange = c->dRangeScratch;
+			CU(c, cudaMemcpyAsync(dRange, range, 8, cudaMemcpyHostToDevice, s));
+			prim_vertex_range_kernel<<<std::min<uint32_t>((primHi - primLo + 255) / 256, (uint32_t)c->numSMs * 8), 256, 0, s>>>(c->dTriRefs.ptr, primLo, primHi, dRange);
+			CU(c, cudaGetLastError());
+			CU(c, cudaMemcpyAsync(range, dRange, 8, cudaMemcpyDeviceToHost, s));
+			CU(c, cudaStreamSynchronize(s));
+			if (range[0] <= range[1])
+			{
+				// chunks are in ascending order of their first transformed-vertex index
+				const auto& cs = c->vsChunkStart;
+				sh.chunkLo = (uint32_t)(std::upper_bound(cs.begin(), cs.end(), range[0]) - cs.begin()) - 1u;
+				sh.chunkHi = (uint32_t)(std::upper_bound(cs.begin(), cs.end(), range[1]) - cs.begin());
+			}
+		}
+		sh.rangeValid = true;
+	}
+
+	b2r_context::Slot& slot = c->slots[c->seq % kRing];
+	if (slot.pending)
+	{
+		CU(c, cudaEventSynchronize(slot.done));
+		int r = harvestSlot(c, slot); if (r) return r;
+	}
+	slot.timed = c->stageTimers != 0;
+	slot.exchanged = slot.timed && sh.bound;
+	memcpy(slot.hViewProj, rc.viewProj, 64);
+	if (c->meshStaticDirty)
+	{
+		// camera-independent per-mesh constants.  The copy goes to the caller's stream, which has joined every frame
+		// enqueued so far (their constants kernels have read the old table); the ring streams fork from it below.
+		if (slot.hStaticCap < c->meshes.size())
+		{
+			if (slot.hStatic) cudaFreeHost(slot.hStatic);
+			slot.hStaticCap = std::max<size_t>(c->meshes.size() * 2, 16);
+			CU(c, cudaMallocHost((void**)&slot.hStatic, slot.hStaticCap * sizeof(MeshStatic)));
+		}
+		c->anyDiffuse = false;
+		for (size_t m = 0; m < c->meshes.size(); ++m)
+		{
+			const HostMesh& hm = c->meshes[m];
+			MeshStatic& ms = slot.hStatic[m];
+			memcpy(ms.world, hm.world, 64);
+			ms.vtxInBase = hm.vtxInBase; ms.vtxOutBase = hm.vtxOutBase; ms.nVertices = hm.nVertices;
+			ms.idxBase = hm.idxBase; ms.nTris = hm.nTris; ms.primBase = hm.primBase;
+			const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);      // CUDARenderer.cu:559-571
+			ms.tex[0] = d ? hm.texIds[0] : -1;
+			ms.tex[1] = n ? hm.texIds[1] : -1;
+			ms.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
+			ms.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
+			ms.pad[0] = ms.pad[1] = 0;
+			c->anyDiffuse |= d;
+		}
+		CU(c, c->dMeshStatic.reserve(std::max<size_t>(c->meshes.size(), 1), s));
+		if (!c->meshes.empty())
+			CU(c, cudaMemcpyAsync(c->dMeshStatic.ptr, slot.hStatic, c->meshes.size() * sizeof(MeshStatic), cudaMemcpyHostToDevice, s));
+		c->vtxNeedsFork = true;
+		c->meshStaticDirty = false;
+	}
+	if (c->vtxNeedsFork)
+	{
+		// after an idle point (or the copy above): every ring stream is ordered behind what the caller's stream holds now
+		CU(c, cudaEventRecord(c->forkEv, s));
+		for (int i = 0; i < D; ++i) c->ringNeedsFork[i] = true;
+		c->vtxNeedsFork = false;
+	}
+	if (c->ringNeedsFork[k])
+	{
+		CU(c, cudaStreamWaitEvent(rs, c->forkEv, 0));
+		c->ringNeedsFork[k] = false;
+	}
+	bool waitedPrev = false;
+	if (slot.timed && c->ringPrev >= 0 && c->ringPrev != k)
+	{
+		CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0));      // serial frames while the stages are timed
+		waitedPrev = true;
+	}
+#define RING_STAGE_EVENT(i) do { if (slot.timed) CU(c, cudaEventRecord(slot.ev[(i)], rs)); } while (0)
+	RING_STAGE_EVENT(0);
+	const uint32_t nMeshes = (uint32_t)c->meshes.size();
+	c->geoIdx = k;
+	float4* pos4 = c->dPos4[k].ptr;
+	MeshConst* meshConst = c->dMeshConst[k].ptr;
+	{
+		// clear + constants, then the vertex stage (all chunks, or the chunks of this rank's primitive slice)
+		const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (nMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
+		CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(std::max<uint32_t>(clearCtas, 1u)), dim3(256), 0, rs, tileCount, tiles, B.counters, B.frameInfo, (uint32_t)kInfoWords,
+			kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
+			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
+		++c->kernelsLaunched;
+		const uint32_t cLo = sliced ? sh.chunkLo : 0u, cHi = sliced ? sh.chunkHi : c->nVsChunks;
+		if (cHi > cLo)
+		{
+			CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(cHi - cLo), dim3(kChunk), 0, rs, c->dVsChunks.ptr + cLo, meshConst, c->dPosIn.ptr, pos4));
+			++c->kernelsLaunched;
+		}
+	}
+	RING_STAGE_EVENT(1);
+	if (c->nTriChunks)
+	{
+		if (primHi > primLo)
+		{
+			CU(c, launchFrameKernel(c, triangle_setup_kernel, dim3((primHi - primLo + kChunk - 1) / kChunk), dim3(kChunk), 0, rs, c->dTriRefs.ptr, pos4,
+				B.rects.ptr, tileCount, B.bigList.ptr, B.counters, primLo, primHi, fp));
+			++c->kernelsLaunched;
+		}
+		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, rs, B.bigList.ptr, B.counters, B.rects.ptr, tileCount, fp));
+		++c->kernelsLaunched;
+	}
+	RING_STAGE_EVENT(2);
+	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, rs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
+		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
+		B.midTiles.ptr, B.longTiles.ptr, B.smallTiles.ptr, B.counters, B.frameInfo));
+	++c->kernelsLaunched;
+	PeerFlags pf{};
+	if (sh.bound)
+	{
+		for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(p == sh.self ? sh.arena : sh.peerArena[p]);
+		// the peers must have finished frame f-D (their raster kernels read the set this frame is about to store into)
+		if (sh.frame >= (uint32_t)D)
+		{
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, rs, pf, (uint32_t)sh.self, (uint32_t)sh.n, 16u, sh.frame - (uint32_t)D + 1u, 0u, 1u, B.frameInfo + 7, 0u));
+			++c->kernelsLaunched;
+		}
+		ShardInbox inbox{};
+		for (int p = 0; p < sh.n; ++p)
+		{
+			uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
+			inbox.tileCount[p] = sh.inboxCount(base, k, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, k, sh.self);
+		}
+		CU(c, launchFrameKernel(c, shard_push_heads_kernel, dim3((tiles + 255) / 256), dim3(256), 0, rs, tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n));
+		++c->kernelsLaunched;
+	}
+	RING_STAGE_EVENT(3);
+	if (c->nPrims)
+	{
+		const uint32_t primBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+		CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, rs, B.rects.ptr, primLo, primHi, tileOffset,
+			B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp));
+		++c->kernelsLaunched;
+	}
+	RING_STAGE_EVENT(4);
+	if (c->sortBins && c->nPrims)
+	{
+		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs); if (r) return r;
+		c->kernelsLaunched += 3;
+	}
+	if (sh.bound && c->nPrims)
+	{
+		ShardRegions R{};
+		for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], k, sh.self);
+		CU(c, launchFrameKernel(c, shard_push_lists_kernel, dim3((tiles + 7) / 8), dim3(256), 0, rs, tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, B.frameInfo));
+		++c->kernelsLaunched;
+	}
+	RING_STAGE_EVENT(5);
+	{
+		RasterArgs A{};
+		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo;
+		if (sh.bound) c->colourIdx = (int)(sh.frame & 1u);       // every rank writes rank 0's surface `frame & 1`
+		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
+		{
+			// this surface is still being copied to the host by an earlier b2r_present_async (sharded: rank 0 arrives at
+			// the barrier below only after that copy, so no peer overwrites pixels in flight)
+			CU(c, cudaStreamWaitEvent(rs, c->copyDone[c->colourIdx], 0));
+			c->copyPending[c->colourIdx] = false;
+		}
+		A.framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->colourIdx];
+		c->lastColourIdx = c->colourIdx;
+		const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
+		if (sh.bound)
+		{
+			ShardTable T{};
+			for (int p = 0; p < sh.n; ++p)
+			{
+				T.tileCount[p] = sh.inboxCount(sh.arena, k, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, k, p);
+				T.binIds[p] = (p == sh.self) ? sh.binIds(sh.arena, k) : sh.region(sh.arena, k, p);
+			}
+			A.framebuffer = sh.colourBase + (size_t)(sh.frame & 1u) * c->width * c->height;
+			// "lists ready": nobody reads the lists a peer pushed before that peer has sorted and pushed them
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, rs, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7, 0u));
+			++c->kernelsLaunched;
+			RING_STAGE_EVENT(8);
+			A.shard = T;
+			RING_STAGE_EVENT(7);
+		}
+		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
+		// raster kernels in frame order: one depth surface, two colour surfaces, monotonic epochs
+		if (!waitedPrev && c->ringPrev >= 0 && c->ringPrev != k) CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0));
+		if (owned)
+		{
+			CU(c, launchRaster(c, dim3(owned, fp.subX * fp.subY), rs, A, fp, rc.vis != 0 || c->anyDiffuse, sliced));
+			++c->kernelsLaunched;
+		}
+		if (sh.bound)
+		{
+			RING_STAGE_EVENT(9);
+			++sh.frame;
+		}
+	}
+	uint32_t* landedFlag = nullptr;
+	if (sh.bound)
+		landedFlag = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]) + 8 + sh.self;
+	RING_STAGE_EVENT(6);
+#undef RING_STAGE_EVENT
+	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, rs, B.frameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8),
+		landedFlag, sh.frame, pf, sh.bound ? (uint32_t)sh.n : 0u, (uint32_t)sh.self));
+	++c->kernelsLaunched;
+	CU(c, cudaEventRecord(c->ringDone[k], rs));
+	c->ringPrev = k;
+	CU(c, cudaEventRecord(slot.done, rs));
+	// the caller's stream observes the frame (events it records, Present, read-backs) without holding back later frames
+	CU(c, cudaStreamWaitEvent(s, c->ringDone[k], 0));
 	CU(c, cudaGetLastError());
 	slot.pending = true;
 	++c->seq;
@@ -711,7 +1028,7 @@ int enqueueColourWait(b2r_context* c)
 	if (!sh.bound || sh.self != 0 || sh.waitedFrame == sh.frame) return B2R_OK;
 	PeerFlags pf{};
 	for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(p == sh.self ? sh.arena : sh.peerArena[p]);
-	CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, c->stream, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame, 0u, 1u, sh.hTimeout));
+	CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, c->stream, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame, 0u, 1u, sh.hTimeout, 1u));
 	sh.waitedFrame = sh.frame;
 	return B2R_OK;
 }
@@ -730,6 +1047,7 @@ int validateFrame(b2r_context* c)
 			return fail(c, B2R_E_STATE, "sharded front end: a peer rank's colours did not arrive within 4 s");
 		}
 		c->vtxNeedsFork = true; c->rasterPending[0] = c->rasterPending[1] = false; c->listsReadyPending[0] = c->listsReadyPending[1] = false;
+		c->ringPrev = -1;
 		for (uint64_t k = 0; k < kRing; ++k)
 		{
 			b2r_context::Slot& slot = c->slots[(c->seq + k) % kRing];     // oldest first
@@ -834,6 +1152,8 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	if (const char* e = getenv("B2R_PDL")) c->usePdl = atoi(e) != 0;                           // debugging aid: programmatic dependent launch
 	if (const char* e = getenv("B2R_OVERLAP_FRONT")) c->overlapFront = atoi(e) != 0;           // see B2R_OPT_OVERLAP_FRONT
 	if (const char* e = getenv("B2R_OVERLAP_FRONT_SHARDED")) c->overlapFrontSharded = atoi(e) != 0;
+	if (const char* e = getenv("B2R_FRAME_RING")) { const int d = atoi(e); c->ringDepth = (d >= 2 && d <= kMaxFrameRing) ? d : 0; }   // see B2R_OPT_FRAME_RING
+	if (const char* e = getenv("B2R_SHARD_SLICED_VERTEX")) c->slicedVertex = atoi(e) != 0;       // see B2R_OPT_SHARD_SLICED_VERTEX
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));
@@ -857,6 +1177,11 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 		CUC(cudaEventCreateWithFlags(&c->frontDone[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&c->rasterDone[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&c->listsReady[i], cudaEventDisableTiming));
+	}
+	for (int i = 0; i < kMaxFrameRing; ++i)
+	{
+		CUC(cudaStreamCreateWithFlags(&c->ringStream[i], cudaStreamNonBlocking));
+		CUC(cudaEventCreateWithFlags(&c->ringDone[i], cudaEventDisableTiming));
 	}
 	for (auto& slot : c->slots)
 	{
@@ -884,6 +1209,12 @@ void b2r_destroy(b2r_context* c)
 	if (c->vtxStream) { cudaStreamSynchronize(c->vtxStream); cudaStreamDestroy(c->vtxStream); }
 	if (c->frontStream) { cudaStreamSynchronize(c->frontStream); cudaStreamDestroy(c->frontStream); }
 	if (c->forkEv) cudaEventDestroy(c->forkEv);
+	for (int i = 0; i < kMaxFrameRing; ++i)
+	{
+		if (c->ringStream[i]) { cudaStreamSynchronize(c->ringStream[i]); cudaStreamDestroy(c->ringStream[i]); }
+		if (c->ringDone[i]) cudaEventDestroy(c->ringDone[i]);
+	}
+	cudaFree(c->dRangeScratch);
 	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->frontDone[i]) cudaEventDestroy(c->frontDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
@@ -1037,9 +1368,45 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_PACKED_OUTPUT: c->packedOutput = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_VERTEX: c->overlapVertex = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_FRONT: c->overlapFront = value ? 1 : 0; break;
+	case B2R_OPT_FRAME_RING:
+	case B2R_OPT_SHARD_SLICED_VERTEX:
+	{
+		// both change which buffers / streams a frame uses: only between frames, and not while the shared arena exists
+		if (option == B2R_OPT_FRAME_RING && value != 0 && (value < 2 || value > kMaxFrameRing))
+			return fail(c, B2R_E_INVALID, "frame ring depth must be 0 (off) or 2..%d", kMaxFrameRing);
+		if (c->shard.prepared) return fail(c, B2R_E_STATE, "set this option before b2r_shard_prepare");
+		CU(c, cudaSetDevice(c->device));
+		int r = validateFrame(c); if (r) return r;
+		if (option == B2R_OPT_FRAME_RING) { c->ringDepth = value; c->sceneDirty = true; }
+		else c->slicedVertex = value ? 1 : 0;
+		break;
+	}
 	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
 	}
 	if (c->ownerRank >= c->ownerCount) { /* tolerated while the pair is being set; checked at render */ }
+	return B2R_OK;
+}
+
+int b2r_get_option(b2r_context* c, int option, int* value)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!value) return fail(c, B2R_E_INVALID, "null output");
+	switch (option)
+	{
+	case B2R_OPT_FILL_RULE_TOP_LEFT: *value = c->fillTopLeft; break;
+	case B2R_OPT_TILE_OWNER_RANK: *value = c->ownerRank; break;
+	case B2R_OPT_TILE_OWNER_COUNT: *value = c->ownerCount; break;
+	case B2R_OPT_DEBUG_SURFACES: *value = c->debugSurfaces; break;
+	case B2R_OPT_STAGE_TIMERS: *value = c->stageTimers; break;
+	case B2R_OPT_SORT_BINS: *value = c->sortBins; break;
+	case B2R_OPT_COUNT_FRAGMENTS: *value = c->countFragments; break;
+	case B2R_OPT_PACKED_OUTPUT: *value = c->packedOutput; break;
+	case B2R_OPT_OVERLAP_VERTEX: *value = c->overlapVertex; break;
+	case B2R_OPT_OVERLAP_FRONT: *value = c->overlapFront; break;
+	case B2R_OPT_FRAME_RING: *value = c->ringDepth; break;
+	case B2R_OPT_SHARD_SLICED_VERTEX: *value = c->slicedVertex; break;
+	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
+	}
 	return B2R_OK;
 }
 
@@ -1130,6 +1497,8 @@ int b2r_read_overtex(b2r_context* c, int id, float* out18)
 	int r = validateFrame(c); if (r) return r;
 	const HostMesh& hm = c->meshes[id];
 	if (!hm.nVertices) return B2R_OK;
+	if (c->ringDepth && c->shard.bound && c->slicedVertex)
+		return fail(c, B2R_E_STATE, "read_overtex: with the sliced vertex stage a rank holds only the transformed vertices of its own primitive slice");
 	CU(c, c->dOvertexScratch.reserve((size_t)hm.nVertices * 18, c->stream));
 	const FrameParams fp = makeParams(c, c->last);
 	overtex_kernel<<<(hm.nVertices + 255) / 256, 256, 0, c->stream>>>(c->dMeshConst[c->geoIdx].ptr, (uint32_t)id, c->dIVertex.ptr, c->dPos4[c->geoIdx].ptr, c->dOvertexScratch.ptr, fp);
@@ -1319,7 +1688,8 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	const size_t def = std::max<size_t>((size_t)1 << 22, (c->nPrims + count - 1) / count * 4);
 	sh.listCap = ((listCapacity ? (size_t)listCapacity : def) + 63) & ~(size_t)63;
 	sh.setBytes = ((size_t)(2 + 2 * count) * sh.tilesPad + sh.listCap * (size_t)(1 + count)) * 4;
-	const size_t bytes = 256 + 2 * sh.setBytes;
+	sh.nSets = c->ringDepth ? c->ringDepth : 2;
+	const size_t bytes = 256 + (size_t)sh.nSets * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));
 	CU(c, cudaMemset(sh.arena, 0, bytes));
 	CU(c, cudaMallocHost((void**)&sh.hTimeout, 8));

@@ -46,8 +46,21 @@ __global__ void __launch_bounds__(256) split_positions_kernel(const float2* __re
 	posIn[first + i] = make_float4(a.x, a.y, b.x, 1.f);
 }
 
-// vertex transform: one CTA per chunk of 256 vertices of one mesh; 16 B in, 16 B out, coalesced.
 // clip = WVP * (p, 1); ndc = clip.xyz / clip.w (IEEE); w kept.  GetNDCVertex, CUDAROPs.cu:99-107.
+// One function for every place a position is transformed (the vertex stage, and the raster kernel when it
+// transforms the vertices of a list entry itself - sharded front end with a sliced vertex stage), hence the same bits.
+__device__ __forceinline__ float4 transformPosition(const float* m /*WVP, data[col][row]*/, float x, float y, float z)
+{
+	const float cx = mulRow4(m, 0, x, y, z);
+	const float cy = mulRow4(m, 1, x, y, z);
+	const float cz = mulRow4(m, 2, x, y, z);
+	const float cw = mulRow4(m, 3, x, y, z);
+	float4 p;
+	p.x = __fdiv_rn(cx, cw); p.y = __fdiv_rn(cy, cw); p.z = __fdiv_rn(cz, cw); p.w = cw;
+	return p;
+}
+
+// vertex transform: one CTA per chunk of 256 vertices of one mesh; 16 B in, 16 B out, coalesced.
 __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
 	const float4* __restrict__ posIn, float4* __restrict__ pos4)
@@ -60,13 +73,22 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	if (threadIdx.x < ch.count) in = __ldcs(posIn + (size_t)ch.inStart + threadIdx.x);
 	__syncthreads();
 	if (threadIdx.x >= ch.count) return;
-	const float cx = mulRow4(sMat, 0, in.x, in.y, in.z);
-	const float cy = mulRow4(sMat, 1, in.x, in.y, in.z);
-	const float cz = mulRow4(sMat, 2, in.x, in.y, in.z);
-	const float cw = mulRow4(sMat, 3, in.x, in.y, in.z);
-	float4 p;
-	p.x = __fdiv_rn(cx, cw); p.y = __fdiv_rn(cy, cw); p.z = __fdiv_rn(cz, cw); p.w = cw;
-	pos4[(size_t)ch.outStart + threadIdx.x] = p;
+	pos4[(size_t)ch.outStart + threadIdx.x] = transformPosition(sMat, in.x, in.y, in.z);
+}
+
+// sharded front end with a sliced vertex stage: the range of transformed-vertex indices the primitives
+// [primLo, primHi) refer to (static: evaluated once per scene and slice).  out[0] = min (preset to 0xFFFFFFFF), out[1] = max (preset to 0)
+__global__ void __launch_bounds__(256) prim_vertex_range_kernel(const uint4* __restrict__ triRefs, uint32_t primLo, uint32_t primHi, uint32_t* __restrict__ out)
+{
+	uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+	for (uint32_t p = primLo + blockIdx.x * blockDim.x + threadIdx.x; p < primHi; p += gridDim.x * blockDim.x)
+	{
+		const uint4 t = __ldg(triRefs + p);
+		lo = min(lo, min(t.x, min(t.y, t.z)));
+		hi = max(hi, max(t.x, max(t.y, t.z)));
+	}
+	lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+	if ((threadIdx.x & 31u) == 0u && lo <= hi) { atomicMin(out, lo); atomicMax(out + 1, hi); }
 }
 
 // the attribute half of GetNDCVertex (CUDAROPs.cu:108-115) for ONE vertex record
@@ -216,16 +238,20 @@ __global__ void __launch_bounds__(64) build_constants_kernel(const float* __rest
 // end of frame: the frame's counters go to the pinned host slot (zero-copy write).  Sharded front end: the same
 // kernel tells rank 0 that this rank's colours of the frame are in rank 0's surface (the raster kernel before it
 // in the stream has completed, so its NVLink stores have landed).
+// Frame ring + sharded front end: it also tells EVERY rank that this rank has finished the frame (flag words 16..23),
+// i.e. no longer reads the list set of the frame's ring slot - what a peer waits for before it stores the lists of a
+// later frame into that set (doneRanks = 0: no such signal).
 __global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words,
-	uint32_t* landedFlag, uint32_t epoch)
+	uint32_t* landedFlag, uint32_t epoch, PeerFlags donePf, uint32_t doneRanks, uint32_t self)
 {
 	pdlPrologue();
 	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];      // visible to the host once the frame's `done` event has completed
+	if ((landedFlag || doneRanks) && threadIdx.x == 0) __threadfence_system();
+	__syncwarp();
 	if (landedFlag && threadIdx.x == 0)
-	{
-		__threadfence_system();
 		*reinterpret_cast<volatile uint32_t*>(landedFlag) = epoch;
-	}
+	if (threadIdx.x < doneRanks)
+		*reinterpret_cast<volatile uint32_t*>(donePf.flags[threadIdx.x] + 16 + self) = epoch;
 }
 
 // Warp-level binning of up to 32 small rectangles (one per lane, rectangle = inclusive tile range,
@@ -691,10 +717,14 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
+// earlyTrigger = 0 (frame ring): the kernel does not release its programmatic dependents before it exits - the CTAs of
+// the raster kernel behind a barrier would otherwise become resident and sit out the wait for the slowest peer on
+// SM slots that the front ends of the following frames (other ring streams) could use.
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch,
-	uint32_t signal, uint32_t wait, unsigned long long* timeoutFlag /*device frameInfo[7] or a pinned host word*/)
+	uint32_t signal, uint32_t wait, unsigned long long* timeoutFlag /*device frameInfo[7] or a pinned host word*/, uint32_t earlyTrigger)
 {
-	pdlPrologue();
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	if (earlyTrigger) asm volatile("griddepcontrol.launch_dependents;");
 	const uint32_t lane = threadIdx.x;
 	__threadfence_system();
 	if (signal && lane < n)

@@ -25,6 +25,7 @@ struct RasterArgs
 	const uint32_t* binIds;
 	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
+	const float4* posIn;        // resident model-space positions (x, y, z, 1): read instead of pos4 by the OTF instantiations
 	const float2* ivertex;      // resident IVertex records (7 float2 each)
 	const MeshConst* meshes;
 	const TexDesc* textures;
@@ -206,24 +207,65 @@ constexpr int kListChunk = 256;       // bin-list entries staged per iteration (
 #endif
 constexpr int kSmallArea = B2R_SMALL_AREA;   // bbox-in-tile areas up to this are rasterised by one thread
 
+// the three transformed positions {ndc.xyz, clip.w} of a primitive.  OTF = false: from the frame's pos4 stream.
+// OTF = true ("on the fly"; sharded front end with a sliced vertex stage, where a rank transforms only the
+// vertices its own primitive slice refers to): transformed here from the resident model-space positions with
+// the mesh's WVP - transformPosition() is the vertex stage's own function, so the bits are those of pos4.
+constexpr uint32_t kSmemMeshes = 4;     // OTF: the WVP matrices of the first meshes are staged in shared memory
+template <bool OTF>
+__device__ __forceinline__ void fetchPositions(const RasterArgs& A, const float (*sWvp)[16], const uint4& tr, float4& p0, float4& p1, float4& p2)
+{
+	if (OTF)
+	{
+		const MeshConst* mc = A.meshes + tr.w;
+		const uint32_t inDelta = __ldg(&mc->vtxInBase) - __ldg(&mc->vtxOutBase);     // transformed-stream index -> input record (mod 2^32)
+		const float4 a = __ldg(A.posIn + (tr.x + inDelta)), b = __ldg(A.posIn + (tr.y + inDelta)), c = __ldg(A.posIn + (tr.z + inDelta));
+		if (tr.w < kSmemMeshes)
+		{
+			const float* m = sWvp[tr.w];
+			p0 = transformPosition(m, a.x, a.y, a.z);
+			p1 = transformPosition(m, b.x, b.y, b.z);
+			p2 = transformPosition(m, c.x, c.y, c.z);
+		}
+		else
+		{
+			const float4* w4 = reinterpret_cast<const float4*>(mc->wvp);       // MeshConst is 208 bytes, wvp at offset 0: 16-byte aligned
+			const float4 c0 = __ldg(w4), c1 = __ldg(w4 + 1), c2 = __ldg(w4 + 2), c3 = __ldg(w4 + 3);
+			const float m[16] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w };
+			p0 = transformPosition(m, a.x, a.y, a.z);
+			p1 = transformPosition(m, b.x, b.y, b.z);
+			p2 = transformPosition(m, c.x, c.y, c.z);
+		}
+	}
+	else
+	{
+		p0 = __ldg(A.pos4 + tr.x); p1 = __ldg(A.pos4 + tr.y); p2 = __ldg(A.pos4 + tr.z);
+	}
+}
+
 // TEXTURED = false is the light variant for frames in which no mesh has a diffuse map and the
 // visualisation is PBR (vertex colours only): the texture/normal-mapping path is compiled out, which
 // frees enough registers for 6 resident CTAs per SM instead of 4.
-template <bool TOPLEFT, bool COUNT, bool TEXTURED>
+template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF = false>
 #ifndef B2R_RASTER_LIGHT_CTAS
 #define B2R_RASTER_LIGHT_CTAS 6
 #endif
 #ifndef B2R_RASTER_FULL_CTAS
 #define B2R_RASTER_FULL_CTAS 4
 #endif
-__global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS : B2R_RASTER_LIGHT_CTAS) raster_shade_kernel(RasterArgs A, FrameParams fp)
+#ifndef B2R_RASTER_LIGHT_OTF_CTAS
+#define B2R_RASTER_LIGHT_OTF_CTAS 5      // the light variant that also transforms its vertices: 48 registers instead of 40
+#endif
+__global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS : (OTF ? B2R_RASTER_LIGHT_OTF_CTAS : B2R_RASTER_LIGHT_CTAS)) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
 	pdlPrologue();
 	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
 	__shared__ uint32_t sNumBig[2];                    // big-triangle count of the current / the next list chunk
+	__shared__ float sWvp[OTF ? kSmemMeshes : 1][16];  // OTF: WVP of the first meshes (visible after the barriers that precede the list sweep)
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
+	if (OTF && threadIdx.x < min(fp.nMeshes, kSmemMeshes) * 16u) sWvp[threadIdx.x >> 4][threadIdx.x & 15u] = A.meshes[threadIdx.x >> 4].wvp[threadIdx.x & 15u];
 	const uint32_t ownedIdx = blockIdx.x;
 	const uint32_t bin = fp.ownerRank + ownedIdx * fp.ownerCount;
 	uint32_t binX, subX;
@@ -293,7 +335,8 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS
 		// rebuild the screen-space triangle from the static reference + the transformed positions
 		// (same code, hence the same bits, wherever a triangle is expanded)
 		const uint4 tr = __ldg(A.triRefs + prim);
-		const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
+		float4 p0, p1, p2;
+		fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
 		TriRecord r;
 		rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
 		// candidate pixels = the record's conservative box clipped to this CTA's block; the box
@@ -452,7 +495,8 @@ __global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS
 		prim = (uint32_t)best;
 		depthOut = (int)(uint32_t)(best >> 32);
 		const uint4 tr = __ldg(A.triRefs + prim);
-		const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
+		float4 p0, p1, p2;
+		fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
 		TriShared t;
 		{
 			TriRecord r;

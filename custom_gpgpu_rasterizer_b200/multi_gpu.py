@@ -98,6 +98,12 @@ def prim_slice(n_prims: int, rank: int, world: int, block: int = 256):
     return lo, hi
 
 
+def check_shard_modes(modes) -> None:
+    """Every rank of a sharded group must run the same frame-ring depth and vertex-stage mode."""
+    if any(m != modes[0] for m in modes):
+        raise RuntimeError(f"ranks disagree on (B2R_OPT_FRAME_RING, B2R_OPT_SHARD_SLICED_VERTEX): {list(modes)}")
+
+
 class ShardedSortFirst:
     """Sharded front end: exchange the CUDA-IPC handles once; afterwards every Renderer.render() on every
     rank is one frame of the distributed pipeline and the composed image lives on rank 0."""
@@ -111,7 +117,10 @@ class ShardedSortFirst:
         arena, colour = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
         renderer._check(_lib.lib.b2r_shard_prepare(renderer.handle, rank, world, list_capacity, arena, colour))
         handles: List[Optional[tuple]] = [None] * world
-        dist.all_gather_object(handles, (bytes(arena), bytes(colour)))
+        # the layout of the shared arena depends on the frame-ring depth, the raster kernel on the sliced vertex stage
+        mode = (renderer.get_option(_lib.OPT_FRAME_RING), renderer.get_option(_lib.OPT_SHARD_SLICED_VERTEX))
+        dist.all_gather_object(handles, (bytes(arena), bytes(colour), mode))
+        check_shard_modes([h[2] for h in handles])
         all_arenas = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(h[0] for h in handles))
         colour0 = (C.c_ubyte * 64).from_buffer_copy(handles[0][1])
         renderer._check(_lib.lib.b2r_shard_bind(renderer.handle, all_arenas, colour0))

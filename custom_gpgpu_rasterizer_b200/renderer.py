@@ -103,6 +103,11 @@ class Renderer:
     def set_option(self, option: int, value: int):
         self._check(lib.b2r_set_option(self._ctx, option, int(value)))
 
+    def get_option(self, option: int) -> int:
+        v = C.c_int(0)
+        self._check(lib.b2r_get_option(self._ctx, option, C.byref(v)))
+        return v.value
+
     def setup_bins(self, bins_x: int, bins_y: int, bin_w: int, bin_h: int, queue_cap: int = 256):
         self._check(lib.b2r_setup_bins(self._ctx, bins_x, bins_y, bin_w, bin_h, queue_cap))
         self.bins = (bins_x, bins_y, bin_w, bin_h)

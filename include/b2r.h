@@ -77,7 +77,21 @@ enum
 	 * unchanged.  Needs B2R_OPT_OVERLAP_VERTEX; ignored while B2R_OPT_STAGE_TIMERS is on.  With the sharded front
 	 * end (b2r_shard_*) a frame's front end additionally waits for the previous frame's "lists ready" barrier
 	 * before it stores into the peers' list sets.  Default 1. */
-	B2R_OPT_OVERLAP_FRONT = 11
+	B2R_OPT_OVERLAP_FRONT = 11,
+	/* frame ring, the alternative to the two options above (EXPERIMENTAL in round 1: written after the round's GPU budget
+	 * was spent, default 0 = off; also B2R_FRAME_RING=D in the environment).  Value D = 2..4: frame f runs from its
+	 * constants to its raster kernel on ring stream f % D and owns slot f % D of everything a frame writes, so the
+	 * geometry front ends of up to D consecutive frames are in flight at once; only the raster kernels are chained in
+	 * frame order.  Meant for the sharded front end (b2r_shard_*), where a rank's front end is a chain of short
+	 * latency-bound kernels: the arena then holds D list sets, every rank announces "frame done" to all ranks, and a
+	 * rank waits for the peers' announcement of frame f-D before it stores the lists of frame f into their set f % D.
+	 * Set it between frames and before b2r_shard_prepare.  Results are unchanged. */
+	B2R_OPT_FRAME_RING = 12,
+	/* sharded front end + frame ring only (EXPERIMENTAL, default 0; also B2R_SHARD_SLICED_VERTEX=1): the vertex stage
+	 * of a rank transforms only the vertices its own primitive slice refers to (1/n of the replicated work) and the
+	 * raster kernel transforms the three vertices of a list entry itself, with the vertex stage's own function on the
+	 * resident model-space positions - same bits.  b2r_read_overtex is not available in this mode. */
+	B2R_OPT_SHARD_SLICED_VERTEX = 13
 };
 
 /* stage indices for b2r_get_stage_ms */
@@ -129,6 +143,9 @@ int b2r_mesh_set_world(b2r_context* ctx, int mesh_id, const float world[16]);
 int b2r_mesh_clear_all(b2r_context* ctx);
 
 int b2r_set_option(b2r_context* ctx, int option, int value);
+/* current value of an option (the defaults of some options come from the environment, see above; the ranks of a
+ * sharded group must agree on B2R_OPT_FRAME_RING and B2R_OPT_SHARD_SLICED_VERTEX) */
+int b2r_get_option(b2r_context* ctx, int option, int* value);
 
 /* CUDARenderer::EnterValidRenderingState/Clear + Render (CUDARenderer.cu:374-381, 1626-1659, 207-354).
  * cam_pos / cam_fwd = Camera::GetPosition/GetForward, view_proj = projection * Inverse(lookAt)

@@ -139,3 +139,39 @@ def test_gloo_sharded_front_end_lists_concatenate_in_rank_order():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True and q.get(timeout=10) is True
+
+
+# ---- frame ring of the sharded front end: ordering rules under random timing (tests/ring_protocol_model.py)
+@pytest.mark.parametrize("ranks,depth", [(2, 2), (2, 3), (4, 3), (8, 3), (8, 4)])
+def test_frame_ring_rules_order_every_list_set_access(ranks, depth):
+    import ring_protocol_model as model
+    for seed in range(40):
+        bad, _ = model.simulate(ranks, depth, 24, np.random.default_rng(seed))
+        assert not bad, f"seed {seed}: {bad[:4]}"
+
+
+def test_frame_ring_model_has_teeth():
+    """Each rule is needed: without it the model finds an unordered access for some timing."""
+    import ring_protocol_model as model
+    found = {"no_done_wait": 0, "epoch_off_by_one": 0, "unchained_rasters": 0}
+    for seed in range(40):
+        rng = lambda: np.random.default_rng(seed)
+        found["no_done_wait"] += any(v[0] == "S1" for v in model.simulate(8, 3, 24, rng(), done_wait=False)[0])
+        found["epoch_off_by_one"] += any(v[0] == "S1" for v in model.simulate(8, 3, 24, rng(), done_lag=1)[0])
+        found["unchained_rasters"] += any(v[0] == "S3" for v in model.simulate(8, 3, 24, rng(), chain_rasters=False)[0])
+    assert all(n > 0 for n in found.values()), found
+
+
+def test_frame_ring_overlaps_front_ends():
+    """What the ring is for: with D frames in flight the steady-state frame time approaches the longest single stage
+    instead of the sum of the stages of one frame."""
+    import ring_protocol_model as model
+    serial = np.diff(model.simulate(8, 1, 40, np.random.default_rng(3), skew=0.0)[1])[10:].mean()
+    ring = np.diff(model.simulate(8, 3, 40, np.random.default_rng(3), skew=0.0)[1])[10:].mean()
+    assert ring < 0.75 * serial, (ring, serial)
+
+
+def test_shard_modes_must_agree():
+    mg.check_shard_modes([(3, 1), (3, 1)])
+    with pytest.raises(RuntimeError):
+        mg.check_shard_modes([(3, 1), (0, 1)])

@@ -25,6 +25,8 @@ if mode == "sharded":
     test_scenes.append(scenes.hostile_scene(640, 480, 600, seed=21))     # degenerate / non-finite triangles
 for sc in test_scenes:
     r = Renderer(sc.width, sc.height, device=local)
+    if rank == 0:
+        print(f"sort-first[{mode}] frame ring {r.get_option(_lib.OPT_FRAME_RING)}, sliced vertex stage {r.get_option(_lib.OPT_SHARD_SLICED_VERTEX)}")
     r.load_scene(sc)
     stream = torch.cuda.Stream()
     r.set_stream(stream.cuda_stream)
@@ -50,6 +52,7 @@ for sc in test_scenes:
     if rank == 0:
         got = r.framebuffer()
         full = Renderer(sc.width, sc.height, device=local)
+        full.set_option(_lib.OPT_FRAME_RING, 0)          # the single-GPU frame of record: serial-capable default scheduler, whatever the environment selects
         full.load_scene(sc)
         full.render(cam, sc.cull, sc.sample, sc.vis)
         want = full.framebuffer()
@@ -85,6 +88,7 @@ for sc in test_scenes:
         dist.barrier()
         if rank == 0:
             full = Renderer(sc.width, sc.height, device=local)
+            full.set_option(_lib.OPT_FRAME_RING, 0)
             full.load_scene(sc)
             bad = 0
             for cam_k, b in zip(cams, bufs):
