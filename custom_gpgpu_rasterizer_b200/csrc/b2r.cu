@@ -441,6 +441,44 @@ int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
 	return B2R_OK;
 }
 
+// camera-independent per-mesh constants (MeshStatic): uploaded only when the mesh list, a world matrix or the texture
+// set changed, through the frame slot's pinned staging buffer, on the caller's stream `s`.  The streams that run the
+// constants kernels must be ordered behind this copy: vtxNeedsFork.
+int uploadMeshStatic(b2r_context* c, b2r_context::Slot& slot, cudaStream_t s)
+{
+	if (slot.hStaticCap < c->meshes.size())
+	{
+		if (slot.hStatic) cudaFreeHost(slot.hStatic);
+		slot.hStatic = nullptr; slot.hStaticCap = 0;
+		const size_t cap = std::max<size_t>(c->meshes.size() * 2, 16);
+		CU(c, cudaMallocHost((void**)&slot.hStatic, cap * sizeof(MeshStatic)));
+		slot.hStaticCap = cap;
+	}
+	c->anyDiffuse = false;
+	for (size_t m = 0; m < c->meshes.size(); ++m)
+	{
+		const HostMesh& hm = c->meshes[m];
+		MeshStatic& ms = slot.hStatic[m];
+		memcpy(ms.world, hm.world, 64);
+		ms.vtxInBase = hm.vtxInBase; ms.vtxOutBase = hm.vtxOutBase; ms.nVertices = hm.nVertices;
+		ms.idxBase = hm.idxBase; ms.nTris = hm.nTris; ms.primBase = hm.primBase;
+		// CUDARenderer.cu:559-571: Norm only with Diff, Spec/Gloss only with Norm
+		const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);
+		ms.tex[0] = d ? hm.texIds[0] : -1;
+		ms.tex[1] = n ? hm.texIds[1] : -1;
+		ms.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
+		ms.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
+		ms.pad[0] = ms.pad[1] = 0;
+		c->anyDiffuse |= d;
+	}
+	CU(c, c->dMeshStatic.reserve(std::max<size_t>(c->meshes.size(), 1), s));
+	if (!c->meshes.empty())
+		CU(c, cudaMemcpyAsync(c->dMeshStatic.ptr, slot.hStatic, c->meshes.size() * sizeof(MeshStatic), cudaMemcpyHostToDevice, s));
+	c->vtxNeedsFork = true;
+	c->meshStaticDirty = false;
+	return B2R_OK;
+}
+
 // canonical (ascending primitive id) order of every tile list: the three tiers of the list sorter, working off the
 // work lists tile_scan_kernel built in the set's buffers
 int enqueueListSort(b2r_context* c, b2r_context::BinSet& B, uint32_t* tileCount, uint32_t* tileOffset, uint32_t* binIds, cudaStream_t s)
@@ -510,38 +548,7 @@ int enqueueFrame(b2r_context* c)
 	slot.timed = c->stageTimers != 0;
 	slot.exchanged = slot.timed && c->shard.bound;
 	memcpy(slot.hViewProj, rc.viewProj, 64);
-	if (c->meshStaticDirty)
-	{
-		// camera-independent per-mesh constants: only when the mesh list, a world matrix or the texture set changed
-		if (slot.hStaticCap < c->meshes.size())
-		{
-			if (slot.hStatic) cudaFreeHost(slot.hStatic);
-			slot.hStaticCap = std::max<size_t>(c->meshes.size() * 2, 16);
-			CU(c, cudaMallocHost((void**)&slot.hStatic, slot.hStaticCap * sizeof(MeshStatic)));
-		}
-		c->anyDiffuse = false;
-		for (size_t m = 0; m < c->meshes.size(); ++m)
-		{
-			const HostMesh& hm = c->meshes[m];
-			MeshStatic& ms = slot.hStatic[m];
-			memcpy(ms.world, hm.world, 64);
-			ms.vtxInBase = hm.vtxInBase; ms.vtxOutBase = hm.vtxOutBase; ms.nVertices = hm.nVertices;
-			ms.idxBase = hm.idxBase; ms.nTris = hm.nTris; ms.primBase = hm.primBase;
-			// CUDARenderer.cu:559-571: Norm only with Diff, Spec/Gloss only with Norm
-			const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);
-			ms.tex[0] = d ? hm.texIds[0] : -1;
-			ms.tex[1] = n ? hm.texIds[1] : -1;
-			ms.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
-			ms.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
-			ms.pad[0] = ms.pad[1] = 0;
-			c->anyDiffuse |= d;
-		}
-		CU(c, c->dMeshStatic.reserve(std::max<size_t>(c->meshes.size(), 1), s));
-		if (!c->meshes.empty())
-			CU(c, cudaMemcpyAsync(c->dMeshStatic.ptr, slot.hStatic, c->meshes.size() * sizeof(MeshStatic), cudaMemcpyHostToDevice, s));
-		c->vtxNeedsFork = true;       // the vertex stream must see this copy
-		c->meshStaticDirty = false;
-	}
+	if (c->meshStaticDirty) { int r = uploadMeshStatic(c, slot, s); if (r) return r; }
 	STAGE_EVENT(c, slot, 0);
 	const uint32_t nMeshes = (uint32_t)c->meshes.size();
 	const int g = (int)(c->seq & 1u);
@@ -826,38 +833,9 @@ int enqueueFrameRing(b2r_context* c)
 	slot.timed = c->stageTimers != 0;
 	slot.exchanged = slot.timed && sh.bound;
 	memcpy(slot.hViewProj, rc.viewProj, 64);
-	if (c->meshStaticDirty)
-	{
-		// camera-independent per-mesh constants.  The copy goes to the caller's stream, which has joined every frame
-		// enqueued so far (their constants kernels have read the old table); the ring streams fork from it below.
-		if (slot.hStaticCap < c->meshes.size())
-		{
-			if (slot.hStatic) cudaFreeHost(slot.hStatic);
-			slot.hStaticCap = std::max<size_t>(c->meshes.size() * 2, 16);
-			CU(c, cudaMallocHost((void**)&slot.hStatic, slot.hStaticCap * sizeof(MeshStatic)));
-		}
-		c->anyDiffuse = false;
-		for (size_t m = 0; m < c->meshes.size(); ++m)
-		{
-			const HostMesh& hm = c->meshes[m];
-			MeshStatic& ms = slot.hStatic[m];
-			memcpy(ms.world, hm.world, 64);
-			ms.vtxInBase = hm.vtxInBase; ms.vtxOutBase = hm.vtxOutBase; ms.nVertices = hm.nVertices;
-			ms.idxBase = hm.idxBase; ms.nTris = hm.nTris; ms.primBase = hm.primBase;
-			const bool d = texValid(c, hm.texIds[0]), n = d && texValid(c, hm.texIds[1]);      // CUDARenderer.cu:559-571
-			ms.tex[0] = d ? hm.texIds[0] : -1;
-			ms.tex[1] = n ? hm.texIds[1] : -1;
-			ms.tex[2] = (n && texValid(c, hm.texIds[2])) ? hm.texIds[2] : -1;
-			ms.tex[3] = (n && texValid(c, hm.texIds[3])) ? hm.texIds[3] : -1;
-			ms.pad[0] = ms.pad[1] = 0;
-			c->anyDiffuse |= d;
-		}
-		CU(c, c->dMeshStatic.reserve(std::max<size_t>(c->meshes.size(), 1), s));
-		if (!c->meshes.empty())
-			CU(c, cudaMemcpyAsync(c->dMeshStatic.ptr, slot.hStatic, c->meshes.size() * sizeof(MeshStatic), cudaMemcpyHostToDevice, s));
-		c->vtxNeedsFork = true;
-		c->meshStaticDirty = false;
-	}
+	// (the copy goes to the caller's stream, which has joined every frame enqueued so far - their constants kernels have
+	// read the old table; the ring streams fork from it below)
+	if (c->meshStaticDirty) { int r = uploadMeshStatic(c, slot, s); if (r) return r; }
 	if (c->vtxNeedsFork)
 	{
 		// after an idle point (or the copy above): every ring stream is ordered behind what the caller's stream holds now

@@ -10,6 +10,12 @@ B2R_FRAME_RING=3 timeout 600 python -m pytest tests/test_gpu_parity.py tests/tes
 B="timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-fill"
 $B > $O/bench_default.json 2> $O/bench_default.err
 for d in 2 3 4; do B2R_FRAME_RING=$d $B > $O/bench_ring$d.json 2> $O/bench_ring$d.err; done
+# BASELINE config 5 (views of the 172-instance scene): shorter frames, more launch-latency-bound - the ring may pay off on one GPU too
+timeout 200 python bench.py --workload views172 --steps 64 > $O/views_default.json 2> $O/views_default.err
+B2R_FRAME_RING=3 timeout 200 python bench.py --workload views172 --steps 64 > $O/views_ring3.json 2> $O/views_ring3.err
+for f in $O/views_*.json; do echo "$f: $(python -c "
+import json,sys
+d=json.loads(open('$f').read().strip().splitlines()[-1]); print(round(d['value'],1), d['unit'], 'e2e', round(d['e2e']['value'],1))" 2>&1 | tail -1)"; done | tee $O/views_summary.txt
 for f in $O/bench_*.json; do echo "$f: $(python - "$f" <<'PY'
 import json,sys
 try:
