@@ -20,6 +20,9 @@ from custom_gpgpu_rasterizer_b200.scenefile import MeshData
 NONE = 0xFFFFFFFF
 INT_MAX = 0x7FFFFFFF
 CLEAR = 0x003F3F3F        # default clear colour 0.25 (CUDARenderer.h:135) through the truncating pack
+# fragments (inside + z in [0,1]) of BASELINE config 4 at 3840x2160: the oracle's `frags_covered` for the 64-layer scene
+# (tests/test_cpu_oracle.py recomputes it when B2R_SLOW_TESTS=1)
+CONFIG4_FRAGMENTS = 530667984
 
 
 def sphere_sub_scene(full, sid: int, nv: int, nt: int):
@@ -56,6 +59,21 @@ def check_sphere_regions(full, fb, depth, winner, sids, nv: int, nt: int, fill_r
         assert np.array_equal(fb[reg], o["framebuffer"][reg]), f"sphere {sid}: colours differ from the oracle"
         compared += int(cov.sum())
     return compared
+
+
+def check_whole_frame(o, fb, depth, winner, counts, ids, visible: int):
+    """The product's surfaces and lists against the oracle's frame `o` of the same scene: winners, integer depth and
+    (untextured scene: no libm on the way) colours bit for bit, the per-tile sets equal, the lists ascending."""
+    assert visible == o["visible_tris"], f"visible triangles {visible}, oracle {o['visible_tris']}"
+    assert np.array_equal(winner, o["winner"]), f"winning primitive differs at {int((winner != o['winner']).sum())} pixels"
+    assert np.array_equal(depth, o["depth"]), f"integer depth differs at {int((depth != o['depth']).sum())} pixels"
+    assert np.array_equal(fb, o["framebuffer"]), f"colour differs at {int((fb != o['framebuffer']).sum())} pixels"
+    assert np.array_equal(counts, o["bin_counts"]), "per-tile list lengths differ"
+    # the oracle's lists are in submission order per tile (ascending already, but do not rely on it): sort segment-wise
+    offs = np.concatenate([[0], np.cumsum(o["bin_counts"].astype(np.int64))])
+    seg = np.repeat(np.arange(len(o["bin_counts"]), dtype=np.int64), o["bin_counts"].astype(np.int64))
+    want = o["bin_ids"].astype(np.int64)[np.lexsort((o["bin_ids"].astype(np.int64), seg))]
+    assert offs[-1] == ids.size and np.array_equal(ids.astype(np.int64), want), "tile lists differ from the oracle's sets in ascending order"
 
 
 def check_frame_invariants(fb, depth, winner):

@@ -154,9 +154,15 @@ def test_fullsize_helpers_on_a_small_grid_with_the_oracle_as_product():
     # the oracle's lists hold the same sets; bring them into the product's canonical order first
     ids = np.concatenate([np.sort(s) for s in oracle_lib.bin_sets(counts, F["bin_ids"])] or [np.zeros(0, np.uint32)])
     fullsize.check_lists(counts, offsets, ids, int(counts.sum()))
+    fullsize.check_whole_frame(F, F["framebuffer"], F["depth"], F["winner"], counts, ids, F["visible_tris"])
     with pytest.raises(AssertionError):
         bad = ids.copy(); bad[[5, 6]] = bad[[6, 5]]
         fullsize.check_lists(counts, offsets, bad, int(counts.sum()))
+    with pytest.raises(AssertionError):
+        fullsize.check_whole_frame(F, F["framebuffer"], F["depth"], F["winner"], counts, bad, F["visible_tris"])
+    with pytest.raises(AssertionError):
+        off = F["depth"].copy(); off[F["winner"] != fullsize.NONE] += 1
+        fullsize.check_whole_frame(F, F["framebuffer"], off, F["winner"], counts, ids, F["visible_tris"])
     with pytest.raises(AssertionError):
         wrong = F["framebuffer"].copy(); wrong[F["winner"] != fullsize.NONE] ^= 1
         fullsize.check_sphere_regions(full, wrong, F["depth"], F["winner"], [12], nv, nt, fill_rule=1)
@@ -167,3 +173,22 @@ def test_fullsize_helpers_on_a_small_grid_with_the_oracle_as_product():
     assert cov.mean() > 0.98
     assert np.array_equal(Q["framebuffer"][cov], o["framebuffer"][cov]) and np.array_equal(Q["depth"][cov], o["depth"][cov])
     assert np.array_equal(Q["winner"][cov].astype(np.int64), o["winner"][cov].astype(np.int64) + 14)
+
+
+@pytest.mark.skipif(os.environ.get("B2R_SLOW_TESTS") != "1", reason="~1 min of CPU: the oracle at BASELINE's full sizes (set B2R_SLOW_TESTS=1)")
+def test_fullsize_constants_from_the_oracle_at_full_size():
+    """The figures tests/test_gpu_zz_fullsize.py relies on, recomputed by the oracle at 3840x2160: the spheres of config 3 are
+    disjoint on screen with 2 pixels of margin, all 625 are visible, and config 4 has the fragment count of fullsize.CONFIG4_FRAGMENTS."""
+    import fullsize
+    from custom_gpgpu_rasterizer_b200 import scenes
+    sc = scenes.sphere_grid_scene(3840, 2160)
+    F = oracle_lib.render(sc, fill_rule=1)
+    assert (F["total_tris"], F["visible_tris"], int(F["bin_counts"].sum())) == (10_000_000, 4_909_458, 7_117_055)
+    sids = [0, 24, 600, 624, 12, 300, 324, 612, 312, 137, 401, 538]
+    assert fullsize.check_sphere_regions(sc, F["framebuffer"], F["depth"], F["winner"], sids, 8282, 16000, fill_rule=1) > 12 * 4000
+    won = F["winner"][F["winner"] != fullsize.NONE]
+    assert np.unique(won // 16000).size == 625
+    quads = scenes.fill_quads_scene(3840, 2160, layers=64, sample=1)
+    Q = oracle_lib.render(quads, fill_rule=1)
+    assert Q["frags_covered"] == Q["frags_passed"] == fullsize.CONFIG4_FRAGMENTS
+    assert int(Q["bin_counts"].sum()) == 2 * 64 * 240 * 135

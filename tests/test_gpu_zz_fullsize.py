@@ -8,6 +8,7 @@ import pytest
 
 import fullsize
 import oracle_lib
+import parity
 from custom_gpgpu_rasterizer_b200 import scenes
 
 pytestmark = pytest.mark.gpu
@@ -29,6 +30,8 @@ def test_config3_10m_triangles_4k_matches_oracle_per_sphere():
         fullsize.check_frame_invariants(fb, depth, winner)
         counts, offsets, ids = r.bin_lists()
         fullsize.check_lists(counts, offsets, ids, r.counters()["pairs"])
+        # the whole frame against the oracle's whole frame (the C restatement renders the 10 M triangles in ~5 s on one core)
+        fullsize.check_whole_frame(oracle_lib.render(sc, fill_rule=1), fb, depth, winner, counts, ids, visible)
         # corners, edge centres, the centre and a few others of the 25 x 25 grid
         sids = [0, 24, 600, 624, 12, 300, 324, 612, 312, 137, 401, 538]
         compared = fullsize.check_sphere_regions(sc, fb, depth, winner, sids, nv, nt, fill_rule=1)
@@ -67,7 +70,11 @@ def test_config4_64_layers_4k_equals_nearest_layer():
     assert cov.all()
     assert np.array_equal(winner[cov].astype(np.int64), o["winner"][cov].astype(np.int64) + 2 * (layers - 1)), "the nearest layer must win every pixel it covers"
     assert np.array_equal(depth[cov], o["depth"][cov]), "integer depth differs from the oracle's nearest layer"
-    assert np.array_equal(fb[cov], o["framebuffer"][cov]), "colours differ from the oracle's nearest layer"
+    # diffuse map only: no libm call on the way to the colour; asserted with north_star's tolerance (+-1 LSB, <= 0.1 % beyond)
+    parity.assert_colour_parity(fb, o["framebuffer"], None, "config 4 vs the oracle's nearest layer")
     assert c["pairs"] == 2 * layers * 240 * 135 and c["big_triangles"] == 2 * layers
-    # every layer covers the screen (a few pixels of the shared diagonal go to one triangle only): F is within 0.1 % of 64 W H
+    # every layer covers the screen but for the rows / columns the rounding of its corners costs it: F is within 0.1 % of
+    # 64 W H, and equals the oracle's count for the 64-layer scene (oracle_lib.render(sc)["frags_covered"], 27 s on one core,
+    # hence the constant)
     assert 0.999 * layers * sc.width * sc.height <= c["fragments"] <= layers * sc.width * sc.height
+    assert c["fragments"] == fullsize.CONFIG4_FRAGMENTS
