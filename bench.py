@@ -33,6 +33,7 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 from custom_gpgpu_rasterizer_b200 import scenes  # noqa: E402  (numpy only)
 
 WIDTH, HEIGHT = 3840, 2160
+METRIC = "frames/s at 4K (device-timed)"      # BASELINE.json's metric; the same string on both arms
 
 
 def load_peaks():
@@ -248,11 +249,11 @@ def run_reference(args, scene):
     mean_s, _ = cpu_reference_arm(scene, steps, warmup)
     fps = 1.0 / mean_s
     line = {
-        "impl": "reference", "metric": "frames/s at 4K (device-timed for the GPU arm; host steady_clock for this arm)",
+        "impl": "reference", "metric": METRIC, "timing": "host steady_clock around Render (this arm runs on the host cores)",
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean_s * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mtris_per_s": scene.n_tris / mean_s / 1e6,
-        "config": workload_config(args.workload, scene),
+        "config": dict(workload_config(args.workload, scene), parallelism="the reference's CPU renderer, one host thread (it is single-threaded)"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
                          "sample": f"full frame of the workload, {steps} frames after {warmup} warm-up; ERenderer.cpp restated (the in-tree file is stale and cannot compile); single-threaded like the reference",
                          "host_cores_available": os.cpu_count()},
@@ -479,10 +480,10 @@ def run_b200(args, scene):
     per_stage = {}
     for k, b in ab.items():
         t = stages["bin_scan"] + stages["bin_scatter"] + stages["bin_sort"] if k == "binning" else stages[stage_of[k]]
-        if k == "setup":
-            pass
+        # N ranks: the bytes are the whole job's, the stage time is a rank's (the ranks work side by side), so the
+        # denominator is the bandwidth of the N GPUs together
         per_stage[k] = {"ms": t, "algorithmic_bytes": b, "gbs": (b / 1e9) / (t / 1e3) if t > 0 else None,
-                        "frac_of_hbm_peak": ((b / 1e9) / (t / 1e3)) / peak if t > 0 else None}
+                        "frac_of_hbm_peak": ((b / 1e9) / (t / 1e3)) / (peak * world) if t > 0 else None}
     dominant = max(per_stage, key=lambda k: per_stage[k]["ms"])
     roof = per_stage[dominant]
     traffic = None
@@ -493,7 +494,7 @@ def run_b200(args, scene):
         pass
 
     line = {
-        "metric": "frames/s at 4K (device-timed)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up/bins/sorts primitive slice r, owners read the peers' lists over NVLink, colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather])),
@@ -501,9 +502,11 @@ def run_b200(args, scene):
         "visible_triangles": visible, "tile_pairs": pairs, "fragments": frags, "covered_pixels": covered_px,
         "list_sorter": {"tiles_sent_to_the_cta_sorter_by_the_warp_sorter": counters["sort_fallback_tiles"], "tiles_beyond_the_sorter": counters["unsorted_tiles"]},
         "stages_ms": stages, "stages": per_stage,
-        "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
-                     "traffic": traffic, "peak_source": peak_src,
-                     "note": "achieved = algorithmic bytes of SURVEY section 8d / stage time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},
+        "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak * world, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
+                     "traffic": traffic if world == 1 else None, "peak_source": peak_src + ("" if world == 1 else f" x {world} GPUs"),
+                     "note": "achieved = algorithmic bytes of SURVEY section 8d (the reference's record sizes: EFFECTIVE bandwidth, a stage that moves fewer bytes than "
+                             "the reference's layout can exceed 1; physical DRAM bytes of the stage per launch are in `traffic`, from the committed ncu capture) / stage "
+                             "time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},
         "e2e": {"value": args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 64,
                 "d2h_bytes_per_step": scene.width * scene.height * 4,
                 "note": "per frame: view-projection matrix from the host (zero-copy read; per-mesh constants are built on the device) + b2r_render + device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), wall clock over all frames incl. the final wait"},
