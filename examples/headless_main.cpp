@@ -86,9 +86,13 @@ int main(int argc, char** argv)
 	windowHelper.Resolution.Width = h.width; windowHelper.Resolution.Height = h.height;
 
 	CUDARenderer* pCudaRenderer = new CUDARenderer{ windowHelper };
+	// the veneer keeps the reference's convention (errors are printed, never thrown); a headless tool must not write a
+	// frame nobody rendered: no CUDA device (there is no CPU fallback) or a failed call ends the program
+	if (!pCudaRenderer->GetContext()) { fprintf(stderr, "headless_main: %s\n", pCudaRenderer->GetLastError()); delete pCudaRenderer; return 3; }
 	pCudaRenderer->SetupBins(IPoint2{ (int)h.binsX, (int)h.binsY }, IPoint2{ (int)h.binW, (int)h.binH }, h.queueCap);
 	pCudaRenderer->LoadScene(sm.GetSceneGraph(), tm);
 	pCudaRenderer->RenderAuto(sm, tm, &camera);
+	if (pCudaRenderer->GetLastError()[0]) { fprintf(stderr, "headless_main: %s\n", pCudaRenderer->GetLastError()); delete pCudaRenderer; return 3; }
 	printf("triangles %u visible %u\n", pCudaRenderer->GetTotalNumTriangles(), pCudaRenderer->GetTotalNumVisibleTriangles());
 
 	FILE* out = fopen(argv[2], "wb");

@@ -154,3 +154,32 @@ def test_synthetic_workloads_have_the_documented_shape():
     assert pos.shape[0] == 8282 and tris.shape[0] == 16000
     sc = scenes.fill_quads_scene(3840, 2160, layers=64)
     assert sc.n_tris == 128 and sc.n_vertices == 256               # config 4
+
+
+def test_every_entry_point_rejects_a_null_context():
+    """Thread-compatible per handle, `int` status everywhere: a null handle is B2R_E_INVALID, never a crash."""
+    for name, (_res, args) in _lib.ABI.items():
+        if name in ("b2r_create", "b2r_destroy", "b2r_last_error"):
+            continue
+        vals = [None if (a is C.c_void_p or a is C.c_char_p or hasattr(a, "contents")) else 0 for a in args]
+        assert getattr(_lib.lib, name)(*vals) == _lib.B2R_E_INVALID, name
+    _lib.lib.b2r_destroy(None)      # like delete: a null handle is fine
+
+
+def test_cpp_veneer_builds_and_fails_loudly_without_a_device(tmp_path):
+    """examples/headless_main.cpp (the reference's main loop against the veneer classes) compiles and links with g++ alone;
+    without a CUDA device it must end with an error and no frame dump - there is no CPU fallback."""
+    import subprocess
+    exe = str(tmp_path / "headless_main")
+    csrc = os.path.join(ROOT, "custom_gpgpu_rasterizer_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", os.path.join(ROOT, "examples", "headless_main.cpp"),
+                           "-I" + os.path.join(csrc, "host"), "-L" + csrc, "-lb2r", "-Wl,-rpath," + csrc, "-o", exe])
+    if _has_gpu():
+        pytest.skip("built; the run is covered by tests/test_gpu_veneer.py on a GPU box")
+    sc = scenes.random_triangles_scene(64, 48, 10, seed=1)
+    sp, op = str(tmp_path / "s.b2rs"), str(tmp_path / "o.raw")
+    with open(sp, "wb") as f:
+        f.write(sc.to_blob())
+    res = subprocess.run([exe, sp, op], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 3 and "no CPU fallback" in (res.stdout + res.stderr)
+    assert not os.path.exists(op)
