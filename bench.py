@@ -190,12 +190,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+ERE_REF = os.path.join(ROOT, "oracle", "_ref", "libere_ref.so")
+ERE_PORT = os.path.join(ROOT, "oracle", "liborc_erenderer.so")
+
+
 def cpu_reference_arm(scene, steps: int, warmup: int):
-    """The reference's CPU software path (ERenderer restatement, oracle/liborc_erenderer.so), 1 thread."""
-    lib_path = os.path.join(ROOT, "oracle", "liborc_erenderer.so")
-    if not os.path.exists(lib_path):
+    """The reference's CPU software path, one thread (it is single-threaded): Elite::Renderer::Render, steady_clock around
+    the call, scene load excluded.  Runs the reference's OWN renderer when it was built here (oracle/_ref/libere_ref.so =
+    CustomCUDARasterizer/ERenderer.cpp compiled unmodified by oracle/build_ref_erenderer.sh; kind "reference"), else the
+    restatement oracle/liborc_erenderer.so, which tests/test_cpu_erenderer.py pins against it bit for bit (kind "port").
+    Returns (mean seconds per frame, per-frame seconds, kind)."""
+    kind = "reference" if os.path.exists(ERE_REF) and not os.environ.get("B2R_CPU_BASELINE_PORT") else "port"
+    if kind == "port" and not os.path.exists(ERE_PORT):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liborc_erenderer.so"])
-    L = C.CDLL(lib_path)
+    L = C.CDLL(ERE_REF if kind == "reference" else ERE_PORT)
     L.ere_load.restype = C.c_void_p
     L.ere_load.argtypes = [C.c_char_p, C.c_uint64]
     L.ere_render.restype = C.c_double
@@ -206,10 +214,16 @@ def cpu_reference_arm(scene, steps: int, warmup: int):
     times = []
     for i in range(warmup + steps):
         t = L.ere_render(S, 0, 0xFFFFFFFF, 0, 0xFFFFFFFF)
+        if t < 0:
+            raise RuntimeError("the CPU renderer rejected the scene")
         if i >= warmup:
             times.append(t)
     L.ere_free(S)
-    return float(np.mean(times)), times
+    return float(np.mean(times)), times, kind
+
+
+CPU_KIND_NOTE = {"reference": "the reference's own Elite::Renderer (CustomCUDARasterizer/ERenderer.cpp compiled unmodified, oracle/build_ref_erenderer.sh)",
+                 "port": "ERenderer restatement (oracle/erenderer_oracle.cpp; bit-identical to the reference's renderer on tests/test_cpu_erenderer.py's scenes)"}
 
 
 def reference_cuda_arm(scene, frames: int, timeout_s: int):
@@ -246,7 +260,7 @@ def run_reference(args, scene):
         return
     # bounded: the full frame costs ~1 s on one core, so a handful of frames stays within minutes
     steps, warmup = min(args.steps, 5), min(args.warmup, 1)
-    mean_s, _ = cpu_reference_arm(scene, steps, warmup)
+    mean_s, _, kind = cpu_reference_arm(scene, steps, warmup)
     fps = 1.0 / mean_s
     line = {
         "impl": "reference", "metric": METRIC, "timing": "host steady_clock around Render (this arm runs on the host cores)",
@@ -254,8 +268,8 @@ def run_reference(args, scene):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mtris_per_s": scene.n_tris / mean_s / 1e6,
         "config": dict(workload_config(args.workload, scene), parallelism="the reference's CPU renderer, one host thread (it is single-threaded)"),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                         "sample": f"full frame of the workload, {steps} frames after {warmup} warm-up; ERenderer.cpp restated (the in-tree file is stale and cannot compile); single-threaded like the reference",
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
+                         "sample": f"full frame of the workload, {steps} frames after {warmup} warm-up; {CPU_KIND_NOTE[kind]}; single-threaded like the reference",
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -523,9 +537,9 @@ def run_b200(args, scene):
         line["view_parallel"] = view_parallel
         line["stages_ms_per_rank"] = stages_per_rank
     if world == 1 and not args.no_cpu_baseline:
-        mean_s, _ = cpu_reference_arm(scene, 3, 1)
-        line["cpu_baseline"] = {"value": 1.0 / mean_s, "unit": "frames/s", "cores": 1, "kind": "port",
-                                "sample": "the full frame of this workload, 3 frames after 1 warm-up, ERenderer restatement (oracle/erenderer_oracle.cpp), single-threaded like the reference",
+        mean_s, _, kind = cpu_reference_arm(scene, 3, 1)
+        line["cpu_baseline"] = {"value": 1.0 / mean_s, "unit": "frames/s", "cores": 1, "kind": kind,
+                                "sample": f"the full frame of this workload, 3 frames after 1 warm-up, {CPU_KIND_NOTE[kind]}, single-threaded like the reference",
                                 "mtris_per_s": scene.n_tris / mean_s / 1e6, "host_cores_available": os.cpu_count()}
     if world == 1 and args.workload == "spheres10m" and not args.no_fill:
         line["fill_test"] = fill_test(r.__class__, _lib, torch, dev, args, peak)

@@ -3,11 +3,15 @@
 // the CPU baseline.  Not part of the product; only bench.py's cpu_baseline / --impl reference
 // legs and tests/ use it.
 //
-// Why a restatement: the in-tree ERenderer.cpp is stale against its own headers
-// (GetVertexAmount / GetIndexAmount / GetTextures / GetWorldMatrix / IsDepthColour do not
-// exist, the file is excluded from the project, vcxproj:126-155) and cannot be compiled.
-// Parity status: UNPINNED - there is no runnable reference for this path; it follows the source
-// line by line (citations below) and is used for timing, not as a correctness oracle.
+// Why a restatement: the in-tree ERenderer.cpp is stale against its own headers (GetVertexAmount / GetIndexAmount /
+// GetTextures / GetWorldMatrix / IsDepthColour do not exist any more; the file is excluded from the project,
+// vcxproj:126-155), so it does not build with the reference's build system - and the restatement travels in this
+// repository, which the reference's sources must not.
+// Parity status: PINNED.  oracle/build_ref_erenderer.sh compiles the reference's ERenderer.cpp UNMODIFIED (with its own
+// Camera / Light / SceneGraph / Texture sources and math headers) against a reconstruction of the two stale interfaces
+// (oracle/ere_shim/) into oracle/_ref/libere_ref.so; tests/test_cpu_erenderer.py compares this restatement with it bit
+// for bit (back buffer and float depth buffer) on 21 scenes incl. the bundled vehicle and BASELINE's full-size scenes,
+// and against committed outputs of that build (tests/golden/erenderer_reference.npz, tools/make_golden.py erenderer).
 //
 // Single-threaded, immediate mode: every depth-passing fragment is shaded (ERenderer.cpp:269-430).
 // Host arithmetic: plain IEEE single precision in source order (compile with -ffp-contract=off).
@@ -286,18 +290,17 @@ EreScene* ere_load(const uint8_t* blob, uint64_t size)
 		m.world = Identity4();
 		for (int i = 0; i < 3; ++i) m.world.d[3][i] += m.pos[i];     // Mesh.cpp:29 (the CPU path uses the Mesh's own matrix)
 	}
-	// camera, same host code as the GPU path (Camera.cpp)
-	const float radians = F.h.fovDeg * (float(3.14159265358979323846) / 180.f);
-	const float fov = tanf(radians / 2.f), aspect = float(F.h.width) / float(F.h.height);
-	M4 lookAt = Identity4();
-	lookAt.d[3][0] = F.h.camPos[0]; lookAt.d[3][1] = F.h.camPos[1]; lookAt.d[3][2] = F.h.camPos[2];
-	F.proj = Identity4();
-	F.proj.d[0][0] = 1.f / (aspect * fov); F.proj.d[1][1] = 1.f / fov;
-	F.proj.d[2][2] = F.h.farZ / (F.h.nearZ - F.h.farZ); F.proj.d[2][3] = -1.f; F.proj.d[3][2] = (F.h.farZ * F.h.nearZ) / (F.h.nearZ - F.h.farZ);
-	F.view = h_Inverse(lookAt);
-	F.viewProj = h_Mul(F.proj, F.view);
-	F.camPos = V3{ lookAt.d[3][0], lookAt.d[3][1], lookAt.d[3][2] };
-	F.camFwd = V3{ lookAt.d[2][0], lookAt.d[2][1], lookAt.d[2][2] };
+	// camera: the call sequence of main.cpp:421-425 on the restated Camera (oracle_math.h; Camera.cpp)
+	Camera cam(F.h.camPos, F.h.fovDeg);
+	cam.SetAspectRatio(float(F.h.width), float(F.h.height));
+	cam.SetNearFar(F.h.nearZ, F.h.farZ);
+	if (F.h.pitchDeg != 0.f) cam.Pitch(F.h.pitchDeg);
+	if (F.h.yawDeg != 0.f) cam.Yaw(F.h.yawDeg);
+	F.proj = cam.proj;
+	F.view = h_Inverse(cam.lookAt);                 // Camera.h:26
+	F.viewProj = h_Mul(F.proj, F.view);             // ERenderer.cpp:54-56
+	F.camPos = V3{ cam.lookAt.d[3][0], cam.lookAt.d[3][1], cam.lookAt.d[3][2] };
+	F.camFwd = V3{ cam.lookAt.d[2][0], cam.lookAt.d[2][1], cam.lookAt.d[2][2] };
 	F.back.resize((size_t)F.h.width * F.h.height);
 	F.depth.resize((size_t)F.h.width * F.h.height);
 	return S;

@@ -77,62 +77,7 @@ struct Frag
 
 struct RGB { float r, g, b; };
 
-// ---- Camera.cpp:6-37, 45-50, 67-81, 97-117
-struct Camera
-{
-	float fov, aspect = 0, nearZ = 0.1f, farZ = 100.f;
-	M4 proj, lookAt;
-	explicit Camera(const float pos[3], float fovDeg)
-	{
-		const float radians = fovDeg * (float(3.14159265358979323846) / 180.f);   // MathUtilities.h:75-78
-		fov = tanf(radians / 2.f);
-		proj = Identity4();
-		lookAt = Identity4();
-		lookAt.d[3][0] = pos[0]; lookAt.d[3][1] = pos[1]; lookAt.d[3][2] = pos[2];
-	}
-	V3& Forward() { return *reinterpret_cast<V3*>(&lookAt.d[2][0]); }
-	V3& Right() { return *reinterpret_cast<V3*>(&lookAt.d[0][0]); }
-	V3& Up() { return *reinterpret_cast<V3*>(&lookAt.d[1][0]); }
-	void RecalculateProjection()
-	{
-		const float A = farZ / (nearZ - farZ);
-		const float B = (farZ * nearZ) / (nearZ - farZ);
-		const float value = 1.f / (aspect * fov);
-		const float invFov = 1.f / fov;
-		proj.d[0][0] = value;
-		proj.d[1][1] = invFov;
-		proj.d[2][2] = A;
-		proj.d[2][3] = -1.f;
-		proj.d[3][2] = B;
-	}
-	void SetAspectRatio(float w, float h) { aspect = w / h; RecalculateProjection(); }
-	void SetNearFar(float n, float f) { nearZ = n; farZ = f; RecalculateProjection(); }
-	void RecalculateVectors()
-	{
-		const V3 worldUp{ 0.f, 1.f, 0.f };
-		h_Normalize(Forward());
-		Right() = h_Cross(worldUp, Forward());
-		h_Normalize(Right());
-		Up() = h_Cross(Forward(), Right());
-		h_Normalize(Up());
-	}
-	void Pitch(float degrees)   // Matrix3.h:320-329
-	{
-		const float radians = degrees * (float(3.14159265358979323846) / 180.f);
-		const float c = (float)cos(radians), s = (float)sin(radians);
-		M3 m; m(0, 0) = 1; m(0, 1) = 0; m(0, 2) = 0; m(1, 0) = 0; m(1, 1) = c; m(1, 2) = -s; m(2, 0) = 0; m(2, 1) = s; m(2, 2) = c;
-		Forward() = h_Mul(m, Forward());
-		RecalculateVectors();
-	}
-	void Yaw(float degrees)     // Matrix3.h:332-341
-	{
-		const float radians = degrees * (float(3.14159265358979323846) / 180.f);
-		const float c = (float)cos(radians), s = (float)sin(radians);
-		M3 m; m(0, 0) = c; m(0, 1) = 0; m(0, 2) = s; m(1, 0) = 0; m(1, 1) = 1; m(1, 2) = 0; m(2, 0) = -s; m(2, 1) = 0; m(2, 2) = c;
-		Forward() = h_Mul(m, Forward());
-		RecalculateVectors();
-	}
-};
+// (Camera: oracle_math.h, shared with the CPU-path restatement)
 
 // ---- RGBRaw.h:23-32 : truncating pack, byte0 = b, byte1 = g, byte2 = r -> 0x00RRGGBB
 inline uint32_t PackColour(const RGB& c)

@@ -111,3 +111,54 @@ def bin_sets(counts, ids):
     """Per-bin sorted id arrays from (counts, concatenated ids)."""
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return [np.sort(ids[offs[b]:offs[b + 1]]) for b in range(len(counts))]
+
+
+# ---------------------------------------------------------------------------------------- the CPU software path
+ERE_PORT = os.path.join(ORACLE_DIR, "liborc_erenderer.so")          # restatement (oracle/erenderer_oracle.cpp)
+ERE_REF = os.path.join(ORACLE_DIR, "_ref", "libere_ref.so")          # the reference's own Elite::Renderer (oracle/build_ref_erenderer.sh)
+_ere = {}
+
+
+def have_erenderer_reference() -> bool:
+    return os.path.exists(ERE_REF)
+
+
+def erenderer_lib(reference: bool = False):
+    """ctypes handle of the CPU-path renderer: the restatement, or the reference's own ERenderer.cpp build."""
+    path = ERE_REF if reference else ERE_PORT
+    if path not in _ere:
+        if not reference and not os.path.exists(path):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "liborc_erenderer.so"])
+        L = C.CDLL(path)
+        L.ere_load.restype = C.c_void_p
+        L.ere_load.argtypes = [C.c_char_p, C.c_uint64]
+        L.ere_error.restype = C.c_char_p
+        L.ere_error.argtypes = [C.c_void_p]
+        L.ere_render.restype = C.c_double
+        L.ere_render.argtypes = [C.c_void_p] + [C.c_uint32] * 4
+        L.ere_free.argtypes = [C.c_void_p]
+        L.ere_backbuffer.restype = C.c_void_p
+        L.ere_backbuffer.argtypes = [C.c_void_p]
+        L.ere_depth.restype = C.c_void_p
+        L.ere_depth.argtypes = [C.c_void_p]
+        _ere[path] = L
+    return _ere[path]
+
+
+def erenderer_render(scene, reference: bool = False) -> dict:
+    """One frame of Elite::Renderer::Render (ERenderer.cpp:42-164): 0x00RRGGBB back buffer, float depth buffer (NaN where
+    nothing was drawn: the reference clears it with memset(0xFF)), seconds spent inside Render."""
+    L = erenderer_lib(reference)
+    blob = scene.to_blob()
+    S = L.ere_load(blob, len(blob))
+    try:
+        err = L.ere_error(S)
+        if err:
+            raise RuntimeError(err.decode())
+        seconds = L.ere_render(S, 0, 0xFFFFFFFF, 0, 0xFFFFFFFF)
+        if seconds < 0:
+            raise RuntimeError("ere_render failed")
+        h, w = scene.height, scene.width
+        return {"framebuffer": _arr(L.ere_backbuffer(S), np.uint32, (h, w)), "depth": _arr(L.ere_depth(S), np.float32, (h, w)), "seconds": seconds}
+    finally:
+        L.ere_free(S)

@@ -32,9 +32,19 @@ def test_reference_arm_prints_one_contract_line():
     bench = _bench_module()
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and abs(d["value"] * d["ms_per_step"] / 1e3 - 1.0) < 1e-6
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference's own CPU renderer when oracle/build_ref_erenderer.sh has built it (this container, and the GPU box, to
+    # which oracle/_ref travels), else the restatement pinned against it
+    built = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libere_ref.so"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if built else "port")
+    assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["triangles"] == 400_000 and d["config"]["resolution"] == "3840x2160"
+
+
+def test_reference_arm_can_be_forced_onto_the_restatement():
+    res = _run("--impl", "reference", "--workload", "spheres_small", "--steps", "1", "--warmup", "0", "--ref-cuda", "0", env={"B2R_CPU_BASELINE_PORT": "1"})
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert json.loads(res.stdout)["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_exit_without_work():

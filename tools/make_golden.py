@@ -6,6 +6,10 @@
   python tools/make_golden.py frames     (GPU box: runs the unmodified reference CUDA renderer
                                           oracle/_ref/ref_render on small scenes; write into gpurun_out/golden/)
 
+  python tools/make_golden.py erenderer  (here, CPU only: runs the reference's own CPU renderer, ERenderer.cpp built by
+                                          oracle/build_ref_erenderer.sh into oracle/_ref/libere_ref.so, on the frame cases and on
+                                          BASELINE config 1 = the bundled textured vehicle at 640x480)
+
 The scenes / OBJ texts are regenerated deterministically by tests/golden_cases.py, so only the
 reference's OUTPUTS are stored.
 """
@@ -82,5 +86,30 @@ def frames():
         print("wrote", name, ref["visible_tris"], bins.shape)
 
 
+def erenderer():
+    """tests/golden/erenderer_reference.npz: SHA-256 of back buffer and depth buffer (float bits) of every frame case as
+    rendered by the reference's Elite::Renderer, the full surfaces of three of them (diagnosable failures), and the
+    same for BASELINE config 1 (bundled vehicle, four maps, 640x480, camera {0,5,65}) when the assets are present."""
+    import hashlib
+    import asset_scenes
+    import oracle_lib
+    assert oracle_lib.have_erenderer_reference(), "run oracle/build_ref_erenderer.sh first"
+    cases = dict(golden_cases.frame_cases())
+    if asset_scenes.have_assets():
+        cases["config1_vehicle_640x480"] = lambda: asset_scenes.vehicle_scene(640, 480, sample=0)
+        cases["config1_vehicle_640x480_linear"] = lambda: asset_scenes.vehicle_scene(640, 480, sample=1)
+    out = {}
+    for name, make in cases.items():
+        r = oracle_lib.erenderer_render(make(), reference=True)
+        fb, depth = r["framebuffer"], r["depth"].view(np.uint32)
+        out[name + "_sha"] = np.array([hashlib.sha256(fb.tobytes()).hexdigest(), hashlib.sha256(depth.tobytes()).hexdigest()])
+        out[name + "_drawn"] = np.array([int((~np.isnan(r["depth"])).sum())])
+        if name in ("soup_textured_linear", "quads_linear", "spheres"):
+            out[name + "_fb"], out[name + "_depth"] = fb, depth
+        print(name, out[name + "_drawn"][0], "pixels drawn", f"{r['seconds'] * 1e3:.1f} ms")
+    np.savez_compressed(os.path.join(GOLD, "erenderer_reference.npz"), **out)
+    print("wrote", os.path.join(GOLD, "erenderer_reference.npz"))
+
+
 if __name__ == "__main__":
-    {"parser": parser, "frames": frames}[sys.argv[1]]()
+    {"parser": parser, "frames": frames, "erenderer": erenderer}[sys.argv[1]]()
