@@ -52,7 +52,29 @@ def make_scene(workload: str):
         return scenes.sphere_grid_scene(WIDTH, HEIGHT, nx=5, ny=5)
     if workload == "fill64":
         return scenes.fill_quads_scene(WIDTH, HEIGHT, layers=64, sample=1)  # BASELINE config 4
+    if workload in ("vehicle480", "vehicle1080"):
+        return make_vehicle_scene(*((640, 480) if workload == "vehicle480" else (1920, 1080)))   # BASELINE configs 1 / 2
     raise SystemExit(f"unknown workload {workload}")
+
+
+def make_vehicle_scene(width, height):
+    """BASELINE configs 1 and 2: the reference's bundled vehicle mesh (the REFERENCE parser's output, committed as a golden
+    vector), camera {0,5,65} / fov 45 (main.cpp:421), back-face culling, point sampling, the four texture slots wired as in
+    main.cpp:172-175.  The maps are the reference's own PNGs when oracle/build_ref.sh has copied them next to the reference
+    binary (data files, decoded by the product's PNG decoder), else synthetic 1024^2 maps - `data` in the JSON line says which."""
+    from custom_gpgpu_rasterizer_b200.renderer import decode_png
+    from custom_gpgpu_rasterizer_b200.scenefile import MeshData, Scene
+    g = np.load(os.path.join(ROOT, "tests", "golden", "objparser_reference.npz"))
+    res = os.path.join(ROOT, "oracle", "_ref", "resources")
+    names = [os.path.join(res, f"vehicle_{k}.png") for k in ("diffuse", "normal", "specular", "gloss")]
+    if all(os.path.exists(n) for n in names):
+        tex, src = [decode_png(n) for n in names], "bundled"
+    else:
+        tex, src = [scenes.checker_texture(1024, 1), scenes.normal_texture(1024, 2), scenes.noise_texture(1024, 3), scenes.noise_texture(1024, 4)], "synthetic"
+    sc = Scene(width, height, meshes=[MeshData(g["res_vehicle_v"], g["res_vehicle_i"], (0.0, 0.0, 0.0), (0, 1, 2, 3))], textures=tex,
+               cull=0, sample=0, vis=0, cam_pos=(0.0, 5.0, 65.0), fov_deg=45.0, near=0.1, far=100.0, name=f"vehicle_{width}x{height}")
+    sc.texture_source = src
+    return sc
 
 
 # ------------------------------------------------------------------------------------ BASELINE config 5 (optional workload)
@@ -265,7 +287,7 @@ def run_reference(args, scene):
     line = {
         "impl": "reference", "metric": METRIC, "timing": "host steady_clock around Render (this arm runs on the host cores)",
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean_s * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_of(scene),
         "mtris_per_s": scene.n_tris / mean_s / 1e6,
         "config": dict(workload_config(args.workload, scene), parallelism="the reference's CPU renderer, one host thread (it is single-threaded)"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
@@ -278,10 +300,18 @@ def run_reference(args, scene):
     print(json.dumps(line), flush=True)
 
 
+def data_of(scene):
+    src = getattr(scene, "texture_source", None)
+    return "synthetic" if src is None else f"the reference's bundled vehicle mesh, {src} texture maps"
+
+
 def workload_config(name, scene):
     return {"workload": {"spheres10m": "BASELINE config 3: 25x25 UV-sphere grid, 10 000 000 triangles / 5 176 250 vertices, 3840x2160, 16x16 tiles (240x135), back-face culling, vertex colours",
                          "fill64": "BASELINE config 4: 64 stacked full-screen textured quads, 3840x2160, linear sampling, no culling",
-                         "spheres_small": "5x5 spheres (400 000 triangles), 3840x2160"}[name],
+                         "spheres_small": "5x5 spheres (400 000 triangles), 3840x2160",
+                         "vehicle480": "BASELINE config 1: the reference's bundled textured vehicle mesh (diffuse / normal / specular / gloss maps), 640x480, camera {0,5,65}, back-face culling, point sampling",
+                         "vehicle1080": "BASELINE config 2: the reference's bundled textured vehicle mesh (diffuse / normal / specular / gloss maps), 1920x1080, 16x16 tiles, back-face culling, point sampling"}[name]
+                        + (f" ({scene.texture_source} texture maps)" if hasattr(scene, "texture_source") else ""),
             "triangles": scene.n_tris, "vertices": scene.n_vertices, "resolution": f"{scene.width}x{scene.height}",
             "l2_policy": "inputs larger than L2 (static position / triangle-reference / vertex streams 530 MB; ~0.9 GB of DRAM traffic per frame)" if name == "spheres10m" else "working set is L2-resident by nature of the workload (textures + 128 triangles); framebuffer write-back 66 MB per frame"}
 
@@ -510,7 +540,7 @@ def run_b200(args, scene):
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_of(scene),
         "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up/bins/sorts primitive slice r, owners read the peers' lists over NVLink, colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather])),
         "mtris_per_s": scene.n_tris * fps / 1e6,
         "visible_triangles": visible, "tile_pairs": pairs, "fragments": frags, "covered_pixels": covered_px,
@@ -596,7 +626,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small", "views172"])
+    ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small", "views172", "vehicle480", "vehicle1080"])
     ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")

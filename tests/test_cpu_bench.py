@@ -47,6 +47,15 @@ def test_reference_arm_can_be_forced_onto_the_restatement():
     assert json.loads(res.stdout)["cpu_baseline"]["kind"] == "port"
 
 
+def test_reference_arm_on_baseline_config_1():
+    """BASELINE configs[0]: the reference's CPU software path on its bundled textured mesh at 640x480."""
+    res = _run("--impl", "reference", "--workload", "vehicle480", "--steps", "2", "--warmup", "1", "--ref-cuda", "0")
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads(res.stdout)
+    assert d["config"]["triangles"] == 11638 and d["config"]["resolution"] == "640x480" and "bundled vehicle mesh" in d["data"]
+    assert 1.0 < d["ms_per_step"] < 2000.0
+
+
 def test_reference_arm_other_ranks_exit_without_work():
     res = _run("--impl", "reference", "--workload", "spheres_small", "--gpus", "2", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert res.returncode == 0 and res.stdout.strip() == ""
