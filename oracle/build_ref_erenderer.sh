@@ -8,8 +8,8 @@
 # itself - every line of arithmetic on the CPU path - is compiled UNMODIFIED, with the reference's own Camera.cpp,
 # Light.cpp, DirectionalLight.cpp, SceneGraph.cpp, Texture.cpp and math / vertex / texture-sampler headers, from a
 # BUILD-TIME scratch copy (oracle/_ref/src_ere, git-ignored: reference sources never enter this repository).  What is
-# ours: the three headers of oracle/ere_shim/ that restore the interfaces the file was written against (they replace
-# the scratch copies of PCH.h, Mesh.h, SceneManager.h), the SDL stand-ins (sdl_stub.cpp, sdl_stub_ere.cpp) and the glue
+# ours: the three headers of oracle/ere_shim/ that restore the interfaces the file was written against (copied over
+# the scratch copies of PCH.h, Mesh.h, SceneManager.h under those names), the SDL stand-ins (sdl_stub.cpp, sdl_stub_ere.cpp) and the glue
 # (ere_ref_driver.cpp).  One leniency patch, as in build_ref.sh: std::powf -> powf (RGBColor.h:126-128; GCC's <cmath>
 # has no std::powf).  Built like the restatement: g++ -O2 -ffp-contract=off (no implicit FMA, IEEE single precision).
 set -euo pipefail
@@ -31,7 +31,9 @@ mkdir -p "$SRC"
 cp "$REF"/*.h "$SRC"/
 for f in ERenderer Camera Light DirectionalLight SceneGraph Texture; do cp "$REF/$f.cpp" "$SRC"/; done
 # our reconstruction of the interfaces ERenderer.cpp predates replaces the current headers of the same name
-cp "$HERE"/ere_shim/PCH.h "$HERE"/ere_shim/Mesh.h "$HERE"/ere_shim/SceneManager.h "$SRC"/
+cp "$HERE"/ere_shim/erenderer_prelude.h "$SRC"/PCH.h
+cp "$HERE"/ere_shim/legacy_mesh_interface.h "$SRC"/Mesh.h
+cp "$HERE"/ere_shim/legacy_scene_manager_interface.h "$SRC"/SceneManager.h
 sed -i 's/std::powf/powf/g' "$SRC/RGBColor.h"
 
 FLAGS=(-std=c++17 -O2 -fPIC -ffp-contract=off -fno-fast-math -w

@@ -2,8 +2,8 @@
 //
 // oracle/build_ref_erenderer.sh compiles the reference's Elite::Renderer (CustomCUDARasterizer/ERenderer.cpp, unmodified)
 // together with its Camera / Light / DirectionalLight / SceneGraph translation units and its math, texture-sampler and
-// vertex headers, against OUR reconstruction of the two interfaces that file predates (oracle/ere_shim/Mesh.h,
-// SceneManager.h, PCH.h) and OUR SDL stand-ins (oracle/sdl_stub.cpp, sdl_stub_ere.cpp), into oracle/_ref/libere_ref.so.
+// vertex headers, against OUR reconstruction of the two interfaces that file predates (oracle/ere_shim/: legacy_mesh_interface.h,
+// legacy_scene_manager_interface.h, erenderer_prelude.h - installed as Mesh.h / SceneManager.h / PCH.h of the build) and OUR SDL stand-ins (oracle/sdl_stub.cpp, sdl_stub_ere.cpp), into oracle/_ref/libere_ref.so.
 // This file is the glue: it exports the same C interface as the restatement (oracle/erenderer_oracle.cpp: ere_load /
 // ere_render / ere_backbuffer / ere_depth / ere_free over a scene dump of custom_gpgpu_rasterizer_b200/scenefile.py),
 // so tests/ can compare the two frame by frame and bench.py can time the real thing (cpu_baseline.kind "reference").
