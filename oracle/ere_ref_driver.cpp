@@ -134,4 +134,23 @@ uint64_t ere_frags_shaded(const EreScene*) { return 0; }      // the reference k
 uint64_t ere_tris_drawn(const EreScene*) { return 0; }
 int ere_is_reference(void) { return 1; }
 
+// The reference's Camera (Camera.h / Camera.cpp, compiled as they lie) through the call sequence of main.cpp:421-425 and
+// SURVEY's config 5 (Pitch, then Yaw): the matrices and vectors the renderers take from it.  Lets tests/ pin the product's
+// host-side Camera (csrc/host/b2r_scene.cpp, b2r_host_camera) and the oracles' restatement against the real class on CPU.
+void ere_reference_camera(const float pos[3], float fovDeg, float width, float height, float nearZ, float farZ, float pitchDeg, float yawDeg,
+	float* viewProj16, float* view16, float* proj16, float* camPos3, float* camFwd3)
+{
+	Camera cam{ FPoint3{ pos[0], pos[1], pos[2] }, fovDeg };
+	cam.SetAspectRatio(width, height);
+	cam.SetNearFarValues(nearZ, farZ);
+	if (pitchDeg != 0.f) cam.Pitch(pitchDeg);
+	if (yawDeg != 0.f) cam.Yaw(yawDeg);
+	const FMatrix4 view = cam.GetViewMatrix();
+	const FMatrix4 proj = cam.GetProjectionMatrix();
+	const FMatrix4 vp = proj * view;                   // CUDARenderer.cu:219, ERenderer.cpp:54-56
+	memcpy(viewProj16, vp.data, 64); memcpy(view16, view.data, 64); memcpy(proj16, proj.data, 64);
+	camPos3[0] = cam.GetPosition().x; camPos3[1] = cam.GetPosition().y; camPos3[2] = cam.GetPosition().z;
+	camFwd3[0] = cam.GetForward().x; camFwd3[1] = cam.GetForward().y; camFwd3[2] = cam.GetForward().z;
+}
+
 }

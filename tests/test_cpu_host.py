@@ -81,6 +81,40 @@ def test_camera_matches_oracle_restatement(cfg):
     assert proj[3, 3] == 1.0 and proj[3, 2] == -1.0
 
 
+CAMERAS = [
+    dict(pos=(0, 1, 5), fov=45.0, w=640, h=480, near=0.1, far=100.0, pitch=0.0, yaw=0.0),
+    dict(pos=(0, 5, 65), fov=45.0, w=1920, h=1080, near=0.1, far=100.0, pitch=0.0, yaw=0.0),
+    dict(pos=(0, 0, 68), fov=45.0, w=3840, h=2160, near=0.1, far=100.0, pitch=0.0, yaw=0.0),
+    dict(pos=(3, -2, 9), fov=70.0, w=333, h=217, near=0.5, far=50.0, pitch=12.5, yaw=-40.0),
+    dict(pos=(-1.5, 0.25, 2), fov=30.0, w=1280, h=720, near=0.01, far=10.0, pitch=-80.0, yaw=359.0),
+] + [dict(pos=None, fov=45.0, w=1920, h=1080, near=1.0, far=2000.0, pitch=-19.654, yaw=360.0 * k / 1024) for k in (0, 1, 255, 389, 512, 777, 1023)]   # config 5's ring
+
+
+@pytest.mark.skipif(not oracle_lib.have_erenderer_reference(), reason="oracle/_ref/libere_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("cfg", CAMERAS, ids=[f"cam{i}" for i in range(len(CAMERAS))])
+def test_camera_matches_the_references_camera_class(cfg):
+    """The veneer's Camera (what the product's host side feeds b2r_render) against the reference's own Camera.cpp, compiled as
+    it lies into oracle/_ref/libere_ref.so: view-projection, view, projection, position and forward vector bit for bit."""
+    L = oracle_lib.erenderer_lib(reference=True)
+    fp = C.POINTER(C.c_float)
+    L.ere_reference_camera.argtypes = [fp] + [C.c_float] * 7 + [fp] * 5
+    L.ere_reference_camera.restype = None
+
+    def ref_camera(pos):
+        out = [np.zeros(n, np.float32) for n in (16, 16, 16, 3, 3)]
+        p = np.asarray(pos, np.float32)
+        L.ere_reference_camera(p.ctypes.data_as(fp), cfg["fov"], float(cfg["w"]), float(cfg["h"]), cfg["near"], cfg["far"], cfg["pitch"], cfg["yaw"],
+                               *[o.ctypes.data_as(fp) for o in out])
+        return dict(zip(("view_proj", "view", "proj", "cam_pos", "cam_fwd"), out))
+    pos = cfg["pos"]
+    if pos is None:         # SURVEY config 5: pos = 743.3 * forward of the pitched / yawed camera
+        pos = tuple(float(np.float32(743.3) * f) for f in ref_camera((0.0, 0.0, 0.0))["cam_fwd"])
+    want = ref_camera(pos)
+    got = host_camera(pos, cfg["fov"], cfg["w"], cfg["h"], cfg["near"], cfg["far"], cfg["pitch"], cfg["yaw"])
+    for k in want:
+        assert np.array_equal(parity.bits(got[k]), parity.bits(want[k])), k
+
+
 def test_mesh_world_is_translated_twice_like_cudamesh():
     w = host_mesh_world((3.0, -2.0, 7.5)).reshape(4, 4).T
     assert np.array_equal(w[:3, 3], np.float32([6.0, -4.0, 15.0]))       # Mesh.cpp:29 + CUDAMesh.cpp:16-18
