@@ -36,3 +36,11 @@ run ring4_sliced B2R_FRAME_RING=4 B2R_SHARD_SLICED_VERTEX=1
 # stream, possibly bad when other ring streams have runnable work; more hardware queues avoid false dependencies between streams
 run ring3_sliced_nopdl B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 B2R_PDL=0
 run ring3_sliced_conn32 B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 CUDA_DEVICE_MAX_CONNECTIONS=32
+# BASELINE config 5 at N ranks: view-parallel (no communication) and sort-first per view (sharded front end, moving camera)
+for m in parallel sortfirst; do
+	port=$((port + 1))
+	timeout 240 $TR --master-port $port bench.py --gpus $N --workload views172 --views-mode $m --steps 64 > $O/views_$m.json 2> $O/views_$m.err
+	echo "== views172 $m: $(python -c "
+import json
+d=json.loads(open('$O/views_$m.json').read().strip().splitlines()[-1]); print(round(d['value'],1), d['unit'], 'e2e', round(d['e2e']['value'],1))" 2>&1 | tail -1)"
+done
