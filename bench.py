@@ -181,9 +181,9 @@ def run_views(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if sort_first else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE config 5: 172 instances of the bundled vehicle mesh (2 001 736 triangles, one vertex buffer + 172 world matrices), "
-                               "1920x1080, 1024 cameras on a ring, PBR shading with four 1024^2 maps, view-parallel (view i -> rank i mod N, no communication)",
+                               "1920x1080, 1024 cameras on a ring, PBR shading with four 1024^2 maps",
                    "triangles": total, "visible_triangles_last_view": visible, "resolution": "1920x1080",
-                   "parallelism": (f"sort-first per view, {world} ranks (sharded front end, frames composed on rank 0)" if sort_first else f"view-parallel, {world} rank(s)")},
+                   "parallelism": (f"sort-first per view, {world} ranks (sharded front end, frames composed on rank 0)" if sort_first else f"view-parallel, {world} rank(s): view i -> rank i mod N, no communication")},
         "mtris_per_s": total * world_views * args.steps / t / 1e6,
         "e2e": {"value": world_views * args.steps / float(e2e.item()), "unit": "views/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": sc.width * sc.height * 4},
         "gpu_launches": launches * args.steps, "clocks": clocks.summary()}), flush=True)
