@@ -6,6 +6,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -80,3 +81,168 @@ def test_algorithmic_bytes_are_surveys_figures():
 def test_gpu_arm_fails_loudly_without_a_gpu():
     res = _run("--workload", "spheres_small", "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-fill")
     assert res.returncode != 0 and res.stdout.strip() == "", "no CPU fallback: the GPU arm must not print a line without a device"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Dry run of the GPU arm's Python plumbing with a fake device: everything bench.py does around the renderer (timing
+# brackets, per-stage roofline, end-to-end leg, auxiliary legs, multi-rank reductions, the JSON line) executes on CPU with
+# the ctypes Renderer and torch.cuda replaced by stand-ins.  It cannot measure anything; it catches a typo that would
+# otherwise cost the bench line at the round-end gate.
+class _FakeRenderer:
+    instances = []
+
+    def __init__(self, width, height, device=0):
+        self.w, self.h, self.opts, self.frames = width, height, {}, 0
+        _FakeRenderer.instances.append(self)
+
+    def set_option(self, o, v):
+        self.opts[o] = v
+
+    def get_option(self, o):
+        return self.opts.get(o, 0)
+
+    def load_scene(self, scene):
+        self.scene = scene
+
+    def set_stream(self, ptr):
+        pass
+
+    def render(self, cam, cull=0, sample=0, vis=0, clear_rgb=None, sync=True):
+        assert cam["view_proj"].shape == (16,)
+        self.frames += 1
+
+    def sync(self):
+        pass
+
+    def counters(self):
+        return {"pairs": 7_117_055, "kernels_launched": 12, "tiles_owned": 32400, "num_bins": 32400, "unsorted_tiles": 0, "big_triangles": 0,
+                "fragments": 3_089_508, "sort_fallback_tiles": 0}
+
+    def stats(self):
+        return self.scene.n_tris, self.scene.n_tris // 2
+
+    def stage_ms_mean(self, reset=True):
+        from custom_gpgpu_rasterizer_b200 import _lib
+        ms = dict(zip(_lib.STAGE_NAMES, (0.04, 0.10, 0.014, 0.055, 0.066, 0.238, 0.513, 0.003, 0.016)))
+        return ms, 20
+
+    def present_async(self, out):
+        assert out.shape == (self.h, self.w) and out.dtype == np.uint32
+
+    def present_wait(self):
+        pass
+
+    def framebuffer(self, out=None):
+        return np.zeros((self.h, self.w), np.uint32)
+
+    def depth(self):
+        d = np.full((self.h, self.w), 0x7FFFFFFF, np.int32)
+        d[: self.h // 2] = 5
+        return d
+
+    def bind_framebuffer(self, ptr):
+        pass
+
+    def close(self):
+        pass
+
+
+class _FakeEvent:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 9.4          # ms for the K frames
+
+
+class _FakeShard:
+    launches_per_frame = 0
+
+    def __init__(self, renderer, rank, world, *a, **k):
+        pass
+
+    def run(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def _fake_device(monkeypatch, world=1):
+    import contextlib
+    import types
+
+    import numpy  # noqa: F401
+    import torch
+    import torch.distributed as dist
+    from custom_gpgpu_rasterizer_b200 import multi_gpu, renderer
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(renderer, "Renderer", _FakeRenderer)
+    monkeypatch.setattr(multi_gpu, "ShardedSortFirst", _FakeShard)
+    monkeypatch.setattr(multi_gpu, "SortFirstGather", _FakeShard)
+    monkeypatch.setattr(torch, "device", lambda *a, **k: cpu)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **k: real_empty(*a, **k))
+    monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
+    monkeypatch.setattr(dist, "all_gather_object", lambda out, obj: out.__setitem__(slice(None), [obj] * len(out)))
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+
+
+CONTRACT_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                 "config", "roofline", "e2e", "gpu_launches", "clocks"}
+
+
+def _dry_run(monkeypatch, capsys, argv, world=1):
+    _fake_device(monkeypatch, world)
+    bench = _bench_module()
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_gpu_arm_dry_run_single_rank(monkeypatch, capsys):
+    d = _dry_run(monkeypatch, capsys, ["--steps", "20", "--warmup", "5"])
+    assert CONTRACT_KEYS <= set(d) and "cpu_baseline" in d and "fill_test" in d
+    assert d["n_gpus"] == 1 and d["config"]["triangles"] == 10_000_000 and "config 3" in d["config"]["workload"]
+    assert abs(d["value"] - 20 / 9.4e-3) < 1e-6 and d["gpu_launches"] == 12 * 20
+    r = d["roofline"]
+    assert r["kernel"] == "raster_shade" and r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"]
+    assert d["e2e"]["d2h_bytes_per_step"] == 3840 * 2160 * 4 and d["e2e"]["value"] > 0
+    assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] > 0
+    assert "error" not in d["fill_test"] and d["fill_test"]["rop_equivalent_bytes"] == 3_089_508 * 12 + 3840 * 2160 * 8
+
+
+def test_gpu_arm_dry_run_eight_ranks(monkeypatch, capsys):
+    d = _dry_run(monkeypatch, capsys, ["--gpus", "8", "--steps", "10", "--warmup", "3", "--no-cpu-baseline"], world=8)
+    assert CONTRACT_KEYS <= set(d) and d["n_gpus"] == 8 and "view_parallel" in d and len(d["stages_ms_per_rank"]) == 8
+    assert "sharded front end" in d["config"]["parallelism"]
+    r = d["roofline"]
+    assert abs(r["peak"] / 8 - _bench_module().load_peaks()[0]) < 1e-6 and r["traffic"] is None      # N GPUs' bandwidth; ncu traffic is a 1-GPU capture
+
+
+@pytest.mark.parametrize("mode,world", [("parallel", 1), ("parallel", 4), ("sortfirst", 4)])
+def test_views_workload_dry_run(monkeypatch, capsys, mode, world):
+    d = _dry_run(monkeypatch, capsys, ["--workload", "views172", "--gpus", str(world), "--steps", "8", "--views-mode", mode], world=world)
+    assert d["unit"] == "views/s" and d["config"]["triangles"] == 172 * 11638
+    assert abs(d["value"] - (1 if mode == "sortfirst" else world) * 8 / 9.4e-3) < 1e-6
+    assert ("sort-first" in d["config"]["parallelism"]) == (mode == "sortfirst")
+
+
+def test_vehicle_workload_dry_run(monkeypatch, capsys):
+    d = _dry_run(monkeypatch, capsys, ["--workload", "vehicle1080", "--steps", "5", "--no-cpu-baseline"])
+    assert d["config"]["triangles"] == 11638 and d["config"]["resolution"] == "1920x1080" and "bundled vehicle mesh" in d["data"]
