@@ -192,3 +192,62 @@ def test_fullsize_constants_from_the_oracle_at_full_size():
     Q = oracle_lib.render(quads, fill_rule=1)
     assert Q["frags_covered"] == Q["frags_passed"] == fullsize.CONFIG4_FRAGMENTS
     assert int(Q["bin_counts"].sum()) == 2 * 64 * 240 * 135
+
+
+class _OracleAsProduct:
+    """Stand-in for custom_gpgpu_rasterizer_b200.renderer.Renderer that answers from the CPU oracle: lets the -m gpu test
+    FUNCTIONS of tests/test_gpu_zz_fullsize.py run on CPU (their Python, their use of the Renderer API, their constants)."""
+    cache = {}
+
+    def __init__(self, width, height, device=0):
+        self.opts = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def set_option(self, o, v):
+        self.opts[o] = v
+
+    def load_scene(self, scene):
+        self.scene = scene
+
+    def render_scene(self, scene, sync=True):
+        if scene.name not in self.cache:
+            self.cache[scene.name] = oracle_lib.render(scene, fill_rule=1)
+        self.o = self.cache[scene.name]
+
+    def framebuffer(self):
+        return self.o["framebuffer"]
+
+    def depth(self):
+        return self.o["depth"]
+
+    def winner(self):
+        return self.o["winner"]
+
+    def stats(self):
+        return self.o["total_tris"], self.o["visible_tris"]
+
+    def bin_lists(self):
+        counts = self.o["bin_counts"]
+        seg = np.repeat(np.arange(len(counts), dtype=np.int64), counts.astype(np.int64))
+        ids = self.o["bin_ids"][np.lexsort((self.o["bin_ids"].astype(np.int64), seg))]
+        offsets = np.concatenate([[0], np.cumsum(counts.astype(np.int64))[:-1]]).astype(np.uint32)
+        return counts, offsets, ids
+
+    def counters(self):
+        big = sum(1 for _ in range(0))
+        return {"pairs": int(self.o["bin_counts"].sum()), "fragments": int(self.o["frags_covered"]),
+                "big_triangles": self.scene.n_tris if self.scene.name.startswith("fillquads") else big}
+
+
+@pytest.mark.skipif(os.environ.get("B2R_SLOW_TESTS") != "1", reason="~2 min of CPU: the full-size -m gpu test functions with the oracle standing in for the product (set B2R_SLOW_TESTS=1)")
+def test_fullsize_gpu_test_functions_run_with_the_oracle_as_product(monkeypatch):
+    from custom_gpgpu_rasterizer_b200 import renderer
+    import test_gpu_zz_fullsize as t
+    monkeypatch.setattr(renderer, "Renderer", _OracleAsProduct)
+    t.test_config3_10m_triangles_4k_matches_oracle_per_sphere()
+    t.test_config4_64_layers_4k_equals_nearest_layer()
