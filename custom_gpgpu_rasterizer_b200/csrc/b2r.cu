@@ -231,6 +231,11 @@ int fail(b2r_context* c, int code, const char* fmt, ...)
 
 uint32_t nBins(const b2r_context* c) { return c->binsX * c->binsY; }
 
+// cudaMemset runs on the legacy default stream and may return before the fill has happened; the context's streams are
+// non-blocking, i.e. NOT ordered behind the legacy stream.  Allocation-time fills are therefore completed before anything
+// else can touch the new buffer (found by tools/trace/stream_order.py).
+cudaError_t finishFills(b2r_context*) { return cudaStreamSynchronize(nullptr); }
+
 int allocSurfaces(b2r_context* c)
 {
 	const size_t n = (size_t)c->width * c->height;
@@ -240,14 +245,17 @@ int allocSurfaces(b2r_context* c)
 	CU(c, cudaMemset(c->dFramebuffer, 0, 2 * n * 4));     // CUDAWindowHelper.h:17-25 zero-initialises
 	c->dColour[0] = c->dFramebuffer; c->dColour[1] = c->dFramebuffer + n;
 	CU(c, cudaMemset(c->dDepth, 0, n * 4));
+	CU(c, finishFills(c));
 	return B2R_OK;
 }
 
 int ensureDebugSurfaces(b2r_context* c)
 {
 	const size_t n = (size_t)c->width * c->height;
+	const bool fresh = !c->dZ || !c->dWinner;
 	if (!c->dZ) { CU(c, cudaMalloc((void**)&c->dZ, n * 4)); CU(c, cudaMemset(c->dZ, 0, n * 4)); }
 	if (!c->dWinner) { CU(c, cudaMalloc((void**)&c->dWinner, n * 4)); CU(c, cudaMemset(c->dWinner, 0xFF, n * 4)); }
+	if (fresh) CU(c, finishFills(c));
 	return B2R_OK;
 }
 
@@ -261,6 +269,7 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	{
 		CU(c, cudaMalloc((void**)&B.frameInfo, kInfoWords * 8 + kCounterWords * 4));
 		CU(c, cudaMemset(B.frameInfo, 0, kInfoWords * 8 + kCounterWords * 4));
+		CU(c, finishFills(c));
 		B.counters = reinterpret_cast<uint32_t*>(B.frameInfo + kInfoWords);
 	}
 	// tile_scan_kernel reads the counts with 16-byte loads; tileOffset[n] = overflow marker for peer ranks
@@ -1670,6 +1679,7 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	const size_t bytes = 256 + (size_t)sh.nSets * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));
 	CU(c, cudaMemset(sh.arena, 0, bytes));
+	CU(c, finishFills(c));
 	CU(c, cudaMallocHost((void**)&sh.hTimeout, 8));
 	*sh.hTimeout = 0;
 	memset(arenaHandle64, 0, 64); memset(colourHandle64, 0, 64);

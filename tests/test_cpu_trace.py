@@ -1,0 +1,84 @@
+"""CPU: stream-order race detection for the frame schedulers - the product's OWN host code (csrc/b2r.cu, unchanged) runs
+against a recording stand-in for the CUDA runtime (tools/trace/fake_cudart.cpp: "device" memory is host memory, kernels
+do not run, every stream / event / copy / launch is logged) and tools/trace/stream_order.py checks that any two device
+operations that touch the same bytes, one of them writing, are ordered by stream order, an event or a host
+synchronisation.  Covers the default three-stream pipeline, serial frames and the frame ring (depth 2-4, never run on a
+GPU in round 1) on one device with frames in flight, a moving camera, pipelined Present, read-backs, stage timers,
+unsorted lists and scene changes between frames.  The detector is shown to have teeth by deleting waits from the log."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "build", "trace")
+sys.path.insert(0, os.path.join(ROOT, "tools", "trace"))
+import stream_order  # noqa: E402
+
+W, H = 320, 240
+MODES = ["default", "serial", "novertex", "ring2", "ring3", "ring4"]
+
+
+@pytest.fixture(scope="module")
+def trace_build():
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not available")
+    subprocess.check_call(["bash", os.path.join(ROOT, "tools", "trace", "build.sh")], stdout=subprocess.DEVNULL)
+    return {"B2R_LIBRARY": os.path.join(OUT, "libb2r_trace.so"), "B2R_TRACE_PARAMS": os.path.join(OUT, "kernel_params.txt")}
+
+
+@pytest.fixture(scope="module")
+def logs(trace_build, tmp_path_factory):
+    d = tmp_path_factory.mktemp("traces")
+    out = {}
+    for mode in MODES:
+        path = str(d / f"{mode}.jsonl")
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", "frames.py"), mode], capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, B2R_TRACE_FILE=path, **trace_build))
+        assert res.returncode == 0 and "scenario done" in res.stdout, res.stdout + res.stderr
+        out[mode] = path
+    return out
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_no_unordered_conflicting_accesses(logs, mode):
+    t = stream_order.Trace(logs[mode], W, H)
+    races = t.analyse()
+    assert not t.warnings, sorted(set(t.warnings))[:5]                      # every pointer argument was resolved to an allocation
+    launches = [o for o in t.ops if o["op"] == "launch"]
+    assert len(launches) > 300 and all(o["args"] for o in launches)
+    streams = {o["stream"] for o in launches}
+    assert len(streams) >= (1 if mode in ("serial", "novertex") else 3), streams    # the frames really were spread over streams
+    assert not races, "\n".join(t.describe(r) for r in races[:8])
+
+
+@pytest.mark.parametrize("mode", ["default", "ring3"])
+def test_detector_has_teeth(logs, mode, tmp_path):
+    lines = open(logs[mode]).readlines()
+
+    def races_without(drop):
+        p = tmp_path / "mutated.jsonl"
+        p.write_text("".join(l for i, l in enumerate(lines) if i not in drop))
+        return len(stream_order.Trace(str(p), W, H).analyse())
+    waits = [i for i, l in enumerate(lines) if '"stream_wait"' in l]
+    syncs = [i for i, l in enumerate(lines) if '"event_sync"' in l or '"stream_sync"' in l]
+    assert len(waits) > 50
+    assert races_without(set(waits)) > 100, "frames in flight without any event wait must race"
+    assert races_without(set(syncs)) > 10, "read-backs without host synchronisation must race"
+    # most single waits are load-bearing (the rest are implied by a host synchronisation or another wait)
+    needed = sum(races_without({w}) > 0 for w in waits[::3])
+    assert needed >= len(waits[::3]) // 3, (needed, len(waits[::3]))
+
+
+def test_allocation_time_fills_are_completed_before_use(logs):
+    """cudaMemset runs on the legacy default stream, which the context's non-blocking streams are not ordered behind: the
+    fills at allocation time must be followed by a synchronisation of that stream (b2r.cu: finishFills)."""
+    t = stream_order.Trace(logs["default"], W, H)
+    ops = t.ops
+    fills = [i for i, o in enumerate(ops) if o["op"] == "memset"]
+    assert fills
+    for i in fills:
+        nxt = next(o for o in ops[i + 1:] if o["op"] not in ("memset", "malloc"))
+        assert nxt["op"] in ("stream_sync", "launch", "memcpy") and nxt["stream"] == 0, (ops[i], nxt)
