@@ -44,7 +44,7 @@ def logs(trace_build, tmp_path_factory):
 
 @pytest.mark.parametrize("mode", MODES)
 def test_no_unordered_conflicting_accesses(logs, mode):
-    t = stream_order.Trace(logs[mode], W, H)
+    t = stream_order.Trace(logs[mode])
     races = t.analyse()
     assert not t.warnings, sorted(set(t.warnings))[:5]                      # every pointer argument was resolved to an allocation
     launches = [o for o in t.ops if o["op"] == "launch"]
@@ -61,7 +61,7 @@ def test_detector_has_teeth(logs, mode, tmp_path):
     def races_without(drop):
         p = tmp_path / "mutated.jsonl"
         p.write_text("".join(l for i, l in enumerate(lines) if i not in drop))
-        return len(stream_order.Trace(str(p), W, H).analyse())
+        return len(stream_order.Trace(str(p)).analyse())
     waits = [i for i, l in enumerate(lines) if '"stream_wait"' in l]
     syncs = [i for i, l in enumerate(lines) if '"event_sync"' in l or '"stream_sync"' in l]
     assert len(waits) > 50
@@ -75,10 +75,60 @@ def test_detector_has_teeth(logs, mode, tmp_path):
 def test_allocation_time_fills_are_completed_before_use(logs):
     """cudaMemset runs on the legacy default stream, which the context's non-blocking streams are not ordered behind: the
     fills at allocation time must be followed by a synchronisation of that stream (b2r.cu: finishFills)."""
-    t = stream_order.Trace(logs["default"], W, H)
+    t = stream_order.Trace(logs["default"])
     ops = t.ops
     fills = [i for i, o in enumerate(ops) if o["op"] == "memset"]
     assert fills
     for i in fills:
         nxt = next(o for o in ops[i + 1:] if o["op"] not in ("memset", "malloc"))
         assert nxt["op"] in ("stream_sync", "launch", "memcpy") and nxt["stream"] == 0, (ops[i], nxt)
+
+
+# ---- the sharded sort-first front end: N contexts of one process stand for the N ranks (tests/trace_scenarios/sharded.py)
+SHARDED = [(2, "default"), (2, "serial"), (2, "ring2"), (2, "ring3"), (2, "ring3sliced"), (3, "ring2"), (4, "default"), (4, "ring4sliced"), (8, "default"), (8, "ring3sliced")]
+
+
+@pytest.fixture(scope="module")
+def sharded_logs(trace_build, tmp_path_factory):
+    d = tmp_path_factory.mktemp("sharded_traces")
+    out = {}
+    for world, mode in SHARDED:
+        path = str(d / f"{world}_{mode}.jsonl")
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", "sharded.py"), str(world), mode], capture_output=True, text=True,
+                             timeout=300, env=dict(os.environ, B2R_TRACE_FILE=path, B2R_TRACE_DEVICES=str(world), **trace_build))
+        assert res.returncode == 0 and "scenario done" in res.stdout, res.stdout + res.stderr
+        out[(world, mode)] = path
+    return out
+
+
+@pytest.mark.parametrize("world,mode", SHARDED)
+def test_sharded_front_end_has_no_unordered_conflicting_accesses(sharded_logs, world, mode):
+    """Lists pushed into the peers' arenas, list sets re-used by later frames, colours stored into rank 0's surface and
+    copied to the host by a pipelined Present: every conflicting pair is ordered by the streams, the events and the
+    flag protocol (lists ready / colours landed / frame done) - default pipeline and the frame ring with the sliced vertex stage."""
+    t = stream_order.Trace(sharded_logs[(world, mode)])
+    races = t.analyse()
+    assert not t.warnings, sorted(set(t.warnings))[:5]
+    assert {o.get("dev", 0) for o in t.ops if o["op"] == "launch"} == set(range(world))
+    pushes = [o for o in t.ops if o["op"] == "launch" and "shard_push_lists" in o["kernel"]]
+    assert len(pushes) >= 20 * world
+    assert not races, "\n".join(t.describe(r) for r in races[:8])
+
+
+@pytest.mark.parametrize("world,mode", [(2, "default"), (2, "ring3"), (4, "ring4sliced")])
+def test_every_element_of_the_flag_protocol_is_load_bearing(sharded_logs, world, mode, tmp_path):
+    import json
+    lines = open(sharded_logs[(world, mode)]).readlines()
+
+    def barrier(line, base):
+        return '"launch"' in line and "peer_barrier" in line and stream_order.u32(json.loads(line)["args"][3]) == base
+
+    def races_without(pred):
+        p = tmp_path / "mutated.jsonl"
+        p.write_text("".join(l for l in lines if not pred(l)))
+        return len(stream_order.Trace(str(p)).analyse())
+    assert races_without(lambda l: barrier(l, 0)) > 50, "without the 'lists ready' barrier a tile owner reads lists that are still being pushed"
+    assert races_without(lambda l: barrier(l, 8)) > 0, "without the 'colours landed' wait rank 0 presents a frame its peers are still writing"
+    assert races_without(lambda l: "host_barrier" in l) > 0, "without the host barrier after bind a peer's first stores race with the arena's initial fill"
+    if mode.startswith("ring"):
+        assert races_without(lambda l: barrier(l, 16)) > 0, "without the 'frame done' wait a list set is overwritten while a peer still rasterises from it"

@@ -20,11 +20,12 @@ namespace {
 
 typedef int cudaError_t;
 struct dim3 { unsigned x, y, z; };
-struct Stream { int id; };
+struct Stream { int id; int dev; };
 struct Event { int id; };
 
 std::mutex g_mu;
 FILE* g_log = nullptr;
+thread_local int t_device = 0;        // cudaSetDevice: which context ("rank") is issuing - several can share this process
 int g_nextStream = 1, g_nextEvent = 1;
 std::map<const void*, std::string> g_kernelName;                 // host stub address -> mangled device name
 std::map<std::string, std::vector<std::pair<int, int>>> g_params; // mangled name -> (offset, size) by ordinal
@@ -59,7 +60,8 @@ void loadParams()
 	fclose(f);
 }
 int streamId(void* s) { return s ? static_cast<Stream*>(s)->id : 0; }
-#define LOG(...) do { std::lock_guard<std::mutex> lk_(g_mu); if (FILE* f_ = log()) { fprintf(f_, __VA_ARGS__); fputc('\n', f_); fflush(f_); } } while (0)
+// every line ends with the issuing device: {"op":...,"dev":d}
+#define LOG(fmt, ...) do { std::lock_guard<std::mutex> lk_(g_mu); if (FILE* f_ = log()) { fprintf(f_, fmt ",\"dev\":%d}\n", ##__VA_ARGS__, t_device); fflush(f_); } } while (0)
 
 void logLaunch(const void* func, dim3 grid, dim3 block, void** args, void* stream, int pdl)
 {
@@ -80,7 +82,7 @@ void logLaunch(const void* func, dim3 grid, dim3 block, void** args, void* strea
 			for (int b = 0; b < pit->second[i].second; ++b) fprintf(f, "%02x", a[b]);
 			fputc('"', f);
 		}
-	fprintf(f, "]}\n");
+	fprintf(f, "],\"dev\":%d}\n", t_device);
 	fflush(f);
 }
 
@@ -111,8 +113,13 @@ cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* shmem, v
 }
 
 // ---- device
-cudaError_t cudaGetDeviceCount(int* n) { *n = getenv("B2R_TRACE_NO_DEVICE") ? 0 : 1; return 0; }
-cudaError_t cudaSetDevice(int) { return 0; }
+cudaError_t cudaGetDeviceCount(int* n)
+{
+	const char* e = getenv("B2R_TRACE_DEVICES");       // several contexts of one process can stand for the ranks of a sharded group
+	*n = e ? atoi(e) : 1;
+	return 0;
+}
+cudaError_t cudaSetDevice(int d) { t_device = d; return 0; }
 cudaError_t cudaDeviceGetAttribute(int* v, int attr, int)
 {
 	switch (attr)
@@ -133,12 +140,12 @@ const char* cudaGetErrorString(cudaError_t e) { return e ? "fake runtime: unsupp
 cudaError_t cudaMalloc(void** p, size_t n)
 {
 	*p = calloc(n ? n : 1, 1);
-	LOG("{\"op\":\"malloc\",\"ptr\":%llu,\"size\":%zu}", (unsigned long long)(uintptr_t)*p, n);
+	LOG("{\"op\":\"malloc\",\"ptr\":%llu,\"size\":%zu", (unsigned long long)(uintptr_t)*p, n);
 	return *p ? 0 : 2;
 }
 cudaError_t cudaFree(void* p)
 {
-	if (p) LOG("{\"op\":\"free\",\"ptr\":%llu}", (unsigned long long)(uintptr_t)p);      // cudaFree synchronises the device
+	if (p) LOG("{\"op\":\"free\",\"ptr\":%llu", (unsigned long long)(uintptr_t)p);      // cudaFree synchronises the device
 	// the block is not returned to the heap: the log identifies allocations by address, and a recycled address would
 	// alias two different buffers
 	return 0;
@@ -146,47 +153,47 @@ cudaError_t cudaFree(void* p)
 cudaError_t cudaMallocHost(void** p, size_t n)
 {
 	*p = calloc(n ? n : 1, 1);
-	LOG("{\"op\":\"malloc_host\",\"ptr\":%llu,\"size\":%zu}", (unsigned long long)(uintptr_t)*p, n);
+	LOG("{\"op\":\"malloc_host\",\"ptr\":%llu,\"size\":%zu", (unsigned long long)(uintptr_t)*p, n);
 	return *p ? 0 : 2;
 }
 cudaError_t cudaFreeHost(void*) { return 0; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, int kind, void* stream)
 {
 	if (n) memmove(dst, src, n);
-	LOG("{\"op\":\"memcpy\",\"dst\":%llu,\"src\":%llu,\"bytes\":%zu,\"kind\":%d,\"stream\":%d,\"async\":1}", (unsigned long long)(uintptr_t)dst, (unsigned long long)(uintptr_t)src, n, kind, streamId(stream));
+	LOG("{\"op\":\"memcpy\",\"dst\":%llu,\"src\":%llu,\"bytes\":%zu,\"kind\":%d,\"stream\":%d,\"async\":1", (unsigned long long)(uintptr_t)dst, (unsigned long long)(uintptr_t)src, n, kind, streamId(stream));
 	return 0;
 }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, int kind)
 {
 	if (n) memmove(dst, src, n);
-	LOG("{\"op\":\"memcpy\",\"dst\":%llu,\"src\":%llu,\"bytes\":%zu,\"kind\":%d,\"stream\":0,\"async\":0}", (unsigned long long)(uintptr_t)dst, (unsigned long long)(uintptr_t)src, n, kind);
+	LOG("{\"op\":\"memcpy\",\"dst\":%llu,\"src\":%llu,\"bytes\":%zu,\"kind\":%d,\"stream\":0,\"async\":0", (unsigned long long)(uintptr_t)dst, (unsigned long long)(uintptr_t)src, n, kind);
 	return 0;
 }
 cudaError_t cudaMemset(void* p, int v, size_t n)
 {
 	if (n) memset(p, v, n);
-	LOG("{\"op\":\"memset\",\"dst\":%llu,\"bytes\":%zu,\"stream\":0}", (unsigned long long)(uintptr_t)p, n);
+	LOG("{\"op\":\"memset\",\"dst\":%llu,\"bytes\":%zu,\"stream\":0", (unsigned long long)(uintptr_t)p, n);
 	return 0;
 }
 
 // ---- streams and events
 cudaError_t cudaStreamCreateWithFlags(void** s, unsigned flags)
 {
-	Stream* st = new Stream{ g_nextStream++ };
+	Stream* st = new Stream{ g_nextStream++, t_device };
 	*s = st;
-	LOG("{\"op\":\"stream_create\",\"stream\":%d,\"flags\":%u}", st->id, flags);
+	LOG("{\"op\":\"stream_create\",\"stream\":%d,\"flags\":%u", st->id, flags);
 	return 0;
 }
 cudaError_t cudaStreamCreateWithPriority(void** s, unsigned flags, int) { return cudaStreamCreateWithFlags(s, flags); }
 cudaError_t cudaStreamDestroy(void*) { return 0; }
-cudaError_t cudaStreamSynchronize(void* s) { LOG("{\"op\":\"stream_sync\",\"stream\":%d}", streamId(s)); return 0; }
+cudaError_t cudaStreamSynchronize(void* s) { LOG("{\"op\":\"stream_sync\",\"stream\":%d", streamId(s)); return 0; }
 cudaError_t cudaEventCreateWithFlags(void** e, unsigned) { *e = new Event{ g_nextEvent++ }; return 0; }
 cudaError_t cudaEventCreate(void** e) { return cudaEventCreateWithFlags(e, 0); }
 cudaError_t cudaEventDestroy(void*) { return 0; }
-cudaError_t cudaEventRecord(void* e, void* s) { LOG("{\"op\":\"event_record\",\"event\":%d,\"stream\":%d}", static_cast<Event*>(e)->id, streamId(s)); return 0; }
-cudaError_t cudaEventSynchronize(void* e) { LOG("{\"op\":\"event_sync\",\"event\":%d}", static_cast<Event*>(e)->id); return 0; }
+cudaError_t cudaEventRecord(void* e, void* s) { LOG("{\"op\":\"event_record\",\"event\":%d,\"stream\":%d", static_cast<Event*>(e)->id, streamId(s)); return 0; }
+cudaError_t cudaEventSynchronize(void* e) { LOG("{\"op\":\"event_sync\",\"event\":%d", static_cast<Event*>(e)->id); return 0; }
 cudaError_t cudaEventElapsedTime(float* ms, void*, void*) { *ms = 0.01f; return 0; }
-cudaError_t cudaStreamWaitEvent(void* s, void* e, unsigned) { LOG("{\"op\":\"stream_wait\",\"stream\":%d,\"event\":%d}", streamId(s), static_cast<Event*>(e)->id); return 0; }
+cudaError_t cudaStreamWaitEvent(void* s, void* e, unsigned) { LOG("{\"op\":\"stream_wait\",\"stream\":%d,\"event\":%d", streamId(s), static_cast<Event*>(e)->id); return 0; }
 
 // ---- launches
 cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t, void* stream)
@@ -206,9 +213,13 @@ cudaError_t cudaLaunchKernelExC(const LaunchConfig* cfg, const void* func, void*
 	return 0;
 }
 
-// ---- IPC: not available without a device
-cudaError_t cudaIpcGetMemHandle(void*, void*) { return 801; }
-cudaError_t cudaIpcOpenMemHandle(void**, ...) { return 801; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return 801; }
+// ---- scenario marker: a host-side barrier between the ranks (what torch.distributed.barrier() is in a real group)
+void b2r_trace_host_barrier(void) { LOG("{\"op\":\"host_barrier\""); }
+
+// ---- IPC between the contexts of THIS process: the handle carries the address, opening it yields the same memory
+struct IpcHandle { char reserved[64]; };
+cudaError_t cudaIpcGetMemHandle(IpcHandle* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return 0; }
+cudaError_t cudaIpcOpenMemHandle(void** p, IpcHandle h, unsigned) { memcpy(p, h.reserved, sizeof *p); return *p ? 0 : 1; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
 
 }

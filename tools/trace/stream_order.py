@@ -1,29 +1,46 @@
 #!/usr/bin/env python
-"""Stream-order race detector for the frame scheduler - needs no GPU.
+"""Stream-order race detector for the frame schedulers - needs no GPU.
 
 Input: the JSON-lines log the recording CUDA runtime (tools/trace/fake_cudart.cpp) writes while the product's own host
 code (build/trace/libb2r_trace.so) runs.  Every device operation (kernel launch, copy, memset) becomes a node with the
-memory ranges it reads / writes; edges are what CUDA guarantees: order within a stream, event record -> stream wait,
-and host synchronisation (cudaStreamSynchronize / cudaEventSynchronize / cudaFree / blocking copies: everything the host
-has waited for precedes everything it issues afterwards).  Two operations CONFLICT when they touch overlapping bytes of
-an allocation, at least one of them writes, and neither is ordered before the other: that is a data race between
-frames in flight, whatever the timing on a real GPU happens to be.
+memory ranges it reads / writes; edges are what CUDA and the product's flag protocol guarantee:
+
+* order within a stream (the legacy default stream of a device is ordered in itself only: the product's streams are
+  non-blocking);
+* event record -> stream wait;
+* host synchronisation of the issuing context (cudaStreamSynchronize / cudaEventSynchronize / cudaFree / blocking
+  copies): what that host thread has waited for precedes everything it issues afterwards.  Several contexts of one
+  process stand for the ranks of a sharded group (the log carries the issuing device); a rank's host synchronisation
+  orders nothing for the other ranks;
+* a host-side barrier between the ranks (log marker written by the scenario where a real group calls
+  torch.distributed.barrier);
+* the cross-GPU flag protocol of the sharded front end, from the scalar arguments of the kernels that implement it:
+  peer_barrier_kernel(signal = 1, wait = 1, slot base b, epoch e) of all ranks form a barrier - everything before the
+  kernel on ANY rank precedes everything after it on EVERY rank; publish_info_kernel signals "colours landed" (to rank
+  0, flag words 8..) and, with the frame ring, "frame done" (to all ranks, words 16..) with its epoch;
+  peer_barrier_kernel(signal = 0, wait = 1, b, e) waits for those signals of all ranks.
+
+Two operations CONFLICT when they touch overlapping bytes, at least one of them writes, and neither is ordered before
+the other: a data race between frames in flight (or between ranks), whatever the timing on a real GPU happens to be.
 
 What a kernel touches is derived from its launch arguments: pointer parameters from the demangled signature
-(`const T*` = read, `T*` = write), the by-value structs RasterArgs / PeerFlags / ShardInbox / ShardRegions from their
-layout (csrc/raster_kernel.cuh, csrc/device_types.cuh).  A pointer argument stands for the range from the pointer to the
-end of its allocation, except the colour surface of the raster kernel (two surfaces share one allocation:
-width * height * 4 bytes).  Programmatic dependent launch does not relax stream order here: every kernel of the product
-begins with griddepcontrol.wait (pdlPrologue), i.e. waits for the completion and memory flush of its predecessor.
+(`const T*` = read, `T*` = write), the by-value structs RasterArgs / ShardInbox / ShardRegions from their layout
+(csrc/raster_kernel.cuh, csrc/device_types.cuh).  A pointer stands for the bytes from it to the next address that is
+ever passed to a kernel as a pointer into the same allocation (or the end of the allocation): sub-buffers carved out of
+one allocation - the two colour surfaces, the list sets / inboxes / regions of the shared arena - are told apart,
+because the base of every sub-buffer is some kernel's argument.  (A pointer into the MIDDLE of a logical buffer, e.g. a
+slice of the vertex chunks, narrows the range of the accesses through the buffer's base: possible false negatives, no
+false positives.)  The flag words themselves are accessed concurrently by design (volatile stores / polling) and are
+left out.  Programmatic dependent launch does not relax stream order here: every kernel of the product begins with
+griddepcontrol.wait (pdlPrologue), i.e. waits for the completion and memory flush of its predecessor.
 
-    python tools/trace/stream_order.py log.jsonl --width W --height H [-v]
+    python tools/trace/stream_order.py log.jsonl [-v]
 exit status 1 when a race is found.  tests/test_cpu_trace.py drives it."""
 from __future__ import annotations
 
 import argparse
 import bisect
 import json
-import re
 import subprocess
 import sys
 from collections import defaultdict
@@ -35,15 +52,18 @@ RASTER_ARGS += [(f"shard.tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(
     + [(f"shard.binIds[{i}]", "r") for i in range(K_MAX_RANKS)]
 STRUCTS = {
     "b2r::RasterArgs": RASTER_ARGS,
-    "b2r::PeerFlags": [(f"flags[{i}]", "w") for i in range(K_MAX_RANKS)],
+    "b2r::PeerFlags": [],                  # the flag words: concurrent by design, see above
     "b2r::ShardInbox": [(f"tileCount[{i}]", "w") for i in range(K_MAX_RANKS)] + [(f"tileOffset[{i}]", "w") for i in range(K_MAX_RANKS)],
     "b2r::ShardRegions": [(f"region[{i}]", "w") for i in range(K_MAX_RANKS)],
     "b2r::FrameParams": [],
 }
+FLAG_POINTERS = {("publish_info_kernel", 3), ("peer_barrier_kernel", 7)}       # landedFlag, timeoutFlag: flag / status words
 
 
 def demangle(names):
     names = sorted(set(names))
+    if not names:
+        return {}
     out = subprocess.run(["cu++filt"] + names, capture_output=True, text=True, check=True).stdout.splitlines()
     return dict(zip(names, out))
 
@@ -73,17 +93,29 @@ def split_params(sig):
     return sig[:i], parts
 
 
-class Trace:
-    def __init__(self, path, width, height):
-        self.ops = [json.loads(l) for l in open(path) if l.strip()]
-        self.width, self.height = width, height
-        self.allocs = []          # sorted list of (start, end, id, kind)
-        self.sig = demangle([o["kernel"] for o in self.ops if o["op"] == "launch"])
-        self.warnings = []
+def u32(raw):
+    return int.from_bytes(bytes.fromhex(raw)[:4], "little")
 
-    # ---- memory map
-    def add_alloc(self, ptr, size, kind):
-        bisect.insort(self.allocs, (ptr, ptr + max(size, 1), len(self.allocs), kind))
+
+class Trace:
+    def __init__(self, path):
+        self.ops = [json.loads(l) for l in open(path) if l.strip()]
+        self.sig = demangle([o["kernel"] for o in self.ops if o["op"] == "launch"])
+        self.parsed = {k: split_params(v) for k, v in self.sig.items()}
+        self.warnings = []
+        self.allocs = []          # sorted (start, end, id, kind)
+        for o in self.ops:
+            if o["op"] in ("malloc", "malloc_host"):
+                bisect.insort(self.allocs, (o["ptr"], o["ptr"] + max(o["size"], 1), len(self.allocs), "device" if o["op"] == "malloc" else "pinned"))
+        # sub-buffer boundaries: every address a kernel receives as a pointer
+        self.cuts = defaultdict(set)
+        for o in self.ops:
+            if o["op"] == "launch":
+                for _what, ptr, _mode in self.pointer_args(o)[1]:
+                    a = self.find(ptr)
+                    if a is not None:
+                        self.cuts[a[0]].add(ptr)
+        self.cuts = {k: sorted(v) for k, v in self.cuts.items()}
 
     def find(self, ptr):
         i = bisect.bisect_right(self.allocs, (ptr, float("inf"), 0, "")) - 1
@@ -91,37 +123,50 @@ class Trace:
             return self.allocs[i]
         return None
 
-    def region(self, ptr, nbytes=None):
-        a = self.find(ptr)
-        if a is None:
-            return None
-        return (a[0], ptr, a[1] if nbytes is None else min(ptr + nbytes, a[1]))      # (allocation, lo, hi)
+    def short(self, o):
+        return self.parsed[o["kernel"]][0].split("(")[0].replace("b2r::", "").replace("void ", "").split("<")[0]
 
-    # ---- accesses of one operation
-    def launch_accesses(self, o):
-        name, params = split_params(self.sig[o["kernel"]])
-        short = name.split("(")[0].replace("b2r::", "").replace("void ", "")
+    def pointer_args(self, o):
+        """(short kernel name, [(description, pointer, mode)]) of a launch."""
+        name, params = self.parsed[o["kernel"]]
+        short = self.short(o)
         args = o["args"]
         if len(args) != len(params):
             self.warnings.append(f"{short}: {len(args)} logged arguments for {len(params)} parameters")
             return short, []
         acc = []
-        for ptype, raw in zip(params, args):
+        for k, (ptype, raw) in enumerate(zip(params, args)):
             b = bytes.fromhex(raw)
             if ptype.endswith("*"):
                 ptr = int.from_bytes(b[:8], "little")
-                if ptr:
-                    acc.append((ptype, ptr, "r" if ptype.startswith("const ") else "w", None))
+                if ptr and (short, k) not in FLAG_POINTERS:
+                    acc.append((f"arg {k} ({ptype})", ptr, "r" if ptype.startswith("const ") else "w"))
             elif ptype in STRUCTS:
-                for k, (field, mode) in enumerate(STRUCTS[ptype]):
-                    ptr = int.from_bytes(b[8 * k:8 * k + 8], "little")
+                for j, (field, mode) in enumerate(STRUCTS[ptype]):
+                    ptr = int.from_bytes(b[8 * j:8 * j + 8], "little")
                     if ptr:
-                        acc.append((f"{ptype}.{field}", ptr, mode, self.width * self.height * 4 if field == "framebuffer" else None))
+                        acc.append((f"{ptype.replace('b2r::', '')}.{field}", ptr, mode))
             elif "*" in ptype or ptype.startswith("b2r::"):
                 self.warnings.append(f"{short}: parameter type {ptype} is not described")
+        return short, acc
+
+    def region(self, ptr, nbytes=None):
+        a = self.find(ptr)
+        if a is None:
+            return None
+        if nbytes is None:
+            cuts = self.cuts.get(a[0], [])
+            i = bisect.bisect_right(cuts, ptr)
+            hi = cuts[i] if i < len(cuts) else a[1]
+        else:
+            hi = min(ptr + nbytes, a[1])
+        return (a[0], ptr, hi)
+
+    def launch_accesses(self, o):
+        short, acc = self.pointer_args(o)
         out = []
-        for what, ptr, mode, nbytes in acc:
-            r = self.region(ptr, nbytes)
+        for what, ptr, mode in acc:
+            r = self.region(ptr)
             if r is None:
                 self.warnings.append(f"{short}: {what} = {ptr:#x} is not inside a known allocation")
             else:
@@ -130,42 +175,42 @@ class Trace:
 
     # ---- the graph
     def analyse(self):
-        nodes = []                # dicts: label, issue index, accesses [(region, mode, what)]
-        anc = []                  # ancestor bitsets
-        last_on_stream, last_record, host = {}, {}, None
+        nodes = []                                   # {label, idx, dev, acc, preds}
+        last_on_stream, last_record, host = {}, {}, {}
+        arrive = defaultdict(list)                   # (slot base, epoch) -> arrive nodes of the barrier kernels
+        complete = defaultdict(list)
+        signals = defaultdict(list)                  # (slot base, epoch) -> signalling nodes (publish_info_kernel)
+        waiters = defaultdict(list)
 
-        def node(label, preds, accesses=(), idx=None):
-            bits = 0
-            for p in preds:
-                if p is not None:
-                    bits |= anc[p] | (1 << p)
-            nodes.append({"label": label, "acc": list(accesses), "idx": idx})
-            anc.append(bits)
+        def node(label, preds, dev, acc=(), idx=None):
+            nodes.append({"label": label, "idx": idx, "dev": dev, "acc": list(acc), "preds": [p for p in preds if p is not None]})
             return len(nodes) - 1
 
-        def host_node(label, preds):
-            nonlocal host
-            host = node("host: " + label, [host] + list(preds))
+        def host_node(label, preds, dev):
+            host[dev] = node("host: " + label, [host.get(dev)] + list(preds), dev)
 
         for idx, o in enumerate(self.ops):
-            op = o["op"]
-            if op == "malloc":
-                self.add_alloc(o["ptr"], o["size"], "device")
-            elif op == "malloc_host":
-                self.add_alloc(o["ptr"], o["size"], "pinned")
+            op, dev = o["op"], o.get("dev", 0)
+            skey = (dev, 0) if o.get("stream", 1) == 0 else o.get("stream")
+            if op == "host_barrier":
+                # the ranks' host threads meet (torch.distributed.barrier in a real group): what any of them has waited for
+                # precedes everything any of them issues afterwards
+                n = node("host barrier between the ranks", list(host.values()), dev)
+                for d in {nd["dev"] for nd in nodes} | set(host):
+                    host[d] = n
             elif op == "free":
-                host_node("cudaFree", list(last_on_stream.values()))            # cudaFree synchronises the device
+                host_node("cudaFree", [n for k, n in last_on_stream.items() if nodes[n]["dev"] == dev], dev)     # synchronises the device
             elif op == "stream_sync":
-                host_node(f"sync stream {o['stream']}", [last_on_stream.get(o["stream"])])
+                host_node(f"sync stream {o['stream']}", [last_on_stream.get(skey)], dev)
             elif op == "event_sync":
-                host_node(f"sync event {o['event']}", [last_record.get(o["event"])])
+                host_node(f"sync event {o['event']}", [last_record.get(o["event"])], dev)
             elif op == "event_record":
-                n = node(f"record e{o['event']} on s{o['stream']}", [last_on_stream.get(o["stream"]), host], idx=idx)
-                last_on_stream[o["stream"]] = n
+                n = node(f"record e{o['event']} on s{o['stream']}", [last_on_stream.get(skey), host.get(dev)], dev, idx=idx)
+                last_on_stream[skey] = n
                 last_record[o["event"]] = n
             elif op == "stream_wait":
-                n = node(f"s{o['stream']} waits e{o['event']}", [last_on_stream.get(o["stream"]), last_record.get(o["event"]), host], idx=idx)
-                last_on_stream[o["stream"]] = n
+                n = node(f"s{o['stream']} waits e{o['event']}", [last_on_stream.get(skey), last_record.get(o["event"]), host.get(dev)], dev, idx=idx)
+                last_on_stream[skey] = n
             elif op in ("launch", "memcpy", "memset"):
                 if op == "launch":
                     label, acc = self.launch_accesses(o)
@@ -180,16 +225,64 @@ class Trace:
                     r = self.region(o["dst"], o["bytes"])
                     if r is not None:
                         acc.append((r, "w", "dst"))
-                s = o["stream"]
-                blocking = op == "memcpy" and not o["async"]
-                # stream 0 = the legacy default stream: ordered in itself, but it does not order anything against the
-                # product's non-blocking streams
-                n = node(f"{label} on s{s}", [last_on_stream.get(s), host], acc, idx)
-                last_on_stream[s] = n
-                if blocking:
-                    host_node("blocking copy", [n])
-        self.nodes, self.anc = nodes, anc
+                tag = f"{label} on s{o['stream']}" + (f" (rank {dev})" if dev else "")
+                if op == "launch" and label == "peer_barrier_kernel":
+                    a = o["args"]
+                    base, epoch, signal, wait = u32(a[3]), u32(a[4]), u32(a[5]), u32(a[6])
+                    n_arrive = node(tag + f" [arrive {base}/{epoch}]", [last_on_stream.get(skey), host.get(dev)], dev, idx=idx)
+                    n = node(tag + f" [pass {base}/{epoch}]", [n_arrive], dev, idx=idx)
+                    if signal:
+                        arrive[(base, epoch)].append(n_arrive)
+                        complete[(base, epoch)].append(n)
+                    elif wait:
+                        waiters[(base, epoch)].append(n)
+                else:
+                    n = node(tag, [last_on_stream.get(skey), host.get(dev)], dev, acc, idx)
+                    if op == "launch" and label == "publish_info_kernel":
+                        a = o["args"]
+                        landed, epoch, done_ranks = int.from_bytes(bytes.fromhex(a[3])[:8], "little"), u32(a[4]), u32(a[6])
+                        if landed:
+                            signals[(8, epoch)].append(n)
+                        if done_ranks:
+                            signals[(16, epoch)].append(n)
+                last_on_stream[skey] = n
+                if op == "memcpy" and not o["async"]:
+                    host_node("blocking copy", [n], dev)
+        for key, cs in complete.items():             # barrier: every arrival precedes every completion
+            for c in cs:
+                nodes[c]["preds"] += arrive[key]
+        for key, ws in waiters.items():              # one-way waits: every rank's signal of that epoch precedes the waiter
+            for w in ws:
+                nodes[w]["preds"] += signals.get(key, [])
+        self.nodes = nodes
+        self.reach()
         return self.races()
+
+    def reach(self):
+        n = len(self.nodes)
+        succ = [[] for _ in range(n)]
+        indeg = [0] * n
+        for j, nd in enumerate(self.nodes):
+            for p in set(nd["preds"]):
+                succ[p].append(j)
+                indeg[j] += 1
+        order, stack = [], [i for i in range(n) if indeg[i] == 0]
+        while stack:
+            i = stack.pop()
+            order.append(i)
+            for j in succ[i]:
+                indeg[j] -= 1
+                if indeg[j] == 0:
+                    stack.append(j)
+        if len(order) != n:
+            raise RuntimeError("the ordering constraints contain a cycle: the schedule would deadlock")
+        anc = [0] * n
+        for j in order:
+            bits = 0
+            for p in self.nodes[j]["preds"]:
+                bits |= anc[p] | (1 << p)
+            anc[j] = bits
+        self.anc = anc
 
     def races(self):
         by_alloc = defaultdict(list)
@@ -204,7 +297,11 @@ class Trace:
                     ni, loi, hii, mi, wi = accs[i]
                     if ni == nj or (mi == "r" and mj == "r") or hii <= loj or hij <= loi:
                         continue
-                    if not (self.anc[nj] >> ni) & 1:
+                    # sharded front end: all ranks store their tiles' colours into rank 0's surface; tile ownership is
+                    # static (tile index mod ranks), so two ranks never write the same pixel, in whatever frames
+                    if wi == wj == "RasterArgs.framebuffer" and self.nodes[ni]["dev"] != self.nodes[nj]["dev"]:
+                        continue
+                    if not ((self.anc[nj] >> ni) & 1 or (self.anc[ni] >> nj) & 1):
                         found.append((ni, nj, alloc, wi, wj, mi, mj))
         return found
 
@@ -219,11 +316,9 @@ class Trace:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("log")
-    ap.add_argument("--width", type=int, required=True)
-    ap.add_argument("--height", type=int, required=True)
     ap.add_argument("-v", action="store_true")
     a = ap.parse_args()
-    t = Trace(a.log, a.width, a.height)
+    t = Trace(a.log)
     races = t.analyse()
     launches = sum(1 for o in t.ops if o["op"] == "launch")
     print(f"{len(t.ops)} logged operations, {launches} kernel launches, {len(t.nodes)} graph nodes, {len(t.allocs)} allocations, {len(races)} unordered conflicting pairs")
