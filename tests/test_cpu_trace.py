@@ -47,6 +47,7 @@ def test_no_unordered_conflicting_accesses(logs, mode):
     t = stream_order.Trace(logs[mode])
     races = t.analyse()
     assert not t.warnings, sorted(set(t.warnings))[:5]                      # every pointer argument was resolved to an allocation
+    assert not t.bad_launches()
     launches = [o for o in t.ops if o["op"] == "launch"]
     assert len(launches) > 300 and all(o["args"] for o in launches)
     streams = {o["stream"] for o in launches}
@@ -110,6 +111,7 @@ def test_sharded_front_end_has_no_unordered_conflicting_accesses(sharded_logs, w
     races = t.analyse()
     assert not t.warnings, sorted(set(t.warnings))[:5]
     assert {o.get("dev", 0) for o in t.ops if o["op"] == "launch"} == set(range(world))
+    assert not t.bad_launches()
     pushes = [o for o in t.ops if o["op"] == "launch" and "shard_push_lists" in o["kernel"]]
     assert len(pushes) >= 20 * world
     assert not races, "\n".join(t.describe(r) for r in races[:8])
@@ -132,3 +134,21 @@ def test_every_element_of_the_flag_protocol_is_load_bearing(sharded_logs, world,
     assert races_without(lambda l: "host_barrier" in l) > 0, "without the host barrier after bind a peer's first stores race with the arena's initial fill"
     if mode.startswith("ring"):
         assert races_without(lambda l: barrier(l, 16)) > 0, "without the 'frame done' wait a list set is overwritten while a peer still rasterises from it"
+
+
+@pytest.mark.parametrize("world,mode,tris", [(1, "default", 0), (1, "ring3", 0), (2, "default", 150), (2, "ring3sliced", 150), (8, "default", 150),
+                                             (8, "ring3sliced", 150), (8, "ring2sliced", 1500)])
+def test_degenerate_work_sizes(trace_build, tmp_path, world, mode, tris):
+    """Empty scene; fewer primitive blocks than ranks (ranks with an empty slice, and no vertex chunk when the vertex stage is
+    sliced): every launch has a valid configuration and the frames are still ordered."""
+    path = str(tmp_path / "log.jsonl")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", "tiny.py"), str(world), mode, str(tris)], capture_output=True, text=True,
+                         timeout=300, env=dict(os.environ, B2R_TRACE_FILE=path, B2R_TRACE_DEVICES=str(world), **trace_build))
+    assert res.returncode == 0 and "done" in res.stdout, res.stdout + res.stderr
+    t = stream_order.Trace(path)
+    races = t.analyse()
+    assert not t.bad_launches(), t.bad_launches()
+    assert not t.warnings, sorted(set(t.warnings))[:5]
+    # (no host barrier marker in this scenario: the arena's initial fill vs the peers' first stores is the host barrier's job)
+    races = [r for r in races if not t.nodes[r[0]]["label"].startswith("memset")]
+    assert not races, "\n".join(t.describe(r) for r in races[:8])

@@ -173,6 +173,16 @@ class Trace:
                 out.append((r, mode, what))
         return short, out
 
+    def bad_launches(self):
+        """Launch configurations a real device rejects (cudaErrorInvalidConfiguration) but the recording runtime accepts."""
+        bad = []
+        for o in self.ops:
+            if o["op"] == "launch":
+                g, b = o["grid"], o["block"]
+                if min(g) < 1 or min(b) < 1 or g[0] > 2**31 - 1 or g[1] > 65535 or g[2] > 65535 or b[0] * b[1] * b[2] > 1024:
+                    bad.append(f"{self.short(o)} grid {g} block {b}")
+        return bad
+
     # ---- the graph
     def analyse(self):
         nodes = []                                   # {label, idx, dev, acc, preds}
@@ -324,6 +334,8 @@ def main():
     print(f"{len(t.ops)} logged operations, {launches} kernel launches, {len(t.nodes)} graph nodes, {len(t.allocs)} allocations, {len(races)} unordered conflicting pairs")
     for w in sorted(set(t.warnings)):
         print("warning:", w)
+    for b in t.bad_launches():
+        print("INVALID LAUNCH:", b)
     seen = set()
     for r in races:
         key = (t.nodes[r[0]]["label"].split(" on ")[0], t.nodes[r[1]]["label"].split(" on ")[0], r[3], r[4])
@@ -331,7 +343,7 @@ def main():
             continue
         seen.add(key)
         print("RACE:", t.describe(r))
-    return 1 if races else 0
+    return 1 if races or t.bad_launches() else 0
 
 
 if __name__ == "__main__":
