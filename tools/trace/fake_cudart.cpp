@@ -156,7 +156,7 @@ cudaError_t cudaMallocHost(void** p, size_t n)
 	LOG("{\"op\":\"malloc_host\",\"ptr\":%llu,\"size\":%zu", (unsigned long long)(uintptr_t)*p, n);
 	return *p ? 0 : 2;
 }
-cudaError_t cudaFreeHost(void*) { return 0; }
+cudaError_t cudaFreeHost(void* p) { if (p) LOG("{\"op\":\"free_host\",\"ptr\":%llu", (unsigned long long)(uintptr_t)p); return 0; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, int kind, void* stream)
 {
 	if (n) memmove(dst, src, n);

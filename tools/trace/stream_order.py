@@ -173,6 +173,16 @@ class Trace:
                 out.append((r, mode, what))
         return short, out
 
+    def leaks(self):
+        """Device and pinned allocations that are never released (the scenario destroys its contexts before it ends)."""
+        live = {}
+        for o in self.ops:
+            if o["op"] in ("malloc", "malloc_host"):
+                live[o["ptr"]] = (o["op"], o["size"])
+            elif o["op"] in ("free", "free_host"):
+                live.pop(o["ptr"], None)
+        return live
+
     def bad_launches(self):
         """Launch configurations a real device rejects (cudaErrorInvalidConfiguration) but the recording runtime accepts."""
         bad = []
