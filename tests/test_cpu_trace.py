@@ -47,7 +47,7 @@ def test_no_unordered_conflicting_accesses(logs, mode):
     t = stream_order.Trace(logs[mode])
     races = t.analyse()
     assert not t.warnings, sorted(set(t.warnings))[:5]                      # every pointer argument was resolved to an allocation
-    assert not t.bad_launches()
+    assert not t.bad_launches() and not t.api_errors()
     assert not t.leaks(), f"allocations alive after b2r_destroy: {list(t.leaks().values())[:6]}"
     launches = [o for o in t.ops if o["op"] == "launch"]
     assert len(launches) > 300 and all(o["args"] for o in launches)
@@ -112,7 +112,7 @@ def test_sharded_front_end_has_no_unordered_conflicting_accesses(sharded_logs, w
     races = t.analyse()
     assert not t.warnings, sorted(set(t.warnings))[:5]
     assert {o.get("dev", 0) for o in t.ops if o["op"] == "launch"} == set(range(world))
-    assert not t.bad_launches()
+    assert not t.bad_launches() and not t.api_errors()
     assert not t.leaks(), f"allocations alive after b2r_shard_release + b2r_destroy: {list(t.leaks().values())[:6]}"
     pushes = [o for o in t.ops if o["op"] == "launch" and "shard_push_lists" in o["kernel"]]
     assert len(pushes) >= 20 * world

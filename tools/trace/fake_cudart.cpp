@@ -21,7 +21,7 @@ namespace {
 typedef int cudaError_t;
 struct dim3 { unsigned x, y, z; };
 struct Stream { int id; int dev; };
-struct Event { int id; };
+struct Event { int id; unsigned flags; bool recorded; };
 
 std::mutex g_mu;
 FILE* g_log = nullptr;
@@ -195,12 +195,19 @@ cudaError_t cudaStreamCreateWithFlags(void** s, unsigned flags)
 cudaError_t cudaStreamCreateWithPriority(void** s, unsigned flags, int) { return cudaStreamCreateWithFlags(s, flags); }
 cudaError_t cudaStreamDestroy(void*) { return 0; }
 cudaError_t cudaStreamSynchronize(void* s) { LOG("{\"op\":\"stream_sync\",\"stream\":%d", streamId(s)); return 0; }
-cudaError_t cudaEventCreateWithFlags(void** e, unsigned) { *e = new Event{ g_nextEvent++ }; return 0; }
+cudaError_t cudaEventCreateWithFlags(void** e, unsigned flags) { *e = new Event{ g_nextEvent++, flags, false }; return 0; }
 cudaError_t cudaEventCreate(void** e) { return cudaEventCreateWithFlags(e, 0); }
 cudaError_t cudaEventDestroy(void*) { return 0; }
-cudaError_t cudaEventRecord(void* e, void* s) { LOG("{\"op\":\"event_record\",\"event\":%d,\"stream\":%d", static_cast<Event*>(e)->id, streamId(s)); return 0; }
+cudaError_t cudaEventRecord(void* e, void* s) { static_cast<Event*>(e)->recorded = true; LOG("{\"op\":\"event_record\",\"event\":%d,\"stream\":%d", static_cast<Event*>(e)->id, streamId(s)); return 0; }
 cudaError_t cudaEventSynchronize(void* e) { LOG("{\"op\":\"event_sync\",\"event\":%d", static_cast<Event*>(e)->id); return 0; }
-cudaError_t cudaEventElapsedTime(float* ms, void*, void*) { *ms = 0.01f; return 0; }
+cudaError_t cudaEventElapsedTime(float* ms, void* a, void* b)
+{
+	// what a real device rejects: events created with cudaEventDisableTiming (flag 2), events never recorded
+	const Event* ea = static_cast<Event*>(a); const Event* eb = static_cast<Event*>(b);
+	if ((ea->flags & 2u) || (eb->flags & 2u) || !ea->recorded || !eb->recorded) { LOG("{\"op\":\"api_error\",\"what\":\"cudaEventElapsedTime on an event without timing or never recorded\""); return 400; }
+	*ms = 0.01f;
+	return 0;
+}
 cudaError_t cudaStreamWaitEvent(void* s, void* e, unsigned) { LOG("{\"op\":\"stream_wait\",\"stream\":%d,\"event\":%d", streamId(s), static_cast<Event*>(e)->id); return 0; }
 
 // ---- launches

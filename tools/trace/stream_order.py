@@ -173,6 +173,10 @@ class Trace:
                 out.append((r, mode, what))
         return short, out
 
+    def api_errors(self):
+        """Calls the recording runtime refused because a real device would (e.g. elapsed time between events without timing)."""
+        return [o["what"] for o in self.ops if o["op"] == "api_error"]
+
     def leaks(self):
         """Device and pinned allocations that are never released (the scenario destroys its contexts before it ends)."""
         live = {}
