@@ -155,3 +155,25 @@ def test_degenerate_work_sizes(trace_build, tmp_path, world, mode, tris):
     # (no host barrier marker in this scenario: the arena's initial fill vs the peers' first stores is the host barrier's job)
     races = [r for r in races if not t.nodes[r[0]]["label"].startswith("memset")]
     assert not races, "\n".join(t.describe(r) for r in races[:8])
+
+
+@pytest.mark.parametrize("argv", [["--steps", "6", "--warmup", "3", "--no-cpu-baseline"],
+                                  ["--workload", "views172", "--steps", "8"],
+                                  ["--workload", "vehicle1080", "--steps", "5", "--no-cpu-baseline"]], ids=["spheres10m+fill64", "views172", "vehicle1080"])
+def test_bench_gpu_arm_end_to_end_on_the_tracing_build(trace_build, tmp_path, argv):
+    """bench.py with the REAL ctypes Renderer and C ABI (only torch.cuda is replaced): every call bench.py makes is marshalled
+    correctly, one JSON line comes out, and bench's own usage pattern (timed loop, unsorted-list frames, pipelined Present
+    loop, stage timers, fragment counting, the fill test's second context) is race-free."""
+    import json
+    path = str(tmp_path / "log.jsonl")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", "bench_dry.py"), *argv], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, B2R_TRACE_FILE=path, **trace_build))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+    t = stream_order.Trace(path)
+    races = t.analyse()
+    assert not t.warnings and not t.bad_launches() and not t.api_errors() and not t.leaks()
+    assert not races, "\n".join(t.describe(r) for r in races[:8])
