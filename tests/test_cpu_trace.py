@@ -177,3 +177,33 @@ def test_bench_gpu_arm_end_to_end_on_the_tracing_build(trace_build, tmp_path, ar
     races = t.analyse()
     assert not t.warnings and not t.bad_launches() and not t.api_errors() and not t.leaks()
     assert not races, "\n".join(t.describe(r) for r in races[:8])
+
+
+def test_api_misuse_returns_status_codes(trace_build, tmp_path):
+    """69 wrong calls (order, ids, null pointers, sizes, options at the wrong time): each returns a negative status with a
+    message, none crashes, and the context renders a normal frame afterwards."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", "api_misuse.py")], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, B2R_TRACE_FILE=str(tmp_path / "log.jsonl"), **trace_build))
+    assert res.returncode == 0 and "checks passed" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "FAIL" not in res.stdout
+
+
+@pytest.mark.skipif(os.environ.get("B2R_SLOW_TESTS") != "1", reason="builds an AddressSanitizer variant of the tracing library (~1 min; set B2R_SLOW_TESTS=1)")
+def test_host_code_is_clean_under_address_sanitizer(tmp_path):
+    """The product's host code (schedulers, uploads, the veneer's OBJ parser / PNG decoder, error paths) under ASan."""
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not shutil.which("nvcc"):
+        pytest.skip("libasan / nvcc not available")
+    subprocess.check_call(["bash", os.path.join(ROOT, "tools", "trace", "build.sh"), "--asan"], stdout=subprocess.DEVNULL)
+    out = os.path.join(ROOT, "build", "trace_asan")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", B2R_LIBRARY=os.path.join(out, "libb2r_trace.so"),
+               B2R_TRACE_PARAMS=os.path.join(out, "kernel_params.txt"))
+    runs = [("frames.py", ["default"], 1), ("frames.py", ["ring3"], 1), ("sharded.py", ["2", "default"], 2), ("sharded.py", ["4", "ring3sliced"], 4),
+            ("tiny.py", ["8", "ring3sliced", "150"], 8), ("api_misuse.py", [], 1)]
+    for script, args, devices in runs:
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", script), *args], capture_output=True, text=True, timeout=600,
+                             env=dict(env, B2R_TRACE_FILE=str(tmp_path / "log.jsonl"), B2R_TRACE_DEVICES=str(devices)))
+        assert res.returncode == 0 and "AddressSanitizer" not in res.stderr, (script, args, res.stdout[-800:], res.stderr[-3000:])
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_cpu_host.py"), "-q", "-x", "-p", "no:cacheprovider",
+                          "-k", "objparser or png or camera or mesh_world or null_context or bad_resolution"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert res.returncode == 0 and "AddressSanitizer" not in res.stderr, res.stdout[-2000:] + res.stderr[-3000:]

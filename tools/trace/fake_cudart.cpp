@@ -233,7 +233,7 @@ void b2r_trace_host_barrier(void) { LOG("{\"op\":\"host_barrier\""); }
 
 // ---- IPC between the contexts of THIS process: the handle carries the address, opening it yields the same memory
 struct IpcHandle { char reserved[64]; };
-cudaError_t cudaIpcGetMemHandle(IpcHandle* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return 0; }
+cudaError_t cudaIpcGetMemHandle(IpcHandle* h, void* p) { if (!h || !p) return 1; memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return 0; }
 cudaError_t cudaIpcOpenMemHandle(void** p, IpcHandle h, unsigned) { memcpy(p, h.reserved, sizeof *p); return *p ? 0 : 1; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
 
