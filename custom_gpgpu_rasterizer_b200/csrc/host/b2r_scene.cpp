@@ -110,9 +110,9 @@ Mesh::Mesh(const std::vector<IVertex>& vertexBuffer, short stride, short type,
 	: Mesh{ nullptr, (unsigned int)vertexBuffer.size(), stride, type, nullptr, (unsigned int)indexBuffer.size(), topology, pos }
 {
 	m_pVertexBuffer = new IVertex[m_NumVertices];
-	memcpy((void*)m_pVertexBuffer, vertexBuffer.data(), sizeof(IVertex) * m_NumVertices);
+	if (m_NumVertices) memcpy((void*)m_pVertexBuffer, vertexBuffer.data(), sizeof(IVertex) * m_NumVertices);     // (empty vector: data() may be null)
 	m_pIndexBuffer = new unsigned int[m_NumIndices];
-	memcpy(m_pIndexBuffer, indexBuffer.data(), sizeof(unsigned int) * m_NumIndices);
+	if (m_NumIndices) memcpy(m_pIndexBuffer, indexBuffer.data(), sizeof(unsigned int) * m_NumIndices);
 	// the reference's copying constructor translates a second time after delegating (Mesh.cpp:12)
 	m_Position += FVector3{ pos.x, pos.y, pos.z };
 }

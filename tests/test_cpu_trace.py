@@ -190,7 +190,7 @@ def test_api_misuse_returns_status_codes(trace_build, tmp_path):
 
 @pytest.mark.skipif(os.environ.get("B2R_SLOW_TESTS") != "1", reason="builds an AddressSanitizer variant of the tracing library (~1 min; set B2R_SLOW_TESTS=1)")
 def test_host_code_is_clean_under_address_sanitizer(tmp_path):
-    """The product's host code (schedulers, uploads, the veneer's OBJ parser / PNG decoder, error paths) under ASan."""
+    """The product's host code (schedulers, uploads, the veneer's OBJ parser / PNG decoder, error paths) under ASan + UBSan."""
     asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not shutil.which("nvcc"):
         pytest.skip("libasan / nvcc not available")
@@ -203,7 +203,7 @@ def test_host_code_is_clean_under_address_sanitizer(tmp_path):
     for script, args, devices in runs:
         res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_scenarios", script), *args], capture_output=True, text=True, timeout=600,
                              env=dict(env, B2R_TRACE_FILE=str(tmp_path / "log.jsonl"), B2R_TRACE_DEVICES=str(devices)))
-        assert res.returncode == 0 and "AddressSanitizer" not in res.stderr, (script, args, res.stdout[-800:], res.stderr[-3000:])
+        assert res.returncode == 0 and "AddressSanitizer" not in res.stderr and "runtime error" not in res.stderr, (script, args, res.stdout[-800:], res.stderr[-3000:])
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_cpu_host.py"), "-q", "-x", "-p", "no:cacheprovider",
                           "-k", "objparser or png or camera or mesh_world or null_context or bad_resolution"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert res.returncode == 0 and "AddressSanitizer" not in res.stderr, res.stdout[-2000:] + res.stderr[-3000:]
