@@ -207,3 +207,15 @@ def test_host_code_is_clean_under_address_sanitizer(tmp_path):
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_cpu_host.py"), "-q", "-x", "-p", "no:cacheprovider",
                           "-k", "objparser or png or camera or mesh_world or null_context or bad_resolution"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert res.returncode == 0 and "AddressSanitizer" not in res.stderr, res.stdout[-2000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("B2R_SLOW_TESTS") != "1", reason="builds a ThreadSanitizer variant of the tracing library (~1 min; set B2R_SLOW_TESTS=1)")
+def test_independent_contexts_on_concurrent_threads_under_thread_sanitizer():
+    """"Thread-compatible per handle": four host threads drive four contexts at the same time (uploads, frames in flight, ring
+    option, read-backs, destroy) while a fifth exercises b2r_create's per-thread error text; TSan sees no shared mutable state."""
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not available")
+    subprocess.check_call(["bash", os.path.join(ROOT, "tools", "trace", "build.sh"), "--tsan"], stdout=subprocess.DEVNULL)
+    out = os.path.join(ROOT, "build", "trace_tsan")
+    res = subprocess.run([os.path.join(out, "threads")], capture_output=True, text=True, timeout=600, env=dict(os.environ, B2R_TRACE_PARAMS=os.path.join(out, "kernel_params.txt")))
+    assert res.returncode == 0 and "0 failures" in res.stdout and "ThreadSanitizer" not in res.stderr, res.stdout[-500:] + res.stderr[-3000:]
