@@ -48,6 +48,10 @@ def test_no_unordered_conflicting_accesses(logs, mode):
     races = t.analyse()
     assert not t.warnings, sorted(set(t.warnings))[:5]                      # every pointer argument was resolved to an allocation
     assert not t.bad_launches() and not t.api_errors()
+    assert not t.wiring_errors(), t.wiring_errors()[:4]
+    sets = t.buffer_sets(0, "tileCount")[:8]                  # the first frames, all enqueued back to back
+    depth = {"default": 2, "serial": 1, "novertex": 1, "ring2": 2, "ring3": 3, "ring4": 4}[mode]
+    assert len(set(sets)) == depth and all(sets[i] == sets[i + depth] for i in range(len(sets) - depth)), [hex(x) for x in sets]
     assert not t.leaks(), f"allocations alive after b2r_destroy: {list(t.leaks().values())[:6]}"
     launches = [o for o in t.ops if o["op"] == "launch"]
     assert len(launches) > 300 and all(o["args"] for o in launches)
@@ -113,6 +117,7 @@ def test_sharded_front_end_has_no_unordered_conflicting_accesses(sharded_logs, w
     assert not t.warnings, sorted(set(t.warnings))[:5]
     assert {o.get("dev", 0) for o in t.ops if o["op"] == "launch"} == set(range(world))
     assert not t.bad_launches() and not t.api_errors()
+    assert not t.wiring_errors(world), t.wiring_errors(world)[:4]
     assert not t.leaks(), f"allocations alive after b2r_shard_release + b2r_destroy: {list(t.leaks().values())[:6]}"
     pushes = [o for o in t.ops if o["op"] == "launch" and "shard_push_lists" in o["kernel"]]
     assert len(pushes) >= 20 * world
@@ -219,3 +224,31 @@ def test_independent_contexts_on_concurrent_threads_under_thread_sanitizer():
     out = os.path.join(ROOT, "build", "trace_tsan")
     res = subprocess.run([os.path.join(out, "threads")], capture_output=True, text=True, timeout=600, env=dict(os.environ, B2R_TRACE_PARAMS=os.path.join(out, "kernel_params.txt")))
     assert res.returncode == 0 and "0 failures" in res.stdout and "ThreadSanitizer" not in res.stderr, res.stdout[-500:] + res.stderr[-3000:]
+
+
+def test_wiring_check_has_teeth(logs, sharded_logs, tmp_path):
+    """A raster kernel given the lists of the other buffer set, and a tile owner given a peer's heads from the wrong list
+    set, are ordered accesses (no race) - the pointer-level dataflow check is what catches them."""
+    import json
+
+    def mutate(path, pick, patch):
+        lines = open(path).readlines()
+        idx = [i for i, l in enumerate(lines) if '"launch"' in l and "raster_shade" in l and pick(l)]
+        a, b = json.loads(lines[idx[4]]), json.loads(lines[idx[5]])
+        raw = bytearray(bytes.fromhex(a["args"][0]))
+        patch(raw, bytes.fromhex(b["args"][0]))
+        a["args"][0] = raw.hex()
+        lines[idx[4]] = json.dumps(a) + "\n"
+        p = tmp_path / "mutated.jsonl"
+        p.write_text("".join(lines))
+        return stream_order.Trace(str(p))
+
+    def other_lists(raw, nxt):
+        raw[16:24] = nxt[16:24]                  # RasterArgs.binIds of the next frame (the other set)
+    t = mutate(logs["default"], lambda l: True, other_lists)
+    assert any("binIds" in e for e in t.wiring_errors())
+
+    def other_inbox(raw, nxt):
+        raw[14 * 8:15 * 8] = nxt[14 * 8:15 * 8]  # RasterArgs.shard.tileCount[0] of the next frame's list set
+    t = mutate(sharded_logs[(2, "ring3")], lambda l: '"dev":1' in l, other_inbox)
+    assert any("reads the heads of rank 0" in e for e in t.wiring_errors(2))

@@ -173,6 +173,100 @@ class Trace:
                 out.append((r, mode, what))
         return short, out
 
+    # ---- wiring: does every kernel of a frame work on that frame's buffers?
+    ROLES = {      # logical buffer -> argument index, per kernel (csrc/b2r.cu: enqueueFrame / enqueueFrameRing / enqueueListSort)
+        "frame_clear_kernel": {"tileCount": 0, "counters": 2, "frameInfo": 3, "hViewProj": 6, "meshStatic": 7, "meshConst": 8},
+        "build_constants_kernel": {"hViewProj": 0, "meshStatic": 1, "meshConst": 2},
+        "vertex_transform_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3},
+        "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5},
+        "bin_big_count_kernel": {"bigList": 0, "counters": 1, "rects": 2, "tileCount": 3},
+        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "midTiles": 7, "longTiles": 8, "smallTiles": 9, "counters": 10, "frameInfo": 11},
+        "bin_scatter_kernel": {"rects": 0, "tileOffset": 3, "tileCursor": 4, "binIds": 5, "bigList": 6, "counters": 7, "frameInfo": 9},
+        "bin_sort_runs_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "smallTiles": 3, "midTiles": 4, "frameInfo": 5},
+        "bin_sort_mid_kernel": {"midTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
+        "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
+        "shard_push_heads_kernel": {"tileCount": 0, "tileOffset": 1},
+        "shard_push_lists_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 7},
+        "publish_info_kernel": {"frameInfo": 0},
+    }
+    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "posIn": 5, "meshConst": 7, "frameInfo": 9}
+
+    def frames(self):
+        """Per device: the launches of every frame, in the order the host issued them (b2r_render issues a whole frame; a
+        frame starts with its constants / clear kernel and ends with publish_info_kernel)."""
+        out, cur = defaultdict(list), {}
+        for o in self.ops:
+            if o["op"] != "launch":
+                continue
+            dev, k = o.get("dev", 0), self.short(o)
+            if k in ("build_constants_kernel", "frame_clear_kernel") and dev not in cur:
+                cur[dev] = []
+            if dev in cur:
+                cur[dev].append(o)
+                if k == "publish_info_kernel":
+                    out[dev].append(cur.pop(dev))
+        return out
+
+    @staticmethod
+    def _ptr(raw, index=0):
+        return int.from_bytes(bytes.fromhex(raw)[8 * index:8 * index + 8], "little")
+
+    def frame_buffers(self, frame):
+        """logical buffer -> {pointer: [kernels]} over the launches of one frame."""
+        seen = defaultdict(lambda: defaultdict(list))
+        for o in frame:
+            k = self.short(o)
+            if k == "raster_shade_kernel":
+                for name, j in self.RASTER_ROLES.items():
+                    seen[name][self._ptr(o["args"][0], j)].append(k)
+            for name, j in self.ROLES.get(k, {}).items():
+                seen[name][self._ptr(o["args"][j])].append(k)
+        return seen
+
+    def wiring_errors(self, ranks=1):
+        """Pointer-level dataflow of every frame: one buffer per logical role inside a frame (the raster kernel consumes the
+        lists, positions, constants and counters its own frame produced); sharded: the peers' heads and lists a tile owner
+        reads are the ones the peers pushed for that frame, and all ranks of a frame store into the same colour surface."""
+        errs = []
+        frames = self.frames()
+        for dev, fl in frames.items():
+            for i, frame in enumerate(fl):
+                for name, ptrs in self.frame_buffers(frame).items():
+                    if len(ptrs) > 1:
+                        errs.append(f"rank {dev} frame {i}: {name} is " + " but ".join(f"{p:#x} in {sorted(set(ks))}" for p, ks in ptrs.items()))
+        if ranks > 1:
+            n_frames = min(len(frames[d]) for d in range(ranks))
+            for i in range(n_frames):
+                get = lambda d, kernel: next((o for o in frames[d][i] if self.short(o) == kernel), None)      # noqa: E731
+                rasters = [get(d, "raster_shade_kernel") for d in range(ranks)]
+                heads = [get(d, "shard_push_heads_kernel") for d in range(ranks)]
+                lists = [get(d, "shard_push_lists_kernel") for d in range(ranks)]
+                if any(x is None for x in rasters + heads):
+                    errs.append(f"frame {i}: a rank has no raster / push-heads launch")
+                    continue
+                surfaces = {self._ptr(r["args"][0], 10) for r in rasters}
+                if len(surfaces) != 1:
+                    errs.append(f"frame {i}: the ranks store their colours into different surfaces {sorted(hex(x) for x in surfaces)}")
+                for q in range(ranks):                     # tile owner q reads ...
+                    for p in range(ranks):                 # ... what rank p pushed
+                        base = 14                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
+                        want_count, want_off = self._ptr(heads[p]["args"][3], q), self._ptr(heads[p]["args"][3], K_MAX_RANKS + q)
+                        got_count, got_off = self._ptr(rasters[q]["args"][0], base + p), self._ptr(rasters[q]["args"][0], base + K_MAX_RANKS + p)
+                        if (want_count, want_off) != (got_count, got_off):
+                            errs.append(f"frame {i}: rank {q} reads the heads of rank {p} at {got_count:#x}/{got_off:#x}, rank {p} pushed them to {want_count:#x}/{want_off:#x}")
+                        got_ids = self._ptr(rasters[q]["args"][0], base + 2 * K_MAX_RANKS + p)
+                        if p == q:
+                            want_ids = self._ptr(rasters[q]["args"][0], 2)
+                        else:
+                            want_ids = self._ptr(lists[p]["args"][4], q) if lists[p] is not None else got_ids
+                        if want_ids != got_ids:
+                            errs.append(f"frame {i}: rank {q} reads the lists of rank {p} at {got_ids:#x}, they are at {want_ids:#x}")
+        return errs
+
+    def buffer_sets(self, dev=0, name="tileCount"):
+        """The sequence of pointers a per-frame buffer takes over the frames of one device (ring slots / frame parity)."""
+        return [next(iter(self.frame_buffers(f)[name])) for f in self.frames()[dev]]
+
     def api_errors(self):
         """Calls the recording runtime refused because a real device would (e.g. elapsed time between events without timing)."""
         return [o["what"] for o in self.ops if o["op"] == "api_error"]
@@ -350,6 +444,10 @@ def main():
         print("warning:", w)
     for b in t.bad_launches():
         print("INVALID LAUNCH:", b)
+    ranks = len({o.get("dev", 0) for o in t.ops if o["op"] == "launch"})
+    wiring = t.wiring_errors(ranks)
+    for w in wiring[:20]:
+        print("WIRING:", w)
     seen = set()
     for r in races:
         key = (t.nodes[r[0]]["label"].split(" on ")[0], t.nodes[r[1]]["label"].split(" on ")[0], r[3], r[4])
@@ -357,7 +455,7 @@ def main():
             continue
         seen.add(key)
         print("RACE:", t.describe(r))
-    return 1 if races or t.bad_launches() else 0
+    return 1 if races or t.bad_launches() or wiring else 0
 
 
 if __name__ == "__main__":
