@@ -244,6 +244,24 @@ class Trace:
                 if any(x is None for x in rasters + heads):
                     errs.append(f"frame {i}: a rank has no raster / push-heads launch")
                     continue
+                # the ranks' primitive slices: contiguous, in rank order, no gap and no overlap (a rank with an empty slice
+                # launches no setup kernel); the scatter kernel works on the slice the setup kernel binned
+                slices = []
+                for d in range(ranks):
+                    setup, scatter = get(d, "triangle_setup_kernel"), get(d, "bin_scatter_kernel")
+                    if setup is not None:
+                        lo, hi = u32(setup["args"][6]), u32(setup["args"][7])
+                        slices.append((lo, hi, d))
+                        if scatter is not None and (u32(scatter["args"][1]), u32(scatter["args"][2])) != (lo, hi):
+                            errs.append(f"frame {i}: rank {d} bins primitives [{lo}, {hi}) but scatters [{u32(scatter['args'][1])}, {u32(scatter['args'][2])})")
+                if slices:
+                    if slices[0][0] != 0 or any(a[1] != b[0] for a, b in zip(slices, slices[1:])) or any(lo >= hi for lo, hi, _ in slices):
+                        errs.append(f"frame {i}: the ranks' primitive slices {[(lo, hi) for lo, hi, _ in slices]} do not tile the primitives in rank order")
+                # the flag epochs of a frame agree on all ranks
+                epochs = {tuple((u32(o["args"][3]), u32(o["args"][4])) for o in frames[d][i] if self.short(o) == "peer_barrier_kernel" and u32(o["args"][5]))
+                          for d in range(ranks)}
+                if len(epochs) != 1:
+                    errs.append(f"frame {i}: the ranks' barrier epochs differ: {sorted(epochs)}")
                 surfaces = {self._ptr(r["args"][0], 10) for r in rasters}
                 if len(surfaces) != 1:
                     errs.append(f"frame {i}: the ranks store their colours into different surfaces {sorted(hex(x) for x in surfaces)}")
