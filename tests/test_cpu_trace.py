@@ -157,6 +157,7 @@ def test_degenerate_work_sizes(trace_build, tmp_path, world, mode, tris):
     races = t.analyse()
     assert not t.bad_launches(), t.bad_launches()
     assert not t.warnings, sorted(set(t.warnings))[:5]
+    assert not t.wiring_errors(world), t.wiring_errors(world)[:4]
     # (no host barrier marker in this scenario: the arena's initial fill vs the peers' first stores is the host barrier's job)
     races = [r for r in races if not t.nodes[r[0]]["label"].startswith("memset")]
     assert not races, "\n".join(t.describe(r) for r in races[:8])
