@@ -253,3 +253,23 @@ def test_wiring_check_has_teeth(logs, sharded_logs, tmp_path):
         raw[14 * 8:15 * 8] = nxt[14 * 8:15 * 8]  # RasterArgs.shard.tileCount[0] of the next frame's list set
     t = mutate(sharded_logs[(2, "ring3")], lambda l: '"dev":1' in l, other_inbox)
     assert any("reads the heads of rank 0" in e for e in t.wiring_errors(2))
+
+
+@pytest.mark.parametrize("graph,cam,total", [(3, (0, 1, 5), 292), (2, (0, 5, 65), 4878), (4, (0, 5, 65), 11638)], ids=["bunny", "tuktuk", "vehicle"])
+def test_reference_scene_code_drives_the_renderer_on_the_tracing_build(trace_build, tmp_path, graph, cam, total):
+    """oracle/_ref/dropin_main (the reference's own CreateScenes + the veneer, see tests/test_gpu_veneer.py) through LoadScene and
+    RenderAuto on the recording runtime: the call sequence of the reference's main() completes, uploads the scene graph's
+    triangles and is race-free.  (The frames themselves are compared on a GPU.)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_main")
+    res_dir = os.path.join(ROOT, "oracle", "_ref", "resources")
+    if not (os.path.exists(exe) and os.path.exists(os.path.join(res_dir, "vehicle.obj"))):
+        pytest.skip("oracle/_ref/dropin_main not built (needs /root/reference at build time)")
+    os.symlink(res_dir, tmp_path / "Resources")
+    log, out = str(tmp_path / "log.jsonl"), str(tmp_path / "o.raw")
+    preload = trace_build["B2R_LIBRARY"] + ":" + os.path.join(OUT, "libfake_cudart.so")       # the binary is linked against the real libb2r.so
+    res = subprocess.run([exe, str(tmp_path), "render", str(graph), "640", "480", *[str(c) for c in cam], "0", "1", out], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, LD_PRELOAD=preload, B2R_TRACE_FILE=log, **trace_build))
+    assert res.returncode == 0 and f"triangles {total} visible" in res.stdout, res.stdout + res.stderr
+    assert os.path.getsize(out) == 640 * 480 * 4
+    t = stream_order.Trace(log)
+    assert not t.analyse() and not t.bad_launches() and not t.wiring_errors() and not t.leaks()
