@@ -1,0 +1,92 @@
+"""Runs under the CPU emulation build of the library (B2R_LIBRARY = build/emu/libb2r_emu.so; tools/emu): the product's
+kernels execute on the host, one CUDA thread per fiber.  Called by tests/test_cpu_emu.py in a subprocess, because the
+library is chosen when custom_gpgpu_rasterizer_b200._lib is imported.  Prints one JSON line.
+
+    python emu_scenarios.py parity <case>            product (emulated) vs the oracle on a golden frame case
+    python emu_scenarios.py schedulers <mode>        frames in flight with a moving camera: every frame vs the oracle"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import golden_cases  # noqa: E402
+import oracle_lib  # noqa: E402
+import parity  # noqa: E402
+from custom_gpgpu_rasterizer_b200 import _lib, scenes  # noqa: E402
+from custom_gpgpu_rasterizer_b200.renderer import Renderer  # noqa: E402
+
+
+def compare(r, sc, o, lists=True):
+    out = {}
+    fb, depth, winner, z = r.framebuffer(), r.depth(), r.winner(), r.z()
+    out["winner"] = bool(np.array_equal(winner, o["winner"]))
+    out["depth"] = bool(np.array_equal(depth, o["depth"]))
+    out["z"] = bool(np.array_equal(parity.bits(z), parity.bits(o["z"])))
+    out["colour_max_diff"] = int(np.abs(parity.channels(fb) - parity.channels(o["framebuffer"])).max())
+    total, visible = r.stats()
+    out["visible"] = bool(visible == o["visible_tris"] and total == o["total_tris"])
+    if lists:
+        counts, offsets, ids = r.bin_lists()
+        want = oracle_lib.bin_sets(o["bin_counts"], o["bin_ids"])
+        out["counts"] = bool(np.array_equal(counts, o["bin_counts"]))
+        out["offsets"] = bool(np.array_equal(offsets, np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32)))
+        out["lists"] = bool(np.array_equal(ids, np.concatenate(want) if want else ids))       # the sets, in ascending order
+        for mi, m in enumerate(sc.meshes):
+            ov = r.overtex(mi, m.vertices.shape[0])
+            out[f"overtex{mi}"] = bool(np.array_equal(parity.bits(ov), parity.bits(o["meshes"][mi]["overtex"])))
+            out[f"visible{mi}"] = bool(np.array_equal(r.visible(mi, m.n_tris), o["meshes"][mi]["visible"]))
+    return out
+
+
+def main():
+    what, arg = sys.argv[1], sys.argv[2]
+    if what == "parity":
+        sc = golden_cases.frame_cases()[arg]()
+        fill_rule = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+        o = oracle_lib.render(sc, fill_rule=fill_rule)
+        with Renderer(sc.width, sc.height) as r:
+            r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+            r.set_option(_lib.OPT_FILL_RULE_TOP_LEFT, fill_rule)
+            r.load_scene(sc)
+            r.render_scene(sc)
+            res = compare(r, sc, o)
+            res["kernels"] = r.counters()["kernels_launched"]
+        print(json.dumps(res))
+    elif what == "schedulers":
+        import dataclasses
+        sc = scenes.random_triangles_scene(160, 112, 120, seed=23, cull=2, textured=True, n_meshes=2, sample=1)
+        cams = [dataclasses.replace(sc, cam_pos=(0.15 * i - 0.5, 0.05 * i, 3.0 + 0.1 * i)) for i in range(7)]
+        wants = [oracle_lib.render(c, fill_rule=1) for c in cams]
+        res = {"frames": []}
+        with Renderer(sc.width, sc.height) as r:
+            r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+            if arg.startswith("ring"):
+                r.set_option(_lib.OPT_FRAME_RING, int(arg[4:]))
+            if arg == "serial":
+                r.set_option(_lib.OPT_OVERLAP_FRONT, 0)
+            if arg == "unsorted":
+                r.set_option(_lib.OPT_SORT_BINS, 0)
+            r.load_scene(sc)
+            # all frames enqueued back to back (no synchronisation in between), Present of each into its own host buffer
+            host = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+            for i, c in enumerate(cams):
+                r.render_scene(c, sync=False)
+                r.present_async(host[i])
+            r.present_wait()
+            for i, (c, o) in enumerate(zip(cams, wants)):
+                res["frames"].append(bool(np.array_equal(host[i], o["framebuffer"])))
+            res["last"] = compare(r, cams[-1], wants[-1])          # the newest frame's surfaces and (canonicalised) lists
+            # and frame by frame with a read-back after each
+            res["stepwise"] = []
+            for c, o in zip(cams[:3], wants[:3]):
+                r.render_scene(c, sync=False)
+                res["stepwise"].append(compare(r, c, o, lists=False))
+        print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""CPU: the product's KERNELS, executed.  tools/emu builds the product's sources with the host compiler on top of a small CUDA
+execution model (tools/emu/emu_cuda.h: every CUDA thread of a block is a fiber; __syncthreads and the *_sync warp
+collectives are rendezvous points; atomics, shared memory, the built-in variables and the intrinsics the kernels use)
+and the host-memory runtime of tools/trace.  The kernel sources are the product's, byte for byte (csrc/*.cuh); only the
+launch syntax of b2r.cu, its inline PTX and one MUFU instruction are rewritten (tools/emu/preprocess.py).  It is test
+infrastructure - the product library has no CPU path - and it is slow (seconds per small frame), but it lets the whole
+pipeline be compared with the oracle without a GPU, in particular the scheduler modes that no GPU was available for:
+
+* parity: transformed vertices, visibility, per-tile lists (sets AND order), winners, integer depth, interpolated z and
+  colour of the emulated product equal the oracle's bit for bit on the golden frame cases;
+* schedulers: seven frames with a moving camera enqueued back to back with a pipelined Present each - default three-stream
+  pipeline, serial frames, unsorted lists canonicalised on read, frame ring of depth 2 / 3 / 4 - every presented frame
+  equals the oracle's.  (A launch executes immediately, block by block: one valid serialisation of the stream order on one
+  device.  That frames in flight are ORDERED is tests/test_cpu_trace.py's job; that they compute the right thing is this
+  file's.)"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+import golden_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "build", "emu", "libb2r_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu_env():
+    if not shutil.which("g++") or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("host compiler / CUDA headers not available")
+    subprocess.check_call(["bash", os.path.join(ROOT, "tools", "emu", "build.sh")], stdout=subprocess.DEVNULL)
+    return dict(os.environ, B2R_LIBRARY=LIB)
+
+
+def run(env, *args):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_scenarios.py"), *args], capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout[-1000:] + res.stderr[-3000:]
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def all_true(d):
+    return all(v is True or (k == "colour_max_diff" and v == 0) or (k == "kernels" and v >= 11) for k, v in d.items())
+
+
+@pytest.mark.parametrize("case", sorted(golden_cases.frame_cases()))
+def test_emulated_product_equals_the_oracle(emu_env, case):
+    res = run(emu_env, "parity", case)
+    assert all_true(res), res
+
+
+@pytest.mark.parametrize("case", ["soup_colour", "quads_linear", "hostile"])
+def test_emulated_product_equals_the_oracle_with_the_reference_fill_rule(emu_env, case):
+    res = run(emu_env, "parity", case, "0")
+    assert all_true(res), res
+
+
+@pytest.mark.parametrize("mode", ["default", "serial", "unsorted", "ring2", "ring3", "ring4"])
+def test_scheduler_modes_compute_the_right_frames(emu_env, mode):
+    res = run(emu_env, "schedulers", mode)
+    assert all(res["frames"]) and len(res["frames"]) == 7, res["frames"]
+    assert all_true(res["last"]), res["last"]
+    assert all(all_true(s) for s in res["stepwise"]), res["stepwise"]
