@@ -88,5 +88,61 @@ def main():
         print(json.dumps(res))
 
 
+def sharded(world, mode):
+    """N contexts of this process as the N ranks of the sharded sort-first front end: every rank renders the same frames
+    (moving camera, all enqueued back to back), rank 0 presents each composed frame; compared with the oracle's frames."""
+    import ctypes as C
+    import dataclasses
+    lib = _lib.lib
+    sc = scenes.random_triangles_scene(160, 112, 700, seed=29, cull=2, textured=True, n_meshes=2, sample=1)
+    cams = [dataclasses.replace(sc, cam_pos=(0.15 * i - 0.5, 0.05 * i, 3.0 + 0.1 * i)) for i in range(7)]
+    wants = [oracle_lib.render(c, fill_rule=1) for c in cams]
+    ranks = [Renderer(sc.width, sc.height, device=d) for d in range(world)]
+    for r in ranks:
+        if mode.startswith("ring"):
+            r.set_option(_lib.OPT_FRAME_RING, int(mode[4]))
+            if mode.endswith("sliced"):
+                r.set_option(_lib.OPT_SHARD_SLICED_VERTEX, 1)
+        if mode == "serial":
+            r.set_option(_lib.OPT_OVERLAP_FRONT, 0)
+        r.load_scene(sc)
+    arenas, colours = [], []
+    for k, r in enumerate(ranks):
+        a, c = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+        r._check(lib.b2r_shard_prepare(r.handle, k, world, 1 << 14, a, c))
+        arenas.append(bytes(a)), colours.append(bytes(c))
+    all_arenas = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(arenas))
+    colour0 = (C.c_ubyte * 64).from_buffer_copy(colours[0])
+    for r in ranks:
+        r._check(lib.b2r_shard_bind(r.handle, all_arenas, colour0))
+    host = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+    for i, c in enumerate(cams):
+        for r in ranks:
+            r.render_scene(c, sync=False)
+        ranks[0].present_async(host[i])
+    ranks[0].present_wait()
+    res = {"frames": [bool(np.array_equal(h, o["framebuffer"])) for h, o in zip(host, wants)]}
+    res["last_framebuffer"] = bool(np.array_equal(ranks[0].framebuffer(), wants[-1]["framebuffer"]))
+    # the ranks' lists of the newest frame concatenate, in rank order, to the single-GPU lists (= the oracle's sets, ascending)
+    per_rank = [r.bin_lists() for r in ranks]
+    n_bins = len(per_rank[0][0])
+    cat = []
+    for b in range(n_bins):
+        for counts, offsets, ids in per_rank:
+            cat.append(ids[offsets[b]:offsets[b] + counts[b]])
+    want = oracle_lib.bin_sets(wants[-1]["bin_counts"], wants[-1]["bin_ids"])
+    res["lists"] = bool(np.array_equal(np.concatenate(cat), np.concatenate(want)))
+    res["visible"] = int(sum(r.stats()[1] for r in ranks)) == int(wants[-1]["visible_tris"])
+    for r in ranks:
+        r.sync()
+    for r in ranks:
+        r._check(lib.b2r_shard_release(r.handle))
+        r.close()
+    print(json.dumps(res))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "sharded":
+        sharded(int(sys.argv[2]), sys.argv[3])
+        sys.exit(0)
     main()

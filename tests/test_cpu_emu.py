@@ -12,7 +12,13 @@ pipeline be compared with the oracle without a GPU, in particular the scheduler 
   pipeline, serial frames, unsorted lists canonicalised on read, frame ring of depth 2 / 3 / 4 - every presented frame
   equals the oracle's.  (A launch executes immediately, block by block: one valid serialisation of the stream order on one
   device.  That frames in flight are ORDERED is tests/test_cpu_trace.py's job; that they compute the right thing is this
-  file's.)"""
+  file's.)  Streams are real queues here (tools/emu/emu_runtime.cpp): work is executed when the host synchronises, newest
+  stream first, so a later frame's front end runs before an earlier frame's raster wherever the product's events allow
+  it - with the event waits switched off (B2R_EMU_IGNORE_WAITS) every presented frame comes out wrong;
+* sharded sort-first front end: N contexts of one process as the N ranks (the flag barriers work because a kernel that
+  sleeps in its spin loop hands the processor to the other streams); seven frames in flight, composed on rank 0 - default
+  pipeline, frame ring, frame ring + sliced vertex stage (the raster kernel transforming its vertices itself): every
+  composed frame equals the oracle's and the ranks' lists concatenate to the oracle's lists."""
 import json
 import os
 import shutil
@@ -63,3 +69,30 @@ def test_scheduler_modes_compute_the_right_frames(emu_env, mode):
     assert all(res["frames"]) and len(res["frames"]) == 7, res["frames"]
     assert all_true(res["last"]), res["last"]
     assert all(all_true(s) for s in res["stepwise"]), res["stepwise"]
+
+
+@pytest.mark.parametrize("mode", ["default", "ring3"])
+def test_the_emulation_is_sensitive_to_the_event_waits(emu_env, mode):
+    res = run(dict(emu_env, B2R_EMU_IGNORE_WAITS="1"), "schedulers", mode)
+    assert not any(res["frames"]), "frames in flight without their event waits must not come out right"
+
+
+SHARDED = [(2, "default"), (2, "ring3sliced"), (4, "ring4sliced")]
+SLOW = os.environ.get("B2R_SLOW_TESTS") == "1"
+if SLOW:
+    SHARDED += [(2, "serial"), (2, "ring3"), (3, "ring2"), (8, "default"), (8, "ring3sliced")]
+
+
+@pytest.mark.parametrize("world,mode", SHARDED)
+def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode):
+    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "sharded", str(world), mode)
+    assert all(res["frames"]) and len(res["frames"]) == 7, res
+    assert res["last_framebuffer"] and res["lists"] and res["visible"], res
+
+
+@pytest.mark.skipif(not SLOW, reason="other stream visiting orders of the emulated executor (set B2R_SLOW_TESTS=1)")
+@pytest.mark.parametrize("order", ["asc", "random:3", "random:11"])
+@pytest.mark.parametrize("mode", ["default", "ring3"])
+def test_scheduler_modes_under_other_execution_orders(emu_env, mode, order):
+    res = run(dict(emu_env, B2R_EMU_ORDER=order), "schedulers", mode)
+    assert all(res["frames"]) and all_true(res["last"]) and all(all_true(s) for s in res["stepwise"]), res

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE -- builds build/emu/libb2r_emu.so: the product's kernels and host code compiled by the HOST compiler on
-# top of tools/emu/emu_cuda.h (CUDA threads as fibers) and the host-memory runtime of tools/trace.  Kernels really run, on
+# top of tools/emu/emu_cuda.h (CUDA threads as fibers) and the queued host-memory runtime tools/emu/emu_runtime.cpp.  Kernels really run, on
 # the CPU, one block at a time - for functional checks of code paths no GPU was available for.  Not a product path: the
 # product library has no CPU fallback.   Use:  B2R_LIBRARY=build/emu/libb2r_emu.so python ...
 set -euo pipefail
@@ -11,9 +11,9 @@ CSRC="$ROOT/custom_gpgpu_rasterizer_b200/csrc"
 CUDAINC="${CUDAINC:-/usr/local/cuda/include}"
 mkdir -p "$OUT/src"
 python3 "$HERE/preprocess.py" "$CSRC" "$OUT/src"
-g++ -O1 -std=c++17 -fPIC -shared -o "$OUT/libfake_cudart.so" "$ROOT/tools/trace/fake_cudart.cpp"
+g++ -O1 -g -std=c++17 -fPIC -shared -o "$OUT/libemu_runtime.so" "$HERE/emu_runtime.cpp"
 FLAGS=(-std=c++17 -O2 -fPIC -ffp-contract=off -mfma -fno-fast-math -w -I"$CUDAINC" -I"$CSRC" -I"$ROOT/include")
 g++ "${FLAGS[@]}" -include "$HERE/emu_cuda.h" -c "$OUT/src/b2r.cpp" -o "$OUT/b2r.o"
 g++ "${FLAGS[@]}" -c "$CSRC/host/b2r_scene.cpp" -o "$OUT/b2r_scene.o"
-g++ -shared -o "$OUT/libb2r_emu.so" "$OUT/b2r.o" "$OUT/b2r_scene.o" -lz -L"$OUT" -lfake_cudart -Wl,-rpath,"$OUT"
+g++ -shared -o "$OUT/libb2r_emu.so" "$OUT/b2r.o" "$OUT/b2r_scene.o" -lz -L"$OUT" -lemu_runtime -Wl,-rpath,"$OUT"
 echo "built $OUT/libb2r_emu.so"

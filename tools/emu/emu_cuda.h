@@ -4,9 +4,8 @@
 // Never part of the product: libb2r.so has no CPU path and fails without a CUDA device.  This header exists to execute
 // the very same kernel sources (csrc/*.cuh, unmodified; b2r.cu with its launch syntax rewritten by tools/emu/preprocess.py)
 // functionally, e.g. to compare the frames of scheduler modes that were never run on a GPU with the default mode and
-// with the oracle.  Memory, streams and events come from the recording runtime of tools/trace (host memory); a launch
-// executes the grid immediately, block after block in index order - one valid serialisation of the stream order on a
-// single device.
+// with the oracle.  Memory, streams and events come from tools/emu/emu_runtime.cpp (host memory; streams are real queues,
+// drained when the host synchronises, newest stream first); a kernel executes block after block in index order.
 //
 // Execution model: every CUDA thread of a block is a fiber (ucontext) on ONE host thread.  A fiber runs until it reaches
 // __syncthreads or a warp collective; the scheduler resumes the others, and resolves a barrier / collective when all
@@ -49,6 +48,8 @@
 #define __align__(n) __attribute__((aligned(n)))
 #define EMU_ASM(...) do { } while (0)  /* inline PTX (griddepcontrol, prefetch, globaltimer): no meaning here */
 
+extern "C" void emu_enqueue_kernel(void* stream, void (*fn)(void*), void* arg, void (*del)(void*));
+extern "C" void emu_kernel_yield(void);
 inline uint3 threadIdx{ 0, 0, 0 }, blockIdx{ 0, 0, 0 };
 inline dim3 blockDim{ 1, 1, 1 }, gridDim{ 1, 1, 1 };
 
@@ -79,7 +80,11 @@ struct Engine
 	void* bodyArg = nullptr;
 	const char* kernelName = "?";
 };
-inline Engine& E() { static Engine e; return e; }
+// one Engine per kernel in execution: a kernel that has given up the processor (__nanosleep, see emu_runtime.cpp) keeps
+// its fibers while other kernels run
+inline Engine*& current() { static Engine* e = nullptr; return e; }
+inline Engine& E() { return *current(); }
+inline std::vector<Engine*>& pool() { static std::vector<Engine*> p; return p; }
 constexpr size_t kStack = 256 * 1024;
 
 inline void yieldToScheduler() { Engine& e = E(); swapcontext(&e.cur->ctx, &e.main); }
@@ -220,7 +225,11 @@ inline void runBlock(Engine& e)
 template <typename F>
 inline void runGrid(const char* name, dim3 grid, dim3 block, size_t dynSmem, F&& f)
 {
-	Engine& e = E();
+	Engine* prev = current();
+	Engine* ep;
+	if (pool().empty()) ep = new Engine; else { ep = pool().back(); pool().pop_back(); }
+	current() = ep;
+	Engine& e = *ep;
 	e.kernelName = name; e.gDim = grid; e.bDim = block;
 	e.dynamicSmem.assign(dynSmem + 16, 0);
 	auto* fp = &f;
@@ -234,23 +243,30 @@ inline void runGrid(const char* name, dim3 grid, dim3 block, size_t dynSmem, F&&
 				::blockIdx = e.bIdx; ::blockDim = block; ::gridDim = grid;
 				runBlock(e);
 			}
+	pool().push_back(ep);
+	current() = prev;
 }
 inline void* dynamicSmemPtr() { return E().dynamicSmem.data(); }
 template <typename K> inline cudaError_t funcSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 
-// kernel<<<grid, block[, smem, stream]>>>(args...)  (rewritten by tools/emu/preprocess.py)
+// kernel<<<grid, block[, smem, stream]>>>(args...)  (rewritten by tools/emu/preprocess.py) and cudaLaunchKernelEx: the launch
+// is QUEUED on its stream (emu_runtime.cpp) with a copy of its arguments and runs when the executor gets to it
+template <typename Tuple, typename K>
+struct Closure { const char* name; K kernel; dim3 grid, block; size_t smem; Tuple params; };
 template <typename... P, typename... A>
-inline void launch(const char* name, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, A&&... args)
+inline void launch(const char* name, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args)
 {
-	std::tuple<typename std::decay<P>::type...> params(std::forward<A>(args)...);
-	runGrid(name, grid, block, smem, [&] { std::apply(kernel, params); });
+	using T = std::tuple<typename std::decay<P>::type...>;
+	using C = Closure<T, void (*)(P...)>;
+	C* c = new C{ name, kernel, grid, block, smem, T(std::forward<A>(args)...) };
+	emu_enqueue_kernel((void*)stream,
+		[](void* p) { C* c = static_cast<C*>(p); runGrid(c->name, c->grid, c->block, c->smem, [c] { std::apply(c->kernel, c->params); }); },
+		c, [](void* p) { delete static_cast<C*>(p); });
 }
-// cudaLaunchKernelEx(&cfg, kernel, args...)
 template <typename... P, typename... A>
 inline cudaError_t launchEx(const cudaLaunchConfig_t* cfg, void (*kernel)(P...), A&&... args)
 {
-	std::tuple<typename std::decay<P>::type...> params(std::forward<A>(args)...);
-	runGrid("kernel", cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [&] { std::apply(kernel, params); });
+	launch("kernel", kernel, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cfg->stream, std::forward<A>(args)...);
 	return cudaSuccess;
 }
 
@@ -279,7 +295,17 @@ template <typename T> inline unsigned __match_any_sync(unsigned m, T v) { return
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline void __threadfence_block() {}
-inline void __nanosleep(unsigned) {}
+// the product sleeps only inside the spin loop of its cross-GPU flag barrier: let the executor run the other streams (the
+// peers' among them) and come back
+inline void __nanosleep(unsigned)
+{
+	emu::Engine* e = emu::current();
+	emu::Fiber* f = e->cur;
+	emu_kernel_yield();
+	emu::current() = e;
+	::threadIdx = f->tid; ::blockIdx = e->bIdx; ::blockDim = e->bDim; ::gridDim = e->gDim;
+}
+inline unsigned long long emuGlobalTimerNs() { static unsigned long long t = 0; return t += 1000; }     // never reaches the 4 s time-out
 
 // ---- atomics (one host thread: plain read-modify-write)
 template <typename T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Rewrites the CUDA-only SYNTAX of the product's sources into calls of tools/emu/emu_cuda.h, into build/emu/src (scratch):
-  kernel<<<grid, block[, smem[, stream]]>>>(args)  ->  emu::launch("kernel", kernel, dim3(grid), dim3(block), smem, args)
+  kernel<<<grid, block[, smem[, stream]]>>>(args)  ->  emu::launch("kernel", kernel, dim3(grid), dim3(block), smem, stream, args)
   cudaLaunchKernelEx(                               ->  emu::launchEx(
   asm volatile(                                     ->  EMU_ASM(
   cudaFuncSetAttribute(                             ->  emu::funcSetAttribute(
@@ -49,7 +49,8 @@ def rewrite_launches(src):
             b += 1
         args = src[a + 1:b].strip()
         smem = cfg[2] if len(cfg) > 2 else "0"
-        out += f'emu::launch("{name}", {name}, dim3({cfg[0]}), dim3({cfg[1]}), {smem}' + (", " + args if args else "") + ")"
+        stream = cfg[3] if len(cfg) > 3 else "nullptr"
+        out += f'emu::launch("{name}", {name}, dim3({cfg[0]}), dim3({cfg[1]}), {smem}, (cudaStream_t)({stream})' + (", " + args if args else "") + ")"
         i = b + 1
 
 
@@ -59,6 +60,7 @@ def main(src_dir, dst_dir):
         s = open(os.path.join(src_dir, rel)).read()
         s = rewrite_launches(s)
         s = s.replace("cudaLaunchKernelEx(", "emu::launchEx(")
+        s = s.replace('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = emuGlobalTimerNs();")
         s = s.replace("asm volatile(", "EMU_ASM(")
         s = s.replace("cudaFuncSetAttribute(", "emu::funcSetAttribute(")
         # MUFU.RCP: the correctly rounded reciprocal stands in for the hardware approximation; the refinement steps that follow
