@@ -96,3 +96,20 @@ def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode):
 def test_scheduler_modes_under_other_execution_orders(emu_env, mode, order):
     res = run(dict(emu_env, B2R_EMU_ORDER=order), "schedulers", mode)
     assert all(res["frames"]) and all_true(res["last"]) and all(all_true(s) for s in res["stepwise"]), res
+
+
+def test_smoke_on_the_emulation(emu_env):
+    """__graft_entry__.smoke() - the round-end gate's first call on the GPU box - end to end on the emulation build."""
+    res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, timeout=900, env=emu_env, cwd=ROOT)
+    assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
+
+
+def test_cpp_veneer_and_drop_in_gpu_tests_on_the_emulation(emu_env):
+    """tests/test_gpu_veneer.py (-m gpu) as it is, with the emulation build standing in for the GPU: the C++ veneer example and
+    oracle/_ref/dropin_main (the reference's own CreateScenes on the veneer; the binaries are linked against the real
+    libb2r.so, hence the preload) render bunny, TukTuk and vehicle exactly like the C-ABI path."""
+    preload = LIB + ":" + os.path.join(os.path.dirname(LIB), "libemu_runtime.so")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_veneer.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
+                         capture_output=True, text=True, timeout=2400, env=dict(emu_env, LD_PRELOAD=preload), cwd=ROOT)
+    assert res.returncode == 0 and " passed" in res.stdout and "failed" not in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "skipped" not in res.stdout or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_main")), res.stdout[-500:]
