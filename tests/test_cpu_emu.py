@@ -113,3 +113,17 @@ def test_cpp_veneer_and_drop_in_gpu_tests_on_the_emulation(emu_env):
                          capture_output=True, text=True, timeout=2400, env=dict(emu_env, LD_PRELOAD=preload), cwd=ROOT)
     assert res.returncode == 0 and " passed" in res.stdout and "failed" not in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
     assert "skipped" not in res.stdout or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_main")), res.stdout[-500:]
+
+
+def test_gpu_unit_tests_on_the_emulation(emu_env):
+    """tests/test_gpu_units.py: every tier of the list sorter (warp run ordering, CTA run ordering / radix, the long radix sort
+    in dynamic shared memory) on lists of up to tens of thousands of entries - as it is, on the emulation build; and the
+    hoisted division against IEEE division on 2^22 operand pairs (here the refinement starts from the correctly rounded
+    reciprocal instead of MUFU.RCP; the 2^32-pair check against div.rn on hardware stays a -m gpu test)."""
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_units.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "list_sort"],
+                         capture_output=True, text=True, timeout=2400, env=emu_env, cwd=ROOT)
+    assert res.returncode == 0 and "3 passed" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+    code = ("import ctypes as C\nfrom custom_gpgpu_rasterizer_b200._lib import lib\nbad = C.c_uint64(1)\n"
+            "assert lib.b2r_selftest_division(0, 1 << 22, 7, C.byref(bad)) == 0 and bad.value == 0, bad.value\nprint('division ok')")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=emu_env, cwd=ROOT)
+    assert res.returncode == 0 and "division ok" in res.stdout, res.stdout + res.stderr[-2000:]
