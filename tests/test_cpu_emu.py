@@ -129,3 +129,13 @@ def test_gpu_unit_tests_on_the_emulation(emu_env):
             "assert lib.b2r_selftest_division(0, 1 << 22, 7, C.byref(bad)) == 0 and bad.value == 0, bad.value\nprint('division ok')")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=emu_env, cwd=ROOT)
     assert res.returncode == 0 and "division ok" in res.stdout, res.stdout + res.stderr[-2000:]
+
+
+@pytest.mark.skipif(os.environ.get("B2R_EMU_FULL") != "1", reason="~20 min of CPU: the whole -m gpu parity file on the emulation build (set B2R_EMU_FULL=1)")
+def test_whole_gpu_parity_file_on_the_emulation(emu_env):
+    """tests/test_gpu_parity.py as it is (64 tests: every scene in both fill rules incl. the bundled vehicle at 1080p, the 172-instance
+    views with 2 M triangles and the 4K slivers, the hostile-input fuzz, pipelined frames, pipelined Present, list-capacity regrowth)
+    with the emulation build standing in for the GPU.  Last full run: 64 passed in 17 min 26 s (round 1, session 4)."""
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
+                         capture_output=True, text=True, timeout=3600, env=emu_env, cwd=ROOT)
+    assert res.returncode == 0 and " passed" in res.stdout and "failed" not in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
