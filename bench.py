@@ -105,6 +105,7 @@ def run_views(args):
     import torch
     import torch.distributed as dist
     from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    refuse_emulation()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -352,11 +353,20 @@ def algorithmic_bytes(scene, visible, pairs, frags, covered_px):
     }
 
 
+def refuse_emulation():
+    """B2R_LIBRARY selects A/B builds of the product library; the CPU emulation build of tools/emu is test infrastructure and
+    is never measured."""
+    from custom_gpgpu_rasterizer_b200 import _lib
+    if hasattr(_lib.lib, "emu_enqueue_kernel"):
+        raise SystemExit(f"bench.py: {_lib.LIB_PATH} is the CPU emulation build (tools/emu) - there is no CPU path to measure")
+
+
 def run_b200(args, scene):
     import torch
     import torch.distributed as dist
     from custom_gpgpu_rasterizer_b200 import _lib
     from custom_gpgpu_rasterizer_b200.renderer import Renderer
+    refuse_emulation()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("B2R_LIBRARY") or os.path.join(_HERE, "csrc", "libb2r.so")     # B2R_LIBRARY: A/B builds of the same ABI
+# B2R_LIBRARY: another build of the same ABI - A/B variants of the product library on a GPU box, or one of the TEST builds
+# (tools/trace: recording runtime; tools/emu: CPU execution of the kernels).  The test builds are never the product: the
+# default is the in-tree libb2r.so, which needs a CUDA device, and bench.py refuses to measure the emulation build.
+LIB_PATH = os.environ.get("B2R_LIBRARY") or os.path.join(_HERE, "csrc", "libb2r.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

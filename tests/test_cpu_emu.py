@@ -103,7 +103,7 @@ def test_scheduler_modes_under_other_execution_orders(emu_env, mode, order):
 def test_smoke_on_the_emulation(emu_env):
     """__graft_entry__.smoke() - the round-end gate's first call on the GPU box - end to end on the emulation build."""
     res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, timeout=900, env=emu_env, cwd=ROOT)
-    assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.returncode == 0 and "smoke ok [CPU EMULATION BUILD" in res.stdout, res.stdout[-1500:] + res.stderr[-3000:]
 
 
 def test_cpp_veneer_and_drop_in_gpu_tests_on_the_emulation(emu_env):
@@ -139,3 +139,8 @@ def test_whole_gpu_parity_file_on_the_emulation(emu_env):
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
                          capture_output=True, text=True, timeout=3600, env=emu_env, cwd=ROOT)
     assert res.returncode == 0 and " passed" in res.stdout and "failed" not in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+def test_bench_refuses_the_emulation_build(emu_env):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "spheres_small", "--steps", "1"], capture_output=True, text=True, timeout=300, env=emu_env)
+    assert res.returncode != 0 and res.stdout.strip() == "" and "CPU emulation build" in res.stderr
