@@ -80,14 +80,16 @@ def test_the_emulation_is_sensitive_to_the_event_waits(emu_env, mode):
     assert not any(res["frames"]), "frames in flight without their event waits must not come out right"
 
 
-SHARDED = [(2, "ring3sliced"), (4, "ring4sliced")]
+# (ranks, mode, meshes): 7 meshes - the raster kernel's on-the-fly vertex transform keeps the matrices of the first 4 meshes in
+# shared memory and loads the others from global memory
+SHARDED = [(2, "ring3sliced", 7), (4, "ring4sliced", 2)]
 if SLOW:
-    SHARDED += [(2, "default"), (2, "serial"), (2, "ring3"), (3, "ring2"), (8, "default"), (8, "ring3sliced")]
+    SHARDED += [(2, "default", 2), (2, "serial", 2), (2, "ring3", 2), (3, "ring2", 2), (8, "default", 2), (8, "ring3sliced", 2)]
 
 
-@pytest.mark.parametrize("world,mode", SHARDED)
-def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode):
-    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "sharded", str(world), mode)
+@pytest.mark.parametrize("world,mode,meshes", SHARDED)
+def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode, meshes):
+    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "sharded", str(world), mode, str(meshes))
     assert all(res["frames"]) and len(res["frames"]) == 7, res
     assert res["last_framebuffer"] and res["lists"] and res["visible"], res
 
