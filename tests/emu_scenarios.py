@@ -141,7 +141,43 @@ def sharded(world, mode, n_meshes=2):
     print(json.dumps(res))
 
 
+def replicated(world):
+    """north_star's literal sort-first form: every rank bins the full mesh, rasterises only the tiles it owns (tile index mod
+    ranks) into a packed tile-major buffer, and rank 0 scatters the peers' buffers into its framebuffer (b2r_unpack_tiles) -
+    what multi_gpu.SortFirstGather does with an NCCL gather in between.  N contexts of this process as the N ranks."""
+    import ctypes as C
+    from custom_gpgpu_rasterizer_b200.multi_gpu import packed_pixels
+    lib = _lib.lib
+    sc = scenes.random_triangles_scene(333, 217, 400, seed=31, cull=2, textured=True, n_meshes=2)       # ragged resolution: partial tiles
+    o = oracle_lib.render(sc, fill_rule=1)
+    ranks = [Renderer(sc.width, sc.height, device=d) for d in range(world)]
+    packed = [None]
+    for k, r in enumerate(ranks):
+        r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
+        r.set_option(_lib.OPT_TILE_OWNER_RANK, k)
+        r.load_scene(sc)
+        if k:
+            n = C.c_uint64(0)
+            r._check(lib.b2r_packed_size(r.handle, k, world, C.byref(n)))
+            assert n.value == packed_pixels(sc.bins_x * sc.bins_y, k, world)
+            packed.append(np.zeros(int(n.value), np.uint32))
+            r.set_option(_lib.OPT_PACKED_OUTPUT, 1)
+            r.bind_framebuffer(packed[k].ctypes.data)
+    for r in ranks:
+        r.render_scene(sc)
+    for k in range(1, world):
+        ranks[0]._check(lib.b2r_unpack_tiles(ranks[0].handle, C.c_void_p(packed[k].ctypes.data), k, world, None))
+    res = {"framebuffer": bool(np.array_equal(ranks[0].framebuffer(), o["framebuffer"])),
+           "pairs": int(sum(r.counters()["pairs"] for r in ranks)) == int(o["bin_counts"].sum())}
+    for r in ranks:
+        r.close()
+    print(json.dumps(res))
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "replicated":
+        replicated(int(sys.argv[2]))
+        sys.exit(0)
     if sys.argv[1] == "sharded":
         sharded(int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2)
         sys.exit(0)

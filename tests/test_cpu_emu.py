@@ -146,3 +146,11 @@ def test_whole_gpu_parity_file_on_the_emulation(emu_env):
 def test_bench_refuses_the_emulation_build(emu_env):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "spheres_small", "--steps", "1"], capture_output=True, text=True, timeout=300, env=emu_env)
     assert res.returncode != 0 and res.stdout.strip() == "" and "CPU emulation build" in res.stderr
+
+
+@pytest.mark.parametrize("world", [3])
+def test_replicated_sort_first_composes_the_right_frame(emu_env, world):
+    """Tile ownership, the packed tile-major output and b2r_unpack_tiles at a ragged resolution (partial tiles): the frame rank 0
+    composes from the ranks' packed buffers is the oracle's, and every (triangle, tile) pair was binned by exactly one owner."""
+    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "replicated", str(world))
+    assert res == {"framebuffer": True, "pairs": True}, res
