@@ -88,13 +88,13 @@ def main():
         print(json.dumps(res))
 
 
-def sharded(world, mode, n_meshes=2):
+def sharded(world, mode, n_meshes=2, n_tris=700):
     """N contexts of this process as the N ranks of the sharded sort-first front end: every rank renders the same frames
     (moving camera, all enqueued back to back), rank 0 presents each composed frame; compared with the oracle's frames."""
     import ctypes as C
     import dataclasses
     lib = _lib.lib
-    sc = scenes.random_triangles_scene(160, 112, 700, seed=29, cull=2, textured=True, n_meshes=n_meshes, sample=1)
+    sc = scenes.random_triangles_scene(160, 112, n_tris, seed=29, cull=2, textured=True, n_meshes=n_meshes, sample=1)
     cams = [dataclasses.replace(sc, cam_pos=(0.15 * i - 0.5, 0.05 * i, 3.0 + 0.1 * i)) for i in range(7)]
     wants = [oracle_lib.render(c, fill_rule=1) for c in cams]
     ranks = [Renderer(sc.width, sc.height, device=d) for d in range(world)]
@@ -179,6 +179,6 @@ if __name__ == "__main__":
         replicated(int(sys.argv[2]))
         sys.exit(0)
     if sys.argv[1] == "sharded":
-        sharded(int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2)
+        sharded(int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 2, int(sys.argv[5]) if len(sys.argv) > 5 else 700)
         sys.exit(0)
     main()

@@ -82,14 +82,16 @@ def test_the_emulation_is_sensitive_to_the_event_waits(emu_env, mode):
 
 # (ranks, mode, meshes): 7 meshes - the raster kernel's on-the-fly vertex transform keeps the matrices of the first 4 meshes in
 # shared memory and loads the others from global memory
-SHARDED = [(2, "ring3sliced", 7), (4, "ring4sliced", 2)]
+# 150 triangles on 8 ranks: one 256-primitive block, i.e. seven ranks with an EMPTY primitive slice
+SHARDED = [(2, "ring3sliced", 7, 700), (4, "ring4sliced", 2, 700), (8, "ring3sliced", 1, 150)]
 if SLOW:
-    SHARDED += [(2, "default", 2), (2, "serial", 2), (2, "ring3", 2), (3, "ring2", 2), (8, "default", 2), (8, "ring3sliced", 2)]
+    SHARDED += [(2, "default", 2, 700), (2, "serial", 2, 700), (2, "ring3", 2, 700), (3, "ring2", 2, 700), (8, "default", 2, 700), (8, "ring3sliced", 2, 700),
+                (8, "default", 1, 150), (4, "ring2sliced", 3, 300)]
 
 
-@pytest.mark.parametrize("world,mode,meshes", SHARDED)
-def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode, meshes):
-    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "sharded", str(world), mode, str(meshes))
+@pytest.mark.parametrize("world,mode,meshes,tris", SHARDED)
+def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode, meshes, tris):
+    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "sharded", str(world), mode, str(meshes), str(tris))
     assert all(res["frames"]) and len(res["frames"]) == 7, res
     assert res["last_framebuffer"] and res["lists"] and res["visible"], res
 
