@@ -44,3 +44,5 @@ for m in parallel sortfirst; do
 import json
 d=json.loads(open('$O/views_$m.json').read().strip().splitlines()[-1]); print(round(d['value'],1), d['unit'], 'e2e', round(d['e2e']['value'],1))" 2>&1 | tail -1)"
 done
+# the on-the-fly raster variant at 4 resident CTAs per SM (no register spills) - build it first with tools/build_variants.sh
+[ -f build/variants/libb2r_otf4.so ] && run ring3_sliced_otf4 B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 B2R_LIBRARY=$PWD/build/variants/libb2r_otf4.so
