@@ -141,6 +141,44 @@ def sharded(world, mode, n_meshes=2, n_tris=700):
     print(json.dumps(res))
 
 
+def dynamic(mode):
+    """Scene changes between frames in flight: a mesh's world matrix (b2r_mesh_set_world), then a third mesh - every frame,
+    enqueued without synchronisation and presented into its own buffer, against the oracle's frame of the scene as it was
+    when the frame was issued."""
+    import dataclasses
+    from custom_gpgpu_rasterizer_b200.renderer import host_mesh_world
+    from custom_gpgpu_rasterizer_b200.scenefile import MeshData
+    lib = _lib.lib
+    base = scenes.random_triangles_scene(160, 112, 150, seed=37, cull=2, textured=True, n_meshes=2)
+    extra = scenes.random_triangles_scene(160, 112, 60, seed=38, cull=2).meshes[0]
+
+    def moved(sc, pos):
+        m0 = sc.meshes[0]
+        return dataclasses.replace(sc, meshes=[MeshData(m0.vertices, m0.indices, pos, m0.tex_ids)] + list(sc.meshes[1:]))
+    s1 = moved(base, (0.4, -0.2, 0.3))
+    s2 = dataclasses.replace(s1, meshes=list(s1.meshes) + [MeshData(extra.vertices, extra.indices, (0.0, 0.3, 0.5), (-1, -1, -1, -1))])
+    plan = [base, base, s1, s1, s1, s2, s2, s2]
+    wants = {id(x): oracle_lib.render(x, fill_rule=1) for x in (base, s1, s2)}
+    host = [np.zeros((base.height, base.width), np.uint32) for _ in plan]
+    with Renderer(base.width, base.height) as r:
+        if mode.startswith("ring"):
+            r.set_option(_lib.OPT_FRAME_RING, int(mode[4:]))
+        r.load_scene(base)
+        cur = base
+        for i, sc in enumerate(plan):
+            if sc is s1 and cur is base:
+                w = host_mesh_world(s1.meshes[0].position)
+                r._check(lib.b2r_mesh_set_world(r.handle, 0, w.ctypes.data_as(_lib._fp)))
+            if sc is s2 and cur is s1:
+                m = s2.meshes[2]
+                r.add_mesh(m.vertices, m.indices, host_mesh_world(m.position), m.tex_ids)
+            cur = sc
+            r.render_scene(sc, sync=False)
+            r.present_async(host[i])
+        r.present_wait()
+    print(json.dumps({"frames": [bool(np.array_equal(h, wants[id(sc)]["framebuffer"])) for h, sc in zip(host, plan)]}))
+
+
 def replicated(world):
     """north_star's literal sort-first form: every rank bins the full mesh, rasterises only the tiles it owns (tile index mod
     ranks) into a packed tile-major buffer, and rank 0 scatters the peers' buffers into its framebuffer (b2r_unpack_tiles) -
@@ -175,6 +213,9 @@ def replicated(world):
 
 
 if __name__ == "__main__":
+    if sys.argv[1] == "dynamic":
+        dynamic(sys.argv[2])
+        sys.exit(0)
     if sys.argv[1] == "replicated":
         replicated(int(sys.argv[2]))
         sys.exit(0)

@@ -156,3 +156,11 @@ def test_replicated_sort_first_composes_the_right_frame(emu_env, world):
     composes from the ranks' packed buffers is the oracle's, and every (triangle, tile) pair was binned by exactly one owner."""
     res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "replicated", str(world))
     assert res == {"framebuffer": True, "pairs": True}, res
+
+
+@pytest.mark.parametrize("mode", ["default", "ring3"])
+def test_scene_changes_between_frames_in_flight(emu_env, mode):
+    """b2r_mesh_set_world and a mesh upload between frames that were enqueued without synchronisation: every presented frame shows
+    the scene as it was when the frame was issued (per-mesh constants, triangle references and buffers are re-made in order)."""
+    res = run(emu_env, "dynamic", mode)
+    assert all(res["frames"]) and len(res["frames"]) == 8, res
