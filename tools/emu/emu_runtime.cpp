@@ -30,7 +30,7 @@ struct Event { unsigned flags; uint64_t enqueued = 0, completed = 0; };
 struct KernelRun
 {
 	ucontext_t ctx;                 // where to resume (initially: the trampoline on `stack`)
-	std::vector<char> stack;
+	char* stack = nullptr;          // from a pool: most kernels run to completion at once and hand it straight back
 	void (*fn)(void*); void* arg; void (*del)(void*);
 	bool started = false, finished = false;
 };
@@ -48,6 +48,8 @@ thread_local int t_device = 0;
 ucontext_t g_executor;
 KernelRun* g_running = nullptr;
 int g_nextStream = 1;
+constexpr size_t kKernelStack = 4u << 20;
+std::vector<char*> g_stackPool;
 
 void kernelTrampoline()
 {
@@ -62,16 +64,17 @@ bool stepKernel(KernelRun* k)
 	if (!k->started)
 	{
 		k->started = true;
-		k->stack.resize(4u << 20);
+		if (g_stackPool.empty()) k->stack = static_cast<char*>(malloc(kKernelStack)); else { k->stack = g_stackPool.back(); g_stackPool.pop_back(); }
 		getcontext(&k->ctx);
-		k->ctx.uc_stack.ss_sp = k->stack.data();
-		k->ctx.uc_stack.ss_size = k->stack.size();
+		k->ctx.uc_stack.ss_sp = k->stack;
+		k->ctx.uc_stack.ss_size = kKernelStack;
 		k->ctx.uc_link = &g_executor;
 		makecontext(&k->ctx, (void (*)())kernelTrampoline, 0);
 	}
 	g_running = k;
 	swapcontext(&g_executor, &k->ctx);
 	g_running = nullptr;
+	if (k->finished && k->stack) { g_stackPool.push_back(k->stack); k->stack = nullptr; }
 	return k->finished;
 }
 
