@@ -164,3 +164,23 @@ def test_scene_changes_between_frames_in_flight(emu_env, mode):
     the scene as it was when the frame was issued (per-mesh constants, triangle references and buffers are re-made in order)."""
     res = run(emu_env, "dynamic", mode)
     assert all(res["frames"]) and len(res["frames"]) == 8, res
+
+
+@pytest.mark.skipif(not SLOW, reason="AddressSanitizer build of the emulation (~3 min; set B2R_SLOW_TESTS=1)")
+def test_kernels_are_memory_safe_under_address_sanitizer(tmp_path):
+    """The emulated kernels under ASan: 'device' buffers are heap blocks and __shared__ arrays are statics, so an out-of-bounds
+    access of any kernel is reported - the role compute-sanitizer's memcheck plays on a GPU.  Hostile inputs, the frame ring,
+    the sharded + sliced front end with 7 meshes (stores into the peers' arenas) and the CTA-level sorters."""
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan):
+        pytest.skip("libasan not available")
+    subprocess.check_call(["bash", os.path.join(ROOT, "tools", "emu", "build.sh"), "--asan"], stdout=subprocess.DEVNULL)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0",
+               B2R_LIBRARY=os.path.join(ROOT, "build", "emu_asan", "libb2r_emu.so"))
+    for args, devices in ((["parity", "hostile_textured"], 1), (["parity", "soup_textured_linear"], 1), (["schedulers", "ring3"], 1), (["sharded", "2", "ring3sliced", "7"], 2)):
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_scenarios.py"), *args], capture_output=True, text=True, timeout=1800,
+                             env=dict(env, B2R_TRACE_DEVICES=str(devices)))
+        assert res.returncode == 0 and "ERROR: AddressSanitizer" not in res.stderr, (args, res.stdout[-500:], res.stderr[-3000:])
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_units.py") + "::test_list_sort_tiers_give_canonical_lists[res1-grid1-tess1]",
+                          "-m", "gpu", "-q", "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=1800, env=env, cwd=ROOT)
+    assert res.returncode == 0 and "ERROR: AddressSanitizer" not in res.stderr, res.stdout[-1500:] + res.stderr[-3000:]

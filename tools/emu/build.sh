@@ -7,13 +7,18 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 OUT="$ROOT/build/emu"
+SAN=""
+# --asan: the same with AddressSanitizer into build/emu_asan - "device" allocations are heap blocks and __shared__ arrays are
+# statics, so a kernel that reads or writes out of bounds is reported (run python under LD_PRELOAD=$(g++ -print-file-name=libasan.so)
+# ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0)
+if [ "${1:-}" = "--asan" ]; then OUT="$ROOT/build/emu_asan"; SAN="-g -fsanitize=address -fno-omit-frame-pointer"; fi
 CSRC="$ROOT/custom_gpgpu_rasterizer_b200/csrc"
 CUDAINC="${CUDAINC:-/usr/local/cuda/include}"
 mkdir -p "$OUT/src"
 python3 "$HERE/preprocess.py" "$CSRC" "$OUT/src"
-g++ -O1 -g -std=c++17 -fPIC -shared -o "$OUT/libemu_runtime.so" "$HERE/emu_runtime.cpp"
-FLAGS=(-std=c++17 -O2 -fPIC -ffp-contract=off -mfma -fno-fast-math -w -I"$CUDAINC" -I"$CSRC" -I"$ROOT/include")
+g++ -O1 -g -std=c++17 -fPIC -shared $SAN -o "$OUT/libemu_runtime.so" "$HERE/emu_runtime.cpp"
+FLAGS=(-std=c++17 ${SAN:--O2} ${SAN:+-O1} -fPIC -ffp-contract=off -mfma -fno-fast-math -w -I"$CUDAINC" -I"$CSRC" -I"$ROOT/include")
 g++ "${FLAGS[@]}" -include "$HERE/emu_cuda.h" -c "$OUT/src/b2r.cpp" -o "$OUT/b2r.o"
 g++ "${FLAGS[@]}" -c "$CSRC/host/b2r_scene.cpp" -o "$OUT/b2r_scene.o"
-g++ -shared -o "$OUT/libb2r_emu.so" "$OUT/b2r.o" "$OUT/b2r_scene.o" -lz -L"$OUT" -lemu_runtime -Wl,-rpath,"$OUT"
+g++ -shared $SAN -o "$OUT/libb2r_emu.so" "$OUT/b2r.o" "$OUT/b2r_scene.o" -lz -L"$OUT" -lemu_runtime -Wl,-rpath,"$OUT"
 echo "built $OUT/libb2r_emu.so"
