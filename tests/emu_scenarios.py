@@ -94,7 +94,10 @@ def sharded(world, mode, n_meshes=2, n_tris=700):
     import ctypes as C
     import dataclasses
     lib = _lib.lib
-    sc = scenes.random_triangles_scene(160, 112, n_tris, seed=29, cull=2, textured=True, n_meshes=n_meshes, sample=1)
+    if os.environ.get("B2R_EMU_SCENE") == "hostile":      # triangles through the camera plane, w = 0, NaN / inf / huge coordinates, degenerate ones
+        sc = scenes.hostile_scene(160, 112, 400, seed=43, textured=True)
+    else:
+        sc = scenes.random_triangles_scene(160, 112, n_tris, seed=29, cull=2, textured=True, n_meshes=n_meshes, sample=1)
     cams = [dataclasses.replace(sc, cam_pos=(0.15 * i - 0.5, 0.05 * i, 3.0 + 0.1 * i)) for i in range(7)]
     wants = [oracle_lib.render(c, fill_rule=1) for c in cams]
     ranks = [Renderer(sc.width, sc.height, device=d) for d in range(world)]

@@ -184,3 +184,12 @@ def test_kernels_are_memory_safe_under_address_sanitizer(tmp_path):
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_units.py") + "::test_list_sort_tiers_give_canonical_lists[res1-grid1-tess1]",
                           "-m", "gpu", "-q", "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=1800, env=env, cwd=ROOT)
     assert res.returncode == 0 and "ERROR: AddressSanitizer" not in res.stderr, res.stdout[-1500:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(not SLOW, reason="set B2R_SLOW_TESTS=1")
+@pytest.mark.parametrize("world,mode", [(2, "ring3sliced"), (4, "default")])
+def test_sharded_front_end_with_hostile_inputs(emu_env, world, mode):
+    """Degenerate / non-finite / camera-plane-crossing triangles through the sharded front end, also with the raster kernel
+    transforming its vertices itself: the composed frames and the concatenated lists are still the oracle's."""
+    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world), B2R_EMU_SCENE="hostile"), "sharded", str(world), mode)
+    assert all(res["frames"]) and res["last_framebuffer"] and res["lists"] and res["visible"], res
