@@ -183,8 +183,8 @@ def run_views(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE config 5: 172 instances of the bundled vehicle mesh (2 001 736 triangles, one vertex buffer + 172 world matrices), "
                                "1920x1080, 1024 cameras on a ring, PBR shading with four 1024^2 maps",
-                   "triangles": total, "visible_triangles_last_view": visible, "resolution": "1920x1080",
-                   "parallelism": (f"sort-first per view, {world} ranks (sharded front end, frames composed on rank 0)" if sort_first else f"view-parallel, {world} rank(s): view i -> rank i mod N, no communication")},
+                   "triangles": total, "visible_triangles_last_view": visible, "resolution": "1920x1080"},
+        "parallelism": (f"sort-first per view, {world} ranks (sharded front end, frames composed on rank 0)" if sort_first else f"view-parallel, {world} rank(s): view i -> rank i mod N, no communication"),
         "mtris_per_s": total * world_views * args.steps / t / 1e6,
         "e2e": {"value": world_views * args.steps / float(e2e.item()), "unit": "views/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": sc.width * sc.height * 4},
         "gpu_launches": launches * args.steps, "clocks": clocks.summary()}), flush=True)
@@ -303,8 +303,9 @@ def run_reference(args, scene):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded: the full frame costs ~1 s on one core, so a handful of frames stays within minutes
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    # the driver's --steps / --warmup are honoured: the full frame costs ~0.55 s on one core of the GPU box, so the default
+    # 20 + 5 frames take ~15 s; only an extravagant request is cut down to stay within minutes (and the line says so)
+    steps, warmup = min(args.steps, 200), min(args.warmup, 50)
     mean_s, _, kind = cpu_reference_arm(scene, steps, warmup)
     fps = 1.0 / mean_s
     line = {
@@ -312,7 +313,8 @@ def run_reference(args, scene):
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean_s * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_of(scene),
         "mtris_per_s": scene.n_tris / mean_s / 1e6,
-        "config": dict(workload_config(args.workload, scene), parallelism="the reference's CPU renderer, one host thread (it is single-threaded)"),
+        "config": workload_config(args.workload, scene),
+        "parallelism": "the reference's CPU renderer, one host thread (it is single-threaded)",
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
                          "sample": f"full frame of the workload, {steps} frames after {warmup} warm-up; {CPU_KIND_NOTE[kind]}; single-threaded like the reference",
                          "host_cores_available": os.cpu_count()},
@@ -412,19 +414,27 @@ def run_b200(args, scene):
 
     # ---- timed region: device time of K frames, max over ranks
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(args.steps):
-                frame()
-            e1.record(stream)
-        barrier()
+    # clocks / throttle reasons are sampled (nvidia-smi, every 100 ms) from here to the end of the per-stage timing below:
+    # the device-timed region, the end-to-end region and the stage timers, plus ~1 s of the same frames in between so that
+    # the median is taken over enough samples under load (K frames alone last a few milliseconds)
+    clocks = ClockSampler(local).__enter__()
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            frame()
+        e1.record(stream)
+    barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     counters = r.counters()
+    # untimed: the same frames for about a second (a fixed number on every rank, derived from the measured frame time)
+    for _ in range(min(4000, int(1000.0 / max(total_ms / args.steps, 0.05)))):
+        frame()
+    r.sync()
+    barrier()
     launches_per_frame = counters["kernels_launched"] + (gather.launches_per_frame if gather else 0)
 
     # ---- the same frames without the in-frame list sort (B2R_OPT_SORT_BINS = 0): the image does not depend on the list
@@ -481,6 +491,16 @@ def run_b200(args, scene):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
+    # correctness token of this run: CRC-32 of the frame the end-to-end region delivered into host memory and of the frame on
+    # the device (N > 1: the frame the ranks composed on rank 0); compared below with a frame rank 0 renders on its own
+    import zlib
+    crc_host = crc_dev = None
+    if rank == 0:
+        crc_host = zlib.crc32(host_fb[(args.steps - 1) & 1].tobytes())
+        crc_dev = zlib.crc32(r.framebuffer().tobytes())
+    else:
+        r.sync()
+    barrier()
 
     # ---- per-stage device times over K more frames (CUDA events recorded between the stages on the same stream)
     r.set_option(_lib.OPT_STAGE_TIMERS, 1)
@@ -490,6 +510,7 @@ def run_b200(args, scene):
     r.sync()
     stages, n_timed = r.stage_ms_mean(reset=True)
     r.set_option(_lib.OPT_STAGE_TIMERS, 0)
+    clocks.__exit__()
     stages_per_rank = None
     if world > 1:
         stages_per_rank = [None] * world
@@ -539,6 +560,15 @@ def run_b200(args, scene):
         gather = None
     depth = r.depth()
     covered_px = int((depth != 0x7FFFFFFF).sum())
+    # the reference frame of the checksum: rank 0 alone, whole frame, in this same process (N > 1: rendered by the
+    # view-parallel leg above, after the sharded group was released)
+    single = None
+    if rank == 0:
+        if world == 1:
+            r.render(cam, scene.cull, scene.sample, scene.vis, sync=True)
+        s_total, s_visible = r.stats()
+        single = {"framebuffer_crc32": zlib.crc32(r.framebuffer().tobytes()), "visible_triangles": s_visible,
+                  "tile_pairs": r.counters()["pairs"], "covered_pixels": covered_px}
     barrier()
 
     if rank != 0:
@@ -573,9 +603,15 @@ def run_b200(args, scene):
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_of(scene),
-        "config": dict(workload_config(args.workload, scene), parallelism=("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up/bins/sorts primitive slice r, owners read the peers' lists over NVLink, colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather])),
+        "config": workload_config(args.workload, scene),
+        "parallelism": ("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up and bins primitive slice r, owners read the peers' lists over NVLink (and put them in order), colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather]),
         "mtris_per_s": scene.n_tris * fps / 1e6,
         "visible_triangles": visible, "tile_pairs": pairs, "fragments": frags, "covered_pixels": covered_px,
+        "checksum": {"framebuffer_crc32": crc_dev, "host_framebuffer_crc32": crc_host, "single_gpu": single,
+                     "match": bool(crc_dev == crc_host == single["framebuffer_crc32"] and visible == single["visible_triangles"] and pairs == single["tile_pairs"]),
+                     "note": "CRC-32 of the 4K frame: on the device after the end-to-end region (N > 1: composed by all ranks on rank 0), as delivered into pinned host "
+                             "memory by the end-to-end region, and of a whole frame rendered by rank 0 alone in this process; the visible-triangle and (triangle, tile) pair "
+                             "counts summed over the ranks must equal the single-GPU frame's too.  A mismatch makes bench.py exit with status 3."},
         "list_sorter": {"tiles_sent_to_the_cta_sorter_by_the_warp_sorter": counters["sort_fallback_tiles"], "tiles_beyond_the_sorter": counters["unsorted_tiles"]},
         "stages_ms": stages, "stages": per_stage,
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak * world, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
@@ -616,6 +652,9 @@ def run_b200(args, scene):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not line["checksum"]["match"]:
+        sys.stderr.write(f"bench.py: CHECKSUM MISMATCH {line['checksum']}\n")
+        sys.exit(3)
 
 
 def fill_test(Renderer, _lib, torch, dev, args, peak):

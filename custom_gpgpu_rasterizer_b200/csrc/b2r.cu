@@ -125,7 +125,7 @@ struct b2r_context
 	struct BinSet
 	{
 		DeviceVec<uint2> rects;
-		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, midTiles, smallTiles, bigList, binIds;
+		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, tileOrder, bigList, binIds;
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[kMaxFrameRing];
@@ -277,8 +277,7 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	CU(c, B.tileOffset.reserve(n + 4, c->stream));
 	CU(c, B.tileCursor.reserve(n, c->stream));
 	CU(c, B.longTiles.reserve(n, c->stream));
-	CU(c, B.midTiles.reserve(n, c->stream));
-	CU(c, B.smallTiles.reserve(n, c->stream));
+	CU(c, B.tileOrder.reserve(n * kTileClasses, c->stream));      // the raster kernel's work order: one list per length class
 	CU(c, B.rects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, B.bigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	// list capacity heuristic; regrown on overflow (see validateFrame), and kept equal across the sets
@@ -294,6 +293,10 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 	if ((uint64_t)bx * bw < c->width || (uint64_t)by * bh < c->height)
 		return fail(c, B2R_E_INVALID, "bins (%ux%u of %ux%u) must cover the %ux%u screen", bx, by, bw, bh, c->width, c->height);
 	if (bx > 32767 || by > 32767) return fail(c, B2R_E_INVALID, "too many bins");
+	// tile_scan_kernel publishes one slice sum per 2048 tiles into a fixed block of the counters (kScanMaxCtas slices)
+	if ((uint64_t)bx * by > (uint64_t)kScanMaxCtas * kScanPerCta)
+		return fail(c, B2R_E_INVALID, "%ux%u bins = %llu tiles exceed the %llu the tile scan is sized for", bx, by,
+			(unsigned long long)bx * by, (unsigned long long)kScanMaxCtas * kScanPerCta);
 	c->binsX = bx; c->binsY = by; c->binW = bw; c->binH = bh;
 	return reserveBinSet(c, c->bins[0]);
 }
@@ -369,6 +372,9 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.nMeshes = (uint32_t)c->meshes.size();
 	fp.packedOutput = (uint32_t)c->packedOutput;
 	fp.shardGeometry = c->shard.bound ? 1u : 0u;
+	const uint32_t subs = fp.subX * fp.subY;
+	fp.subsMagic = subs > 1 ? (uint32_t)(0x100000000ull / subs) : 0u;
+	fp.sortLists = c->sortBins ? 1u : 0u;
 	return fp;
 }
 
@@ -387,10 +393,13 @@ cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 g
 
 // the raster kernel instantiation of a frame: fill rule, fragment counter, light variant (the frame cannot reach the
 // texture / visualiser paths), positions transformed on the fly (sharded front end with a sliced vertex stage)
-cudaError_t launchRaster(const b2r_context* c, dim3 grid, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool onTheFly)
+// The kernel is persistent: `blocks` = the 16x16 pixel blocks of the frame (an upper bound of its work items), the grid is
+// what fits the GPU at the variant's occupancy.
+cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool onTheFly)
 {
 	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (onTheFly ? 8 : 0);
 	const dim3 block(kTile * kTile);
+	const dim3 grid(std::min<uint32_t>(blocks, (uint32_t)(c->numSMs * rasterCtasPerSM(textured, onTheFly))));
 #define B2R_RASTER_CASE(v, tl, cnt, tex, otf) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, otf>, grid, block, 0, s, A, fp);
 	switch (variant)
 	{
@@ -488,13 +497,19 @@ int uploadMeshStatic(b2r_context* c, b2r_context::Slot& slot, cudaStream_t s)
 	return B2R_OK;
 }
 
-// canonical (ascending primitive id) order of every tile list: the three tiers of the list sorter, working off the
-// work lists tile_scan_kernel built in the set's buffers
-int enqueueListSort(b2r_context* c, b2r_context::BinSet& B, uint32_t* tileCount, uint32_t* tileOffset, uint32_t* binIds, cudaStream_t s)
+// Canonical (ascending primitive id) order of the tile lists.  Inside a frame the lists of up to kStage entries are
+// sorted by the raster kernel itself (the CTA that rasterises a tile stages its list in shared memory anyway); what is
+// left for a kernel of its own are the few longer lists (tile_scan_kernel's "long" work list), before the raster.
+// everything = true (b2r_read_bins after frames rendered with B2R_OPT_SORT_BINS = 0, or with the sharded front end,
+// where a tile's list is sorted at its owner): also the short lists, one CTA per tile.
+int enqueueListSort(b2r_context* c, b2r_context::BinSet& B, uint32_t* tileCount, uint32_t* tileOffset, uint32_t* binIds, cudaStream_t s, bool everything)
 {
 	const uint32_t tiles = nBins(c);
-	CU(c, launchFrameKernel(c, bin_sort_runs_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, tileCount, tileOffset, binIds, B.smallTiles.ptr, B.midTiles.ptr, B.frameInfo));
-	CU(c, launchFrameKernel(c, bin_sort_mid_kernel, dim3(c->numSMs * 4), dim3(256), 0, s, B.midTiles.ptr, tileCount, tileOffset, binIds, B.frameInfo));
+	if (everything)
+	{
+		bin_sort_tiles_kernel<<<std::min<uint32_t>(tiles, (uint32_t)c->numSMs * 6u), kSortThreads, 0, s>>>(tileCount, tileOffset, binIds, tiles, B.frameInfo);
+		CU(c, cudaGetLastError());
+	}
 	CU(c, launchFrameKernel(c, bin_sort_long_kernel, dim3(c->numSMs), dim3(1024), kSortLongSmem, s, B.longTiles.ptr, tileCount, tileOffset,
 		binIds, B.frameInfo));
 	return B2R_OK;
@@ -537,7 +552,8 @@ int enqueueFrame(b2r_context* c)
 	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, set) : B.binIds.ptr;
 	const size_t listCap = sh.bound ? sh.listCap : B.binIds.cap;
 	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds; c->curRects = B.rects.ptr;
-	c->curSet = &B; c->curSorted = c->sortBins != 0;
+	// sharded front end: a tile's list is put in order at its owner; the rank's own buffer is canonicalised when it is read
+	c->curSet = &B; c->curSorted = c->sortBins != 0 && !sh.bound;
 	uint32_t primLo = 0, primHi = (uint32_t)c->nPrims;
 	if (sh.bound)
 	{
@@ -627,8 +643,8 @@ int enqueueFrame(b2r_context* c)
 	}
 	STAGE_EVENT(c, slot, 2);
 	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, fs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
-		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
-		B.midTiles.ptr, B.longTiles.ptr, B.smallTiles.ptr, B.counters, B.frameInfo));
+		(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
+		(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, B.frameInfo));
 	++c->kernelsLaunched;
 	if (sh.bound)
 	{
@@ -656,8 +672,8 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs); if (r) return r;
-		c->kernelsLaunched += 3;
+		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs, false); if (r) return r;
+		c->kernelsLaunched += 1;
 	}
 	if (sh.bound && c->nPrims)
 	{
@@ -678,7 +694,7 @@ int enqueueFrame(b2r_context* c)
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
-		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = sh.bound ? nullptr : B.tileOrder.ptr;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -714,9 +730,8 @@ int enqueueFrame(b2r_context* c)
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
 		if (owned)
 		{
-			const dim3 grid(owned, fp.subX * fp.subY);
 			// light variant when the frame cannot reach the texture / visualiser paths
-			CU(c, launchRaster(c, grid, s, A, fp, rc.vis != 0 || c->anyDiffuse, false));
+			CU(c, launchRaster(c, owned * fp.subX * fp.subY, s, A, fp, rc.vis != 0 || c->anyDiffuse, false));
 			++c->kernelsLaunched;
 		}
 		// the vertex stage of frame f+2 may overwrite pos4 / constants of this parity once this raster is done
@@ -798,7 +813,8 @@ int enqueueFrameRing(b2r_context* c)
 	uint32_t* binIds = sh.bound ? sh.binIds(sh.arena, k) : B.binIds.ptr;
 	const size_t listCap = sh.bound ? sh.listCap : B.binIds.cap;
 	c->curTileCount = tileCount; c->curTileOffset = tileOffset; c->curBinIds = binIds; c->curRects = B.rects.ptr;
-	c->curSet = &B; c->curSorted = c->sortBins != 0;
+	// sharded front end: a tile's list is put in order at its owner; the rank's own buffer is canonicalised when it is read
+	c->curSet = &B; c->curSorted = c->sortBins != 0 && !sh.bound;
 	uint32_t primLo = 0, primHi = (uint32_t)c->nPrims;
 	if (sh.bound)
 	{
@@ -897,8 +913,8 @@ int enqueueFrameRing(b2r_context* c)
 	}
 	RING_STAGE_EVENT(2);
 	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, rs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
-		(unsigned long long)listCap, (uint32_t)kSortWarpRadix, (uint32_t)kSortSmall,
-		B.midTiles.ptr, B.longTiles.ptr, B.smallTiles.ptr, B.counters, B.frameInfo));
+		(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
+		(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, B.frameInfo));
 	++c->kernelsLaunched;
 	PeerFlags pf{};
 	if (sh.bound)
@@ -930,8 +946,8 @@ int enqueueFrameRing(b2r_context* c)
 	RING_STAGE_EVENT(4);
 	if (c->sortBins && c->nPrims)
 	{
-		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs); if (r) return r;
-		c->kernelsLaunched += 3;
+		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs, false); if (r) return r;
+		c->kernelsLaunched += 1;
 	}
 	if (sh.bound && c->nPrims)
 	{
@@ -945,7 +961,7 @@ int enqueueFrameRing(b2r_context* c)
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
-		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = sh.bound ? nullptr : B.tileOrder.ptr;
 		if (sh.bound) c->colourIdx = (int)(sh.frame & 1u);       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -978,7 +994,7 @@ int enqueueFrameRing(b2r_context* c)
 		if (!waitedPrev && c->ringPrev >= 0 && c->ringPrev != k) CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0));
 		if (owned)
 		{
-			CU(c, launchRaster(c, dim3(owned, fp.subX * fp.subY), rs, A, fp, rc.vis != 0 || c->anyDiffuse, sliced));
+			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse, sliced));
 			++c->kernelsLaunched;
 		}
 		if (sh.bound)
@@ -1210,7 +1226,7 @@ void b2r_destroy(b2r_context* c)
 	for (auto& B : c->bins)
 	{
 		B.rects.release(); B.tileCount.release(); B.tileOffset.release(); B.tileCursor.release(); B.longTiles.release();
-		B.midTiles.release(); B.smallTiles.release(); B.bigList.release(); B.binIds.release();
+		B.tileOrder.release(); B.bigList.release(); B.binIds.release();
 		cudaFree(B.frameInfo);
 	}
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
@@ -1234,6 +1250,8 @@ int b2r_setup_bins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32
 {
 	if (!c) return B2R_E_INVALID;
 	CU(c, cudaSetDevice(c->device));
+	// the shared arena (tile tables, inboxes of every rank) was sized for the grid at b2r_shard_prepare
+	if (c->shard.prepared) return fail(c, B2R_E_STATE, "setup_bins: the bin grid is fixed while the sharded front end is prepared (b2r_shard_release first)");
 	int r = validateFrame(c); if (r) return r;
 	return setBins(c, bx, by, bw, bh);
 }
@@ -1346,13 +1364,20 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	switch (option)
 	{
 	case B2R_OPT_FILL_RULE_TOP_LEFT: c->fillTopLeft = value ? 1 : 0; break;
-	case B2R_OPT_TILE_OWNER_RANK: if (value < 0) return fail(c, B2R_E_INVALID, "rank < 0"); c->ownerRank = value; break;
-	case B2R_OPT_TILE_OWNER_COUNT: if (value < 1) return fail(c, B2R_E_INVALID, "count < 1"); c->ownerCount = value; break;
+	case B2R_OPT_TILE_OWNER_RANK:
+	case B2R_OPT_TILE_OWNER_COUNT:
+	case B2R_OPT_PACKED_OUTPUT:
+		// the sharded front end fixes ownership (rank, count) and the output layout at b2r_shard_prepare: the raster kernel
+		// indexes the per-rank tables of the arena with them
+		if (c->shard.prepared) return fail(c, B2R_E_STATE, "tile ownership / packed output cannot change while the sharded front end is prepared");
+		if (option == B2R_OPT_TILE_OWNER_RANK) { if (value < 0) return fail(c, B2R_E_INVALID, "rank < 0"); c->ownerRank = value; }
+		else if (option == B2R_OPT_TILE_OWNER_COUNT) { if (value < 1) return fail(c, B2R_E_INVALID, "count < 1"); c->ownerCount = value; }
+		else c->packedOutput = value ? 1 : 0;
+		break;
 	case B2R_OPT_DEBUG_SURFACES: c->debugSurfaces = value ? 1 : 0; break;
 	case B2R_OPT_STAGE_TIMERS: c->stageTimers = value ? 1 : 0; break;
 	case B2R_OPT_SORT_BINS: c->sortBins = value ? 1 : 0; break;
 	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
-	case B2R_OPT_PACKED_OUTPUT: c->packedOutput = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_VERTEX: c->overlapVertex = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_FRONT: c->overlapFront = value ? 1 : 0; break;
 	case B2R_OPT_FRAME_RING:
@@ -1404,6 +1429,15 @@ int b2r_render(b2r_context* c, const float camPos[3], const float camFwd[3], con
 	if (!camPos || !camFwd || !viewProj) return fail(c, B2R_E_INVALID, "null camera argument");
 	if (cull < 0 || cull > 2 || sample < 0 || sample > 1 || vis < 0 || vis > 2) return fail(c, B2R_E_INVALID, "bad render state");
 	if (c->ownerRank >= c->ownerCount) return fail(c, B2R_E_INVALID, "tile owner rank %d >= count %d", c->ownerRank, c->ownerCount);
+	if (c->packedOutput && !c->boundFramebuffer)
+	{
+		// tile-major output holds whole 16x16 blocks: more pixels than the W x H surface when the screen is ragged
+		const uint64_t subs = (uint64_t)((c->binW + kTile - 1) / kTile) * ((c->binH + kTile - 1) / kTile);
+		const uint64_t tiles = nBins(c), owned = tiles > (uint64_t)c->ownerRank ? (tiles - c->ownerRank + c->ownerCount - 1) / c->ownerCount : 0;
+		if (owned * subs * kTile * kTile > (uint64_t)c->width * c->height)
+			return fail(c, B2R_E_STATE, "packed output of %llu pixels does not fit the %ux%u colour surface: bind a buffer of b2r_packed_size pixels (b2r_bind_framebuffer)",
+				(unsigned long long)(owned * subs * kTile * kTile), c->width, c->height);
+	}
 	CU(c, cudaSetDevice(c->device));
 	RenderCall& rc = c->last;
 	memcpy(rc.camPos, camPos, 12); memcpy(rc.camFwd, camFwd, 12); memcpy(rc.viewProj, viewProj, 64);
@@ -1522,7 +1556,7 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	{
 		// B2R_OPT_SORT_BINS = 0: the frame left the lists in scatter order (the image does not depend on it);
 		// whoever looks at them gets the canonical order - sort the newest frame's lists now, in place
-		r = enqueueListSort(c, *c->curSet, c->curTileCount, c->curTileOffset, c->curBinIds, c->stream); if (r) return r;
+		r = enqueueListSort(c, *c->curSet, c->curTileCount, c->curTileOffset, c->curBinIds, c->stream, true); if (r) return r;
 		CU(c, cudaStreamSynchronize(c->stream));
 		// counters of the sorter (tiles beyond its reach, fallbacks) as after an in-frame sort
 		CU(c, cudaMemcpy(c->lastInfo.frameInfo, c->curSet->frameInfo, sizeof(c->lastInfo.frameInfo), cudaMemcpyDeviceToHost));
@@ -1720,8 +1754,10 @@ int b2r_shard_release(b2r_context* c)
 	if (!c) return B2R_E_INVALID;
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c);
+	const bool was = c->shard.prepared;
 	releaseShard(c);
 	c->colourIdx = 0;
+	if (was) { c->ownerRank = 0; c->ownerCount = 1; }      // b2r_shard_prepare set them: later frames are whole frames again
 	return r;
 }
 

@@ -515,17 +515,30 @@ __global__ void __launch_bounds__(256) bin_big_count_kernel(
 	binBigBody<false>(blockIdx.x, gridDim.x, bigList, counters, rects, tileCount, nullptr, nullptr, nullptr, fp);
 }
 
+// Work order of the raster kernel: tiles grouped into classes by list length, longest first (class c holds the
+// tiles with at least kClassMin[c] entries; the last class the empty ones), so that its persistent CTAs take the
+// long lists first and the tail of the kernel is made of short ones (longest-processing-time-first scheduling).
+constexpr uint32_t kTileClasses = 6;
+constexpr uint32_t kInfoClassBase = 8;       // frameInfo[8 .. 13]: tiles per class; frameInfo[14]: the raster kernel's work counter
+constexpr uint32_t kInfoWorkCounter = kInfoClassBase + kTileClasses;
+constexpr uint32_t kEmptyBatch = 4;          // empty tiles cleared per work item
+__device__ __forceinline__ uint32_t tileClass(uint32_t n)
+{
+	return n >= 1024u ? 0u : n >= 512u ? 1u : n >= 256u ? 2u : n >= 96u ? 3u : n >= 1u ? 4u : 5u;
+}
+
 // exclusive scan of the per-tile counts: a chained scan over a handful of co-resident CTAs (2048 tiles
 // each; a 4K frame is 16 CTAs).  Every CTA publishes the sum of its slice, adds up the published sums of
 // its predecessors (they are all resident, so spinning is safe) and scans its slice locally.  Also clears
-// the cursors, publishes the pair total / overflow flag and builds the two work lists of the list sorter
-// (tiles whose list is too long for the warp-level sort).
+// the cursors, publishes the pair total / overflow flag, builds the work list of the long-list sorter
+// (tiles whose list is too long for the raster kernel's in-CTA sort) and the raster kernel's work order
+// (tileOrder = kTileClasses lists of nTiles entries; null: not wanted).
 constexpr uint32_t kScanThreads = 256, kScanPerThread = 8, kScanPerCta = kScanThreads * kScanPerThread;
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t nTiles, unsigned long long capacity, uint32_t midThreshold, uint32_t longThreshold,
-	uint32_t* __restrict__ midTiles, uint32_t* __restrict__ longTiles, uint32_t* __restrict__ smallTiles, uint32_t* __restrict__ counters,
-	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[5]=mid tiles,[8]=small tiles; [6] is the run sorter's fallback count*/)
+	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold,
+	uint32_t* __restrict__ longTiles, uint32_t* __restrict__ tileOrder, uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
+	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[6]=lists sorted by the bitonic fallback,[8..13]=tiles per class*/)
 {
 	pdlPrologue();
 	// published slice sums: bit 63 = ready (frame_clear_kernel zeroes them)
@@ -627,36 +640,44 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 		}
 		#pragma unroll
 		for (uint32_t e = 0; e < 4; ++e)
-		{
-			const uint32_t c = v[q * 4 + e];
-			if (i + e < nTiles && c > midThreshold)
-			{
-				if (c > longThreshold) longTiles[atomicAdd(&frameInfo[3], 1ull)] = i + e;
-				else midTiles[atomicAdd(&frameInfo[5], 1ull)] = i + e;
-			}
-		}
+			if (i + e < nTiles && v[q * 4 + e] > longThreshold) longTiles[atomicAdd(&frameInfo[3], 1ull)] = i + e;
 	}
-	// work list of the warp-level sorter: the tiles with 2..midThreshold entries, compacted (most tiles of a frame
-	// are empty or hold a single id, and a sorter warp that finds nothing to do still pins its CTA's shared memory).
-	// One atomic per warp; inside a warp the tiles stay in ascending order.
+	// the raster kernel's work order: one atomic per warp and class; inside a warp the tiles stay in ascending order.
+	// Sort-first with a replicated front end: only the tiles this rank owns (the others hold no entries here and
+	// belong to other ranks' surfaces).
+	if (tileOrder)
 	{
-		uint32_t mine = 0;
-		#pragma unroll
-		for (uint32_t e = 0; e < kScanPerThread; ++e) mine += (first + e < nTiles && v[e] >= 2u && v[e] <= midThreshold) ? 1u : 0u;
-		uint32_t inclS = mine;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1)
-		{
-			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inclS, d);
-			if (lane >= (uint32_t)d) inclS += t;
-		}
-		const uint32_t warpTotal = __shfl_sync(0xFFFFFFFFu, inclS, 31);
-		uint32_t base = 0;
-		if (lane == 0 && warpTotal) base = (uint32_t)atomicAdd(&frameInfo[8], (unsigned long long)warpTotal);
-		base = __shfl_sync(0xFFFFFFFFu, base, 0) + inclS - mine;
+		uint32_t cls[kScanPerThread];
 		#pragma unroll
 		for (uint32_t e = 0; e < kScanPerThread; ++e)
-			if (first + e < nTiles && v[e] >= 2u && v[e] <= midThreshold) smallTiles[base++] = first + e;
+		{
+			const uint32_t t = first + e;
+			const bool mine = t < nTiles && (ownerCount <= 1u || t % ownerCount == ownerRank);
+			cls[e] = mine ? tileClass(v[e]) : kTileClasses;
+		}
+		#pragma unroll
+		for (uint32_t c = 0; c < kTileClasses; ++c)
+		{
+			uint32_t mine = 0;
+			#pragma unroll
+			for (uint32_t e = 0; e < kScanPerThread; ++e) mine += (cls[e] == c) ? 1u : 0u;
+			if (!__any_sync(0xFFFFFFFFu, mine != 0u)) continue;
+			uint32_t inclS = mine;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inclS, d);
+				if (lane >= (uint32_t)d) inclS += t;
+			}
+			const uint32_t warpTotal = __shfl_sync(0xFFFFFFFFu, inclS, 31);
+			uint32_t base = 0;
+			if (lane == 0) base = (uint32_t)atomicAdd(&frameInfo[kInfoClassBase + c], (unsigned long long)warpTotal);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0) + inclS - mine;
+			uint32_t* dst = tileOrder + (size_t)c * nTiles;
+			#pragma unroll
+			for (uint32_t e = 0; e < kScanPerThread; ++e)
+				if (cls[e] == c) dst[base++] = first + e;
+		}
 	}
 }
 
@@ -744,180 +765,162 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t
 
 // per-tile sort of the id lists (ascending primitive id = submission order): makes the lists
 // bit-reproducible regardless of the order the scatter atomics were served.
-//  tier 1: one WARP per tile, lists up to kSortWarpRadix entries.  warpBinRects() writes one ascending
-//          run per (warp, tile) and the runs of different warps cover disjoint id ranges, so the list
-//          is sorted by ORDERING THE RUNS by their first key and moving them (bin_sort_runs_kernel).
-//          Tiles where that does not hold (interleaved or too many runs) are appended to the mid list.
-//  tier 2: the tiles tile_scan_kernel put on the "mid" work list (up to kSortSmall entries), one
-//          CTA per tile: run ordering at CTA scale, block radix sort in static shared memory as fallback
-//  tier 3: the "long" work list (up to kSortLarge entries) in dynamic shared memory, one CTA per SM
-//  longer lists stay in scatter order and are counted in frameInfo[2] (the image does not
+//  lists up to kStage entries are sorted by the CTA that RASTERISES the tile (raster_shade_kernel stages the ids of
+//          its tile in shared memory anyway): ctaSortTileList below.  warpBinRects() writes one ascending run per
+//          (warp, tile) and the runs of different warps cover disjoint id ranges, so the list is sorted by ORDERING
+//          THE RUNS by their first key and moving them; where that does not hold (interleaved or too many runs) the
+//          staged keys go through a bitonic network.  In the sharded front end the owner of a tile sorts the
+//          concatenation of the ranks' segments, so the sorting work is divided with the tiles.
+//  longer lists (tile_scan_kernel's "long" work list, up to kSortLarge entries) are radix-sorted in dynamic shared
+//          memory, one CTA per SM, before the raster kernel (bin_sort_long_kernel)
+//  lists beyond that stay in scatter order and are counted in frameInfo[2] (the image does not
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
-constexpr int kSortWarpRadix = 1024; // <= : tier 1, one warp per tile (run ordering in shared memory)
-constexpr int kSortSmall = 4096;     // <= : tier 2, one CTA per tile
-constexpr int kSortLarge = 40960;    // <= : tier 3, one CTA per SM, dynamic shared memory
+//  B2R_OPT_SORT_BINS = 0 leaves all lists in scatter order; b2r_read_bins then canonicalises them when they are
+//  read (bin_sort_tiles_kernel: the same CTA-level sort, one CTA per tile).
+constexpr int kStage = 2048;         // <= : staged + sorted by the tile's raster CTA
+constexpr int kSortLarge = 40960;    // <= : one CTA per SM, dynamic shared memory
 constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
+constexpr int kSortThreads = 256, kSortPerThread = kStage / kSortThreads;     // 8 consecutive keys per thread
+constexpr int kCtaRuns = 512;        // more runs than this: bitonic fallback
 
-// register bitonic network over 256 keys held 8 per lane, virtual index v = i*32 + lane
-__device__ __forceinline__ void warpBitonic256(uint32_t (&a)[8], uint32_t lane)
+// exclusive scan of one value per thread over a 256-thread CTA; *total receives the block sum
+__device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* sWarp /*[9]*/, uint32_t* total)
 {
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
 	#pragma unroll
-	for (uint32_t k = 2; k <= 256; k <<= 1)
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+	__syncthreads();                       // sWarp may still be read from a previous call
+	if (lane == 31) sWarp[warp] = incl;
+	__syncthreads();
+	if (threadIdx.x == 0)
 	{
-		#pragma unroll
-		for (uint32_t j = k >> 1; j > 0; j >>= 1)
-		{
-			if (j >= 32)
-			{
-				const int ji = j >> 5;
-				#pragma unroll
-				for (int i = 0; i < 8; ++i)
-				{
-					const int p = i ^ ji;
-					if (p > i)
-					{
-						const bool up = (((uint32_t)i * 32u) & k) == 0;     // k >= 64 here: direction depends on i only
-						const uint32_t x = a[i], y = a[p];
-						if ((x > y) == up) { a[i] = y; a[p] = x; }
-					}
-				}
-			}
-			else
-			{
-				#pragma unroll
-				for (int i = 0; i < 8; ++i)
-				{
-					const uint32_t v = (uint32_t)i * 32u + lane;
-					const bool up = (v & k) == 0;
-					const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, a[i], j);
-					const bool lower = (lane & j) == 0;
-					a[i] = (lower == up) ? min(a[i], y) : max(a[i], y);
-				}
-			}
-		}
+		uint32_t run = 0;
+		for (int w = 0; w < 8; ++w) { const uint32_t c = sWarp[w]; sWarp[w] = run; run += c; }
+		sWarp[8] = run;
 	}
+	__syncthreads();
+	*total = sWarp[8];
+	return sWarp[warp] + incl - v;
 }
 
-#ifndef B2R_SORT_MAX_RUNS
-#define B2R_SORT_MAX_RUNS 64
-#endif
-constexpr int kMaxRuns = B2R_SORT_MAX_RUNS;   // more runs than this: the tile goes to the CTA-level sorter
-__global__ void __launch_bounds__(256) bin_sort_runs_kernel(
-	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
-	const uint32_t* __restrict__ smallTiles, uint32_t* __restrict__ fallbackTiles, unsigned long long* __restrict__ frameInfo)
+// scratch of ctaSortTileList (the raster kernel overlays it on its big-triangle buffer, which is idle until the sweep)
+struct __align__(16) SortScratch
 {
-	pdlPrologue();
-	__shared__ uint32_t sK[8][kSortWarpRadix];
-	__shared__ uint16_t sStart[8][kMaxRuns + 1], sOrder[8][kMaxRuns], sOut[8][kMaxRuns];
-	if (frameInfo[1]) return;
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	// the grid covers the worst case (every tile on the list); the CTAs behind the list's end leave at once
-	const uint32_t entry = blockIdx.x * 8 + warp;
-	if (entry >= (uint32_t)frameInfo[8]) return;
-	const uint32_t tile = __ldg(smallTiles + entry);
-	const uint32_t n = tileCount[tile];
-	if (n < 2 || n > (uint32_t)kSortWarpRadix) return;
-	uint32_t* list = binIds + tileOffset[tile];
-	uint32_t* K = sK[warp];
-	uint16_t* S = sStart[warp];
-	const unsigned ltMask = (1u << lane) - 1u;
-	// 1. stage the keys and find the runs.  A run = the ids one scatter warp wrote: it ends where the
-	//    next key is smaller or belongs to another 32-aligned id group (warpBinRects: one ascending run
-	//    per warp and tile, and a warp's ids are one aligned group of 32)
-	uint32_t runs = 0, carry = 0;
-	bool descent = false;
-	// stage the list in shared memory first: the loads are independent, so they are all in flight together
-	// (the run detection below is a serial chain over the 32-entry batches)
-	#pragma unroll 4
-	for (uint32_t i = lane; i < n; i += 32) K[i] = list[i];
-	__syncwarp();
-	for (uint32_t b = 0; b < n; b += 32)
+	uint32_t head[kCtaRuns];
+	uint16_t start[kCtaRuns + 2], order[kCtaRuns], out[kCtaRuns];
+	uint32_t warpScan[9];
+};
+
+// Sort the n <= kStage keys staged in K (shared memory, capacity kStage, 16-byte aligned) into ascending order and
+// store them through put(position, key) - the tile's list in global memory (one contiguous list, or the ranks'
+// segments of the sharded front end).  All 256 threads of the CTA call it; K holds some permutation of the keys
+// afterwards.  Returns 0 = the list was in order already (nothing stored), 1 = runs moved, 2 = bitonic fallback.
+template <typename Put>
+__device__ __forceinline__ int ctaSortTileList(uint32_t* K, uint32_t n, SortScratch& S, Put put)
+{
+	const uint32_t tid = threadIdx.x;
+	// 1. run starts among this thread's kSortPerThread consecutive keys.  A run = the ids one scatter warp wrote: it ends
+	//    where the next key is smaller or belongs to another 32-aligned id group
+	const uint32_t first = tid * kSortPerThread;
+	uint32_t key[kSortPerThread];
+	uint32_t flags = 0;
+	int descent = 0;
+	if (first < n)
 	{
-		const uint32_t i = b + lane;
-		const uint32_t k = (i < n) ? K[i] : 0xFFFFFFFFu;
-		uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k, 1);
-		if (lane == 0) prev = carry;
-		const bool start = (i < n) && (i == 0 || prev > k || (prev >> 5) != (k >> 5));
-		descent |= (i < n) && i > 0 && prev > k;
-		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
-		if (start)
+		const uint4 a = *reinterpret_cast<const uint4*>(K + first), b = *reinterpret_cast<const uint4*>(K + first + 4);
+		key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
+		uint32_t prev = first ? K[first - 1] : 0u;
+		#pragma unroll
+		for (uint32_t k = 0; k < (uint32_t)kSortPerThread; ++k)
 		{
-			const uint32_t r = runs + (uint32_t)__popc(m & ltMask);
-			if (r < (uint32_t)kMaxRuns) S[r] = (uint16_t)i;
+			const uint32_t i = first + k;
+			if (i < n)
+			{
+				if (i == 0 || prev > key[k] || (prev >> 5) != (key[k] >> 5)) flags |= 1u << k;
+				descent |= (i > 0 && prev > key[k]);
+			}
+			prev = key[k];
 		}
-		runs += (uint32_t)__popc(m);
-		carry = __shfl_sync(0xFFFFFFFFu, k, 31);
 	}
-	if (!__any_sync(0xFFFFFFFFu, descent)) return;           // already in canonical order
-	__syncwarp();
-	if (n <= 256 && runs > 24)
-	{
-		// short list made of many short runs (e.g. cooperatively binned big triangles): sort the keys directly
-		uint32_t a[8];
-		#pragma unroll
-		for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; a[i] = (v < n) ? K[v] : 0xFFFFFFFFu; }
-		warpBitonic256(a, lane);
-		#pragma unroll
-		for (int i = 0; i < 8; ++i) { const uint32_t v = i * 32 + lane; if (v < n) list[v] = a[i]; }
-		return;
-	}
-	bool fallback = runs > (uint32_t)kMaxRuns;
+	if (!__syncthreads_or(descent)) return 0;
+	uint32_t runs = 0;
+	const uint32_t runBase = blockExclusiveScan256((uint32_t)__popc(flags), S.warpScan, &runs);
+	bool fallback = runs > (uint32_t)kCtaRuns;
 	if (!fallback)
 	{
-		if (lane == 0) S[runs] = (uint16_t)n;
-		__syncwarp();
+		for (uint32_t k = 0, r = runBase; k < (uint32_t)kSortPerThread; ++k)
+			if (flags & (1u << k)) { S.start[r] = (uint16_t)(first + k); S.head[r] = key[k]; ++r; }
+		if (tid == 0) S.start[runs] = (uint16_t)n;
+		__syncthreads();
 		// 2. order the runs by their first key (keys are distinct primitive ids)
-		for (uint32_t r = lane; r < runs; r += 32)
+		for (uint32_t r = tid; r < runs; r += kSortThreads)
 		{
-			const uint32_t head = K[S[r]];
+			const uint32_t head = S.head[r];
 			uint32_t rank = 0;
-			for (uint32_t q = 0; q < runs; ++q) rank += (K[S[q]] < head) ? 1u : 0u;
-			sOrder[warp][rank] = (uint16_t)r;
+			for (uint32_t q = 0; q < runs; ++q) rank += (S.head[q] < head) ? 1u : 0u;
+			S.order[rank] = (uint16_t)r;
 		}
-		__syncwarp();
-		// 3. output position of every run = prefix of the run lengths in that order; the runs must
-		//    cover disjoint id ranges (last key of a run < first key of the next one)
-		uint32_t running = 0;
-		bool bad = false;
-		for (uint32_t b = 0; b < runs; b += 32)
+		__syncthreads();
+		// 3. output position of every run = prefix of the run lengths in that order (two runs per thread); the runs
+		//    must cover disjoint id ranges (last key of a run < first key of the next one)
+		uint32_t len0 = 0, len1 = 0, r0 = 0, r1 = 0;
+		int bad = 0;
+		const uint32_t k0 = 2 * tid, k1 = 2 * tid + 1;
+		if (k0 < runs)
 		{
-			const uint32_t kk = b + lane;
-			uint32_t len = 0, r = 0;
-			if (kk < runs)
+			r0 = S.order[k0]; len0 = (uint32_t)S.start[r0 + 1] - (uint32_t)S.start[r0];
+			if (k0 + 1 < runs) bad |= K[S.start[r0 + 1] - 1] > S.head[S.order[k0 + 1]];
+		}
+		if (k1 < runs)
+		{
+			r1 = S.order[k1]; len1 = (uint32_t)S.start[r1 + 1] - (uint32_t)S.start[r1];
+			if (k1 + 1 < runs) bad |= K[S.start[r1 + 1] - 1] > S.head[S.order[k1 + 1]];
+		}
+		uint32_t total = 0;
+		const uint32_t pos = blockExclusiveScan256(len0 + len1, S.warpScan, &total);
+		if (k0 < runs) S.out[r0] = (uint16_t)pos;
+		if (k1 < runs) S.out[r1] = (uint16_t)(pos + len0);
+		fallback = __syncthreads_or(bad) != 0;
+	}
+	if (!fallback)
+	{
+		// 4. move every key to its run's output position
+		#pragma unroll
+		for (uint32_t k = 0; k < (uint32_t)kSortPerThread; ++k)
+		{
+			const uint32_t i = first + k;
+			if (i < n)
 			{
-				r = sOrder[warp][kk];
-				len = (uint32_t)S[r + 1] - (uint32_t)S[r];
-				if (kk + 1 < runs) bad |= K[S[r + 1] - 1] > K[S[sOrder[warp][kk + 1]]];
+				const uint32_t r = runBase + (uint32_t)__popc(flags & ((2u << k) - 1u)) - 1u;
+				put((uint32_t)S.out[r] + (i - (uint32_t)S.start[r]), key[k]);
 			}
-			uint32_t incl = len;
-			#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-			if (kk < runs) sOut[warp][r] = (uint16_t)(running + incl - len);
-			running += __shfl_sync(0xFFFFFFFFu, incl, 31);
 		}
-		fallback = __any_sync(0xFFFFFFFFu, bad);
+		return 1;
 	}
-	if (fallback)
-	{
-		// interleaved or too many runs (incoherent warps, big triangles in a long list): radix-sort this tile instead
-		if (lane == 0) { fallbackTiles[atomicAdd(&frameInfo[5], 1ull)] = tile; atomicAdd(&frameInfo[6], 1ull); }
-		return;
-	}
-	__syncwarp();
-	// 4. move every key to its run's output position
-	uint32_t before = 0;
-	for (uint32_t b = 0; b < n; b += 32)
-	{
-		const uint32_t i = b + lane;
-		const bool start = (i < n) && (i == 0 || K[i - 1] > K[i] || (K[i - 1] >> 5) != (K[i] >> 5));
-		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
-		if (i < n)
-		{
-			const uint32_t r = before + (uint32_t)__popc(m & (ltMask | (1u << lane))) - 1u;
-			list[(uint32_t)sOut[warp][r] + (i - (uint32_t)S[r])] = K[i];
-		}
-		before += (uint32_t)__popc(m);
-	}
+	// interleaved or too many runs (incoherent warps, cooperatively binned big triangles): bitonic network over the
+	// staged keys, padded to a power of two.  Short lists are sorted by one warp alone (no CTA barriers).
+	uint32_t P = 2;
+	while (P < n) P <<= 1;
+	for (uint32_t i = n + tid; i < P; i += kSortThreads) K[i] = 0xFFFFFFFFu;
+	__syncthreads();
+	const bool oneWarp = P <= 256u;
+	const uint32_t workers = oneWarp ? 32u : (uint32_t)kSortThreads;
+	if (!oneWarp || tid < 32u)
+		for (uint32_t k = 2; k <= P; k <<= 1)
+			for (uint32_t j = k >> 1; j > 0; j >>= 1)
+			{
+				for (uint32_t idx = tid; idx < (P >> 1); idx += workers)
+				{
+					const uint32_t i = ((idx & ~(j - 1u)) << 1) | (idx & (j - 1u)), p = i | j;
+					const uint32_t x = K[i], y = K[p];
+					if ((x > y) == ((i & k) == 0u)) { K[i] = y; K[p] = x; }
+				}
+				if (oneWarp) __syncwarp(); else __syncthreads();
+			}
+	if (oneWarp) __syncthreads();
+	for (uint32_t i = tid; i < n; i += kSortThreads) put(i, K[i]);
+	return 2;
 }
 
 // Block-level stable LSD radix sort (8-bit digits) of one tile list.  Keys are distinct primitive
@@ -1014,122 +1017,25 @@ __device__ __forceinline__ void radixSortTileList(uint32_t* __restrict__ list, u
 		for (uint32_t i = tid; i < n; i += WARPS * 32) list[i] = src[i];
 }
 
-// exclusive scan of one value per thread over a 256-thread CTA; *total receives the block sum
-__device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* sWarp /*[9]*/, uint32_t* total)
+// canonical order on demand (b2r_read_bins after frames rendered with B2R_OPT_SORT_BINS = 0): the raster kernel's
+// CTA-level sort as a kernel of its own, one CTA per tile with 2..kStage entries
+__global__ void __launch_bounds__(kSortThreads) bin_sort_tiles_kernel(
+	const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds, uint32_t nTiles,
+	unsigned long long* __restrict__ frameInfo)
 {
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t incl = v;
-	#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-	__syncthreads();                       // sWarp may still be read from a previous call
-	if (lane == 31) sWarp[warp] = incl;
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		uint32_t run = 0;
-		for (int w = 0; w < 8; ++w) { const uint32_t c = sWarp[w]; sWarp[w] = run; run += c; }
-		sWarp[8] = run;
-	}
-	__syncthreads();
-	*total = sWarp[8];
-	return sWarp[warp] + incl - v;
-}
-
-// tier 2 (kSortWarpRadix < n <= kSortSmall): one CTA per tile.  Same idea as bin_sort_runs_kernel at CTA
-// scale: the list consists of at most kMidRuns ascending runs (one per (warp, tile) pair of the scatter)
-// that cover disjoint id ranges, so ordering the RUN HEADS and moving whole runs sorts the list; if the
-// runs interleave or there are too many of them the CTA falls back to the radix sort.
-constexpr int kMidRuns = 512, kMidPerThread = kSortSmall / 256;
-__global__ void __launch_bounds__(256) bin_sort_mid_kernel(
-	const uint32_t* __restrict__ midTiles, const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
-	uint32_t* __restrict__ binIds, const unsigned long long* __restrict__ frameInfo)
-{
-	pdlPrologue();
-	__shared__ uint32_t sA[kSortSmall], sB[kSortSmall], sHist[8 * 256], sRed[2 * 8 + 2];
-	__shared__ uint32_t sHead[kMidRuns], sWarpScan[9];
-	__shared__ uint16_t sStart[kMidRuns + 1], sOrder[kMidRuns], sOut[kMidRuns];
+	__shared__ __align__(16) uint32_t sK[kStage];
+	__shared__ SortScratch sS;
 	if (frameInfo[1]) return;
-	const uint32_t nMid = (uint32_t)frameInfo[5];
-	const uint32_t tid = threadIdx.x;
-	for (uint32_t w = blockIdx.x; w < nMid; w += gridDim.x)
+	for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x)
 	{
-		const uint32_t tile = midTiles[w];
 		const uint32_t n = tileCount[tile];
+		if (n < 2 || n > (uint32_t)kStage) continue;
 		uint32_t* list = binIds + tileOffset[tile];
 		__syncthreads();
-		for (uint32_t i = tid; i < n; i += 256) sA[i] = list[i];
+		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) sK[i] = list[i];
 		__syncthreads();
-		// 1. run starts of this thread's kMidPerThread consecutive entries
-		const uint32_t first = tid * kMidPerThread;
-		uint32_t flags = 0;
-		int descent = 0;
-		#pragma unroll
-		for (uint32_t k = 0; k < (uint32_t)kMidPerThread; ++k)
-		{
-			const uint32_t i = first + k;
-			if (i < n)
-			{
-				const uint32_t cur = sA[i], prev = i ? sA[i - 1] : 0u;
-				if (i == 0 || prev > cur || (prev >> 5) != (cur >> 5)) flags |= 1u << k;
-				descent |= (i > 0 && prev > cur);
-			}
-		}
-		if (!__syncthreads_or(descent)) continue;          // already in canonical order
-		uint32_t runs = 0;
-		const uint32_t runBase = blockExclusiveScan256((uint32_t)__popc(flags), sWarpScan, &runs);
-		bool fallback = runs > (uint32_t)kMidRuns;
-		if (!fallback)
-		{
-			for (uint32_t k = 0, r = runBase; k < (uint32_t)kMidPerThread; ++k)
-				if (flags & (1u << k)) { sStart[r] = (uint16_t)(first + k); sHead[r] = sA[first + k]; ++r; }
-			if (tid == 0) sStart[runs] = (uint16_t)n;
-			__syncthreads();
-			// 2. order the runs by their first key (keys are distinct primitive ids)
-			for (uint32_t r = tid; r < runs; r += 256)
-			{
-				const uint32_t head = sHead[r];
-				uint32_t rank = 0;
-				for (uint32_t q = 0; q < runs; ++q) rank += (sHead[q] < head) ? 1u : 0u;
-				sOrder[rank] = (uint16_t)r;
-			}
-			__syncthreads();
-			// 3. output position of every run = prefix of the run lengths in that order (two runs per thread);
-			//    the runs must cover disjoint id ranges (last key of a run < first key of the next one)
-			uint32_t len0 = 0, len1 = 0, r0 = 0, r1 = 0;
-			int bad = 0;
-			const uint32_t k0 = 2 * tid, k1 = 2 * tid + 1;
-			if (k0 < runs)
-			{
-				r0 = sOrder[k0]; len0 = (uint32_t)sStart[r0 + 1] - (uint32_t)sStart[r0];
-				if (k0 + 1 < runs) bad |= sA[sStart[r0 + 1] - 1] > sHead[sOrder[k0 + 1]];
-			}
-			if (k1 < runs)
-			{
-				r1 = sOrder[k1]; len1 = (uint32_t)sStart[r1 + 1] - (uint32_t)sStart[r1];
-				if (k1 + 1 < runs) bad |= sA[sStart[r1 + 1] - 1] > sHead[sOrder[k1 + 1]];
-			}
-			uint32_t total = 0;
-			const uint32_t pos = blockExclusiveScan256(len0 + len1, sWarpScan, &total);
-			if (k0 < runs) sOut[r0] = (uint16_t)pos;
-			if (k1 < runs) sOut[r1] = (uint16_t)(pos + len0);
-			fallback = __syncthreads_or(bad) != 0;
-		}
-		if (fallback)
-		{
-			radixSortTileList<8>(list, n, sA, sB, sHist, sRed);
-			continue;
-		}
-		// 4. move every key to its run's output position
-		#pragma unroll
-		for (uint32_t k = 0; k < (uint32_t)kMidPerThread; ++k)
-		{
-			const uint32_t i = first + k;
-			if (i < n)
-			{
-				const uint32_t r = runBase + (uint32_t)__popc(flags & ((2u << k) - 1u)) - 1u;
-				list[(uint32_t)sOut[r] + (i - (uint32_t)sStart[r])] = sA[i];
-			}
-		}
+		const int how = ctaSortTileList(sK, n, sS, [&](uint32_t pos, uint32_t key) { list[pos] = key; });
+		if (how == 2 && threadIdx.x == 0) atomicAdd(&frameInfo[6], 1ull);
 	}
 }
 

@@ -22,7 +22,7 @@ struct RasterArgs
 {
 	const uint32_t* tileCount;
 	const uint32_t* tileOffset;
-	const uint32_t* binIds;
+	const uint32_t* binIds;     // (the kernel writes the lists it sorts back through these pointers)
 	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
 	const float4* posIn;        // resident model-space positions (x, y, z, 1): read instead of pos4 by the OTF instantiations
@@ -35,6 +35,7 @@ struct RasterArgs
 	float* zSurface;        // debug surfaces (may be null)
 	uint32_t* winnerSurface;
 	ShardTable shard;       // sharded front end only (fp.shardGeometry): the per-rank lists of this rank's tiles, all in local memory
+	const uint32_t* tileOrder;  // the work order tile_scan_kernel prepared: kTileClasses lists of nTiles entries (not with the sharded front end)
 };
 
 // expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
@@ -198,10 +199,10 @@ __device__ __forceinline__ RGB shadePixel(const RasterArgs& A, const MeshConst& 
 	return c;
 }
 
-#ifndef B2R_RASTER_PREFETCH
-#define B2R_RASTER_PREFETCH 1
+constexpr int kListChunk = 256;       // bin-list entries processed per sweep iteration (one per thread)
+#ifndef B2R_RASTER_LOOKAHEAD
+#define B2R_RASTER_LOOKAHEAD 1        // a thread holds the vertex reference of its NEXT list entry in registers while it works on the current one
 #endif
-constexpr int kListChunk = 256;       // bin-list entries staged per iteration (one per thread)
 #ifndef B2R_SMALL_AREA
 #define B2R_SMALL_AREA 48
 #endif
@@ -243,10 +244,11 @@ __device__ __forceinline__ void fetchPositions(const RasterArgs& A, const float 
 	}
 }
 
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 // TEXTURED = false is the light variant for frames in which no mesh has a diffuse map and the
 // visualisation is PBR (vertex colours only): the texture/normal-mapping path is compiled out, which
 // frees enough registers for 6 resident CTAs per SM instead of 4.
-template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF = false>
 #ifndef B2R_RASTER_LIGHT_CTAS
 #define B2R_RASTER_LIGHT_CTAS 6
 #endif
@@ -256,327 +258,428 @@ template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF = false>
 #ifndef B2R_RASTER_LIGHT_OTF_CTAS
 #define B2R_RASTER_LIGHT_OTF_CTAS 5      // the light variant that also transforms its vertices: 48 registers instead of 40
 #endif
-__global__ void __launch_bounds__(kTile * kTile, TEXTURED ? B2R_RASTER_FULL_CTAS : (OTF ? B2R_RASTER_LIGHT_OTF_CTAS : B2R_RASTER_LIGHT_CTAS)) raster_shade_kernel(RasterArgs A, FrameParams fp)
+constexpr int rasterCtasPerSM(bool textured, bool otf) { return textured ? B2R_RASTER_FULL_CTAS : (otf ? B2R_RASTER_LIGHT_OTF_CTAS : B2R_RASTER_LIGHT_CTAS); }
+
+// The kernel is PERSISTENT: rasterCtasPerSM() CTAs per SM take work items off a counter (frameInfo[kInfoWorkCounter]).
+// A work item is one 16x16 pixel block (a tile, or one sub-block of a bin larger than 16x16) in the order
+// tile_scan_kernel prepared - longest lists first, the empty tiles last, kEmptyBatch of them per item - or, with the
+// sharded front end, the rank's own tiles in index order (their merged lengths are only known tile by tile).
+template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF = false>
+__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(RasterArgs A, FrameParams fp)
 {
 	pdlPrologue();
-	__shared__ TriShared sBig[kListChunk];             // expanded records of the pixel-parallel triangles
+	// expanded records of the pixel-parallel triangles during the sweep; before it, the scratch of the list sort
+	__shared__ __align__(16) unsigned char sBigRaw[sizeof(TriShared) * kListChunk];
+	static_assert(sizeof(SortScratch) <= sizeof(TriShared) * kListChunk, "the sort scratch overlays the big-triangle buffer");
+	TriShared* const sBig = reinterpret_cast<TriShared*>(sBigRaw);
+	SortScratch& sSort = *reinterpret_cast<SortScratch*>(sBigRaw);
+	__shared__ __align__(16) uint32_t sIds[kStage];    // the tile's list (primitive ids), staged for the sort and the sweep
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
 	__shared__ uint32_t sNumBig[2];                    // big-triangle count of the current / the next list chunk
-	__shared__ float sWvp[OTF ? kSmemMeshes : 1][16];  // OTF: WVP of the first meshes (visible after the barriers that precede the list sweep)
+	__shared__ uint32_t sWork[2];
+	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
+	__shared__ float sWvp[OTF ? kSmemMeshes : 1][16];  // OTF: WVP of the first meshes (visible after the first barrier)
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
-	if (OTF && threadIdx.x < min(fp.nMeshes, kSmemMeshes) * 16u) sWvp[threadIdx.x >> 4][threadIdx.x & 15u] = A.meshes[threadIdx.x >> 4].wvp[threadIdx.x & 15u];
-	const uint32_t ownedIdx = blockIdx.x;
-	const uint32_t bin = fp.ownerRank + ownedIdx * fp.ownerCount;
-	uint32_t binX, subX;
-	const uint32_t binY = divMagic(bin, fp.binsX, fp.binsXMagic, binX);
-	const uint32_t subY = divMagic(blockIdx.y, fp.subX, fp.subXMagic, subX);
 	const int tid = threadIdx.x;
-	const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
-	// extent of this CTA's pixel block inside the bin and the screen
-	const int ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
-	const int ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
-	const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
-	const bool live = px < ex && py < ey;
-	const float fx = (float)px, fy = (float)py;
-	// rows covered by this warp (two 16-pixel rows): triangles whose bbox misses them are skipped warp-wide
-	const int warpY0 = oy + ((tid >> 5) << 1), warpY1 = warpY0 + 2;
+	if (OTF && (uint32_t)tid < min(fp.nMeshes, kSmemMeshes) * 16u) sWvp[tid >> 4][tid & 15u] = A.meshes[tid >> 4].wvp[tid & 15u];
+	const uint32_t nTilesAll = fp.binsX * fp.binsY;
+	const uint32_t subs = fp.subX * fp.subY;
 
-	int bestZ = 0x7FFFFFFF;          // register copy of this pixel's depth/winner for the pixel-parallel path
-	uint32_t bestPrim = kNoPrim;
-	uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
-	sKey[tid] = kEmptyKey;
-	if (tid < 2) sNumBig[tid] = 0;
-	uint32_t n;
-	const uint32_t* list = nullptr;
-	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
-	if (fp.shardGeometry)
+	// work items: [sCum[c], sCum[c + 1]) = class c (in shared memory: live across the whole persistent loop)
+	__shared__ uint32_t sCum[kTileClasses + 2];        // [kTileClasses + 1] = 16x16 blocks of the empty class
+	if (tid == 0)
 	{
-		// Sharded front end.  Rank p built the ascending list of ITS primitive slice for every tile and pushed
-		// the heads (after its scan) and the sorted ids (after its sort) of the tiles owned here into this
-		// rank's memory.  The slices are contiguous and ordered by rank, so the tile's list is the
-		// concatenation of the n segments in rank order: read the n heads at once, one lane per rank.
-		if (tid < 32)
-		{
-			uint32_t cnt = 0, off = 0, bad = 0;
-			if ((uint32_t)tid < fp.ownerCount)
-			{
-				cnt = __ldg(A.shard.tileCount[tid] + bin);
-				off = __ldg(A.shard.tileOffset[tid] + bin);
-				bad = __ldg(A.shard.tileOffset[tid] + fp.binsX * fp.binsY) == 0xFFFFFFFFu;   // that rank's list buffer overflowed
-			}
-			uint32_t incl = cnt;
-			#pragma unroll
-			for (int d = 1; d < kMaxRanks; d <<= 1)
-			{
-				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-				if (tid >= d) incl += t;
-			}
-			if (__any_sync(0xFFFFFFFFu, bad))
-			{
-				incl = 0;                                  // void frame: the host reports the undersized list capacity
-				if (tid == 0) A.frameInfo[1] = 1ull;
-			}
-			if (tid < kMaxRanks) { sSegEnd[tid] = incl; sSegOff[tid] = off; }
-		}
-		__syncthreads();
-		n = sSegEnd[fp.ownerCount - 1];
-	}
-	else
-	{
-		n = A.tileCount[bin];
-		list = A.binIds + A.tileOffset[bin];
-	}
-
-	// One list entry -> screen-space triangle + its candidate box inside this CTA's block.  Returns the number of
-	// candidate pixels (0: nothing to do).
-	auto expandEntry = [&](uint32_t prim, TriShared& t, int& x0, int& x1, int& y0, int& y1) -> int
-	{
-		// rebuild the screen-space triangle from the static reference + the transformed positions
-		// (same code, hence the same bits, wherever a triangle is expanded)
-		const uint4 tr = __ldg(A.triRefs + prim);
-		float4 p0, p1, p2;
-		fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
-		TriRecord r;
-		rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
-		// candidate pixels = the record's conservative box clipped to this CTA's block; the box
-		// contains every pixel whose edge functions can all be >= 0, so this equals the
-		// reference's test of every pixel of the bin (CUDARenderer.cu:1116-1127)
-		x0 = max((int)(r.cbX & 0xFFFFu), ox); x1 = min((int)(r.cbX >> 16), ex);
-		y0 = max((int)(r.cbY & 0xFFFFu), oy); y1 = min((int)(r.cbY >> 16), ey);
-		const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
-		if (area > 0) expandRecord(r, prim, t);
-		return area;
-	};
-	auto listEntry = [&](uint32_t e) -> uint32_t
-	{
+		uint32_t run = 0, emptyBlocks = 0;
+		sCum[0] = 0;
 		if (fp.shardGeometry)
 		{
-			uint32_t seg = 0;
-			while (e >= sSegEnd[seg]) ++seg;
-			return __ldg(A.shard.binIds[seg] + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u)));
+			const uint32_t owned = nTilesAll > fp.ownerRank ? (nTilesAll - fp.ownerRank + fp.ownerCount - 1u) / fp.ownerCount : 0u;
+			for (uint32_t c = 0; c < kTileClasses; ++c) sCum[c + 1] = owned * subs;
 		}
-		return __ldg(list + e);
-	};
-	// pixel-parallel path: every thread tests its own pixel against the large triangles staged in sBig
-	auto pixelParallel = [&](uint32_t nBig)
-	{
-		for (uint32_t j = 0; j < nBig; ++j)
-		{
-			TriShared t = sBig[j];
-			const int ty0 = (int)(t.yExtent & 0xFFFFu), ty1 = (int)(t.yExtent >> 16);
-			if (ty1 <= warpY0 || ty0 >= warpY1) continue;          // warp-uniform
-			if (!COUNT && t.zLow > bestZ) continue;                // cannot win this pixel (per lane)
-			Bary bc; int zi;
-			if (live && fragmentTest<TOPLEFT>(t, fx, fy, bc, zi))
+		else
+			for (uint32_t c = 0; c < kTileClasses; ++c)
 			{
-				if (COUNT) ++nFrags;
-				if (zi < bestZ || (zi == bestZ && t.prim < bestPrim)) { bestZ = zi; bestPrim = t.prim; }
+				const uint32_t blocks = (uint32_t)A.frameInfo[kInfoClassBase + c] * subs;
+				if (c + 1 == kTileClasses) emptyBlocks = blocks;
+				run += (c + 1 < kTileClasses) ? blocks : (blocks + kEmptyBatch - 1u) / kEmptyBatch;
+				sCum[c + 1] = run;
 			}
-		}
-	};
-
-	if (n && !fp.shardGeometry) __syncthreads();       // sKey / counters initialised (the sharded path has synchronised above)
-	// Sweep 1, no barriers: every thread walks its entries of all chunks of the list.  Small triangles are resolved
-	// right away (triangle-parallel, atomicMin into sKey); large ones are only collected in sBig - up to kListChunk of
-	// them for the WHOLE list - and rasterised pixel-parallel after the sweep.  The warps of the CTA therefore drift
-	// apart over a long list instead of meeting at two barriers per chunk, and their memory round trips
-	// (id -> vertex reference -> positions) overlap each other's arithmetic.
-#if B2R_RASTER_PREFETCH
-	uint32_t primAhead = 0;
-	if (!fp.shardGeometry && (uint32_t)tid < n) primAhead = __ldg(list + tid);
-#endif
-	for (uint32_t base = 0; base < n; base += kListChunk)
-	{
-#if B2R_RASTER_PREFETCH
-		// the id of the next chunk's entry is loaded one chunk ahead, its vertex reference pulled into L2 afterwards
-		const uint32_t primNow = primAhead;
-		const bool haveNext = !fp.shardGeometry && base + kListChunk + (uint32_t)tid < n;
-		if (haveNext) primAhead = __ldg(list + base + kListChunk + tid);
-#endif
-		if (base + (uint32_t)tid < n)
-		{
-#if B2R_RASTER_PREFETCH
-			const uint32_t prim = fp.shardGeometry ? listEntry(base + tid) : primNow;
-#else
-			const uint32_t prim = listEntry(base + tid);
-#endif
-			TriShared t;
-			int x0, x1, y0, y1;
-			const int area = expandEntry(prim, t, x0, x1, y0, y1);
-			if (area > kSmallArea)
-			{
-				const uint32_t slot = atomicAdd(&sNumBig[0], 1u);
-				if (slot < (uint32_t)kListChunk)
-				{
-					TriShared& dst = sBig[slot];
-					dst = t;
-					dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);      // bbox rows for the warp-level reject
-				}
-			}
-			else if (area > 0)
-			{
-				// triangle-parallel: this thread walks the few candidate pixels
-				for (int y = y0; y < y1; ++y)
-					for (int x = x0; x < x1; ++x)
-					{
-						Bary bc; int zi;
-						if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
-						{
-							const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
-							atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
-							if (COUNT) ++nFrags;
-						}
-					}
-			}
-		}
-#if B2R_RASTER_PREFETCH
-		if (haveNext) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.triRefs + primAhead));
-#endif
+		sCum[kTileClasses + 1] = emptyBlocks;
 	}
-	if (n)
+
+	for (uint32_t iter = 0; ; ++iter)
 	{
+		if (tid == 0) sWork[iter & 1u] = (uint32_t)atomicAdd(&A.frameInfo[kInfoWorkCounter], 1ull);
 		__syncthreads();
-		const uint32_t nBigTotal = sNumBig[0];
-		if (nBigTotal <= (uint32_t)kListChunk)
-			pixelParallel(nBigTotal);
+		const uint32_t item = sWork[iter & 1u];
+		if (item >= sCum[kTileClasses]) break;
+		// item -> pixel blocks [v0, v1) of one class list (one block, or a batch of empty ones)
+		uint32_t cls = 0, v0 = item, v1 = item + 1;
+		const uint32_t* order = nullptr;
+		if (!fp.shardGeometry)
+		{
+			uint32_t start = 0;
+			#pragma unroll
+			for (uint32_t c = 1; c < kTileClasses; ++c)
+			{
+				const uint32_t lo = sCum[c];
+				if (item >= lo) { cls = c; start = lo; }
+			}
+			v0 = item - start; v1 = v0 + 1;
+			if (cls == kTileClasses - 1u)
+			{
+				v0 *= kEmptyBatch;
+				v1 = min(v0 + kEmptyBatch, sCum[kTileClasses + 1]);
+			}
+			order = A.tileOrder + (size_t)cls * nTilesAll;
+		}
+	for (uint32_t vb = v0; vb < v1; ++vb)
+	{
+		uint32_t sub;
+		const uint32_t slot = divMagic(vb, subs, fp.subsMagic, sub);
+		const uint32_t bin = fp.shardGeometry ? fp.ownerRank + slot * fp.ownerCount : __ldg(order + slot);
+		uint32_t binX, subX;
+		const uint32_t binY = divMagic(bin, fp.binsX, fp.binsXMagic, binX);
+		const uint32_t subY = divMagic(sub, fp.subX, fp.subXMagic, subX);
+		const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
+		// extent of this CTA's pixel block inside the bin and the screen
+		const int ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
+		const int ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
+		const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
+		const bool live = px < ex && py < ey;
+		const float fx = (float)px, fy = (float)py;
+		// rows covered by this warp (two 16-pixel rows): triangles whose bbox misses them are skipped warp-wide
+		const int warpY0 = oy + ((tid >> 5) << 1), warpY1 = warpY0 + 2;
+
+		int bestZ = 0x7FFFFFFF;          // register copy of this pixel's depth/winner for the pixel-parallel path
+		uint32_t bestPrim = kNoPrim;
+		uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
+		uint32_t n;
+		const uint32_t* list = nullptr;
+		if (fp.shardGeometry)
+		{
+			// Sharded front end.  Rank p built the list of ITS primitive slice for every tile and pushed the heads
+			// (after its scan) and the ids (after its scatter) of the tiles owned here into this rank's memory.
+			// The slices are contiguous and ordered by rank, so the tile's list is the concatenation of the n
+			// segments in rank order: read the n heads at once, one lane per rank.
+			__syncthreads();                  // the previous block's readers of sSegEnd / sSegOff are done
+			if (tid < 32)
+			{
+				uint32_t cnt = 0, off = 0, bad = 0;
+				if ((uint32_t)tid < fp.ownerCount)
+				{
+					cnt = __ldg(A.shard.tileCount[tid] + bin);
+					off = __ldg(A.shard.tileOffset[tid] + bin);
+					bad = __ldg(A.shard.tileOffset[tid] + nTilesAll) == 0xFFFFFFFFu;   // that rank's list buffer overflowed
+				}
+				uint32_t incl = cnt;
+				#pragma unroll
+				for (int d = 1; d < kMaxRanks; d <<= 1)
+				{
+					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+					if (tid >= d) incl += t;
+				}
+				if (__any_sync(0xFFFFFFFFu, bad))
+				{
+					incl = 0;                                  // void frame: the host reports the undersized list capacity
+					if (tid == 0) A.frameInfo[1] = 1ull;
+				}
+				if (tid < kMaxRanks) { sSegEnd[tid] = incl; sSegOff[tid] = off; }
+			}
+			__syncthreads();
+			n = sSegEnd[fp.ownerCount - 1];
+		}
 		else
 		{
-			// Sweep 2 (more large triangles than sBig holds): chunk by chunk, large triangles only - the small ones
-			// are done.  Two barriers per chunk: the counter of the NEXT chunk is reset while the current one is being
-			// filled, and the trailing barrier protects sBig from the next chunk.
-			__syncthreads();                               // everybody has read the total
-			if (tid < 2) sNumBig[tid] = 0;
-			__syncthreads();
-			for (uint32_t base = 0, it = 0; base < n; base += kListChunk, ++it)
+			n = (cls == kTileClasses - 1u) ? 0u : __ldg(A.tileCount + bin);
+			list = A.binIds + __ldg(A.tileOffset + bin);
+		}
+
+		// global slot of entry e of the (concatenated) list
+		auto listSlot = [&](uint32_t e) -> uint32_t*
+		{
+			if (fp.shardGeometry)
 			{
-				if (tid == 0) sNumBig[(it + 1u) & 1u] = 0;
-				if (base + (uint32_t)tid < n)
+				uint32_t seg = 0;
+				while (e >= sSegEnd[seg]) ++seg;
+				return const_cast<uint32_t*>(A.shard.binIds[seg]) + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u));
+			}
+			return const_cast<uint32_t*>(list) + e;
+		};
+		// One list entry -> screen-space triangle + its candidate box inside this CTA's block.  Returns the number of
+		// candidate pixels (0: nothing to do).
+		auto expandEntry = [&](uint32_t prim, const uint4& tr, TriShared& t, int& x0, int& x1, int& y0, int& y1) -> int
+		{
+			// rebuild the screen-space triangle from the static reference + the transformed positions
+			// (same code, hence the same bits, wherever a triangle is expanded)
+			float4 p0, p1, p2;
+			fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
+			TriRecord r;
+			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
+			// candidate pixels = the record's conservative box clipped to this CTA's block; the box
+			// contains every pixel whose edge functions can all be >= 0, so this equals the
+			// reference's test of every pixel of the bin (CUDARenderer.cu:1116-1127)
+			x0 = max((int)(r.cbX & 0xFFFFu), ox); x1 = min((int)(r.cbX >> 16), ex);
+			y0 = max((int)(r.cbY & 0xFFFFu), oy); y1 = min((int)(r.cbY >> 16), ey);
+			const int area = (x1 > x0 && y1 > y0) ? (x1 - x0) * (y1 - y0) : 0;
+			if (area > 0) expandRecord(r, prim, t);
+			return area;
+		};
+		// pixel-parallel path: every thread tests its own pixel against the large triangles staged in sBig
+		auto pixelParallel = [&](uint32_t nBig)
+		{
+			for (uint32_t j = 0; j < nBig; ++j)
+			{
+				TriShared t = sBig[j];
+				const int ty0 = (int)(t.yExtent & 0xFFFFu), ty1 = (int)(t.yExtent >> 16);
+				if (ty1 <= warpY0 || ty0 >= warpY1) continue;          // warp-uniform
+				if (!COUNT && t.zLow > bestZ) continue;                // cannot win this pixel (per lane)
+				Bary bc; int zi;
+				if (live && fragmentTest<TOPLEFT>(t, fx, fy, bc, zi))
+				{
+					if (COUNT) ++nFrags;
+					if (zi < bestZ || (zi == bestZ && t.prim < bestPrim)) { bestZ = zi; bestPrim = t.prim; }
+				}
+			}
+		};
+
+		unsigned long long best = kEmptyKey;
+		if (n)
+		{
+			sKey[tid] = kEmptyKey;
+			if (tid < 2) sNumBig[tid] = 0;
+			// lists of up to kStage entries are staged in shared memory: sorted here (canonical ascending order in
+			// global memory - the sweep itself does not depend on the order) and then swept from there
+			const bool staged = n <= (uint32_t)kStage;
+			if (staged)
+			{
+				for (uint32_t e = tid; e < n; e += kListChunk)
+				{
+					const uint32_t prim = *listSlot(e);
+					sIds[e] = prim;
+					if (e < 2u * kListChunk) prefetchL2(A.triRefs + prim);      // the vertex references of the first entries arrive while the list is sorted
+				}
+			}
+			__syncthreads();                  // sKey / counters initialised, list staged
+			if (staged && fp.sortLists && n > 1u)
+			{
+				const int how = ctaSortTileList(sIds, n, sSort, [&](uint32_t pos, uint32_t key) { *listSlot(pos) = key; });
+				if (how == 2 && tid == 0) atomicAdd(&A.frameInfo[6], 1ull);
+				__syncthreads();              // the scratch becomes the big-triangle buffer
+			}
+			auto idAt = [&](uint32_t e) -> uint32_t { return staged ? sIds[e] : *listSlot(e); };
+
+			// Sweep 1, no barriers: every thread walks its entries of all chunks of the list.  Small triangles are resolved
+			// right away (triangle-parallel, atomicMin into sKey); large ones are only collected in sBig - up to kListChunk of
+			// them for the WHOLE list - and rasterised pixel-parallel after the sweep.  The warps of the CTA therefore drift
+			// apart over a long list instead of meeting at two barriers per chunk, and their memory round trips
+			// (vertex reference -> positions) overlap each other's arithmetic.  A thread loads the vertex reference of its
+			// next entry before it works on the current one and pulls that entry's positions into L2 afterwards.
+#if B2R_RASTER_LOOKAHEAD
+			uint32_t primNext = 0;
+			uint4 trNext = make_uint4(0, 0, 0, 0);
+			bool haveNext = (uint32_t)tid < n;
+			if (haveNext) { primNext = idAt(tid); trNext = __ldg(A.triRefs + primNext); }
+#endif
+			for (uint32_t base = 0; base < n; base += kListChunk)
+			{
+#if B2R_RASTER_LOOKAHEAD
+				const bool have = haveNext;
+				const uint32_t prim = primNext;
+				const uint4 tr = trNext;
+				haveNext = base + kListChunk + (uint32_t)tid < n;
+				if (haveNext) { primNext = idAt(base + kListChunk + tid); trNext = __ldg(A.triRefs + primNext); }
+#else
+				const bool have = base + (uint32_t)tid < n;
+				const bool haveNext = base + kListChunk + (uint32_t)tid < n;
+				uint32_t prim = 0;
+				uint4 tr = make_uint4(0, 0, 0, 0);
+				if (have) { prim = idAt(base + tid); tr = __ldg(A.triRefs + prim); }
+#endif
+				if (have)
 				{
 					TriShared t;
 					int x0, x1, y0, y1;
-					if (expandEntry(listEntry(base + tid), t, x0, x1, y0, y1) > kSmallArea)
+					const int area = expandEntry(prim, tr, t, x0, x1, y0, y1);
+					if (area > kSmallArea)
 					{
-						TriShared& dst = sBig[atomicAdd(&sNumBig[it & 1u], 1u)];
-						dst = t;
-						dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
+						const uint32_t slotBig = atomicAdd(&sNumBig[0], 1u);
+						if (slotBig < (uint32_t)kListChunk)
+						{
+							TriShared& dst = sBig[slotBig];
+							dst = t;
+							dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);      // bbox rows for the warp-level reject
+						}
+					}
+					else if (area > 0)
+					{
+						// triangle-parallel: this thread walks the few candidate pixels
+						for (int y = y0; y < y1; ++y)
+							for (int x = x0; x < x1; ++x)
+							{
+								Bary bc; int zi;
+								if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+								{
+									const unsigned long long key = ((unsigned long long)(uint32_t)zi << 32) | prim;
+									atomicMin(&sKey[(x - ox) + (y - oy) * kTile], key);
+									if (COUNT) ++nFrags;
+								}
+							}
 					}
 				}
-				__syncthreads();
-				pixelParallel(sNumBig[it & 1u]);
-				if (base + kListChunk < n) __syncthreads();
+#if B2R_RASTER_LOOKAHEAD
+				if (haveNext && !OTF) { prefetchL2(A.pos4 + trNext.x); prefetchL2(A.pos4 + trNext.y); prefetchL2(A.pos4 + trNext.z); }
+#else
+				if (haveNext && staged) prefetchL2(A.triRefs + sIds[base + kListChunk + tid]);
+#endif
 			}
+			__syncthreads();
+			const uint32_t nBigTotal = sNumBig[0];
+			if (nBigTotal <= (uint32_t)kListChunk)
+				pixelParallel(nBigTotal);
+			else
+			{
+				// Sweep 2 (more large triangles than sBig holds): chunk by chunk, large triangles only - the small ones
+				// are done.  Two barriers per chunk: the counter of the NEXT chunk is reset while the current one is being
+				// filled, and the trailing barrier protects sBig from the next chunk.
+				__syncthreads();                               // everybody has read the total
+				if (tid < 2) sNumBig[tid] = 0;
+				__syncthreads();
+				for (uint32_t base = 0, it = 0; base < n; base += kListChunk, ++it)
+				{
+					if (tid == 0) sNumBig[(it + 1u) & 1u] = 0;
+					if (base + (uint32_t)tid < n)
+					{
+						TriShared t;
+						int x0, x1, y0, y1;
+						const uint32_t prim = idAt(base + tid);
+						if (expandEntry(prim, __ldg(A.triRefs + prim), t, x0, x1, y0, y1) > kSmallArea)
+						{
+							TriShared& dst = sBig[atomicAdd(&sNumBig[it & 1u], 1u)];
+							dst = t;
+							dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
+						}
+					}
+					__syncthreads();
+					pixelParallel(sNumBig[it & 1u]);
+					if (base + kListChunk < n) __syncthreads();
+				}
+			}
+			best = (bestPrim == kNoPrim) ? kEmptyKey : (((unsigned long long)(uint32_t)bestZ << 32) | bestPrim);
+			best = min(best, sKey[tid]);
+			if (COUNT)
+			{
+				unsigned int v = nFrags;
+				for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+				if ((tid & 31) == 0 && v) atomicAdd(&A.frameInfo[4], (unsigned long long)v);
+			}
+			// (no barrier here: the shared-memory state of this block is not touched again before the barrier of the
+			// next work-item fetch, which every thread passes before the next block initialises it)
 		}
-	}
-	unsigned long long best = (bestPrim == kNoPrim) ? kEmptyKey : (((unsigned long long)(uint32_t)bestZ << 32) | bestPrim);
-	best = min(best, sKey[tid]);
-	if (COUNT)
-	{
-		unsigned int v = nFrags;
-		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-		if ((tid & 31) == 0 && v) atomicAdd(&A.frameInfo[4], (unsigned long long)v);
-	}
-	if (!live) return;
+		if (!live) continue;
 
-	// ---- deferred shade of the winner (PS_Kernel, CUDARenderer.cu:833-897) + ROP write-back
-	const size_t pix = (size_t)px + (size_t)py * fp.width;
-	uint32_t colour;
-	int depthOut = 0x7FFFFFFF;
-	float zOut = 0.f;
-	uint32_t prim = kNoPrim;
-	if (best == kEmptyKey)
-	{
-		// untouched fragment: zero-cleared PixelShade whose colour32 is the clear colour
-		if (fp.visState == 0u) colour = packColour(fp.clearRGB[0], fp.clearRGB[1], fp.clearRGB[2]);
-		else colour = 0u;   // Depth: (0-.985)/.015*255 < 0 -> 0 ; Normal: n = 0
-	}
-	else
-	{
-		prim = (uint32_t)best;
-		depthOut = (int)(uint32_t)(best >> 32);
-		const uint4 tr = __ldg(A.triRefs + prim);
-		float4 p0, p1, p2;
-		fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
-		TriShared t;
+		// ---- deferred shade of the winner (PS_Kernel, CUDARenderer.cu:833-897) + ROP write-back
+		const size_t pix = (size_t)px + (size_t)py * fp.width;
+		uint32_t colour;
+		int depthOut = 0x7FFFFFFF;
+		float zOut = 0.f;
+		uint32_t prim = kNoPrim;
+		if (best == kEmptyKey)
 		{
-			TriRecord r;
-			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
-			expandRecord(r, prim, t);
-		}
-		Bary bc; int zi;
-		fragmentTest<false>(t, fx, fy, bc, zi);      // same arithmetic as the coverage pass
-		zOut = bc.z;
-		const MeshConst& mc = A.meshes[tr.w];
-		if (fp.visState == 1u)
-		{
-			const float r = __fdiv_rn(bc.z - 0.985f, 1.f - 0.985f);   // Remap, MathUtilities.h:175-178
-			colour = (__float2uint_rz(r * 255.f) & 0xFFu) << 16;
+			// untouched fragment: zero-cleared PixelShade whose colour32 is the clear colour
+			if (fp.visState == 0u) colour = packColour(fp.clearRGB[0], fp.clearRGB[1], fp.clearRGB[2]);
+			else colour = 0u;   // Depth: (0-.985)/.015*255 < 0 -> 0 ; Normal: n = 0
 		}
 		else
 		{
-			Interp S;
-			S.b0 = bc.b0; S.b1 = bc.b1; S.b2 = bc.b2;
-			S.iw0 = __frcp_rn(p0.w); S.iw1 = __frcp_rn(p1.w); S.iw2 = __frcp_rn(p2.w);
-			const uint32_t inDelta = mc.vtxInBase - mc.vtxOutBase;     // transformed-stream index -> IVertex record (mod 2^32)
-			const float2* r0 = A.ivertex + (size_t)(tr.x + inDelta) * 7;
-			const float2* r1 = A.ivertex + (size_t)(tr.y + inDelta) * 7;
-			const float2* r2 = A.ivertex + (size_t)(tr.z + inDelta) * 7;
-			const bool textured = TEXTURED && (fp.visState == 0u) && mc.tex[0] >= 0;
-			if (!TEXTURED || (fp.visState == 0u && !textured))
+			prim = (uint32_t)best;
+			depthOut = (int)(uint32_t)(best >> 32);
+			const uint4 tr = __ldg(A.triRefs + prim);
+			float4 p0, p1, p2;
+			fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
+			TriShared t;
 			{
-				// vertex colour (IVertex floats 11..13, copied unchanged by GetNDCVertex), NOT multiplied
-				// by wInterpolated (CUDAROPs.cu:379)
-				const float2 a0 = __ldg(r0 + 5), b0 = __ldg(r0 + 6), a1 = __ldg(r1 + 5), b1 = __ldg(r1 + 6), a2 = __ldg(r2 + 5), b2 = __ldg(r2 + 6);
-				colour = packColour(S(a0.y, a1.y, a2.y), S(b0.x, b1.x, b2.x), S(b0.y, b1.y, b2.y));
+				TriRecord r;
+				rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
+				expandRecord(r, prim, t);
 			}
-			else if (fp.visState == 0u && mc.tex[1] < 0)
+			Bary bc; int zi;
+			fragmentTest<false>(t, fx, fy, bc, zi);      // same arithmetic as the coverage pass
+			zOut = bc.z;
+			const MeshConst& mc = A.meshes[tr.w];
+			if (fp.visState == 1u)
 			{
-				// diffuse map only: ShadePixelSafe returns the diffuse sample (CUDAROPs.cu:465-468); only uv is needed
-				const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
-				const float2 a0 = __ldg(r0 + 1), b0 = __ldg(r0 + 2), a1 = __ldg(r1 + 1), b1 = __ldg(r1 + 2), a2 = __ldg(r2 + 1), b2 = __ldg(r2 + 2);
-				const float u = S(a0.y, a1.y, a2.y) * wInterp, vv = S(b0.x, b1.x, b2.x) * wInterp;
-				const RGB c = sampleTex(A.textures[mc.tex[0]], u, vv, fp.sampleState);
-				colour = packColour(c.r, c.g, c.b);
+				const float r = __fdiv_rn(bc.z - 0.985f, 1.f - 0.985f);   // Remap, MathUtilities.h:175-178
+				colour = (__float2uint_rz(r * 255.f) & 0xFFu) << 16;
 			}
 			else
 			{
-				// transform the three vertices' attributes now (the reference did it for every vertex in VS_Kernel)
-				float v[14];
-				VertexAttrs t0, t1, t2;
-				#pragma unroll
-				for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r0 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
-				transformAttributes(v, mc, fp.camPos, t0);
-				#pragma unroll
-				for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r1 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
-				transformAttributes(v, mc, fp.camPos, t1);
-				#pragma unroll
-				for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r2 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
-				transformAttributes(v, mc, fp.camPos, t2);
-				const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
-				const float nx = S(t0.n[0], t1.n[0], t2.n[0]) * wInterp, ny = S(t0.n[1], t1.n[1], t2.n[1]) * wInterp, nz = S(t0.n[2], t1.n[2], t2.n[2]) * wInterp;
-				if (fp.visState == 2u)
-					colour = packColour(nx, ny, nz);
+				Interp S;
+				S.b0 = bc.b0; S.b1 = bc.b1; S.b2 = bc.b2;
+				S.iw0 = __frcp_rn(p0.w); S.iw1 = __frcp_rn(p1.w); S.iw2 = __frcp_rn(p2.w);
+				const uint32_t inDelta = mc.vtxInBase - mc.vtxOutBase;     // transformed-stream index -> IVertex record (mod 2^32)
+				const float2* r0 = A.ivertex + (size_t)(tr.x + inDelta) * 7;
+				const float2* r1 = A.ivertex + (size_t)(tr.y + inDelta) * 7;
+				const float2* r2 = A.ivertex + (size_t)(tr.z + inDelta) * 7;
+				const bool textured = TEXTURED && (fp.visState == 0u) && mc.tex[0] >= 0;
+				if (!TEXTURED || (fp.visState == 0u && !textured))
+				{
+					// vertex colour (IVertex floats 11..13, copied unchanged by GetNDCVertex), NOT multiplied
+					// by wInterpolated (CUDAROPs.cu:379)
+					const float2 a0 = __ldg(r0 + 5), b0 = __ldg(r0 + 6), a1 = __ldg(r1 + 5), b1 = __ldg(r1 + 6), a2 = __ldg(r2 + 5), b2 = __ldg(r2 + 6);
+					colour = packColour(S(a0.y, a1.y, a2.y), S(b0.x, b1.x, b2.x), S(b0.y, b1.y, b2.y));
+				}
+				else if (fp.visState == 0u && mc.tex[1] < 0)
+				{
+					// diffuse map only: ShadePixelSafe returns the diffuse sample (CUDAROPs.cu:465-468); only uv is needed
+					const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
+					const float2 a0 = __ldg(r0 + 1), b0 = __ldg(r0 + 2), a1 = __ldg(r1 + 1), b1 = __ldg(r1 + 2), a2 = __ldg(r2 + 1), b2 = __ldg(r2 + 2);
+					const float u = S(a0.y, a1.y, a2.y) * wInterp, vv = S(b0.x, b1.x, b2.x) * wInterp;
+					const RGB c = sampleTex(A.textures[mc.tex[0]], u, vv, fp.sampleState);
+					colour = packColour(c.r, c.g, c.b);
+				}
 				else
 				{
-					const float u = S(t0.uv[0], t1.uv[0], t2.uv[0]) * wInterp, vv = S(t0.uv[1], t1.uv[1], t2.uv[1]) * wInterp;
-					const float tx = S(t0.tan[0], t1.tan[0], t2.tan[0]), ty = S(t0.tan[1], t1.tan[1], t2.tan[1]), tz = S(t0.tan[2], t1.tan[2], t2.tan[2]);   // no wInterp (CUDAROPs.cu:372)
-					float vx = S(t0.vd[0], t1.vd[0], t2.vd[0]), vy = S(t0.vd[1], t1.vd[1], t2.vd[1]), vz = S(t0.vd[2], t1.vd[2], t2.vd[2]);
-					normalize3(vx, vy, vz);
-					const RGB c = shadePixel(A, mc, fp.sampleState, u, vv, nx, ny, nz, tx, ty, tz, vx, vy, vz);
-					colour = packColour(c.r, c.g, c.b);
+					// transform the three vertices' attributes now (the reference did it for every vertex in VS_Kernel)
+					float v[14];
+					VertexAttrs t0, t1, t2;
+					#pragma unroll
+					for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r0 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+					transformAttributes(v, mc, fp.camPos, t0);
+					#pragma unroll
+					for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r1 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+					transformAttributes(v, mc, fp.camPos, t1);
+					#pragma unroll
+					for (int k = 0; k < 7; ++k) { const float2 q = __ldg(r2 + k); v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+					transformAttributes(v, mc, fp.camPos, t2);
+					const float wInterp = __frcp_rn(sum3(S.iw0, bc.b0, S.iw1, bc.b1, S.iw2, bc.b2));
+					const float nx = S(t0.n[0], t1.n[0], t2.n[0]) * wInterp, ny = S(t0.n[1], t1.n[1], t2.n[1]) * wInterp, nz = S(t0.n[2], t1.n[2], t2.n[2]) * wInterp;
+					if (fp.visState == 2u)
+						colour = packColour(nx, ny, nz);
+					else
+					{
+						const float u = S(t0.uv[0], t1.uv[0], t2.uv[0]) * wInterp, vv = S(t0.uv[1], t1.uv[1], t2.uv[1]) * wInterp;
+						const float tx = S(t0.tan[0], t1.tan[0], t2.tan[0]), ty = S(t0.tan[1], t1.tan[1], t2.tan[1]), tz = S(t0.tan[2], t1.tan[2], t2.tan[2]);   // no wInterp (CUDAROPs.cu:372)
+						float vx = S(t0.vd[0], t1.vd[0], t2.vd[0]), vy = S(t0.vd[1], t1.vd[1], t2.vd[1]), vz = S(t0.vd[2], t1.vd[2], t2.vd[2]);
+						normalize3(vx, vy, vz);
+						const RGB c = shadePixel(A, mc, fp.sampleState, u, vv, nx, ny, nz, tx, ty, tz, vx, vy, vz);
+						colour = packColour(c.r, c.g, c.b);
+					}
 				}
 			}
 		}
+		// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
+		// gathered with one contiguous NCCL transfer / written straight into a peer's memory
+		if (fp.packedOutput) A.framebuffer[((size_t)((bin - fp.ownerRank) / fp.ownerCount) * subs + sub) * (kTile * kTile) + tid] = colour;
+		else A.framebuffer[pix] = colour;
+		A.depth[pix] = depthOut;
+		if (fp.debugSurfaces)
+		{
+			A.zSurface[pix] = zOut;
+			A.winnerSurface[pix] = prim;
+		}
 	}
-	// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
-	// gathered with one contiguous NCCL transfer / written straight into a peer's memory
-	if (fp.packedOutput) A.framebuffer[((size_t)ownedIdx * gridDim.y + blockIdx.y) * (kTile * kTile) + tid] = colour;
-	else A.framebuffer[pix] = colour;
-	A.depth[pix] = depthOut;
-	if (fp.debugSurfaces)
-	{
-		A.zSurface[pix] = zOut;
-		A.winnerSurface[pix] = prim;
 	}
 }
 

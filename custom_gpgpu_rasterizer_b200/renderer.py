@@ -136,6 +136,12 @@ class Renderer:
         self.n_meshes += 1
         return out.value
 
+    def set_world(self, mesh: int, world: np.ndarray):
+        """Per-frame world matrix of a loaded mesh (SceneGraph::Update, SceneGraph.cpp:30-39): takes effect with the next
+        render(); frames already enqueued keep the matrices they were enqueued with."""
+        w = np.ascontiguousarray(world, np.float32).reshape(16)
+        self._check(lib.b2r_mesh_set_world(self._ctx, mesh, _fptr(w)))
+
     def clear_meshes(self):
         self._check(lib.b2r_mesh_clear_all(self._ctx))
         self.n_meshes = 0

@@ -115,7 +115,7 @@ class _FakeRenderer:
         pass
 
     def counters(self):
-        return {"pairs": 7_117_055, "kernels_launched": 12, "tiles_owned": 32400, "num_bins": 32400, "unsorted_tiles": 0, "big_triangles": 0,
+        return {"pairs": 7_117_055, "kernels_launched": 10, "tiles_owned": 32400, "num_bins": 32400, "unsorted_tiles": 0, "big_triangles": 0,
                 "fragments": 3_089_508, "sort_fallback_tiles": 0}
 
     def stats(self):
@@ -128,6 +128,7 @@ class _FakeRenderer:
 
     def present_async(self, out):
         assert out.shape == (self.h, self.w) and out.dtype == np.uint32
+        out[:] = self.framebuffer()
 
     def present_wait(self):
         pass
@@ -219,7 +220,8 @@ def test_gpu_arm_dry_run_single_rank(monkeypatch, capsys):
     d = _dry_run(monkeypatch, capsys, ["--steps", "20", "--warmup", "5"])
     assert CONTRACT_KEYS <= set(d) and "cpu_baseline" in d and "fill_test" in d
     assert d["n_gpus"] == 1 and d["config"]["triangles"] == 10_000_000 and "config 3" in d["config"]["workload"]
-    assert abs(d["value"] - 20 / 9.4e-3) < 1e-6 and d["gpu_launches"] == 12 * 20
+    assert abs(d["value"] - 20 / 9.4e-3) < 1e-6 and d["gpu_launches"] == 10 * 20
+    assert d["checksum"]["match"] is True and d["checksum"]["framebuffer_crc32"] == d["checksum"]["host_framebuffer_crc32"]
     r = d["roofline"]
     assert r["kernel"] == "raster_shade" and r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"]
     assert d["e2e"]["d2h_bytes_per_step"] == 3840 * 2160 * 4 and d["e2e"]["value"] > 0
@@ -230,7 +232,8 @@ def test_gpu_arm_dry_run_single_rank(monkeypatch, capsys):
 def test_gpu_arm_dry_run_eight_ranks(monkeypatch, capsys):
     d = _dry_run(monkeypatch, capsys, ["--gpus", "8", "--steps", "10", "--warmup", "3", "--no-cpu-baseline"], world=8)
     assert CONTRACT_KEYS <= set(d) and d["n_gpus"] == 8 and "view_parallel" in d and len(d["stages_ms_per_rank"]) == 8
-    assert "sharded front end" in d["config"]["parallelism"]
+    assert "sharded front end" in d["parallelism"] and "parallelism" not in d["config"]
+    assert d["checksum"]["match"] is True
     r = d["roofline"]
     assert abs(r["peak"] / 8 - _bench_module().load_peaks()[0]) < 1e-6 and r["traffic"] is None      # N GPUs' bandwidth; ncu traffic is a 1-GPU capture
 
@@ -240,7 +243,7 @@ def test_views_workload_dry_run(monkeypatch, capsys, mode, world):
     d = _dry_run(monkeypatch, capsys, ["--workload", "views172", "--gpus", str(world), "--steps", "8", "--views-mode", mode], world=world)
     assert d["unit"] == "views/s" and d["config"]["triangles"] == 172 * 11638
     assert abs(d["value"] - (1 if mode == "sortfirst" else world) * 8 / 9.4e-3) < 1e-6
-    assert ("sort-first" in d["config"]["parallelism"]) == (mode == "sortfirst")
+    assert ("sort-first" in d["parallelism"]) == (mode == "sortfirst")
 
 
 def test_vehicle_workload_dry_run(monkeypatch, capsys):

@@ -289,3 +289,53 @@ def test_pipelined_front_end_matches_serial_frames():
         for k in (5, 2, 9):
             r.render(cams[k], sc.cull, sc.sample, sc.vis)
             assert np.array_equal(r.framebuffer(), want[k]) and np.array_equal(r.bin_lists()[2], want_ids[k])
+
+
+def test_moving_meshes_set_world_frames_in_flight():
+    """b2r_mesh_set_world (SURVEY section 8 f4: SceneGraph::Update / the per-mesh WVP upload of CUDARenderer.cu:241-246): three
+    meshes move every frame while the camera moves too; eight frames are enqueued back to back (a frame keeps the matrices
+    it was enqueued with) and each presented frame must be the oracle's frame of that instant - colour bit for bit (vertex
+    colours: no libm on the way), and winners, integer depth and the ascending tile lists of the last one."""
+    import copy
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer, host_camera, host_mesh_world
+    sc = scenes.random_triangles_scene(640, 480, 450, seed=91, cull=0, n_meshes=3)
+    n_frames = 8
+
+    def positions(k):
+        return [(0.35 * k - 1.0, 0.0, 0.1 * k), (0.0, 0.25 * k - 0.8, 0.0), (-0.2 * k, 0.1 * k, -0.15 * k)]
+
+    def camera(k):
+        return (0.1 * k, 1.0 - 0.05 * k, 5.0 + 0.2 * k)
+
+    want = []
+    for k in range(n_frames):
+        s2 = copy.copy(sc)
+        s2.meshes = [copy.copy(m) for m in sc.meshes]
+        for m, p in zip(s2.meshes, positions(k)):
+            m.position = p
+        s2.cam_pos = camera(k)
+        want.append(oracle_lib.render(s2, fill_rule=1))
+    assert not np.array_equal(want[0]["framebuffer"], want[1]["framebuffer"])
+    for ring in (0, 3):
+        with Renderer(sc.width, sc.height) as r:
+            r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+            if ring:
+                r.set_option(_lib.OPT_FRAME_RING, ring)
+            r.load_scene(sc)
+            bufs = [np.zeros((sc.height, sc.width), np.uint32) for _ in range(n_frames)]
+            for k in range(n_frames):
+                for mesh, p in enumerate(positions(k)):
+                    r.set_world(mesh, host_mesh_world(p))
+                cam = host_camera(camera(k), sc.fov_deg, sc.width, sc.height, sc.near, sc.far)
+                r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+                r.present_async(bufs[k])
+            r.present_wait()
+            for k in range(n_frames):
+                assert np.array_equal(bufs[k], want[k]["framebuffer"]), f"frame ring {ring}: frame {k} is not the oracle's frame of that instant"
+            o = want[-1]
+            assert np.array_equal(r.depth(), o["depth"]) and np.array_equal(r.winner(), o["winner"])
+            counts, _, ids = r.bin_lists()
+            assert np.array_equal(counts, o["bin_counts"]) and np.array_equal(ids, o["bin_ids"])
+            total, visible = r.stats()
+            assert visible == o["visible_tris"]

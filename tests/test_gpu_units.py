@@ -17,8 +17,9 @@ def test_hoisted_division_is_bit_exact():
 
 @pytest.mark.parametrize("res,grid,tess", [((640, 360), (3, 2), (101, 150)), ((320, 180), (1, 1), (201, 300)), ((1920, 1080), (6, 4), (61, 90))])
 def test_list_sort_tiers_give_canonical_lists(res, grid, tess):
-    """Every sorter tier (warp run ordering, warp radix, CTA run ordering / radix, long radix) must turn the
-    scatter-order lists into ascending primitive ids without changing their content."""
+    """Every sorter tier (the raster kernel's in-CTA run ordering / bitonic fallback for lists of up to 2048 entries, the long
+    radix sort before it, and the stand-alone CTA sort b2r_read_bins uses after frames rendered without the in-frame sort)
+    must turn the scatter-order lists into ascending primitive ids without changing their content."""
     import numpy as np
     from custom_gpgpu_rasterizer_b200 import _lib, scenes
     from custom_gpgpu_rasterizer_b200.renderer import Renderer
@@ -35,16 +36,16 @@ def test_list_sort_tiers_give_canonical_lists(res, grid, tess):
     unsorted_tiles = r.counters()["unsorted_tiles"]
     assert np.array_equal(c0, c1) and np.array_equal(o0, o1)
     assert np.array_equal(r.framebuffer(), fb0), "the image must not depend on the list order"
-    tiers = {"warp": 0, "mid": 0, "long": 0, "beyond": 0}
+    tiers = {"cta": 0, "long": 0, "beyond": 0}
     for t in np.flatnonzero(c1):
         seg = i1[o1[t]: o1[t] + c1[t]]
         n = int(c1[t])
-        tiers["warp" if n <= 1024 else "mid" if n <= 4096 else "long" if n <= 40960 else "beyond"] += 1
+        tiers["cta" if n <= 2048 else "long" if n <= 40960 else "beyond"] += 1
         if n <= 40960:
             assert np.all(seg[1:] > seg[:-1]), f"tile {t} ({n} entries) is not in ascending primitive order"
             # B2R_OPT_SORT_BINS = 0 leaves the frame's lists in scatter order, but whoever reads them gets the canonical order
             assert np.array_equal(i0[o0[t]: o0[t] + c0[t]], seg), f"tile {t}: lists read back without the in-frame sort are not canonical"
         assert np.array_equal(np.sort(seg), np.sort(i0[o0[t]: o0[t] + c0[t]])), f"tile {t}: content changed by the sort"
     assert unsorted_tiles == tiers["beyond"]
-    assert tiers["mid"] + tiers["long"] > 0, f"scene does not exercise the CTA-level sorters: {tiers}"
+    assert tiers["cta"] > 0 and tiers["long"] > 0, f"scene does not exercise both sorters: {tiers}"
     r.close()

@@ -35,7 +35,7 @@ run ring4_sliced B2R_FRAME_RING=4 B2R_SHARD_SLICED_VERTEX=1
 # programmatic dependent launch parks the next kernel's CTAs on SM slots while the current kernel's tail drains: good for one
 # stream, possibly bad when other ring streams have runnable work; more hardware queues avoid false dependencies between streams
 run ring3_sliced_nopdl B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 B2R_PDL=0
-run ring3_sliced_conn32 B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 CUDA_DEVICE_MAX_CONNECTIONS=32
+#run ring3_sliced_conn32 B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 CUDA_DEVICE_MAX_CONNECTIONS=32
 # BASELINE config 5 at N ranks: view-parallel (no communication) and sort-first per view (sharded front end, moving camera)
 for m in parallel sortfirst; do
 	port=$((port + 1))

@@ -46,10 +46,10 @@ import sys
 from collections import defaultdict
 
 K_MAX_RANKS = 8
-RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "r"), ("triRefs", "r"), ("pos4", "r"), ("posIn", "r"), ("ivertex", "r"),
+RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("posIn", "r"), ("ivertex", "r"),
                ("meshes", "r"), ("textures", "r"), ("frameInfo", "w"), ("framebuffer", "w"), ("depth", "w"), ("zSurface", "w"), ("winnerSurface", "w")]
 RASTER_ARGS += [(f"shard.tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"shard.tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)] \
-    + [(f"shard.binIds[{i}]", "r") for i in range(K_MAX_RANKS)]
+    + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r")]      # the raster kernel sorts the lists it stages, in place
 STRUCTS = {
     "b2r::RasterArgs": RASTER_ARGS,
     "b2r::PeerFlags": [],                  # the flag words: concurrent by design, see above
@@ -180,16 +180,15 @@ class Trace:
         "vertex_transform_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3},
         "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5},
         "bin_big_count_kernel": {"bigList": 0, "counters": 1, "rects": 2, "tileCount": 3},
-        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "midTiles": 7, "longTiles": 8, "smallTiles": 9, "counters": 10, "frameInfo": 11},
+        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "counters": 10, "frameInfo": 11},
         "bin_scatter_kernel": {"rects": 0, "tileOffset": 3, "tileCursor": 4, "binIds": 5, "bigList": 6, "counters": 7, "frameInfo": 9},
-        "bin_sort_runs_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "smallTiles": 3, "midTiles": 4, "frameInfo": 5},
-        "bin_sort_mid_kernel": {"midTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
+        "bin_sort_tiles_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 4},
         "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
         "shard_push_heads_kernel": {"tileCount": 0, "tileOffset": 1},
         "shard_push_lists_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 7},
         "publish_info_kernel": {"frameInfo": 0},
     }
-    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "posIn": 5, "meshConst": 7, "frameInfo": 9}
+    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "posIn": 5, "meshConst": 7, "frameInfo": 9, "tileOrder": 14 + 3 * K_MAX_RANKS}
 
     def frames(self):
         """Per device: the launches of every frame, in the order the host issued them (b2r_render issues a whole frame; a
