@@ -125,7 +125,8 @@ struct b2r_context
 	struct BinSet
 	{
 		DeviceVec<uint2> rects;
-		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, tileOrder, bigList, binIds;
+		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, bigList, binIds;
+		DeviceVec<uint4> tileOrder;                   // the raster kernel's work order: one list of {tile, count, offset, 0} per length class
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[kMaxFrameRing];
@@ -142,6 +143,9 @@ struct b2r_context
 	int slicedVertex = 0;              // sharded front end: transform only the vertices of this rank's primitive slice;
 	                                   // the raster kernel transforms the vertices of its list entries itself (B2R_SHARD_SLICED_VERTEX)
 	int overlapFrontSharded = 1;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=0 switches it off)
+	int shardLocalColour = 0;          // B2R_OPT_SHARD_LOCAL_COLOUR: sharded front end, every rank keeps its tiles' colours in its own surface
+	// distributed Present: the caller's host frame (e.g. a shared-memory mapping), registered and mapped for this device
+	void* hostFrame = nullptr; uint32_t* hostFrameDev = nullptr; uint64_t hostFrameBytes = 0;
 	cudaEvent_t listsReady[2] = { nullptr, nullptr };   // sharded + pipelined: the "lists ready" barrier of a frame has completed
 	bool listsReadyPending[2] = { false, false };
 	bool lastPipelined = false;        // the newest enqueued frame ran its front end on the second stream
@@ -277,7 +281,7 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	CU(c, B.tileOffset.reserve(n + 4, c->stream));
 	CU(c, B.tileCursor.reserve(n, c->stream));
 	CU(c, B.longTiles.reserve(n, c->stream));
-	CU(c, B.tileOrder.reserve(n * kTileClasses, c->stream));      // the raster kernel's work order: one list per length class
+	CU(c, B.tileOrder.reserve(n * kTileClasses, c->stream));
 	CU(c, B.rects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, B.bigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	// list capacity heuristic; regrown on overflow (see validateFrame), and kept equal across the sets
@@ -374,7 +378,8 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.shardGeometry = c->shard.bound ? 1u : 0u;
 	const uint32_t subs = fp.subX * fp.subY;
 	fp.subsMagic = subs > 1 ? (uint32_t)(0x100000000ull / subs) : 0u;
-	fp.sortLists = c->sortBins ? 1u : 0u;
+	// with several 16x16 blocks per bin the CTAs of a bin share its list: it is sorted by a kernel of its own before the raster
+	fp.sortLists = (c->sortBins && subs == 1) ? 1u : 0u;
 	return fp;
 }
 
@@ -393,13 +398,12 @@ cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 g
 
 // the raster kernel instantiation of a frame: fill rule, fragment counter, light variant (the frame cannot reach the
 // texture / visualiser paths), positions transformed on the fly (sharded front end with a sliced vertex stage)
-// The kernel is persistent: `blocks` = the 16x16 pixel blocks of the frame (an upper bound of its work items), the grid is
-// what fits the GPU at the variant's occupancy.
+// `blocks` = the 16x16 pixel blocks of the frame, an upper bound of the kernel's work items (CTAs behind the last item leave at once)
 cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool onTheFly)
 {
 	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (onTheFly ? 8 : 0);
 	const dim3 block(kTile * kTile);
-	const dim3 grid(std::min<uint32_t>(blocks, (uint32_t)(c->numSMs * rasterCtasPerSM(textured, onTheFly))));
+	const dim3 grid(blocks);
 #define B2R_RASTER_CASE(v, tl, cnt, tex, otf) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, otf>, grid, block, 0, s, A, fp);
 	switch (variant)
 	{
@@ -672,8 +676,9 @@ int enqueueFrame(b2r_context* c)
 	STAGE_EVENT(c, slot, 4);
 	if (c->sortBins && c->nPrims)
 	{
-		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs, false); if (r) return r;
-		c->kernelsLaunched += 1;
+		const bool bigBins = c->binW > (uint32_t)kTile || c->binH > (uint32_t)kTile;
+		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs, bigBins); if (r) return r;
+		c->kernelsLaunched += bigBins ? 2 : 1;
 	}
 	if (sh.bound && c->nPrims)
 	{
@@ -694,7 +699,7 @@ int enqueueFrame(b2r_context* c)
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
-		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = sh.bound ? nullptr : B.tileOrder.ptr;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -716,7 +721,7 @@ int enqueueFrame(b2r_context* c)
 				T.binIds[p] = (p == sh.self) ? sh.binIds(sh.arena, set) : sh.region(sh.arena, set, p);
 				pf.flags[p] = reinterpret_cast<uint32_t*>(base);
 			}
-			A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
+			if (!c->shardLocalColour) A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
 			// "lists ready": nobody reads a peer's lists before that peer has sorted them.  (Rank 0 arrives only
 			// after the Present copy of this surface - the wait above - so no peer overwrites pixels in flight.)
 			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, s, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7, 1u));
@@ -725,6 +730,12 @@ int enqueueFrame(b2r_context* c)
 			c->listsReadyPending[g] = true;
 			STAGE_EVENT(c, slot, 8);
 			A.shard = T;
+			// the raster kernel's work order from the merged heads: this rank's tiles, longest lists first
+			if (owned)
+			{
+				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, s, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo));
+				++c->kernelsLaunched;
+			}
 			STAGE_EVENT(c, slot, 7);
 		}
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
@@ -751,7 +762,7 @@ int enqueueFrame(b2r_context* c)
 	// "colours landed": publish_info_kernel tells rank 0 that this rank's tiles of the frame are in rank 0's surface;
 	// rank 0 waits for the flags only when it reads or presents the frame (enqueueColourWait)
 	uint32_t* landedFlag = nullptr;
-	if (sh.bound)
+	if (sh.bound && !c->shardLocalColour)
 		landedFlag = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]) + 8 + sh.self;
 	STAGE_EVENT(c, slot, 6);
 	// frameInfo and counters[0..1] are adjacent on the device (one allocation): one copy
@@ -946,8 +957,9 @@ int enqueueFrameRing(b2r_context* c)
 	RING_STAGE_EVENT(4);
 	if (c->sortBins && c->nPrims)
 	{
-		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs, false); if (r) return r;
-		c->kernelsLaunched += 1;
+		const bool bigBins = c->binW > (uint32_t)kTile || c->binH > (uint32_t)kTile;
+		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs, bigBins); if (r) return r;
+		c->kernelsLaunched += bigBins ? 2 : 1;
 	}
 	if (sh.bound && c->nPrims)
 	{
@@ -961,7 +973,7 @@ int enqueueFrameRing(b2r_context* c)
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
-		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = sh.bound ? nullptr : B.tileOrder.ptr;
+		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		if (sh.bound) c->colourIdx = (int)(sh.frame & 1u);       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -981,12 +993,17 @@ int enqueueFrameRing(b2r_context* c)
 				T.tileCount[p] = sh.inboxCount(sh.arena, k, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, k, p);
 				T.binIds[p] = (p == sh.self) ? sh.binIds(sh.arena, k) : sh.region(sh.arena, k, p);
 			}
-			A.framebuffer = sh.colourBase + (size_t)(sh.frame & 1u) * c->width * c->height;
+			if (!c->shardLocalColour) A.framebuffer = sh.colourBase + (size_t)(sh.frame & 1u) * c->width * c->height;
 			// "lists ready": nobody reads the lists a peer pushed before that peer has sorted and pushed them
 			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, rs, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7, 0u));
 			++c->kernelsLaunched;
 			RING_STAGE_EVENT(8);
 			A.shard = T;
+			if (owned)
+			{
+				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo));
+				++c->kernelsLaunched;
+			}
 			RING_STAGE_EVENT(7);
 		}
 		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
@@ -1004,7 +1021,7 @@ int enqueueFrameRing(b2r_context* c)
 		}
 	}
 	uint32_t* landedFlag = nullptr;
-	if (sh.bound)
+	if (sh.bound && !c->shardLocalColour)
 		landedFlag = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]) + 8 + sh.self;
 	RING_STAGE_EVENT(6);
 #undef RING_STAGE_EVENT
@@ -1028,7 +1045,7 @@ int enqueueFrameRing(b2r_context* c)
 int enqueueColourWait(b2r_context* c)
 {
 	b2r_context::Shard& sh = c->shard;
-	if (!sh.bound || sh.self != 0 || sh.waitedFrame == sh.frame) return B2R_OK;
+	if (!sh.bound || sh.self != 0 || sh.waitedFrame == sh.frame || c->shardLocalColour) return B2R_OK;
 	PeerFlags pf{};
 	for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(p == sh.self ? sh.arena : sh.peerArena[p]);
 	CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, c->stream, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame, 0u, 1u, sh.hTimeout, 1u));
@@ -1231,6 +1248,7 @@ void b2r_destroy(b2r_context* c)
 	}
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
 	releaseShard(c);
+	if (c->hostFrame) cudaHostUnregister(c->hostFrame);
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->frameDone) cudaEventDestroy(c->frameDone);
 	for (auto& e : c->copyDone) if (e) cudaEventDestroy(e);
@@ -1380,6 +1398,15 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_VERTEX: c->overlapVertex = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_FRONT: c->overlapFront = value ? 1 : 0; break;
+	case B2R_OPT_SHARD_LOCAL_COLOUR:
+	{
+		// changes where the frames' colours go: only between frames
+		CU(c, cudaSetDevice(c->device));
+		int r = validateFrame(c); if (r) return r;
+		c->shardLocalColour = value ? 1 : 0;
+		if (c->shard.bound) c->shard.waitedFrame = c->shard.frame;
+		break;
+	}
 	case B2R_OPT_FRAME_RING:
 	case B2R_OPT_SHARD_SLICED_VERTEX:
 	{
@@ -1417,6 +1444,7 @@ int b2r_get_option(b2r_context* c, int option, int* value)
 	case B2R_OPT_OVERLAP_FRONT: *value = c->overlapFront; break;
 	case B2R_OPT_FRAME_RING: *value = c->ringDepth; break;
 	case B2R_OPT_SHARD_SLICED_VERTEX: *value = c->slicedVertex; break;
+	case B2R_OPT_SHARD_LOCAL_COLOUR: *value = c->shardLocalColour; break;
 	default: return fail(c, B2R_E_INVALID, "unknown option %d", option);
 	}
 	return B2R_OK;
@@ -1471,6 +1499,17 @@ int b2r_read_framebuffer(b2r_context* c, uint32_t* out)
 	if (!c) return B2R_E_INVALID;
 	return readSurface(c, c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->lastColourIdx], out, "read_framebuffer");
 }
+static int ensureCopyStream(b2r_context* c)
+{
+	if (!c->copyStream)
+	{
+		CU(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+		CU(c, cudaEventCreateWithFlags(&c->frameDone, cudaEventDisableTiming));
+		for (auto& e : c->copyDone) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	return B2R_OK;
+}
+
 int b2r_present_async(b2r_context* c, uint32_t* hostPixels)
 {
 	if (!c) return B2R_E_INVALID;
@@ -1479,17 +1518,62 @@ int b2r_present_async(b2r_context* c, uint32_t* hostPixels)
 	if (c->boundFramebuffer) return fail(c, B2R_E_STATE, "present_async: the colour surface is bound to caller memory");
 	CU(c, cudaSetDevice(c->device));
 	const size_t bytes = (size_t)c->width * c->height * 4;
-	if (!c->copyStream)
-	{
-		CU(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-		CU(c, cudaEventCreateWithFlags(&c->frameDone, cudaEventDisableTiming));
-		for (auto& e : c->copyDone) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	}
+	{ int r = ensureCopyStream(c); if (r) return r; }
 	const int idx = c->lastColourIdx;
 	{ int r = enqueueColourWait(c); if (r) return r; }
 	CU(c, cudaEventRecord(c->frameDone, c->stream));
 	CU(c, cudaStreamWaitEvent(c->copyStream, c->frameDone, 0));
 	CU(c, cudaMemcpyAsync(hostPixels, c->dColour[idx], bytes, cudaMemcpyDeviceToHost, c->copyStream));
+	CU(c, cudaEventRecord(c->copyDone[idx], c->copyStream));
+	c->copyPending[idx] = true;
+	if (!c->shard.bound) c->colourIdx = idx ^ 1;          // the next frame renders into the other surface (sharded: frame parity)
+	return B2R_OK;
+}
+
+int b2r_host_frame_register(b2r_context* c, void* host, uint64_t bytes)
+{
+	if (!c) return B2R_E_INVALID;
+	CU(c, cudaSetDevice(c->device));
+	if (c->copyStream) CU(c, cudaStreamSynchronize(c->copyStream));
+	int r = validateFrame(c); if (r) return r;
+	if (c->hostFrame)
+	{
+		CU(c, cudaHostUnregister(c->hostFrame));
+		c->hostFrame = nullptr; c->hostFrameDev = nullptr; c->hostFrameBytes = 0;
+	}
+	if (!host && !bytes) return B2R_OK;
+	if (!host || bytes < (uint64_t)c->width * c->height * 4) return fail(c, B2R_E_INVALID, "host frame: need at least width*height*4 bytes");
+	CU(c, cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+	void* dev = nullptr;
+	cudaError_t e = cudaHostGetDevicePointer(&dev, host, 0);
+	if (e != cudaSuccess) { cudaHostUnregister(host); return fail(c, B2R_E_CUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e)); }
+	c->hostFrame = host; c->hostFrameDev = (uint32_t*)dev; c->hostFrameBytes = bytes;
+	return B2R_OK;
+}
+
+int b2r_present_tiles_async(b2r_context* c, uint64_t byteOffset)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "present_tiles_async: nothing rendered yet");
+	if (!c->hostFrameDev) return fail(c, B2R_E_STATE, "present_tiles_async: no host frame registered (b2r_host_frame_register)");
+	if (c->boundFramebuffer || c->packedOutput) return fail(c, B2R_E_STATE, "present_tiles_async: needs the context's own row-major colour surface");
+	if (c->shard.bound && !c->shardLocalColour) return fail(c, B2R_E_STATE, "present_tiles_async: with the sharded front end set B2R_OPT_SHARD_LOCAL_COLOUR");
+	const uint64_t frameBytes = (uint64_t)c->width * c->height * 4;
+	if ((byteOffset & 15u) || byteOffset + frameBytes > c->hostFrameBytes) return fail(c, B2R_E_INVALID, "present_tiles_async: offset %llu outside the registered host frame", (unsigned long long)byteOffset);
+	CU(c, cudaSetDevice(c->device));
+	{ int r = ensureCopyStream(c); if (r) return r; }
+	const int idx = c->lastColourIdx;
+	const FrameParams fp = makeParams(c, c->last);
+	const uint32_t tiles = nBins(c);
+	const uint32_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - (uint32_t)c->ownerRank + (uint32_t)c->ownerCount - 1) / (uint32_t)c->ownerCount : 0;
+	CU(c, cudaEventRecord(c->frameDone, c->stream));
+	CU(c, cudaStreamWaitEvent(c->copyStream, c->frameDone, 0));
+	if (owned)
+	{
+		const uint32_t blocks = owned * fp.subX * fp.subY;
+		present_tiles_kernel<<<(blocks + 3) / 4, 256, 0, c->copyStream>>>(c->dColour[idx], c->hostFrameDev + byteOffset / 4, (uint32_t)c->ownerRank, (uint32_t)c->ownerCount, owned, fp);
+		CU(c, cudaGetLastError());
+	}
 	CU(c, cudaEventRecord(c->copyDone[idx], c->copyStream));
 	c->copyPending[idx] = true;
 	if (!c->shard.bound) c->colourIdx = idx ^ 1;          // the next frame renders into the other surface (sharded: frame parity)
@@ -1757,7 +1841,7 @@ int b2r_shard_release(b2r_context* c)
 	const bool was = c->shard.prepared;
 	releaseShard(c);
 	c->colourIdx = 0;
-	if (was) { c->ownerRank = 0; c->ownerCount = 1; }      // b2r_shard_prepare set them: later frames are whole frames again
+	if (was) { c->ownerRank = 0; c->ownerCount = 1; c->shardLocalColour = 0; }      // b2r_shard_prepare set them: later frames are whole frames again
 	return r;
 }
 

@@ -532,12 +532,13 @@ __device__ __forceinline__ uint32_t tileClass(uint32_t n)
 // its predecessors (they are all resident, so spinning is safe) and scans its slice locally.  Also clears
 // the cursors, publishes the pair total / overflow flag, builds the work list of the long-list sorter
 // (tiles whose list is too long for the raster kernel's in-CTA sort) and the raster kernel's work order
-// (tileOrder = kTileClasses lists of nTiles entries; null: not wanted).
+// (tileOrder = kTileClasses lists of nTiles {tile, count, offset, 0} entries; null: not wanted - the sharded front
+// end builds it from the merged heads of all ranks, shard_merge_heads_kernel).
 constexpr uint32_t kScanThreads = 256, kScanPerThread = 8, kScanPerCta = kScanThreads * kScanPerThread;
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
 	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold,
-	uint32_t* __restrict__ longTiles, uint32_t* __restrict__ tileOrder, uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
+	uint32_t* __restrict__ longTiles, uint4* __restrict__ tileOrder, uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
 	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[6]=lists sorted by the bitonic fallback,[8..13]=tiles per class*/)
 {
 	pdlPrologue();
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	}
 	__syncthreads();
 	unsigned long long run = sPrefix + (warp ? sWarp[warp - 1] : 0ull) + incl - sum;
+	uint32_t off[kScanPerThread];
 	#pragma unroll
 	for (uint32_t q = 0; q < kScanPerThread / 4; ++q)
 	{
@@ -627,6 +629,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 		o.y = (uint32_t)run; run += v[q * 4 + 1];
 		o.z = (uint32_t)run; run += v[q * 4 + 2];
 		o.w = (uint32_t)run; run += v[q * 4 + 3];
+		off[q * 4] = o.x; off[q * 4 + 1] = o.y; off[q * 4 + 2] = o.z; off[q * 4 + 3] = o.w;
 		if (i + 3 < nTiles)
 		{
 			*reinterpret_cast<uint4*>(tileOffset + i) = o;
@@ -673,10 +676,10 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 			uint32_t base = 0;
 			if (lane == 0) base = (uint32_t)atomicAdd(&frameInfo[kInfoClassBase + c], (unsigned long long)warpTotal);
 			base = __shfl_sync(0xFFFFFFFFu, base, 0) + inclS - mine;
-			uint32_t* dst = tileOrder + (size_t)c * nTiles;
+			uint4* dst = tileOrder + (size_t)c * nTiles;
 			#pragma unroll
 			for (uint32_t e = 0; e < kScanPerThread; ++e)
-				if (cls[e] == c) dst[base++] = first + e;
+				if (cls[e] == c) dst[base++] = make_uint4(first + e, v[e], off[e], 0u);      // the raster kernel's work item: tile, list length, list offset
 		}
 	}
 }
@@ -804,6 +807,122 @@ __device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* 
 	return sWarp[warp] + incl - v;
 }
 
+// Bitonic network over the n <= kStage keys staged in K (capacity kStage), padded to a power of two; the sorted keys are
+// stored through put(position, key).  All 256 threads call it.  Short lists are sorted by one warp alone (no CTA barriers).
+template <typename Put>
+__device__ __forceinline__ void ctaBitonicSortList(uint32_t* K, uint32_t n, Put put)
+{
+	const uint32_t tid = threadIdx.x;
+	uint32_t P = 2;
+	while (P < n) P <<= 1;
+	for (uint32_t i = n + tid; i < P; i += kSortThreads) K[i] = 0xFFFFFFFFu;
+	__syncthreads();
+	const bool oneWarp = P <= 256u;
+	const uint32_t workers = oneWarp ? 32u : (uint32_t)kSortThreads;
+	if (!oneWarp || tid < 32u)
+		for (uint32_t k = 2; k <= P; k <<= 1)
+			for (uint32_t j = k >> 1; j > 0; j >>= 1)
+			{
+				for (uint32_t idx = tid; idx < (P >> 1); idx += workers)
+				{
+					const uint32_t i = ((idx & ~(j - 1u)) << 1) | (idx & (j - 1u)), p = i | j;
+					const uint32_t x = K[i], y = K[p];
+					if ((x > y) == ((i & k) == 0u)) { K[i] = y; K[p] = x; }
+				}
+				if (oneWarp) __syncwarp(); else __syncthreads();
+			}
+	if (oneWarp) __syncthreads();
+	for (uint32_t i = tid; i < n; i += kSortThreads) put(i, K[i]);
+}
+
+// The same run ordering by ONE warp, without CTA barriers: the raster kernel's warp 0 sorts the staged list of its
+// tile while the other warps already sweep it (the sweep does not depend on the order).  Returns 0 = in order
+// already, 1 = runs moved, 2 = not applicable (too many or interleaved runs: the caller falls back to the bitonic
+// network once the sweep is over).  K is only read.
+constexpr int kWarpRuns = 192;
+struct WarpSortScratch
+{
+	uint32_t head[kWarpRuns];
+	uint16_t start[kWarpRuns + 2], order[kWarpRuns], out[kWarpRuns];
+};
+template <typename Put>
+__device__ __forceinline__ int warpSortTileList(const uint32_t* K, uint32_t n, WarpSortScratch& S, uint32_t lane, Put put)
+{
+	const unsigned ltMask = (1u << lane) - 1u;
+	// 1. the runs.  A run = the ids one scatter warp wrote: it ends where the next key is smaller or belongs to
+	//    another 32-aligned id group (warpBinRects: one ascending run per warp and tile)
+	uint32_t runs = 0, carry = 0;
+	bool descent = false;
+	for (uint32_t b = 0; b < n; b += 32)
+	{
+		const uint32_t i = b + lane;
+		const uint32_t k = (i < n) ? K[i] : 0xFFFFFFFFu;
+		uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k, 1);
+		if (lane == 0) prev = carry;
+		const bool start = (i < n) && (i == 0 || prev > k || (prev >> 5) != (k >> 5));
+		descent |= (i < n) && i > 0 && prev > k;
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
+		if (start)
+		{
+			const uint32_t r = runs + (uint32_t)__popc(m & ltMask);
+			if (r < (uint32_t)kWarpRuns) { S.start[r] = (uint16_t)i; S.head[r] = k; }
+		}
+		runs += (uint32_t)__popc(m);
+		carry = __shfl_sync(0xFFFFFFFFu, k, 31);
+	}
+	if (!__any_sync(0xFFFFFFFFu, descent)) return 0;
+	if (runs > (uint32_t)kWarpRuns) return 2;
+	if (lane == 0) S.start[runs] = (uint16_t)n;
+	__syncwarp();
+	// 2. order the runs by their first key (keys are distinct primitive ids)
+	for (uint32_t r = lane; r < runs; r += 32)
+	{
+		const uint32_t head = S.head[r];
+		uint32_t rank = 0;
+		for (uint32_t q = 0; q < runs; ++q) rank += (S.head[q] < head) ? 1u : 0u;
+		S.order[rank] = (uint16_t)r;
+	}
+	__syncwarp();
+	// 3. output position of every run = prefix of the run lengths in that order; the runs must cover disjoint id
+	//    ranges (last key of a run < first key of the next one)
+	uint32_t running = 0;
+	bool bad = false;
+	for (uint32_t b = 0; b < runs; b += 32)
+	{
+		const uint32_t kk = b + lane;
+		uint32_t len = 0, r = 0;
+		if (kk < runs)
+		{
+			r = S.order[kk];
+			len = (uint32_t)S.start[r + 1] - (uint32_t)S.start[r];
+			if (kk + 1 < runs) bad |= K[S.start[r + 1] - 1] > S.head[S.order[kk + 1]];
+		}
+		uint32_t incl = len;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+		if (kk < runs) S.out[r] = (uint16_t)(running + incl - len);
+		running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+	}
+	if (__any_sync(0xFFFFFFFFu, bad)) return 2;
+	__syncwarp();
+	// 4. move every key to its run's output position
+	uint32_t before = 0;
+	for (uint32_t b = 0; b < n; b += 32)
+	{
+		const uint32_t i = b + lane;
+		const uint32_t k = (i < n) ? K[i] : 0u, prev = (i < n && i > 0) ? K[i - 1] : 0u;
+		const bool start = (i < n) && (i == 0 || prev > k || (prev >> 5) != (k >> 5));
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, start);
+		if (i < n)
+		{
+			const uint32_t r = before + (uint32_t)__popc(m & (ltMask | (1u << lane))) - 1u;
+			put((uint32_t)S.out[r] + (i - (uint32_t)S.start[r]), k);
+		}
+		before += (uint32_t)__popc(m);
+	}
+	return 1;
+}
+
 // scratch of ctaSortTileList (the raster kernel overlays it on its big-triangle buffer, which is idle until the sweep)
 struct __align__(16) SortScratch
 {
@@ -898,28 +1017,8 @@ __device__ __forceinline__ int ctaSortTileList(uint32_t* K, uint32_t n, SortScra
 		}
 		return 1;
 	}
-	// interleaved or too many runs (incoherent warps, cooperatively binned big triangles): bitonic network over the
-	// staged keys, padded to a power of two.  Short lists are sorted by one warp alone (no CTA barriers).
-	uint32_t P = 2;
-	while (P < n) P <<= 1;
-	for (uint32_t i = n + tid; i < P; i += kSortThreads) K[i] = 0xFFFFFFFFu;
-	__syncthreads();
-	const bool oneWarp = P <= 256u;
-	const uint32_t workers = oneWarp ? 32u : (uint32_t)kSortThreads;
-	if (!oneWarp || tid < 32u)
-		for (uint32_t k = 2; k <= P; k <<= 1)
-			for (uint32_t j = k >> 1; j > 0; j >>= 1)
-			{
-				for (uint32_t idx = tid; idx < (P >> 1); idx += workers)
-				{
-					const uint32_t i = ((idx & ~(j - 1u)) << 1) | (idx & (j - 1u)), p = i | j;
-					const uint32_t x = K[i], y = K[p];
-					if ((x > y) == ((i & k) == 0u)) { K[i] = y; K[p] = x; }
-				}
-				if (oneWarp) __syncwarp(); else __syncthreads();
-			}
-	if (oneWarp) __syncthreads();
-	for (uint32_t i = tid; i < n; i += kSortThreads) put(i, K[i]);
+	// interleaved or too many runs (incoherent warps, cooperatively binned big triangles)
+	ctaBitonicSortList(K, n, put);
 	return 2;
 }
 

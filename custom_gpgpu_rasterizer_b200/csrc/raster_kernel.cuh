@@ -35,7 +35,7 @@ struct RasterArgs
 	float* zSurface;        // debug surfaces (may be null)
 	uint32_t* winnerSurface;
 	ShardTable shard;       // sharded front end only (fp.shardGeometry): the per-rank lists of this rank's tiles, all in local memory
-	const uint32_t* tileOrder;  // the work order tile_scan_kernel prepared: kTileClasses lists of nTiles entries (not with the sharded front end)
+	const uint4* tileOrder;     // the work order: kTileClasses lists of nTiles {tile, list length, list offset, 0} entries (tile_scan_kernel / shard_merge_heads_kernel)
 };
 
 // expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
@@ -260,92 +260,153 @@ __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefet
 #endif
 constexpr int rasterCtasPerSM(bool textured, bool otf) { return textured ? B2R_RASTER_FULL_CTAS : (otf ? B2R_RASTER_LIGHT_OTF_CTAS : B2R_RASTER_LIGHT_CTAS); }
 
-// The kernel is PERSISTENT: rasterCtasPerSM() CTAs per SM take work items off a counter (frameInfo[kInfoWorkCounter]).
-// A work item is one 16x16 pixel block (a tile, or one sub-block of a bin larger than 16x16) in the order
-// tile_scan_kernel prepared - longest lists first, the empty tiles last, kEmptyBatch of them per item - or, with the
-// sharded front end, the rank's own tiles in index order (their merged lengths are only known tile by tile).
+// big triangles of the pixel-parallel path as they wait in shared memory (64 bytes; the edge vectors are rebuilt from
+// the vertices with the subtractions of expandRecord, hence the same bits)
+struct __align__(16) TriBig
+{
+	float x0, y0, x1, y1;
+	float x2, y2, z0, z1;
+	float z2, area, rcpArea, divLo;
+	uint32_t prim; int zLow; uint32_t yExtent, pad;
+};
+__device__ __forceinline__ void packBig(const TriShared& t, uint32_t yExtent, TriBig& b)
+{
+	b.x0 = t.x0; b.y0 = t.y0; b.x1 = t.x1; b.y1 = t.y1; b.x2 = t.x2; b.y2 = t.y2; b.z0 = t.z0; b.z1 = t.z1;
+	b.z2 = t.z2; b.area = t.area; b.rcpArea = t.rcpArea; b.divLo = t.divLo; b.prim = t.prim; b.zLow = t.zLow; b.yExtent = yExtent; b.pad = 0;
+}
+__device__ __forceinline__ void unpackBig(const TriBig& b, TriShared& t)
+{
+	t.x0 = b.x0; t.y0 = b.y0; t.x1 = b.x1; t.y1 = b.y1; t.x2 = b.x2; t.y2 = b.y2; t.z0 = b.z0; t.z1 = b.z1;
+	t.z2 = b.z2; t.area = b.area; t.rcpArea = b.rcpArea; t.divLo = b.divLo; t.prim = b.prim; t.zLow = b.zLow; t.yExtent = b.yExtent;
+	t.eAx = b.x1 - b.x0; t.eAy = b.y1 - b.y0;
+	t.eBx = b.x2 - b.x1; t.eBy = b.y2 - b.y1;
+	t.eCx = b.x0 - b.x2; t.eCy = b.y0 - b.y2;
+}
+
+// the list of the tile a CTA rasterises
+struct WorkItem
+{
+	uint32_t count, offset;           // length of the tile's list, its offset in binIds (single GPU / replicated front end)
+	uint32_t segEnd[kMaxRanks], segOff[kMaxRanks];    // sharded front end: the ranks' segments of the list (prefix ends, offsets)
+};
+
+// global slot of entry e of a tile's (concatenated) list
+__device__ __forceinline__ uint32_t* listSlotOf(const RasterArgs& A, const WorkItem& item, bool shard, uint32_t e)
+{
+	if (shard)
+	{
+		uint32_t seg = 0;
+		while (e >= item.segEnd[seg]) ++seg;
+		return const_cast<uint32_t*>(A.shard.binIds[seg]) + item.segOff[seg] + (e - (seg ? item.segEnd[seg - 1] : 0u));
+	}
+	return const_cast<uint32_t*>(A.binIds) + item.offset + e;
+}
+
+// The single-warp / whole-CTA sort helpers are real functions (not inlined): they run once per tile, and their
+// registers must not count against the sweep's.
+// warp 0: canonical order of the staged list (stored to global memory); returns warpSortTileList's verdict
+__device__ B2R_NOINLINE int sortStagedList(const RasterArgs& A, const WorkItem& item, bool shard, const uint32_t* K, uint32_t n, WarpSortScratch& S)
+{
+	return warpSortTileList(K, n, S, threadIdx.x & 31u, [&](uint32_t pos, uint32_t key) { *listSlotOf(A, item, shard, pos) = key; });
+}
+// all threads: the bitonic fallback for lists whose runs warp 0 could not order
+__device__ B2R_NOINLINE void sortStagedListFallback(const RasterArgs& A, const WorkItem& item, bool shard, uint32_t* K, uint32_t n)
+{
+	ctaBitonicSortList(K, n, [&](uint32_t pos, uint32_t key) { *listSlotOf(A, item, shard, pos) = key; });
+}
+
+// One CTA = one work item = one 16x16 pixel block (a tile, or one sub-block of a bin larger than 16x16), or kEmptyBatch
+// blocks of empty tiles.  The items are numbered in the order tile_scan_kernel (sharded front end:
+// shard_merge_heads_kernel) prepared - longest lists first, the empty tiles last - and the hardware hands out CTAs in
+// index order, so the long lists start first and the tail of the kernel is made of short ones.  The grid covers the
+// worst case (one item per block); the CTAs behind the last item leave at once.
+// Lists of up to kStage entries are staged in shared memory; warp 0 then puts the staged list into canonical order
+// (and stores it) while warps 1..7 already sweep it - the sweep does not depend on the order.
 template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF = false>
-__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(RasterArgs A, FrameParams fp)
+__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
 {
 	pdlPrologue();
-	// expanded records of the pixel-parallel triangles during the sweep; before it, the scratch of the list sort
-	__shared__ __align__(16) unsigned char sBigRaw[sizeof(TriShared) * kListChunk];
-	static_assert(sizeof(SortScratch) <= sizeof(TriShared) * kListChunk, "the sort scratch overlays the big-triangle buffer");
-	TriShared* const sBig = reinterpret_cast<TriShared*>(sBigRaw);
-	SortScratch& sSort = *reinterpret_cast<SortScratch*>(sBigRaw);
+	__shared__ __align__(16) TriBig sBig[kListChunk];   // the pixel-parallel triangles of the block
 	__shared__ __align__(16) uint32_t sIds[kStage];    // the tile's list (primitive ids), staged for the sort and the sweep
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
+	__shared__ WarpSortScratch sSort;
+	__shared__ WorkItem sItem;
 	__shared__ uint32_t sNumBig[2];                    // big-triangle count of the current / the next list chunk
-	__shared__ uint32_t sWork[2];
-	__shared__ uint32_t sSegEnd[kMaxRanks], sSegOff[kMaxRanks];
+	__shared__ uint32_t sSortFallback;
 	__shared__ float sWvp[OTF ? kSmemMeshes : 1][16];  // OTF: WVP of the first meshes (visible after the first barrier)
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
 	const int tid = threadIdx.x;
-	if (OTF && (uint32_t)tid < min(fp.nMeshes, kSmemMeshes) * 16u) sWvp[tid >> 4][tid & 15u] = A.meshes[tid >> 4].wvp[tid & 15u];
+	const uint32_t lane = (uint32_t)tid & 31u, warp = (uint32_t)tid >> 5;
 	const uint32_t nTilesAll = fp.binsX * fp.binsY;
 	const uint32_t subs = fp.subX * fp.subY;
-
-	// work items: [sCum[c], sCum[c + 1]) = class c (in shared memory: live across the whole persistent loop)
-	__shared__ uint32_t sCum[kTileClasses + 2];        // [kTileClasses + 1] = 16x16 blocks of the empty class
-	if (tid == 0)
+	// this CTA's work item: class, first block, number of blocks (the class counts are the same few words for every
+	// CTA: L1 hits but for the first CTA of an SM)
+	uint32_t cls = 0, start = 0, run = 0, emptyBlocks = 0;
+	#pragma unroll
+	for (uint32_t c = 0; c < kTileClasses; ++c)
 	{
-		uint32_t run = 0, emptyBlocks = 0;
-		sCum[0] = 0;
-		if (fp.shardGeometry)
-		{
-			const uint32_t owned = nTilesAll > fp.ownerRank ? (nTilesAll - fp.ownerRank + fp.ownerCount - 1u) / fp.ownerCount : 0u;
-			for (uint32_t c = 0; c < kTileClasses; ++c) sCum[c + 1] = owned * subs;
-		}
-		else
-			for (uint32_t c = 0; c < kTileClasses; ++c)
-			{
-				const uint32_t blocks = (uint32_t)A.frameInfo[kInfoClassBase + c] * subs;
-				if (c + 1 == kTileClasses) emptyBlocks = blocks;
-				run += (c + 1 < kTileClasses) ? blocks : (blocks + kEmptyBatch - 1u) / kEmptyBatch;
-				sCum[c + 1] = run;
-			}
-		sCum[kTileClasses + 1] = emptyBlocks;
+		const uint32_t blocks = (uint32_t)__ldg(A.frameInfo + kInfoClassBase + c) * subs;
+		if (blockIdx.x >= run) { cls = c; start = run; }
+		if (c + 1 == kTileClasses) emptyBlocks = blocks;
+		run += (c + 1 < kTileClasses) ? blocks : (blocks + kEmptyBatch - 1u) / kEmptyBatch;
 	}
+	if (blockIdx.x >= run) return;
+	uint32_t v0 = blockIdx.x - start, v1 = v0 + 1;
+	if (cls == kTileClasses - 1u)
+	{
+		v0 *= kEmptyBatch;
+		v1 = min(v0 + kEmptyBatch, emptyBlocks);
+	}
+	if (OTF && (uint32_t)tid < min(fp.nMeshes, kSmemMeshes) * 16u) sWvp[tid >> 4][tid & 15u] = A.meshes[tid >> 4].wvp[tid & 15u];
+	const bool shard = fp.shardGeometry != 0u;
+	const WorkItem& item = sItem;
 
-	for (uint32_t iter = 0; ; ++iter)
+	// pixel block `sub` of bin `bin`: origin and extent inside the bin and the screen
+	auto blockRect = [&](uint32_t bin, uint32_t sub, int& ox, int& oy, int& ex, int& ey)
 	{
-		if (tid == 0) sWork[iter & 1u] = (uint32_t)atomicAdd(&A.frameInfo[kInfoWorkCounter], 1ull);
-		__syncthreads();
-		const uint32_t item = sWork[iter & 1u];
-		if (item >= sCum[kTileClasses]) break;
-		// item -> pixel blocks [v0, v1) of one class list (one block, or a batch of empty ones)
-		uint32_t cls = 0, v0 = item, v1 = item + 1;
-		const uint32_t* order = nullptr;
-		if (!fp.shardGeometry)
-		{
-			uint32_t start = 0;
-			#pragma unroll
-			for (uint32_t c = 1; c < kTileClasses; ++c)
-			{
-				const uint32_t lo = sCum[c];
-				if (item >= lo) { cls = c; start = lo; }
-			}
-			v0 = item - start; v1 = v0 + 1;
-			if (cls == kTileClasses - 1u)
-			{
-				v0 *= kEmptyBatch;
-				v1 = min(v0 + kEmptyBatch, sCum[kTileClasses + 1]);
-			}
-			order = A.tileOrder + (size_t)cls * nTilesAll;
-		}
-	for (uint32_t vb = v0; vb < v1; ++vb)
-	{
-		uint32_t sub;
-		const uint32_t slot = divMagic(vb, subs, fp.subsMagic, sub);
-		const uint32_t bin = fp.shardGeometry ? fp.ownerRank + slot * fp.ownerCount : __ldg(order + slot);
 		uint32_t binX, subX;
 		const uint32_t binY = divMagic(bin, fp.binsX, fp.binsXMagic, binX);
 		const uint32_t subY = divMagic(sub, fp.subX, fp.subXMagic, subX);
-		const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
-		// extent of this CTA's pixel block inside the bin and the screen
-		const int ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
-		const int ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
+		ox = (int)(binX * fp.binW + subX * kTile); oy = (int)(binY * fp.binH + subY * kTile);
+		ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
+		ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
+	};
+	// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
+	// gathered with one contiguous NCCL transfer / written straight into a peer's memory
+	auto storePixel = [&](uint32_t bin, uint32_t sub, size_t pix, uint32_t colour, int depthOut, float zOut, uint32_t prim)
+	{
+		if (fp.packedOutput) A.framebuffer[((size_t)((bin - fp.ownerRank) / fp.ownerCount) * subs + sub) * (kTile * kTile) + tid] = colour;
+		else A.framebuffer[pix] = colour;
+		A.depth[pix] = depthOut;
+		if (fp.debugSurfaces)
+		{
+			A.zSurface[pix] = zOut;
+			A.winnerSurface[pix] = prim;
+		}
+	};
+	if (cls == kTileClasses - 1u)
+	{
+		// a batch of empty tiles: untouched fragments = zero-cleared PixelShade whose colour32 is the clear colour
+		// (Depth: (0-.985)/.015*255 < 0 -> 0 ; Normal: n = 0)
+		const uint32_t clear = (fp.visState == 0u) ? packColour(fp.clearRGB[0], fp.clearRGB[1], fp.clearRGB[2]) : 0u;
+		for (uint32_t vb = v0; vb < v1; ++vb)
+		{
+			uint32_t sub;
+			const uint32_t bin = __ldg(&A.tileOrder[(size_t)cls * nTilesAll + divMagic(vb, subs, fp.subsMagic, sub)].x);
+			int ox, oy, ex, ey;
+			blockRect(bin, sub, ox, oy, ex, ey);
+			const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
+			if (px < ex && py < ey) storePixel(bin, sub, (size_t)px + (size_t)py * fp.width, clear, 0x7FFFFFFF, 0.f, kNoPrim);
+		}
+		return;
+	}
+	{
+		uint32_t sub;
+		const uint4 desc = __ldg(A.tileOrder + (size_t)cls * nTilesAll + divMagic(v0, subs, fp.subsMagic, sub));      // {tile, list length, list offset, 0}
+		const uint32_t bin = desc.x;
+		int ox, oy, ex, ey;
+		blockRect(bin, sub, ox, oy, ex, ey);
 		const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
 		const bool live = px < ex && py < ey;
 		const float fx = (float)px, fy = (float)py;
@@ -355,64 +416,16 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 		int bestZ = 0x7FFFFFFF;          // register copy of this pixel's depth/winner for the pixel-parallel path
 		uint32_t bestPrim = kNoPrim;
 		uint32_t nFrags = 0;             // fragments that pass the inside + z-range tests (COUNT builds only)
-		uint32_t n;
-		const uint32_t* list = nullptr;
-		if (fp.shardGeometry)
-		{
-			// Sharded front end.  Rank p built the list of ITS primitive slice for every tile and pushed the heads
-			// (after its scan) and the ids (after its scatter) of the tiles owned here into this rank's memory.
-			// The slices are contiguous and ordered by rank, so the tile's list is the concatenation of the n
-			// segments in rank order: read the n heads at once, one lane per rank.
-			__syncthreads();                  // the previous block's readers of sSegEnd / sSegOff are done
-			if (tid < 32)
-			{
-				uint32_t cnt = 0, off = 0, bad = 0;
-				if ((uint32_t)tid < fp.ownerCount)
-				{
-					cnt = __ldg(A.shard.tileCount[tid] + bin);
-					off = __ldg(A.shard.tileOffset[tid] + bin);
-					bad = __ldg(A.shard.tileOffset[tid] + nTilesAll) == 0xFFFFFFFFu;   // that rank's list buffer overflowed
-				}
-				uint32_t incl = cnt;
-				#pragma unroll
-				for (int d = 1; d < kMaxRanks; d <<= 1)
-				{
-					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-					if (tid >= d) incl += t;
-				}
-				if (__any_sync(0xFFFFFFFFu, bad))
-				{
-					incl = 0;                                  // void frame: the host reports the undersized list capacity
-					if (tid == 0) A.frameInfo[1] = 1ull;
-				}
-				if (tid < kMaxRanks) { sSegEnd[tid] = incl; sSegOff[tid] = off; }
-			}
-			__syncthreads();
-			n = sSegEnd[fp.ownerCount - 1];
-		}
-		else
-		{
-			n = (cls == kTileClasses - 1u) ? 0u : __ldg(A.tileCount + bin);
-			list = A.binIds + __ldg(A.tileOffset + bin);
-		}
+		const uint32_t n = desc.y;
 
-		// global slot of entry e of the (concatenated) list
-		auto listSlot = [&](uint32_t e) -> uint32_t*
-		{
-			if (fp.shardGeometry)
-			{
-				uint32_t seg = 0;
-				while (e >= sSegEnd[seg]) ++seg;
-				return const_cast<uint32_t*>(A.shard.binIds[seg]) + sSegOff[seg] + (e - (seg ? sSegEnd[seg - 1] : 0u));
-			}
-			return const_cast<uint32_t*>(list) + e;
-		};
+		auto listSlot = [&](uint32_t e) -> uint32_t* { return listSlotOf(A, item, shard, e); };
 		// One list entry -> screen-space triangle + its candidate box inside this CTA's block.  Returns the number of
 		// candidate pixels (0: nothing to do).
-		auto expandEntry = [&](uint32_t prim, const uint4& tr, TriShared& t, int& x0, int& x1, int& y0, int& y1) -> int
+		auto expandEntry = [&](uint32_t prim, TriShared& t, int& x0, int& x1, int& y0, int& y1) -> int
 		{
 			// rebuild the screen-space triangle from the static reference + the transformed positions
 			// (same code, hence the same bits, wherever a triangle is expanded)
+			const uint4 tr = __ldg(A.triRefs + prim);
 			float4 p0, p1, p2;
 			fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
 			TriRecord r;
@@ -431,10 +444,12 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 		{
 			for (uint32_t j = 0; j < nBig; ++j)
 			{
-				TriShared t = sBig[j];
-				const int ty0 = (int)(t.yExtent & 0xFFFFu), ty1 = (int)(t.yExtent >> 16);
+				const uint32_t yExtent = sBig[j].yExtent;
+				const int ty0 = (int)(yExtent & 0xFFFFu), ty1 = (int)(yExtent >> 16);
 				if (ty1 <= warpY0 || ty0 >= warpY1) continue;          // warp-uniform
-				if (!COUNT && t.zLow > bestZ) continue;                // cannot win this pixel (per lane)
+				if (!COUNT && sBig[j].zLow > bestZ) continue;          // cannot win this pixel (per lane)
+				TriShared t;
+				unpackBig(sBig[j], t);
 				Bary bc; int zi;
 				if (live && fragmentTest<TOPLEFT>(t, fx, fy, bc, zi))
 				{
@@ -448,69 +463,73 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 		if (n)
 		{
 			sKey[tid] = kEmptyKey;
-			if (tid < 2) sNumBig[tid] = 0;
-			// lists of up to kStage entries are staged in shared memory: sorted here (canonical ascending order in
-			// global memory - the sweep itself does not depend on the order) and then swept from there
+			if (tid == 0) { sNumBig[0] = 0; sNumBig[1] = 0; sSortFallback = 0; sItem.count = n; sItem.offset = desc.z; }
+			if (shard)
+			{
+				// Sharded front end.  Rank p built the list of ITS primitive slice for every tile and pushed the heads
+				// (after its scan) and the ids (after its scatter) of the tiles owned here into this rank's memory.  The
+				// slices are contiguous and ordered by rank, so the tile's list is the concatenation of the segments in
+				// rank order: one lane per rank reads that rank's head.
+				if (tid < 32)
+				{
+					uint32_t cnt = 0, off = 0;
+					if (lane < fp.ownerCount)
+					{
+						cnt = __ldg(A.shard.tileCount[lane] + bin);
+						off = __ldg(A.shard.tileOffset[lane] + bin);
+					}
+					uint32_t incl = cnt;
+					#pragma unroll
+					for (int d = 1; d < kMaxRanks; d <<= 1)
+					{
+						const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+						if (lane >= (uint32_t)d) incl += t;
+					}
+					if (lane < kMaxRanks) { sItem.segEnd[lane] = incl; sItem.segOff[lane] = off; }
+				}
+				__syncthreads();
+			}
+			// lists of up to kStage entries are staged in shared memory: warp 0 sorts them there (canonical ascending order
+			// in global memory - the sweep itself does not depend on the order) while the other warps sweep them
 			const bool staged = n <= (uint32_t)kStage;
 			if (staged)
 			{
+				const uint32_t* list = A.binIds + desc.z;
 				for (uint32_t e = tid; e < n; e += kListChunk)
 				{
-					const uint32_t prim = *listSlot(e);
+					const uint32_t prim = shard ? *listSlot(e) : __ldg(list + e);
 					sIds[e] = prim;
-					if (e < 2u * kListChunk) prefetchL2(A.triRefs + prim);      // the vertex references of the first entries arrive while the list is sorted
+					if (e < (uint32_t)kListChunk) prefetchL2(A.triRefs + prim);      // the vertex references of the first entries
 				}
 			}
 			__syncthreads();                  // sKey / counters initialised, list staged
-			if (staged && fp.sortLists && n > 1u)
+			const bool sortHere = staged && fp.sortLists && n > 1u;
+			if (warp == 0 && sortHere)
 			{
-				const int how = ctaSortTileList(sIds, n, sSort, [&](uint32_t pos, uint32_t key) { *listSlot(pos) = key; });
-				if (how == 2 && tid == 0) atomicAdd(&A.frameInfo[6], 1ull);
-				__syncthreads();              // the scratch becomes the big-triangle buffer
+				const int how = sortStagedList(A, item, shard, sIds, n, sSort);
+				if (how == 2 && lane == 0) sSortFallback = 1u;
 			}
 			auto idAt = [&](uint32_t e) -> uint32_t { return staged ? sIds[e] : *listSlot(e); };
 
-			// Sweep 1, no barriers: every thread walks its entries of all chunks of the list.  Small triangles are resolved
+			// Sweep 1, no barriers: every sweeping thread walks its entries of the list.  Small triangles are resolved
 			// right away (triangle-parallel, atomicMin into sKey); large ones are only collected in sBig - up to kListChunk of
 			// them for the WHOLE list - and rasterised pixel-parallel after the sweep.  The warps of the CTA therefore drift
 			// apart over a long list instead of meeting at two barriers per chunk, and their memory round trips
-			// (vertex reference -> positions) overlap each other's arithmetic.  A thread loads the vertex reference of its
-			// next entry before it works on the current one and pulls that entry's positions into L2 afterwards.
-#if B2R_RASTER_LOOKAHEAD
-			uint32_t primNext = 0;
-			uint4 trNext = make_uint4(0, 0, 0, 0);
-			bool haveNext = (uint32_t)tid < n;
-			if (haveNext) { primNext = idAt(tid); trNext = __ldg(A.triRefs + primNext); }
-#endif
-			for (uint32_t base = 0; base < n; base += kListChunk)
-			{
-#if B2R_RASTER_LOOKAHEAD
-				const bool have = haveNext;
-				const uint32_t prim = primNext;
-				const uint4 tr = trNext;
-				haveNext = base + kListChunk + (uint32_t)tid < n;
-				if (haveNext) { primNext = idAt(base + kListChunk + tid); trNext = __ldg(A.triRefs + primNext); }
-#else
-				const bool have = base + (uint32_t)tid < n;
-				const bool haveNext = base + kListChunk + (uint32_t)tid < n;
-				uint32_t prim = 0;
-				uint4 tr = make_uint4(0, 0, 0, 0);
-				if (have) { prim = idAt(base + tid); tr = __ldg(A.triRefs + prim); }
-#endif
-				if (have)
+			// (vertex reference -> positions) overlap each other's arithmetic.  While warp 0 sorts, warps 1..7 sweep.
+			const uint32_t sweepers = sortHere ? (uint32_t)kListChunk - 32u : (uint32_t)kListChunk;
+			const uint32_t me = sortHere ? (uint32_t)tid - 32u : (uint32_t)tid;      // warp 0: >= sweepers while it sorts
+			if (me < sweepers)
+				for (uint32_t e = me; e < n; e += sweepers)
 				{
+					const uint32_t prim = idAt(e);
+					if (staged && e + sweepers < n) prefetchL2(A.triRefs + sIds[e + sweepers]);
 					TriShared t;
 					int x0, x1, y0, y1;
-					const int area = expandEntry(prim, tr, t, x0, x1, y0, y1);
+					const int area = expandEntry(prim, t, x0, x1, y0, y1);
 					if (area > kSmallArea)
 					{
 						const uint32_t slotBig = atomicAdd(&sNumBig[0], 1u);
-						if (slotBig < (uint32_t)kListChunk)
-						{
-							TriShared& dst = sBig[slotBig];
-							dst = t;
-							dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);      // bbox rows for the warp-level reject
-						}
+						if (slotBig < (uint32_t)kListChunk) packBig(t, (uint32_t)y0 | ((uint32_t)y1 << 16), sBig[slotBig]);   // bbox rows for the warp-level reject
 					}
 					else if (area > 0)
 					{
@@ -528,13 +547,13 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 							}
 					}
 				}
-#if B2R_RASTER_LOOKAHEAD
-				if (haveNext && !OTF) { prefetchL2(A.pos4 + trNext.x); prefetchL2(A.pos4 + trNext.y); prefetchL2(A.pos4 + trNext.z); }
-#else
-				if (haveNext && staged) prefetchL2(A.triRefs + sIds[base + kListChunk + tid]);
-#endif
-			}
 			__syncthreads();
+			if (sSortFallback)
+			{
+				// too many or interleaved runs for warp 0 (incoherent warps, cooperatively binned big triangles): bitonic network
+				sortStagedListFallback(A, item, shard, sIds, n);
+				if (tid == 0) atomicAdd(&A.frameInfo[6], 1ull);
+			}
 			const uint32_t nBigTotal = sNumBig[0];
 			if (nBigTotal <= (uint32_t)kListChunk)
 				pixelParallel(nBigTotal);
@@ -546,23 +565,18 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 				__syncthreads();                               // everybody has read the total
 				if (tid < 2) sNumBig[tid] = 0;
 				__syncthreads();
-				for (uint32_t base = 0, it = 0; base < n; base += kListChunk, ++it)
+				for (uint32_t base = 0, it2 = 0; base < n; base += kListChunk, ++it2)
 				{
-					if (tid == 0) sNumBig[(it + 1u) & 1u] = 0;
+					if (tid == 0) sNumBig[(it2 + 1u) & 1u] = 0;
 					if (base + (uint32_t)tid < n)
 					{
 						TriShared t;
 						int x0, x1, y0, y1;
-						const uint32_t prim = idAt(base + tid);
-						if (expandEntry(prim, __ldg(A.triRefs + prim), t, x0, x1, y0, y1) > kSmallArea)
-						{
-							TriShared& dst = sBig[atomicAdd(&sNumBig[it & 1u], 1u)];
-							dst = t;
-							dst.yExtent = (uint32_t)y0 | ((uint32_t)y1 << 16);
-						}
+						if (expandEntry(idAt(base + tid), t, x0, x1, y0, y1) > kSmallArea)
+							packBig(t, (uint32_t)y0 | ((uint32_t)y1 << 16), sBig[atomicAdd(&sNumBig[it2 & 1u], 1u)]);
 					}
 					__syncthreads();
-					pixelParallel(sNumBig[it & 1u]);
+					pixelParallel(sNumBig[it2 & 1u]);
 					if (base + kListChunk < n) __syncthreads();
 				}
 			}
@@ -574,10 +588,8 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 				for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
 				if ((tid & 31) == 0 && v) atomicAdd(&A.frameInfo[4], (unsigned long long)v);
 			}
-			// (no barrier here: the shared-memory state of this block is not touched again before the barrier of the
-			// next work-item fetch, which every thread passes before the next block initialises it)
 		}
-		if (!live) continue;
+		if (!live) return;
 
 		// ---- deferred shade of the winner (PS_Kernel, CUDARenderer.cu:833-897) + ROP write-back
 		const size_t pix = (size_t)px + (size_t)py * fp.width;
@@ -669,20 +681,38 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 				}
 			}
 		}
-		// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
-		// gathered with one contiguous NCCL transfer / written straight into a peer's memory
-		if (fp.packedOutput) A.framebuffer[((size_t)((bin - fp.ownerRank) / fp.ownerCount) * subs + sub) * (kTile * kTile) + tid] = colour;
-		else A.framebuffer[pix] = colour;
-		A.depth[pix] = depthOut;
-		if (fp.debugSurfaces)
-		{
-			A.zSurface[pix] = zOut;
-			A.winnerSurface[pix] = prim;
-		}
-	}
+		storePixel(bin, sub, pix, colour, depthOut, zOut, prim);
 	}
 }
 
+// Sharded front end, after the "lists ready" barrier: the work order of this rank's raster kernel.  The length of a
+// tile's list is the sum of the heads the ranks pushed for it; the owned tiles are grouped into the same length
+// classes tile_scan_kernel uses on a single GPU (longest first), entries {tile, merged length, 0, 0}.  Also raises the
+// overflow flag if any rank's list buffer was too small (its marker word rides behind its offsets).
+__global__ void __launch_bounds__(256) shard_merge_heads_kernel(ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
+	uint4* __restrict__ tileOrder, unsigned long long* __restrict__ frameInfo)
+{
+	pdlPrologue();
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+	const uint32_t tile = rank + k * nRanks;
+	if (k < nRanks && __ldg(T.tileOffset[k] + nTiles) == 0xFFFFFFFFu) frameInfo[1] = 1ull;
+	uint32_t n = 0, cls = kTileClasses;
+	if (tile < nTiles)
+	{
+		for (uint32_t p = 0; p < nRanks; ++p) n += __ldg(T.tileCount[p] + tile);
+		cls = tileClass(n);
+	}
+	#pragma unroll
+	for (uint32_t c = 0; c < kTileClasses; ++c)
+	{
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+		if (!m) continue;
+		uint32_t base = 0;
+		if (lane == 0) base = (uint32_t)atomicAdd(&frameInfo[kInfoClassBase + c], (unsigned long long)__popc(m));
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (cls == c) tileOrder[(size_t)c * nTiles + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = make_uint4(tile, n, 0u, 0u);
+	}
+}
 
 // Sharded front end, exchange step 1: right after its scan every rank stores the heads (count, offset) of its
 // lists into the inbox of each tile's owner, so the transfer hides behind scatter + sort.
@@ -719,6 +749,31 @@ __global__ void __launch_bounds__(256) shard_push_lists_kernel(const uint32_t* _
 	const uint4* src = reinterpret_cast<const uint4*>(binIds);
 	uint4* dst = reinterpret_cast<uint4*>(R.region[owner]);
 	for (uint32_t v = (off >> 2) + lane, vEnd = (off + cnt + 3) >> 2; v < vEnd; v += 32) dst[v] = src[v];
+}
+
+// Distributed Present: copy the 16x16 tiles this rank owns from its colour surface into the row-major frame in mapped
+// host memory (zero-copy stores over this GPU's own PCIe link).  64 threads per tile: one 16-byte store per thread, a
+// tile row = one 64-byte segment.  Four tiles per CTA.
+__global__ void __launch_bounds__(256) present_tiles_kernel(const uint32_t* __restrict__ colour, uint32_t* __restrict__ hostFrame,
+	uint32_t rank, uint32_t count, uint32_t owned, FrameParams fp)
+{
+	const uint32_t k = blockIdx.x * 4u + (threadIdx.x >> 6), t = threadIdx.x & 63u;
+	if (k >= owned * fp.subX * fp.subY) return;
+	uint32_t sub, binX, subX;
+	const uint32_t slot = divMagic(k, fp.subX * fp.subY, fp.subsMagic, sub);
+	const uint32_t bin = rank + slot * count;
+	const uint32_t binY = divMagic(bin, fp.binsX, fp.binsXMagic, binX);
+	const uint32_t subY = divMagic(sub, fp.subX, fp.subXMagic, subX);
+	const int ox = (int)(binX * fp.binW + subX * kTile), oy = (int)(binY * fp.binH + subY * kTile);
+	const int ex = min(min(ox + kTile, (int)((binX + 1) * fp.binW)), (int)fp.width);
+	const int ey = min(min(oy + kTile, (int)((binY + 1) * fp.binH)), (int)fp.height);
+	const int py = oy + (int)(t >> 2), px = ox + (int)(t & 3u) * 4;
+	if (py >= ey || px >= ex) return;
+	const size_t pix = (size_t)px + (size_t)py * fp.width;
+	if (px + 4 <= ex && (pix & 3u) == 0u)
+		*reinterpret_cast<uint4*>(hostFrame + pix) = *reinterpret_cast<const uint4*>(colour + pix);
+	else
+		for (int x = px; x < min(px + 4, ex); ++x) hostFrame[(size_t)x + (size_t)py * fp.width] = colour[(size_t)x + (size_t)py * fp.width];
 }
 
 // sort-first composition on the gathering rank: scatter one rank's packed tile-major colours back

@@ -91,7 +91,12 @@ enum
 	 * of a rank transforms only the vertices its own primitive slice refers to (1/n of the replicated work) and the
 	 * raster kernel transforms the three vertices of a list entry itself, with the vertex stage's own function on the
 	 * resident model-space positions - same bits.  b2r_read_overtex is not available in this mode. */
-	B2R_OPT_SHARD_SLICED_VERTEX = 13
+	B2R_OPT_SHARD_SLICED_VERTEX = 13,
+	/* sharded front end: every rank keeps the colours of the tiles it owns in its OWN colour surface instead of
+	 * storing them into rank 0's over NVLink (no "colours landed" flags either).  For consumers on the host
+	 * (b2r_present_tiles_async: every rank delivers its tiles over its own PCIe link); the frame is then never
+	 * composed on a device.  Set it between frames, after b2r_shard_bind.  Default 0. */
+	B2R_OPT_SHARD_LOCAL_COLOUR = 14
 };
 
 /* stage indices for b2r_get_stage_ms */
@@ -165,6 +170,20 @@ int b2r_read_framebuffer(b2r_context* ctx, uint32_t* out);
  * b2r_present_wait blocks until every outstanding copy has landed (and the frames are complete). */
 int b2r_present_async(b2r_context* ctx, uint32_t* host_pixels);
 int b2r_present_wait(b2r_context* ctx);
+/* Distributed Present (sort-first over several GPUs; CUDARenderer::Present, CUDARenderer.cu:383-395, when the
+ * consumer of the frame is the host): the frame is composed in HOST memory that all ranks share - e.g. a POSIX
+ * shared-memory mapping - and every rank delivers the tiles it owns over its own PCIe link, instead of all colours
+ * travelling to rank 0 and leaving through one link.
+ *   b2r_host_frame_register(ctx, host, bytes)   page-locks and maps the caller's memory for this context's device
+ *                                               (cudaHostRegister); host = NULL, bytes = 0 releases it
+ *   b2r_present_tiles_async(ctx, byte_offset)   starts copying this rank's tiles (B2R_OPT_TILE_OWNER_*; all tiles
+ *                                               on a single GPU) of the newest frame into the row-major width x
+ *                                               height frame at host + byte_offset; returns immediately; the next
+ *                                               frame renders into the other colour surface (as b2r_present_async)
+ * b2r_present_wait blocks until this rank's copies have landed; a consumer of the composed frame additionally
+ * needs a barrier across the ranks.  With the sharded front end use B2R_OPT_SHARD_LOCAL_COLOUR. */
+int b2r_host_frame_register(b2r_context* ctx, void* host, uint64_t bytes);
+int b2r_present_tiles_async(b2r_context* ctx, uint64_t byte_offset);
 /* depth buffer as the reference keeps it (int z*2^31, INT_MAX = empty; CUDAROPs.cu:386, CUDARenderer.cu:1640) */
 int b2r_read_depth(b2r_context* ctx, int32_t* out);
 /* parity surfaces (need B2R_OPT_DEBUG_SURFACES=1 before the render): PixelShade.zInterpolated

@@ -13,9 +13,6 @@ build() { # name, extra nvcc flags...
   echo "built $OUT/libb2r_$name.so"
 }
 build otf4 -DB2R_RASTER_LIGHT_OTF_CTAS=4
-# round 2: the persistent raster kernel with the in-CTA list sort
-#   la0: no register look-ahead of the next entry's vertex reference (L2 prefetch only)
-#   light5: the light raster instantiation at 5 resident CTAs per SM (48 registers) instead of 6 (40 registers, spills)
-build la0 -DB2R_RASTER_LOOKAHEAD=0
+# round 2: the persistent raster kernel (warp 0 sorts the staged list while the other warps sweep it)
+#   light5: the light raster instantiation at 5 resident CTAs per SM (48 registers) instead of 6 (40 registers, more spills)
 build light5 -DB2R_RASTER_LIGHT_CTAS=5
-build la0_light5 -DB2R_RASTER_LOOKAHEAD=0 -DB2R_RASTER_LIGHT_CTAS=5

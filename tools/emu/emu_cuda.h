@@ -45,6 +45,7 @@
 #define __shared__ static             /* one block runs at a time: block-shared = one static instance */
 #define __constant__ static
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))
 #define EMU_ASM(...) do { } while (0)  /* inline PTX (griddepcontrol, prefetch, globaltimer): no meaning here */
 

@@ -177,6 +177,10 @@ cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *
 cudaError_t cudaFree(void* p) { drain(); (void)p; return 0; }          // synchronises the device; the block is kept (no address reuse)
 cudaError_t cudaMallocHost(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 cudaError_t cudaFreeHost(void*) { return 0; }
+// mapped host memory: "device" memory is host memory here, so the device view of a registered range is the range itself
+cudaError_t cudaHostRegister(void*, size_t, unsigned) { return 0; }
+cudaError_t cudaHostUnregister(void*) { return 0; }
+cudaError_t cudaHostGetDevicePointer(void** dev, void* host, unsigned) { *dev = host; return 0; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, int, void* stream)
 {
 	Op op; op.type = Op::COPY; op.dst = dst; op.src = src; op.bytes = n;

@@ -8,7 +8,7 @@ timeout 1200 python -m pytest tests -m gpu -q -x -n 4 > $O/pytest_default.log 2>
 tail -n 4 $O/pytest_default.log
 B="timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline"
 $B > $O/bench_default.json 2> $O/bench_default.err
-for v in la0 light5 la0_light5; do
+for v in light5; do
   [ -f build/variants/libb2r_$v.so ] && B2R_LIBRARY=$PWD/build/variants/libb2r_$v.so $B --no-fill > $O/bench_$v.json 2> $O/bench_$v.err
 done
 B2R_FRAME_RING=3 $B --no-fill > $O/bench_ring3.json 2> $O/bench_ring3.err

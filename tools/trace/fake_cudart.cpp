@@ -165,6 +165,10 @@ cudaError_t cudaMallocHost(void** p, size_t n)
 	return *p ? 0 : 2;
 }
 cudaError_t cudaFreeHost(void* p) { if (p) LOG("{\"op\":\"free_host\",\"ptr\":%llu", (unsigned long long)(uintptr_t)p); return 0; }
+// a registered (mapped) host range is logged like a pinned allocation; its device view is the range itself
+cudaError_t cudaHostRegister(void* p, size_t n, unsigned) { LOG("{\"op\":\"malloc_host\",\"ptr\":%llu,\"size\":%zu", (unsigned long long)(uintptr_t)p, n); return 0; }
+cudaError_t cudaHostUnregister(void* p) { if (p) LOG("{\"op\":\"free_host\",\"ptr\":%llu", (unsigned long long)(uintptr_t)p); return 0; }
+cudaError_t cudaHostGetDevicePointer(void** dev, void* host, unsigned) { *dev = host; return 0; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, int kind, void* stream)
 {
 	if (n) memmove(dst, src, n);

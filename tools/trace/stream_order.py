@@ -52,6 +52,8 @@ RASTER_ARGS += [(f"shard.tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(
     + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r")]      # the raster kernel sorts the lists it stages, in place
 STRUCTS = {
     "b2r::RasterArgs": RASTER_ARGS,
+    "b2r::ShardTable": [(f"tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)]
+                       + [(f"binIds[{i}]", "r") for i in range(K_MAX_RANKS)],
     "b2r::PeerFlags": [],                  # the flag words: concurrent by design, see above
     "b2r::ShardInbox": [(f"tileCount[{i}]", "w") for i in range(K_MAX_RANKS)] + [(f"tileOffset[{i}]", "w") for i in range(K_MAX_RANKS)],
     "b2r::ShardRegions": [(f"region[{i}]", "w") for i in range(K_MAX_RANKS)],
@@ -185,6 +187,7 @@ class Trace:
         "bin_sort_tiles_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 4},
         "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
         "shard_push_heads_kernel": {"tileCount": 0, "tileOffset": 1},
+        "shard_merge_heads_kernel": {"tileOrder": 4, "frameInfo": 5},
         "shard_push_lists_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 7},
         "publish_info_kernel": {"frameInfo": 0},
     }
@@ -219,7 +222,8 @@ class Trace:
                 for name, j in self.RASTER_ROLES.items():
                     seen[name][self._ptr(o["args"][0], j)].append(k)
             for name, j in self.ROLES.get(k, {}).items():
-                seen[name][self._ptr(o["args"][j])].append(k)
+                if self._ptr(o["args"][j]):                   # a null pointer = the kernel does not take part in that role
+                    seen[name][self._ptr(o["args"][j])].append(k)
         return seen
 
     def wiring_errors(self, ranks=1):
