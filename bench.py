@@ -234,6 +234,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class SharedHostFrames:
+    """Host memory shared by the ranks of one box (a file in /dev/shm mapped by every rank): the frame a distributed Present
+    composes.  Rank 0 creates and removes the file."""
+
+    def __init__(self, name: str, nbytes: int, rank: int, barrier):
+        import mmap
+        self.path, self.rank = os.path.join("/dev/shm", name), rank
+        if rank == 0:
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, nbytes)
+        barrier()
+        if rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self.map = mmap.mmap(fd, nbytes)
+        os.close(fd)
+        self.array = np.frombuffer(self.map, dtype=np.uint32)
+        barrier()
+
+    def close(self):
+        self.array = None
+        try:
+            self.map.close()
+        except BufferError:
+            pass
+        if self.rank == 0 and os.path.exists(self.path):
+            os.unlink(self.path)
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 ERE_REF = os.path.join(ROOT, "oracle", "_ref", "libere_ref.so")
 ERE_PORT = os.path.join(ROOT, "oracle", "liborc_erenderer.so")
@@ -380,6 +408,12 @@ def run_b200(args, scene):
 
     r = Renderer(scene.width, scene.height, device=local)
     sharded = world > 1 and args.gather == "sharded"
+    # frame ring (B2R_OPT_FRAME_RING): frame f runs on ring stream f mod D with its own buffer set, so the front ends of D
+    # consecutive frames overlap; measured best at D = 3 on one GPU and D = 4 with the sharded front end.  B2R_FRAME_RING in
+    # the environment overrides (0 = the three-stream pipeline).
+    ring = int(os.environ["B2R_FRAME_RING"]) if "B2R_FRAME_RING" in os.environ else (args.ring if args.ring >= 0 else (4 if sharded else 3))
+    if world == 1 or sharded:
+        r.set_option(_lib.OPT_FRAME_RING, ring)
     if not sharded:
         r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
         r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
@@ -467,36 +501,74 @@ def run_b200(args, scene):
     host_enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
     r.sync()
 
-    # ---- end to end through the public API: per-frame constants H2D + render + framebuffer D2H to pinned host memory
-    pinned = [torch.empty((scene.height, scene.width), dtype=torch.int32, pin_memory=True) for _ in range(2)]
-    host_fb = [p.numpy().view(np.uint32) for p in pinned]
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        frame()
-        if rank == 0:
-            # Present(): device->host copy of the (gathered) frame into pinned memory; pipelined - the copy of
-            # frame i overlaps the rendering of frame i+1 (two colour surfaces, two host buffers)
-            if world == 1 or sharded:
-                r.present_async(host_fb[i & 1])
-            else:
-                r.framebuffer(out=host_fb[i & 1])
-    if rank == 0 and (world == 1 or sharded):
+    # ---- end to end through the public API: per-frame constants H2D + render + framebuffer D2H to host memory
+    import zlib
+    frame_bytes = scene.width * scene.height * 4
+    crc_host = crc_dev = None
+    distributed = sharded and args.present != "central"
+    if distributed:
+        # Distributed Present (N > 1): the host frame lives in memory all ranks share (a /dev/shm mapping, two frames) and every
+        # rank delivers its part over its own PCIe link.  "band" (default): the frame is composed on rank 0 over NVLink as in
+        # the device-timed region and rank r copies the r-th band of rows out of rank 0's memory with its own copy engine
+        # (b2r_present_band_async).  "tiles": every rank keeps the colours of its tiles and stores them into the host frame
+        # from a kernel (b2r_present_tiles_async); nothing crosses NVLink.
+        tiles_mode = args.present == "tiles"
+        present = r.present_tiles_async if tiles_mode else r.present_band_async
+        shm = SharedHostFrames(f"b2r_bench_{os.environ.get('MASTER_PORT', '0')}", 2 * frame_bytes, rank, barrier)
+        host_fb = shm.array.reshape(2, scene.height, scene.width)
+        r.register_host_frame(shm.array)
+        if tiles_mode:
+            r.set_option(_lib.OPT_SHARD_LOCAL_COLOUR, 1)
+        for i in range(2):
+            frame()
+            present((i & 1) * frame_bytes)
         r.present_wait()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            frame()
+            present((i & 1) * frame_bytes)
+        r.present_wait()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if rank == 0:
+            crc_host = zlib.crc32(host_fb[(args.steps - 1) & 1].tobytes())
+        barrier()
+        if tiles_mode:
+            r.set_option(_lib.OPT_SHARD_LOCAL_COLOUR, 0)
+        r.register_host_frame(None)
+        host_fb = None
+        shm.close()
+        frame()                                   # a frame composed on rank 0's device again, for the device-side checksum
     else:
-        r.sync()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        pinned = [torch.empty((scene.height, scene.width), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        host_fb = [p.numpy().view(np.uint32) for p in pinned]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            frame()
+            if rank == 0:
+                # Present(): device->host copy of the (gathered) frame into pinned memory; pipelined - the copy of
+                # frame i overlaps the rendering of frame i+1 (two colour surfaces, two host buffers)
+                if world == 1 or sharded:
+                    r.present_async(host_fb[i & 1])
+                else:
+                    r.framebuffer(out=host_fb[i & 1])
+        if rank == 0 and (world == 1 or sharded):
+            r.present_wait()
+        else:
+            r.sync()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if rank == 0:
+            crc_host = zlib.crc32(host_fb[(args.steps - 1) & 1].tobytes())
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
     # correctness token of this run: CRC-32 of the frame the end-to-end region delivered into host memory and of the frame on
     # the device (N > 1: the frame the ranks composed on rank 0); compared below with a frame rank 0 renders on its own
-    import zlib
-    crc_host = crc_dev = None
     if rank == 0:
-        crc_host = zlib.crc32(host_fb[(args.steps - 1) & 1].tobytes())
         crc_dev = zlib.crc32(r.framebuffer().tobytes())
     else:
         r.sync()
@@ -621,7 +693,14 @@ def run_b200(args, scene):
                              "time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},
         "e2e": {"value": args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 64,
                 "d2h_bytes_per_step": scene.width * scene.height * 4,
-                "note": "per frame: view-projection matrix from the host (zero-copy read; per-mesh constants are built on the device) + b2r_render + device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), wall clock over all frames incl. the final wait"},
+                "note": ("per frame: view-projection matrix from the host (zero-copy read; per-mesh constants are built on the device) + b2r_render + " +
+                         ("DISTRIBUTED Present into one host frame all ranks share (/dev/shm mapping registered with cudaHostRegister): " +
+                          ("every rank stores the tiles it owns from a kernel over its own PCIe link (b2r_present_tiles_async)" if args.present == "tiles" else
+                           "rank r copies the r-th band of rows of the frame composed on rank 0 with its own copy engine over its own PCIe link (b2r_present_band_async)") +
+                          ", d2h bytes = the whole frame summed over the ranks; " if distributed else
+                          "device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), ") +
+                         "wall clock over all frames incl. the final wait and a barrier across the ranks")},
+        "frame_ring": ring if (world == 1 or sharded) else 0,
         "gpu_launches": launches_per_frame * args.steps,
         "gpu_launches_per_step": launches_per_frame,
         "host_enqueue_ms_per_frame": host_enqueue_ms,
@@ -707,6 +786,8 @@ def main():
     ap.add_argument("--workload", default="spheres10m", choices=["spheres10m", "fill64", "spheres_small", "views172", "vehicle480", "vehicle1080"])
     ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--views-mode", default="parallel", choices=["parallel", "sortfirst"], help="--workload views172 at N > 1: independent views per rank (default) or every view rendered sort-first by all ranks")
+    ap.add_argument("--present", default="band", choices=["band", "tiles", "central"], help="N > 1, end-to-end leg: distributed Present by row bands out of rank 0's surface (default) or by owned tiles, or through rank 0's PCIe link alone")
+    ap.add_argument("--ring", type=int, default=-1, help="frame ring depth (B2R_OPT_FRAME_RING): 0 = three-stream pipeline, 2..4; default 3 on one GPU, 4 with the sharded front end")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
     ap.add_argument("--ref-cuda", type=int, default=2, metavar="FRAMES", help="--impl reference only: also time the reference's own CUDA renderer (oracle/_ref/ref_render) on GPU 0 for this many frames (0 = skip)")

@@ -35,6 +35,7 @@ OPT_OVERLAP_VERTEX = 10
 OPT_OVERLAP_FRONT = 11
 OPT_FRAME_RING = 12
 OPT_SHARD_SLICED_VERTEX = 13
+OPT_SHARD_LOCAL_COLOUR = 14
 STAGE_NAMES = ("vertex", "setup", "bin_scan", "bin_scatter", "bin_sort", "raster_shade", "total", "exchange", "peer_wait")
 NUM_STAGES = 9
 
@@ -59,6 +60,9 @@ ABI = {
     "b2r_read_framebuffer": (_i32, [_vp, _vp]),
     "b2r_present_async": (_i32, [_vp, _vp]),
     "b2r_present_wait": (_i32, [_vp]),
+    "b2r_host_frame_register": (_i32, [_vp, _vp, _u64]),
+    "b2r_present_tiles_async": (_i32, [_vp, _u64]),
+    "b2r_present_band_async": (_i32, [_vp, _u64]),
     "b2r_read_depth": (_i32, [_vp, _vp]),
     "b2r_read_z": (_i32, [_vp, _vp]),
     "b2r_read_winner": (_i32, [_vp, _vp]),

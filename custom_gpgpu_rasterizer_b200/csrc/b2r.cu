@@ -995,7 +995,11 @@ int enqueueFrameRing(b2r_context* c)
 			}
 			if (!c->shardLocalColour) A.framebuffer = sh.colourBase + (size_t)(sh.frame & 1u) * c->width * c->height;
 			// "lists ready": nobody reads the lists a peer pushed before that peer has sorted and pushed them
-			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, rs, pf, (uint32_t)sh.self, (uint32_t)sh.n, 0u, sh.frame + 1u, 1u, 1u, B.frameInfo + 7, 0u));
+			// (one set of flag words per ring slot, 32 + 8 k: the barriers of consecutive frames sit on different ring streams
+			// and may run in either order - with shared words the older frame's epoch could overwrite the newer one's, and a
+			// newer epoch would release the older frame's barrier before that frame's lists have been pushed; frames of the
+			// same slot follow each other on one stream, so a slot's words rise monotonically)
+			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, rs, pf, (uint32_t)sh.self, (uint32_t)sh.n, 32u + 8u * (uint32_t)k, sh.frame + 1u, 1u, 1u, B.frameInfo + 7, 0u));
 			++c->kernelsLaunched;
 			RING_STAGE_EVENT(8);
 			A.shard = T;
@@ -1577,6 +1581,43 @@ int b2r_present_tiles_async(b2r_context* c, uint64_t byteOffset)
 	CU(c, cudaEventRecord(c->copyDone[idx], c->copyStream));
 	c->copyPending[idx] = true;
 	if (!c->shard.bound) c->colourIdx = idx ^ 1;          // the next frame renders into the other surface (sharded: frame parity)
+	return B2R_OK;
+}
+
+int b2r_present_band_async(b2r_context* c, uint64_t byteOffset)
+{
+	if (!c) return B2R_E_INVALID;
+	if (!c->haveFrame) return fail(c, B2R_E_STATE, "present_band_async: nothing rendered yet");
+	if (!c->hostFrame) return fail(c, B2R_E_STATE, "present_band_async: no host frame registered (b2r_host_frame_register)");
+	if (c->boundFramebuffer || c->packedOutput) return fail(c, B2R_E_STATE, "present_band_async: needs the row-major colour surface");
+	if (c->shard.bound && c->shardLocalColour) return fail(c, B2R_E_STATE, "present_band_async: the frame is not composed on rank 0 (B2R_OPT_SHARD_LOCAL_COLOUR is set)");
+	const uint64_t frameBytes = (uint64_t)c->width * c->height * 4;
+	if ((byteOffset & 15u) || byteOffset + frameBytes > c->hostFrameBytes) return fail(c, B2R_E_INVALID, "present_band_async: offset %llu outside the registered host frame", (unsigned long long)byteOffset);
+	CU(c, cudaSetDevice(c->device));
+	{ int r = ensureCopyStream(c); if (r) return r; }
+	b2r_context::Shard& sh = c->shard;
+	const int idx = c->lastColourIdx;
+	// this rank's band: whole rows of bins
+	const uint32_t n = sh.bound ? (uint32_t)sh.n : 1u, self = sh.bound ? (uint32_t)sh.self : 0u;
+	const uint32_t binRows = (c->binsY + n - 1) / n;
+	const uint64_t row0 = std::min<uint64_t>((uint64_t)self * binRows * c->binH, c->height), row1 = std::min<uint64_t>((uint64_t)(self + 1) * binRows * c->binH, c->height);
+	CU(c, cudaEventRecord(c->frameDone, c->stream));
+	CU(c, cudaStreamWaitEvent(c->copyStream, c->frameDone, 0));
+	const uint32_t* src = c->dColour[idx];
+	if (sh.bound)
+	{
+		// every rank's colours of the frame have landed in rank 0's surface (flag words 8..15 of rank 0's arena, polled
+		// over NVLink by the other ranks)
+		PeerFlags pf{};
+		for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]);
+		CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, c->copyStream, pf, (uint32_t)sh.self, (uint32_t)sh.n, 8u, sh.frame, 0u, 1u, sh.hTimeout, 1u));
+		src = sh.colourBase + (size_t)idx * c->width * c->height;
+	}
+	if (row1 > row0)
+		CU(c, cudaMemcpyAsync(static_cast<uint8_t*>(c->hostFrame) + byteOffset + row0 * c->width * 4, src + row0 * c->width, (row1 - row0) * c->width * 4, cudaMemcpyDeviceToHost, c->copyStream));
+	CU(c, cudaEventRecord(c->copyDone[idx], c->copyStream));
+	c->copyPending[idx] = true;
+	if (!sh.bound) c->colourIdx = idx ^ 1;          // the next frame renders into the other surface (sharded: frame parity)
 	return B2R_OK;
 }
 

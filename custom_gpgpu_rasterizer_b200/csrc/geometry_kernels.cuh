@@ -780,10 +780,11 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t
 //  depend on list order: the depth resolve is an order-independent min over (z, primitive id)).
 //  B2R_OPT_SORT_BINS = 0 leaves all lists in scatter order; b2r_read_bins then canonicalises them when they are
 //  read (bin_sort_tiles_kernel: the same CTA-level sort, one CTA per tile).
-constexpr int kStage = 2048;         // <= : staged + sorted by the tile's raster CTA
+constexpr int kStage = 3072;         // <= : staged + sorted by the tile's raster CTA (12 KB of its shared memory)
 constexpr int kSortLarge = 40960;    // <= : one CTA per SM, dynamic shared memory
 constexpr size_t kSortLongSmem = (size_t)(kSortLarge + 32 * 256 + 2 * 32 + 2) * sizeof(uint32_t);
-constexpr int kSortThreads = 256, kSortPerThread = kStage / kSortThreads;     // 8 consecutive keys per thread
+constexpr int kSortThreads = 256, kSortPerThread = kStage / kSortThreads;     // 12 consecutive keys per thread
+static_assert(kSortPerThread % 4 == 0 && kSortPerThread <= 32, "ctaSortTileList reads its keys with 16-byte loads and keeps the run flags in one word");
 constexpr int kCtaRuns = 512;        // more runs than this: bitonic fallback
 
 // exclusive scan of one value per thread over a 256-thread CTA; *total receives the block sum
@@ -807,30 +808,47 @@ __device__ __forceinline__ uint32_t blockExclusiveScan256(uint32_t v, uint32_t* 
 	return sWarp[warp] + incl - v;
 }
 
-// Bitonic network over the n <= kStage keys staged in K (capacity kStage), padded to a power of two; the sorted keys are
-// stored through put(position, key).  All 256 threads call it.  Short lists are sorted by one warp alone (no CTA barriers).
+// Bitonic network over the n <= kStage keys staged in K; the sorted keys are stored through put(position, key).  All 256
+// threads call it.  The network is the all-ascending ("flip") formulation - every compare-exchange moves the smaller key
+// to the lower index - so n need not be a power of two: the positions from n to the next power of two hold a virtual
+// +infinity and exchanges with them are skipped.  Short lists are sorted by one warp alone (no CTA barriers).
 template <typename Put>
 __device__ __forceinline__ void ctaBitonicSortList(uint32_t* K, uint32_t n, Put put)
 {
 	const uint32_t tid = threadIdx.x;
 	uint32_t P = 2;
 	while (P < n) P <<= 1;
-	for (uint32_t i = n + tid; i < P; i += kSortThreads) K[i] = 0xFFFFFFFFu;
-	__syncthreads();
 	const bool oneWarp = P <= 256u;
 	const uint32_t workers = oneWarp ? 32u : (uint32_t)kSortThreads;
 	if (!oneWarp || tid < 32u)
 		for (uint32_t k = 2; k <= P; k <<= 1)
-			for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			// flip: element off of the lower half of a k-block against its mirror image in the upper half
+			for (uint32_t idx = tid; idx < (P >> 1); idx += workers)
+			{
+				const uint32_t half = k >> 1, blockBase = (idx / half) * k, off = idx & (half - 1u);
+				const uint32_t i = blockBase + off, p = blockBase + k - 1u - off;
+				if (p < n)
+				{
+					const uint32_t x = K[i], y = K[p];
+					if (x > y) { K[i] = y; K[p] = x; }
+				}
+			}
+			if (oneWarp) __syncwarp(); else __syncthreads();
+			for (uint32_t j = k >> 2; j > 0; j >>= 1)
 			{
 				for (uint32_t idx = tid; idx < (P >> 1); idx += workers)
 				{
-					const uint32_t i = ((idx & ~(j - 1u)) << 1) | (idx & (j - 1u)), p = i | j;
-					const uint32_t x = K[i], y = K[p];
-					if ((x > y) == ((i & k) == 0u)) { K[i] = y; K[p] = x; }
+					const uint32_t i = ((idx & ~(j - 1u)) << 1) | (idx & (j - 1u)), p = i + j;
+					if (p < n)
+					{
+						const uint32_t x = K[i], y = K[p];
+						if (x > y) { K[i] = y; K[p] = x; }
+					}
 				}
 				if (oneWarp) __syncwarp(); else __syncthreads();
 			}
+		}
 	if (oneWarp) __syncthreads();
 	for (uint32_t i = tid; i < n; i += kSortThreads) put(i, K[i]);
 }
@@ -947,8 +965,12 @@ __device__ __forceinline__ int ctaSortTileList(uint32_t* K, uint32_t n, SortScra
 	int descent = 0;
 	if (first < n)
 	{
-		const uint4 a = *reinterpret_cast<const uint4*>(K + first), b = *reinterpret_cast<const uint4*>(K + first + 4);
-		key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
+		#pragma unroll
+		for (int q = 0; q < kSortPerThread / 4; ++q)
+		{
+			const uint4 a = *reinterpret_cast<const uint4*>(K + first + 4 * q);
+			key[4 * q] = a.x; key[4 * q + 1] = a.y; key[4 * q + 2] = a.z; key[4 * q + 3] = a.w;
+		}
 		uint32_t prev = first ? K[first - 1] : 0u;
 		#pragma unroll
 		for (uint32_t k = 0; k < (uint32_t)kSortPerThread; ++k)

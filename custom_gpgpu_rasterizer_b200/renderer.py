@@ -192,6 +192,23 @@ class Renderer:
         """Pipelined Present: start copying the newest frame into `out` (pinned), do not wait."""
         self._check(lib.b2r_present_async(self._ctx, out.ctypes.data))
 
+    def register_host_frame(self, frame: Optional[np.ndarray]):
+        """Distributed Present: page-lock and map `frame` (host memory all ranks share, e.g. a /dev/shm mapping; at least
+        width*height uint32) for this context's device; None releases it."""
+        if frame is None:
+            self._check(lib.b2r_host_frame_register(self._ctx, None, 0))
+        else:
+            self._check(lib.b2r_host_frame_register(self._ctx, frame.ctypes.data, frame.nbytes))
+
+    def present_tiles_async(self, byte_offset: int = 0):
+        """Start copying the tiles this rank owns of the newest frame into the registered host frame (+ byte_offset)."""
+        self._check(lib.b2r_present_tiles_async(self._ctx, int(byte_offset)))
+
+    def present_band_async(self, byte_offset: int = 0):
+        """Sharded front end: start copying this rank's band of rows of the frame composed on rank 0 into the registered host
+        frame (+ byte_offset) with this rank's own copy engine / PCIe link."""
+        self._check(lib.b2r_present_band_async(self._ctx, int(byte_offset)))
+
     def present_wait(self):
         self._check(lib.b2r_present_wait(self._ctx))
 

@@ -184,6 +184,16 @@ int b2r_present_wait(b2r_context* ctx);
  * needs a barrier across the ranks.  With the sharded front end use B2R_OPT_SHARD_LOCAL_COLOUR. */
 int b2r_host_frame_register(b2r_context* ctx, void* host, uint64_t bytes);
 int b2r_present_tiles_async(b2r_context* ctx, uint64_t byte_offset);
+/* Distributed Present of the sharded front end in its default form (frame composed in rank 0's surface over NVLink):
+ * rank r copies the r-th band of tile rows of the composed frame - a contiguous range of the row-major surface - from
+ * rank 0's memory (mapped on every rank by b2r_shard_bind) into the registered host frame at host + byte_offset,
+ * with its own copy engine over its own PCIe link, after waiting (on the device) until every rank's colours of the
+ * frame have landed on rank 0.  All ranks call it after the same b2r_render; the n bands make up the frame.
+ * b2r_present_wait blocks until this rank's band has landed; a consumer needs a barrier across the ranks.  A rank's
+ * next frame of the same parity waits for this rank's copy before it arrives at the frame's "lists ready" barrier,
+ * so no rank overwrites the surface while any band of it is still being read.  On a context without a sharded group
+ * the band is the whole frame. */
+int b2r_present_band_async(b2r_context* ctx, uint64_t byte_offset);
 /* depth buffer as the reference keeps it (int z*2^31, INT_MAX = empty; CUDAROPs.cu:386, CUDARenderer.cu:1640) */
 int b2r_read_depth(b2r_context* ctx, int32_t* out);
 /* parity surfaces (need B2R_OPT_DEBUG_SURFACES=1 before the render): PixelShade.zInterpolated

@@ -136,6 +136,40 @@ def sharded(world, mode, n_meshes=2, n_tris=700):
     want = oracle_lib.bin_sets(wants[-1]["bin_counts"], wants[-1]["bin_ids"])
     res["lists"] = bool(np.array_equal(np.concatenate(cat), np.concatenate(want)))
     res["visible"] = int(sum(r.stats()[1] for r in ranks)) == int(wants[-1]["visible_tris"])
+    # distributed Present: every rank keeps its tiles' colours and copies them into ONE host frame all ranks share
+    # (b2r_present_tiles_async); two frames in flight into the two halves of the host buffer
+    shared = np.zeros((2, sc.height, sc.width), np.uint32)
+    for r in ranks:
+        r.sync()
+    for r in ranks:
+        r.register_host_frame(shared)
+        r.set_option(_lib.OPT_SHARD_LOCAL_COLOUR, 1)
+    for i in (2, 5):
+        for r in ranks:
+            r.render_scene(cams[i], sync=False)
+            r.present_tiles_async((i & 1) * sc.width * sc.height * 4)
+    for r in ranks:
+        r.present_wait()
+    res["distributed_present"] = bool(np.array_equal(shared[0], wants[2]["framebuffer"]) and np.array_equal(shared[1], wants[5]["framebuffer"]))
+    for r in ranks:
+        r.set_option(_lib.OPT_SHARD_LOCAL_COLOUR, 0)
+        r.register_host_frame(None)
+    # ... and by row bands out of the frame composed on rank 0 (b2r_present_band_async), again two frames in flight
+    shared[:] = 0
+    for r in ranks:
+        r.register_host_frame(shared)
+    for i in (4, 1):
+        for r in ranks:
+            r.render_scene(cams[i], sync=False)
+            r.present_band_async((i & 1) * sc.width * sc.height * 4)
+    for r in ranks:
+        r.present_wait()
+    res["band_present"] = bool(np.array_equal(shared[0], wants[4]["framebuffer"]) and np.array_equal(shared[1], wants[1]["framebuffer"]))
+    for r in ranks:
+        r.register_host_frame(None)
+    for r in ranks:
+        r.render_scene(cams[3], sync=False)
+    res["composed_on_rank0_again"] = bool(np.array_equal(ranks[0].framebuffer(), wants[3]["framebuffer"]))
     for r in ranks:
         r.sync()
     for r in ranks:

@@ -133,6 +133,16 @@ class _FakeRenderer:
     def present_wait(self):
         pass
 
+    def register_host_frame(self, frame):
+        self.host_frame = frame
+
+    def present_band_async(self, byte_offset=0):
+        self.present_tiles_async(byte_offset)
+
+    def present_tiles_async(self, byte_offset=0):
+        n = self.w * self.h
+        self.host_frame[byte_offset // 4: byte_offset // 4 + n] = self.framebuffer().reshape(-1)
+
     def framebuffer(self, out=None):
         return np.zeros((self.h, self.w), np.uint32)
 

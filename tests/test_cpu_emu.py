@@ -94,6 +94,7 @@ def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode, meshe
     res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world)), "sharded", str(world), mode, str(meshes), str(tris))
     assert all(res["frames"]) and len(res["frames"]) == 7, res
     assert res["last_framebuffer"] and res["lists"] and res["visible"], res
+    assert res["distributed_present"] and res["band_present"] and res["composed_on_rank0_again"], res
 
 
 @pytest.mark.skipif(not SLOW, reason="other stream visiting orders of the emulated executor (set B2R_SLOW_TESTS=1)")

@@ -17,7 +17,7 @@ CUDAINC="${CUDAINC:-/usr/local/cuda/include}"
 mkdir -p "$OUT/src"
 python3 "$HERE/preprocess.py" "$CSRC" "$OUT/src"
 g++ -O1 -g -std=c++17 -fPIC -shared $SAN -o "$OUT/libemu_runtime.so" "$HERE/emu_runtime.cpp"
-FLAGS=(-std=c++17 ${SAN:--O2} ${SAN:+-O1} -fPIC -ffp-contract=off -mfma -fno-fast-math -w -I"$CUDAINC" -I"$CSRC" -I"$ROOT/include")
+FLAGS=(${B2R_EMU_EXTRA:-} -std=c++17 ${SAN:--O2} ${SAN:+-O1} -fPIC -ffp-contract=off -mfma -fno-fast-math -w -I"$CUDAINC" -I"$CSRC" -I"$ROOT/include")
 g++ "${FLAGS[@]}" -include "$HERE/emu_cuda.h" -c "$OUT/src/b2r.cpp" -o "$OUT/b2r.o"
 g++ "${FLAGS[@]}" -c "$CSRC/host/b2r_scene.cpp" -o "$OUT/b2r_scene.o"
 g++ -shared $SAN -o "$OUT/libb2r_emu.so" "$OUT/b2r.o" "$OUT/b2r_scene.o" -lz -L"$OUT" -lemu_runtime -Wl,-rpath,"$OUT"

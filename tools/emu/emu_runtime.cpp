@@ -131,7 +131,21 @@ void drain()
 }
 void requireEmpty(Stream* s, const char* what)
 {
-	if (s && !s->q.empty()) { fprintf(stderr, "emu runtime: deadlock - %s: stream %d (device %d) still has %zu operations that can never run\n", what, s->id, s->dev, s->q.size()); abort(); }
+	if (s && !s->q.empty())
+	{
+		fprintf(stderr, "emu runtime: deadlock - %s: stream %d (device %d) still has %zu operations that can never run\n", what, s->id, s->dev, s->q.size());
+		static const char* names[] = { "kernel", "copy", "memset", "record", "wait" };
+		for (Stream* t : g_streams)
+			if (!t->q.empty())
+			{
+				const Op& op = t->q.front();
+				fprintf(stderr, "  stream %d (device %d): %zu ops, head = %s", t->id, t->dev, t->q.size(), names[op.type]);
+				if (op.type == Op::WAIT) fprintf(stderr, " event %p seq %llu (completed %llu)", (void*)op.event, (unsigned long long)op.seq, (unsigned long long)op.event->completed);
+				if (op.type == Op::KERNEL) fprintf(stderr, " fn %p started %d", (void*)op.kernel->fn, (int)op.kernel->started);
+				fprintf(stderr, "\n");
+			}
+		abort();
+	}
 }
 Stream* legacy(int dev)
 {

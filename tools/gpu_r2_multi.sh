@@ -23,7 +23,7 @@ run() {   # name, env...
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print("  ", round(d["value"],1), "fps | e2e", round(d["e2e"]["value"],1), "| view-parallel", round(d["view_parallel"]["value"],1), "|", d.get("stages_ms_per_rank",[None])[0])
+    print("  ", round(d["value"],1), "fps | e2e", round(d["e2e"]["value"],1), "| crc", d["checksum"]["match"], "| view-parallel", round(d["view_parallel"]["value"],1), "|", d.get("stages_ms_per_rank",[None])[0])
 except Exception as e: print("   no bench line:", e)
 PY
 }
@@ -31,11 +31,23 @@ run default B2R_FRAME_RING=0
 run ring3 B2R_FRAME_RING=3
 run ring4 B2R_FRAME_RING=4
 run ring3_sliced B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1
-run ring4_sliced B2R_FRAME_RING=4 B2R_SHARD_SLICED_VERTEX=1
-# programmatic dependent launch parks the next kernel's CTAs on SM slots while the current kernel's tail drains: good for one
-# stream, possibly bad when other ring streams have runnable work; more hardware queues avoid false dependencies between streams
-run ring3_sliced_nopdl B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 B2R_PDL=0
-#run ring3_sliced_conn32 B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 CUDA_DEVICE_MAX_CONNECTIONS=32
+# the end-to-end leg through rank 0 alone (colours over NVLink, one PCIe link) next to the distributed Present of the lines above
+port=$((port + 1))
+B2R_FRAME_RING=3 timeout 240 $TR --master-port $port bench.py --gpus $N --steps 60 --warmup 5 --present central > $O/bench_ring3_central.json 2> $O/bench_ring3_central.err
+python - "$O/bench_ring3_central.json" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print("== ring3, central Present: e2e", round(d["e2e"]["value"],1), "crc", d["checksum"]["match"])
+except Exception as e: print("   no bench line:", e)
+PY
+port=$((port + 1))
+B2R_FRAME_RING=3 timeout 240 $TR --master-port $port bench.py --gpus $N --steps 60 --warmup 5 --present tiles > $O/bench_ring3_tiles.json 2> $O/bench_ring3_tiles.err
+python - "$O/bench_ring3_tiles.json" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print("== ring3, Present by tiles: e2e", round(d["e2e"]["value"],1), "crc", d["checksum"]["match"])
+except Exception as e: print("   no bench line:", e)
+PY
 # BASELINE config 5 at N ranks: view-parallel (no communication) and sort-first per view (sharded front end, moving camera)
 for m in parallel sortfirst; do
 	port=$((port + 1))
@@ -44,5 +56,3 @@ for m in parallel sortfirst; do
 import json
 d=json.loads(open('$O/views_$m.json').read().strip().splitlines()[-1]); print(round(d['value'],1), d['unit'], 'e2e', round(d['e2e']['value'],1))" 2>&1 | tail -1)"
 done
-# the on-the-fly raster variant at 4 resident CTAs per SM (no register spills) - build it first with tools/build_variants.sh
-[ -f build/variants/libb2r_otf4.so ] && run ring3_sliced_otf4 B2R_FRAME_RING=3 B2R_SHARD_SLICED_VERTEX=1 B2R_LIBRARY=$PWD/build/variants/libb2r_otf4.so
