@@ -430,8 +430,10 @@ def run_b200(args, scene):
         from custom_gpgpu_rasterizer_b200.multi_gpu import ShardedSortFirst, SortFirstGather
         gather = ShardedSortFirst(r, rank, world) if sharded else SortFirstGather(r, scene, rank, world, stream, mode=args.gather)
 
+    prepared = r.prepare_camera(cam)          # the camera marshalled once: the frame loop is one ctypes call per frame
+
     def frame():
-        r.render(cam, scene.cull, scene.sample, scene.vis, sync=False)
+        r.render_prepared(prepared, scene.cull, scene.sample, scene.vis)
         if gather is not None:
             gather.run()
 

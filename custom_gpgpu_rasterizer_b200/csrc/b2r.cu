@@ -140,6 +140,7 @@ struct b2r_context
 	bool ringNeedsFork[kMaxFrameRing] = {};
 	int ringPrev = -1;                 // ring slot of the previous frame while it may still be in flight
 	uint32_t* dRangeScratch = nullptr;
+	DeviceVec<uint4> dVertexMarks[kMaxFrameRing];   // sliced vertex stage: one bit per transformed vertex, per ring slot
 	int slicedVertex = 0;              // sharded front end: transform only the vertices of this rank's primitive slice;
 	                                   // the raster kernel transforms the vertices of its list entries itself (B2R_SHARD_SLICED_VERTEX)
 	int overlapFrontSharded = 1;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=0 switches it off)
@@ -162,9 +163,14 @@ struct b2r_context
 		cudaEvent_t done = nullptr;
 		cudaEvent_t ev[10] = {};                    // 0..6 stage boundaries; sharded: 7 after pull, 8 after barrier A, 9 after raster
 		bool pending = false, timed = false, exchanged = false;
+		bool longSkipped = false;                   // the frame was enqueued without the long-list sorter (see longLikely)
 	} slots[kRing];
 	uint64_t seq = 0;
 	HostInfo lastInfo{};                           // info of the newest harvested frame
+	// Lists longer than kStage are sorted by a kernel of their own (bin_sort_long_kernel), which costs a launch per frame.
+	// It is only enqueued while the newest harvested frame of the scene had such lists (or none has been harvested yet);
+	// a frame that turns out to have them after all gets its long lists canonicalised when they are read.
+	bool longLikely = true, lastLongSkipped = false;
 	size_t overflowNeed = 0;
 	double stageAccum[B2R_NUM_STAGES] = {};
 	float stageLast[B2R_NUM_STAGES] = {};
@@ -302,6 +308,7 @@ int setBins(b2r_context* c, uint32_t bx, uint32_t by, uint32_t bw, uint32_t bh)
 		return fail(c, B2R_E_INVALID, "%ux%u bins = %llu tiles exceed the %llu the tile scan is sized for", bx, by,
 			(unsigned long long)bx * by, (unsigned long long)kScanMaxCtas * kScanPerCta);
 	c->binsX = bx; c->binsY = by; c->binW = bw; c->binH = bh;
+	c->longLikely = true;
 	return reserveBinSet(c, c->bins[0]);
 }
 
@@ -342,6 +349,7 @@ int rebuildScene(b2r_context* c)
 	for (auto& B : c->bins)
 		if (B.frameInfo) { int r = reserveBinSet(c, B); if (r) return r; }
 	c->sceneDirty = false;
+	c->longLikely = true;
 	return B2R_OK;
 }
 
@@ -397,25 +405,21 @@ cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 g
 }
 
 // the raster kernel instantiation of a frame: fill rule, fragment counter, light variant (the frame cannot reach the
-// texture / visualiser paths), positions transformed on the fly (sharded front end with a sliced vertex stage)
+// texture / visualiser paths)
 // `blocks` = the 16x16 pixel blocks of the frame, an upper bound of the kernel's work items (CTAs behind the last item leave at once)
-cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool onTheFly)
+cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured)
 {
-	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (onTheFly ? 8 : 0);
+	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0);
 	const dim3 block(kTile * kTile);
 	const dim3 grid(blocks);
-#define B2R_RASTER_CASE(v, tl, cnt, tex, otf) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, otf>, grid, block, 0, s, A, fp);
+#define B2R_RASTER_CASE(v, tl, cnt, tex) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex>, grid, block, 0, s, A, fp);
 	switch (variant)
 	{
-	B2R_RASTER_CASE(0, false, false, false, false) B2R_RASTER_CASE(1, true, false, false, false)
-	B2R_RASTER_CASE(2, false, true, false, false)  B2R_RASTER_CASE(3, true, true, false, false)
-	B2R_RASTER_CASE(4, false, false, true, false)  B2R_RASTER_CASE(5, true, false, true, false)
-	B2R_RASTER_CASE(6, false, true, true, false)   B2R_RASTER_CASE(7, true, true, true, false)
-	B2R_RASTER_CASE(8, false, false, false, true)  B2R_RASTER_CASE(9, true, false, false, true)
-	B2R_RASTER_CASE(10, false, true, false, true)  B2R_RASTER_CASE(11, true, true, false, true)
-	B2R_RASTER_CASE(12, false, false, true, true)  B2R_RASTER_CASE(13, true, false, true, true)
-	B2R_RASTER_CASE(14, false, true, true, true)
-	default: return launchFrameKernel(c, raster_shade_kernel<true, true, true, true>, grid, block, 0, s, A, fp);
+	B2R_RASTER_CASE(0, false, false, false) B2R_RASTER_CASE(1, true, false, false)
+	B2R_RASTER_CASE(2, false, true, false)  B2R_RASTER_CASE(3, true, true, false)
+	B2R_RASTER_CASE(4, false, false, true)  B2R_RASTER_CASE(5, true, false, true)
+	B2R_RASTER_CASE(6, false, true, true)
+	default: return launchFrameKernel(c, raster_shade_kernel<true, true, true>, grid, block, 0, s, A, fp);
 	}
 #undef B2R_RASTER_CASE
 }
@@ -427,6 +431,8 @@ int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
 {
 	slot.pending = false;
 	c->lastInfo = *slot.hInfo;
+	c->longLikely = slot.hInfo->frameInfo[3] != 0;
+	c->lastLongSkipped = slot.longSkipped;
 	if (slot.hInfo->frameInfo[1])
 		c->overflowNeed = std::max(c->overflowNeed, (size_t)slot.hInfo->frameInfo[0]);
 	if (slot.hInfo->frameInfo[7])
@@ -625,7 +631,7 @@ int enqueueFrame(b2r_context* c)
 	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (clearMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
 	CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(clearCtas), dim3(256), 0, fs, tileCount, tiles, B.counters, B.frameInfo, (uint32_t)kInfoWords,
 		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
-		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes));
+		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes, (uint4*)nullptr, 0u, PeerFlags{}, 0u, 0u, 0u));
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks && !overlap)
@@ -646,20 +652,19 @@ int enqueueFrame(b2r_context* c)
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 2);
-	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, fs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
-		(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
-		(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, B.frameInfo));
-	++c->kernelsLaunched;
-	if (sh.bound)
 	{
-		// the heads of this rank's lists go to the tiles' owners now, so the transfer hides behind scatter + sort
+		// sharded: the heads of this rank's lists go to the tiles' owners from the scan kernel itself, so the transfer hides
+		// behind scatter + push of the lists
 		ShardInbox inbox{};
-		for (int p = 0; p < sh.n; ++p)
-		{
-			uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
-			inbox.tileCount[p] = sh.inboxCount(base, set, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, set, sh.self);
-		}
-		CU(c, launchFrameKernel(c, shard_push_heads_kernel, dim3((tiles + 255) / 256), dim3(256), 0, fs, tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n));
+		if (sh.bound)
+			for (int p = 0; p < sh.n; ++p)
+			{
+				uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
+				inbox.tileCount[p] = sh.inboxCount(base, set, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, set, sh.self);
+			}
+		CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, fs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
+			(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
+			(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, inbox, sh.bound ? (uint32_t)sh.n : 0u, B.frameInfo));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 3);
@@ -674,9 +679,10 @@ int enqueueFrame(b2r_context* c)
 		}
 	}
 	STAGE_EVENT(c, slot, 4);
-	if (c->sortBins && c->nPrims)
+	const bool bigBins = c->binW > (uint32_t)kTile || c->binH > (uint32_t)kTile;
+	slot.longSkipped = c->sortBins && c->nPrims && !bigBins && !c->longLikely;
+	if (c->sortBins && c->nPrims && !slot.longSkipped)
 	{
-		const bool bigBins = c->binW > (uint32_t)kTile || c->binH > (uint32_t)kTile;
 		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs, bigBins); if (r) return r;
 		c->kernelsLaunched += bigBins ? 2 : 1;
 	}
@@ -698,7 +704,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
@@ -742,7 +748,7 @@ int enqueueFrame(b2r_context* c)
 		if (owned)
 		{
 			// light variant when the frame cannot reach the texture / visualiser paths
-			CU(c, launchRaster(c, owned * fp.subX * fp.subY, s, A, fp, rc.vis != 0 || c->anyDiffuse, false));
+			CU(c, launchRaster(c, owned * fp.subX * fp.subY, s, A, fp, rc.vis != 0 || c->anyDiffuse));
 			++c->kernelsLaunched;
 		}
 		// the vertex stage of frame f+2 may overwrite pos4 / constants of this parity once this raster is done
@@ -833,9 +839,12 @@ int enqueueFrameRing(b2r_context* c)
 		primLo = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)sh.self / (uint64_t)sh.n * kChunk);
 		primHi = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)(sh.self + 1) / (uint64_t)sh.n * kChunk);
 	}
-	// sliced vertex stage (sharded only): this rank transforms the vertex chunks its primitive slice refers to, and
-	// its raster kernel transforms the vertices of its list entries itself (OTF instantiations)
+	// sliced vertex stage (sharded only): this rank transforms the vertex chunks its primitive slice refers to before it
+	// bins, and - after the exchange - the vertices the lists of its own tiles refer to (shard_mark_vertices_kernel,
+	// vertex_transform_marked_kernel)
 	const bool sliced = sh.bound && c->slicedVertex;
+	const uint32_t markQuads = sliced ? (uint32_t)((c->nVtxOut + 127) / 128) : 0u;
+	if (sliced) CU(c, c->dVertexMarks[k].reserve(std::max<size_t>(markQuads, 1), s));
 	if (sliced && !sh.rangeValid)
 	{
 		sh.chunkLo = sh.chunkHi = 0;
@@ -892,6 +901,9 @@ int enqueueFrameRing(b2r_context* c)
 	}
 #define RING_STAGE_EVENT(i) do { if (slot.timed) CU(c, cudaEventRecord(slot.ev[(i)], rs)); } while (0)
 	RING_STAGE_EVENT(0);
+	PeerFlags pf{};
+	if (sh.bound)
+		for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(p == sh.self ? sh.arena : sh.peerArena[p]);
 	const uint32_t nMeshes = (uint32_t)c->meshes.size();
 	c->geoIdx = k;
 	float4* pos4 = c->dPos4[k].ptr;
@@ -901,7 +913,8 @@ int enqueueFrameRing(b2r_context* c)
 		const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (nMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
 		CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(std::max<uint32_t>(clearCtas, 1u)), dim3(256), 0, rs, tileCount, tiles, B.counters, B.frameInfo, (uint32_t)kInfoWords,
 			kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
-			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
+			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes, sliced ? c->dVertexMarks[k].ptr : (uint4*)nullptr, markQuads,
+			pf, (uint32_t)sh.self, (sh.bound && sh.frame >= (uint32_t)D) ? (uint32_t)sh.n : 0u, sh.frame - (uint32_t)D + 1u));
 		++c->kernelsLaunched;
 		const uint32_t cLo = sliced ? sh.chunkLo : 0u, cHi = sliced ? sh.chunkHi : c->nVsChunks;
 		if (cHi > cLo)
@@ -923,27 +936,17 @@ int enqueueFrameRing(b2r_context* c)
 		++c->kernelsLaunched;
 	}
 	RING_STAGE_EVENT(2);
-	CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, rs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
-		(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
-		(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, B.frameInfo));
-	++c->kernelsLaunched;
-	PeerFlags pf{};
-	if (sh.bound)
 	{
-		for (int p = 0; p < sh.n; ++p) pf.flags[p] = reinterpret_cast<uint32_t*>(p == sh.self ? sh.arena : sh.peerArena[p]);
-		// the peers must have finished frame f-D (their raster kernels read the set this frame is about to store into)
-		if (sh.frame >= (uint32_t)D)
-		{
-			CU(c, launchFrameKernel(c, peer_barrier_kernel, dim3(1), dim3(32), 0, rs, pf, (uint32_t)sh.self, (uint32_t)sh.n, 16u, sh.frame - (uint32_t)D + 1u, 0u, 1u, B.frameInfo + 7, 0u));
-			++c->kernelsLaunched;
-		}
 		ShardInbox inbox{};
-		for (int p = 0; p < sh.n; ++p)
-		{
-			uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
-			inbox.tileCount[p] = sh.inboxCount(base, k, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, k, sh.self);
-		}
-		CU(c, launchFrameKernel(c, shard_push_heads_kernel, dim3((tiles + 255) / 256), dim3(256), 0, rs, tileCount, tileOffset, tiles, inbox, (uint32_t)sh.n));
+		if (sh.bound)
+			for (int p = 0; p < sh.n; ++p)
+			{
+				uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
+				inbox.tileCount[p] = sh.inboxCount(base, k, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, k, sh.self);
+			}
+		CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, rs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
+			(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
+			(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, inbox, sh.bound ? (uint32_t)sh.n : 0u, B.frameInfo));
 		++c->kernelsLaunched;
 	}
 	RING_STAGE_EVENT(3);
@@ -955,9 +958,10 @@ int enqueueFrameRing(b2r_context* c)
 		++c->kernelsLaunched;
 	}
 	RING_STAGE_EVENT(4);
-	if (c->sortBins && c->nPrims)
+	const bool bigBins = c->binW > (uint32_t)kTile || c->binH > (uint32_t)kTile;
+	slot.longSkipped = c->sortBins && c->nPrims && !bigBins && !c->longLikely;
+	if (c->sortBins && c->nPrims && !slot.longSkipped)
 	{
-		const bool bigBins = c->binW > (uint32_t)kTile || c->binH > (uint32_t)kTile;
 		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs, bigBins); if (r) return r;
 		c->kernelsLaunched += bigBins ? 2 : 1;
 	}
@@ -972,7 +976,7 @@ int enqueueFrameRing(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		if (sh.bound) c->colourIdx = (int)(sh.frame & 1u);       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
@@ -1007,6 +1011,14 @@ int enqueueFrameRing(b2r_context* c)
 			{
 				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo));
 				++c->kernelsLaunched;
+				if (sliced && c->nVsChunks)
+				{
+					CU(c, launchFrameKernel(c, shard_mark_vertices_kernel, dim3((owned + 7) / 8), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, c->dTriRefs.ptr,
+						reinterpret_cast<uint32_t*>(c->dVertexMarks[k].ptr), B.frameInfo));
+					CU(c, launchFrameKernel(c, vertex_transform_marked_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, rs, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4,
+						reinterpret_cast<const uint32_t*>(c->dVertexMarks[k].ptr), sh.chunkLo, sh.chunkHi, B.frameInfo));
+					c->kernelsLaunched += 2;
+				}
 			}
 			RING_STAGE_EVENT(7);
 		}
@@ -1015,7 +1027,7 @@ int enqueueFrameRing(b2r_context* c)
 		if (!waitedPrev && c->ringPrev >= 0 && c->ringPrev != k) CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0));
 		if (owned)
 		{
-			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse, sliced));
+			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse));
 			++c->kernelsLaunched;
 		}
 		if (sh.bound)
@@ -1239,6 +1251,7 @@ void b2r_destroy(b2r_context* c)
 		if (c->ringDone[i]) cudaEventDestroy(c->ringDone[i]);
 	}
 	cudaFree(c->dRangeScratch);
+	for (auto& v : c->dVertexMarks) v.release();
 	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->frontDone[i]) cudaEventDestroy(c->frontDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
@@ -1677,15 +1690,16 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	const uint64_t pairs = c->lastInfo.frameInfo[0];
 	if (total) *total = pairs;
 	const uint32_t n = nBins(c);
-	if (ids && !c->curSorted && c->curSet && c->nPrims && !c->lastInfo.frameInfo[1])
+	const bool longLeft = c->sortBins && c->lastLongSkipped && c->lastInfo.frameInfo[3] != 0;      // the frame ran without the long-list sorter but had long lists
+	if (ids && (!c->curSorted || longLeft) && c->curSet && c->nPrims && !c->lastInfo.frameInfo[1])
 	{
 		// B2R_OPT_SORT_BINS = 0: the frame left the lists in scatter order (the image does not depend on it);
 		// whoever looks at them gets the canonical order - sort the newest frame's lists now, in place
-		r = enqueueListSort(c, *c->curSet, c->curTileCount, c->curTileOffset, c->curBinIds, c->stream, true); if (r) return r;
+		r = enqueueListSort(c, *c->curSet, c->curTileCount, c->curTileOffset, c->curBinIds, c->stream, !c->curSorted); if (r) return r;
 		CU(c, cudaStreamSynchronize(c->stream));
 		// counters of the sorter (tiles beyond its reach, fallbacks) as after an in-frame sort
 		CU(c, cudaMemcpy(c->lastInfo.frameInfo, c->curSet->frameInfo, sizeof(c->lastInfo.frameInfo), cudaMemcpyDeviceToHost));
-		c->curSorted = true;
+		c->curSorted = true; c->lastLongSkipped = false;
 	}
 	if (counts) CU(c, cudaMemcpy(counts, c->curTileCount, (size_t)n * 4, cudaMemcpyDeviceToHost));
 	if (offsets) CU(c, cudaMemcpy(offsets, c->curTileOffset, (size_t)n * 4, cudaMemcpyDeviceToHost));

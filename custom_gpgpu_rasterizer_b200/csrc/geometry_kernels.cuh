@@ -76,6 +76,28 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 	pos4[(size_t)ch.outStart + threadIdx.x] = transformPosition(sMat, in.x, in.y, in.z);
 }
 
+// sharded front end with a sliced vertex stage: the vertices shard_mark_vertices_kernel marked for this rank's raster
+// kernel (one bit per transformed vertex), chunks [skipLo, skipHi) excepted - the rank's own slice, transformed before
+// binning.  Same function, same bits as vertex_transform_kernel.
+__global__ void __launch_bounds__(kChunk) vertex_transform_marked_kernel(
+	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes, const float4* __restrict__ posIn, float4* __restrict__ pos4,
+	const uint32_t* __restrict__ marks, uint32_t skipLo, uint32_t skipHi, const unsigned long long* __restrict__ frameInfo)
+{
+	pdlPrologue();
+	if (frameInfo[1]) return;
+	if (blockIdx.x >= skipLo && blockIdx.x < skipHi) return;
+	__shared__ float sMat[16];
+	const Chunk ch = chunks[blockIdx.x];
+	const uint32_t v = ch.outStart + threadIdx.x;
+	const bool want = threadIdx.x < ch.count && ((__ldg(marks + (v >> 5)) >> (v & 31u)) & 1u);
+	if (!__syncthreads_or(want)) return;
+	if (threadIdx.x < 16) sMat[threadIdx.x] = meshes[ch.mesh].wvp[threadIdx.x];
+	float4 in = make_float4(0.f, 0.f, 0.f, 1.f);
+	if (want) in = __ldg(posIn + (size_t)ch.inStart + threadIdx.x);
+	__syncthreads();
+	if (want) pos4[v] = transformPosition(sMat, in.x, in.y, in.z);
+}
+
 // sharded front end with a sliced vertex stage: the range of transformed-vertex indices the primitives
 // [primLo, primHi) refer to (static: evaluated once per scene and slice).  out[0] = min (preset to 0xFFFFFFFF), out[1] = max (preset to 0)
 __global__ void __launch_bounds__(256) prim_vertex_range_kernel(const uint4* __restrict__ triRefs, uint32_t primLo, uint32_t primHi, uint32_t* __restrict__ out)
@@ -209,16 +231,43 @@ __device__ __forceinline__ void buildMeshConsts(uint32_t gtid, uint32_t gsize, c
 	for (uint32_t m = gtid; m < nMeshes; m += gsize) buildMeshConst(vp, meshStatic[m], meshConst[m]);
 }
 
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+// one warp: spin until the flag words [slotBase, slotBase + n) of this rank have reached `epoch` (stored by the peers over
+// NVLink); a peer that never arrives raises *timeoutFlag after ~4 s instead of hanging the GPU
+__device__ __forceinline__ void peerFlagsWait(PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch, unsigned long long* timeoutFlag)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	if (lane < n)
+	{
+		const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(pf.flags[self] + slotBase + lane);
+		const unsigned long long t0 = globalTimerNs();
+		while ((int)(*f - epoch) < 0)
+		{
+			if (globalTimerNs() - t0 > 4000000000ull) { *timeoutFlag = 1ull; break; }
+			__nanosleep(64);
+		}
+	}
+	__threadfence_system();
+}
+
 // start of frame: zero the tile counts (tileCount is padded to a multiple of 4 words) and the counters, and
 // build the per-mesh constants.  Together with publish_info_kernel this keeps the frame off the copy engines,
 // which belong to Present: a cudaMemcpyAsync here can be queued behind the previous frame's 33 MB framebuffer copy.
 __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__ tileCount, uint32_t nTiles,
 	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords,
-	const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes)
+	const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes,
+	uint4* __restrict__ marks /*vertex marks of the sliced vertex stage, or null*/, uint32_t markQuads,
+	PeerFlags waitPf, uint32_t waitSelf, uint32_t waitRanks /*0: no wait*/, uint32_t waitEpoch)
 {
 	pdlPrologue();
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	buildMeshConsts(gtid, gsize, hostViewProj, meshStatic, meshConst, nMeshes);
+	for (uint32_t i = gtid; i < markQuads; i += gsize) marks[i] = make_uint4(0, 0, 0, 0);
 	const uint32_t q = (nTiles + 3) / 4;
 	for (uint32_t i = gtid; i < q; i += gsize)
 		reinterpret_cast<uint4*>(tileCount)[i] = make_uint4(0, 0, 0, 0);
@@ -226,6 +275,14 @@ __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__
 	{
 		for (uint32_t i = threadIdx.x; i < counterWords; i += blockDim.x) counters[i] = 0;
 		if (threadIdx.x < infoWords) frameInfo[threadIdx.x] = 0;
+		// frame ring + sharded front end: the peers must have finished the frame that used this ring slot before (their
+		// raster kernels read the list set this frame is about to store into: "frame done" words 16..23); normally long
+		// satisfied.  The kernels that store into peer memory follow this one in the stream.
+		if (waitRanks && threadIdx.x < 32)
+		{
+			__syncwarp();
+			peerFlagsWait(waitPf, waitSelf, waitRanks, 16u, waitEpoch, frameInfo + 7);
+		}
 	}
 }
 // the constants alone, for frames whose vertex stage runs ahead on its own stream
@@ -539,6 +596,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
 	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold,
 	uint32_t* __restrict__ longTiles, uint4* __restrict__ tileOrder, uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
+	ShardInbox inbox, uint32_t inboxRanks /*sharded front end: the heads (count, offset) of this rank's lists go to the inbox of each tile's owner; 0: no*/,
 	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[6]=lists sorted by the bitonic fallback,[8..13]=tiles per class*/)
 {
 	pdlPrologue();
@@ -613,7 +671,8 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 				const unsigned long long pairs = before + blockTotal;
 				frameInfo[0] = pairs;
 				frameInfo[1] = (pairs > capacity) ? 1ull : 0ull;
-				tileOffset[nTiles] = (pairs > capacity) ? 0xFFFFFFFFu : 0u;    // what a peer rank reads (sharded front end)
+				tileOffset[nTiles] = (pairs > capacity) ? 0xFFFFFFFFu : 0u;
+				for (uint32_t p = 0; p < inboxRanks; ++p) inbox.tileOffset[p][nTiles] = (pairs > capacity) ? 0xFFFFFFFFu : 0u;      // overflow marker, to every rank
 			}
 		}
 	}
@@ -644,6 +703,22 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 		#pragma unroll
 		for (uint32_t e = 0; e < 4; ++e)
 			if (i + e < nTiles && v[q * 4 + e] > longThreshold) longTiles[atomicAdd(&frameInfo[3], 1ull)] = i + e;
+	}
+	// Sharded front end, exchange step 1: the heads of this rank's lists go to the tiles' owners right away (posted
+	// NVLink stores), so the transfer hides behind scatter + push of the lists themselves
+	if (inboxRanks)
+	{
+		#pragma unroll
+		for (uint32_t e = 0; e < kScanPerThread; ++e)
+		{
+			const uint32_t t = first + e;
+			if (t < nTiles)
+			{
+				const uint32_t owner = t % inboxRanks;
+				inbox.tileCount[owner][t] = v[e];
+				inbox.tileOffset[owner][t] = off[e];
+			}
+		}
 	}
 	// the raster kernel's work order: one atomic per warp and class; inside a warp the tiles stay in ascending order.
 	// Sort-first with a replicated front end: only the tiles this rank owns (the others hold no entries here and
@@ -735,12 +810,6 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 // 8..15) is signalled by publish_info_kernel and waited for by rank 0 only when it reads or presents the frame.  The preceding kernels of the stream have completed,
 // so their writes (bin lists; colours stored into rank 0's surface) are visible before the flag.  A peer
 // that never arrives raises frameInfo[7] after ~4 s instead of hanging the GPU.
-__device__ __forceinline__ unsigned long long globalTimerNs()
-{
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-}
 // earlyTrigger = 0 (frame ring): the kernel does not release its programmatic dependents before it exits - the CTAs of
 // the raster kernel behind a barrier would otherwise become resident and sit out the wait for the slowest peer on
 // SM slots that the front ends of the following frames (other ring streams) could use.

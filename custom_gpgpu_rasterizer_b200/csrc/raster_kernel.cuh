@@ -25,7 +25,6 @@ struct RasterArgs
 	const uint32_t* binIds;     // (the kernel writes the lists it sorts back through these pointers)
 	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
-	const float4* posIn;        // resident model-space positions (x, y, z, 1): read instead of pos4 by the OTF instantiations
 	const float2* ivertex;      // resident IVertex records (7 float2 each)
 	const MeshConst* meshes;
 	const TexDesc* textures;
@@ -208,42 +207,6 @@ constexpr int kListChunk = 256;       // bin-list entries processed per sweep it
 #endif
 constexpr int kSmallArea = B2R_SMALL_AREA;   // bbox-in-tile areas up to this are rasterised by one thread
 
-// the three transformed positions {ndc.xyz, clip.w} of a primitive.  OTF = false: from the frame's pos4 stream.
-// OTF = true ("on the fly"; sharded front end with a sliced vertex stage, where a rank transforms only the
-// vertices its own primitive slice refers to): transformed here from the resident model-space positions with
-// the mesh's WVP - transformPosition() is the vertex stage's own function, so the bits are those of pos4.
-constexpr uint32_t kSmemMeshes = 4;     // OTF: the WVP matrices of the first meshes are staged in shared memory
-template <bool OTF>
-__device__ __forceinline__ void fetchPositions(const RasterArgs& A, const float (*sWvp)[16], const uint4& tr, float4& p0, float4& p1, float4& p2)
-{
-	if (OTF)
-	{
-		const MeshConst* mc = A.meshes + tr.w;
-		const uint32_t inDelta = __ldg(&mc->vtxInBase) - __ldg(&mc->vtxOutBase);     // transformed-stream index -> input record (mod 2^32)
-		const float4 a = __ldg(A.posIn + (tr.x + inDelta)), b = __ldg(A.posIn + (tr.y + inDelta)), c = __ldg(A.posIn + (tr.z + inDelta));
-		if (tr.w < kSmemMeshes)
-		{
-			const float* m = sWvp[tr.w];
-			p0 = transformPosition(m, a.x, a.y, a.z);
-			p1 = transformPosition(m, b.x, b.y, b.z);
-			p2 = transformPosition(m, c.x, c.y, c.z);
-		}
-		else
-		{
-			const float4* w4 = reinterpret_cast<const float4*>(mc->wvp);       // MeshConst is 208 bytes, wvp at offset 0: 16-byte aligned
-			const float4 c0 = __ldg(w4), c1 = __ldg(w4 + 1), c2 = __ldg(w4 + 2), c3 = __ldg(w4 + 3);
-			const float m[16] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w };
-			p0 = transformPosition(m, a.x, a.y, a.z);
-			p1 = transformPosition(m, b.x, b.y, b.z);
-			p2 = transformPosition(m, c.x, c.y, c.z);
-		}
-	}
-	else
-	{
-		p0 = __ldg(A.pos4 + tr.x); p1 = __ldg(A.pos4 + tr.y); p2 = __ldg(A.pos4 + tr.z);
-	}
-}
-
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // TEXTURED = false is the light variant for frames in which no mesh has a diffuse map and the
@@ -255,10 +218,7 @@ __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefet
 #ifndef B2R_RASTER_FULL_CTAS
 #define B2R_RASTER_FULL_CTAS 4
 #endif
-#ifndef B2R_RASTER_LIGHT_OTF_CTAS
-#define B2R_RASTER_LIGHT_OTF_CTAS 5      // the light variant that also transforms its vertices: 48 registers instead of 40
-#endif
-constexpr int rasterCtasPerSM(bool textured, bool otf) { return textured ? B2R_RASTER_FULL_CTAS : (otf ? B2R_RASTER_LIGHT_OTF_CTAS : B2R_RASTER_LIGHT_CTAS); }
+constexpr int rasterCtasPerSM(bool textured) { return textured ? B2R_RASTER_FULL_CTAS : B2R_RASTER_LIGHT_CTAS; }
 
 // big triangles of the pixel-parallel path as they wait in shared memory (64 bytes; the edge vectors are rebuilt from
 // the vertices with the subtractions of expandRecord, hence the same bits)
@@ -322,8 +282,8 @@ __device__ B2R_NOINLINE void sortStagedListFallback(const RasterArgs& A, const W
 // worst case (one item per block); the CTAs behind the last item leave at once.
 // Lists of up to kStage entries are staged in shared memory; warp 0 then puts the staged list into canonical order
 // (and stores it) while warps 1..7 already sweep it - the sweep does not depend on the order.
-template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF = false>
-__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
+template <bool TOPLEFT, bool COUNT, bool TEXTURED>
+__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
 {
 	pdlPrologue();
 	__shared__ __align__(16) TriBig sBig[kListChunk];   // the pixel-parallel triangles of the block
@@ -333,7 +293,6 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 	__shared__ WorkItem sItem;
 	__shared__ uint32_t sNumBig[2];                    // big-triangle count of the current / the next list chunk
 	__shared__ uint32_t sSortFallback;
-	__shared__ float sWvp[OTF ? kSmemMeshes : 1][16];  // OTF: WVP of the first meshes (visible after the first barrier)
 
 	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
 	const int tid = threadIdx.x;
@@ -358,7 +317,6 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 		v0 *= kEmptyBatch;
 		v1 = min(v0 + kEmptyBatch, emptyBlocks);
 	}
-	if (OTF && (uint32_t)tid < min(fp.nMeshes, kSmemMeshes) * 16u) sWvp[tid >> 4][tid & 15u] = A.meshes[tid >> 4].wvp[tid & 15u];
 	const bool shard = fp.shardGeometry != 0u;
 	const WorkItem& item = sItem;
 
@@ -426,8 +384,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 			// rebuild the screen-space triangle from the static reference + the transformed positions
 			// (same code, hence the same bits, wherever a triangle is expanded)
 			const uint4 tr = __ldg(A.triRefs + prim);
-			float4 p0, p1, p2;
-			fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
+			const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
 			TriRecord r;
 			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
 			// candidate pixels = the record's conservative box clipped to this CTA's block; the box
@@ -608,8 +565,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 			prim = (uint32_t)best;
 			depthOut = (int)(uint32_t)(best >> 32);
 			const uint4 tr = __ldg(A.triRefs + prim);
-			float4 p0, p1, p2;
-			fetchPositions<OTF>(A, sWvp, tr, p0, p1, p2);
+			const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
 			TriShared t;
 			{
 				TriRecord r;
@@ -714,23 +670,36 @@ __global__ void __launch_bounds__(256) shard_merge_heads_kernel(ShardTable T, ui
 	}
 }
 
-// Sharded front end, exchange step 1: right after its scan every rank stores the heads (count, offset) of its
-// lists into the inbox of each tile's owner, so the transfer hides behind scatter + sort.
-__global__ void __launch_bounds__(256) shard_push_heads_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
-	uint32_t nTiles, ShardInbox inbox, uint32_t nRanks)
+// Sharded front end with a sliced vertex stage: a rank transforms the vertices its own primitive slice refers to before
+// it bins them, and - here, once the lists of its tiles have arrived - marks the vertices its RASTER kernel will need
+// (the three vertices of every entry of every owned tile's list) in a bitmap over the transformed-vertex stream;
+// vertex_transform_marked_kernel then transforms exactly those.  With n ranks and interleaved tile ownership that is
+// about 1/n of the front-facing vertices instead of all vertices on every rank.  One warp per owned tile.
+__global__ void __launch_bounds__(256) shard_mark_vertices_kernel(ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
+	const uint4* __restrict__ triRefs, uint32_t* __restrict__ marks, const unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < nTiles)
+	if (frameInfo[1]) return;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t tile = rank + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * nRanks;
+	if (tile >= nTiles) return;
+	for (uint32_t p = 0; p < nRanks; ++p)
 	{
-		const uint32_t owner = t % nRanks;
-		inbox.tileCount[owner][t] = tileCount[t];
-		inbox.tileOffset[owner][t] = tileOffset[t];
+		const uint32_t cnt = __ldg(T.tileCount[p] + tile);
+		if (!cnt) continue;
+		const uint32_t* seg = T.binIds[p] + __ldg(T.tileOffset[p] + tile);
+		for (uint32_t e = lane; e < cnt; e += 32)
+		{
+			const uint4 tr = __ldg(triRefs + __ldg(seg + e));
+			// (plain test before the atomic: neighbouring triangles share their vertices, most bits are set already)
+			if (!((marks[tr.x >> 5] >> (tr.x & 31u)) & 1u)) atomicOr(&marks[tr.x >> 5], 1u << (tr.x & 31u));
+			if (!((marks[tr.y >> 5] >> (tr.y & 31u)) & 1u)) atomicOr(&marks[tr.y >> 5], 1u << (tr.y & 31u));
+			if (!((marks[tr.z >> 5] >> (tr.z & 31u)) & 1u)) atomicOr(&marks[tr.z >> 5], 1u << (tr.z & 31u));
+		}
 	}
-	if (t < nRanks) inbox.tileOffset[t][nTiles] = tileOffset[nTiles];      // overflow marker, to everybody
 }
 
-// after the sort: mirror the list of every tile into its owner's memory, at the SAME offset inside the region
+// Sharded front end, exchange step 2, after the scatter: mirror the list of every tile into its owner's memory, at the SAME offset inside the region
 // reserved there for this rank, so no rank needs another rank's offsets.  Posted NVLink stores of aligned
 // 16-byte vectors; the few ids of the neighbouring lists that ride along belong to tiles t-1 / t+1, which
 // have other owners, so nobody reads them there.

@@ -170,6 +170,18 @@ class Renderer:
         if sync:
             self.sync()
 
+    def prepare_camera(self, cam: Dict[str, np.ndarray]):
+        """Marshal a camera once for render_prepared(): frame loops that re-use a camera skip the per-call conversions."""
+        cp = np.ascontiguousarray(cam["cam_pos"], np.float32); cf = np.ascontiguousarray(cam["cam_fwd"], np.float32)
+        vp = np.ascontiguousarray(cam["view_proj"], np.float32)
+        return (cp, cf, vp, _fptr(cp), _fptr(cf), _fptr(vp))
+
+    def render_prepared(self, prep, cull: int = 0, sample: int = 0, vis: int = 0):
+        """b2r_render with a camera marshalled by prepare_camera(); asynchronous."""
+        rc = lib.b2r_render(self._ctx, prep[3], prep[4], prep[5], cull, sample, vis, None)
+        if rc != _lib.B2R_OK:
+            self._check(rc)
+
     def render_scene(self, scene: Scene, sync: bool = True):
         cam = host_camera(scene.cam_pos, scene.fov_deg, scene.width, scene.height, scene.near, scene.far, scene.pitch_deg, scene.yaw_deg)
         self.render(cam, scene.cull, scene.sample, scene.vis, sync=sync)

@@ -111,6 +111,12 @@ class _FakeRenderer:
         assert cam["view_proj"].shape == (16,)
         self.frames += 1
 
+    def prepare_camera(self, cam):
+        return cam
+
+    def render_prepared(self, prep, cull=0, sample=0, vis=0):
+        self.render(prep, cull, sample, vis, sync=False)
+
     def sync(self):
         pass
 

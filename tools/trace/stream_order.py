@@ -46,7 +46,7 @@ import sys
 from collections import defaultdict
 
 K_MAX_RANKS = 8
-RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("posIn", "r"), ("ivertex", "r"),
+RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("ivertex", "r"),
                ("meshes", "r"), ("textures", "r"), ("frameInfo", "w"), ("framebuffer", "w"), ("depth", "w"), ("zSurface", "w"), ("winnerSurface", "w")]
 RASTER_ARGS += [(f"shard.tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"shard.tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)] \
     + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r")]      # the raster kernel sorts the lists it stages, in place
@@ -180,18 +180,19 @@ class Trace:
         "frame_clear_kernel": {"tileCount": 0, "counters": 2, "frameInfo": 3, "hViewProj": 6, "meshStatic": 7, "meshConst": 8},
         "build_constants_kernel": {"hViewProj": 0, "meshStatic": 1, "meshConst": 2},
         "vertex_transform_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3},
+        "vertex_transform_marked_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3, "frameInfo": 7},
+        "shard_mark_vertices_kernel": {"triRefs": 4, "frameInfo": 6},
         "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5},
         "bin_big_count_kernel": {"bigList": 0, "counters": 1, "rects": 2, "tileCount": 3},
-        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "counters": 10, "frameInfo": 11},
+        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "counters": 10, "frameInfo": 13},
         "bin_scatter_kernel": {"rects": 0, "tileOffset": 3, "tileCursor": 4, "binIds": 5, "bigList": 6, "counters": 7, "frameInfo": 9},
         "bin_sort_tiles_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 4},
         "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
-        "shard_push_heads_kernel": {"tileCount": 0, "tileOffset": 1},
         "shard_merge_heads_kernel": {"tileOrder": 4, "frameInfo": 5},
         "shard_push_lists_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 7},
         "publish_info_kernel": {"frameInfo": 0},
     }
-    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "posIn": 5, "meshConst": 7, "frameInfo": 9, "tileOrder": 14 + 3 * K_MAX_RANKS}
+    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "meshConst": 6, "frameInfo": 8, "tileOrder": 13 + 3 * K_MAX_RANKS}
 
     def frames(self):
         """Per device: the launches of every frame, in the order the host issued them (b2r_render issues a whole frame; a
@@ -242,7 +243,7 @@ class Trace:
             for i in range(n_frames):
                 get = lambda d, kernel: next((o for o in frames[d][i] if self.short(o) == kernel), None)      # noqa: E731
                 rasters = [get(d, "raster_shade_kernel") for d in range(ranks)]
-                heads = [get(d, "shard_push_heads_kernel") for d in range(ranks)]
+                heads = [get(d, "tile_scan_kernel") for d in range(ranks)]          # the scan kernel pushes the heads (its ShardInbox argument)
                 lists = [get(d, "shard_push_lists_kernel") for d in range(ranks)]
                 if any(x is None for x in rasters + heads):
                     errs.append(f"frame {i}: a rank has no raster / push-heads launch")
@@ -265,13 +266,13 @@ class Trace:
                           for d in range(ranks)}
                 if len(epochs) != 1:
                     errs.append(f"frame {i}: the ranks' barrier epochs differ: {sorted(epochs)}")
-                surfaces = {self._ptr(r["args"][0], 10) for r in rasters}
+                surfaces = {self._ptr(r["args"][0], 9) for r in rasters}
                 if len(surfaces) != 1:
                     errs.append(f"frame {i}: the ranks store their colours into different surfaces {sorted(hex(x) for x in surfaces)}")
                 for q in range(ranks):                     # tile owner q reads ...
                     for p in range(ranks):                 # ... what rank p pushed
-                        base = 14                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
-                        want_count, want_off = self._ptr(heads[p]["args"][3], q), self._ptr(heads[p]["args"][3], K_MAX_RANKS + q)
+                        base = 13                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
+                        want_count, want_off = self._ptr(heads[p]["args"][11], q), self._ptr(heads[p]["args"][11], K_MAX_RANKS + q)
                         got_count, got_off = self._ptr(rasters[q]["args"][0], base + p), self._ptr(rasters[q]["args"][0], base + K_MAX_RANKS + p)
                         if (want_count, want_off) != (got_count, got_off):
                             errs.append(f"frame {i}: rank {q} reads the heads of rank {p} at {got_count:#x}/{got_off:#x}, rank {p} pushed them to {want_count:#x}/{want_off:#x}")
@@ -384,6 +385,10 @@ class Trace:
                             signals[(8, epoch)].append(n)
                         if done_ranks:
                             signals[(16, epoch)].append(n)
+                    if op == "launch" and label == "frame_clear_kernel" and len(o["args"]) > 15 and u32(o["args"][14]):
+                        # frame ring + sharded front end: block 0 of the clear kernel ends with the one-way wait for the
+                        # peers' "frame done" of the frame that used this ring slot before (wait ranks, wait epoch)
+                        waiters[(16, u32(o["args"][15]))].append(n)
                 last_on_stream[skey] = n
                 if op == "memcpy" and not o["async"]:
                     host_node("blocking copy", [n], dev)
