@@ -60,6 +60,7 @@ ABI = {
     "b2r_read_framebuffer": (_i32, [_vp, _vp]),
     "b2r_present_async": (_i32, [_vp, _vp]),
     "b2r_present_wait": (_i32, [_vp]),
+    "b2r_draw_texture": (_i32, [_vp, _vp, _u32, _u32, _i32, _i32, _i32, _fp]),
     "b2r_host_frame_register": (_i32, [_vp, _vp, _u64]),
     "b2r_present_tiles_async": (_i32, [_vp, _u64]),
     "b2r_present_band_async": (_i32, [_vp, _u64]),

@@ -1516,6 +1516,33 @@ int b2r_read_framebuffer(b2r_context* c, uint32_t* out)
 	if (!c) return B2R_E_INVALID;
 	return readSurface(c, c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->lastColourIdx], out, "read_framebuffer");
 }
+int b2r_draw_texture(b2r_context* c, const uint32_t* pixels, uint32_t w, uint32_t h, int global, int stretched, int sample, const float clearRGB[3])
+{
+	if (!c) return B2R_E_INVALID;
+	if (!pixels || !w || !h || sample < 0 || sample > 1) return fail(c, B2R_E_INVALID, "draw_texture: bad arguments");
+	if (c->boundFramebuffer) return fail(c, B2R_E_STATE, "draw_texture: the colour surface is bound to caller memory");
+	CU(c, cudaSetDevice(c->device));
+	int r = validateFrame(c); if (r) return r;
+	uint32_t* d = nullptr;
+	CU(c, cudaMalloc((void**)&d, (size_t)w * h * 4));
+	cudaError_t e = cudaMemcpyAsync(d, pixels, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess)
+	{
+		static const float defClear[3] = { 0.25f, 0.25f, 0.25f };
+		const float* cl = clearRGB ? clearRGB : defClear;
+		const uint32_t clear = ((uint32_t)(cl[2] * 255.f) & 0xFFu) | (((uint32_t)(cl[1] * 255.f) & 0xFFu) << 8) | (((uint32_t)(cl[0] * 255.f) & 0xFFu) << 16);
+		draw_texture_kernel<<<dim3((c->width + 15) / 16, (c->height + 15) / 16), 256, 0, c->stream>>>(c->dColour[c->colourIdx], TexDesc{ d, w, h }, c->width, c->height,
+			global ? 1u : 0u, stretched ? 1u : 0u, (uint32_t)sample, clear);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(c, B2R_E_CUDA, "draw_texture failed: %s", cudaGetErrorString(e));
+	c->lastColourIdx = c->colourIdx;
+	c->haveFrame = true;
+	return B2R_OK;
+}
+
 static int ensureCopyStream(b2r_context* c)
 {
 	if (!c->copyStream)

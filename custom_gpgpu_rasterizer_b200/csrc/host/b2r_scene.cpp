@@ -12,6 +12,7 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <memory>
 #include <unordered_map>
 
 // =========================================================================== Resolution
@@ -300,6 +301,12 @@ void ObjParser::Assign(unsigned int faceCount, std::vector<IVertex>& vertices, s
 
 	if (!(isUVs && isNormals) && !(isUVs && !isNormals) && !(!isUVs && !isNormals))
 		return;   // normals without uvs: the reference has no branch for it and leaves the buffers empty
+	// file-supplied indices (1-based in the file; index 0 wraps to 0xFFFFFFFF): the reference reads out of bounds here,
+	// a library must not - a face that refers to data the file does not hold leaves the buffers empty
+	for (size_t i = 0; i < numIndices; ++i)
+		if (m_PositionIndices[i] >= m_Positions.size() || (isUVs && (i >= m_UVIndices.size() || m_UVIndices[i] >= m_UVs.size())) ||
+			(isUVs && isNormals && (i >= m_NormalIndices.size() || m_NormalIndices[i] >= m_Normals.size())))
+			return;
 	if (isUVs && isNormals) vertexType |= (int)VertexType::Tan;
 
 	for (size_t i = 0; i < numIndices; ++i)
@@ -385,12 +392,14 @@ bool DecodePNG(const char* path, std::vector<unsigned int>& out, unsigned int& w
 		const uint32_t len = be32(&file[off]);
 		const unsigned char* type = &file[off + 4];
 		if (off + 12 + len > file.size()) return false;
+		if (!memcmp(type, "IHDR", 4) && len < 13) return false;
 		if (!memcmp(type, "IHDR", 4)) { w = be32(&file[off + 8]); h = be32(&file[off + 12]); bitDepth = file[off + 16]; colourType = file[off + 17]; interlace = file[off + 20]; }
 		else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), &file[off + 8], &file[off + 8] + len);
 		else if (!memcmp(type, "IEND", 4)) break;
 		off += 12 + (size_t)len;
 	}
 	if (bitDepth != 8 || interlace != 0 || (colourType != 6 && colourType != 2) || !w || !h) return false;
+	if (w > 32768u || h > 32768u) return false;      // dimensions come from the file: keep the allocations below sane
 	const unsigned int bpp = colourType == 6 ? 4 : 3;
 	const size_t stride = (size_t)w * bpp;
 	std::vector<unsigned char> raw((stride + 1) * h);
@@ -478,6 +487,7 @@ void CUDATextureManager::RemoveCUDATexture(int id)   // CUDATextureManager.cpp:3
 CUDARenderer::CUDARenderer(const WindowHelper& windowHelper)   // CUDARenderer.cu:34-46
 	: m_WindowHelper{ windowHelper }
 {
+	m_BenchMarker.m_pRenderer = this;
 	const int r = b2r_create(0, windowHelper.Resolution.Width, windowHelper.Resolution.Height, &m_pContext);
 	if (r != B2R_OK)
 		std::cout << "!CUDARenderer > " << b2r_last_error(nullptr) << "!\n";   // errors are reported, never thrown (PCH.h:46-56)
@@ -495,13 +505,18 @@ void CUDARenderer::LoadScene(const SceneGraph* pSceneGraph, const CUDATextureMan
 	if (!m_pContext) return;
 	m_TotalNumTriangles = 0;
 	b2r_mesh_clear_all(m_pContext);
+	// the device textures of the previous LoadScene go first: in the reference they belong to the texture manager and are
+	// not re-created per scene; here every LoadScene uploads the manager's current textures
+	for (int id : m_ContextTextureIds) b2r_texture_destroy(m_pContext, id);
+	m_ContextTextureIds.clear();
+	m_pSceneGraph = pSceneGraph; m_DeviceWorlds.clear(); m_MeshIds.clear();
 	// textures: the manager's dense ids are kept (CUDATextureManager.cpp:29-37)
 	std::vector<int> ctxId(tm.GetNumTextures(), -1);
 	for (unsigned int id = 0; id < tm.GetNumTextures(); ++id)
 	{
 		const CUDATexture* t = tm.GetCUDATexture((int)id);
-		if (t && t->IsAllocated())
-			b2r_texture_create_rgba8(m_pContext, t->GetPixels().data(), t->GetWidth(), t->GetHeight(), &ctxId[id]);
+		if (t && t->IsAllocated() && b2r_texture_create_rgba8(m_pContext, t->GetPixels().data(), t->GetWidth(), t->GetHeight(), &ctxId[id]) == B2R_OK)
+			m_ContextTextureIds.push_back(ctxId[id]);
 	}
 	for (const Mesh* pMesh : pSceneGraph->GetMeshes())
 	{
@@ -519,6 +534,7 @@ void CUDARenderer::LoadScene(const SceneGraph* pSceneGraph, const CUDATextureMan
 		int meshId = -1;
 		const int r = b2r_mesh_upload(m_pContext, pMesh->GetVertexBuffer(), pMesh->GetNumVertices(), pMesh->GetIndexBuffer(),
 			pMesh->GetNumIndices(), (int)pMesh->GetTopology(), &world.data[0][0], tex, &meshId);
+		m_DeviceWorlds.push_back(world); m_MeshIds.push_back(r == B2R_OK ? meshId : -1);
 		if (r != B2R_OK) { std::cout << "!CUDARenderer::LoadScene > " << b2r_last_error(m_pContext) << "!\n"; continue; }
 		m_TotalNumTriangles += pMesh->GetTotalNumTriangles();
 	}
@@ -542,6 +558,23 @@ void CUDARenderer::Render(const SceneManager& sm, const CUDATextureManager&, con
 	const FMatrix4 viewProjectionMatrix = pCamera->GetProjectionMatrix() * viewMatrix;
 	const float pos[3] = { camPos.x, camPos.y, camPos.z }, fwd[3] = { camFwd.x, camFwd.y, camFwd.z };
 	const float clear[3] = { m_ClearColour.r, m_ClearColour.g, m_ClearColour.b };
+	if (m_DynamicWorlds && m_pSceneGraph && m_pSceneGraph->GetMeshes().size() == m_DeviceWorlds.size())
+	{
+		// SceneGraph::Update (SceneGraph.cpp:30-39) / anybody who moved a mesh: the device gets the matrices that changed,
+		// with CUDAMesh's translation rule (CUDAMesh.cpp:16-18) applied to the current matrix
+		size_t i = 0;
+		for (const Mesh* pMesh : m_pSceneGraph->GetMeshes())
+		{
+			FMatrix4 world = pMesh->GetWorldConst();
+			const FPoint3& pos = pMesh->GetPositionConst();
+			world.data[3][0] += pos.x; world.data[3][1] += pos.y; world.data[3][2] += pos.z;
+			if (m_MeshIds[i] >= 0 && memcmp(&world.data[0][0], &m_DeviceWorlds[i].data[0][0], 64) != 0)
+			{
+				if (b2r_mesh_set_world(m_pContext, m_MeshIds[i], &world.data[0][0]) == B2R_OK) m_DeviceWorlds[i] = world;
+			}
+			++i;
+		}
+	}
 	int r = b2r_render(m_pContext, pos, fwd, &viewProjectionMatrix.data[0][0], (int)sm.GetCullingMode(), (int)sm.GetSampleState(),
 		(int)sm.GetVisualisationState(), clear);
 	if (r == B2R_OK) r = b2r_sync(m_pContext);   // Render is synchronous on return (CUDARenderer.cu:339)
@@ -567,6 +600,24 @@ unsigned int CUDARenderer::GetTotalNumVisibleTriangles() const
 	if (m_pContext) b2r_get_stats(m_pContext, &total, &visible);
 	return visible;
 }
+void CUDARenderer::DrawTextureImpl(const char* tp, int global, bool stretched, SampleState sampleState)   // CUDARenderer.cu:1968-2012
+{
+	if (!m_pContext) return;
+	CUDATexture texture{};
+	if (!texture.Create(tp)) { std::cout << "!CUDARenderer::DrawTexture > cannot load " << (tp ? tp : "(null)") << "!\n"; return; }
+	EnterValidRenderingState();
+	const float clear[3] = { m_ClearColour.r, m_ClearColour.g, m_ClearColour.b };
+	if (b2r_draw_texture(m_pContext, texture.GetPixels().data(), texture.GetWidth(), texture.GetHeight(), global, stretched ? 1 : 0, (int)sampleState, clear) != B2R_OK)
+	{
+		std::cout << "!CUDARenderer::DrawTexture > " << b2r_last_error(m_pContext) << "!\n";
+		return;
+	}
+	Present();
+}
+void CUDARenderer::DrawTexture(char* tp) { DrawTextureImpl(tp, 0, true, SampleState::Point); }
+void CUDARenderer::DrawTextureGlobal(char* tp, bool isStretchedToWindow, SampleState sampleState) { DrawTextureImpl(tp, 1, isStretchedToWindow, sampleState); }
+void CUDABenchMarker::StartTimer() { if (m_pRenderer) m_pRenderer->StartTimer(); }
+float CUDABenchMarker::StopTimer() { return m_pRenderer ? m_pRenderer->StopTimer() : 0.f; }
 void CUDARenderer::DisplayGPUSpecs(int) {}
 void CUDARenderer::KernelWarmUp() {}
 void CUDARenderer::StartTimer() { if (m_pContext) b2r_set_option(m_pContext, B2R_OPT_STAGE_TIMERS, 1); }
@@ -578,7 +629,17 @@ float CUDARenderer::StopTimer()
 }
 
 // =========================================================================== Elite::Renderer
-Elite::Renderer::Renderer(const WindowHelper& windowHelper) : m_Renderer{ windowHelper }, m_WindowHelper{ windowHelper } {}
+unsigned int Elite::Renderer::DefaultWidth = 640, Elite::Renderer::DefaultHeight = 480;
+static WindowHelper ownedWindow(SDL_Window* pWindow, std::vector<unsigned int>& pixels)
+{
+	pixels.assign((size_t)Elite::Renderer::DefaultWidth * Elite::Renderer::DefaultHeight, 0u);
+	WindowHelper h{};
+	h.pWindow = pWindow; h.pBackBufferPixels = pixels.data();
+	h.Resolution.Width = Elite::Renderer::DefaultWidth; h.Resolution.Height = Elite::Renderer::DefaultHeight;
+	return h;
+}
+Elite::Renderer::Renderer(SDL_Window* pWindow) : m_OwnPixels{}, m_OwnHelper{ ownedWindow(pWindow, m_OwnPixels) }, m_WindowHelper{ m_OwnHelper }, m_Renderer{ m_OwnHelper } {}
+Elite::Renderer::Renderer(const WindowHelper& windowHelper) : m_OwnPixels{}, m_OwnHelper{}, m_WindowHelper{ windowHelper }, m_Renderer{ windowHelper } {}
 Elite::Renderer::~Renderer() = default;
 void Elite::Renderer::LoadScene(const SceneGraph* pSceneGraph, const CUDATextureManager& tm) { m_pTextures = &tm; m_Renderer.LoadScene(pSceneGraph, tm); }
 void Elite::Renderer::Render(const SceneManager& sm)   // ERenderer.cpp:42-164: same entry point, B200 path behind it
@@ -636,11 +697,13 @@ void b2r_host_mesh_world(const float pos[3], int vectorCtor, float* world16)
 
 struct b2r_host_obj { std::vector<IVertex> v; std::vector<unsigned int> idx; short vertexType = 0; };
 b2r_host_obj* b2r_host_obj_parse(const char* path, int invertY, int pointerFlavour)
+try
 {
+	if (!path) return nullptr;
 	ObjParser parser;
 	if (!parser.OpenFile(path)) return nullptr;
 	parser.SetInvertYAxis(invertY != 0);
-	b2r_host_obj* o = new b2r_host_obj;
+	std::unique_ptr<b2r_host_obj> o(new b2r_host_obj);
 	if (pointerFlavour)
 	{
 		IVertex* pv = nullptr; unsigned int nv = 0, ni = 0; unsigned int* pi = nullptr;
@@ -650,8 +713,9 @@ b2r_host_obj* b2r_host_obj_parse(const char* path, int invertY, int pointerFlavo
 	}
 	else
 		parser.ReadFromObjFile(o->v, o->idx, o->vertexType);
-	return o;
+	return o.release();
 }
+catch (...) { return nullptr; }      // malformed file (std::stof / stoi / substr throw): no exception crosses the C boundary
 unsigned int b2r_host_obj_num_vertices(const b2r_host_obj* o) { return (unsigned int)o->v.size(); }
 unsigned int b2r_host_obj_num_indices(const b2r_host_obj* o) { return (unsigned int)o->idx.size(); }
 int b2r_host_obj_vertex_type(const b2r_host_obj* o) { return o->vertexType; }
@@ -660,12 +724,14 @@ const unsigned int* b2r_host_obj_indices(const b2r_host_obj* o) { return o->idx.
 void b2r_host_obj_free(b2r_host_obj* o) { delete o; }
 
 int b2r_host_png_decode(const char* path, unsigned int* w, unsigned int* h, unsigned int* outPixels, unsigned long long capacity)
+try
 {
 	std::vector<unsigned int> px; unsigned int ww = 0, hh = 0;
-	if (!DecodePNG(path, px, ww, hh)) return -1;
+	if (!path || !w || !h || !DecodePNG(path, px, ww, hh)) return -1;
 	*w = ww; *h = hh;
 	if (outPixels && capacity >= px.size()) memcpy(outPixels, px.data(), px.size() * 4);
 	return 0;
 }
+catch (...) { return -1; }
 
 }

@@ -295,6 +295,22 @@ private:
 	std::vector<CUDATexture*> m_pCUDATextures;
 };
 
+// ---- CUDABenchMarker.h : StartTimer / StopTimer around a frame (the reference times with a cudaEvent pair and averages;
+// here the renderer's own per-stage device timers are read, StopTimer returns the last frame's total in ms)
+class CUDARenderer;
+class CUDABenchMarker
+{
+public:
+	explicit CUDABenchMarker(int amountOfTimes = 4, int amountOfTimeAverages = 10) : m_AmountOfTimes(amountOfTimes), m_AmountOfTimeAverages(amountOfTimeAverages) {}
+	virtual ~CUDABenchMarker() = default;
+	virtual void StartTimer();
+	virtual float StopTimer();
+private:
+	friend class CUDARenderer;
+	int m_AmountOfTimes, m_AmountOfTimeAverages;
+	CUDARenderer* m_pRenderer{};
+};
+
 // ---- CUDARenderer.h
 class CUDARenderer final
 {
@@ -303,6 +319,10 @@ public:
 	~CUDARenderer() noexcept;
 	CUDARenderer(const CUDARenderer&) = delete;
 	CUDARenderer& operator=(const CUDARenderer&) = delete;
+
+	// testing purposes (CUDARenderer.h:43-45): the texture file drawn over the window, then Present
+	void DrawTexture(char* tp);
+	void DrawTextureGlobal(char* tp, bool isStretchedToWindow = true, SampleState sampleState = (SampleState)0);
 
 	void LoadScene(const SceneGraph* pSceneGraph, const CUDATextureManager& tm);
 	void SetupBins(const IPoint2& numBins, const IPoint2& binDim, unsigned int binQueueMaxSize);
@@ -316,8 +336,14 @@ public:
 	void KernelWarmUp();
 	void StartTimer();
 	float StopTimer();
+	CUDABenchMarker& GetBenchMarker() { return m_BenchMarker; }
 
 	// additions of the headless build
+	// The reference snapshots every mesh's world matrix when the scene is loaded (CUDAMesh.cpp:16-18), so its GPU path never
+	// sees SceneGraph::Update.  Here Render() compares the meshes' current world matrices with the ones the device holds
+	// and refreshes those that changed (b2r_mesh_set_world; the per-mesh WVP upload of CUDARenderer.cu:241-246 is then
+	// rebuilt on the device).  With unchanged matrices - the reference's main passes elapsedSec = 0 - nothing differs.
+	void SetDynamicWorlds(bool enabled) { m_DynamicWorlds = enabled; }
 	b2r_context* GetContext() const { return m_pContext; }
 	void SetClearColour(const RGBColor& colour) { m_ClearColour = colour; }
 	const char* GetLastError() const;
@@ -327,6 +353,12 @@ private:
 	const WindowHelper& m_WindowHelper;
 	b2r_context* m_pContext{};
 	RGBColor m_ClearColour{ 0.25f, 0.25f, 0.25f };
+	CUDABenchMarker m_BenchMarker{};
+	const SceneGraph* m_pSceneGraph{};              // not owned: the graph of the last LoadScene, for the world-matrix refresh
+	std::vector<FMatrix4> m_DeviceWorlds;           // world matrix the device holds for mesh i
+	std::vector<int> m_MeshIds, m_ContextTextureIds;
+	bool m_DynamicWorlds{ true };
+	void DrawTextureImpl(const char* tp, int global, bool stretched, SampleState sampleState);
 	void* m_TimerStart{};
 	void* m_TimerStop{};
 };
@@ -338,7 +370,13 @@ namespace Elite
 	class Renderer final
 	{
 	public:
+		// ERenderer.h:28.  This build has no SDL to ask the window for its size or surface: the renderer then owns a back
+		// buffer of DefaultWidth x DefaultHeight (640 x 480, Resolution::SD, the reference's default; main.cpp:405) and the
+		// window pointer is only kept.  GetBackBufferPixels() is the frame.
+		Renderer(SDL_Window* pWindow);
 		Renderer(const WindowHelper& windowHelper);
+		static unsigned int DefaultWidth, DefaultHeight;
+		const unsigned int* GetBackBufferPixels() const { return m_WindowHelper.pBackBufferPixels; }
 		~Renderer();
 		Renderer(const Renderer&) = delete;
 		Renderer& operator=(const Renderer&) = delete;
@@ -347,8 +385,10 @@ namespace Elite
 		void SetCamera(Camera* pCamera) { m_pCamera = pCamera; }
 		bool SaveBackbufferToImage() const;     // writes BackbufferRender.bmp like ERenderer.cpp:174-177
 	private:
-		CUDARenderer m_Renderer;
+		std::vector<unsigned int> m_OwnPixels;      // SDL_Window* constructor only
+		WindowHelper m_OwnHelper;
 		const WindowHelper& m_WindowHelper;
+		CUDARenderer m_Renderer;
 		const CUDATextureManager* m_pTextures{};
 		Camera* m_pCamera{};
 	};

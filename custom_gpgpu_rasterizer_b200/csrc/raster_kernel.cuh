@@ -720,6 +720,36 @@ __global__ void __launch_bounds__(256) shard_push_lists_kernel(const uint32_t* _
 	for (uint32_t v = (off >> 2) + lane, vEnd = (off + cnt + 3) >> 2; v < vEnd; v += 32) dst[v] = src[v];
 }
 
+// CUDARenderer::DrawTexture / DrawTextureGlobal (testing aids of the reference, CUDARenderer.cu:1565-1620, 1968-2012): the
+// texture stretched over the window (or texel-for-pixel), no geometry.  global = 0: TextureTestKernel - the texel CUDA's
+// point filter returns for normalised (x / width, y / height), bytes 0 and 2 swapped, alpha kept; global = 1:
+// DrawTextureGlobalKernel - CUDATextureSampler::Sample + the truncating colour pack.  The reference launches
+// (width / 16) x (height / 16) blocks of 16 x 16 threads: the remainder columns / rows keep the cleared colour.
+__global__ void __launch_bounds__(256) draw_texture_kernel(uint32_t* __restrict__ framebuffer, TexDesc tex, uint32_t width, uint32_t height,
+	uint32_t global, uint32_t stretched, uint32_t sampleState, uint32_t clearColour)
+{
+	const uint32_t x = blockIdx.x * 16u + (threadIdx.x & 15u), y = blockIdx.y * 16u + (threadIdx.x >> 4);
+	if (x >= width || y >= height) return;
+	uint32_t colour = clearColour;
+	if (x < (width / 16u) * 16u && y < (height / 16u) * 16u)
+	{
+		if (!global)
+		{
+			const float u = __fdiv_rn((float)x, (float)width), v = __fdiv_rn((float)y, (float)height);
+			const uint32_t tx = min((uint32_t)__float2int_rd(u * (float)tex.w), tex.w - 1u), ty = min((uint32_t)__float2int_rd(v * (float)tex.h), tex.h - 1u);
+			const uint32_t s = __ldg(tex.px + (size_t)tx + (size_t)ty * tex.w);
+			colour = (s & 0xFF00FF00u) | ((s & 0xFFu) << 16) | ((s >> 16) & 0xFFu);
+		}
+		else
+		{
+			const float u = __fdiv_rn((float)x, stretched ? (float)width : (float)tex.w), v = __fdiv_rn((float)y, stretched ? (float)height : (float)tex.h);
+			const RGB c = sampleTex(tex, u, v, sampleState);
+			colour = packColour(c.r, c.g, c.b);
+		}
+	}
+	framebuffer[(size_t)x + (size_t)y * width] = colour;
+}
+
 // Distributed Present: copy the 16x16 tiles this rank owns from its colour surface into the row-major frame in mapped
 // host memory (zero-copy stores over this GPU's own PCIe link).  64 threads per tile: one 16-byte store per thread, a
 // tile row = one 64-byte segment.  Four tiles per CTA.

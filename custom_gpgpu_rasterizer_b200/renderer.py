@@ -151,7 +151,10 @@ class Renderer:
         assert scene.width == self.width and scene.height == self.height
         self.setup_bins(scene.bins_x, scene.bins_y, scene.bin_w, scene.bin_h, scene.queue_cap)
         self.clear_meshes()
+        for t in getattr(self, "_scene_textures", []):       # the device textures of the previous load_scene
+            self._check(lib.b2r_texture_destroy(self._ctx, t))
         tex_map = [self.add_texture(t) for t in scene.textures]
+        self._scene_textures = list(tex_map)
         uploaded = {}       # meshes sharing the very same vertex / index memory become instances (b2r_mesh_instance)
         for m in scene.meshes:
             tex = [tex_map[t] if 0 <= t < len(tex_map) else -1 for t in m.tex_ids]

@@ -99,6 +99,33 @@ int main(int argc, char** argv)
 	if (!out) return 2;
 	fwrite(backBuffer.data(), 4, backBuffer.size(), out);
 	fclose(out);
+	// optional: --move dx dy dz  ->  the first mesh is moved the way an Update would move it (its world matrix), the scene
+	// manager is updated (SceneGraph::Update with elapsedSec 0, as in the reference's main loop) and the next frame goes to
+	// <out>.moved: the renderer picks the new matrix up by itself
+	for (int a = 3; a + 3 < argc; ++a)
+		if (std::string(argv[a]) == "--move" && !sm.GetSceneGraph()->GetMeshes().empty())
+		{
+			FMatrix4& world = sm.GetSceneGraph()->GetMeshes()[0]->GetWorld();
+			for (int k = 0; k < 3; ++k) world.data[3][k] += (float)atof(argv[a + 1 + k]);
+			sm.Update(0.f);
+			pCudaRenderer->RenderAuto(sm, tm, &camera);
+			printf("moved: triangles %u visible %u\n", pCudaRenderer->GetTotalNumTriangles(), pCudaRenderer->GetTotalNumVisibleTriangles());
+			FILE* o2 = fopen((std::string(argv[2]) + ".moved").c_str(), "wb");
+			if (!o2) return 2;
+			fwrite(backBuffer.data(), 4, backBuffer.size(), o2);
+			fclose(o2);
+		}
+	// optional: --texture file.png global stretched sample  ->  CUDARenderer::DrawTexture / DrawTextureGlobal into <out>.tex
+	for (int a = 3; a + 4 < argc; ++a)
+		if (std::string(argv[a]) == "--texture")
+		{
+			if (atoi(argv[a + 2])) pCudaRenderer->DrawTextureGlobal(argv[a + 1], atoi(argv[a + 3]) != 0, (SampleState)atoi(argv[a + 4]));
+			else pCudaRenderer->DrawTexture(argv[a + 1]);
+			FILE* o3 = fopen((std::string(argv[2]) + ".tex").c_str(), "wb");
+			if (!o3) return 2;
+			fwrite(backBuffer.data(), 4, backBuffer.size(), o3);
+			fclose(o3);
+		}
 	delete pCudaRenderer;
 	return 0;
 }

@@ -170,6 +170,14 @@ int b2r_read_framebuffer(b2r_context* ctx, uint32_t* out);
  * b2r_present_wait blocks until every outstanding copy has landed (and the frames are complete). */
 int b2r_present_async(b2r_context* ctx, uint32_t* host_pixels);
 int b2r_present_wait(b2r_context* ctx);
+/* CUDARenderer::DrawTexture(char*) / DrawTextureGlobal(char*, bool, SampleState) (CUDARenderer.h:43-45, CUDARenderer.cu:1968-2012;
+ * "testing purposes" in the reference): fills the colour surface with the RGBA8 texture `pixels` (byte 0 = R) - global = 0: one
+ * point-filtered texel per pixel at normalised window coordinates, written with bytes 0 and 2 swapped (TextureTestKernel);
+ * global = 1: CUDATextureSampler::Sample at x / width (stretched) or x / texture width, packed like a shaded pixel
+ * (DrawTextureGlobalKernel).  Synchronous; the result is read with b2r_read_framebuffer. */
+int b2r_draw_texture(b2r_context* ctx, const uint32_t* pixels, uint32_t width, uint32_t height, int global, int stretched, int sample_state,
+                     const float clear_rgb[3]);
+
 /* Distributed Present (sort-first over several GPUs; CUDARenderer::Present, CUDARenderer.cu:383-395, when the
  * consumer of the frame is the host): the frame is composed in HOST memory that all ranks share - e.g. a POSIX
  * shared-memory mapping - and every rank delivers the tiles it owns over its own PCIe link, instead of all colours

@@ -242,3 +242,35 @@ def test_reference_scene_code_builds_its_scene_graphs_on_the_veneer(tmp_path):
     ]
     g = np.load(os.path.join(GOLD, "objparser_reference.npz"))                         # the reference parser's own counts
     assert g["res_vehicle_v"].shape[0] == 12965 and g["res_tuktuk_v"].shape[0] == 4728
+
+
+def test_malformed_obj_and_png_do_not_cross_the_c_boundary(tmp_path):
+    """ADVICE (round 1): the C shims b2r_host_obj_parse / b2r_host_png_decode must return an error for malformed files - no
+    exception through ctypes, no out-of-bounds read for face indices the file does not define, no allocation from an absurd
+    IHDR."""
+    import struct
+    import zlib
+    from custom_gpgpu_rasterizer_b200.renderer import decode_png, parse_obj
+    bad_objs = {"lonely_v": "v\n", "not_numbers": "v a b c\nf 1 2 3\n", "empty_corner": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1// 2 3\n",
+                "index_zero": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 0 1 2\n", "index_beyond": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n",
+                "uv_beyond": "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nf 1/1 2/5 3/1\n"}
+    for name, text in bad_objs.items():
+        p = tmp_path / (name + ".obj")
+        p.write_text(text)
+        try:
+            v, i, _ = parse_obj(str(p), invert_y=False)
+        except FileNotFoundError:
+            continue                      # the shim reported a failure
+        assert v.shape[0] == 0 and i.size == 0, f"{name}: a face that refers to missing data must leave the buffers empty"
+
+    def chunk(t, data):
+        return struct.pack(">I", len(data)) + t + data + struct.pack(">I", zlib.crc32(t + data))
+    sig = b"\x89PNG\r\n\x1a\n"
+    bad_pngs = {"short_ihdr": sig + chunk(b"IHDR", b"\x00" * 5) + chunk(b"IDAT", zlib.compress(b"\x00" * 64)) + chunk(b"IEND", b""),
+                "huge": sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 0x7FFFFFFF, 0x7FFFFFFF, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\x00" * 64)) + chunk(b"IEND", b""),
+                "truncated": sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 4, 4, 8, 6, 0, 0, 0))[:20]}
+    for name, data in bad_pngs.items():
+        p = tmp_path / (name + ".png")
+        p.write_bytes(data)
+        with pytest.raises(ValueError):
+            decode_png(str(p))

@@ -87,3 +87,58 @@ def test_reference_scene_code_on_the_veneer_matches_c_abi(graph, cam, sample, tm
         total, visible = r.stats()
     assert f"triangles {total} visible {visible}" in out.stdout
     assert visible > 0 and np.array_equal(got, want)
+
+
+def test_veneer_refreshes_moved_meshes_and_draws_textures(headless, tmp_path):
+    """SURVEY section 8 f4 through the class surface: a mesh's world matrix changes between two RenderAuto calls (what
+    SceneGraph::Update does, SceneGraph.cpp:30-39) and the renderer picks it up (CUDARenderer::Render ->
+    b2r_mesh_set_world).  The second frame is the ORACLE's frame of the moved scene: Mesh::m_Position aliases the
+    translation of the world matrix (Mesh.h:50), so a shift d of the matrix is a mesh constructed d further along (the
+    device's matrix = matrix + position, CUDAMesh.cpp:16-18, doubles both).  Then CUDARenderer::DrawTextureGlobal / DrawTexture (CUDARenderer.h:43-45)
+    against a numpy model of the sampler."""
+    import copy
+    import struct
+    import zlib
+    import oracle_lib
+    sc = scenes.random_triangles_scene(640, 480, 300, seed=67, cull=0, n_meshes=2)
+    sc.meshes[0].position = (0.5, 0.25, 0.0)
+    d = (0.5, -0.25, 0.125)
+    # a 48 x 40 RGBA PNG written by hand (no filter, zlib stored through zlib.compress)
+    rng = np.random.default_rng(5)
+    tex = rng.integers(0, 256, (40, 48, 4), dtype=np.uint8)
+    raw = b"".join(b"\x00" + tex[y].tobytes() for y in range(40))
+
+    def chunk(t, data):
+        return struct.pack(">I", len(data)) + t + data + struct.pack(">I", zlib.crc32(t + data))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 48, 40, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    tp = str(tmp_path / "t.png")
+    open(tp, "wb").write(png)
+    sp, op = str(tmp_path / "s.b2rs"), str(tmp_path / "o.raw")
+    open(sp, "wb").write(sc.to_blob())
+    out = subprocess.run([headless, sp, op, "--move", *[str(x) for x in d], "--texture", tp, "1", "1", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    first = np.fromfile(op, dtype=np.uint32).reshape(sc.height, sc.width)
+    moved = np.fromfile(op + ".moved", dtype=np.uint32).reshape(sc.height, sc.width)
+    drawn = np.fromfile(op + ".tex", dtype=np.uint32).reshape(sc.height, sc.width)
+    assert np.array_equal(first, oracle_lib.render(sc, fill_rule=1)["framebuffer"])
+    sc2 = copy.copy(sc)
+    sc2.meshes = [copy.copy(m) for m in sc.meshes]
+    sc2.meshes[0].position = tuple(p + x for p, x in zip(sc.meshes[0].position, d))
+    want = oracle_lib.render(sc2, fill_rule=1)
+    assert not np.array_equal(first, moved)
+    assert np.array_equal(moved, want["framebuffer"]), "the frame after the move is not the oracle's frame of the moved scene"
+    assert f"moved: triangles {want['total_tris']} visible {want['visible_tris']}" in out.stdout
+    # DrawTextureGlobal, stretched, point sampling: CUDATextureSampler::SamplePoint at (x / W, y / H), truncating pack
+    # (CUDATextureSampler.cuh:80-104, RGBRaw.h:23-32); fma(u, w, 0.5) = the float64 evaluation rounded once
+    W, H = sc.width, sc.height
+    u = (np.arange(W, dtype=np.float32) / np.float32(W)).astype(np.float32)
+    v = (np.arange(H, dtype=np.float32) / np.float32(H)).astype(np.float32)
+    tx = (u.astype(np.float64) * 48 + 0.5).astype(np.float32).astype(np.int64)
+    ty = (v.astype(np.float64) * 40 + 0.5).astype(np.float32).astype(np.int64)
+    ok = (tx[None, :] < 48) & (ty[:, None] < 40)
+    s = tex[np.minimum(ty, 39)[:, None], np.minimum(tx, 47)[None, :]].astype(np.float32)
+    c = (s / np.float32(255.0)).astype(np.float32)                      # RGBColor in [0, 1]
+    c = np.where(ok[..., None], c[..., :3], np.array([1.0, 0.0, 1.0], np.float32))     # magenta outside
+    q = (c * np.float32(255.0)).astype(np.float32).astype(np.uint32) & 255
+    want_tex = (q[..., 0] << 16) | (q[..., 1] << 8) | q[..., 2]
+    assert np.array_equal(drawn[:H // 16 * 16, :W // 16 * 16], want_tex[:H // 16 * 16, :W // 16 * 16])
