@@ -51,10 +51,28 @@ def make_scene(workload: str):
     if workload == "spheres_small":                                        # quick functional check
         return scenes.sphere_grid_scene(WIDTH, HEIGHT, nx=5, ny=5)
     if workload == "fill64":
-        return scenes.fill_quads_scene(WIDTH, HEIGHT, layers=64, sample=1)  # BASELINE config 4
+        return make_fill_scene()                                            # BASELINE config 4
     if workload in ("vehicle480", "vehicle1080"):
         return make_vehicle_scene(*((640, 480) if workload == "vehicle480" else (1920, 1080)))   # BASELINE configs 1 / 2
     raise SystemExit(f"unknown workload {workload}")
+
+
+def make_fill_scene():
+    """BASELINE config 4: 64 stacked full-screen quads at 4K, linear sampling.  The diffuse map is the reference's bundled
+    uv_grid_2.png when oracle/build_ref.sh has copied the assets next to the reference binary - a data
+    file, decoded by the product's own PNG decoder - else a synthetic 1024^2 checker; `fill_texture` says which."""
+    path = os.path.join(ROOT, "oracle", "_ref", "resources", "uv_grid_2.png")
+    tex, src = None, "synthetic 1024x1024 checker"
+    if os.path.exists(path):
+        try:
+            from custom_gpgpu_rasterizer_b200.renderer import decode_png
+            tex = decode_png(path)
+            src = f"uv_grid_2.png ({tex.shape[1]}x{tex.shape[0]}, the reference's bundled map)"
+        except Exception:      # noqa: BLE001
+            tex = None
+    sc = scenes.fill_quads_scene(WIDTH, HEIGHT, layers=64, sample=1, texture=tex)
+    sc.fill_texture = src
+    return sc
 
 
 def make_vehicle_scene(width, height):
@@ -773,7 +791,7 @@ def fill_test(Renderer, _lib, torch, dev, args, peak):
     px = sc.width * sc.height
     rop_bytes = frags * 4 + frags * 8 + px * 8          # back-to-front: every fragment passes depth (F = Fp)
     t = stages["raster_shade"]
-    return {"workload": "BASELINE config 4: 64 stacked full-screen textured quads, 3840x2160, linear sampling",
+    return {"workload": "BASELINE config 4: 64 stacked full-screen textured quads, 3840x2160, linear sampling", "texture": getattr(sc, "fill_texture", None),
             "frames_per_s": 1e3 / ms, "ms_per_frame": ms, "fragments": frags, "gfragments_per_s": frags / (t / 1e3) / 1e9,
             "raster_shade_ms": t, "rop_equivalent_bytes": rop_bytes, "rop_equivalent_gbs": (rop_bytes / 1e9) / (t / 1e3),
             "frac_of_hbm_peak": (rop_bytes / 1e9) / (t / 1e3) / peak, "physical_write_back_bytes": px * 8, "stages_ms": stages}

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__
 	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords,
 	const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes,
 	uint4* __restrict__ marks /*vertex marks of the sliced vertex stage, or null*/, uint32_t markQuads,
-	PeerFlags waitPf, uint32_t waitSelf, uint32_t waitRanks /*0: no wait*/, uint32_t waitEpoch)
+	const __grid_constant__ PeerFlags waitPf, uint32_t waitSelf, uint32_t waitRanks /*0: no wait*/, uint32_t waitEpoch)
 {
 	pdlPrologue();
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(64) build_constants_kernel(const float* __rest
 // i.e. no longer reads the list set of the frame's ring slot - what a peer waits for before it stores the lists of a
 // later frame into that set (doneRanks = 0: no such signal).
 __global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long long* __restrict__ info, unsigned long long* __restrict__ hostInfo, uint32_t words,
-	uint32_t* landedFlag, uint32_t epoch, PeerFlags donePf, uint32_t doneRanks, uint32_t self)
+	uint32_t* landedFlag, uint32_t epoch, const __grid_constant__ PeerFlags donePf, uint32_t doneRanks, uint32_t self)
 {
 	pdlPrologue();
 	if (threadIdx.x < words) hostInfo[threadIdx.x] = info[threadIdx.x];      // visible to the host once the frame's `done` event has completed
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
 	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold,
 	uint32_t* __restrict__ longTiles, uint4* __restrict__ tileOrder, uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
-	ShardInbox inbox, uint32_t inboxRanks /*sharded front end: the heads (count, offset) of this rank's lists go to the inbox of each tile's owner; 0: no*/,
+	const __grid_constant__ ShardInbox inbox, uint32_t inboxRanks /*sharded front end: the heads (count, offset) of this rank's lists go to the inbox of each tile's owner; 0: no*/,
 	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[6]=lists sorted by the bitonic fallback,[8..13]=tiles per class*/)
 {
 	pdlPrologue();
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 // earlyTrigger = 0 (frame ring): the kernel does not release its programmatic dependents before it exits - the CTAs of
 // the raster kernel behind a barrier would otherwise become resident and sit out the wait for the slowest peer on
 // SM slots that the front ends of the following frames (other ring streams) could use.
-__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch,
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerFlags pf, uint32_t self, uint32_t n, uint32_t slotBase, uint32_t epoch,
 	uint32_t signal, uint32_t wait, unsigned long long* timeoutFlag /*device frameInfo[7] or a pinned host word*/, uint32_t earlyTrigger)
 {
 	asm volatile("griddepcontrol.wait;" ::: "memory");

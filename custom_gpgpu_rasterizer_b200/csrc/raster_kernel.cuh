@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 // tile's list is the sum of the heads the ranks pushed for it; the owned tiles are grouped into the same length
 // classes tile_scan_kernel uses on a single GPU (longest first), entries {tile, merged length, 0, 0}.  Also raises the
 // overflow flag if any rank's list buffer was too small (its marker word rides behind its offsets).
-__global__ void __launch_bounds__(256) shard_merge_heads_kernel(ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
+__global__ void __launch_bounds__(256) shard_merge_heads_kernel(const __grid_constant__ ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
 	uint4* __restrict__ tileOrder, unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256) shard_merge_heads_kernel(ShardTable T, ui
 // (the three vertices of every entry of every owned tile's list) in a bitmap over the transformed-vertex stream;
 // vertex_transform_marked_kernel then transforms exactly those.  With n ranks and interleaved tile ownership that is
 // about 1/n of the front-facing vertices instead of all vertices on every rank.  One warp per owned tile.
-__global__ void __launch_bounds__(256) shard_mark_vertices_kernel(ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
+__global__ void __launch_bounds__(256) shard_mark_vertices_kernel(const __grid_constant__ ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
 	const uint4* __restrict__ triRefs, uint32_t* __restrict__ marks, const unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(256) shard_mark_vertices_kernel(ShardTable T, 
 // 16-byte vectors; the few ids of the neighbouring lists that ride along belong to tiles t-1 / t+1, which
 // have other owners, so nobody reads them there.
 __global__ void __launch_bounds__(256) shard_push_lists_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
-	const uint32_t* __restrict__ binIds, uint32_t nTiles, ShardRegions R, uint32_t nRanks, uint32_t self,
+	const uint32_t* __restrict__ binIds, uint32_t nTiles, const __grid_constant__ ShardRegions R, uint32_t nRanks, uint32_t self,
 	const unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
