@@ -684,12 +684,33 @@ def run_b200(args, scene):
                         "frac_of_hbm_peak": ((b / 1e9) / (t / 1e3)) / (peak * world) if t > 0 else None}
     dominant = max(per_stage, key=lambda k: per_stage[k]["ms"])
     roof = per_stage[dominant]
-    traffic = None
+    # physical side of every stage, from the committed ncu capture of this build (profiles/ncu_traffic.json, written by
+    # tools/ncu_traffic.py): DRAM bytes per launch, and the issue-slot picture of the stage's dominant kernel.  Physical
+    # GB/s = those bytes / the stage time measured in THIS run.
+    traffic, dominant_kernel = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dominant)
-    except Exception:
+            prof = json.load(f).get(args.workload, {})
+        for k, st in per_stage.items():
+            p = prof.get(k)
+            if p is None or world != 1:
+                continue
+            nbytes = p["dram_bytes"] if isinstance(p, dict) else float(p)
+            st["physical_dram_bytes"] = nbytes
+            st["physical_gbs"] = (nbytes / 1e9) / (st["ms"] / 1e3) if st["ms"] > 0 else None
+            st["physical_frac_of_hbm_peak"] = st["physical_gbs"] / peak if st["ms"] > 0 else None
+            if isinstance(p, dict) and p.get("kernels"):
+                kn, kd = max(p["kernels"].items(), key=lambda kv: kv[1]["time_us"])
+                st["dominant_kernel"] = {"name": kn, "sm_throughput_pct": kd.get("sm_pct"), "dram_throughput_pct": kd.get("dram_pct"),
+                                         "threads_per_instruction": kd.get("threads_per_inst"), "issue_active_pct": kd.get("issue_active_pct")}
+        if world == 1 and dominant in prof:
+            traffic = per_stage[dominant].get("physical_dram_bytes")
+            dominant_kernel = per_stage[dominant].get("dominant_kernel")
+    except Exception:      # noqa: BLE001
         pass
+    phys_frac = per_stage[dominant].get("physical_frac_of_hbm_peak")
+    # honest label: a stage that keeps DRAM below 40 % of the measured peak is not bandwidth-bound, whatever its effective figure
+    bound = "hbm" if (phys_frac is None or phys_frac >= 0.4) else "issue/latency (DRAM < 40 % of peak: warp instruction issue and memory latency, see dominant_kernel)"
 
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -706,8 +727,9 @@ def run_b200(args, scene):
                              "counts summed over the ranks must equal the single-GPU frame's too.  A mismatch makes bench.py exit with status 3."},
         "list_sorter": {"tiles_sent_to_the_cta_sorter_by_the_warp_sorter": counters["sort_fallback_tiles"], "tiles_beyond_the_sorter": counters["unsorted_tiles"]},
         "stages_ms": stages, "stages": per_stage,
-        "roofline": {"kernel": dominant, "bound": "hbm", "achieved": roof["gbs"], "peak": peak * world, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
-                     "traffic": traffic if world == 1 else None, "peak_source": peak_src + ("" if world == 1 else f" x {world} GPUs"),
+        "roofline": {"kernel": dominant, "bound": bound, "achieved": roof["gbs"], "peak": peak * world, "unit": "GB/s", "frac": roof["frac_of_hbm_peak"],
+                     "traffic": traffic if world == 1 else None, "physical_frac": phys_frac, "dominant_kernel": dominant_kernel,
+                     "peak_source": peak_src + ("" if world == 1 else f" x {world} GPUs"),
                      "note": "achieved = algorithmic bytes of SURVEY section 8d (the reference's record sizes: EFFECTIVE bandwidth, a stage that moves fewer bytes than "
                              "the reference's layout can exceed 1; physical DRAM bytes of the stage per launch are in `traffic`, from the committed ncu capture) / stage "
                              "time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},

@@ -137,10 +137,13 @@ struct b2r_context
 	int ringDepth = 0;
 	cudaStream_t ringStream[kMaxFrameRing] = {};
 	cudaEvent_t ringDone[kMaxFrameRing] = {};     // raster + publish of the newest frame of that ring slot
+	cudaEvent_t ringRasterDone[kMaxFrameRing] = {}; // its raster kernel alone
+	int ringPrev2 = -1;                // ring slot of the frame before the previous one
+	int relaxedChain = 1;              // frame ring: raster kernels of consecutive frames may overlap (B2R_RING_RELAXED=0: strictly chained)
 	bool ringNeedsFork[kMaxFrameRing] = {};
 	int ringPrev = -1;                 // ring slot of the previous frame while it may still be in flight
 	uint32_t* dRangeScratch = nullptr;
-	DeviceVec<uint4> dVertexMarks[kMaxFrameRing];   // sliced vertex stage: one bit per transformed vertex, per ring slot
+	DeviceVec<uint4> dVertexMarks[kMaxFrameRing];   // sliced vertex stage: one byte per transformed vertex, per ring slot
 	int slicedVertex = 0;              // sharded front end: transform only the vertices of this rank's primitive slice;
 	                                   // the raster kernel transforms the vertices of its list entries itself (B2R_SHARD_SLICED_VERTEX)
 	int overlapFrontSharded = 1;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=0 switches it off)
@@ -179,6 +182,7 @@ struct b2r_context
 
 	// surfaces
 	uint32_t* dFramebuffer = nullptr; int32_t* dDepth = nullptr; float* dZ = nullptr; uint32_t* dWinner = nullptr;
+	int32_t* dDepthOf[2] = { nullptr, nullptr };    // integer depth surfaces, paired with the colour surfaces (one allocation)
 	uint32_t* boundFramebuffer = nullptr;
 	// pipelined Present: two colour surfaces; while one is copied to the host on copyStream the next
 	// frame renders into the other
@@ -251,10 +255,11 @@ int allocSurfaces(b2r_context* c)
 	const size_t n = (size_t)c->width * c->height;
 	// two colour surfaces in ONE allocation (pipelined Present; one IPC handle for the sharded mode)
 	CU(c, cudaMalloc((void**)&c->dFramebuffer, 2 * n * 4));
-	CU(c, cudaMalloc((void**)&c->dDepth, n * 4));
+	CU(c, cudaMalloc((void**)&c->dDepth, 2 * n * 4));
+	c->dDepthOf[0] = c->dDepth; c->dDepthOf[1] = c->dDepth + n;
 	CU(c, cudaMemset(c->dFramebuffer, 0, 2 * n * 4));     // CUDAWindowHelper.h:17-25 zero-initialises
 	c->dColour[0] = c->dFramebuffer; c->dColour[1] = c->dFramebuffer + n;
-	CU(c, cudaMemset(c->dDepth, 0, n * 4));
+	CU(c, cudaMemset(c->dDepth, 0, 2 * n * 4));
 	CU(c, finishFills(c));
 	return B2R_OK;
 }
@@ -673,8 +678,12 @@ int enqueueFrame(b2r_context* c)
 		{
 			// per-primitive CTAs, followed by the CTAs that scatter the cooperatively binned (big) triangles
 			const uint32_t primBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+			// sharded: the ids of tiles other ranks own are mirrored into those ranks' arenas as they are scattered
+			ShardRegions R{};
+			if (sh.bound)
+				for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], set, sh.self);
 			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, fs, B.rects.ptr, primLo, primHi, tileOffset,
-				B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp));
+				B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp, R, sh.bound ? (uint32_t)sh.n : 0u, (uint32_t)sh.self));
 			++c->kernelsLaunched;
 		}
 	}
@@ -685,14 +694,6 @@ int enqueueFrame(b2r_context* c)
 	{
 		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, fs, bigBins); if (r) return r;
 		c->kernelsLaunched += bigBins ? 2 : 1;
-	}
-	if (sh.bound && c->nPrims)
-	{
-		// mirror the sorted lists into their owners' memory (posted stores; landed by the time of the barrier)
-		ShardRegions R{};
-		for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], set, sh.self);
-		CU(c, launchFrameKernel(c, shard_push_lists_kernel, dim3((tiles + 7) / 8), dim3(256), 0, fs, tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, B.frameInfo));
-		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 5);
 	if (pipelined)
@@ -744,7 +745,7 @@ int enqueueFrame(b2r_context* c)
 			}
 			STAGE_EVENT(c, slot, 7);
 		}
-		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
+		A.depth = c->dDepthOf[c->colourIdx]; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
 		if (owned)
 		{
 			// light variant when the frame cannot reach the texture / visualiser paths
@@ -843,7 +844,7 @@ int enqueueFrameRing(b2r_context* c)
 	// bins, and - after the exchange - the vertices the lists of its own tiles refer to (shard_mark_vertices_kernel,
 	// vertex_transform_marked_kernel)
 	const bool sliced = sh.bound && c->slicedVertex;
-	const uint32_t markQuads = sliced ? (uint32_t)((c->nVtxOut + 127) / 128) : 0u;
+	const uint32_t markQuads = sliced ? (uint32_t)((c->nVtxOut + 15) / 16) : 0u;
 	if (sliced) CU(c, c->dVertexMarks[k].reserve(std::max<size_t>(markQuads, 1), s));
 	if (sliced && !sh.rangeValid)
 	{
@@ -953,8 +954,11 @@ int enqueueFrameRing(b2r_context* c)
 	if (c->nPrims)
 	{
 		const uint32_t primBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+		ShardRegions R{};
+		if (sh.bound)
+			for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], k, sh.self);
 		CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, rs, B.rects.ptr, primLo, primHi, tileOffset,
-			B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp));
+			B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp, R, sh.bound ? (uint32_t)sh.n : 0u, (uint32_t)sh.self));
 		++c->kernelsLaunched;
 	}
 	RING_STAGE_EVENT(4);
@@ -965,20 +969,15 @@ int enqueueFrameRing(b2r_context* c)
 		int r = enqueueListSort(c, B, tileCount, tileOffset, binIds, rs, bigBins); if (r) return r;
 		c->kernelsLaunched += bigBins ? 2 : 1;
 	}
-	if (sh.bound && c->nPrims)
-	{
-		ShardRegions R{};
-		for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], k, sh.self);
-		CU(c, launchFrameKernel(c, shard_push_lists_kernel, dim3((tiles + 7) / 8), dim3(256), 0, rs, tileCount, tileOffset, binIds, tiles, R, (uint32_t)sh.n, (uint32_t)sh.self, B.frameInfo));
-		++c->kernelsLaunched;
-	}
 	RING_STAGE_EVENT(5);
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
-		if (sh.bound) c->colourIdx = (int)(sh.frame & 1u);       // every rank writes rank 0's surface `frame & 1`
+		// the frames of the ring alternate strictly between the two colour + depth surface pairs (sharded: every rank writes
+		// rank 0's surface `frame & 1`), which is what lets consecutive raster kernels overlap (below)
+		c->colourIdx = sh.bound ? (int)(sh.frame & 1u) : (int)(c->seq & 1u);
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
 			// this surface is still being copied to the host by an earlier b2r_present_async (sharded: rank 0 arrives at
@@ -1014,17 +1013,27 @@ int enqueueFrameRing(b2r_context* c)
 				if (sliced && c->nVsChunks)
 				{
 					CU(c, launchFrameKernel(c, shard_mark_vertices_kernel, dim3((owned + 7) / 8), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, c->dTriRefs.ptr,
-						reinterpret_cast<uint32_t*>(c->dVertexMarks[k].ptr), B.frameInfo));
+						reinterpret_cast<uint8_t*>(c->dVertexMarks[k].ptr), B.frameInfo));
 					CU(c, launchFrameKernel(c, vertex_transform_marked_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, rs, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4,
-						reinterpret_cast<const uint32_t*>(c->dVertexMarks[k].ptr), sh.chunkLo, sh.chunkHi, B.frameInfo));
+						reinterpret_cast<const uint8_t*>(c->dVertexMarks[k].ptr), sh.chunkLo, sh.chunkHi, B.frameInfo));
 					c->kernelsLaunched += 2;
 				}
 			}
 			RING_STAGE_EVENT(7);
 		}
-		A.depth = c->dDepth; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
+		A.depth = c->dDepthOf[c->colourIdx]; A.zSurface = c->dZ; A.winnerSurface = c->dWinner;
 		// raster kernels in frame order: one depth surface, two colour surfaces, monotonic epochs
-		if (!waitedPrev && c->ringPrev >= 0 && c->ringPrev != k) CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0));
+		// Frames alternate between two colour + depth surface pairs, so the raster kernel of frame f only has to follow
+		// the raster of frame f-2 (same pair); consecutive frames' raster kernels may overlap - a rank's raster kernel is a
+		// few waves of latency-bound CTAs that do not fill the GPU on their own.  The publish kernels stay chained in frame
+		// order (below): the "colours landed" / "frame done" epochs must rise monotonically.  The debug surfaces (one pair)
+		// and the strict mode keep the raster kernels themselves in frame order.
+		const bool relaxed = c->relaxedChain && !c->debugSurfaces && !c->boundFramebuffer && !c->packedOutput;
+		if (!waitedPrev)
+		{
+			if (!relaxed) { if (c->ringPrev >= 0 && c->ringPrev != k) CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0)); }
+			else if (c->ringPrev2 >= 0 && c->ringPrev2 != k) CU(c, cudaStreamWaitEvent(rs, c->ringRasterDone[c->ringPrev2], 0));
+		}
 		if (owned)
 		{
 			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse));
@@ -1039,12 +1048,15 @@ int enqueueFrameRing(b2r_context* c)
 	uint32_t* landedFlag = nullptr;
 	if (sh.bound && !c->shardLocalColour)
 		landedFlag = reinterpret_cast<uint32_t*>(sh.self == 0 ? sh.arena : sh.peerArena[0]) + 8 + sh.self;
+	CU(c, cudaEventRecord(c->ringRasterDone[k], rs));
+	if (c->ringPrev >= 0 && c->ringPrev != k) CU(c, cudaStreamWaitEvent(rs, c->ringDone[c->ringPrev], 0));      // publish kernels in frame order
 	RING_STAGE_EVENT(6);
 #undef RING_STAGE_EVENT
 	CU(c, launchFrameKernel(c, publish_info_kernel, dim3(1), dim3(32), 0, rs, B.frameInfo, reinterpret_cast<unsigned long long*>(slot.hInfo), (uint32_t)(sizeof(b2r_context::HostInfo) / 8),
 		landedFlag, sh.frame, pf, sh.bound ? (uint32_t)sh.n : 0u, (uint32_t)sh.self));
 	++c->kernelsLaunched;
 	CU(c, cudaEventRecord(c->ringDone[k], rs));
+	c->ringPrev2 = c->ringPrev;
 	c->ringPrev = k;
 	CU(c, cudaEventRecord(slot.done, rs));
 	// the caller's stream observes the frame (events it records, Present, read-backs) without holding back later frames
@@ -1083,7 +1095,7 @@ int validateFrame(b2r_context* c)
 			return fail(c, B2R_E_STATE, "sharded front end: a peer rank's colours did not arrive within 4 s");
 		}
 		c->vtxNeedsFork = true; c->rasterPending[0] = c->rasterPending[1] = false; c->listsReadyPending[0] = c->listsReadyPending[1] = false;
-		c->ringPrev = -1;
+		c->ringPrev = -1; c->ringPrev2 = -1;
 		for (uint64_t k = 0; k < kRing; ++k)
 		{
 			b2r_context::Slot& slot = c->slots[(c->seq + k) % kRing];     // oldest first
@@ -1190,6 +1202,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	if (const char* e = getenv("B2R_OVERLAP_FRONT_SHARDED")) c->overlapFrontSharded = atoi(e) != 0;
 	if (const char* e = getenv("B2R_FRAME_RING")) { const int d = atoi(e); c->ringDepth = (d >= 2 && d <= kMaxFrameRing) ? d : 0; }   // see B2R_OPT_FRAME_RING
 	if (const char* e = getenv("B2R_SHARD_SLICED_VERTEX")) c->slicedVertex = atoi(e) != 0;       // see B2R_OPT_SHARD_SLICED_VERTEX
+	if (const char* e = getenv("B2R_RING_RELAXED")) c->relaxedChain = atoi(e) != 0;
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));
@@ -1218,6 +1231,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	{
 		CUC(cudaStreamCreateWithFlags(&c->ringStream[i], cudaStreamNonBlocking));
 		CUC(cudaEventCreateWithFlags(&c->ringDone[i], cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&c->ringRasterDone[i], cudaEventDisableTiming));
 	}
 	for (auto& slot : c->slots)
 	{
@@ -1249,6 +1263,7 @@ void b2r_destroy(b2r_context* c)
 	{
 		if (c->ringStream[i]) { cudaStreamSynchronize(c->ringStream[i]); cudaStreamDestroy(c->ringStream[i]); }
 		if (c->ringDone[i]) cudaEventDestroy(c->ringDone[i]);
+		if (c->ringRasterDone[i]) cudaEventDestroy(c->ringRasterDone[i]);
 	}
 	cudaFree(c->dRangeScratch);
 	for (auto& v : c->dVertexMarks) v.release();
@@ -1670,7 +1685,7 @@ int b2r_present_wait(b2r_context* c)
 	return validateFrame(c);
 }
 
-int b2r_read_depth(b2r_context* c, int32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dDepth, out, "read_depth"); }
+int b2r_read_depth(b2r_context* c, int32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dDepthOf[c->lastColourIdx], out, "read_depth"); }
 int b2r_read_z(b2r_context* c, float* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dZ, out, "read_z"); }
 int b2r_read_winner(b2r_context* c, uint32_t* out) { if (!c) return B2R_E_INVALID; return readSurface(c, c->dWinner, out, "read_winner"); }
 
@@ -1797,7 +1812,7 @@ int b2r_device_surfaces(b2r_context* c, void** framebuffer, void** depth)
 {
 	if (!c) return B2R_E_INVALID;
 	if (framebuffer) *framebuffer = c->boundFramebuffer ? c->boundFramebuffer : c->dColour[c->lastColourIdx];
-	if (depth) *depth = c->dDepth;
+	if (depth) *depth = c->dDepthOf[c->lastColourIdx];
 	return B2R_OK;
 }
 

@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 }
 
 // sharded front end with a sliced vertex stage: the vertices shard_mark_vertices_kernel marked for this rank's raster
-// kernel (one bit per transformed vertex), chunks [skipLo, skipHi) excepted - the rank's own slice, transformed before
+// kernel (one byte per transformed vertex), chunks [skipLo, skipHi) excepted - the rank's own slice, transformed before
 // binning.  Same function, same bits as vertex_transform_kernel.
 __global__ void __launch_bounds__(kChunk) vertex_transform_marked_kernel(
 	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes, const float4* __restrict__ posIn, float4* __restrict__ pos4,
-	const uint32_t* __restrict__ marks, uint32_t skipLo, uint32_t skipHi, const unsigned long long* __restrict__ frameInfo)
+	const uint8_t* __restrict__ marks, uint32_t skipLo, uint32_t skipHi, const unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
 	if (frameInfo[1]) return;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_marked_kernel(
 	__shared__ float sMat[16];
 	const Chunk ch = chunks[blockIdx.x];
 	const uint32_t v = ch.outStart + threadIdx.x;
-	const bool want = threadIdx.x < ch.count && ((__ldg(marks + (v >> 5)) >> (v & 31u)) & 1u);
+	const bool want = threadIdx.x < ch.count && __ldg(marks + v) != 0;
 	if (!__syncthreads_or(want)) return;
 	if (threadIdx.x < 16) sMat[threadIdx.x] = meshes[ch.mesh].wvp[threadIdx.x];
 	float4 in = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -319,10 +319,23 @@ __global__ void __launch_bounds__(32) publish_info_kernel(const unsigned long lo
 // of different warps cover disjoint id ranges - the property bin_sort_runs_kernel relies on.
 // Warps whose union is large (incoherent geometry) fall back to per-lane iteration.
 constexpr uint32_t kUnionTilesMax = 64;
+// Sharded front end: an id scattered into the list of a tile another rank owns is also stored into the region reserved for
+// this rank in the owner's arena, at the same offset as locally (posted NVLink store; the lanes of a run write consecutive
+// words, which travel as one transaction), so the exchange of the lists needs no pass of its own.
+struct ListMirror { const ShardRegions* regions; uint32_t nRanks, self; };       // nRanks = 0: no mirror
+__device__ __forceinline__ void mirrorStore(const ListMirror& M, uint32_t tile, uint32_t pos, uint32_t prim)
+{
+	if (M.nRanks)
+	{
+		const uint32_t owner = tile % M.nRanks;
+		if (owner != M.self) M.regions->region[owner][pos] = prim;
+	}
+}
+
 template <bool SCATTER>
 __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, int by0, int by1, uint32_t prim,
 	uint32_t* __restrict__ counters /*tileCount or tileCursor*/, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ binIds,
-	const FrameParams& fp)
+	const FrameParams& fp, const ListMirror& M = ListMirror{ nullptr, 0u, 0u })
 {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned have = __ballot_sync(0xFFFFFFFFu, nTiles > 0);
@@ -358,7 +371,13 @@ __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, 
 				{
 					const unsigned mask = __shfl_sync(0xFFFFFFFFu, myMask, u);
 					const uint32_t base = __shfl_sync(0xFFFFFFFFu, myBase, u);
-					if ((mask >> lane) & 1u) binIds[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = prim;
+					const uint32_t tileU = M.nRanks ? __shfl_sync(0xFFFFFFFFu, myTile, u) : 0u;
+					if ((mask >> lane) & 1u)
+					{
+						const uint32_t pos = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+						binIds[pos] = prim;
+						mirrorStore(M, tileU, pos, prim);
+					}
 				}
 			}
 			else if (myMask)
@@ -378,7 +397,12 @@ __device__ __forceinline__ void warpBinRects(uint32_t nTiles, int bx0, int bx1, 
 				if (!tileOwned(fp, tile)) tile = kNoTile;
 			}
 			const uint32_t slot = warpTileAdd<SCATTER>(counters, tile);
-			if (SCATTER && tile != kNoTile) binIds[__ldg(tileOffset + tile) + slot] = prim;
+			if (SCATTER && tile != kNoTile)
+			{
+				const uint32_t pos = __ldg(tileOffset + tile) + slot;
+				binIds[pos] = prim;
+				mirrorStore(M, tile, pos, prim);
+			}
 		}
 	}
 }
@@ -542,7 +566,7 @@ template <bool SCATTER>
 __device__ __forceinline__ void binBigBody(uint32_t cta, uint32_t nCtas,
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, const uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
-	uint32_t* __restrict__ binIds, const FrameParams& fp)
+	uint32_t* __restrict__ binIds, const FrameParams& fp, const ListMirror& M = ListMirror{ nullptr, 0u, 0u })
 {
 	const uint32_t nBig = counters[1];
 	for (uint32_t b = cta; b < nBig; b += nCtas)
@@ -556,7 +580,11 @@ __device__ __forceinline__ void binBigBody(uint32_t cta, uint32_t nCtas,
 			const uint32_t tile = (uint32_t)(bx0 + i % w) + (uint32_t)(by0 + i / w) * fp.binsX;
 			if (!tileOwned(fp, tile)) continue;
 			if (SCATTER)
-				binIds[tileOffset[tile] + atomicAdd(&tileCursor[tile], 1u)] = prim;
+			{
+				const uint32_t pos = tileOffset[tile] + atomicAdd(&tileCursor[tile], 1u);
+				binIds[pos] = prim;
+				mirrorStore(M, tile, pos, prim);
+			}
 			else
 				atomicAdd(&tileCount[tile], 1u);
 		}
@@ -769,14 +797,16 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	const uint2* __restrict__ rects, uint32_t primLo, uint32_t primHi, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ binIds,
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, uint32_t primBlocks,
-	const unsigned long long* __restrict__ frameInfo, FrameParams fp)
+	const unsigned long long* __restrict__ frameInfo, FrameParams fp,
+	const __grid_constant__ ShardRegions mirror, uint32_t mirrorRanks /*sharded front end: number of ranks, else 0*/, uint32_t mirrorSelf)
 {
 	pdlPrologue();
 	if (frameInfo[1]) return;   // capacity overflow: the host regrows the list buffer and re-runs the frame
+	const ListMirror M{ &mirror, mirrorRanks, mirrorSelf };
 	if (blockIdx.x >= primBlocks)
 	{
 		// the CTAs behind the per-primitive part scatter the cooperatively binned (big) triangles
-		binBigBody<true>(blockIdx.x - primBlocks, gridDim.x - primBlocks, bigList, counters, rects, nullptr, tileOffset, tileCursor, binIds, fp);
+		binBigBody<true>(blockIdx.x - primBlocks, gridDim.x - primBlocks, bigList, counters, rects, nullptr, tileOffset, tileCursor, binIds, fp, M);
 		return;
 	}
 	// kScatterPerThread primitives per thread (a CTA covers kScatterPerThread * 256 consecutive ids): the rectangle
@@ -800,7 +830,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 			nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
 			if (nTiles > fp.bigRectTiles) nTiles = 0;   // binBigBody
 		}
-		warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp);
+		warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp, M);
 	}
 }
 

@@ -672,11 +672,12 @@ __global__ void __launch_bounds__(256) shard_merge_heads_kernel(const __grid_con
 
 // Sharded front end with a sliced vertex stage: a rank transforms the vertices its own primitive slice refers to before
 // it bins them, and - here, once the lists of its tiles have arrived - marks the vertices its RASTER kernel will need
-// (the three vertices of every entry of every owned tile's list) in a bitmap over the transformed-vertex stream;
+// (the three vertices of every entry of every owned tile's list) in a byte map over the transformed-vertex stream
+// (plain idempotent stores: neighbouring triangles share their vertices, a bit map would need contended atomics);
 // vertex_transform_marked_kernel then transforms exactly those.  With n ranks and interleaved tile ownership that is
 // about 1/n of the front-facing vertices instead of all vertices on every rank.  One warp per owned tile.
 __global__ void __launch_bounds__(256) shard_mark_vertices_kernel(const __grid_constant__ ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
-	const uint4* __restrict__ triRefs, uint32_t* __restrict__ marks, const unsigned long long* __restrict__ frameInfo)
+	const uint4* __restrict__ triRefs, uint8_t* __restrict__ marks, const unsigned long long* __restrict__ frameInfo)
 {
 	pdlPrologue();
 	if (frameInfo[1]) return;
@@ -691,33 +692,9 @@ __global__ void __launch_bounds__(256) shard_mark_vertices_kernel(const __grid_c
 		for (uint32_t e = lane; e < cnt; e += 32)
 		{
 			const uint4 tr = __ldg(triRefs + __ldg(seg + e));
-			// (plain test before the atomic: neighbouring triangles share their vertices, most bits are set already)
-			if (!((marks[tr.x >> 5] >> (tr.x & 31u)) & 1u)) atomicOr(&marks[tr.x >> 5], 1u << (tr.x & 31u));
-			if (!((marks[tr.y >> 5] >> (tr.y & 31u)) & 1u)) atomicOr(&marks[tr.y >> 5], 1u << (tr.y & 31u));
-			if (!((marks[tr.z >> 5] >> (tr.z & 31u)) & 1u)) atomicOr(&marks[tr.z >> 5], 1u << (tr.z & 31u));
+			marks[tr.x] = 1; marks[tr.y] = 1; marks[tr.z] = 1;
 		}
 	}
-}
-
-// Sharded front end, exchange step 2, after the scatter: mirror the list of every tile into its owner's memory, at the SAME offset inside the region
-// reserved there for this rank, so no rank needs another rank's offsets.  Posted NVLink stores of aligned
-// 16-byte vectors; the few ids of the neighbouring lists that ride along belong to tiles t-1 / t+1, which
-// have other owners, so nobody reads them there.
-__global__ void __launch_bounds__(256) shard_push_lists_kernel(const uint32_t* __restrict__ tileCount, const uint32_t* __restrict__ tileOffset,
-	const uint32_t* __restrict__ binIds, uint32_t nTiles, const __grid_constant__ ShardRegions R, uint32_t nRanks, uint32_t self,
-	const unsigned long long* __restrict__ frameInfo)
-{
-	pdlPrologue();
-	if (frameInfo[1]) return;
-	const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
-	if (t >= nTiles) return;
-	const uint32_t owner = t % nRanks;
-	if (owner == self) return;
-	const uint32_t cnt = __ldg(tileCount + t), off = __ldg(tileOffset + t);
-	if (!cnt) return;
-	const uint4* src = reinterpret_cast<const uint4*>(binIds);
-	uint4* dst = reinterpret_cast<uint4*>(R.region[owner]);
-	for (uint32_t v = (off >> 2) + lane, vEnd = (off + cnt + 3) >> 2; v < vEnd; v += 32) dst[v] = src[v];
 }
 
 // CUDARenderer::DrawTexture / DrawTextureGlobal (testing aids of the reference, CUDARenderer.cu:1565-1620, 1968-2012): the

@@ -339,3 +339,34 @@ def test_moving_meshes_set_world_frames_in_flight():
             assert np.array_equal(counts, o["bin_counts"]) and np.array_equal(ids, o["bin_ids"])
             total, visible = r.stats()
             assert visible == o["visible_tris"]
+
+
+@pytest.mark.parametrize("ring", [2, 3, 4])
+def test_frame_ring_frames_equal_the_oracle(ring):
+    """B2R_OPT_FRAME_RING = D (what bench.py runs with): frame f goes from its constants to its raster kernel on ring stream
+    f mod D with its own buffer set.  Ten frames of a moving camera enqueued back to back - tiny triangles (in-CTA list sort,
+    long lists), a textured soup (bitonic fallback of the sort, full raster variant) - each presented frame must be the
+    oracle's, and so must winners, depth and the ascending lists of the last one."""
+    import dataclasses
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer, host_camera
+    for sc in (scenes.sphere_grid_scene(800, 448, nx=5, ny=3, stacks=61, slices=80, cam_z=11.0),
+               scenes.random_triangles_scene(640, 480, 500, seed=97, cull=0, textured=True, n_meshes=3, sample=1)):
+        cams = [dataclasses.replace(sc, cam_pos=(sc.cam_pos[0] + 0.12 * k - 0.5, sc.cam_pos[1] + 0.05 * (k % 3), sc.cam_pos[2] - 0.15 * k)) for k in range(10)]
+        wants = [oracle_lib.render(c, fill_rule=1) for c in cams]
+        with Renderer(sc.width, sc.height) as r:
+            r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+            r.set_option(_lib.OPT_FRAME_RING, ring)
+            r.load_scene(sc)
+            bufs = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+            for c, b in zip(cams, bufs):
+                r.render_scene(c, sync=False)
+                r.present_async(b)
+            r.present_wait()
+            for k, (b, o) in enumerate(zip(bufs, wants)):
+                d = np.abs(parity.channels(b) - parity.channels(o["framebuffer"])).max()
+                assert d <= (1 if sc.textures else 0), f"{sc.name}, ring {ring}: frame {k} differs from the oracle by {d} LSB"
+            o = wants[-1]
+            assert np.array_equal(r.depth(), o["depth"]) and np.array_equal(r.winner(), o["winner"])
+            counts, _, ids = r.bin_lists()
+            assert np.array_equal(counts, o["bin_counts"]) and np.array_equal(ids, o["bin_ids"])

@@ -185,11 +185,10 @@ class Trace:
         "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5},
         "bin_big_count_kernel": {"bigList": 0, "counters": 1, "rects": 2, "tileCount": 3},
         "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "counters": 10, "frameInfo": 13},
-        "bin_scatter_kernel": {"rects": 0, "tileOffset": 3, "tileCursor": 4, "binIds": 5, "bigList": 6, "counters": 7, "frameInfo": 9},
+        "bin_scatter_kernel": {"rects": 0, "tileOffset": 3, "tileCursor": 4, "binIds": 5, "bigList": 6, "counters": 7, "frameInfo": 9},      # args[11] = ShardRegions: the mirror of the lists in the owners' arenas
         "bin_sort_tiles_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 4},
         "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
         "shard_merge_heads_kernel": {"tileOrder": 4, "frameInfo": 5},
-        "shard_push_lists_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 7},
         "publish_info_kernel": {"frameInfo": 0},
     }
     RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "meshConst": 6, "frameInfo": 8, "tileOrder": 13 + 3 * K_MAX_RANKS}
@@ -244,7 +243,7 @@ class Trace:
                 get = lambda d, kernel: next((o for o in frames[d][i] if self.short(o) == kernel), None)      # noqa: E731
                 rasters = [get(d, "raster_shade_kernel") for d in range(ranks)]
                 heads = [get(d, "tile_scan_kernel") for d in range(ranks)]          # the scan kernel pushes the heads (its ShardInbox argument)
-                lists = [get(d, "shard_push_lists_kernel") for d in range(ranks)]
+                lists = [get(d, "bin_scatter_kernel") for d in range(ranks)]          # the scatter kernel mirrors the lists (its ShardRegions argument)
                 if any(x is None for x in rasters + heads):
                     errs.append(f"frame {i}: a rank has no raster / push-heads launch")
                     continue
@@ -280,7 +279,7 @@ class Trace:
                         if p == q:
                             want_ids = self._ptr(rasters[q]["args"][0], 2)
                         else:
-                            want_ids = self._ptr(lists[p]["args"][4], q) if lists[p] is not None else got_ids
+                            want_ids = self._ptr(lists[p]["args"][11], q) if lists[p] is not None else got_ids
                         if want_ids != got_ids:
                             errs.append(f"frame {i}: rank {q} reads the lists of rank {p} at {got_ids:#x}, they are at {want_ids:#x}")
         return errs
