@@ -45,6 +45,6 @@ for arg in sys.argv[1:]:
         s["kernels"][k] = {"time_us": round(t, 2), "dram_bytes": rd + wr, "sm_pct": num(r[col["sm__throughput.avg.pct_of_peak_sustained_elapsed"]]),
                            "dram_pct": num(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
                            "threads_per_inst": num(r[col["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
-                           "issue_active_pct": num(r[col["smsp__issue_active.avg.pct"]]) if "smsp__issue_active.avg.pct" in col else None}
+                           "issue_active_pct": num(r[col["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]]) if "sm__issue_active.avg.pct_of_peak_sustained_elapsed" in col else None}
     out[name] = stages
 print(json.dumps(out, indent=1))
