@@ -252,6 +252,39 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def calibrate_bands(torch, dist, dev, shared, scene, rank, world, barrier, reps=30):
+    """Rows [begin, end) of the frame per rank for the distributed Present, in proportion to the device->host rate every rank
+    reaches while ALL ranks copy into the shared host frame (whole 16-row tile rows; every rank gets at least one)."""
+    rows16 = (scene.height + 15) // 16
+    n = scene.width * (scene.height // world // 16 * 16 or 16)               # pixels of an equal band
+    src = torch.zeros(n, dtype=torch.int32, device=dev)
+    dst = torch.from_numpy(shared[:scene.width * scene.height].view(np.int32))[rank * n: rank * n + n] if rank * n + n <= scene.width * scene.height else None
+    if dst is None:
+        dst = torch.from_numpy(shared[:n].view(np.int32))
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    rate = n * 4 * reps / (time.perf_counter() - t0)
+    barrier()
+    rates = [None] * world
+    dist.all_gather_object(rates, rate)
+    w = np.array([max(float(x), 1.0) for x in rates])
+    share = np.maximum(np.round(np.cumsum(w) / w.sum() * rows16).astype(int), np.arange(1, world + 1))     # cumulative tile rows, >= 1 each
+    share = np.minimum(share, rows16 - (world - 1 - np.arange(world)))
+    share = np.maximum.accumulate(np.clip(share, 0, rows16))      # (fewer tile rows than ranks: some bands stay empty)
+    share[-1] = rows16
+    bounds, lo = [], 0
+    for hi in share:
+        bounds.append((min(lo * 16, scene.height), min(int(hi) * 16, scene.height)))
+        lo = int(hi)
+    return bounds
+
+
 class SharedHostFrames:
     """Host memory shared by the ranks of one box (a file in /dev/shm mapped by every rank): the frame a distributed Present
     composes.  Rank 0 creates and removes the file."""
@@ -533,10 +566,18 @@ def run_b200(args, scene):
         # (b2r_present_band_async).  "tiles": every rank keeps the colours of its tiles and stores them into the host frame
         # from a kernel (b2r_present_tiles_async); nothing crosses NVLink.
         tiles_mode = args.present == "tiles"
-        present = r.present_tiles_async if tiles_mode else r.present_band_async
         shm = SharedHostFrames(f"b2r_bench_{os.environ.get('MASTER_PORT', '0')}", 2 * frame_bytes, rank, barrier)
         host_fb = shm.array.reshape(2, scene.height, scene.width)
         r.register_host_frame(shm.array)
+        band_rows = None
+        if tiles_mode:
+            present = r.present_tiles_async
+        else:
+            # the GPUs of a box do not always reach the host equally fast (measured on this pool's 8-GPU boxes: four links at
+            # ~16 GB/s, four at ~48 GB/s when all copy at once), so the bands are sized by a short calibration: every rank
+            # copies 1/N of a frame into the shared frame 30 times, all ranks at once, and gets rows in proportion to its rate
+            band_rows = calibrate_bands(torch, dist, dev, shm.array, scene, rank, world, barrier)
+            present = lambda off: r.present_rows_async(off, band_rows[rank][0], band_rows[rank][1])      # noqa: E731
         if tiles_mode:
             r.set_option(_lib.OPT_SHARD_LOCAL_COLOUR, 1)
         for i in range(2):
@@ -735,6 +776,8 @@ def run_b200(args, scene):
                              "time from CUDA events between the stages on the launching stream, averaged over %d frames" % n_timed},
         "e2e": {"value": args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 64,
                 "d2h_bytes_per_step": scene.width * scene.height * 4,
+                "present": (args.present if distributed else "rank 0") if world > 1 else "single GPU",
+                "band_rows_per_rank": [b[1] - b[0] for b in band_rows] if (distributed and band_rows) else None,
                 "note": ("per frame: view-projection matrix from the host (zero-copy read; per-mesh constants are built on the device) + b2r_render + " +
                          ("DISTRIBUTED Present into one host frame all ranks share (/dev/shm mapping registered with cudaHostRegister): " +
                           ("every rank stores the tiles it owns from a kernel over its own PCIe link (b2r_present_tiles_async)" if args.present == "tiles" else

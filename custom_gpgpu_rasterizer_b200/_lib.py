@@ -64,6 +64,7 @@ ABI = {
     "b2r_host_frame_register": (_i32, [_vp, _vp, _u64]),
     "b2r_present_tiles_async": (_i32, [_vp, _u64]),
     "b2r_present_band_async": (_i32, [_vp, _u64]),
+    "b2r_present_rows_async": (_i32, [_vp, _u64, _u32, _u32]),
     "b2r_read_depth": (_i32, [_vp, _vp]),
     "b2r_read_z": (_i32, [_vp, _vp]),
     "b2r_read_winner": (_i32, [_vp, _vp]),

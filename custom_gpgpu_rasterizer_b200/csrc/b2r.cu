@@ -612,7 +612,7 @@ int enqueueFrame(b2r_context* c)
 		if (c->rasterPending[g]) CU(c, cudaStreamWaitEvent(v, c->rasterDone[g], 0));
 		CU(c, launchFrameKernel(c, build_constants_kernel, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((nMeshes + 63) / 64, (uint32_t)c->numSMs * 4))), dim3(64), 0, v, 
 			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes));
-		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, v, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
+		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3((c->nVsChunks + kVsPerCta - 1) / kVsPerCta), dim3(kChunk), 0, v, c->dVsChunks.ptr, c->nVsChunks, meshConst, c->dPosIn.ptr, pos4));
 		c->kernelsLaunched += 2;
 		CU(c, cudaEventRecord(c->vtxDone[g], v));
 	}
@@ -641,7 +641,7 @@ int enqueueFrame(b2r_context* c)
 
 	if (c->nVsChunks && !overlap)
 	{
-		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, fs, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4));
+		CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3((c->nVsChunks + kVsPerCta - 1) / kVsPerCta), dim3(kChunk), 0, fs, c->dVsChunks.ptr, c->nVsChunks, meshConst, c->dPosIn.ptr, pos4));
 		++c->kernelsLaunched;
 	}
 	STAGE_EVENT(c, slot, 1);
@@ -920,7 +920,7 @@ int enqueueFrameRing(b2r_context* c)
 		const uint32_t cLo = sliced ? sh.chunkLo : 0u, cHi = sliced ? sh.chunkHi : c->nVsChunks;
 		if (cHi > cLo)
 		{
-			CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3(cHi - cLo), dim3(kChunk), 0, rs, c->dVsChunks.ptr + cLo, meshConst, c->dPosIn.ptr, pos4));
+			CU(c, launchFrameKernel(c, vertex_transform_kernel, dim3((cHi - cLo + kVsPerCta - 1) / kVsPerCta), dim3(kChunk), 0, rs, c->dVsChunks.ptr + cLo, cHi - cLo, meshConst, c->dPosIn.ptr, pos4));
 			++c->kernelsLaunched;
 		}
 	}
@@ -1639,7 +1639,7 @@ int b2r_present_tiles_async(b2r_context* c, uint64_t byteOffset)
 	return B2R_OK;
 }
 
-int b2r_present_band_async(b2r_context* c, uint64_t byteOffset)
+static int presentRows(b2r_context* c, uint64_t byteOffset, bool explicitRows, uint32_t rowBegin, uint32_t rowEnd)
 {
 	if (!c) return B2R_E_INVALID;
 	if (!c->haveFrame) return fail(c, B2R_E_STATE, "present_band_async: nothing rendered yet");
@@ -1655,7 +1655,12 @@ int b2r_present_band_async(b2r_context* c, uint64_t byteOffset)
 	// this rank's band: whole rows of bins
 	const uint32_t n = sh.bound ? (uint32_t)sh.n : 1u, self = sh.bound ? (uint32_t)sh.self : 0u;
 	const uint32_t binRows = (c->binsY + n - 1) / n;
-	const uint64_t row0 = std::min<uint64_t>((uint64_t)self * binRows * c->binH, c->height), row1 = std::min<uint64_t>((uint64_t)(self + 1) * binRows * c->binH, c->height);
+	uint64_t row0 = std::min<uint64_t>((uint64_t)self * binRows * c->binH, c->height), row1 = std::min<uint64_t>((uint64_t)(self + 1) * binRows * c->binH, c->height);
+	if (explicitRows)
+	{
+		if (rowBegin > rowEnd || rowEnd > c->height) return fail(c, B2R_E_INVALID, "present_rows_async: rows [%u, %u) outside the %u rows of the frame", rowBegin, rowEnd, c->height);
+		row0 = rowBegin; row1 = rowEnd;
+	}
 	CU(c, cudaEventRecord(c->frameDone, c->stream));
 	CU(c, cudaStreamWaitEvent(c->copyStream, c->frameDone, 0));
 	const uint32_t* src = c->dColour[idx];
@@ -1675,6 +1680,9 @@ int b2r_present_band_async(b2r_context* c, uint64_t byteOffset)
 	if (!sh.bound) c->colourIdx = idx ^ 1;          // the next frame renders into the other surface (sharded: frame parity)
 	return B2R_OK;
 }
+
+int b2r_present_band_async(b2r_context* c, uint64_t byteOffset) { return presentRows(c, byteOffset, false, 0u, 0u); }
+int b2r_present_rows_async(b2r_context* c, uint64_t byteOffset, uint32_t rowBegin, uint32_t rowEnd) { return presentRows(c, byteOffset, true, rowBegin, rowEnd); }
 
 int b2r_present_wait(b2r_context* c)
 {

@@ -60,20 +60,46 @@ __device__ __forceinline__ float4 transformPosition(const float* m /*WVP, data[c
 	return p;
 }
 
-// vertex transform: one CTA per chunk of 256 vertices of one mesh; 16 B in, 16 B out, coalesced.
+// vertex transform: one CTA per kVsPerCta chunks of 256 vertices (a chunk belongs to one mesh); 16 B in, 16 B out, coalesced.
+// The kernel is latency-bound (chunk descriptor -> position -> 3 IEEE divisions -> store), so a thread works on kVsPerCta
+// vertices whose descriptor and position loads are all issued before the first is used.
+#ifndef B2R_VS_PER_CTA
+#define B2R_VS_PER_CTA 4
+#endif
+constexpr uint32_t kVsPerCta = B2R_VS_PER_CTA;
 __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
-	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes,
+	const Chunk* __restrict__ chunks, uint32_t nChunks, const MeshConst* __restrict__ meshes,
 	const float4* __restrict__ posIn, float4* __restrict__ pos4)
 {
 	pdlPrologue();
-	__shared__ float sMat[16];
-	const Chunk ch = chunks[blockIdx.x];
-	if (threadIdx.x < 16) sMat[threadIdx.x] = meshes[ch.mesh].wvp[threadIdx.x];
-	float4 in = make_float4(0.f, 0.f, 0.f, 1.f);
-	if (threadIdx.x < ch.count) in = __ldcs(posIn + (size_t)ch.inStart + threadIdx.x);
+	__shared__ float sMat[kVsPerCta][16];
+	uint32_t mesh[kVsPerCta], count[kVsPerCta], inStart[kVsPerCta], outStart[kVsPerCta];
+	float4 in[kVsPerCta];
+	#pragma unroll
+	for (uint32_t k = 0; k < kVsPerCta; ++k)
+	{
+		const uint32_t c = blockIdx.x * kVsPerCta + k;
+		uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+		if (c < nChunks)
+		{
+			const uint2* d = reinterpret_cast<const uint2*>(chunks + c);      // {mesh, count}, {inStart, outStart}, ...
+			a = __ldg(d); b = __ldg(d + 1);
+		}
+		mesh[k] = a.x; count[k] = a.y; inStart[k] = b.x; outStart[k] = b.y;
+	}
+	#pragma unroll
+	for (uint32_t k = 0; k < kVsPerCta; ++k)
+	{
+		in[k] = make_float4(0.f, 0.f, 0.f, 1.f);
+		if (threadIdx.x < count[k]) in[k] = __ldcs(posIn + (size_t)inStart[k] + threadIdx.x);
+	}
+	#pragma unroll
+	for (uint32_t k = 0; k < kVsPerCta; ++k)
+		if ((threadIdx.x >> 4) == k && count[k]) sMat[k][threadIdx.x & 15u] = meshes[mesh[k]].wvp[threadIdx.x & 15u];
 	__syncthreads();
-	if (threadIdx.x >= ch.count) return;
-	pos4[(size_t)ch.outStart + threadIdx.x] = transformPosition(sMat, in.x, in.y, in.z);
+	#pragma unroll
+	for (uint32_t k = 0; k < kVsPerCta; ++k)
+		if (threadIdx.x < count[k]) pos4[(size_t)outStart[k] + threadIdx.x] = transformPosition(sMat[k], in[k].x, in[k].y, in[k].z);
 }
 
 // sharded front end with a sliced vertex stage: the vertices shard_mark_vertices_kernel marked for this rank's raster

@@ -224,6 +224,10 @@ class Renderer:
         frame (+ byte_offset) with this rank's own copy engine / PCIe link."""
         self._check(lib.b2r_present_band_async(self._ctx, int(byte_offset)))
 
+    def present_rows_async(self, byte_offset: int, row_begin: int, row_end: int):
+        """present_band_async with the band chosen by the caller: rows [row_begin, row_end) of the frame."""
+        self._check(lib.b2r_present_rows_async(self._ctx, int(byte_offset), int(row_begin), int(row_end)))
+
     def present_wait(self):
         self._check(lib.b2r_present_wait(self._ctx))
 

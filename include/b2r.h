@@ -202,6 +202,10 @@ int b2r_present_tiles_async(b2r_context* ctx, uint64_t byte_offset);
  * so no rank overwrites the surface while any band of it is still being read.  On a context without a sharded group
  * the band is the whole frame. */
 int b2r_present_band_async(b2r_context* ctx, uint64_t byte_offset);
+/* The same with the band given by the caller - rows [row_begin, row_end) of the frame - for boxes whose GPUs do not reach the
+ * host equally fast: the ranks' bands must tile the frame, their sizes are the caller's choice (bench.py sizes them by a
+ * short calibration of every rank's device->host bandwidth with all ranks copying at once). */
+int b2r_present_rows_async(b2r_context* ctx, uint64_t byte_offset, uint32_t row_begin, uint32_t row_end);
 /* depth buffer as the reference keeps it (int z*2^31, INT_MAX = empty; CUDAROPs.cu:386, CUDARenderer.cu:1640) */
 int b2r_read_depth(b2r_context* ctx, int32_t* out);
 /* parity surfaces (need B2R_OPT_DEBUG_SURFACES=1 before the render): PixelShade.zInterpolated

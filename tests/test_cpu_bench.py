@@ -145,6 +145,10 @@ class _FakeRenderer:
     def present_band_async(self, byte_offset=0):
         self.present_tiles_async(byte_offset)
 
+    def present_rows_async(self, byte_offset, row_begin, row_end):
+        assert 0 <= row_begin <= row_end <= self.h
+        self.present_tiles_async(byte_offset)
+
     def present_tiles_async(self, byte_offset=0):
         n = self.w * self.h
         self.host_frame[byte_offset // 4: byte_offset // 4 + n] = self.framebuffer().reshape(-1)

@@ -179,7 +179,7 @@ class Trace:
     ROLES = {      # logical buffer -> argument index, per kernel (csrc/b2r.cu: enqueueFrame / enqueueFrameRing / enqueueListSort)
         "frame_clear_kernel": {"tileCount": 0, "counters": 2, "frameInfo": 3, "hViewProj": 6, "meshStatic": 7, "meshConst": 8},
         "build_constants_kernel": {"hViewProj": 0, "meshStatic": 1, "meshConst": 2},
-        "vertex_transform_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3},
+        "vertex_transform_kernel": {"meshConst": 2, "posIn": 3, "pos4": 4},
         "vertex_transform_marked_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3, "frameInfo": 7},
         "shard_mark_vertices_kernel": {"triRefs": 4, "frameInfo": 6},
         "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5},
