@@ -36,6 +36,7 @@ OPT_OVERLAP_FRONT = 11
 OPT_FRAME_RING = 12
 OPT_SHARD_SLICED_VERTEX = 13
 OPT_SHARD_LOCAL_COLOUR = 14
+OPT_DIRECT_MAX_AREA = 15
 STAGE_NAMES = ("vertex", "setup", "bin_scan", "bin_scatter", "bin_sort", "raster_shade", "total", "exchange", "peer_wait")
 NUM_STAGES = 9
 

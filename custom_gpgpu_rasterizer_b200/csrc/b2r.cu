@@ -33,6 +33,10 @@ namespace {
 constexpr int kRing = 4;
 constexpr int kMaxFrameRing = 4;      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
 constexpr int kInfoWords = 16;
+#ifndef B2R_DIRECT_MAX_AREA
+#define B2R_DIRECT_MAX_AREA 64
+#endif
+constexpr int kDirectMaxAreaDefault = B2R_DIRECT_MAX_AREA;
 thread_local std::string g_createError;
 
 // grow-only device array
@@ -89,6 +93,8 @@ struct b2r_context
 
 	// options
 	int fillTopLeft = 1, ownerRank = 0, ownerCount = 1, debugSurfaces = 0, stageTimers = 0, sortBins = 1, packedOutput = 0;
+	int directMaxArea = kDirectMaxAreaDefault;      // B2R_OPT_DIRECT_MAX_AREA
+	bool lastDirect = false;                        // the newest enqueued frame resolved small triangles in its setup kernel (its lists hold the others only)
 
 	// scene
 	std::vector<HostMesh> meshes;
@@ -126,7 +132,11 @@ struct b2r_context
 	{
 		DeviceVec<uint2> rects;
 		DeviceVec<uint32_t> tileCount, tileOffset, tileCursor, longTiles, bigList, binIds;
-		DeviceVec<uint4> tileOrder;                   // the raster kernel's work order: one list of {tile, count, offset, 0} per length class
+		DeviceVec<uint4> tileOrder;                   // the raster kernel's work order: one list of {tile, count, offset, key-buffer flag} per length class
+		// direct path (B2R_OPT_DIRECT_MAX_AREA): 64-bit depth|id key per pixel in 16x16 blocks, all empty between frames (the
+		// raster kernel resets what it merges), and one "holds fragments" byte per tile
+		DeviceVec<unsigned long long> keys;
+		DeviceVec<uint8_t> dirty;
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[kMaxFrameRing];
@@ -299,6 +309,16 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	size_t listCap = std::max<size_t>((size_t)1 << 22, c->nPrims * 3);
 	for (const auto& other : c->bins) listCap = std::max(listCap, other.binIds.cap);
 	CU(c, B.binIds.reserve(listCap, c->stream));
+	if (c->directMaxArea)
+	{
+		const size_t keyWords = (size_t)((c->width + 15) / 16) * ((c->height + 15) / 16) * 256;
+		const unsigned long long* oldKeys = B.keys.ptr; const uint8_t* oldDirty = B.dirty.ptr;
+		CU(c, B.keys.reserve(keyWords, c->stream));
+		CU(c, B.dirty.reserve(n + 16, c->stream));
+		if (B.keys.ptr != oldKeys) CU(c, cudaMemsetAsync(B.keys.ptr, 0xFF, B.keys.cap * 8, c->stream));
+		if (B.dirty.ptr != oldDirty) CU(c, cudaMemsetAsync(B.dirty.ptr, 0, B.dirty.cap, c->stream));
+		if (B.keys.ptr != oldKeys || B.dirty.ptr != oldDirty) CU(c, cudaStreamSynchronize(c->stream));
+	}
 	return B2R_OK;
 }
 
@@ -370,6 +390,12 @@ int rebuildTextures(b2r_context* c)
 	return B2R_OK;
 }
 
+// the direct path of the setup kernel (not with the sharded front end: its key buffers are per rank)
+bool directActive(const b2r_context* c) { return c->directMaxArea > 0 && !c->shard.bound; }
+
+// the setup kernel instantiation of a frame: fill rule, direct path
+cudaError_t launchSetup(const b2r_context* c, cudaStream_t s, b2r_context::BinSet& B, const float4* pos4, uint32_t* tileCount, uint32_t primLo, uint32_t primHi, const FrameParams& fp);
+
 FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 {
 	FrameParams fp{};
@@ -393,6 +419,9 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.subsMagic = subs > 1 ? (uint32_t)(0x100000000ull / subs) : 0u;
 	// with several 16x16 blocks per bin the CTAs of a bin share its list: it is sorted by a kernel of its own before the raster
 	fp.sortLists = (c->sortBins && subs == 1) ? 1u : 0u;
+	fp.directMaxArea = directActive(c) ? (uint32_t)c->directMaxArea : 0u;
+	fp.keyBlocksX = (c->width + 15) / 16;
+	fp.countFragments = (uint32_t)c->countFragments;
 	return fp;
 }
 
@@ -427,6 +456,32 @@ cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, 
 	default: return launchFrameKernel(c, raster_shade_kernel<true, true, true>, grid, block, 0, s, A, fp);
 	}
 #undef B2R_RASTER_CASE
+}
+
+// persistent grid of the setup kernel: as many CTAs as are resident at once (its warps stride over the primitive groups)
+template <typename K>
+uint32_t setupGrid(const b2r_context* c, K kernel, bool direct, uint32_t prims, int& cached)
+{
+	if (cached < 1)
+	{
+		int n = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kChunk, 0) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = setupCtasPerSM(direct); }
+		cached = n;
+	}
+	const uint32_t groups = (prims + 31u) / 32u;
+	return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c->numSMs * (uint32_t)cached, (groups + kChunk / 32 - 1) / (kChunk / 32)));
+}
+
+cudaError_t launchSetup(const b2r_context* c, cudaStream_t s, b2r_context::BinSet& B, const float4* pos4, uint32_t* tileCount, uint32_t primLo, uint32_t primHi, const FrameParams& fp)
+{
+	static thread_local int occ[4] = { 0, 0, 0, 0 };      // CTAs per SM of the four instantiations (a property of the binary)
+	const dim3 block(kChunk);
+#define B2R_SETUP_CASE(i, tl, direct) return launchFrameKernel(c, triangle_setup_kernel<tl, direct>, dim3(setupGrid(c, triangle_setup_kernel<tl, direct>, direct, primHi - primLo, occ[i])), block, 0, s, \
+		(const uint4*)c->dTriRefs.ptr, pos4, B.rects.ptr, tileCount, B.bigList.ptr, B.counters, B.keys.ptr, B.dirty.ptr, B.frameInfo, primLo, primHi, fp)
+	if (fp.directMaxArea) { if (c->fillTopLeft) B2R_SETUP_CASE(0, true, true); B2R_SETUP_CASE(1, false, true); }
+	if (c->fillTopLeft) B2R_SETUP_CASE(2, true, false);
+	B2R_SETUP_CASE(3, false, false);
+#undef B2R_SETUP_CASE
 }
 
 #define STAGE_EVENT(c, slot, i) do { if ((slot).timed) CU((c), cudaEventRecord((slot).ev[(i)], (c)->stream)); } while (0)
@@ -649,8 +704,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		if (primHi > primLo)
 		{
-			CU(c, launchFrameKernel(c, triangle_setup_kernel, dim3((primHi - primLo + kChunk - 1) / kChunk), dim3(kChunk), 0, fs, c->dTriRefs.ptr, pos4,
-				B.rects.ptr, tileCount, B.bigList.ptr, B.counters, primLo, primHi, fp));
+			CU(c, launchSetup(c, fs, B, pos4, tileCount, primLo, primHi, fp));
 			++c->kernelsLaunched;
 		}
 		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, fs, B.bigList.ptr, B.counters, B.rects.ptr, tileCount, fp));
@@ -668,7 +722,7 @@ int enqueueFrame(b2r_context* c)
 				inbox.tileCount[p] = sh.inboxCount(base, set, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, set, sh.self);
 			}
 		CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, fs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
-			(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
+			(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr, fp.directMaxArea ? (const uint8_t*)B.dirty.ptr : (const uint8_t*)nullptr,
 			(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, inbox, sh.bound ? (uint32_t)sh.n : 0u, B.frameInfo));
 		++c->kernelsLaunched;
 	}
@@ -707,6 +761,7 @@ int enqueueFrame(b2r_context* c)
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
+		A.keys = B.keys.ptr; A.dirty = B.dirty.ptr; c->lastDirect = fp.directMaxArea != 0u;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
 		if (!c->boundFramebuffer && c->copyPending[c->colourIdx])
 		{
@@ -929,8 +984,7 @@ int enqueueFrameRing(b2r_context* c)
 	{
 		if (primHi > primLo)
 		{
-			CU(c, launchFrameKernel(c, triangle_setup_kernel, dim3((primHi - primLo + kChunk - 1) / kChunk), dim3(kChunk), 0, rs, c->dTriRefs.ptr, pos4,
-				B.rects.ptr, tileCount, B.bigList.ptr, B.counters, primLo, primHi, fp));
+			CU(c, launchSetup(c, rs, B, pos4, tileCount, primLo, primHi, fp));
 			++c->kernelsLaunched;
 		}
 		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, rs, B.bigList.ptr, B.counters, B.rects.ptr, tileCount, fp));
@@ -946,7 +1000,7 @@ int enqueueFrameRing(b2r_context* c)
 				inbox.tileCount[p] = sh.inboxCount(base, k, sh.self); inbox.tileOffset[p] = sh.inboxOffset(base, k, sh.self);
 			}
 		CU(c, launchFrameKernel(c, tile_scan_kernel, dim3((tiles + kScanPerCta - 1) / kScanPerCta), dim3(kScanThreads), 0, rs, tileCount, tileOffset, B.tileCursor.ptr, tiles,
-			(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr,
+			(unsigned long long)listCap, (uint32_t)kStage, B.longTiles.ptr, sh.bound ? nullptr : B.tileOrder.ptr, fp.directMaxArea ? (const uint8_t*)B.dirty.ptr : (const uint8_t*)nullptr,
 			(uint32_t)c->ownerRank, (uint32_t)c->ownerCount, B.counters, inbox, sh.bound ? (uint32_t)sh.n : 0u, B.frameInfo));
 		++c->kernelsLaunched;
 	}
@@ -975,6 +1029,7 @@ int enqueueFrameRing(b2r_context* c)
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
 		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
+		A.keys = B.keys.ptr; A.dirty = B.dirty.ptr; c->lastDirect = fp.directMaxArea != 0u;
 		// the frames of the ring alternate strictly between the two colour + depth surface pairs (sharded: every rank writes
 		// rank 0's surface `frame & 1`), which is what lets consecutive raster kernels overlap (below)
 		c->colourIdx = sh.bound ? (int)(sh.frame & 1u) : (int)(c->seq & 1u);
@@ -1112,7 +1167,13 @@ int validateFrame(b2r_context* c)
 		const size_t need = c->overflowNeed;
 		c->overflowNeed = 0;
 		for (auto& B : c->bins)
-			if (B.frameInfo) CU(c, B.binIds.reserve(need + need / 4, c->stream));
+			if (B.frameInfo)
+			{
+				CU(c, B.binIds.reserve(need + need / 4, c->stream));
+				// a voided frame's raster kernel did not merge (and reset) what its setup kernel put into the key buffer
+				if (B.keys.ptr) CU(c, cudaMemsetAsync(B.keys.ptr, 0xFF, B.keys.cap * 8, c->stream));
+				if (B.dirty.ptr) CU(c, cudaMemsetAsync(B.dirty.ptr, 0, B.dirty.cap, c->stream));
+			}
 		int r = enqueueFrame(c);
 		if (r) return r;
 	}
@@ -1203,6 +1264,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	if (const char* e = getenv("B2R_FRAME_RING")) { const int d = atoi(e); c->ringDepth = (d >= 2 && d <= kMaxFrameRing) ? d : 0; }   // see B2R_OPT_FRAME_RING
 	if (const char* e = getenv("B2R_SHARD_SLICED_VERTEX")) c->slicedVertex = atoi(e) != 0;       // see B2R_OPT_SHARD_SLICED_VERTEX
 	if (const char* e = getenv("B2R_RING_RELAXED")) c->relaxedChain = atoi(e) != 0;
+	if (const char* e = getenv("B2R_DIRECT_MAX_AREA")) { const int a = atoi(e); c->directMaxArea = (a >= 0 && a <= 4096) ? a : kDirectMaxAreaDefault; }   // see B2R_OPT_DIRECT_MAX_AREA
 	auto bail = [&](int code) { g_createError = c->error; b2r_destroy(c); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, B2R_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(B2R_E_CUDA); } } while (0)
 	CUC(cudaSetDevice(device));
@@ -1275,7 +1337,7 @@ void b2r_destroy(b2r_context* c)
 	for (auto& B : c->bins)
 	{
 		B.rects.release(); B.tileCount.release(); B.tileOffset.release(); B.tileCursor.release(); B.longTiles.release();
-		B.tileOrder.release(); B.bigList.release(); B.binIds.release();
+		B.tileOrder.release(); B.bigList.release(); B.binIds.release(); B.keys.release(); B.dirty.release();
 		cudaFree(B.frameInfo);
 	}
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);
@@ -1430,6 +1492,17 @@ int b2r_set_option(b2r_context* c, int option, int value)
 	case B2R_OPT_COUNT_FRAGMENTS: c->countFragments = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_VERTEX: c->overlapVertex = value ? 1 : 0; break;
 	case B2R_OPT_OVERLAP_FRONT: c->overlapFront = value ? 1 : 0; break;
+	case B2R_OPT_DIRECT_MAX_AREA:
+	{
+		if (value < 0 || value > 4096) return fail(c, B2R_E_INVALID, "direct-path area must be 0 (off) .. 4096 pixels");
+		// the key buffers exist only while the path is on: between frames
+		CU(c, cudaSetDevice(c->device));
+		int r = validateFrame(c); if (r) return r;
+		c->directMaxArea = value;
+		for (auto& B : c->bins)
+			if (B.frameInfo) { r = reserveBinSet(c, B); if (r) return r; }
+		break;
+	}
 	case B2R_OPT_SHARD_LOCAL_COLOUR:
 	{
 		// changes where the frames' colours go: only between frames
@@ -1474,6 +1547,7 @@ int b2r_get_option(b2r_context* c, int option, int* value)
 	case B2R_OPT_PACKED_OUTPUT: *value = c->packedOutput; break;
 	case B2R_OPT_OVERLAP_VERTEX: *value = c->overlapVertex; break;
 	case B2R_OPT_OVERLAP_FRONT: *value = c->overlapFront; break;
+	case B2R_OPT_DIRECT_MAX_AREA: *value = c->directMaxArea; break;
 	case B2R_OPT_FRAME_RING: *value = c->ringDepth; break;
 	case B2R_OPT_SHARD_SLICED_VERTEX: *value = c->slicedVertex; break;
 	case B2R_OPT_SHARD_LOCAL_COLOUR: *value = c->shardLocalColour; break;
@@ -1737,6 +1811,26 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	if (!c->haveFrame) return fail(c, B2R_E_STATE, "read_bins: nothing rendered yet");
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
+	const bool rerun = c->lastDirect;
+	const int savedDirect = c->directMaxArea;
+	if (rerun)
+	{
+		// the newest frame resolved its small triangles in the setup kernel, so its lists hold the other triangles only: the
+		// bins of the frame (every visible triangle in every tile of its rectangle, as the reference's TB_Kernel fills
+		// them) are produced by running the frame once more with every triangle binned
+		c->directMaxArea = 0;
+		r = enqueueFrame(c);
+		if (!r) r = validateFrame(c);
+		c->directMaxArea = savedDirect;
+		if (r) return r;
+	}
+	// (and once the bins have been copied out, the frame is run a third time the way it was rendered, so that the surfaces
+	// and counters read afterwards are again those of the frame as the caller rendered it)
+	struct Restore
+	{
+		b2r_context* c; bool on;
+		~Restore() { if (on && enqueueFrame(c) == B2R_OK) validateFrame(c); }
+	} restore{ c, rerun };
 	const uint64_t pairs = c->lastInfo.frameInfo[0];
 	if (total) *total = pairs;
 	const uint32_t n = nBins(c);
@@ -1802,7 +1896,7 @@ int b2r_get_counters(b2r_context* c, uint64_t* out, int n)
 	int r = validateFrame(c); if (r) return r;
 	const uint32_t tiles = nBins(c);
 	const uint64_t owned = (tiles > (uint32_t)c->ownerRank) ? (tiles - c->ownerRank + c->ownerCount - 1) / c->ownerCount : 0;
-	const uint64_t v[8] = { c->lastInfo.frameInfo[0], c->kernelsLaunched, owned, tiles, c->lastInfo.frameInfo[2], c->lastInfo.counters[1], c->lastInfo.frameInfo[4], c->lastInfo.frameInfo[6] };
+	const uint64_t v[8] = { c->lastInfo.frameInfo[0] + c->lastInfo.frameInfo[kInfoDirectPairs], c->kernelsLaunched, owned, tiles, c->lastInfo.frameInfo[2], c->lastInfo.counters[1], c->lastInfo.frameInfo[4], c->lastInfo.frameInfo[6] };
 	for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
 	return B2R_OK;
 }

@@ -199,6 +199,8 @@ __device__ __forceinline__ bool tileOwned(const FrameParams& fp, uint32_t tile)
 // same few tiles).  Every lane of the warp must call this the same number of times (`steps` =
 // warp-wide maximum of nTiles); lanes with k >= nTiles pass tile = kNoTile.
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+constexpr uint32_t kBinnedCounterWord = 2;         // counters[2]: primitives with a small rectangle that went into the lists (what bin_scatter_kernel has to visit)
+constexpr uint32_t kRectDirect = 0x80000000u;      // rects[prim].x bit 31: the setup kernel resolved the triangle itself (direct path), it is in no list
 // counters[]: [0] visible triangles (summed by tile_scan_kernel), [1] big triangles,
 // [kVisBase + 32*s] partial visible counts, one 128-byte line per slot,
 // [kScanBase ...] the 64-bit slice sums of the chained tile scan
@@ -508,82 +510,7 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	r.pad = 0;
 }
 
-// triangle setup: one thread per primitive of [primLo, primHi).
-// cull (CUDARenderer.cu:760-777), frustum reject (CUDAROPs.cu:147-178), screen mapping (:88-97),
-// inflated bbox (:180-200), bin rectangle (CUDARenderer.cu:935-942), per-tile counts.
-__global__ void __launch_bounds__(kChunk) triangle_setup_kernel(
-	const uint4* __restrict__ triRefs, const float4* __restrict__ pos4, uint2* __restrict__ rects,
-	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig*/,
-	uint32_t primLo, uint32_t primHi, FrameParams fp)
-{
-	pdlPrologue();
-	bool visible = false;
-	const uint32_t prim = primLo + blockIdx.x * kChunk + threadIdx.x;
-	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
-	if (prim < primHi)
-	{
-		const uint4 tr = __ldcs(triRefs + prim);
-		const float4 p0 = __ldg(pos4 + tr.x), p1 = __ldg(pos4 + tr.y), p2 = __ldg(pos4 + tr.z);
-		visible = true;
-		if (fp.cullMode != 2u)
-		{
-			const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
-			const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
-			float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
-			normalize3(nx, ny, nz);
-			// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
-			const float d = (fp.cullMode == 0u)
-				? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
-				: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
-			if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
-		}
-		if (visible)
-		{
-			const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
-			const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
-			const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
-			visible = !(xOut || yOut || zOut);
-		}
-		if (visible)
-		{
-			TriRecord r;
-			const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
-			const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
-			const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
-			const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
-			const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
-			// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
-			const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
-			bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
-			by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
-			bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
-			by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
-		}
-		// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
-		// from a visible primitive whose rectangle happens to be empty
-		rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16))
-		                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
-	}
-	// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
-	{
-		const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
-		if ((threadIdx.x & 31) == 0 && vis)
-			atomicAdd(&counters[kVisBase + ((blockIdx.x * 8 + (threadIdx.x >> 5)) % kVisSlots) * 32], (uint32_t)__popc(vis));
-	}
-
-	// per-tile counts, warp-aggregated
-	uint32_t nTiles = 0;
-	if (visible && bx0 <= bx1 && by0 <= by1)
-	{
-		nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
-		if (nTiles > fp.bigRectTiles)
-		{
-			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
-			nTiles = 0;
-		}
-	}
-	warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
-}
+// (triangle_setup_kernel lives in raster_kernel.cuh: it resolves small triangles itself and shares the fragment test)
 
 // cooperative binning of triangles with large rectangles (full-screen quads ...): one CTA per
 // big triangle, threads stride over its tiles.  SCATTER=false counts (bin_big_count_kernel), true writes
@@ -632,6 +559,7 @@ __global__ void __launch_bounds__(256) bin_big_count_kernel(
 constexpr uint32_t kTileClasses = 6;
 constexpr uint32_t kInfoClassBase = 8;       // frameInfo[8 .. 13]: tiles per class; frameInfo[14]: the raster kernel's work counter
 constexpr uint32_t kInfoWorkCounter = kInfoClassBase + kTileClasses;
+constexpr uint32_t kInfoDirectPairs = 5;     // frameInfo[5]: (triangle, tile) pairs of the triangles the setup kernel resolved itself (never binned)
 constexpr uint32_t kEmptyBatch = 4;          // empty tiles cleared per work item
 __device__ __forceinline__ uint32_t tileClass(uint32_t n)
 {
@@ -649,7 +577,8 @@ constexpr uint32_t kScanThreads = 256, kScanPerThread = 8, kScanPerCta = kScanTh
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	const uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
 	uint32_t nTiles, unsigned long long capacity, uint32_t longThreshold,
-	uint32_t* __restrict__ longTiles, uint4* __restrict__ tileOrder, uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
+	uint32_t* __restrict__ longTiles, uint4* __restrict__ tileOrder, const uint8_t* __restrict__ dirty /*direct path: tiles whose key-buffer blocks hold fragments, or null*/,
+	uint32_t ownerRank, uint32_t ownerCount, uint32_t* __restrict__ counters,
 	const __grid_constant__ ShardInbox inbox, uint32_t inboxRanks /*sharded front end: the heads (count, offset) of this rank's lists go to the inbox of each tile's owner; 0: no*/,
 	unsigned long long* __restrict__ frameInfo /*[0]=pairs,[1]=overflow,[2]=unsorted tiles,[3]=long tiles,[6]=lists sorted by the bitonic fallback,[8..13]=tiles per class*/)
 {
@@ -659,8 +588,11 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	if (blockIdx.x == 0 && threadIdx.x < 32)
 	{
 		uint32_t v = counters[kVisBase + threadIdx.x * 32] + counters[kVisBase + (threadIdx.x + 32) * 32];
-		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-		if (threadIdx.x == 0) counters[0] = v;
+		// (triangle, tile) pairs of the triangles the setup kernel resolved itself (64-bit partial sums next to the visible counts)
+		const unsigned long long* dp = reinterpret_cast<const unsigned long long*>(counters + kVisBase);
+		unsigned long long d2 = dp[threadIdx.x * 16 + 1] + dp[(threadIdx.x + 32) * 16 + 1];
+		for (int d = 16; d > 0; d >>= 1) { v += __shfl_down_sync(0xFFFFFFFFu, v, d); d2 += __shfl_down_sync(0xFFFFFFFFu, d2, d); }
+		if (threadIdx.x == 0) { counters[0] = v; frameInfo[kInfoDirectPairs] = d2; }
 	}
 	__shared__ unsigned long long sWarp[kScanThreads / 32];
 	__shared__ unsigned long long sPrefix;
@@ -780,12 +712,17 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 	if (tileOrder)
 	{
 		uint32_t cls[kScanPerThread];
+		// direct path: a tile whose key-buffer blocks hold fragments is a work item even with an empty list
+		// (the map is padded to a multiple of 16 bytes; first is a multiple of kScanPerThread = 8)
+		unsigned long long dirtyBytes = 0ull;
+		if (dirty && first < nTiles) dirtyBytes = *reinterpret_cast<const unsigned long long*>(dirty + first);
 		#pragma unroll
 		for (uint32_t e = 0; e < kScanPerThread; ++e)
 		{
 			const uint32_t t = first + e;
 			const bool mine = t < nTiles && (ownerCount <= 1u || t % ownerCount == ownerRank);
-			cls[e] = mine ? tileClass(v[e]) : kTileClasses;
+			const bool d = ((dirtyBytes >> (8u * e)) & 0xFFull) != 0ull;
+			cls[e] = mine ? ((v[e] == 0u && d) ? kTileClasses - 2u : tileClass(v[e])) : kTileClasses;
 		}
 		#pragma unroll
 		for (uint32_t c = 0; c < kTileClasses; ++c)
@@ -808,7 +745,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(
 			uint4* dst = tileOrder + (size_t)c * nTiles;
 			#pragma unroll
 			for (uint32_t e = 0; e < kScanPerThread; ++e)
-				if (cls[e] == c) dst[base++] = make_uint4(first + e, v[e], off[e], 0u);      // the raster kernel's work item: tile, list length, list offset
+				if (cls[e] == c) dst[base++] = make_uint4(first + e, v[e], off[e], (uint32_t)((dirtyBytes >> (8u * e)) & 0xFFull));      // the raster kernel's work item: tile, list length, list offset, key-buffer flag
 		}
 	}
 }
@@ -835,6 +772,8 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 		binBigBody<true>(blockIdx.x - primBlocks, gridDim.x - primBlocks, bigList, counters, rects, nullptr, tileOffset, tileCursor, binIds, fp, M);
 		return;
 	}
+	// nothing but directly resolved (or culled) primitives: no rectangle to re-read (triangle_setup_kernel counts the others)
+	if (__ldg(counters + kBinnedCounterWord) == 0u) return;
 	// kScatterPerThread primitives per thread (a CTA covers kScatterPerThread * 256 consecutive ids): the rectangle
 	// loads are issued together, so their latency is paid once; each warpBinRects call still sees one aligned
 	// group of 32 consecutive ids, which is all the run sorter assumes
@@ -850,8 +789,8 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	{
 		const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
 		uint32_t nTiles = 0;
-		const int bx0 = rc[k].x & 0xFFFF, by0 = rc[k].y & 0xFFFF, bx1 = rc[k].x >> 16, by1 = rc[k].y >> 16;
-		if (bx0 <= bx1 && by0 <= by1)
+		const int bx0 = rc[k].x & 0xFFFF, by0 = rc[k].y & 0xFFFF, bx1 = (rc[k].x >> 16) & 0x7FFF, by1 = rc[k].y >> 16;
+		if (bx0 <= bx1 && by0 <= by1 && !(rc[k].x & kRectDirect))
 		{
 			nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
 			if (nTiles > fp.bigRectTiles) nTiles = 0;   // binBigBody

@@ -34,7 +34,9 @@ struct RasterArgs
 	float* zSurface;        // debug surfaces (may be null)
 	uint32_t* winnerSurface;
 	ShardTable shard;       // sharded front end only (fp.shardGeometry): the per-rank lists of this rank's tiles, all in local memory
-	const uint4* tileOrder;     // the work order: kTileClasses lists of nTiles {tile, list length, list offset, 0} entries (tile_scan_kernel / shard_merge_heads_kernel)
+	const uint4* tileOrder;     // the work order: kTileClasses lists of nTiles {tile, list length, list offset, key-buffer flag} entries (tile_scan_kernel / shard_merge_heads_kernel)
+	unsigned long long* keys;   // direct path: the frame's key buffer (see keyIndex) and its per-tile "holds fragments" map
+	uint8_t* dirty;
 };
 
 // expanded per-triangle data kept in shared memory while a chunk of the bin list is processed
@@ -97,6 +99,175 @@ __device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, 
 	t.prim = prim;
 	t.divLo = r.divLo; t.rcpArea = r.rcpArea; t.zLow = r.zLow;
 	t.yExtent = 0;
+}
+
+// triangle setup: one thread per primitive of [primLo, primHi).
+// cull (CUDARenderer.cu:760-777), frustum reject (CUDAROPs.cu:147-178), screen mapping (:88-97),
+// inflated bbox (:180-200), bin rectangle (CUDARenderer.cu:935-942), per-tile counts.
+//
+// DIRECT: the direct path for small triangles.  The reference tests a triangle against every pixel of every bin of its
+// rectangle (CUDARenderer.cu:1116-1127); the pixels that can pass are those of the triangle's candidate box
+// (rasterConstants) inside the rectangle's bins.  When that is at most fp.directMaxArea pixels the thread runs the
+// fragment test on them right here and resolves depth with a 64-bit atomicMin on the frame's key buffer - the same
+// (z_int << 32 | primitive id) key and the same order-independent min the raster kernel keeps per tile - and the
+// triangle is never counted, scattered, sorted or staged.  A triangle without any candidate pixel (between the pixel
+// centres) costs nothing further.  The raster kernel merges the key buffer into its tiles' resolve (and resets it).
+// On a scene of sub-pixel triangles this removes the bin lists altogether; the 66 MB key buffer of a 4K frame lives
+// in B200's 126 MB L2.
+//
+// The kernel is persistent and software-pipelined.  A primitive costs two dependent memory round trips (vertex
+// reference -> three positions) before a few hundred instructions of arithmetic; with one primitive per thread the SM
+// idles on those round trips more than half of the time (ncu: issue slots 46 % busy, long-scoreboard 48 %).  Here a
+// warp walks over groups of 32 consecutive primitives (group g, g + W, g + 2W ... for W resident warps) and keeps two
+// groups in flight behind the one it works on: the positions of the NEXT group and the vertex references of the one after
+// are requested before the arithmetic of the current group starts and are consumed an iteration later.
+#ifndef B2R_SETUP_DIRECT_CTAS
+#define B2R_SETUP_DIRECT_CTAS 3
+#endif
+#ifndef B2R_SETUP_PLAIN_CTAS
+#define B2R_SETUP_PLAIN_CTAS 5
+#endif
+constexpr int setupCtasPerSM(bool direct) { return direct ? B2R_SETUP_DIRECT_CTAS : B2R_SETUP_PLAIN_CTAS; }
+template <bool TOPLEFT, bool DIRECT>
+__global__ void __launch_bounds__(kChunk, setupCtasPerSM(DIRECT)) triangle_setup_kernel(
+	const uint4* __restrict__ triRefs, const float4* __restrict__ pos4, uint2* __restrict__ rects,
+	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig,[2]=binned*/,
+	unsigned long long* __restrict__ keys, uint8_t* __restrict__ dirty, unsigned long long* __restrict__ frameInfo,
+	uint32_t primLo, uint32_t primHi, const __grid_constant__ FrameParams fp)
+{
+	pdlPrologue();
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t nWarps = gridDim.x * (kChunk / 32), warpId = blockIdx.x * (kChunk / 32) + (threadIdx.x >> 5);
+	const uint32_t nGroups = (primHi - primLo + 31u) / 32u;
+	if (warpId >= nGroups) return;
+	auto loadRef = [&](uint32_t g) -> uint4
+	{
+		const uint32_t q = primLo + g * 32u + lane;
+		return (g < nGroups && q < primHi) ? __ldcs(triRefs + q) : make_uint4(0u, 0u, 0u, 0u);
+	};
+	// pipeline fill: positions of this warp's first group, vertex references of its second
+	uint4 trNext = loadRef(warpId);
+	float4 q0 = __ldg(pos4 + trNext.x), q1 = __ldg(pos4 + trNext.y), q2 = __ldg(pos4 + trNext.z);
+	trNext = loadRef(warpId + nWarps);
+	uint32_t nFrags = 0, visTotal = 0, binnedTotal = 0;
+	unsigned long long directTotal = 0ull;
+	for (uint32_t g = warpId; g < nGroups; g += nWarps)
+	{
+		const float4 p0 = q0, p1 = q1, p2 = q2;
+		if (g + nWarps < nGroups)
+		{
+			// (the references were requested an iteration ago; index 0 of a lane past the end is a valid position)
+			q0 = __ldg(pos4 + trNext.x); q1 = __ldg(pos4 + trNext.y); q2 = __ldg(pos4 + trNext.z);
+			trNext = loadRef(g + 2u * nWarps);
+		}
+		const uint32_t prim = primLo + g * 32u + lane;
+		bool visible = false;
+		int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+		uint32_t nTiles = 0, directTiles = 0;
+		if (prim < primHi)
+		{
+			visible = true;
+			if (fp.cullMode != 2u)
+			{
+				const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+				const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+				float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
+				normalize3(nx, ny, nz);
+				// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
+				const float d = (fp.cullMode == 0u)
+					? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
+					: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
+				if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
+			}
+			if (visible)
+			{
+				const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
+				const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
+				const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
+				visible = !(xOut || yOut || zOut);
+			}
+			if (visible)
+			{
+				TriRecord r;
+				const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
+				const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
+				const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
+				const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
+				const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
+				// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
+				const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+				bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
+				by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
+				bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
+				by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
+				if (bx0 <= bx1 && by0 <= by1)
+				{
+					nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
+					if (DIRECT)
+					{
+						rasterConstants(b, fp, r);
+						// candidate pixels: the candidate box inside the bins of the rectangle (the box is already clamped to the screen)
+						const int x0 = max((int)(r.cbX & 0xFFFFu), bx0 * (int)fp.binW), x1 = min((int)(r.cbX >> 16), (bx1 + 1) * (int)fp.binW);
+						const int y0 = max((int)(r.cbY & 0xFFFFu), by0 * (int)fp.binH), y1 = min((int)(r.cbY >> 16), (by1 + 1) * (int)fp.binH);
+						const uint32_t area = (x1 > x0 && y1 > y0) ? (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) : 0u;
+						if (area <= fp.directMaxArea)
+						{
+							directTiles = nTiles;
+							nTiles = 0;
+							if (area)
+							{
+								TriShared t;
+								expandRecord(r, prim, t);
+								const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
+								for (int y = y0; y < y1; ++y)
+									for (int x = x0; x < x1; ++x)
+									{
+										Bary bc; int zi;
+										if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+										{
+											const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
+											if (replicated && tile % fp.ownerCount != fp.ownerRank) continue;
+											atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | prim);
+											dirty[tile] = 1;
+											++nFrags;
+										}
+									}
+							}
+						}
+					}
+				}
+			}
+			// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
+			// from a visible primitive whose rectangle happens to be empty
+			// (bit 31 of the first word: resolved here, not to be scattered into the lists)
+			rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16) | (directTiles ? kRectDirect : 0u), (uint32_t)by0 | ((uint32_t)by1 << 16))
+			                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
+		}
+		// statistics of the group (flushed once per warp at the end)
+		visTotal += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, visible));
+		if (DIRECT) directTotal += (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, min(directTiles, 0x00FFFFFFu));      // (a rectangle has at most 2^22 tiles)
+
+		// per-tile counts, warp-aggregated
+		if (nTiles > fp.bigRectTiles)
+		{
+			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
+			nTiles = 0;
+		}
+		binnedTotal += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, nTiles > 0u));
+		warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
+	}
+	// statistics: a few atomics per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+	{
+		uint32_t* slot = &counters[kVisBase + (warpId % kVisSlots) * 32];
+		if (DIRECT && fp.countFragments) nFrags = __reduce_add_sync(0xFFFFFFFFu, nFrags);
+		if (lane == 0)
+		{
+			if (visTotal) atomicAdd(slot, visTotal);
+			if (binnedTotal) atomicAdd(&counters[kBinnedCounterWord], binnedTotal);
+			if (DIRECT && directTotal) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, directTotal);
+			if (DIRECT && fp.countFragments && nFrags) atomicAdd(&frameInfo[4], (unsigned long long)nFrags);
+		}
+	}
 }
 
 // ---- texture sampling (CUDATextureSampler.cuh:80-191) -------------------------------------
@@ -545,6 +716,18 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 				for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
 				if ((tid & 31) == 0 && v) atomicAdd(&A.frameInfo[4], (unsigned long long)v);
 			}
+		}
+		if (desc.w)
+		{
+			// direct path: the fragments the setup kernel resolved for this block's pixels; the key buffer is left empty for
+			// the next frame that uses it
+			if (live)
+			{
+				unsigned long long* kp = A.keys + keyIndex(fp.keyBlocksX, px, py);
+				const unsigned long long k = *kp;
+				if (k != kEmptyKey) { *kp = kEmptyKey; best = min(best, k); }
+			}
+			if (tid == 0 && sub == 0) A.dirty[bin] = 0;
 		}
 		if (!live) return;
 

@@ -96,7 +96,15 @@ enum
 	 * storing them into rank 0's over NVLink (no "colours landed" flags either).  For consumers on the host
 	 * (b2r_present_tiles_async: every rank delivers its tiles over its own PCIe link); the frame is then never
 	 * composed on a device.  Set it between frames, after b2r_shard_bind.  Default 0. */
-	B2R_OPT_SHARD_LOCAL_COLOUR = 14
+	B2R_OPT_SHARD_LOCAL_COLOUR = 14,
+	/* Direct path for small triangles: a triangle with at most this many candidate pixels (its conservative pixel box
+	 * inside the bins of its rectangle - the pixels the reference's per-bin test, CUDARenderer.cu:1116-1127, can pass)
+	 * is resolved by the setup kernel itself with 64-bit atomicMin operations on a per-pixel (depth, primitive id) key
+	 * buffer instead of going through the bin lists; the raster kernel merges the key buffer into its tiles.  Same
+	 * fragments, same keys, same order-independent min: the frame is identical bit for bit.  0 switches the path off
+	 * (every visible triangle is binned).  b2r_read_bins always returns the complete bins (it re-runs the newest frame
+	 * with the path off when needed).  Not used by the sharded front end.  Default 64; set it between frames. */
+	B2R_OPT_DIRECT_MAX_AREA = 15
 };
 
 /* stage indices for b2r_get_stage_ms */

@@ -43,7 +43,7 @@ def compare(r, sc, o, lists=True):
 
 
 def main():
-    what, arg = sys.argv[1], sys.argv[2]
+    what, arg = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
     if what == "parity":
         sc = golden_cases.frame_cases()[arg]()
         fill_rule = int(sys.argv[3]) if len(sys.argv) > 3 else 1
@@ -56,6 +56,8 @@ def main():
             res = compare(r, sc, o)
             res["kernels"] = r.counters()["kernels_launched"]
         print(json.dumps(res))
+    elif what == "direct":
+        print(json.dumps(direct_path_checks(small=True, quick=(arg == "quick"))))
     elif what == "schedulers":
         import dataclasses
         sc = scenes.random_triangles_scene(160, 112, 120, seed=23, cull=2, textured=True, n_meshes=2, sample=1)
@@ -86,6 +88,102 @@ def main():
                 r.render_scene(c, sync=False)
                 res["stepwise"].append(compare(r, c, o, lists=False))
         print(json.dumps(res))
+
+
+def direct_path_checks(small=True, quick=False):
+    """Direct path of the setup kernel (B2R_OPT_DIRECT_MAX_AREA) against the all-binned path on the same frames: every
+    surface, the statistics and the (complete) bins must be identical, for several bin grids, thresholds, fill rules,
+    sort-first tile ownership and with frames in flight (the key buffer must be empty again after every frame).
+    Also used on the GPU (tests/test_gpu_parity.py) with larger frames."""
+    import dataclasses
+    w, h = (160, 112) if small else (640, 360)
+    n = 1 if small else 6
+    cases = {
+        "tiny": scenes.random_triangles_scene(w, h, 900 * n, seed=71, cull=2, size=0.05),
+        "mixed": scenes.random_triangles_scene(w, h, 500 * n, seed=72, cull=0, size=0.3, textured=True, n_meshes=2, sample=1),
+        "spheres": scenes.sphere_grid_scene(w, h, 3, 2, 21 if small else 41, 24 if small else 60),
+        "hostile": scenes.hostile_scene(w, h, 300 * n, seed=73, textured=True),
+        "sliver": scenes.sliver_scene(w, h, 400 * n, seed=74),
+    }
+    res = {}
+
+    def surfaces(r):
+        return [r.framebuffer().copy(), r.depth().copy(), r.winner().copy(), parity.bits(r.z()).copy()]
+
+    for name, sc in cases.items():
+        if quick and name in ("spheres", "sliver"):
+            continue
+        for grid in ("default", "32x32", "24x20", "40x8"):
+            if grid != "default" and (name not in ("tiny", "mixed") or (quick and grid != "24x20")):
+                continue
+            for fill in (1, 0):
+                if fill == 0 and (grid != "default" or (quick and name != "mixed")):
+                    continue
+                with Renderer(sc.width, sc.height) as r:
+                    r.set_option(_lib.OPT_DEBUG_SURFACES, 1)
+                    r.set_option(_lib.OPT_COUNT_FRAGMENTS, 1)
+                    r.set_option(_lib.OPT_FILL_RULE_TOP_LEFT, fill)
+                    r.load_scene(sc)
+                    if grid != "default":
+                        bw, bh = (int(v) for v in grid.split("x"))
+                        r.setup_bins((sc.width + bw - 1) // bw, (sc.height + bh - 1) // bh, bw, bh)
+                    r.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)
+                    r.render_scene(sc)
+                    want, wc, wstats = surfaces(r), r.counters(), r.stats()
+                    wbins = r.bin_lists()
+                    for area in ((16, 4096) if quick else (1, 16, 64, 4096)):
+                        r.set_option(_lib.OPT_DIRECT_MAX_AREA, area)
+                        r.render_scene(sc)
+                        got, gc = surfaces(r), r.counters()
+                        ok = all(np.array_equal(a, b) for a, b in zip(want, got))
+                        ok = ok and gc["pairs"] == wc["pairs"] and gc["fragments"] == wc["fragments"] and r.stats() == wstats
+                        r.render_scene(sc)      # again: the key buffer was left empty
+                        ok = ok and all(np.array_equal(a, b) for a, b in zip(want, surfaces(r)))
+                        gbins = r.bin_lists()      # complete bins (re-run without the path), then the path again
+                        ok = ok and all(np.array_equal(a, b) for a, b in zip(wbins, gbins))
+                        r.render_scene(sc)
+                        ok = ok and all(np.array_equal(a, b) for a, b in zip(want, surfaces(r)))
+                        res[f"{name}/{grid}/fill{fill}/area{area}"] = bool(ok)
+    # sort-first with a replicated front end: each owner renders its tiles only; composed = the whole frame
+    sc = cases["mixed"]
+    with Renderer(sc.width, sc.height) as r:
+        r.load_scene(sc)
+        r.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)
+        r.render_scene(sc)
+        want = r.framebuffer().copy()
+        r.set_option(_lib.OPT_DIRECT_MAX_AREA, 64)
+        composed = np.zeros_like(want)
+        tiles_x = (sc.width + 15) // 16
+        ty, tx = np.meshgrid(np.arange(sc.height) // 16, np.arange(sc.width) // 16, indexing="ij")
+        for rank in range(3):
+            r.set_option(_lib.OPT_TILE_OWNER_COUNT, 3)
+            r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
+            r.render_scene(sc)
+            fb = r.framebuffer()
+            mine = (tx + ty * tiles_x) % 3 == rank
+            composed[mine] = fb[mine]
+        res["owners3"] = bool(np.array_equal(composed, want))
+    # frames in flight with a moving camera: three-stream pipeline and the frame ring
+    sc = cases["tiny"]
+    cams = [dataclasses.replace(sc, cam_pos=(0.15 * i - 0.5, 0.05 * i, 3.0 + 0.1 * i)) for i in range(6)]
+    for mode in ("pipeline", "ring3"):
+        with Renderer(sc.width, sc.height) as r:
+            if mode == "ring3":
+                r.set_option(_lib.OPT_FRAME_RING, 3)
+            r.load_scene(sc)
+            r.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)
+            wants = []
+            for c in cams:
+                r.render_scene(c)
+                wants.append(r.framebuffer().copy())
+            r.set_option(_lib.OPT_DIRECT_MAX_AREA, 64)
+            host = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]
+            for i, c in enumerate(cams):
+                r.render_scene(c, sync=False)
+                r.present_async(host[i])
+            r.present_wait()
+            res[f"inflight/{mode}"] = bool(all(np.array_equal(a, b) for a, b in zip(host, wants)))
+    return res
 
 
 def sharded(world, mode, n_meshes=2, n_tris=700):

@@ -74,6 +74,15 @@ def test_scheduler_modes_compute_the_right_frames(emu_env, mode):
     assert all(all_true(s) for s in res["stepwise"]), res["stepwise"]
 
 
+def test_direct_path_equals_the_binned_path(emu_env):
+    """B2R_OPT_DIRECT_MAX_AREA (small triangles resolved by the setup kernel with atomicMin on the key buffer) against the
+    all-binned path: surfaces, statistics and complete bins identical for several bin grids, thresholds, fill rules,
+    sort-first ownership and with frames in flight (tests/emu_scenarios.py direct_path_checks)."""
+    res = run(emu_env, "direct", "full" if SLOW else "quick")
+    assert res and all(res.values()), {k: v for k, v in res.items() if not v}
+    assert "inflight/ring3" in res and "owners3" in res
+
+
 @pytest.mark.parametrize("mode", ["ring3"] + (["default"] if SLOW else []))
 def test_the_emulation_is_sensitive_to_the_event_waits(emu_env, mode):
     res = run(dict(emu_env, B2R_EMU_IGNORE_WAITS="1"), "schedulers", mode)

@@ -370,3 +370,12 @@ def test_frame_ring_frames_equal_the_oracle(ring):
             assert np.array_equal(r.depth(), o["depth"]) and np.array_equal(r.winner(), o["winner"])
             counts, _, ids = r.bin_lists()
             assert np.array_equal(counts, o["bin_counts"]) and np.array_equal(ids, o["bin_ids"])
+
+
+def test_direct_path_equals_the_binned_path():
+    """B2R_OPT_DIRECT_MAX_AREA: small triangles resolved by the setup kernel (64-bit atomicMin on the key buffer) against the
+    all-binned path - surfaces, statistics and complete bins identical for several bin grids, thresholds, fill rules,
+    sort-first ownership and frames in flight."""
+    import emu_scenarios
+    res = emu_scenarios.direct_path_checks(small=False)
+    assert res and all(res.values()), {k: v for k, v in res.items() if not v}

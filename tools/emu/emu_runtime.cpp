@@ -223,6 +223,14 @@ cudaError_t cudaMemset(void* p, int v, size_t n)
 	legacy(t_device)->q.push_back(op);
 	return 0;
 }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 0; return 1; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 0; return 1; }      // "unsupported": the product falls back to its launch bounds
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, void* stream)
+{
+	Op op; op.type = Op::MEMSET; op.dst = p; op.value = v; op.bytes = n;
+	streamOf(stream)->q.push_back(op);
+	return 0;
+}
 
 // ---- streams and events
 cudaError_t cudaStreamCreateWithFlags(void** s, unsigned) { Stream* st = new Stream{ g_nextStream++, t_device, {} }; g_streams.push_back(st); *s = st; return 0; }

@@ -187,6 +187,14 @@ cudaError_t cudaMemset(void* p, int v, size_t n)
 	LOG("{\"op\":\"memset\",\"dst\":%llu,\"bytes\":%zu,\"stream\":0", (unsigned long long)(uintptr_t)p, n);
 	return 0;
 }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 0; return 1; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 0; return 1; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, void* stream)
+{
+	if (n) memset(p, v, n);
+	LOG("{\"op\":\"memset\",\"dst\":%llu,\"bytes\":%zu,\"stream\":%d", (unsigned long long)(uintptr_t)p, n, streamId(stream));
+	return 0;
+}
 
 // ---- streams and events
 cudaError_t cudaStreamCreateWithFlags(void** s, unsigned flags)
