@@ -116,6 +116,7 @@ struct b2r_context
 	int overlapVertex = 1, usePdl = 1;
 	DeviceVec<float> dOvertexScratch;
 	DeviceVec<uint4> dTriRefs;         // static {v0, v1, v2, mesh} per primitive, rebuilt when the mesh list changes
+	DeviceVec<float4> dColourOut;      // static vertex colours, indexed like the transformed positions (build_colour_stream_kernel)
 	DeviceVec<Chunk> dVsChunks, dTriChunks;
 	uint32_t nVsChunks = 0, nTriChunks = 0;
 	DeviceVec<MeshConst> dMeshConst[kMaxFrameRing];
@@ -137,6 +138,7 @@ struct b2r_context
 		// raster kernel resets what it merges), and one "holds fragments" byte per tile
 		DeviceVec<unsigned long long> keys;
 		DeviceVec<uint8_t> dirty;
+		DeviceVec<uint32_t> binSlots;                 // direct path: the primitives that still go into the lists, in 32-entry slots (triangle_setup_kernel)
 		uint32_t* counters = nullptr;                 // [0] visible, [1] nBig
 		unsigned long long* frameInfo = nullptr;      // [0] pairs [1] overflow [2] unsorted tiles [3] long tiles [4] fragments F
 	} bins[kMaxFrameRing];
@@ -315,6 +317,7 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 		const unsigned long long* oldKeys = B.keys.ptr; const uint8_t* oldDirty = B.dirty.ptr;
 		CU(c, B.keys.reserve(keyWords, c->stream));
 		CU(c, B.dirty.reserve(n + 16, c->stream));
+		CU(c, B.binSlots.reserve(((c->nPrims + 31) / 32 + 8) * 32, c->stream));
 		if (B.keys.ptr != oldKeys) CU(c, cudaMemsetAsync(B.keys.ptr, 0xFF, B.keys.cap * 8, c->stream));
 		if (B.dirty.ptr != oldDirty) CU(c, cudaMemsetAsync(B.dirty.ptr, 0, B.dirty.cap, c->stream));
 		if (B.keys.ptr != oldKeys || B.dirty.ptr != oldDirty) CU(c, cudaStreamSynchronize(c->stream));
@@ -364,6 +367,12 @@ int rebuildScene(b2r_context* c)
 	if (c->nTriChunks)
 	{
 		build_trirefs_kernel<<<c->nTriChunks, kChunk, 0, c->stream>>>(c->dTriChunks.ptr, c->dIndices.ptr, c->dTriRefs.ptr);
+		CU(c, cudaGetLastError());
+	}
+	CU(c, c->dColourOut.reserve(std::max<size_t>(c->nVtxOut, 1), c->stream));
+	if (c->nVsChunks)
+	{
+		build_colour_stream_kernel<<<c->nVsChunks, kChunk, 0, c->stream>>>(c->dVsChunks.ptr, c->dIVertex.ptr, c->dColourOut.ptr);
 		CU(c, cudaGetLastError());
 	}
 	for (int i = 0; i < std::max(2, c->ringDepth); ++i)
@@ -458,29 +467,14 @@ cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, 
 #undef B2R_RASTER_CASE
 }
 
-// persistent grid of the setup kernel: as many CTAs as are resident at once (its warps stride over the primitive groups)
-template <typename K>
-uint32_t setupGrid(const b2r_context* c, K kernel, bool direct, uint32_t prims, int& cached)
-{
-	if (cached < 1)
-	{
-		int n = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kChunk, 0) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = setupCtasPerSM(direct); }
-		cached = n;
-	}
-	const uint32_t groups = (prims + 31u) / 32u;
-	return std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c->numSMs * (uint32_t)cached, (groups + kChunk / 32 - 1) / (kChunk / 32)));
-}
-
 cudaError_t launchSetup(const b2r_context* c, cudaStream_t s, b2r_context::BinSet& B, const float4* pos4, uint32_t* tileCount, uint32_t primLo, uint32_t primHi, const FrameParams& fp)
 {
-	static thread_local int occ[4] = { 0, 0, 0, 0 };      // CTAs per SM of the four instantiations (a property of the binary)
-	const dim3 block(kChunk);
-#define B2R_SETUP_CASE(i, tl, direct) return launchFrameKernel(c, triangle_setup_kernel<tl, direct>, dim3(setupGrid(c, triangle_setup_kernel<tl, direct>, direct, primHi - primLo, occ[i])), block, 0, s, \
-		(const uint4*)c->dTriRefs.ptr, pos4, B.rects.ptr, tileCount, B.bigList.ptr, B.counters, B.keys.ptr, B.dirty.ptr, B.frameInfo, primLo, primHi, fp)
-	if (fp.directMaxArea) { if (c->fillTopLeft) B2R_SETUP_CASE(0, true, true); B2R_SETUP_CASE(1, false, true); }
-	if (c->fillTopLeft) B2R_SETUP_CASE(2, true, false);
-	B2R_SETUP_CASE(3, false, false);
+	const dim3 grid((primHi - primLo + kChunk - 1) / kChunk), block(kChunk);
+#define B2R_SETUP_CASE(tl, direct) return launchFrameKernel(c, triangle_setup_kernel<tl, direct>, grid, block, 0, s, (const uint4*)c->dTriRefs.ptr, pos4, B.rects.ptr, \
+		tileCount, B.bigList.ptr, B.counters, B.binSlots.ptr, B.keys.ptr, B.dirty.ptr, B.frameInfo, primLo, primHi, fp)
+	if (fp.directMaxArea) { if (c->fillTopLeft) B2R_SETUP_CASE(true, true); B2R_SETUP_CASE(false, true); }
+	if (c->fillTopLeft) B2R_SETUP_CASE(true, false);
+	B2R_SETUP_CASE(false, false);
 #undef B2R_SETUP_CASE
 }
 
@@ -736,7 +730,7 @@ int enqueueFrame(b2r_context* c)
 			ShardRegions R{};
 			if (sh.bound)
 				for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], set, sh.self);
-			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, fs, B.rects.ptr, primLo, primHi, tileOffset,
+			CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, fs, B.rects.ptr, fp.directMaxArea ? (const uint32_t*)B.binSlots.ptr : (const uint32_t*)nullptr, primLo, primHi, tileOffset,
 				B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp, R, sh.bound ? (uint32_t)sh.n : 0u, (uint32_t)sh.self));
 			++c->kernelsLaunched;
 		}
@@ -759,7 +753,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr; A.colour = c->dColourOut.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		A.keys = B.keys.ptr; A.dirty = B.dirty.ptr; c->lastDirect = fp.directMaxArea != 0u;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
@@ -1011,7 +1005,7 @@ int enqueueFrameRing(b2r_context* c)
 		ShardRegions R{};
 		if (sh.bound)
 			for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], k, sh.self);
-		CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, rs, B.rects.ptr, primLo, primHi, tileOffset,
+		CU(c, launchFrameKernel(c, bin_scatter_kernel, dim3(primBlocks + (uint32_t)c->numSMs * 2), dim3(256), 0, rs, B.rects.ptr, fp.directMaxArea ? (const uint32_t*)B.binSlots.ptr : (const uint32_t*)nullptr, primLo, primHi, tileOffset,
 			B.tileCursor.ptr, binIds, B.bigList.ptr, B.counters, primBlocks, B.frameInfo, fp, R, sh.bound ? (uint32_t)sh.n : 0u, (uint32_t)sh.self));
 		++c->kernelsLaunched;
 	}
@@ -1027,7 +1021,7 @@ int enqueueFrameRing(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr; A.colour = c->dColourOut.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		A.keys = B.keys.ptr; A.dirty = B.dirty.ptr; c->lastDirect = fp.directMaxArea != 0u;
 		// the frames of the ring alternate strictly between the two colour + depth surface pairs (sharded: every rank writes
@@ -1332,12 +1326,12 @@ void b2r_destroy(b2r_context* c)
 	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->frontDone[i]) cudaEventDestroy(c->frontDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();
-	c->dTriRefs.release(); c->dVsChunks.release(); c->dTriChunks.release();
+	c->dTriRefs.release(); c->dColourOut.release(); c->dVsChunks.release(); c->dTriChunks.release();
 	for (auto& v : c->dMeshConst) v.release(); c->dMeshStatic.release(); c->dTexDesc.release();
 	for (auto& B : c->bins)
 	{
 		B.rects.release(); B.tileCount.release(); B.tileOffset.release(); B.tileCursor.release(); B.longTiles.release();
-		B.tileOrder.release(); B.bigList.release(); B.binIds.release(); B.keys.release(); B.dirty.release();
+		B.tileOrder.release(); B.bigList.release(); B.binIds.release(); B.keys.release(); B.dirty.release(); B.binSlots.release();
 		cudaFree(B.frameInfo);
 	}
 	cudaFree(c->dFramebuffer); cudaFree(c->dDepth); cudaFree(c->dZ); cudaFree(c->dWinner);

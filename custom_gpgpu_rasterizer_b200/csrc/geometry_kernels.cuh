@@ -199,7 +199,7 @@ __device__ __forceinline__ bool tileOwned(const FrameParams& fp, uint32_t tile)
 // same few tiles).  Every lane of the warp must call this the same number of times (`steps` =
 // warp-wide maximum of nTiles); lanes with k >= nTiles pass tile = kNoTile.
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-constexpr uint32_t kBinnedCounterWord = 2;         // counters[2]: primitives with a small rectangle that went into the lists (what bin_scatter_kernel has to visit)
+constexpr uint32_t kBinSlotsWord = 2;              // counters[2]: direct path - 32-entry slots of primitives with a small rectangle that went into the lists (what bin_scatter_kernel has to visit)
 constexpr uint32_t kRectDirect = 0x80000000u;      // rects[prim].x bit 31: the setup kernel resolved the triangle itself (direct path), it is in no list
 // counters[]: [0] visible triangles (summed by tile_scan_kernel), [1] big triangles,
 // [kVisBase + 32*s] partial visible counts, one 128-byte line per slot,
@@ -446,6 +446,19 @@ __global__ void __launch_bounds__(kChunk) build_trirefs_kernel(const Chunk* __re
 	if (threadIdx.x >= ch.count) return;
 	const uint32_t* ip = indices + (size_t)ch.inStart + (size_t)threadIdx.x * 3;
 	triRefs[ch.primStart + threadIdx.x] = make_uint4(ch.outStart + __ldg(ip), ch.outStart + __ldg(ip + 1), ch.outStart + __ldg(ip + 2), ch.mesh);
+}
+
+// scene-load time: the vertex colours (IVertex floats 11..13, which GetNDCVertex copies unchanged) as a 16-byte stream
+// indexed like the transformed positions, so the deferred shade of an untextured pixel is vertex reference -> {3 positions,
+// 3 colours} in ONE round of independent 16-byte loads instead of reference -> mesh constants -> six 8-byte loads out of
+// the 56-byte records
+__global__ void __launch_bounds__(kChunk) build_colour_stream_kernel(const Chunk* __restrict__ chunks, const float2* __restrict__ ivertex, float4* __restrict__ colourOut)
+{
+	const Chunk ch = chunks[blockIdx.x];
+	if (threadIdx.x >= ch.count) return;
+	const float2* rec = ivertex + (size_t)(ch.inStart + threadIdx.x) * 7;
+	const float2 a = __ldg(rec + 5), b = __ldg(rec + 6);
+	colourOut[(size_t)ch.outStart + threadIdx.x] = make_float4(a.y, b.x, b.y, 0.f);
 }
 
 // screen mapping of the three NDC vertices (CUDAROPs.cu:88-97) and the float bounds
@@ -757,7 +770,7 @@ constexpr int kScatterPerThread = B2R_SCATTER_PER_THREAD;
 // scatter of the small rectangles: one thread per primitive, re-reading the 8 B rectangle; the
 // slot inside the tile's list comes from a warp-aggregated atomic on the tile cursor.
 __global__ void __launch_bounds__(256) bin_scatter_kernel(
-	const uint2* __restrict__ rects, uint32_t primLo, uint32_t primHi, const uint32_t* __restrict__ tileOffset,
+	const uint2* __restrict__ rects, const uint32_t* __restrict__ binSlots /*direct path: see triangle_setup_kernel; else null*/, uint32_t primLo, uint32_t primHi, const uint32_t* __restrict__ tileOffset,
 	uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ binIds,
 	const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ counters, uint32_t primBlocks,
 	const unsigned long long* __restrict__ frameInfo, FrameParams fp,
@@ -772,22 +785,40 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 		binBigBody<true>(blockIdx.x - primBlocks, gridDim.x - primBlocks, bigList, counters, rects, nullptr, tileOffset, tileCursor, binIds, fp, M);
 		return;
 	}
-	// nothing but directly resolved (or culled) primitives: no rectangle to re-read (triangle_setup_kernel counts the others)
-	if (__ldg(counters + kBinnedCounterWord) == 0u) return;
 	// kScatterPerThread primitives per thread (a CTA covers kScatterPerThread * 256 consecutive ids): the rectangle
 	// loads are issued together, so their latency is paid once; each warpBinRects call still sees one aligned
 	// group of 32 consecutive ids, which is all the run sorter assumes
 	uint2 rc[kScatterPerThread];
-	#pragma unroll
-	for (int k = 0; k < kScatterPerThread; ++k)
+	uint32_t prims[kScatterPerThread];
+	if (binSlots)
 	{
-		const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
-		rc[k] = (prim < primHi) ? __ldg(rects + prim) : make_uint2(0x0000FFFFu, 0x0000FFFFu);
+		// direct path: only the primitives triangle_setup_kernel left in the slots (one slot = the ids of one of its warps, in lane
+		// order - so each warpBinRects call below still sees ascending ids of one aligned group of 32)
+		const uint32_t nSlots = __ldg(counters + kBinSlotsWord);
+		if (blockIdx.x * (kScatterPerThread * 8u) >= nSlots) return;
+		#pragma unroll
+		for (int k = 0; k < kScatterPerThread; ++k)
+		{
+			const uint32_t slot = (blockIdx.x * kScatterPerThread + k) * 8u + (threadIdx.x >> 5);
+			prims[k] = slot < nSlots ? __ldg(binSlots + (size_t)slot * 32u + (threadIdx.x & 31u)) : kNoPrim;
+		}
+	}
+	else
+	{
+		#pragma unroll
+		for (int k = 0; k < kScatterPerThread; ++k)
+		{
+			const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
+			prims[k] = prim < primHi ? prim : kNoPrim;
+		}
 	}
 	#pragma unroll
 	for (int k = 0; k < kScatterPerThread; ++k)
+		rc[k] = (prims[k] != kNoPrim) ? __ldg(rects + prims[k]) : make_uint2(0x0000FFFFu, 0x0000FFFFu);
+	#pragma unroll
+	for (int k = 0; k < kScatterPerThread; ++k)
 	{
-		const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
+		const uint32_t prim = prims[k];
 		uint32_t nTiles = 0;
 		const int bx0 = rc[k].x & 0xFFFF, by0 = rc[k].y & 0xFFFF, bx1 = (rc[k].x >> 16) & 0x7FFF, by1 = rc[k].y >> 16;
 		if (bx0 <= bx1 && by0 <= by1 && !(rc[k].x & kRectDirect))

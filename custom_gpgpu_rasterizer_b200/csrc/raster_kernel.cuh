@@ -26,6 +26,7 @@ struct RasterArgs
 	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
 	const float2* ivertex;      // resident IVertex records (7 float2 each)
+	const float4* colour;       // the records' vertex colours, indexed like pos4 (build_colour_stream_kernel)
 	const MeshConst* meshes;
 	const TexDesc* textures;
 	unsigned long long* frameInfo;
@@ -115,158 +116,191 @@ __device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, 
 // On a scene of sub-pixel triangles this removes the bin lists altogether; the 66 MB key buffer of a 4K frame lives
 // in B200's 126 MB L2.
 //
-// The kernel is persistent and software-pipelined.  A primitive costs two dependent memory round trips (vertex
-// reference -> three positions) before a few hundred instructions of arithmetic; with one primitive per thread the SM
-// idles on those round trips more than half of the time (ncu: issue slots 46 % busy, long-scoreboard 48 %).  Here a
-// warp walks over groups of 32 consecutive primitives (group g, g + W, g + 2W ... for W resident warps) and keeps two
-// groups in flight behind the one it works on: the positions of the NEXT group and the vertex references of the one after
-// are requested before the arithmetic of the current group starts and are consumed an iteration later.
+// The direct path runs in two phases inside the CTA, with a stream compaction through shared memory in between.  Phase
+// A is the setup proper, one thread per primitive: two dependent memory round trips (vertex reference -> three
+// positions), cull, rectangle, candidate box; a small triangle that has candidate pixels leaves a 64-byte record in
+// shared memory.  Phase B takes the records one per thread - the culled, off-pixel and binned primitives are gone, so
+// its warps are full - and walks the candidate pixels.  The two phases do not share registers (the fused
+// one-primitive-per-thread form needed 64-80 and idled on the round trips: ncu issue slots 46 % busy), so five CTAs
+// are resident per SM and the arithmetic of one hides the round trips of the others.
 #ifndef B2R_SETUP_DIRECT_CTAS
-#define B2R_SETUP_DIRECT_CTAS 3
+#define B2R_SETUP_DIRECT_CTAS 5
 #endif
-#ifndef B2R_SETUP_PLAIN_CTAS
-#define B2R_SETUP_PLAIN_CTAS 5
-#endif
-constexpr int setupCtasPerSM(bool direct) { return direct ? B2R_SETUP_DIRECT_CTAS : B2R_SETUP_PLAIN_CTAS; }
+struct __align__(16) DirectRecord
+{
+	float x0, y0, x1, y1;
+	float x2, y2, z0, z1;
+	float z2, area, rcpArea, divLo;
+	uint32_t prim, boxX /*x0 | x1 << 16*/, boxY /*y0 | y1 << 16*/, pad;
+};
 template <bool TOPLEFT, bool DIRECT>
-__global__ void __launch_bounds__(kChunk, setupCtasPerSM(DIRECT)) triangle_setup_kernel(
+__global__ void __launch_bounds__(kChunk, DIRECT ? B2R_SETUP_DIRECT_CTAS : 1) triangle_setup_kernel(
 	const uint4* __restrict__ triRefs, const float4* __restrict__ pos4, uint2* __restrict__ rects,
-	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig,[2]=binned*/,
+	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig,[2]=slots*/,
+	uint32_t* __restrict__ binSlots /*DIRECT: the primitives bin_scatter_kernel has to visit, one 32-entry slot per warp that has any*/,
 	unsigned long long* __restrict__ keys, uint8_t* __restrict__ dirty, unsigned long long* __restrict__ frameInfo,
 	uint32_t primLo, uint32_t primHi, const __grid_constant__ FrameParams fp)
 {
 	pdlPrologue();
+	__shared__ DirectRecord sRec[DIRECT ? kChunk : 1];
+	__shared__ uint32_t sRecCount;
+	if (DIRECT && threadIdx.x == 0) sRecCount = 0;
+	if (DIRECT) __syncthreads();
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t nWarps = gridDim.x * (kChunk / 32), warpId = blockIdx.x * (kChunk / 32) + (threadIdx.x >> 5);
-	const uint32_t nGroups = (primHi - primLo + 31u) / 32u;
-	if (warpId >= nGroups) return;
-	auto loadRef = [&](uint32_t g) -> uint4
+	bool visible = false;
+	const uint32_t prim = primLo + blockIdx.x * kChunk + threadIdx.x;
+	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+	uint32_t nTiles = 0, directTiles = 0;
+	bool record = false;
+	DirectRecord rec;
+	if (prim < primHi)
 	{
-		const uint32_t q = primLo + g * 32u + lane;
-		return (g < nGroups && q < primHi) ? __ldcs(triRefs + q) : make_uint4(0u, 0u, 0u, 0u);
-	};
-	// pipeline fill: positions of this warp's first group, vertex references of its second
-	uint4 trNext = loadRef(warpId);
-	float4 q0 = __ldg(pos4 + trNext.x), q1 = __ldg(pos4 + trNext.y), q2 = __ldg(pos4 + trNext.z);
-	trNext = loadRef(warpId + nWarps);
-	uint32_t nFrags = 0, visTotal = 0, binnedTotal = 0;
-	unsigned long long directTotal = 0ull;
-	for (uint32_t g = warpId; g < nGroups; g += nWarps)
-	{
-		const float4 p0 = q0, p1 = q1, p2 = q2;
-		if (g + nWarps < nGroups)
+		const uint4 tr = __ldcs(triRefs + prim);
+		const float4 p0 = __ldg(pos4 + tr.x), p1 = __ldg(pos4 + tr.y), p2 = __ldg(pos4 + tr.z);
+		visible = true;
+		if (fp.cullMode != 2u)
 		{
-			// (the references were requested an iteration ago; index 0 of a lane past the end is a valid position)
-			q0 = __ldg(pos4 + trNext.x); q1 = __ldg(pos4 + trNext.y); q2 = __ldg(pos4 + trNext.z);
-			trNext = loadRef(g + 2u * nWarps);
+			const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+			const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+			float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
+			normalize3(nx, ny, nz);
+			// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
+			const float d = (fp.cullMode == 0u)
+				? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
+				: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
+			if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
 		}
-		const uint32_t prim = primLo + g * 32u + lane;
-		bool visible = false;
-		int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
-		uint32_t nTiles = 0, directTiles = 0;
-		if (prim < primHi)
+		if (visible)
 		{
-			visible = true;
-			if (fp.cullMode != 2u)
+			const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
+			const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
+			const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
+			visible = !(xOut || yOut || zOut);
+		}
+		if (visible)
+		{
+			TriRecord r;
+			const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
+			const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
+			const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
+			const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
+			const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
+			// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
+			const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+			bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
+			by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
+			bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
+			by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
+			if (bx0 <= bx1 && by0 <= by1)
 			{
-				const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
-				const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
-				float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
-				normalize3(nx, ny, nz);
-				// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
-				const float d = (fp.cullMode == 0u)
-					? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
-					: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
-				if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
-			}
-			if (visible)
-			{
-				const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
-				const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
-				const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
-				visible = !(xOut || yOut || zOut);
-			}
-			if (visible)
-			{
-				TriRecord r;
-				const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
-				const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
-				const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
-				const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
-				const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
-				// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
-				const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
-				bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
-				by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
-				bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
-				by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
-				if (bx0 <= bx1 && by0 <= by1)
+				nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
+				if (DIRECT)
 				{
-					nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
-					if (DIRECT)
+					rasterConstants(b, fp, r);
+					// candidate pixels: the candidate box inside the bins of the rectangle (the box is already clamped to the screen)
+					const int x0 = max((int)(r.cbX & 0xFFFFu), bx0 * (int)fp.binW), x1 = min((int)(r.cbX >> 16), (bx1 + 1) * (int)fp.binW);
+					const int y0 = max((int)(r.cbY & 0xFFFFu), by0 * (int)fp.binH), y1 = min((int)(r.cbY >> 16), (by1 + 1) * (int)fp.binH);
+					const uint32_t area = (x1 > x0 && y1 > y0) ? (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) : 0u;
+					if (area <= fp.directMaxArea)
 					{
-						rasterConstants(b, fp, r);
-						// candidate pixels: the candidate box inside the bins of the rectangle (the box is already clamped to the screen)
-						const int x0 = max((int)(r.cbX & 0xFFFFu), bx0 * (int)fp.binW), x1 = min((int)(r.cbX >> 16), (bx1 + 1) * (int)fp.binW);
-						const int y0 = max((int)(r.cbY & 0xFFFFu), by0 * (int)fp.binH), y1 = min((int)(r.cbY >> 16), (by1 + 1) * (int)fp.binH);
-						const uint32_t area = (x1 > x0 && y1 > y0) ? (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) : 0u;
-						if (area <= fp.directMaxArea)
+						directTiles = nTiles;
+						nTiles = 0;
+						if (area)
 						{
-							directTiles = nTiles;
-							nTiles = 0;
-							if (area)
-							{
-								TriShared t;
-								expandRecord(r, prim, t);
-								const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
-								for (int y = y0; y < y1; ++y)
-									for (int x = x0; x < x1; ++x)
-									{
-										Bary bc; int zi;
-										if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
-										{
-											const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
-											if (replicated && tile % fp.ownerCount != fp.ownerRank) continue;
-											atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | prim);
-											dirty[tile] = 1;
-											++nFrags;
-										}
-									}
-							}
+							record = true;
+							rec.x0 = r.x0; rec.y0 = r.y0; rec.x1 = r.x1; rec.y1 = r.y1; rec.x2 = r.x2; rec.y2 = r.y2;
+							rec.z0 = r.z0; rec.z1 = r.z1; rec.z2 = r.z2; rec.area = r.area; rec.rcpArea = r.rcpArea; rec.divLo = r.divLo;
+							rec.prim = prim; rec.boxX = (uint32_t)x0 | ((uint32_t)x1 << 16); rec.boxY = (uint32_t)y0 | ((uint32_t)y1 << 16); rec.pad = 0u;
 						}
 					}
 				}
 			}
-			// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
-			// from a visible primitive whose rectangle happens to be empty
-			// (bit 31 of the first word: resolved here, not to be scattered into the lists)
-			rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16) | (directTiles ? kRectDirect : 0u), (uint32_t)by0 | ((uint32_t)by1 << 16))
-			                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
 		}
-		// statistics of the group (flushed once per warp at the end)
-		visTotal += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, visible));
-		if (DIRECT) directTotal += (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, min(directTiles, 0x00FFFFFFu));      // (a rectangle has at most 2^22 tiles)
-
-		// per-tile counts, warp-aggregated
-		if (nTiles > fp.bigRectTiles)
-		{
-			bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
-			nTiles = 0;
-		}
-		binnedTotal += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, nTiles > 0u));
-		warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
+		// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
+		// from a visible primitive whose rectangle happens to be empty
+		// (bit 31 of the first word: resolved here, not to be scattered into the lists)
+		rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16) | (directTiles ? kRectDirect : 0u), (uint32_t)by0 | ((uint32_t)by1 << 16))
+		                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
 	}
-	// statistics: a few atomics per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+	if (DIRECT)
 	{
-		uint32_t* slot = &counters[kVisBase + (warpId % kVisSlots) * 32];
-		if (DIRECT && fp.countFragments) nFrags = __reduce_add_sync(0xFFFFFFFFu, nFrags);
-		if (lane == 0)
+		// compaction: one shared-memory atomic per warp
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, record);
+		if (m)
 		{
-			if (visTotal) atomicAdd(slot, visTotal);
-			if (binnedTotal) atomicAdd(&counters[kBinnedCounterWord], binnedTotal);
-			if (DIRECT && directTotal) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, directTotal);
-			if (DIRECT && fp.countFragments && nFrags) atomicAdd(&frameInfo[4], (unsigned long long)nFrags);
+			uint32_t base = 0;
+			if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&sRecCount, (uint32_t)__popc(m));
+			base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+			if (record) sRec[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
 		}
+	}
+	// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+	{
+		const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
+		uint32_t* slot = &counters[kVisBase + ((blockIdx.x * 8 + (threadIdx.x >> 5)) % kVisSlots) * 32];
+		if (lane == 0 && vis) atomicAdd(slot, (uint32_t)__popc(vis));
+		if (DIRECT)
+		{
+			const uint32_t dt = __reduce_add_sync(0xFFFFFFFFu, min(directTiles, 0x00FFFFFFu));      // (a rectangle has at most 2^22 tiles)
+			if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, (unsigned long long)dt);
+		}
+	}
+	// per-tile counts, warp-aggregated
+	if (nTiles > fp.bigRectTiles)
+	{
+		bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
+		nTiles = 0;
+	}
+	if (DIRECT)
+	{
+		// the few triangles that still go into the lists: the scatter kernel visits them through 32-entry slots (this warp's
+		// ids in lane order, kNoPrim where a lane has none) instead of re-reading the rectangle of every primitive
+		const unsigned binned = __ballot_sync(0xFFFFFFFFu, nTiles > 0u);
+		if (binned)
+		{
+			uint32_t slot = 0;
+			if (lane == 0) slot = atomicAdd(&counters[kBinSlotsWord], 1u);
+			slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+			binSlots[(size_t)slot * 32u + lane] = nTiles > 0u ? prim : kNoPrim;
+		}
+	}
+	warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
+	if (!DIRECT) return;
+
+	// ---- phase B: the recorded triangles, one per thread
+	__syncthreads();
+	uint32_t nFrags = 0;
+	if (threadIdx.x < sRecCount)
+	{
+		const DirectRecord& q = sRec[threadIdx.x];
+		TriShared t;
+		t.x0 = q.x0; t.y0 = q.y0; t.x1 = q.x1; t.y1 = q.y1; t.x2 = q.x2; t.y2 = q.y2;
+		t.z0 = q.z0; t.z1 = q.z1; t.z2 = q.z2; t.area = q.area; t.rcpArea = q.rcpArea; t.divLo = q.divLo;
+		t.eAx = q.x1 - q.x0; t.eAy = q.y1 - q.y0;      // the subtractions of expandRecord: same bits as in the raster kernel
+		t.eBx = q.x2 - q.x1; t.eBy = q.y2 - q.y1;
+		t.eCx = q.x0 - q.x2; t.eCy = q.y0 - q.y2;
+		t.prim = q.prim; t.zLow = 0; t.yExtent = 0;
+		const int x0 = (int)(q.boxX & 0xFFFFu), x1 = (int)(q.boxX >> 16), y0 = (int)(q.boxY & 0xFFFFu), y1 = (int)(q.boxY >> 16);
+		const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+		const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
+		for (int y = y0; y < y1; ++y)
+			for (int x = x0; x < x1; ++x)
+			{
+				Bary bc; int zi;
+				if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+				{
+					const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
+					if (replicated && tile % fp.ownerCount != fp.ownerRank) continue;
+					atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | t.prim);
+					dirty[tile] = 1;
+					++nFrags;
+				}
+			}
+	}
+	if (fp.countFragments)
+	{
+		nFrags = __reduce_add_sync(0xFFFFFFFFu, nFrags);
+		if (lane == 0 && nFrags) atomicAdd(&frameInfo[4], (unsigned long long)nFrags);
 	}
 }
 
@@ -777,9 +811,9 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 				if (!TEXTURED || (fp.visState == 0u && !textured))
 				{
 					// vertex colour (IVertex floats 11..13, copied unchanged by GetNDCVertex), NOT multiplied
-					// by wInterpolated (CUDAROPs.cu:379)
-					const float2 a0 = __ldg(r0 + 5), b0 = __ldg(r0 + 6), a1 = __ldg(r1 + 5), b1 = __ldg(r1 + 6), a2 = __ldg(r2 + 5), b2 = __ldg(r2 + 6);
-					colour = packColour(S(a0.y, a1.y, a2.y), S(b0.x, b1.x, b2.x), S(b0.y, b1.y, b2.y));
+					// by wInterpolated (CUDAROPs.cu:379); read from the colour stream (same values, indexed like the positions)
+					const float4 c0 = __ldg(A.colour + tr.x), c1 = __ldg(A.colour + tr.y), c2 = __ldg(A.colour + tr.z);
+					colour = packColour(S(c0.x, c1.x, c2.x), S(c0.y, c1.y, c2.y), S(c0.z, c1.z, c2.z));
 				}
 				else if (fp.visState == 0u && mc.tex[1] < 0)
 				{

@@ -87,7 +87,9 @@ def test_allocation_time_fills_are_completed_before_use(logs):
     assert fills
     for i in fills:
         nxt = next(o for o in ops[i + 1:] if o["op"] not in ("memset", "malloc"))
-        assert nxt["op"] in ("stream_sync", "launch", "memcpy") and nxt["stream"] == 0, (ops[i], nxt)
+        # (a fill on one of the context's own streams - cudaMemsetAsync: the key buffer of the direct path - is ordered by that
+        # stream: it must be synchronised, or followed by more work of the same stream, before anything else)
+        assert nxt["op"] in ("stream_sync", "launch", "memcpy") and nxt["stream"] == ops[i]["stream"], (ops[i], nxt)
 
 
 # ---- the sharded sort-first front end: N contexts of one process stand for the N ranks (tests/trace_scenarios/sharded.py)
@@ -262,7 +264,7 @@ def test_wiring_check_has_teeth(logs, sharded_logs, tmp_path):
     assert any("binIds" in e for e in t.wiring_errors())
 
     def other_inbox(raw, nxt):
-        raw[13 * 8:14 * 8] = nxt[13 * 8:14 * 8]  # RasterArgs.shard.tileCount[0] of the next frame's list set
+        raw[14 * 8:15 * 8] = nxt[14 * 8:15 * 8]  # RasterArgs.shard.tileCount[0] of the next frame's list set
     t = mutate(sharded_logs[(2, "ring3")], lambda l: '"dev":1' in l, other_inbox)
     assert any("reads the heads of rank 0" in e for e in t.wiring_errors(2))
 

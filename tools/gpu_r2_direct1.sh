@@ -11,7 +11,7 @@ B="timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-fill
 for a in 0 16 64; do
 	B2R_DIRECT_MAX_AREA=$a $B > $O/bench_spheres_a$a.json 2> $O/bench_spheres_a$a.err
 done
-for v in setup4; do
+for v in none; do
 	[ -f build/variants/libb2r_$v.so ] && B2R_LIBRARY=$PWD/build/variants/libb2r_$v.so $B > $O/bench_spheres_$v.json 2> $O/bench_spheres_$v.err
 done
 for w in vehicle480 vehicle1080 views172; do

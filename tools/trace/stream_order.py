@@ -46,10 +46,10 @@ import sys
 from collections import defaultdict
 
 K_MAX_RANKS = 8
-RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("ivertex", "r"),
+RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("ivertex", "r"), ("colour", "r"),
                ("meshes", "r"), ("textures", "r"), ("frameInfo", "w"), ("framebuffer", "w"), ("depth", "w"), ("zSurface", "w"), ("winnerSurface", "w")]
 RASTER_ARGS += [(f"shard.tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"shard.tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)] \
-    + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r")]      # the raster kernel sorts the lists it stages, in place
+    + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r"), ("keys", "w"), ("dirty", "w")]      # the raster kernel sorts the lists it stages, in place, and resets the key buffer it merges
 STRUCTS = {
     "b2r::RasterArgs": RASTER_ARGS,
     "b2r::ShardTable": [(f"tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)]
@@ -182,16 +182,17 @@ class Trace:
         "vertex_transform_kernel": {"meshConst": 2, "posIn": 3, "pos4": 4},
         "vertex_transform_marked_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3, "frameInfo": 7},
         "shard_mark_vertices_kernel": {"triRefs": 4, "frameInfo": 6},
-        "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5},
+        "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5, "binSlots": 6, "keys": 7, "dirty": 8, "frameInfo": 9},
         "bin_big_count_kernel": {"bigList": 0, "counters": 1, "rects": 2, "tileCount": 3},
-        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "counters": 10, "frameInfo": 13},
-        "bin_scatter_kernel": {"rects": 0, "tileOffset": 3, "tileCursor": 4, "binIds": 5, "bigList": 6, "counters": 7, "frameInfo": 9},      # args[11] = ShardRegions: the mirror of the lists in the owners' arenas
+        "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "dirty": 8, "counters": 11, "frameInfo": 14},
+        "bin_scatter_kernel": {"rects": 0, "binSlots": 1, "tileOffset": 4, "tileCursor": 5, "binIds": 6, "bigList": 7, "counters": 8, "frameInfo": 10},      # args[12] = ShardRegions: the mirror of the lists in the owners' arenas
         "bin_sort_tiles_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 4},
         "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
         "shard_merge_heads_kernel": {"tileOrder": 4, "frameInfo": 5},
         "publish_info_kernel": {"frameInfo": 0},
     }
-    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "meshConst": 6, "frameInfo": 8, "tileOrder": 13 + 3 * K_MAX_RANKS}
+    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "meshConst": 7, "frameInfo": 9, "tileOrder": 14 + 3 * K_MAX_RANKS,
+                    "keys": 15 + 3 * K_MAX_RANKS, "dirty": 16 + 3 * K_MAX_RANKS}
 
     def frames(self):
         """Per device: the launches of every frame, in the order the host issued them (b2r_render issues a whole frame; a
@@ -253,10 +254,10 @@ class Trace:
                 for d in range(ranks):
                     setup, scatter = get(d, "triangle_setup_kernel"), get(d, "bin_scatter_kernel")
                     if setup is not None:
-                        lo, hi = u32(setup["args"][6]), u32(setup["args"][7])
+                        lo, hi = u32(setup["args"][10]), u32(setup["args"][11])
                         slices.append((lo, hi, d))
-                        if scatter is not None and (u32(scatter["args"][1]), u32(scatter["args"][2])) != (lo, hi):
-                            errs.append(f"frame {i}: rank {d} bins primitives [{lo}, {hi}) but scatters [{u32(scatter['args'][1])}, {u32(scatter['args'][2])})")
+                        if scatter is not None and (u32(scatter["args"][2]), u32(scatter["args"][3])) != (lo, hi):
+                            errs.append(f"frame {i}: rank {d} bins primitives [{lo}, {hi}) but scatters [{u32(scatter['args'][2])}, {u32(scatter['args'][3])})")
                 if slices:
                     if slices[0][0] != 0 or any(a[1] != b[0] for a, b in zip(slices, slices[1:])) or any(lo >= hi for lo, hi, _ in slices):
                         errs.append(f"frame {i}: the ranks' primitive slices {[(lo, hi) for lo, hi, _ in slices]} do not tile the primitives in rank order")
@@ -265,13 +266,13 @@ class Trace:
                           for d in range(ranks)}
                 if len(epochs) != 1:
                     errs.append(f"frame {i}: the ranks' barrier epochs differ: {sorted(epochs)}")
-                surfaces = {self._ptr(r["args"][0], 9) for r in rasters}
+                surfaces = {self._ptr(r["args"][0], 10) for r in rasters}
                 if len(surfaces) != 1:
                     errs.append(f"frame {i}: the ranks store their colours into different surfaces {sorted(hex(x) for x in surfaces)}")
                 for q in range(ranks):                     # tile owner q reads ...
                     for p in range(ranks):                 # ... what rank p pushed
-                        base = 13                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
-                        want_count, want_off = self._ptr(heads[p]["args"][11], q), self._ptr(heads[p]["args"][11], K_MAX_RANKS + q)
+                        base = 14                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
+                        want_count, want_off = self._ptr(heads[p]["args"][12], q), self._ptr(heads[p]["args"][12], K_MAX_RANKS + q)
                         got_count, got_off = self._ptr(rasters[q]["args"][0], base + p), self._ptr(rasters[q]["args"][0], base + K_MAX_RANKS + p)
                         if (want_count, want_off) != (got_count, got_off):
                             errs.append(f"frame {i}: rank {q} reads the heads of rank {p} at {got_count:#x}/{got_off:#x}, rank {p} pushed them to {want_count:#x}/{want_off:#x}")
@@ -279,7 +280,7 @@ class Trace:
                         if p == q:
                             want_ids = self._ptr(rasters[q]["args"][0], 2)
                         else:
-                            want_ids = self._ptr(lists[p]["args"][11], q) if lists[p] is not None else got_ids
+                            want_ids = self._ptr(lists[p]["args"][12], q) if lists[p] is not None else got_ids
                         if want_ids != got_ids:
                             errs.append(f"frame {i}: rank {q} reads the lists of rank {p} at {got_ids:#x}, they are at {want_ids:#x}")
         return errs
