@@ -786,7 +786,7 @@ def run_b200(args, scene):
                           "device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), ") +
                          "wall clock over all frames incl. the final wait and a barrier across the ranks")},
         "frame_ring": ring if (world == 1 or sharded) else 0,
-        "direct_max_area": (0 if sharded else r.get_option(_lib.OPT_DIRECT_MAX_AREA)),
+        "direct_max_area": r.get_option(_lib.OPT_DIRECT_MAX_AREA),
         "gpu_launches": launches_per_frame * args.steps,
         "gpu_launches_per_step": launches_per_frame,
         "host_enqueue_ms_per_frame": host_enqueue_ms,

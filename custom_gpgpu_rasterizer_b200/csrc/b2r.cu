@@ -229,6 +229,14 @@ struct b2r_context
 		uint32_t* inboxOffset(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + n + src) * tilesPad; }
 		uint32_t* binIds(uint8_t* base, int set) const { return tileCount(base, set) + (size_t)(2 + 2 * n) * tilesPad; }
 		uint32_t* region(uint8_t* base, int set, int src) const { return binIds(base, set) + (size_t)(1 + src) * listCap; }   // lists pushed by rank src
+		// direct path (direct = true: decided at b2r_shard_prepare, the same on every rank): behind the list regions of a set, the
+		// key-buffer blocks rank src pushed for the tiles owned here (256 keys per owned tile) and its per-tile bytes
+		bool direct = false;
+		size_t ownedMax = 0;
+		unsigned long long* keyInbox(uint8_t* base, int set, int src) const
+		{ return reinterpret_cast<unsigned long long*>(region(base, set, n)) + (size_t)src * ownedMax * 256; }
+		uint8_t* dirtyInbox(uint8_t* base, int set, int src) const
+		{ return reinterpret_cast<uint8_t*>(keyInbox(base, set, n)) + (size_t)src * tilesPad; }
 	} shard;
 	// bin buffers of the newest frame (the DeviceVecs, or one set of the shard arena)
 	uint32_t* curTileCount = nullptr; uint32_t* curTileOffset = nullptr; uint32_t* curBinIds = nullptr;
@@ -399,8 +407,8 @@ int rebuildTextures(b2r_context* c)
 	return B2R_OK;
 }
 
-// the direct path of the setup kernel (not with the sharded front end: its key buffers are per rank)
-bool directActive(const b2r_context* c) { return c->directMaxArea > 0 && !c->shard.bound; }
+// the direct path of the setup kernel (sharded front end: only when the arena was prepared for it)
+bool directActive(const b2r_context* c) { return c->directMaxArea > 0 && (!c->shard.bound || c->shard.direct); }
 
 // the setup kernel instantiation of a frame: fill rule, direct path
 cudaError_t launchSetup(const b2r_context* c, cudaStream_t s, b2r_context::BinSet& B, const float4* pos4, uint32_t* tileCount, uint32_t primLo, uint32_t primHi, const FrameParams& fp);
@@ -450,19 +458,20 @@ cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 g
 // the raster kernel instantiation of a frame: fill rule, fragment counter, light variant (the frame cannot reach the
 // texture / visualiser paths)
 // `blocks` = the 16x16 pixel blocks of the frame, an upper bound of the kernel's work items (CTAs behind the last item leave at once)
-cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured)
+cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool otf = false)
 {
-	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0);
+	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (otf ? 8 : 0);
 	const dim3 block(kTile * kTile);
 	const dim3 grid(blocks);
-#define B2R_RASTER_CASE(v, tl, cnt, tex) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex>, grid, block, 0, s, A, fp);
+#define B2R_RASTER_CASE(v, tl, cnt, tex) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, false>, grid, block, 0, s, A, fp); \
+	case v + 8: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, true>, grid, block, 0, s, A, fp);
 	switch (variant)
 	{
 	B2R_RASTER_CASE(0, false, false, false) B2R_RASTER_CASE(1, true, false, false)
 	B2R_RASTER_CASE(2, false, true, false)  B2R_RASTER_CASE(3, true, true, false)
 	B2R_RASTER_CASE(4, false, false, true)  B2R_RASTER_CASE(5, true, false, true)
-	B2R_RASTER_CASE(6, false, true, true)
-	default: return launchFrameKernel(c, raster_shade_kernel<true, true, true>, grid, block, 0, s, A, fp);
+	B2R_RASTER_CASE(6, false, true, true)   B2R_RASTER_CASE(7, true, true, true)
+	default: return cudaErrorInvalidValue;
 	}
 #undef B2R_RASTER_CASE
 }
@@ -476,6 +485,23 @@ cudaError_t launchSetup(const b2r_context* c, cudaStream_t s, b2r_context::BinSe
 	if (c->fillTopLeft) B2R_SETUP_CASE(true, false);
 	B2R_SETUP_CASE(false, false);
 #undef B2R_SETUP_CASE
+}
+
+// sharded front end + direct path: this rank's touched key-buffer blocks go to the tiles' owners (shard_push_keys_kernel)
+int enqueueKeyPush(b2r_context* c, b2r_context::BinSet& B, int set, cudaStream_t s)
+{
+	const b2r_context::Shard& sh = c->shard;
+	ShardKeyPush P{};
+	for (int p = 0; p < sh.n; ++p)
+	{
+		if (p == sh.self) continue;
+		P.keyInbox[p] = sh.keyInbox(sh.peerArena[p], set, sh.self);
+		P.dirtyInbox[p] = sh.dirtyInbox(sh.peerArena[p], set, sh.self);
+	}
+	const uint32_t tiles = nBins(c);
+	CU(c, launchFrameKernel(c, shard_push_keys_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, B.keys.ptr, B.dirty.ptr, P, tiles, (uint32_t)sh.self, (uint32_t)sh.n));
+	++c->kernelsLaunched;
+	return B2R_OK;
 }
 
 #define STAGE_EVENT(c, slot, i) do { if ((slot).timed) CU((c), cudaEventRecord((slot).ev[(i)], (c)->stream)); } while (0)
@@ -700,6 +726,7 @@ int enqueueFrame(b2r_context* c)
 		{
 			CU(c, launchSetup(c, fs, B, pos4, tileCount, primLo, primHi, fp));
 			++c->kernelsLaunched;
+			if (sh.bound && fp.directMaxArea) { int r = enqueueKeyPush(c, B, set, fs); if (r) return r; }
 		}
 		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, fs, B.bigList.ptr, B.counters, B.rects.ptr, tileCount, fp));
 		++c->kernelsLaunched;
@@ -725,7 +752,9 @@ int enqueueFrame(b2r_context* c)
 	{
 		{
 			// per-primitive CTAs, followed by the CTAs that scatter the cooperatively binned (big) triangles
-			const uint32_t primBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+			// (direct path: a fixed number of CTAs strides over the slots of the primitives that are binned at all)
+			const uint32_t allBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+			const uint32_t primBlocks = fp.directMaxArea ? std::max<uint32_t>(1u, std::min<uint32_t>(allBlocks, (uint32_t)c->numSMs * 4u)) : allBlocks;
 			// sharded: the ids of tiles other ranks own are mirrored into those ranks' arenas as they are scattered
 			ShardRegions R{};
 			if (sh.bound)
@@ -753,7 +782,7 @@ int enqueueFrame(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr; A.colour = c->dColourOut.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr; A.colour = c->dColourOut.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		A.keys = B.keys.ptr; A.dirty = B.dirty.ptr; c->lastDirect = fp.directMaxArea != 0u;
 		if (sh.bound) c->colourIdx = set;       // every rank writes rank 0's surface `frame & 1`
@@ -775,6 +804,7 @@ int enqueueFrame(b2r_context* c)
 				uint8_t* base = (p == sh.self) ? sh.arena : sh.peerArena[p];
 				T.tileCount[p] = sh.inboxCount(sh.arena, set, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, set, p);
 				T.binIds[p] = (p == sh.self) ? sh.binIds(sh.arena, set) : sh.region(sh.arena, set, p);
+				if (sh.direct) { T.keyInbox[p] = sh.keyInbox(sh.arena, set, p); T.dirtyInbox[p] = sh.dirtyInbox(sh.arena, set, p); }
 				pf.flags[p] = reinterpret_cast<uint32_t*>(base);
 			}
 			if (!c->shardLocalColour) A.framebuffer = sh.colourBase + (size_t)set * c->width * c->height;
@@ -789,7 +819,8 @@ int enqueueFrame(b2r_context* c)
 			// the raster kernel's work order from the merged heads: this rank's tiles, longest lists first
 			if (owned)
 			{
-				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, s, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo));
+				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, s, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo,
+					fp.directMaxArea ? (const uint8_t*)B.dirty.ptr : (const uint8_t*)nullptr));
 				++c->kernelsLaunched;
 			}
 			STAGE_EVENT(c, slot, 7);
@@ -980,6 +1011,7 @@ int enqueueFrameRing(b2r_context* c)
 		{
 			CU(c, launchSetup(c, rs, B, pos4, tileCount, primLo, primHi, fp));
 			++c->kernelsLaunched;
+			if (sh.bound && fp.directMaxArea) { int r = enqueueKeyPush(c, B, k, rs); if (r) return r; }
 		}
 		CU(c, launchFrameKernel(c, bin_big_count_kernel, dim3(c->numSMs * 4), dim3(256), 0, rs, B.bigList.ptr, B.counters, B.rects.ptr, tileCount, fp));
 		++c->kernelsLaunched;
@@ -1001,7 +1033,8 @@ int enqueueFrameRing(b2r_context* c)
 	RING_STAGE_EVENT(3);
 	if (c->nPrims)
 	{
-		const uint32_t primBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+		const uint32_t allBlocks = (primHi - primLo + 256 * kScatterPerThread - 1) / (256 * kScatterPerThread);
+		const uint32_t primBlocks = fp.directMaxArea ? std::max<uint32_t>(1u, std::min<uint32_t>(allBlocks, (uint32_t)c->numSMs * 4u)) : allBlocks;
 		ShardRegions R{};
 		if (sh.bound)
 			for (int p = 0; p < sh.n; ++p) R.region[p] = (p == sh.self) ? nullptr : sh.region(sh.peerArena[p], k, sh.self);
@@ -1021,7 +1054,7 @@ int enqueueFrameRing(b2r_context* c)
 	{
 		RasterArgs A{};
 		A.tileCount = tileCount; A.tileOffset = tileOffset; A.binIds = binIds;
-		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.ivertex = c->dIVertex.ptr; A.colour = c->dColourOut.ptr;
+		A.triRefs = c->dTriRefs.ptr; A.pos4 = pos4; A.posIn = c->dPosIn.ptr; A.ivertex = c->dIVertex.ptr; A.colour = c->dColourOut.ptr;
 		A.meshes = meshConst; A.textures = c->dTexDesc.ptr; A.frameInfo = B.frameInfo; A.tileOrder = B.tileOrder.ptr;
 		A.keys = B.keys.ptr; A.dirty = B.dirty.ptr; c->lastDirect = fp.directMaxArea != 0u;
 		// the frames of the ring alternate strictly between the two colour + depth surface pairs (sharded: every rank writes
@@ -1044,6 +1077,7 @@ int enqueueFrameRing(b2r_context* c)
 			{
 				T.tileCount[p] = sh.inboxCount(sh.arena, k, p); T.tileOffset[p] = sh.inboxOffset(sh.arena, k, p);
 				T.binIds[p] = (p == sh.self) ? sh.binIds(sh.arena, k) : sh.region(sh.arena, k, p);
+				if (sh.direct) { T.keyInbox[p] = sh.keyInbox(sh.arena, k, p); T.dirtyInbox[p] = sh.dirtyInbox(sh.arena, k, p); }
 			}
 			if (!c->shardLocalColour) A.framebuffer = sh.colourBase + (size_t)(sh.frame & 1u) * c->width * c->height;
 			// "lists ready": nobody reads the lists a peer pushed before that peer has sorted and pushed them
@@ -1057,16 +1091,9 @@ int enqueueFrameRing(b2r_context* c)
 			A.shard = T;
 			if (owned)
 			{
-				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo));
+				CU(c, launchFrameKernel(c, shard_merge_heads_kernel, dim3((owned + 255) / 256), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, B.tileOrder.ptr, B.frameInfo,
+					fp.directMaxArea ? (const uint8_t*)B.dirty.ptr : (const uint8_t*)nullptr));
 				++c->kernelsLaunched;
-				if (sliced && c->nVsChunks)
-				{
-					CU(c, launchFrameKernel(c, shard_mark_vertices_kernel, dim3((owned + 7) / 8), dim3(256), 0, rs, T, tiles, (uint32_t)sh.self, (uint32_t)sh.n, c->dTriRefs.ptr,
-						reinterpret_cast<uint8_t*>(c->dVertexMarks[k].ptr), B.frameInfo));
-					CU(c, launchFrameKernel(c, vertex_transform_marked_kernel, dim3(c->nVsChunks), dim3(kChunk), 0, rs, c->dVsChunks.ptr, meshConst, c->dPosIn.ptr, pos4,
-						reinterpret_cast<const uint8_t*>(c->dVertexMarks[k].ptr), sh.chunkLo, sh.chunkHi, B.frameInfo));
-					c->kernelsLaunched += 2;
-				}
 			}
 			RING_STAGE_EVENT(7);
 		}
@@ -1085,7 +1112,9 @@ int enqueueFrameRing(b2r_context* c)
 		}
 		if (owned)
 		{
-			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse));
+			// sliced vertex stage: this rank has transformed the vertices of its own primitive slice only - the raster kernel
+			// transforms the vertices of its list entries and of its pixels' winners itself
+			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse, sliced));
 			++c->kernelsLaunched;
 		}
 		if (sh.bound)
@@ -1805,6 +1834,9 @@ int b2r_read_bins(b2r_context* c, uint32_t* counts, uint32_t* offsets, uint32_t*
 	if (!c->haveFrame) return fail(c, B2R_E_STATE, "read_bins: nothing rendered yet");
 	CU(c, cudaSetDevice(c->device));
 	int r = validateFrame(c); if (r) return r;
+	if (c->lastDirect && c->shard.bound)
+		return fail(c, B2R_E_STATE, "read_bins: the newest frame of the sharded front end resolved its small triangles through the key buffers, so this rank's lists "
+			"hold the other triangles only; render the frame with B2R_OPT_DIRECT_MAX_AREA = 0 on every rank to read complete lists");
 	const bool rerun = c->lastDirect;
 	const int savedDirect = c->directMaxArea;
 	if (rerun)
@@ -1986,6 +2018,11 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	const size_t def = std::max<size_t>((size_t)1 << 22, (c->nPrims + count - 1) / count * 4);
 	sh.listCap = ((listCapacity ? (size_t)listCapacity : def) + 63) & ~(size_t)63;
 	sh.setBytes = ((size_t)(2 + 2 * count) * sh.tilesPad + sh.listCap * (size_t)(1 + count)) * 4;
+	// direct path across ranks: the peers push 16x16 key blocks, so the tiles must BE the key buffer's blocks
+	sh.direct = c->directMaxArea > 0 && c->binW == (uint32_t)kTile && c->binH == (uint32_t)kTile && c->binsX == (c->width + kTile - 1) / kTile;
+	sh.ownedMax = (tiles + count - 1) / count;
+	if (sh.direct) sh.setBytes += (size_t)count * (sh.ownedMax * 256 * 8 + sh.tilesPad);
+	sh.setBytes = (sh.setBytes + 255) & ~(size_t)255;
 	sh.nSets = c->ringDepth ? c->ringDepth : 2;
 	const size_t bytes = 256 + (size_t)sh.nSets * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));

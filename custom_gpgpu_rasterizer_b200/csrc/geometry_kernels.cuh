@@ -787,46 +787,45 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(
 	}
 	// kScatterPerThread primitives per thread (a CTA covers kScatterPerThread * 256 consecutive ids): the rectangle
 	// loads are issued together, so their latency is paid once; each warpBinRects call still sees one aligned
-	// group of 32 consecutive ids, which is all the run sorter assumes
-	uint2 rc[kScatterPerThread];
-	uint32_t prims[kScatterPerThread];
-	if (binSlots)
+	// group of 32 consecutive ids, which is all the run sorter assumes.
+	// Direct path: only the primitives triangle_setup_kernel left in the slots (one slot = the ids of one of its warps, in
+	// lane order - so each call still sees ascending ids of one aligned group of 32); the grid is a fixed number of CTAs
+	// that stride over the slots (their number is only known on the device, and is usually tiny).
+	const uint32_t nSlots = binSlots ? __ldg(counters + kBinSlotsWord) : 0u;
+	for (uint32_t vb = blockIdx.x; binSlots ? vb * (kScatterPerThread * 8u) < nSlots : vb == blockIdx.x; vb += primBlocks)
 	{
-		// direct path: only the primitives triangle_setup_kernel left in the slots (one slot = the ids of one of its warps, in lane
-		// order - so each warpBinRects call below still sees ascending ids of one aligned group of 32)
-		const uint32_t nSlots = __ldg(counters + kBinSlotsWord);
-		if (blockIdx.x * (kScatterPerThread * 8u) >= nSlots) return;
+		uint2 rc[kScatterPerThread];
+		uint32_t prims[kScatterPerThread];
 		#pragma unroll
 		for (int k = 0; k < kScatterPerThread; ++k)
 		{
-			const uint32_t slot = (blockIdx.x * kScatterPerThread + k) * 8u + (threadIdx.x >> 5);
-			prims[k] = slot < nSlots ? __ldg(binSlots + (size_t)slot * 32u + (threadIdx.x & 31u)) : kNoPrim;
+			if (binSlots)
+			{
+				const uint32_t slot = (vb * kScatterPerThread + k) * 8u + (threadIdx.x >> 5);
+				prims[k] = slot < nSlots ? __ldg(binSlots + (size_t)slot * 32u + (threadIdx.x & 31u)) : kNoPrim;
+			}
+			else
+			{
+				const uint32_t prim = primLo + (vb * kScatterPerThread + k) * blockDim.x + threadIdx.x;
+				prims[k] = prim < primHi ? prim : kNoPrim;
+			}
 		}
-	}
-	else
-	{
+		#pragma unroll
+		for (int k = 0; k < kScatterPerThread; ++k)
+			rc[k] = (prims[k] != kNoPrim) ? __ldg(rects + prims[k]) : make_uint2(0x0000FFFFu, 0x0000FFFFu);
 		#pragma unroll
 		for (int k = 0; k < kScatterPerThread; ++k)
 		{
-			const uint32_t prim = primLo + (blockIdx.x * kScatterPerThread + k) * blockDim.x + threadIdx.x;
-			prims[k] = prim < primHi ? prim : kNoPrim;
+			const uint32_t prim = prims[k];
+			uint32_t nTiles = 0;
+			const int bx0 = rc[k].x & 0xFFFF, by0 = rc[k].y & 0xFFFF, bx1 = (rc[k].x >> 16) & 0x7FFF, by1 = rc[k].y >> 16;
+			if (bx0 <= bx1 && by0 <= by1 && !(rc[k].x & kRectDirect))
+			{
+				nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
+				if (nTiles > fp.bigRectTiles) nTiles = 0;   // binBigBody
+			}
+			warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp, M);
 		}
-	}
-	#pragma unroll
-	for (int k = 0; k < kScatterPerThread; ++k)
-		rc[k] = (prims[k] != kNoPrim) ? __ldg(rects + prims[k]) : make_uint2(0x0000FFFFu, 0x0000FFFFu);
-	#pragma unroll
-	for (int k = 0; k < kScatterPerThread; ++k)
-	{
-		const uint32_t prim = prims[k];
-		uint32_t nTiles = 0;
-		const int bx0 = rc[k].x & 0xFFFF, by0 = rc[k].y & 0xFFFF, bx1 = (rc[k].x >> 16) & 0x7FFF, by1 = rc[k].y >> 16;
-		if (bx0 <= bx1 && by0 <= by1 && !(rc[k].x & kRectDirect))
-		{
-			nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
-			if (nTiles > fp.bigRectTiles) nTiles = 0;   // binBigBody
-		}
-		warpBinRects<true>(nTiles, bx0, bx1, by0, by1, prim, tileCursor, tileOffset, binIds, fp, M);
 	}
 }
 

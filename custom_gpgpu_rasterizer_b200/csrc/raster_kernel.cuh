@@ -25,6 +25,7 @@ struct RasterArgs
 	const uint32_t* binIds;     // (the kernel writes the lists it sorts back through these pointers)
 	const uint4* triRefs;       // static {v0, v1, v2, mesh} per primitive (global transformed-vertex indices)
 	const float4* pos4;
+	const float4* posIn;        // model-space positions (x, y, z, 1) of the IVertex records: the OTF instantiation transforms what it needs itself
 	const float2* ivertex;      // resident IVertex records (7 float2 each)
 	const float4* colour;       // the records' vertex colours, indexed like pos4 (build_colour_stream_kernel)
 	const MeshConst* meshes;
@@ -267,35 +268,49 @@ __global__ void __launch_bounds__(kChunk, DIRECT ? B2R_SETUP_DIRECT_CTAS : 1) tr
 	warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
 	if (!DIRECT) return;
 
-	// ---- phase B: the recorded triangles, one per thread
+	// ---- phase B: the recorded triangles.  A CTA's 256 primitives leave only a few dozen records (culled, off-pixel and
+	// binned ones are gone), so each record is shared by k = 256 / records neighbouring threads that take every k-th
+	// candidate pixel: all warps of the CTA stay busy and the trip counts inside a warp are even.
 	__syncthreads();
 	uint32_t nFrags = 0;
-	if (threadIdx.x < sRecCount)
+	const uint32_t nRec = sRecCount;
+	const uint32_t share = nRec ? (uint32_t)kChunk / nRec : 1u;          // >= 1 (nRec <= kChunk)
+	const uint32_t recIdx = threadIdx.x / share, first = threadIdx.x - recIdx * share;
+	if (recIdx < nRec)
 	{
-		const DirectRecord& q = sRec[threadIdx.x];
-		TriShared t;
-		t.x0 = q.x0; t.y0 = q.y0; t.x1 = q.x1; t.y1 = q.y1; t.x2 = q.x2; t.y2 = q.y2;
-		t.z0 = q.z0; t.z1 = q.z1; t.z2 = q.z2; t.area = q.area; t.rcpArea = q.rcpArea; t.divLo = q.divLo;
-		t.eAx = q.x1 - q.x0; t.eAy = q.y1 - q.y0;      // the subtractions of expandRecord: same bits as in the raster kernel
-		t.eBx = q.x2 - q.x1; t.eBy = q.y2 - q.y1;
-		t.eCx = q.x0 - q.x2; t.eCy = q.y0 - q.y2;
-		t.prim = q.prim; t.zLow = 0; t.yExtent = 0;
+		const DirectRecord& q = sRec[recIdx];
 		const int x0 = (int)(q.boxX & 0xFFFFu), x1 = (int)(q.boxX >> 16), y0 = (int)(q.boxY & 0xFFFFu), y1 = (int)(q.boxY >> 16);
-		const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
-		const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
-		for (int y = y0; y < y1; ++y)
-			for (int x = x0; x < x1; ++x)
+		const uint32_t w = (uint32_t)(x1 - x0), area = w * (uint32_t)(y1 - y0);
+		if (first < area)
+		{
+			TriShared t;
+			t.x0 = q.x0; t.y0 = q.y0; t.x1 = q.x1; t.y1 = q.y1; t.x2 = q.x2; t.y2 = q.y2;
+			t.z0 = q.z0; t.z1 = q.z1; t.z2 = q.z2; t.area = q.area; t.rcpArea = q.rcpArea; t.divLo = q.divLo;
+			t.eAx = q.x1 - q.x0; t.eAy = q.y1 - q.y0;      // the subtractions of expandRecord: same bits as in the raster kernel
+			t.eBx = q.x2 - q.x1; t.eBy = q.y2 - q.y1;
+			t.eCx = q.x0 - q.x2; t.eCy = q.y0 - q.y2;
+			t.prim = q.prim; t.zLow = 0; t.yExtent = 0;
+			const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+			const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
+			const uint32_t row = first / w;
+			int y = y0 + (int)row, x = x0 + (int)(first - row * w);
+			for (uint32_t i = first; i < area; i += share)
 			{
 				Bary bc; int zi;
 				if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
 				{
 					const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
-					if (replicated && tile % fp.ownerCount != fp.ownerRank) continue;
-					atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | t.prim);
-					dirty[tile] = 1;
-					++nFrags;
+					if (!replicated || tile % fp.ownerCount == fp.ownerRank)
+					{
+						atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | t.prim);
+						dirty[tile] = 1;
+						++nFrags;
+					}
 				}
+				x += (int)share;
+				while (x >= x1) { x -= (int)w; ++y; }
 			}
+		}
 	}
 	if (fp.countFragments)
 	{
@@ -487,7 +502,29 @@ __device__ B2R_NOINLINE void sortStagedListFallback(const RasterArgs& A, const W
 // worst case (one item per block); the CTAs behind the last item leave at once.
 // Lists of up to kStage entries are staged in shared memory; warp 0 then puts the staged list into canonical order
 // (and stores it) while warps 1..7 already sweep it - the sweep does not depend on the order.
-template <bool TOPLEFT, bool COUNT, bool TEXTURED>
+// the three transformed positions of a primitive.  OTF (sharded front end with a sliced vertex stage: a rank has transformed
+// only the vertices of its own primitive slice): from the resident model-space positions with the vertex stage's own
+// function - same bits as the stream vertex_transform_kernel writes.
+template <bool OTF>
+__device__ __forceinline__ void fetchPositions(const RasterArgs& A, const uint4& tr, float4& p0, float4& p1, float4& p2)
+{
+	if (OTF)
+	{
+		const MeshConst& mc = A.meshes[tr.w];
+		const uint32_t d = mc.vtxInBase - mc.vtxOutBase;     // transformed-stream index -> IVertex record (mod 2^32)
+		const float4 a = __ldg(A.posIn + (tr.x + d)), b = __ldg(A.posIn + (tr.y + d)), c = __ldg(A.posIn + (tr.z + d));
+		float m[16];
+		#pragma unroll
+		for (int i = 0; i < 16; ++i) m[i] = __ldg(&mc.wvp[i]);
+		p0 = transformPosition(m, a.x, a.y, a.z); p1 = transformPosition(m, b.x, b.y, b.z); p2 = transformPosition(m, c.x, c.y, c.z);
+	}
+	else
+	{
+		p0 = __ldg(A.pos4 + tr.x); p1 = __ldg(A.pos4 + tr.y); p2 = __ldg(A.pos4 + tr.z);
+	}
+}
+
+template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF>
 __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
 {
 	pdlPrologue();
@@ -589,7 +626,8 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 			// rebuild the screen-space triangle from the static reference + the transformed positions
 			// (same code, hence the same bits, wherever a triangle is expanded)
 			const uint4 tr = __ldg(A.triRefs + prim);
-			const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
+			float4 p0, p1, p2;
+			fetchPositions<OTF>(A, tr, p0, p1, p2);
 			TriRecord r;
 			rasterConstants(screenMap(p0, p1, p2, fp, r), fp, r);
 			// candidate pixels = the record's conservative box clipped to this CTA's block; the box
@@ -754,14 +792,29 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 		if (desc.w)
 		{
 			// direct path: the fragments the setup kernel resolved for this block's pixels; the key buffer is left empty for
-			// the next frame that uses it
-			if (live)
+			// the next frame that uses it.  Sharded front end: desc.w is a mask of ranks - this rank's own key buffer, and the
+			// blocks the peers pushed into the inbox (16x16 bins: one 256-key block per owned tile)
+			const bool own = !shard || ((desc.w >> fp.ownerRank) & 1u);
+			if (own)
 			{
-				unsigned long long* kp = A.keys + keyIndex(fp.keyBlocksX, px, py);
-				const unsigned long long k = *kp;
-				if (k != kEmptyKey) { *kp = kEmptyKey; best = min(best, k); }
+				if (live)
+				{
+					unsigned long long* kp = A.keys + keyIndex(fp.keyBlocksX, px, py);
+					const unsigned long long k = *kp;
+					if (k != kEmptyKey) { *kp = kEmptyKey; best = min(best, k); }
+				}
+				if (tid == 0 && sub == 0) A.dirty[bin] = 0;
 			}
-			if (tid == 0 && sub == 0) A.dirty[bin] = 0;
+			if (shard)
+			{
+				const size_t slot = ((size_t)(bin / fp.ownerCount) << 8) + (size_t)tid;
+				for (uint32_t p = 0; p < fp.ownerCount; ++p)
+					if (p != fp.ownerRank && ((desc.w >> p) & 1u))
+					{
+						best = min(best, A.shard.keyInbox[p][slot]);
+						if (tid == 0) A.shard.dirtyInbox[p][bin] = 0;
+					}
+			}
 		}
 		if (!live) return;
 
@@ -782,7 +835,8 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 			prim = (uint32_t)best;
 			depthOut = (int)(uint32_t)(best >> 32);
 			const uint4 tr = __ldg(A.triRefs + prim);
-			const float4 p0 = __ldg(A.pos4 + tr.x), p1 = __ldg(A.pos4 + tr.y), p2 = __ldg(A.pos4 + tr.z);
+			float4 p0, p1, p2;
+			fetchPositions<OTF>(A, tr, p0, p1, p2);
 			TriShared t;
 			{
 				TriRecord r;
@@ -858,22 +912,56 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) rast
 	}
 }
 
+// Sharded front end + direct path.  Every rank resolves the small triangles of ITS primitive slice into its own key
+// buffer (triangle_setup_kernel), for the whole screen; this kernel then hands the touched blocks to the ranks that own
+// the tiles: one warp per tile, a 2 KB block (16x16 keys) travels as 16-byte posted NVLink stores into slot `self` of
+// the owner's key inbox, followed by the tile's byte in the owner's map; the local block is reset on the way, so the
+// key buffer is empty again for the frame that uses it next.  Blocks of tiles owned here stay where they are (the
+// raster kernel merges them like on a single GPU).  A frame of sub-pixel triangles exchanges a few MB per rank
+// instead of bin lists.  Needs 16x16 bins on the key buffer's block grid (tile index = block index).
+__global__ void __launch_bounds__(256) shard_push_keys_kernel(unsigned long long* __restrict__ keys, uint8_t* __restrict__ dirty,
+	const __grid_constant__ ShardKeyPush P, uint32_t nTiles, uint32_t self, uint32_t nRanks)
+{
+	pdlPrologue();
+	const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+	if (tile >= nTiles) return;
+	const uint32_t owner = tile % nRanks;
+	if (owner == self || dirty[tile] == 0) return;
+	uint4* src = reinterpret_cast<uint4*>(keys + ((size_t)tile << 8));
+	uint4* dst = reinterpret_cast<uint4*>(P.keyInbox[owner] + ((size_t)(tile / nRanks) << 8));
+	const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+	#pragma unroll
+	for (uint32_t i = 0; i < 4; ++i)
+	{
+		const uint4 v = src[i * 32u + lane];
+		dst[i * 32u + lane] = v;
+		src[i * 32u + lane] = empty;
+	}
+	__syncwarp();
+	if (lane == 0) { P.dirtyInbox[owner][tile] = 1; dirty[tile] = 0; }
+}
+
 // Sharded front end, after the "lists ready" barrier: the work order of this rank's raster kernel.  The length of a
 // tile's list is the sum of the heads the ranks pushed for it; the owned tiles are grouped into the same length
 // classes tile_scan_kernel uses on a single GPU (longest first), entries {tile, merged length, 0, 0}.  Also raises the
 // overflow flag if any rank's list buffer was too small (its marker word rides behind its offsets).
 __global__ void __launch_bounds__(256) shard_merge_heads_kernel(const __grid_constant__ ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
-	uint4* __restrict__ tileOrder, unsigned long long* __restrict__ frameInfo)
+	uint4* __restrict__ tileOrder, unsigned long long* __restrict__ frameInfo, const uint8_t* __restrict__ dirty /*direct path: this rank's own map, or null*/)
 {
 	pdlPrologue();
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
 	const uint32_t tile = rank + k * nRanks;
 	if (k < nRanks && __ldg(T.tileOffset[k] + nTiles) == 0xFFFFFFFFu) frameInfo[1] = 1ull;
-	uint32_t n = 0, cls = kTileClasses;
+	uint32_t n = 0, cls = kTileClasses, keyMask = 0;
 	if (tile < nTiles)
 	{
 		for (uint32_t p = 0; p < nRanks; ++p) n += __ldg(T.tileCount[p] + tile);
-		cls = tileClass(n);
+		// direct path: which ranks hold fragments of this tile in a key buffer (bit p: rank p's block in the inbox; bit
+		// `rank`: this rank's own key buffer).  Plain loads: the peers' bytes arrived before the "lists ready" barrier.
+		if (dirty)
+			for (uint32_t p = 0; p < nRanks; ++p)
+				if ((p == rank ? dirty[tile] : T.dirtyInbox[p][tile]) != 0) keyMask |= 1u << p;
+		cls = (n == 0u && keyMask) ? kTileClasses - 2u : tileClass(n);
 	}
 	#pragma unroll
 	for (uint32_t c = 0; c < kTileClasses; ++c)
@@ -883,7 +971,7 @@ __global__ void __launch_bounds__(256) shard_merge_heads_kernel(const __grid_con
 		uint32_t base = 0;
 		if (lane == 0) base = (uint32_t)atomicAdd(&frameInfo[kInfoClassBase + c], (unsigned long long)__popc(m));
 		base = __shfl_sync(0xFFFFFFFFu, base, 0);
-		if (cls == c) tileOrder[(size_t)c * nTiles + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = make_uint4(tile, n, 0u, 0u);
+		if (cls == c) tileOrder[(size_t)c * nTiles + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = make_uint4(tile, n, 0u, keyMask);
 	}
 }
 

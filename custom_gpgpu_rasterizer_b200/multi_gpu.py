@@ -15,7 +15,8 @@ each rank's share of the final colours, W*H*4*(world-1)/world bytes per frame:
 * class ShardedSortFirst (b2r_shard_*): the geometry front end is divided as well - rank r sets up, bins
   and sorts the r-th contiguous slice of the primitives into the lists of ALL tiles; a tile's owner walks
   the ranks' lists in rank order over NVLink and every rank stores its colours straight into rank 0's
-  surface.  No collective on the data path: two flag barriers per frame inside b2r_render.
+  surface.  Small triangles (direct path, B2R_OPT_DIRECT_MAX_AREA) are resolved by the rank that set them up into its own
+  key buffer; the touched 16x16 key blocks go to the tiles' owners instead of list entries.  No collective on the data path: two flag barriers per frame inside b2r_render.
 
 The pure index helpers below are shared with the CPU (gloo) tests.
 """
@@ -99,9 +100,10 @@ def prim_slice(n_prims: int, rank: int, world: int, block: int = 256):
 
 
 def check_shard_modes(modes) -> None:
-    """Every rank of a sharded group must run the same frame-ring depth and vertex-stage mode."""
+    """Every rank of a sharded group must run the same frame-ring depth, vertex-stage mode and direct-path switch (the
+    layout of the shared arena depends on them)."""
     if any(m != modes[0] for m in modes):
-        raise RuntimeError(f"ranks disagree on (B2R_OPT_FRAME_RING, B2R_OPT_SHARD_SLICED_VERTEX): {list(modes)}")
+        raise RuntimeError(f"ranks disagree on (B2R_OPT_FRAME_RING, B2R_OPT_SHARD_SLICED_VERTEX, B2R_OPT_DIRECT_MAX_AREA > 0): {list(modes)}")
 
 
 class ShardedSortFirst:
@@ -118,7 +120,7 @@ class ShardedSortFirst:
         renderer._check(_lib.lib.b2r_shard_prepare(renderer.handle, rank, world, list_capacity, arena, colour))
         handles: List[Optional[tuple]] = [None] * world
         # the layout of the shared arena depends on the frame-ring depth, the raster kernel on the sliced vertex stage
-        mode = (renderer.get_option(_lib.OPT_FRAME_RING), renderer.get_option(_lib.OPT_SHARD_SLICED_VERTEX))
+        mode = (renderer.get_option(_lib.OPT_FRAME_RING), renderer.get_option(_lib.OPT_SHARD_SLICED_VERTEX), int(renderer.get_option(_lib.OPT_DIRECT_MAX_AREA) > 0))
         dist.all_gather_object(handles, (bytes(arena), bytes(colour), mode))
         check_shard_modes([h[2] for h in handles])
         all_arenas = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(h[0] for h in handles))

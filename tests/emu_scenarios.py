@@ -194,6 +194,8 @@ def sharded(world, mode, n_meshes=2, n_tris=700):
     lib = _lib.lib
     if os.environ.get("B2R_EMU_SCENE") == "hostile":      # triangles through the camera plane, w = 0, NaN / inf / huge coordinates, degenerate ones
         sc = scenes.hostile_scene(160, 112, 400, seed=43, textured=True)
+    elif os.environ.get("B2R_EMU_SCENE") == "tiny":       # mostly triangles of a few pixels (the direct path: key-buffer blocks pushed to the owners) among larger ones
+        sc = scenes.random_triangles_scene(160, 112, n_tris * 3, seed=31, cull=2, textured=True, n_meshes=n_meshes, sample=1, size=0.12)
     else:
         sc = scenes.random_triangles_scene(160, 112, n_tris, seed=29, cull=2, textured=True, n_meshes=n_meshes, sample=1)
     cams = [dataclasses.replace(sc, cam_pos=(0.15 * i - 0.5, 0.05 * i, 3.0 + 0.1 * i)) for i in range(7)]
@@ -224,8 +226,20 @@ def sharded(world, mode, n_meshes=2, n_tris=700):
     ranks[0].present_wait()
     res = {"frames": [bool(np.array_equal(h, o["framebuffer"])) for h, o in zip(host, wants)]}
     res["last_framebuffer"] = bool(np.array_equal(ranks[0].framebuffer(), wants[-1]["framebuffer"]))
-    # the ranks' lists of the newest frame concatenate, in rank order, to the single-GPU lists (= the oracle's sets, ascending)
+    res["visible_direct"] = int(sum(r.stats()[1] for r in ranks)) == int(wants[-1]["visible_tris"])
+    res["pairs_direct"] = int(sum(r.counters()["pairs"] for r in ranks)) == int(wants[-1]["bin_counts"].sum())
+    # the ranks' lists of the newest frame concatenate, in rank order, to the single-GPU lists (= the oracle's sets, ascending).
+    # Complete lists need the direct path off (it hands small triangles to the owners as key-buffer blocks, not as list
+    # entries): the newest frame once more, every triangle binned, on every rank
+    direct = ranks[0].get_option(_lib.OPT_DIRECT_MAX_AREA)
+    for r in ranks:
+        r.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)
+    for r in ranks:
+        r.render_scene(cams[-1], sync=False)
+    res["last_framebuffer_binned"] = bool(np.array_equal(ranks[0].framebuffer(), wants[-1]["framebuffer"]))
     per_rank = [r.bin_lists() for r in ranks]
+    for r in ranks:
+        r.set_option(_lib.OPT_DIRECT_MAX_AREA, direct)
     n_bins = len(per_rank[0][0])
     cat = []
     for b in range(n_bins):

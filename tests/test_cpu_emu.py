@@ -106,6 +106,17 @@ def test_sharded_front_end_composes_the_right_frames(emu_env, world, mode, meshe
     assert res["distributed_present"] and res["band_present"] and res["composed_on_rank0_again"], res
 
 
+@pytest.mark.parametrize("world,mode,meshes,tris", [(4, "ring4sliced", 2, 400)] + ([(2, "default", 2, 500), (8, "ring3", 3, 500), (3, "serial", 1, 400)] if SLOW else []))
+def test_sharded_front_end_with_small_triangles_through_the_key_buffers(emu_env, world, mode, meshes, tris):
+    """A scene of mostly few-pixel triangles: the ranks resolve them into their own key buffers (direct path) and push the
+    touched 16x16 key blocks to the tile owners; with the sliced vertex stage the raster kernel transforms the winners'
+    vertices itself.  Every composed frame equals the oracle's; the statistics add up across the ranks."""
+    res = run(dict(emu_env, B2R_TRACE_DEVICES=str(world), B2R_EMU_SCENE="tiny"), "sharded", str(world), mode, str(meshes), str(tris))
+    assert all(res["frames"]) and len(res["frames"]) == 7, res
+    assert res["last_framebuffer"] and res["last_framebuffer_binned"] and res["lists"] and res["visible"] and res["visible_direct"] and res["pairs_direct"], res
+    assert res["distributed_present"] and res["band_present"] and res["composed_on_rank0_again"], res
+
+
 @pytest.mark.skipif(not SLOW, reason="other stream visiting orders of the emulated executor (set B2R_SLOW_TESTS=1)")
 @pytest.mark.parametrize("order", ["asc", "random:3", "random:11"])
 @pytest.mark.parametrize("mode", ["default", "ring3"])

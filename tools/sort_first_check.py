@@ -44,15 +44,31 @@ for sc in test_scenes:
     dist.barrier()
     torch.cuda.synchronize()
     lists = None
+    got = r.framebuffer() if rank == 0 else None
     if mode == "sharded":
-        # the per-tile concatenation of the ranks' lists, in rank order, must be the single-GPU list
+        # the per-tile concatenation of the ranks' lists, in rank order, must be the single-GPU list.  With the direct path
+        # the small triangles reach the tile owners as key-buffer blocks, not as list entries: complete lists come from
+        # the same frame rendered once more with every triangle binned, on every rank (the composed frame is compared too)
+        direct = r.get_option(_lib.OPT_DIRECT_MAX_AREA)
+        if direct:
+            r.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)
+            r.render(cam, sc.cull, sc.sample, sc.vis, sync=False)
+            g.run()
+            r.sync()
+            dist.barrier()
+            torch.cuda.synchronize()
+            if rank == 0 and not np.array_equal(r.framebuffer(), got):
+                print(f"sort-first[{mode}] world={world} {sc.name}: DIFFERENT frames with / without the direct path")
+                ok = False
         counts, offsets, ids = r.bin_lists()
+        if direct:
+            r.set_option(_lib.OPT_DIRECT_MAX_AREA, direct)
         lists = [None] * world
         dist.all_gather_object(lists, (counts, offsets, ids))
     if rank == 0:
-        got = r.framebuffer()
         full = Renderer(sc.width, sc.height, device=local)
         full.set_option(_lib.OPT_FRAME_RING, 0)          # the single-GPU frame of record: serial-capable default scheduler, whatever the environment selects
+        full.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)     # ... with every triangle binned
         full.load_scene(sc)
         full.render(cam, sc.cull, sc.sample, sc.vis)
         want = full.framebuffer()
