@@ -476,14 +476,32 @@ cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, 
 #undef B2R_RASTER_CASE
 }
 
+// persistent grid of the setup kernel: as many CTAs as are resident at once (each strides over the 256-primitive chunks)
+template <typename K>
+uint32_t setupGrid(const b2r_context* c, K kernel, uint32_t prims, int& cached)
+{
+	if (cached < 1)
+	{
+		int n = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kChunk, 0) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = B2R_SETUP_CTAS; }
+		cached = n;
+	}
+	uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c->numSMs * (uint32_t)cached, (prims + kChunk - 1) / kChunk));
+	// testing aid: a smaller grid makes every CTA walk several chunks (the copy pipeline's steady state) on small scenes too
+	static const int forced = [] { const char* e = getenv("B2R_SETUP_GRID"); return e ? atoi(e) : 0; }();
+	if (forced > 0) grid = std::min<uint32_t>(grid, (uint32_t)forced);
+	return grid;
+}
+
 cudaError_t launchSetup(const b2r_context* c, cudaStream_t s, b2r_context::BinSet& B, const float4* pos4, uint32_t* tileCount, uint32_t primLo, uint32_t primHi, const FrameParams& fp)
 {
-	const dim3 grid((primHi - primLo + kChunk - 1) / kChunk), block(kChunk);
-#define B2R_SETUP_CASE(tl, direct) return launchFrameKernel(c, triangle_setup_kernel<tl, direct>, grid, block, 0, s, (const uint4*)c->dTriRefs.ptr, pos4, B.rects.ptr, \
-		tileCount, B.bigList.ptr, B.counters, B.binSlots.ptr, B.keys.ptr, B.dirty.ptr, B.frameInfo, primLo, primHi, fp)
-	if (fp.directMaxArea) { if (c->fillTopLeft) B2R_SETUP_CASE(true, true); B2R_SETUP_CASE(false, true); }
-	if (c->fillTopLeft) B2R_SETUP_CASE(true, false);
-	B2R_SETUP_CASE(false, false);
+	static thread_local int occ[4] = { 0, 0, 0, 0 };      // resident CTAs per SM of the four instantiations (a property of the binary)
+	const dim3 block(kChunk);
+#define B2R_SETUP_CASE(i, tl, direct) return launchFrameKernel(c, triangle_setup_kernel<tl, direct>, dim3(setupGrid(c, triangle_setup_kernel<tl, direct>, primHi - primLo, occ[i])), block, 0, s, \
+		(const uint4*)c->dTriRefs.ptr, pos4, B.rects.ptr, tileCount, B.bigList.ptr, B.counters, B.binSlots.ptr, B.keys.ptr, B.dirty.ptr, B.frameInfo, primLo, primHi, fp)
+	if (fp.directMaxArea) { if (c->fillTopLeft) B2R_SETUP_CASE(0, true, true); B2R_SETUP_CASE(1, false, true); }
+	if (c->fillTopLeft) B2R_SETUP_CASE(2, true, false);
+	B2R_SETUP_CASE(3, false, false);
 #undef B2R_SETUP_CASE
 }
 

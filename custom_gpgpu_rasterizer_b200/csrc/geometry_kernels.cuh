@@ -476,6 +476,12 @@ __device__ __forceinline__ ScreenBounds screenMap(const float4& p0, const float4
 	return b;
 }
 
+// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn): the smallest weight that takes it
+__device__ __forceinline__ float divisionThreshold(float area)
+{
+	return (area >= kDivLo && area <= kDivHi) ? fmaxf(kDivLo, area * 5.42101086e-20f) : __int_as_float(0x7F800000);
+}
+
 // the per-triangle constants of the raster kernel's fragment test (area, candidate box, hoisted
 // reciprocal, conservative depth bound).  Evaluated by the raster kernel for every list entry.
 __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const FrameParams& fp, TriRecord& r)
@@ -511,8 +517,7 @@ __device__ __forceinline__ void rasterConstants(const ScreenBounds& b, const Fra
 	}
 	r.cbX = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
 	r.cbY = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
-	// hoisted division only for quotients in [2^-64, ~1] with a sane divisor (else __fdiv_rn) ...
-	r.divLo = (r.area >= kDivLo && r.area <= kDivHi) ? fmaxf(kDivLo, r.area * 5.42101086e-20f) : __int_as_float(0x7F800000);
+	r.divLo = divisionThreshold(r.area);
 	// ... and a conservative lower bound of the integer depth.  The computed weights of a produced fragment are
 	// >= 0 and, for a well-conditioned triangle, sum to 1 within k (= 2^-18 D^2 / area < 1/2, the relative error
 	// of the edge functions and of the area), so z >= min(z_i) * (1 - k) for min(z_i) > 0.  A needle / degenerate

@@ -117,25 +117,28 @@ __device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, 
 // On a scene of sub-pixel triangles this removes the bin lists altogether; the 66 MB key buffer of a 4K frame lives
 // in B200's 126 MB L2.
 //
-// The direct path runs in two phases inside the CTA, with a stream compaction through shared memory in between.  Phase
-// A is the setup proper, one thread per primitive: two dependent memory round trips (vertex reference -> three
-// positions), cull, rectangle, candidate box; a small triangle that has candidate pixels leaves a 64-byte record in
-// shared memory.  Phase B takes the records one per thread - the culled, off-pixel and binned primitives are gone, so
-// its warps are full - and walks the candidate pixels.  The two phases do not share registers (the fused
-// one-primitive-per-thread form needed 64-80 and idled on the round trips: ncu issue slots 46 % busy), so five CTAs
-// are resident per SM and the arithmetic of one hides the round trips of the others.
-#ifndef B2R_SETUP_DIRECT_CTAS
-#define B2R_SETUP_DIRECT_CTAS 5
+// Structure.  A primitive costs two DEPENDENT memory round trips (vertex reference -> three positions) before a few
+// hundred instructions of arithmetic, and a one-primitive-per-thread kernel idles on them (ncu: 28-45 % of the warp
+// samples wait for the positions, issue slots ~50 % busy, whatever the occupancy).  So the kernel is persistent - a CTA
+// strides over chunks of 256 primitives - and every thread runs a three-stage pipeline of asynchronous copies
+// (cp.async, global -> shared without passing through registers): while the CTA works on chunk i, the positions of chunk
+// i+1 and the vertex references of chunk i+2 are in flight.  A thread only ever reads back what it copied itself, so the
+// pipeline needs no barrier.
+// The direct path then runs in two phases with a stream compaction through shared memory in between.  Phase A is the
+// setup proper, one thread per primitive: cull, rectangle, candidate box; a small triangle that has candidate pixels
+// leaves a 48-byte record in shared memory.  Phase B shares each record between k = 256 / records neighbouring threads
+// that take every k-th candidate pixel - the culled, off-pixel and binned primitives are gone, all warps stay busy.
+#ifndef B2R_SETUP_CTAS
+#define B2R_SETUP_CTAS 5
 #endif
 struct __align__(16) DirectRecord
 {
 	float x0, y0, x1, y1;
 	float x2, y2, z0, z1;
-	float z2, area, rcpArea, divLo;
-	uint32_t prim, boxX /*x0 | x1 << 16*/, boxY /*y0 | y1 << 16*/, pad;
+	float z2; uint32_t prim, boxX /*x0 | x1 << 16*/, boxY /*y0 | y1 << 16*/;
 };
 template <bool TOPLEFT, bool DIRECT>
-__global__ void __launch_bounds__(kChunk, DIRECT ? B2R_SETUP_DIRECT_CTAS : 1) triangle_setup_kernel(
+__global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 	const uint4* __restrict__ triRefs, const float4* __restrict__ pos4, uint2* __restrict__ rects,
 	uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint32_t* __restrict__ counters /*[0]=visible,[1]=nBig,[2]=slots*/,
 	uint32_t* __restrict__ binSlots /*DIRECT: the primitives bin_scatter_kernel has to visit, one 32-entry slot per warp that has any*/,
@@ -143,176 +146,228 @@ __global__ void __launch_bounds__(kChunk, DIRECT ? B2R_SETUP_DIRECT_CTAS : 1) tr
 	uint32_t primLo, uint32_t primHi, const __grid_constant__ FrameParams fp)
 {
 	pdlPrologue();
-	__shared__ DirectRecord sRec[DIRECT ? kChunk : 1];
-	__shared__ uint32_t sRecCount;
-	if (DIRECT && threadIdx.x == 0) sRecCount = 0;
+	__shared__ __align__(16) uint4 sRef[2][kChunk];              // vertex references of chunks i+1 / i+2
+	__shared__ __align__(16) float4 sPos[2][3][kChunk];          // positions of chunks i / i+1
+	__shared__ __align__(16) DirectRecord sRec[DIRECT ? kChunk : 1];
+	__shared__ uint32_t sRecCount[2];                            // records of the current chunk / being reset for the next
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	const uint32_t nChunks = (primHi - primLo + kChunk - 1) / kChunk;
+	if (blockIdx.x >= nChunks) return;
+	auto primOf = [&](uint32_t chunk) { return primLo + chunk * kChunk + tid; };
+	// pipeline fill (the step is gridDim.x chunks, and a chunk's buffers are chosen by the parity of its POSITION in this
+	// CTA's sequence, not of its index)
+	const uint32_t step = gridDim.x;
+	if (DIRECT && tid < 2) sRecCount[tid] = 0;
 	if (DIRECT) __syncthreads();
-	const uint32_t lane = threadIdx.x & 31u;
-	bool visible = false;
-	const uint32_t prim = primLo + blockIdx.x * kChunk + threadIdx.x;
-	int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
-	uint32_t nTiles = 0, directTiles = 0;
-	bool record = false;
-	DirectRecord rec;
-	if (prim < primHi)
 	{
-		const uint4 tr = __ldcs(triRefs + prim);
-		const float4 p0 = __ldg(pos4 + tr.x), p1 = __ldg(pos4 + tr.y), p2 = __ldg(pos4 + tr.z);
-		visible = true;
-		if (fp.cullMode != 2u)
+		const uint32_t c0 = blockIdx.x;
+		if (primOf(c0) < primHi) cpAsync16(&sRef[0][tid], triRefs + primOf(c0));
+		cpAsyncCommit(); cpAsyncWaitAll();
+		if (primOf(c0) < primHi)
 		{
-			const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
-			const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
-			float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
-			normalize3(nx, ny, nz);
-			// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
-			const float d = (fp.cullMode == 0u)
-				? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
-				: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
-			if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
+			const uint4 tr = sRef[0][tid];
+			cpAsync16(&sPos[0][0][tid], pos4 + tr.x); cpAsync16(&sPos[0][1][tid], pos4 + tr.y); cpAsync16(&sPos[0][2][tid], pos4 + tr.z);
 		}
-		if (visible)
+		if (c0 + step < nChunks && primOf(c0 + step) < primHi) cpAsync16(&sRef[1][tid], triRefs + primOf(c0 + step));
+		cpAsyncCommit();
+	}
+	uint32_t nFrags = 0;
+	uint32_t it = 0;
+	for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += step, ++it)
+	{
+		const uint32_t cur = it & 1u, nxt = cur ^ 1u;
+		// positions of this chunk and references of the next have landed (requested one whole iteration ago)
+		cpAsyncWaitAll();
+		// request: positions of the next chunk, references of the one after (into the buffers this iteration does not read)
 		{
-			const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
-			const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
-			const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
-			visible = !(xOut || yOut || zOut);
-		}
-		if (visible)
-		{
-			TriRecord r;
-			const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
-			const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
-			const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
-			const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
-			const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
-			// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
-			const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
-			bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
-			by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
-			bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
-			by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
-			if (bx0 <= bx1 && by0 <= by1)
+			const uint32_t c1 = chunk + step, c2 = chunk + 2u * step;
+			float4 keep0, keep1, keep2;
+			const uint32_t prim0 = primOf(chunk);
+			// (this chunk's positions are read into registers first: sRef[cur] is about to be overwritten, sPos[cur] is not)
+			keep0 = sPos[cur][0][tid]; keep1 = sPos[cur][1][tid]; keep2 = sPos[cur][2][tid];
+			if (c1 < nChunks && primOf(c1) < primHi)
 			{
-				nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
-				if (DIRECT)
+				const uint4 tr = sRef[nxt][tid];
+				cpAsync16(&sPos[nxt][0][tid], pos4 + tr.x); cpAsync16(&sPos[nxt][1][tid], pos4 + tr.y); cpAsync16(&sPos[nxt][2][tid], pos4 + tr.z);
+			}
+			if (c2 < nChunks && primOf(c2) < primHi) cpAsync16(&sRef[cur][tid], triRefs + primOf(c2));
+			cpAsyncCommit();
+
+			// ---- phase A: setup of primitive prim0
+			const float4 p0 = keep0, p1 = keep1, p2 = keep2;
+			const uint32_t prim = prim0;
+			bool visible = false;
+			int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+			uint32_t nTiles = 0, directTiles = 0;
+			bool record = false;
+			DirectRecord rec;
+			if (prim < primHi)
+			{
+				visible = true;
+				if (fp.cullMode != 2u)
 				{
-					rasterConstants(b, fp, r);
-					// candidate pixels: the candidate box inside the bins of the rectangle (the box is already clamped to the screen)
-					const int x0 = max((int)(r.cbX & 0xFFFFu), bx0 * (int)fp.binW), x1 = min((int)(r.cbX >> 16), (bx1 + 1) * (int)fp.binW);
-					const int y0 = max((int)(r.cbY & 0xFFFFu), by0 * (int)fp.binH), y1 = min((int)(r.cbY >> 16), (by1 + 1) * (int)fp.binH);
-					const uint32_t area = (x1 > x0 && y1 > y0) ? (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) : 0u;
-					if (area <= fp.directMaxArea)
+					const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
+					const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
+					float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
+					normalize3(nx, ny, nz);
+					// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
+					const float d = (fp.cullMode == 0u)
+						? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
+						: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
+					if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
+				}
+				if (visible)
+				{
+					const bool xOut = (p0.x < -1.f && p1.x < -1.f && p2.x < -1.f) || (p0.x > 1.f && p1.x > 1.f && p2.x > 1.f);
+					const bool yOut = (p0.y < -1.f && p1.y < -1.f && p2.y < -1.f) || (p0.y > 1.f && p1.y > 1.f && p2.y > 1.f);
+					const bool zOut = (p0.z < 0.f && p1.z < 0.f && p2.z < 0.f) || (p0.z > 1.f && p1.z > 1.f && p2.z > 1.f);
+					visible = !(xOut || yOut || zOut);
+				}
+				if (visible)
+				{
+					TriRecord r;
+					const ScreenBounds b = screenMap(p0, p1, p2, fp, r);
+					const int xMin = bboxCoord(b.minx, -1, (int)fp.width);
+					const int yMin = bboxCoord(b.miny, -1, (int)fp.height);
+					const int xMax = bboxCoord(b.maxx, +1, (int)fp.width);
+					const int yMax = bboxCoord(b.maxy, +1, (int)fp.height);
+					// C integer division of the non-negative shorts (CUDARenderer.cu:935-942); a shift for power-of-two bins
+					const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+					bx0 = clampi(px ? xMin >> fp.binShiftX : xMin / (int)fp.binW, 0, (int)fp.binsX);
+					by0 = clampi(py ? yMin >> fp.binShiftY : yMin / (int)fp.binH, 0, (int)fp.binsY);
+					bx1 = clampi(px ? xMax >> fp.binShiftX : xMax / (int)fp.binW, 0, (int)fp.binsX - 1);
+					by1 = clampi(py ? yMax >> fp.binShiftY : yMax / (int)fp.binH, 0, (int)fp.binsY - 1);
+					if (bx0 <= bx1 && by0 <= by1)
 					{
-						directTiles = nTiles;
-						nTiles = 0;
-						if (area)
+						nTiles = (uint32_t)(bx1 - bx0 + 1) * (uint32_t)(by1 - by0 + 1);
+						if (DIRECT)
 						{
-							record = true;
-							rec.x0 = r.x0; rec.y0 = r.y0; rec.x1 = r.x1; rec.y1 = r.y1; rec.x2 = r.x2; rec.y2 = r.y2;
-							rec.z0 = r.z0; rec.z1 = r.z1; rec.z2 = r.z2; rec.area = r.area; rec.rcpArea = r.rcpArea; rec.divLo = r.divLo;
-							rec.prim = prim; rec.boxX = (uint32_t)x0 | ((uint32_t)x1 << 16); rec.boxY = (uint32_t)y0 | ((uint32_t)y1 << 16); rec.pad = 0u;
+							rasterConstants(b, fp, r);
+							// candidate pixels: the candidate box inside the bins of the rectangle (the box is already clamped to the screen)
+							const int x0 = max((int)(r.cbX & 0xFFFFu), bx0 * (int)fp.binW), x1 = min((int)(r.cbX >> 16), (bx1 + 1) * (int)fp.binW);
+							const int y0 = max((int)(r.cbY & 0xFFFFu), by0 * (int)fp.binH), y1 = min((int)(r.cbY >> 16), (by1 + 1) * (int)fp.binH);
+							const uint32_t area = (x1 > x0 && y1 > y0) ? (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) : 0u;
+							if (area <= fp.directMaxArea)
+							{
+								directTiles = nTiles;
+								nTiles = 0;
+								if (area)
+								{
+									record = true;
+									rec.x0 = r.x0; rec.y0 = r.y0; rec.x1 = r.x1; rec.y1 = r.y1; rec.x2 = r.x2; rec.y2 = r.y2;
+									rec.z0 = r.z0; rec.z1 = r.z1; rec.z2 = r.z2;
+									rec.prim = prim; rec.boxX = (uint32_t)x0 | ((uint32_t)x1 << 16); rec.boxY = (uint32_t)y0 | ((uint32_t)y1 << 16);
+								}
+							}
 						}
 					}
 				}
+				// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
+				// from a visible primitive whose rectangle happens to be empty
+				// (bit 31 of the first word: resolved here, not to be scattered into the lists)
+				rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16) | (directTiles ? kRectDirect : 0u), (uint32_t)by0 | ((uint32_t)by1 << 16))
+				                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
 			}
-		}
-		// culled primitives are marked (0xFFFF, 0): an empty rectangle that b2r_read_visible can tell
-		// from a visible primitive whose rectangle happens to be empty
-		// (bit 31 of the first word: resolved here, not to be scattered into the lists)
-		rects[prim] = visible ? make_uint2((uint32_t)bx0 | ((uint32_t)bx1 << 16) | (directTiles ? kRectDirect : 0u), (uint32_t)by0 | ((uint32_t)by1 << 16))
-		                      : make_uint2(0x0000FFFFu, 0x0000FFFFu);
-	}
-	if (DIRECT)
-	{
-		// compaction: one shared-memory atomic per warp
-		const unsigned m = __ballot_sync(0xFFFFFFFFu, record);
-		if (m)
-		{
-			uint32_t base = 0;
-			if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&sRecCount, (uint32_t)__popc(m));
-			base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-			if (record) sRec[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
-		}
-	}
-	// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
-	{
-		const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
-		uint32_t* slot = &counters[kVisBase + ((blockIdx.x * 8 + (threadIdx.x >> 5)) % kVisSlots) * 32];
-		if (lane == 0 && vis) atomicAdd(slot, (uint32_t)__popc(vis));
-		if (DIRECT)
-		{
-			const uint32_t dt = __reduce_add_sync(0xFFFFFFFFu, min(directTiles, 0x00FFFFFFu));      // (a rectangle has at most 2^22 tiles)
-			if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, (unsigned long long)dt);
-		}
-	}
-	// per-tile counts, warp-aggregated
-	if (nTiles > fp.bigRectTiles)
-	{
-		bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
-		nTiles = 0;
-	}
-	if (DIRECT)
-	{
-		// the few triangles that still go into the lists: the scatter kernel visits them through 32-entry slots (this warp's
-		// ids in lane order, kNoPrim where a lane has none) instead of re-reading the rectangle of every primitive
-		const unsigned binned = __ballot_sync(0xFFFFFFFFu, nTiles > 0u);
-		if (binned)
-		{
-			uint32_t slot = 0;
-			if (lane == 0) slot = atomicAdd(&counters[kBinSlotsWord], 1u);
-			slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-			binSlots[(size_t)slot * 32u + lane] = nTiles > 0u ? prim : kNoPrim;
-		}
-	}
-	warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
-	if (!DIRECT) return;
-
-	// ---- phase B: the recorded triangles.  A CTA's 256 primitives leave only a few dozen records (culled, off-pixel and
-	// binned ones are gone), so each record is shared by k = 256 / records neighbouring threads that take every k-th
-	// candidate pixel: all warps of the CTA stay busy and the trip counts inside a warp are even.
-	__syncthreads();
-	uint32_t nFrags = 0;
-	const uint32_t nRec = sRecCount;
-	const uint32_t share = nRec ? (uint32_t)kChunk / nRec : 1u;          // >= 1 (nRec <= kChunk)
-	const uint32_t recIdx = threadIdx.x / share, first = threadIdx.x - recIdx * share;
-	if (recIdx < nRec)
-	{
-		const DirectRecord& q = sRec[recIdx];
-		const int x0 = (int)(q.boxX & 0xFFFFu), x1 = (int)(q.boxX >> 16), y0 = (int)(q.boxY & 0xFFFFu), y1 = (int)(q.boxY >> 16);
-		const uint32_t w = (uint32_t)(x1 - x0), area = w * (uint32_t)(y1 - y0);
-		if (first < area)
-		{
-			TriShared t;
-			t.x0 = q.x0; t.y0 = q.y0; t.x1 = q.x1; t.y1 = q.y1; t.x2 = q.x2; t.y2 = q.y2;
-			t.z0 = q.z0; t.z1 = q.z1; t.z2 = q.z2; t.area = q.area; t.rcpArea = q.rcpArea; t.divLo = q.divLo;
-			t.eAx = q.x1 - q.x0; t.eAy = q.y1 - q.y0;      // the subtractions of expandRecord: same bits as in the raster kernel
-			t.eBx = q.x2 - q.x1; t.eBy = q.y2 - q.y1;
-			t.eCx = q.x0 - q.x2; t.eCy = q.y0 - q.y2;
-			t.prim = q.prim; t.zLow = 0; t.yExtent = 0;
-			const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
-			const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
-			const uint32_t row = first / w;
-			int y = y0 + (int)row, x = x0 + (int)(first - row * w);
-			for (uint32_t i = first; i < area; i += share)
+			if (DIRECT)
 			{
-				Bary bc; int zi;
-				if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+				// compaction: one shared-memory atomic per warp
+				const unsigned m = __ballot_sync(0xFFFFFFFFu, record);
+				if (m)
 				{
-					const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
-					if (!replicated || tile % fp.ownerCount == fp.ownerRank)
+					uint32_t base = 0;
+					if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&sRecCount[cur], (uint32_t)__popc(m));
+					base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+					if (record) sRec[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
+				}
+			}
+			// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+			{
+				const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
+				uint32_t* slot = &counters[kVisBase + ((chunk * 8 + (tid >> 5)) % kVisSlots) * 32];
+				if (lane == 0 && vis) atomicAdd(slot, (uint32_t)__popc(vis));
+				if (DIRECT)
+				{
+					const uint32_t dt = __reduce_add_sync(0xFFFFFFFFu, min(directTiles, 0x00FFFFFFu));      // (a rectangle has at most 2^22 tiles)
+					if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, (unsigned long long)dt);
+				}
+			}
+			// per-tile counts, warp-aggregated
+			if (nTiles > fp.bigRectTiles)
+			{
+				bigList[atomicAdd(&counters[1], 1u)] = prim;      // handled cooperatively (binBigBody)
+				nTiles = 0;
+			}
+			if (DIRECT)
+			{
+				// the few triangles that still go into the lists: the scatter kernel visits them through 32-entry slots (this warp's
+				// ids in lane order, kNoPrim where a lane has none) instead of re-reading the rectangle of every primitive
+				const unsigned binned = __ballot_sync(0xFFFFFFFFu, nTiles > 0u);
+				if (binned)
+				{
+					uint32_t slot = 0;
+					if (lane == 0) slot = atomicAdd(&counters[kBinSlotsWord], 1u);
+					slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+					binSlots[(size_t)slot * 32u + lane] = nTiles > 0u ? prim : kNoPrim;
+				}
+			}
+			warpBinRects<false>(nTiles, bx0, bx1, by0, by1, prim, tileCount, nullptr, nullptr, fp);
+		}
+		if (!DIRECT) continue;
+
+		// ---- phase B: the recorded triangles of the chunk
+		__syncthreads();
+		const uint32_t nRec = sRecCount[cur];
+		if (tid == 0) sRecCount[nxt] = 0;      // (its last readers left before the previous iteration's closing barrier; the next phase A starts behind this one's)
+		if (nRec)
+		{
+			// threads per record: the largest power of two <= 256 / records (a shift instead of a division)
+			const uint32_t shareLog = 31u - (uint32_t)__clz((uint32_t)kChunk / nRec);
+			const uint32_t share = 1u << shareLog;
+			const uint32_t recIdx = tid >> shareLog, first = tid & (share - 1u);
+			if (recIdx < nRec)
+			{
+				const DirectRecord& q = sRec[recIdx];
+				const int x0 = (int)(q.boxX & 0xFFFFu), x1 = (int)(q.boxX >> 16), y0 = (int)(q.boxY & 0xFFFFu), y1 = (int)(q.boxY >> 16);
+				const uint32_t w = (uint32_t)(x1 - x0), area = w * (uint32_t)(y1 - y0);
+				if (first < area)
+				{
+					TriShared t;
+					t.x0 = q.x0; t.y0 = q.y0; t.x1 = q.x1; t.y1 = q.y1; t.x2 = q.x2; t.y2 = q.y2;
+					t.z0 = q.z0; t.z1 = q.z1; t.z2 = q.z2;
+					// the same functions of the same coordinates as rasterConstants / expandRecord: same bits as in the raster kernel
+					t.area = fabsf(diff2(t.x0 - t.x1, t.y0 - t.y2, t.y0 - t.y1, t.x0 - t.x2));
+					t.rcpArea = refinedReciprocal(t.area);
+					t.divLo = divisionThreshold(t.area);
+					t.eAx = q.x1 - q.x0; t.eAy = q.y1 - q.y0;
+					t.eBx = q.x2 - q.x1; t.eBy = q.y2 - q.y1;
+					t.eCx = q.x0 - q.x2; t.eCy = q.y0 - q.y2;
+					t.prim = q.prim; t.zLow = 0; t.yExtent = 0;
+					const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
+					const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
+					int y = y0, x = x0 + (int)first;
+					while (x >= x1) { x -= (int)w; ++y; }
+					for (uint32_t i = first; i < area; i += share)
 					{
-						atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | t.prim);
-						dirty[tile] = 1;
-						++nFrags;
+						Bary bc; int zi;
+						if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
+						{
+							const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
+							if (!replicated || tile % fp.ownerCount == fp.ownerRank)
+							{
+								atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | t.prim);
+								dirty[tile] = 1;
+								++nFrags;
+							}
+						}
+						x += (int)share;
+						while (x >= x1) { x -= (int)w; ++y; }
 					}
 				}
-				x += (int)share;
-				while (x >= x1) { x -= (int)w; ++y; }
 			}
 		}
+		__syncthreads();                   // every thread is done with the records before the next chunk's are written
 	}
-	if (fp.countFragments)
+	if (DIRECT && fp.countFragments)
 	{
 		nFrags = __reduce_add_sync(0xFFFFFFFFu, nFrags);
 		if (lane == 0 && nFrags) atomicAdd(&frameInfo[4], (unsigned long long)nFrags);

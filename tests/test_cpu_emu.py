@@ -78,7 +78,8 @@ def test_direct_path_equals_the_binned_path(emu_env):
     """B2R_OPT_DIRECT_MAX_AREA (small triangles resolved by the setup kernel with atomicMin on the key buffer) against the
     all-binned path: surfaces, statistics and complete bins identical for several bin grids, thresholds, fill rules,
     sort-first ownership and with frames in flight (tests/emu_scenarios.py direct_path_checks)."""
-    res = run(emu_env, "direct", "full" if SLOW else "quick")
+    # (B2R_SETUP_GRID: two CTAs for the setup kernel, so that each walks several 256-primitive chunks through its copy pipeline)
+    res = run(dict(emu_env, B2R_SETUP_GRID="2"), "direct", "full" if SLOW else "quick")
     assert res and all(res.values()), {k: v for k, v in res.items() if not v}
     assert "inflight/ring3" in res and "owners3" in res
 

@@ -5,6 +5,7 @@
   asm volatile(                                     ->  EMU_ASM(
   cudaFuncSetAttribute(                             ->  emu::funcSetAttribute(
   asm("rcp.approx.ftz.f32 ...")                     ->  r = 1.0f / b;
+  asm volatile("cp.async.ca.shared.global ...")     ->  memcpy(smemDst, gsrc, 16);
   extern __shared__ T name[];                       ->  T* name = (T*)emu::dynamicSmemPtr();
 Nothing else is touched: the kernels that run in the emulator are the product's kernels."""
 import os
@@ -61,6 +62,8 @@ def main(src_dir, dst_dir):
         s = rewrite_launches(s)
         s = s.replace("cudaLaunchKernelEx(", "emu::launchEx(")
         s = s.replace('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = emuGlobalTimerNs();")
+        # cp.async: a plain copy at issue time (the emulator has no asynchronous copies; commit / wait become no-ops below)
+        s = s.replace('asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");', "memcpy(smemDst, gsrc, 16);")
         s = s.replace("asm volatile(", "EMU_ASM(")
         s = s.replace("cudaFuncSetAttribute(", "emu::funcSetAttribute(")
         # MUFU.RCP: the correctly rounded reciprocal stands in for the hardware approximation; the refinement steps that follow
