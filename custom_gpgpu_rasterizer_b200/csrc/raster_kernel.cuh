@@ -119,15 +119,17 @@ __device__ __forceinline__ void expandRecord(const TriRecord& r, uint32_t prim, 
 //
 // Structure.  A primitive costs two DEPENDENT memory round trips (vertex reference -> three positions) before a few
 // hundred instructions of arithmetic, and a one-primitive-per-thread kernel idles on them (ncu: 28-45 % of the warp
-// samples wait for the positions, issue slots ~50 % busy, whatever the occupancy).  So the kernel is persistent - a CTA
-// strides over chunks of 256 primitives - and every thread runs a three-stage pipeline of asynchronous copies
-// (cp.async, global -> shared without passing through registers): while the CTA works on chunk i, the positions of chunk
-// i+1 and the vertex references of chunk i+2 are in flight.  A thread only ever reads back what it copied itself, so the
-// pipeline needs no barrier.
-// The direct path then runs in two phases with a stream compaction through shared memory in between.  Phase A is the
-// setup proper, one thread per primitive: cull, rectangle, candidate box; a small triangle that has candidate pixels
-// leaves a 48-byte record in shared memory.  Phase B shares each record between k = 256 / records neighbouring threads
-// that take every k-th candidate pixel - the culled, off-pixel and binned primitives are gone, all warps stay busy.
+// samples wait for the positions, issue slots ~50 % busy, whatever the occupancy).  So the kernel is persistent - every
+// WARP strides over groups of 32 consecutive primitives - and every thread runs a three-stage pipeline of asynchronous
+// copies (cp.async, global -> shared without passing through registers): while the warp works on group i, the positions
+// of group i+1 and the vertex references of group i+2 are in flight.  A thread only ever reads back what it copied
+// itself, so the pipeline needs no barrier.
+// The direct path then runs in two phases with a stream compaction through shared memory in between, warp by warp (a
+// CTA-wide compaction cost two barriers per 256 primitives and 32 % of the warp samples, because culled and visible
+// warps differ widely in work).  Phase A is the setup proper, one lane per primitive: cull, rectangle, candidate box; a
+// small triangle that has candidate pixels leaves a 48-byte record in the warp's shared-memory slice.  Phase B shares
+// each record between k = 32 / records neighbouring lanes (a power of two) that take every k-th candidate pixel - the
+// culled, off-pixel and binned primitives are gone, the lanes stay busy.
 #ifndef B2R_SETUP_CTAS
 #define B2R_SETUP_CTAS 5
 #endif
@@ -148,19 +150,17 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 	pdlPrologue();
 	__shared__ __align__(16) uint4 sRef[2][kChunk];              // vertex references of chunks i+1 / i+2
 	__shared__ __align__(16) float4 sPos[2][3][kChunk];          // positions of chunks i / i+1
-	__shared__ __align__(16) DirectRecord sRec[DIRECT ? kChunk : 1];
-	__shared__ uint32_t sRecCount[2];                            // records of the current chunk / being reset for the next
-	const uint32_t tid = threadIdx.x, lane = tid & 31u;
-	const uint32_t nChunks = (primHi - primLo + kChunk - 1) / kChunk;
-	if (blockIdx.x >= nChunks) return;
-	auto primOf = [&](uint32_t chunk) { return primLo + chunk * kChunk + tid; };
+	__shared__ __align__(16) DirectRecord sRec[DIRECT ? kChunk : 1];      // 32 per warp
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t nChunks = (primHi - primLo + 31u) / 32u;        // ("chunk" = a warp's group of 32 primitives)
+	const uint32_t firstChunk = blockIdx.x * (kChunk / 32) + warp;
+	if (firstChunk >= nChunks) return;
+	auto primOf = [&](uint32_t chunk) { return primLo + chunk * 32u + lane; };
 	// pipeline fill (the step is gridDim.x chunks, and a chunk's buffers are chosen by the parity of its POSITION in this
 	// CTA's sequence, not of its index)
-	const uint32_t step = gridDim.x;
-	if (DIRECT && tid < 2) sRecCount[tid] = 0;
-	if (DIRECT) __syncthreads();
+	const uint32_t step = gridDim.x * (kChunk / 32);
 	{
-		const uint32_t c0 = blockIdx.x;
+		const uint32_t c0 = firstChunk;
 		if (primOf(c0) < primHi) cpAsync16(&sRef[0][tid], triRefs + primOf(c0));
 		cpAsyncCommit(); cpAsyncWaitAll();
 		if (primOf(c0) < primHi)
@@ -173,9 +173,10 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 	}
 	uint32_t nFrags = 0;
 	uint32_t it = 0;
-	for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += step, ++it)
+	for (uint32_t chunk = firstChunk; chunk < nChunks; chunk += step, ++it)
 	{
 		const uint32_t cur = it & 1u, nxt = cur ^ 1u;
+		uint32_t nRec = 0;
 		// positions of this chunk and references of the next have landed (requested one whole iteration ago)
 		cpAsyncWaitAll();
 		// request: positions of the next chunk, references of the one after (into the buffers this iteration does not read)
@@ -270,20 +271,15 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 			}
 			if (DIRECT)
 			{
-				// compaction: one shared-memory atomic per warp
+				// compaction into the warp's slice of the record buffer
 				const unsigned m = __ballot_sync(0xFFFFFFFFu, record);
-				if (m)
-				{
-					uint32_t base = 0;
-					if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&sRecCount[cur], (uint32_t)__popc(m));
-					base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-					if (record) sRec[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
-				}
+				nRec = (uint32_t)__popc(m);
+				if (record) sRec[warp * 32u + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
 			}
 			// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
 			{
 				const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
-				uint32_t* slot = &counters[kVisBase + ((chunk * 8 + (tid >> 5)) % kVisSlots) * 32];
+				uint32_t* slot = &counters[kVisBase + (chunk % kVisSlots) * 32];
 				if (lane == 0 && vis) atomicAdd(slot, (uint32_t)__popc(vis));
 				if (DIRECT)
 				{
@@ -314,19 +310,17 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 		}
 		if (!DIRECT) continue;
 
-		// ---- phase B: the recorded triangles of the chunk
-		__syncthreads();
-		const uint32_t nRec = sRecCount[cur];
-		if (tid == 0) sRecCount[nxt] = 0;      // (its last readers left before the previous iteration's closing barrier; the next phase A starts behind this one's)
+		// ---- phase B: the recorded triangles of the group
+		__syncwarp();
 		if (nRec)
 		{
-			// threads per record: the largest power of two <= 256 / records (a shift instead of a division)
-			const uint32_t shareLog = 31u - (uint32_t)__clz((uint32_t)kChunk / nRec);
+			// lanes per record: the largest power of two <= 32 / records
+			const uint32_t shareLog = 31u - (uint32_t)__clz(32u / nRec);
 			const uint32_t share = 1u << shareLog;
-			const uint32_t recIdx = tid >> shareLog, first = tid & (share - 1u);
+			const uint32_t recIdx = lane >> shareLog, first = lane & (share - 1u);
 			if (recIdx < nRec)
 			{
-				const DirectRecord& q = sRec[recIdx];
+				const DirectRecord& q = sRec[warp * 32u + recIdx];
 				const int x0 = (int)(q.boxX & 0xFFFFu), x1 = (int)(q.boxX >> 16), y0 = (int)(q.boxY & 0xFFFFu), y1 = (int)(q.boxY >> 16);
 				const uint32_t w = (uint32_t)(x1 - x0), area = w * (uint32_t)(y1 - y0);
 				if (first < area)
@@ -365,7 +359,7 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 				}
 			}
 		}
-		__syncthreads();                   // every thread is done with the records before the next chunk's are written
+		__syncwarp();                      // every lane is done with the records before the next group's are written
 	}
 	if (DIRECT && fp.countFragments)
 	{
