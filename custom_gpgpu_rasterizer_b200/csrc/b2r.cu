@@ -34,7 +34,7 @@ constexpr int kRing = 4;
 constexpr int kMaxFrameRing = 4;      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
 constexpr int kInfoWords = 16;
 #ifndef B2R_DIRECT_MAX_AREA
-#define B2R_DIRECT_MAX_AREA 64
+#define B2R_DIRECT_MAX_AREA 16
 #endif
 constexpr int kDirectMaxAreaDefault = B2R_DIRECT_MAX_AREA;
 thread_local std::string g_createError;

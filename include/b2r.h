@@ -103,7 +103,7 @@ enum
 	 * buffer instead of going through the bin lists; the raster kernel merges the key buffer into its tiles.  Same
 	 * fragments, same keys, same order-independent min: the frame is identical bit for bit.  0 switches the path off
 	 * (every visible triangle is binned).  b2r_read_bins always returns the complete bins (it re-runs the newest frame
-	 * with the path off when needed).  Not used by the sharded front end.  Default 64; set it between frames. */
+	 * with the path off when needed).  Sharded front end: the ranks exchange the touched 16x16 key blocks instead of list entries (needs 16x16 bins; the switch is fixed at b2r_shard_prepare and must agree on all ranks).  Default 16; set it between frames. */
 	B2R_OPT_DIRECT_MAX_AREA = 15
 };
 
