@@ -421,16 +421,19 @@ def workload_config(name, scene):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def algorithmic_bytes(scene, visible, pairs, frags, covered_px):
-    """SURVEY.md section 8d / BASELINE.md section 3 contract figures."""
+def algorithmic_bytes(scene, visible, pairs, frags, covered_px, direct=False):
+    """SURVEY.md section 8d / BASELINE.md section 3 contract figures.  direct: the frame resolved its small triangles in the
+    setup kernel (B2R_OPT_DIRECT_MAX_AREA), so the consumption of the (triangle, tile) pairs and the depth test of the
+    fragments are work of the SETUP stage; the raster stage keeps the resolve + write-back.  The frame total is the same."""
     V, T, Tv, P, N = scene.n_vertices, scene.n_tris, visible, pairs, scene.bins_x * scene.bins_y
     px = scene.width * scene.height
+    moved = (frags * 4 + P * 52) if direct else 0
     return {
         "vertex": V * 128,
-        "setup": T * 60 + Tv * 12,
+        "setup": T * 60 + Tv * 12 + moved,
         "binning": Tv * 120 + P * 4 + N * 16,
         # fill/ROP: F*4 (depth read) + Fp*8 (depth+colour write) + W*H*8 (write-back) + list consumption P*(4+48)
-        "raster_shade": frags * 4 + covered_px * 8 + px * 8 + P * 52,
+        "raster_shade": frags * 4 + covered_px * 8 + px * 8 + P * 52 - moved,
     }
 
 
@@ -465,6 +468,10 @@ def run_b200(args, scene):
     ring = int(os.environ["B2R_FRAME_RING"]) if "B2R_FRAME_RING" in os.environ else (args.ring if args.ring >= 0 else (4 if sharded else 3))
     if world == 1 or sharded:
         r.set_option(_lib.OPT_FRAME_RING, ring)
+    # sharded front end: every rank transforms only the vertices of its own primitive slice, the raster kernel transforms the
+    # vertices of its pixels' winners itself (measured at 8 ranks: 9 370 against 7 958 frames/s); needs the frame ring
+    if sharded and ring and "B2R_SHARD_SLICED_VERTEX" not in os.environ:
+        r.set_option(_lib.OPT_SHARD_SLICED_VERTEX, 1)
     if not sharded:
         r.set_option(_lib.OPT_TILE_OWNER_COUNT, world)
         r.set_option(_lib.OPT_TILE_OWNER_RANK, rank)
@@ -714,7 +721,8 @@ def run_b200(args, scene):
 
     fps = args.steps / (total_ms / 1e3)
     peak, peak_src = load_peaks()
-    ab = algorithmic_bytes(scene, visible, pairs, frags, covered_px)
+    direct_area = r.get_option(_lib.OPT_DIRECT_MAX_AREA)
+    ab = algorithmic_bytes(scene, visible, pairs, frags, covered_px, direct=direct_area > 0 and args.workload != "fill64")
     stage_of = {"vertex": "vertex", "setup": "setup", "binning": None, "raster_shade": "raster_shade"}
     per_stage = {}
     for k, b in ab.items():
@@ -758,7 +766,7 @@ def run_b200(args, scene):
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_of(scene),
         "config": workload_config(args.workload, scene),
-        "parallelism": ("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r sets up and bins primitive slice r, owners read the peers' lists over NVLink (and put them in order), colours stored straight into rank 0's surface, two flag barriers per frame, no collective"}[args.gather]),
+        "parallelism": ("single GPU" if world == 1 else f"sort-first, {world} ranks, tile owner = tile index mod {world}, " + {"nccl": "every rank bins the full mesh, NCCL gather of packed tiles to rank 0", "p2p": "every rank bins the full mesh, peer-to-peer ROP write-back into rank 0 over NVLink (CUDA IPC)", "sharded": "sharded front end: rank r transforms, sets up and bins primitive slice r; small triangles are resolved by that rank into its own key buffer and the touched 16x16 key blocks go to the tile owners over NVLink (direct path), the other triangles as list entries; owners merge, shade and store their colours straight into rank 0's surface; two flag barriers per frame, no collective"}[args.gather]),
         "mtris_per_s": scene.n_tris * fps / 1e6,
         "visible_triangles": visible, "tile_pairs": pairs, "fragments": frags, "covered_pixels": covered_px,
         "checksum": {"framebuffer_crc32": crc_dev, "host_framebuffer_crc32": crc_host, "single_gpu": single,
@@ -786,7 +794,7 @@ def run_b200(args, scene):
                           "device->host copy of the framebuffer into pinned memory (b2r_present_async, pipelined over two surfaces; RenderAuto = Render + Present), ") +
                          "wall clock over all frames incl. the final wait and a barrier across the ranks")},
         "frame_ring": ring if (world == 1 or sharded) else 0,
-        "direct_max_area": r.get_option(_lib.OPT_DIRECT_MAX_AREA),
+        "direct_max_area": direct_area,
         "gpu_launches": launches_per_frame * args.steps,
         "gpu_launches_per_step": launches_per_frame,
         "host_enqueue_ms_per_frame": host_enqueue_ms,
