@@ -92,7 +92,7 @@ struct b2r_context
 	std::string error;
 
 	// options
-	int fillTopLeft = 1, ownerRank = 0, ownerCount = 1, debugSurfaces = 0, stageTimers = 0, sortBins = 1, packedOutput = 0;
+	int fillTopLeft = 1, ownerRank = 0, ownerCount = 1, debugSurfaces = 0, stageTimers = 0, sortBins = 0, packedOutput = 0;
 	int directMaxArea = kDirectMaxAreaDefault;      // B2R_OPT_DIRECT_MAX_AREA
 	bool lastDirect = false;                        // the newest enqueued frame resolved small triangles in its setup kernel (its lists hold the others only)
 
@@ -316,7 +316,9 @@ int reserveBinSet(b2r_context* c, b2r_context::BinSet& B)
 	CU(c, B.rects.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	CU(c, B.bigList.reserve(std::max<size_t>(c->nPrims, 1), c->stream));
 	// list capacity heuristic; regrown on overflow (see validateFrame), and kept equal across the sets
-	size_t listCap = std::max<size_t>((size_t)1 << 22, c->nPrims * 3);
+	// (a few large triangles can fill every tile: a margin in proportion to the bin grid - 160 entries per tile - keeps e.g.
+	// 64 full-screen layers at 4K, 4.15 M pairs, clear of the 4 M floor)
+	size_t listCap = std::max<size_t>(std::max<size_t>((size_t)1 << 22, c->nPrims * 3), n * 160);
 	for (const auto& other : c->bins) listCap = std::max(listCap, other.binIds.cap);
 	CU(c, B.binIds.reserve(listCap, c->stream));
 	if (c->directMaxArea)

@@ -71,7 +71,10 @@ def main():
             if arg == "serial":
                 r.set_option(_lib.OPT_OVERLAP_FRONT, 0)
             if arg == "unsorted":
-                r.set_option(_lib.OPT_SORT_BINS, 0)
+                r.set_option(_lib.OPT_SORT_BINS, 0)      # (the library default)
+            if arg == "sorted":
+                r.set_option(_lib.OPT_SORT_BINS, 1)      # lists put in order inside the frame (by the raster kernel)
+                r.set_option(_lib.OPT_DIRECT_MAX_AREA, 0)     # ... with every triangle in the lists
             r.load_scene(sc)
             # all frames enqueued back to back (no synchronisation in between), Present of each into its own host buffer
             host = [np.zeros((sc.height, sc.width), np.uint32) for _ in cams]

@@ -66,7 +66,7 @@ def test_emulated_product_equals_the_oracle_with_the_reference_fill_rule(emu_env
 SLOW = os.environ.get("B2R_SLOW_TESTS") == "1"          # the full matrix takes ~10 min of CPU; the default subset ~4 min
 
 
-@pytest.mark.parametrize("mode", ["default", "unsorted", "ring3"] + (["serial", "ring2", "ring4"] if SLOW else []))
+@pytest.mark.parametrize("mode", ["default", "sorted", "ring3"] + (["unsorted", "serial", "ring2", "ring4"] if SLOW else []))
 def test_scheduler_modes_compute_the_right_frames(emu_env, mode):
     res = run(emu_env, "schedulers", mode)
     assert all(res["frames"]) and len(res["frames"]) == 7, res["frames"]

@@ -264,7 +264,7 @@ def test_wiring_check_has_teeth(logs, sharded_logs, tmp_path):
     assert any("binIds" in e for e in t.wiring_errors())
 
     def other_inbox(raw, nxt):
-        raw[14 * 8:15 * 8] = nxt[14 * 8:15 * 8]  # RasterArgs.shard.tileCount[0] of the next frame's list set
+        raw[15 * 8:16 * 8] = nxt[15 * 8:16 * 8]  # RasterArgs.shard.tileCount[0] of the next frame's list set
     t = mutate(sharded_logs[(2, "ring3")], lambda l: '"dev":1' in l, other_inbox)
     assert any("reads the heads of rank 0" in e for e in t.wiring_errors(2))
 

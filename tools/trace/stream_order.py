@@ -46,14 +46,17 @@ import sys
 from collections import defaultdict
 
 K_MAX_RANKS = 8
-RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("ivertex", "r"), ("colour", "r"),
+RASTER_ARGS = [("tileCount", "r"), ("tileOffset", "r"), ("binIds", "w"), ("triRefs", "r"), ("pos4", "r"), ("posIn", "r"), ("ivertex", "r"), ("colour", "r"),
                ("meshes", "r"), ("textures", "r"), ("frameInfo", "w"), ("framebuffer", "w"), ("depth", "w"), ("zSurface", "w"), ("winnerSurface", "w")]
 RASTER_ARGS += [(f"shard.tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"shard.tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)] \
-    + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r"), ("keys", "w"), ("dirty", "w")]      # the raster kernel sorts the lists it stages, in place, and resets the key buffer it merges
+    + [(f"shard.binIds[{i}]", "w") for i in range(K_MAX_RANKS)] + [(f"shard.keyInbox[{i}]", "r") for i in range(K_MAX_RANKS)] \
+    + [(f"shard.dirtyInbox[{i}]", "w") for i in range(K_MAX_RANKS)] + [("tileOrder", "r"), ("keys", "w"), ("dirty", "w")]      # the raster kernel sorts the lists it stages, in place, and resets the key buffer it merges
 STRUCTS = {
     "b2r::RasterArgs": RASTER_ARGS,
     "b2r::ShardTable": [(f"tileCount[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"tileOffset[{i}]", "r") for i in range(K_MAX_RANKS)]
-                       + [(f"binIds[{i}]", "r") for i in range(K_MAX_RANKS)],
+                       + [(f"binIds[{i}]", "r") for i in range(K_MAX_RANKS)] + [(f"keyInbox[{i}]", "r") for i in range(K_MAX_RANKS)]
+                       + [(f"dirtyInbox[{i}]", "r") for i in range(K_MAX_RANKS)],
+    "b2r::ShardKeyPush": [(f"keyInbox[{i}]", "w") for i in range(K_MAX_RANKS)] + [(f"dirtyInbox[{i}]", "w") for i in range(K_MAX_RANKS)],
     "b2r::PeerFlags": [],                  # the flag words: concurrent by design, see above
     "b2r::ShardInbox": [(f"tileCount[{i}]", "w") for i in range(K_MAX_RANKS)] + [(f"tileOffset[{i}]", "w") for i in range(K_MAX_RANKS)],
     "b2r::ShardRegions": [(f"region[{i}]", "w") for i in range(K_MAX_RANKS)],
@@ -188,11 +191,12 @@ class Trace:
         "bin_scatter_kernel": {"rects": 0, "binSlots": 1, "tileOffset": 4, "tileCursor": 5, "binIds": 6, "bigList": 7, "counters": 8, "frameInfo": 10},      # args[12] = ShardRegions: the mirror of the lists in the owners' arenas
         "bin_sort_tiles_kernel": {"tileCount": 0, "tileOffset": 1, "binIds": 2, "frameInfo": 4},
         "bin_sort_long_kernel": {"longTiles": 0, "tileCount": 1, "tileOffset": 2, "binIds": 3, "frameInfo": 4},
-        "shard_merge_heads_kernel": {"tileOrder": 4, "frameInfo": 5},
+        "shard_merge_heads_kernel": {"tileOrder": 4, "frameInfo": 5, "dirty": 6},
+        "shard_push_keys_kernel": {"keys": 0, "dirty": 1},
         "publish_info_kernel": {"frameInfo": 0},
     }
-    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "meshConst": 7, "frameInfo": 9, "tileOrder": 14 + 3 * K_MAX_RANKS,
-                    "keys": 15 + 3 * K_MAX_RANKS, "dirty": 16 + 3 * K_MAX_RANKS}
+    RASTER_ROLES = {"tileCount": 0, "tileOffset": 1, "binIds": 2, "triRefs": 3, "pos4": 4, "meshConst": 8, "frameInfo": 10, "tileOrder": 15 + 5 * K_MAX_RANKS,
+                    "keys": 16 + 5 * K_MAX_RANKS, "dirty": 17 + 5 * K_MAX_RANKS}
 
     def frames(self):
         """Per device: the launches of every frame, in the order the host issued them (b2r_render issues a whole frame; a
@@ -266,12 +270,12 @@ class Trace:
                           for d in range(ranks)}
                 if len(epochs) != 1:
                     errs.append(f"frame {i}: the ranks' barrier epochs differ: {sorted(epochs)}")
-                surfaces = {self._ptr(r["args"][0], 10) for r in rasters}
+                surfaces = {self._ptr(r["args"][0], 11) for r in rasters}
                 if len(surfaces) != 1:
                     errs.append(f"frame {i}: the ranks store their colours into different surfaces {sorted(hex(x) for x in surfaces)}")
                 for q in range(ranks):                     # tile owner q reads ...
                     for p in range(ranks):                 # ... what rank p pushed
-                        base = 14                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
+                        base = 15                          # RasterArgs.shard: tileCount[8], tileOffset[8], binIds[8]
                         want_count, want_off = self._ptr(heads[p]["args"][12], q), self._ptr(heads[p]["args"][12], K_MAX_RANKS + q)
                         got_count, got_off = self._ptr(rasters[q]["args"][0], base + p), self._ptr(rasters[q]["args"][0], base + K_MAX_RANKS + p)
                         if (want_count, want_off) != (got_count, got_off):
