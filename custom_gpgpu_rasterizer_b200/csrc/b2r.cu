@@ -72,7 +72,7 @@ struct HostMesh
 	int texIds[4];
 };
 
-struct HostTexture { uint32_t* px = nullptr; uint32_t w = 0, h = 0; bool alive = false; };
+struct HostTexture { uint32_t* px = nullptr; uint32_t w = 0, h = 0; bool alive = false; uint32_t tiledShift = 0; };
 
 struct RenderCall
 {
@@ -399,9 +399,9 @@ int rebuildScene(b2r_context* c)
 
 int rebuildTextures(b2r_context* c)
 {
-	std::vector<TexDesc> td(std::max<size_t>(c->textures.size(), 1), TexDesc{ nullptr, 0, 0 });
+	std::vector<TexDesc> td(std::max<size_t>(c->textures.size(), 1), TexDesc{ nullptr, 0, 0, 0, 0 });
 	for (size_t i = 0; i < c->textures.size(); ++i)
-		if (c->textures[i].alive) td[i] = TexDesc{ c->textures[i].px, c->textures[i].w, c->textures[i].h };
+		if (c->textures[i].alive) td[i] = TexDesc{ c->textures[i].px, c->textures[i].w, c->textures[i].h, c->textures[i].tiledShift, 0u };
 	CU(c, c->dTexDesc.reserve(td.size(), c->stream));
 	CU(c, cudaMemcpyAsync(c->dTexDesc.ptr, td.data(), td.size() * sizeof(TexDesc), cudaMemcpyHostToDevice, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
@@ -1418,6 +1418,22 @@ int b2r_texture_create_rgba8(b2r_context* c, const uint32_t* pixels, uint32_t w,
 	CU(c, cudaSetDevice(c->device));
 	HostTexture t; t.w = w; t.h = h; t.alive = true;
 	CU(c, cudaMalloc((void**)&t.px, (size_t)w * h * 4));
+	// round-2 experiment (variant build -DB2R_TEX_TILED_LAYOUT + B2R_TEX_TILED=1; measured: no gain): 8x4-texel tiles
+	std::vector<uint32_t> tiled;
+#ifdef B2R_TEX_TILED_LAYOUT
+	static const bool wantTiled = [] { const char* e = getenv("B2R_TEX_TILED"); return e && atoi(e) != 0; }();
+#else
+	const bool wantTiled = false;
+#endif
+	if (wantTiled && w >= 8 && (w & (w - 1)) == 0 && h % 4 == 0)
+	{
+		while ((1u << t.tiledShift) < w) ++t.tiledShift;
+		tiled.resize((size_t)w * h);
+		for (uint32_t y = 0; y < h; ++y)
+			for (uint32_t x = 0; x < w; ++x)
+				tiled[((((size_t)(y >> 2) * (w >> 3) + (x >> 3)) << 5) | ((y & 3u) << 3) | (x & 7u))] = pixels[(size_t)y * w + x];
+		pixels = tiled.data();
+	}
 	cudaError_t e = cudaMemcpyAsync(t.px, pixels, (size_t)w * h * 4, cudaMemcpyHostToDevice, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	if (e != cudaSuccess) { cudaFree(t.px); return fail(c, B2R_E_CUDA, "texture upload failed: %s", cudaGetErrorString(e)); }
@@ -1663,7 +1679,7 @@ int b2r_draw_texture(b2r_context* c, const uint32_t* pixels, uint32_t w, uint32_
 		static const float defClear[3] = { 0.25f, 0.25f, 0.25f };
 		const float* cl = clearRGB ? clearRGB : defClear;
 		const uint32_t clear = ((uint32_t)(cl[2] * 255.f) & 0xFFu) | (((uint32_t)(cl[1] * 255.f) & 0xFFu) << 8) | (((uint32_t)(cl[0] * 255.f) & 0xFFu) << 16);
-		draw_texture_kernel<<<dim3((c->width + 15) / 16, (c->height + 15) / 16), 256, 0, c->stream>>>(c->dColour[c->colourIdx], TexDesc{ d, w, h }, c->width, c->height,
+		draw_texture_kernel<<<dim3((c->width + 15) / 16, (c->height + 15) / 16), 256, 0, c->stream>>>(c->dColour[c->colourIdx], TexDesc{ d, w, h, 0u, 0u }, c->width, c->height,
 			global ? 1u : 0u, stretched ? 1u : 0u, (uint32_t)sample, clear);
 		e = cudaGetLastError();
 	}

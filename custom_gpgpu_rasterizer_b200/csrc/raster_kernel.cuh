@@ -381,7 +381,7 @@ __device__ __forceinline__ RGB samplePoint(const TexDesc& t, float u, float v)
 {
 	int x, y;
 	if (!texelCoords(t, u, v, x, y)) return RGB{ 1.f, 0.f, 1.f };
-	const uint32_t s = __ldg(t.px + (size_t)x + (size_t)y * t.w);
+	const uint32_t s = __ldg(t.px + texelIndex(t, (uint32_t)x + (uint32_t)y * t.w));
 	return RGB{ __fdiv_rn((float)(s & 0xFFu), 255.f), __fdiv_rn((float)((s >> 8) & 0xFFu), 255.f), __fdiv_rn((float)((s >> 16) & 0xFFu), 255.f) };
 }
 __device__ __forceinline__ RGB sampleLinear(const TexDesc& t, float u, float v)
@@ -394,7 +394,8 @@ __device__ __forceinline__ RGB sampleLinear(const TexDesc& t, float u, float v)
 	int n1 = o + 1;          if (n1 >= texSize) n1 = o;
 	int n2 = o + (int)t.w;   if (n2 >= texSize) n2 = o;
 	int n3 = o - (int)t.w;   if (n3 < 0) n3 = o;
-	const uint32_t s0 = __ldg(t.px + n0), s1 = __ldg(t.px + n1), s2 = __ldg(t.px + n2), s3 = __ldg(t.px + n3), sc = __ldg(t.px + o);
+	const uint32_t s0 = __ldg(t.px + texelIndex(t, (uint32_t)n0)), s1 = __ldg(t.px + texelIndex(t, (uint32_t)n1)), s2 = __ldg(t.px + texelIndex(t, (uint32_t)n2)),
+		s3 = __ldg(t.px + texelIndex(t, (uint32_t)n3)), sc = __ldg(t.px + texelIndex(t, (uint32_t)o));
 	// all partial sums are exact in fp32 (multiples of 1/8 below 2^11), so the order is free
 	const float r = (float)((s0 & 0xFFu) + (s1 & 0xFFu) + (s2 & 0xFFu) + (s3 & 0xFFu)) * 0.125f + (float)(sc & 0xFFu) * 0.5f;
 	const float g = (float)(((s0 >> 8) & 0xFFu) + ((s1 >> 8) & 0xFFu) + ((s2 >> 8) & 0xFFu) + ((s3 >> 8) & 0xFFu)) * 0.125f + (float)((sc >> 8) & 0xFFu) * 0.5f;
@@ -1068,7 +1069,7 @@ __global__ void __launch_bounds__(256) draw_texture_kernel(uint32_t* __restrict_
 		{
 			const float u = __fdiv_rn((float)x, (float)width), v = __fdiv_rn((float)y, (float)height);
 			const uint32_t tx = min((uint32_t)__float2int_rd(u * (float)tex.w), tex.w - 1u), ty = min((uint32_t)__float2int_rd(v * (float)tex.h), tex.h - 1u);
-			const uint32_t s = __ldg(tex.px + (size_t)tx + (size_t)ty * tex.w);
+			const uint32_t s = __ldg(tex.px + texelIndex(tex, tx + ty * tex.w));
 			colour = (s & 0xFF00FF00u) | ((s & 0xFFu) << 16) | ((s >> 16) & 0xFFu);
 		}
 		else

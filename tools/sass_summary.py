@@ -22,13 +22,13 @@ for line in out.splitlines():
     if m and cur:
         kernels[cur][m.group(1)] += 1
 dem = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
-GROUPS = [("global loads", r"^LDG"), ("global stores", r"^STG"), ("shared ld/st", r"^(LDS|STS)"), ("local (spill) ld/st", r"^(LDL|STL)"),
+GROUPS = [("global loads", r"^LDG(?!STS)"), ("async copies global->shared (LDGSTS = cp.async)", r"^LDGSTS"), ("global stores", r"^STG"), ("shared ld/st", r"^(LDS|STS)"), ("local (spill) ld/st", r"^(LDL|STL)"),
           ("global atomics / reductions", r"^(ATOMG|ATOM\b|ATOM\.|RED)"), ("shared atomics", r"^ATOMS"), ("warp collectives", r"^(SHFL|VOTE|MATCH|REDUX|CREDUX)"),
           ("barriers", r"^BAR"), ("prefetch (CCTL / PREFETCH)", r"^(CCTL|PREFETCH)"), ("PDL (ACQBULK / griddepcontrol: DEPBAR-less)", r"^(ACQBULK|PREEXIT)"),
           ("TMA (UBLKCP / UTMALDG / UTMASTG)", r"^(UBLKCP|UTMA)"), ("tensor core (HMMA / IMMA / UTCMMA / tcgen05)", r"^(HMMA|IMMA|DMMA|QMMA|UTC)"),
           ("MUFU", r"^MUFU"), ("FP32 FMA/MUL/ADD", r"^(FFMA|FMUL|FADD)\b"), ("integer IMAD/IADD/LOP", r"^(IMAD|IADD3|VIADD|LOP3)")]
 print(f"# SASS summary of `{lib}` ({', '.join(arch)})\n")
-print("One row per kernel: static instruction counts by class (cuobjdump -sass).  No TMA and no tensor-core instruction appears in any kernel -")
+print("One row per kernel: static instruction counts by class (cuobjdump -sass).  No TMA and no tensor-core instruction appears in any kernel (the setup kernel's copy pipeline is cp.async = LDGSTS: its sources are gathers, not tiles a tensor map could describe) -")
 print("the pipeline is gather / scatter / per-pixel arithmetic (DESIGN.md section 4); programmatic dependent launch shows as ACQBULK / PREEXIT-style control in the prologues.\n")
 print("| kernel | instructions | " + " | ".join(g for g, _ in GROUPS) + " |")
 print("|---|---|" + "---|" * len(GROUPS))
