@@ -30,9 +30,10 @@ using namespace b2r;
 
 namespace {
 
-constexpr int kRing = 4;
-constexpr int kMaxFrameRing = 4;      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
+constexpr int kRing = 8;
+constexpr int kMaxFrameRing = 8;      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
 constexpr int kInfoWords = 16;
+constexpr size_t kArenaFlagBytes = 512;   // flag words of the sharded front end: 32 + 8 per ring slot (device_types.cuh: PeerFlags)
 #ifndef B2R_DIRECT_MAX_AREA
 #define B2R_DIRECT_MAX_AREA 16
 #endif
@@ -222,8 +223,8 @@ struct b2r_context
 		uint32_t frame = 0;                    // frames rendered since the bind (same on every rank)
 		uint32_t waitedFrame = 0;              // rank 0: frames whose "colours landed" flags have been waited for
 		unsigned long long* hTimeout = nullptr; // pinned: raised by a colour wait that ran into its time-out
-		// arena: 256 B of flag words, then per set {tileCount, tileOffset, inbox count[n], inbox offset[n], binIds, region[n]}
-		uint32_t* tileCount(uint8_t* base, int set) const { return reinterpret_cast<uint32_t*>(base + 256 + (size_t)set * setBytes); }
+		// arena: kArenaFlagBytes of flag words, then per set {tileCount, tileOffset, inbox count[n], inbox offset[n], binIds, region[n]}
+		uint32_t* tileCount(uint8_t* base, int set) const { return reinterpret_cast<uint32_t*>(base + kArenaFlagBytes + (size_t)set * setBytes); }
 		uint32_t* tileOffset(uint8_t* base, int set) const { return tileCount(base, set) + tilesPad; }
 		uint32_t* inboxCount(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + src) * tilesPad; }
 		uint32_t* inboxOffset(uint8_t* base, int set, int src) const { return tileCount(base, set) + (size_t)(2 + n + src) * tilesPad; }
@@ -2060,7 +2061,7 @@ int b2r_shard_prepare(b2r_context* c, int rank, int count, uint64_t listCapacity
 	if (sh.direct) sh.setBytes += (size_t)count * (sh.ownedMax * 256 * 8 + sh.tilesPad);
 	sh.setBytes = (sh.setBytes + 255) & ~(size_t)255;
 	sh.nSets = c->ringDepth ? c->ringDepth : 2;
-	const size_t bytes = 256 + (size_t)sh.nSets * sh.setBytes;
+	const size_t bytes = kArenaFlagBytes + (size_t)sh.nSets * sh.setBytes;
 	CU(c, cudaMalloc((void**)&sh.arena, bytes));
 	CU(c, cudaMemset(sh.arena, 0, bytes));
 	CU(c, finishFills(c));
