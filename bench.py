@@ -882,7 +882,7 @@ def main():
     ap.add_argument("--gather", default="sharded", choices=["nccl", "p2p", "sharded"], help="sort-first composition: NCCL gather of packed tiles, peer-to-peer ROP write-back over NVLink, or the sharded front end (b2r_shard_*)")
     ap.add_argument("--views-mode", default="parallel", choices=["parallel", "sortfirst"], help="--workload views172 at N > 1: independent views per rank (default) or every view rendered sort-first by all ranks")
     ap.add_argument("--present", default="band", choices=["band", "tiles", "central"], help="N > 1, end-to-end leg: distributed Present by row bands out of rank 0's surface (default) or by owned tiles, or through rank 0's PCIe link alone")
-    ap.add_argument("--ring", type=int, default=-1, help="frame ring depth (B2R_OPT_FRAME_RING): 0 = three-stream pipeline, 2..8; default 3 on one GPU, 4 with the sharded front end")
+    ap.add_argument("--ring", type=int, default=-1, help="frame ring depth (B2R_OPT_FRAME_RING): 0 = three-stream pipeline, 2..4; default 3 on one GPU, 4 with the sharded front end")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fill", action="store_true")
     ap.add_argument("--ref-cuda", type=int, default=2, metavar="FRAMES", help="--impl reference only: also time the reference's own CUDA renderer (oracle/_ref/ref_render) on GPU 0 for this many frames (0 = skip)")

@@ -30,8 +30,8 @@ using namespace b2r;
 
 namespace {
 
-constexpr int kRing = 8;
-constexpr int kMaxFrameRing = 8;      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
+constexpr int kRing = 4;            // (measured at 8 ranks, round 2: 8 slots / rings of 6 and 8 frames are SLOWER - 7 700 / 5 100 / 1 050 frames/s at depth
+constexpr int kMaxFrameRing = 4;    //  4 / 6 / 8: more frames in flight means more resident kernels spinning on peer flags; profiles/r02_ab_log.md)      // B2R_OPT_FRAME_RING: at most this many frames with their own streams / buffer sets (<= kRing)
 constexpr int kInfoWords = 16;
 constexpr size_t kArenaFlagBytes = 512;   // flag words of the sharded front end: 32 + 8 per ring slot (device_types.cuh: PeerFlags)
 #ifndef B2R_DIRECT_MAX_AREA
@@ -156,7 +156,6 @@ struct b2r_context
 	bool ringNeedsFork[kMaxFrameRing] = {};
 	int ringPrev = -1;                 // ring slot of the previous frame while it may still be in flight
 	uint32_t* dRangeScratch = nullptr;
-	DeviceVec<uint4> dVertexMarks[kMaxFrameRing];   // sliced vertex stage: one byte per transformed vertex, per ring slot
 	int slicedVertex = 0;              // sharded front end: transform only the vertices of this rank's primitive slice;
 	                                   // the raster kernel transforms the vertices of its list entries itself (B2R_SHARD_SLICED_VERTEX)
 	int overlapFrontSharded = 1;       // ... also with the sharded front end (B2R_OVERLAP_FRONT_SHARDED=0 switches it off)
@@ -732,7 +731,7 @@ int enqueueFrame(b2r_context* c)
 	const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (clearMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
 	CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(clearCtas), dim3(256), 0, fs, tileCount, tiles, B.counters, B.frameInfo, (uint32_t)kInfoWords,
 		kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
-		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes, (uint4*)nullptr, 0u, PeerFlags{}, 0u, 0u, 0u));
+		slot.hViewProj, c->dMeshStatic.ptr, meshConst, clearMeshes, PeerFlags{}, 0u, 0u, 0u));
 	++c->kernelsLaunched;
 
 	if (c->nVsChunks && !overlap)
@@ -941,12 +940,9 @@ int enqueueFrameRing(b2r_context* c)
 		primLo = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)sh.self / (uint64_t)sh.n * kChunk);
 		primHi = (uint32_t)std::min<uint64_t>(c->nPrims, blocks * (uint64_t)(sh.self + 1) / (uint64_t)sh.n * kChunk);
 	}
-	// sliced vertex stage (sharded only): this rank transforms the vertex chunks its primitive slice refers to before it
-	// bins, and - after the exchange - the vertices the lists of its own tiles refer to (shard_mark_vertices_kernel,
-	// vertex_transform_marked_kernel)
+	// sliced vertex stage (sharded only): this rank transforms only the vertex chunks its primitive slice refers to; its
+	// raster kernel (OTF instantiation) transforms the vertices of its list entries and of its pixels' winners itself
 	const bool sliced = sh.bound && c->slicedVertex;
-	const uint32_t markQuads = sliced ? (uint32_t)((c->nVtxOut + 15) / 16) : 0u;
-	if (sliced) CU(c, c->dVertexMarks[k].reserve(std::max<size_t>(markQuads, 1), s));
 	if (sliced && !sh.rangeValid)
 	{
 		sh.chunkLo = sh.chunkHi = 0;
@@ -1015,7 +1011,7 @@ int enqueueFrameRing(b2r_context* c)
 		const uint32_t clearCtas = std::min<uint32_t>(std::max<uint32_t>((tiles + 4095) / 4096, (nMeshes + 255) / 256), (uint32_t)c->numSMs * 4);
 		CU(c, launchFrameKernel(c, frame_clear_kernel, dim3(std::max<uint32_t>(clearCtas, 1u)), dim3(256), 0, rs, tileCount, tiles, B.counters, B.frameInfo, (uint32_t)kInfoWords,
 			kScanBase + 2u * ((tiles + kScanPerCta - 1) / kScanPerCta),
-			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes, sliced ? c->dVertexMarks[k].ptr : (uint4*)nullptr, markQuads,
+			slot.hViewProj, c->dMeshStatic.ptr, meshConst, nMeshes,
 			pf, (uint32_t)sh.self, (sh.bound && sh.frame >= (uint32_t)D) ? (uint32_t)sh.n : 0u, sh.frame - (uint32_t)D + 1u));
 		++c->kernelsLaunched;
 		const uint32_t cLo = sliced ? sh.chunkLo : 0u, cHi = sliced ? sh.chunkHi : c->nVsChunks;
@@ -1372,7 +1368,6 @@ void b2r_destroy(b2r_context* c)
 		if (c->ringRasterDone[i]) cudaEventDestroy(c->ringRasterDone[i]);
 	}
 	cudaFree(c->dRangeScratch);
-	for (auto& v : c->dVertexMarks) v.release();
 	for (int i = 0; i < 2; ++i) { if (c->vtxDone[i]) cudaEventDestroy(c->vtxDone[i]); if (c->frontDone[i]) cudaEventDestroy(c->frontDone[i]); if (c->rasterDone[i]) cudaEventDestroy(c->rasterDone[i]); if (c->listsReady[i]) cudaEventDestroy(c->listsReady[i]); }
 	for (auto& t : c->textures) if (t.alive) cudaFree(t.px);
 	c->dIVertex.release(); c->dIndices.release(); c->dPosIn.release(); for (auto& v : c->dPos4) v.release(); c->dOvertexScratch.release();

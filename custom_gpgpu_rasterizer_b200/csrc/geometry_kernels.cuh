@@ -102,28 +102,6 @@ __global__ void __launch_bounds__(kChunk) vertex_transform_kernel(
 		if (threadIdx.x < count[k]) pos4[(size_t)outStart[k] + threadIdx.x] = transformPosition(sMat[k], in[k].x, in[k].y, in[k].z);
 }
 
-// sharded front end with a sliced vertex stage: the vertices shard_mark_vertices_kernel marked for this rank's raster
-// kernel (one byte per transformed vertex), chunks [skipLo, skipHi) excepted - the rank's own slice, transformed before
-// binning.  Same function, same bits as vertex_transform_kernel.
-__global__ void __launch_bounds__(kChunk) vertex_transform_marked_kernel(
-	const Chunk* __restrict__ chunks, const MeshConst* __restrict__ meshes, const float4* __restrict__ posIn, float4* __restrict__ pos4,
-	const uint8_t* __restrict__ marks, uint32_t skipLo, uint32_t skipHi, const unsigned long long* __restrict__ frameInfo)
-{
-	pdlPrologue();
-	if (frameInfo[1]) return;
-	if (blockIdx.x >= skipLo && blockIdx.x < skipHi) return;
-	__shared__ float sMat[16];
-	const Chunk ch = chunks[blockIdx.x];
-	const uint32_t v = ch.outStart + threadIdx.x;
-	const bool want = threadIdx.x < ch.count && __ldg(marks + v) != 0;
-	if (!__syncthreads_or(want)) return;
-	if (threadIdx.x < 16) sMat[threadIdx.x] = meshes[ch.mesh].wvp[threadIdx.x];
-	float4 in = make_float4(0.f, 0.f, 0.f, 1.f);
-	if (want) in = __ldg(posIn + (size_t)ch.inStart + threadIdx.x);
-	__syncthreads();
-	if (want) pos4[v] = transformPosition(sMat, in.x, in.y, in.z);
-}
-
 // sharded front end with a sliced vertex stage: the range of transformed-vertex indices the primitives
 // [primLo, primHi) refer to (static: evaluated once per scene and slice).  out[0] = min (preset to 0xFFFFFFFF), out[1] = max (preset to 0)
 __global__ void __launch_bounds__(256) prim_vertex_range_kernel(const uint4* __restrict__ triRefs, uint32_t primLo, uint32_t primHi, uint32_t* __restrict__ out)
@@ -289,13 +267,11 @@ __device__ __forceinline__ void peerFlagsWait(PeerFlags pf, uint32_t self, uint3
 __global__ void __launch_bounds__(256) frame_clear_kernel(uint32_t* __restrict__ tileCount, uint32_t nTiles,
 	uint32_t* __restrict__ counters, unsigned long long* __restrict__ frameInfo, uint32_t infoWords, uint32_t counterWords,
 	const float* __restrict__ hostViewProj, const MeshStatic* __restrict__ meshStatic, MeshConst* __restrict__ meshConst, uint32_t nMeshes,
-	uint4* __restrict__ marks /*vertex marks of the sliced vertex stage, or null*/, uint32_t markQuads,
 	const __grid_constant__ PeerFlags waitPf, uint32_t waitSelf, uint32_t waitRanks /*0: no wait*/, uint32_t waitEpoch)
 {
 	pdlPrologue();
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	buildMeshConsts(gtid, gsize, hostViewProj, meshStatic, meshConst, nMeshes);
-	for (uint32_t i = gtid; i < markQuads; i += gsize) marks[i] = make_uint4(0, 0, 0, 0);
 	const uint32_t q = (nTiles + 3) / 4;
 	for (uint32_t i = gtid; i < q; i += gsize)
 		reinterpret_cast<uint4*>(tileCount)[i] = make_uint4(0, 0, 0, 0);

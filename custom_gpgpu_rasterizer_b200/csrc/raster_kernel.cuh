@@ -1025,33 +1025,6 @@ __global__ void __launch_bounds__(256) shard_merge_heads_kernel(const __grid_con
 	}
 }
 
-// Sharded front end with a sliced vertex stage: a rank transforms the vertices its own primitive slice refers to before
-// it bins them, and - here, once the lists of its tiles have arrived - marks the vertices its RASTER kernel will need
-// (the three vertices of every entry of every owned tile's list) in a byte map over the transformed-vertex stream
-// (plain idempotent stores: neighbouring triangles share their vertices, a bit map would need contended atomics);
-// vertex_transform_marked_kernel then transforms exactly those.  With n ranks and interleaved tile ownership that is
-// about 1/n of the front-facing vertices instead of all vertices on every rank.  One warp per owned tile.
-__global__ void __launch_bounds__(256) shard_mark_vertices_kernel(const __grid_constant__ ShardTable T, uint32_t nTiles, uint32_t rank, uint32_t nRanks,
-	const uint4* __restrict__ triRefs, uint8_t* __restrict__ marks, const unsigned long long* __restrict__ frameInfo)
-{
-	pdlPrologue();
-	if (frameInfo[1]) return;
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t tile = rank + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * nRanks;
-	if (tile >= nTiles) return;
-	for (uint32_t p = 0; p < nRanks; ++p)
-	{
-		const uint32_t cnt = __ldg(T.tileCount[p] + tile);
-		if (!cnt) continue;
-		const uint32_t* seg = T.binIds[p] + __ldg(T.tileOffset[p] + tile);
-		for (uint32_t e = lane; e < cnt; e += 32)
-		{
-			const uint4 tr = __ldg(triRefs + __ldg(seg + e));
-			marks[tr.x] = 1; marks[tr.y] = 1; marks[tr.z] = 1;
-		}
-	}
-}
-
 // CUDARenderer::DrawTexture / DrawTextureGlobal (testing aids of the reference, CUDARenderer.cu:1565-1620, 1968-2012): the
 // texture stretched over the window (or texel-for-pixel), no geometry.  global = 0: TextureTestKernel - the texel CUDA's
 // point filter returns for normalised (x / width, y / height), bytes 0 and 2 swapped, alpha kept; global = 1:

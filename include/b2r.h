@@ -84,7 +84,7 @@ enum
 	 * before it stores into the peers' list sets.  Default 1. */
 	B2R_OPT_OVERLAP_FRONT = 11,
 	/* frame ring, the alternative to the two options above (EXPERIMENTAL in round 1: written after the round's GPU budget
-	 * was spent, default 0 = off; also B2R_FRAME_RING=D in the environment).  Value D = 2..8: frame f runs from its
+	 * was spent, default 0 = off; also B2R_FRAME_RING=D in the environment).  Value D = 2..4: frame f runs from its
 	 * constants to its raster kernel on ring stream f % D and owns slot f % D of everything a frame writes, so the
 	 * geometry front ends of up to D consecutive frames are in flight at once; only the raster kernels are chained in
 	 * frame order.  Meant for the sharded front end (b2r_shard_*), where a rank's front end is a chain of short

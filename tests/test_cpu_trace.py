@@ -150,7 +150,7 @@ def test_every_element_of_the_flag_protocol_is_load_bearing(sharded_logs, world,
         def no_done_wait(line):
             if '"launch"' in line and "frame_clear_kernel" in line:
                 o = json.loads(line)
-                o["args"][14] = "00000000"
+                o["args"][12] = "00000000"
                 return json.dumps(o) + "\n"
             return line
         p = tmp_path / "mutated.jsonl"

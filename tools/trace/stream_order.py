@@ -183,8 +183,6 @@ class Trace:
         "frame_clear_kernel": {"tileCount": 0, "counters": 2, "frameInfo": 3, "hViewProj": 6, "meshStatic": 7, "meshConst": 8},
         "build_constants_kernel": {"hViewProj": 0, "meshStatic": 1, "meshConst": 2},
         "vertex_transform_kernel": {"meshConst": 2, "posIn": 3, "pos4": 4},
-        "vertex_transform_marked_kernel": {"meshConst": 1, "posIn": 2, "pos4": 3, "frameInfo": 7},
-        "shard_mark_vertices_kernel": {"triRefs": 4, "frameInfo": 6},
         "triangle_setup_kernel": {"triRefs": 0, "pos4": 1, "rects": 2, "tileCount": 3, "bigList": 4, "counters": 5, "binSlots": 6, "keys": 7, "dirty": 8, "frameInfo": 9},
         "bin_big_count_kernel": {"bigList": 0, "counters": 1, "rects": 2, "tileCount": 3},
         "tile_scan_kernel": {"tileCount": 0, "tileOffset": 1, "tileCursor": 2, "longTiles": 6, "tileOrder": 7, "dirty": 8, "counters": 11, "frameInfo": 14},
@@ -389,10 +387,10 @@ class Trace:
                             signals[(8, epoch)].append(n)
                         if done_ranks:
                             signals[(16, epoch)].append(n)
-                    if op == "launch" and label == "frame_clear_kernel" and len(o["args"]) > 15 and u32(o["args"][14]):
+                    if op == "launch" and label == "frame_clear_kernel" and len(o["args"]) > 13 and u32(o["args"][12]):
                         # frame ring + sharded front end: block 0 of the clear kernel ends with the one-way wait for the
                         # peers' "frame done" of the frame that used this ring slot before (wait ranks, wait epoch)
-                        waiters[(16, u32(o["args"][15]))].append(n)
+                        waiters[(16, u32(o["args"][13]))].append(n)
                 last_on_stream[skey] = n
                 if op == "memcpy" and not o["async"]:
                     host_node("blocking copy", [n], dev)
