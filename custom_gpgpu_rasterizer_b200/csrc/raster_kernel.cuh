@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 		if (c0 + step < nChunks && primOf(c0 + step) < primHi) cpAsync16(&sRef[1][tid], triRefs + primOf(c0 + step));
 		cpAsyncCommit();
 	}
-	uint32_t nFrags = 0;
+	uint32_t nFrags = 0, visAcc = 0;
+	unsigned long long directAcc = 0ull;
 	uint32_t it = 0;
 	for (uint32_t chunk = firstChunk; chunk < nChunks; chunk += step, ++it)
 	{
@@ -205,17 +206,12 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 			if (prim < primHi)
 			{
 				visible = true;
-				if (fp.cullMode != 2u)
+				if ((fp.cullMode & 0xFFu) != 2u)
 				{
 					const float ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
 					const float bx = p2.x - p0.x, by = p2.y - p0.y, bz = p2.z - p0.z;
-					float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
-					normalize3(nx, ny, nz);
-					// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
-					const float d = (fp.cullMode == 0u)
-						? fmaf(nz, fp.camFwd[2], fmaf(nx, fp.camFwd[0], ny * fp.camFwd[1]))
-						: fmaf(nz, fp.camFwd[2], fmaf(ny, fp.camFwd[1], nx * fp.camFwd[0]));
-					if (d <= 0.f) visible = false;   // live FrontFace branch uses the same test (CUDARenderer.cu:773)
+					const float nx = diff2(ay, bz, az, by), ny = diff2(az, bx, ax, bz), nz = diff2(ax, by, ay, bx);
+					if (backFace(nx, ny, nz, fp.camFwd, fp.cullMode)) visible = false;
 				}
 				if (visible)
 				{
@@ -276,17 +272,9 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 				nRec = (uint32_t)__popc(m);
 				if (record) sRec[warp * 32u + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
 			}
-			// statistics: one atomic per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
-			{
-				const unsigned vis = __ballot_sync(0xFFFFFFFFu, visible);
-				uint32_t* slot = &counters[kVisBase + (chunk % kVisSlots) * 32];
-				if (lane == 0 && vis) atomicAdd(slot, (uint32_t)__popc(vis));
-				if (DIRECT)
-				{
-					const uint32_t dt = __reduce_add_sync(0xFFFFFFFFu, min(directTiles, 0x00FFFFFFu));      // (a rectangle has at most 2^22 tiles)
-					if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, (unsigned long long)dt);
-				}
-			}
+			// statistics of the group, accumulated per warp and flushed once when the warp is done
+			visAcc += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, visible));
+			if (DIRECT) directAcc += min(directTiles, 0x00FFFFFFu);      // per lane (a rectangle has at most 2^22 tiles)
 			// per-tile counts, warp-aggregated
 			if (nTiles > fp.bigRectTiles)
 			{
@@ -360,6 +348,18 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 			}
 		}
 		__syncwarp();                      // every lane is done with the records before the next group's are written
+	}
+	// statistics: a few atomics per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+	{
+		uint32_t* slot = &counters[kVisBase + (firstChunk % kVisSlots) * 32];
+		if (lane == 0 && visAcc) atomicAdd(slot, visAcc);
+		if (DIRECT)
+		{
+			unsigned long long dt = directAcc;
+			#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) dt += __shfl_down_sync(0xFFFFFFFFu, dt, d);
+			if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, dt);
+		}
 	}
 	if (DIRECT && fp.countFragments)
 	{
