@@ -124,3 +124,7 @@ class B2RError(RuntimeError):
 # test hook: hoisted division of the raster kernel vs __fdiv_rn
 lib.b2r_selftest_division.restype = _i32
 lib.b2r_selftest_division.argtypes = [_i32, _u64, _u32, _u64p]
+# test hook: sign-only back-face test of the setup kernel vs the reference's normalise + dot (counts[0] = disagreements,
+# counts[1] = cases the short cut decided)
+lib.b2r_selftest_cull.restype = _i32
+lib.b2r_selftest_cull.argtypes = [_i32, _u64, _u32, _u64p]

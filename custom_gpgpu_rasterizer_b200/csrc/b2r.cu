@@ -426,7 +426,10 @@ FrameParams makeParams(const b2r_context* c, const RenderCall& rc)
 	fp.subXMagic = fp.subX > 1 ? (uint32_t)(0x100000000ull / fp.subX) : 0u;
 	auto log2OrMinus1 = [](uint32_t v) { int s = 0; while ((1u << s) < v) ++s; return (1u << s) == v ? s : -1; };
 	fp.binShiftX = log2OrMinus1(c->binW); fp.binShiftY = log2OrMinus1(c->binH);
-	fp.cullMode = (uint32_t)rc.cull; fp.sampleState = (uint32_t)rc.sample; fp.visState = (uint32_t)rc.vis;
+	fp.cullMode = (uint32_t)rc.cull;
+	// the sign-only back-face test (geometry_kernels.cuh backFace) is proven for camera-forward components of at most 2^20
+	if (std::fabs(rc.camFwd[0]) <= 1048576.f && std::fabs(rc.camFwd[1]) <= 1048576.f && std::fabs(rc.camFwd[2]) <= 1048576.f) fp.cullMode |= kCullFastOk;
+	fp.sampleState = (uint32_t)rc.sample; fp.visState = (uint32_t)rc.vis;
 	fp.fillTopLeft = (uint32_t)c->fillTopLeft;
 	fp.ownerRank = (uint32_t)c->ownerRank; fp.ownerCount = (uint32_t)c->ownerCount;
 	fp.debugSurfaces = (uint32_t)c->debugSurfaces;
@@ -1261,8 +1264,80 @@ __global__ void division_selftest_kernel(unsigned long long nPairs, uint32_t see
 	if (bad) atomicAdd(mismatches, bad);
 }
 
+// ---- self test: the sign-only back-face test of geometry_kernels.cuh against the reference's arithmetic --------------
+// Operands are drawn to sit where the short cut could go wrong: dot products within a few ulp of zero (the normal is
+// built perpendicular to the camera axis and then nudged), normals from 2^-70 to 2^70 (both sides of the magnitude
+// guard), zero / subnormal components, axis-aligned and non-unit camera axes up to the 2^20 the host admits, and
+// NaN / Inf.  out[0] counts disagreements, out[1] the cases the short cut decided.
+__global__ void cull_selftest_kernel(unsigned long long nCases, uint32_t seed, unsigned long long* out)
+{
+	unsigned long long bad = 0, fast = 0;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nCases; i += (unsigned long long)gridDim.x * blockDim.x)
+	{
+		uint32_t h[8];
+		h[0] = hash32((uint32_t)i ^ seed);
+		for (int k = 1; k < 8; ++k) h[k] = hash32(h[k - 1] + (uint32_t)(i >> 32) + 0x9E3779B9u * (uint32_t)k + 0x85EBCA6Bu * seed);      // (h[0] alone visits the same 2^32 values for every seed)
+		auto unit = [](uint32_t x) { return (float)(x >> 8) * (1.f / 8388608.f) - 1.f; };      // [-1, 1)
+		// camera axis
+		float c[3] = { unit(h[0]), unit(h[1]), unit(h[2]) };
+		const uint32_t cKind = h[3] & 7u;
+		if (cKind == 0u) { c[0] = 0.f; c[1] = 0.f; c[2] = (h[3] & 8u) ? 1.f : -1.f; }
+		else if (cKind == 1u) c[(h[3] >> 4) % 3u] = 0.f;
+		else if (cKind == 2u) { const float k = __uint_as_float((127u + (h[3] >> 4) % 20u) << 23); c[0] *= k; c[1] *= k; c[2] *= k; }
+		else if (cKind == 3u) { const float k = __uint_as_float((127u - (h[3] >> 4) % 40u) << 23); c[0] *= k; c[1] *= k; c[2] *= k; }
+		else { float x = c[0], y = c[1], z = c[2]; normalize3(x, y, z); c[0] = x; c[1] = y; c[2] = z; }
+		// normal
+		float n[3] = { unit(h[4]), unit(h[5]), unit(h[6]) };
+		const uint32_t nKind = h[7] & 7u;
+		if (nKind <= 3u)
+		{
+			// perpendicular to c up to rounding, then nudged by 0 .. 2^-12 of c
+			const float cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2], nc = n[0] * c[0] + n[1] * c[1] + n[2] * c[2];
+			const float k = cc > 0.f ? nc / cc : 0.f;
+			const float nudge = (nKind == 0u) ? 0.f : unit(h[7] >> 3 | h[6] << 29) * __uint_as_float((127u - 12u - (h[7] >> 8) % 24u) << 23);
+			for (int a = 0; a < 3; ++a) n[a] = fmaf(-k + nudge, c[a], n[a]);
+		}
+		else if (nKind == 4u) n[(h[7] >> 4) % 3u] = 0.f;
+		else if (nKind == 5u) { n[(h[7] >> 4) % 3u] = 0.f; n[(h[7] >> 6) % 3u] = 0.f; }
+		// magnitude 2^-70 .. 2^70, mostly the 2^-30 .. 2^0 of real cross products
+		const int e = (h[7] & 0x100u) ? -(int)((h[7] >> 9) % 31u) : (int)((h[7] >> 9) % 141u) - 70;
+		const float scale = __uint_as_float((uint32_t)(127 + e) << 23);
+		for (int a = 0; a < 3; ++a) n[a] *= scale;
+		if ((h[7] >> 20) % 4096u == 0u) n[(h[7] >> 4) % 3u] = __uint_as_float(0x7FC00000u);         // NaN
+		if ((h[7] >> 20) % 4096u == 1u) n[(h[7] >> 4) % 3u] = __uint_as_float(0x7F800000u);         // Inf
+		if ((h[7] >> 20) % 4096u == 2u) n[(h[7] >> 4) % 3u] = __uint_as_float(h[6] & 0x7FFFFFu);    // subnormal
+		const bool admitted = fabsf(c[0]) <= 1048576.f && fabsf(c[1]) <= 1048576.f && fabsf(c[2]) <= 1048576.f;      // makeParams
+		#pragma unroll
+		for (uint32_t mode = 0; mode < 2; ++mode)
+		{
+			const bool a = backFace(n[0], n[1], n[2], c, mode | (admitted ? kCullFastOk : 0u));
+			const bool b = backFaceExact(n[0], n[1], n[2], c, mode);
+			if (a != b) ++bad;
+		}
+		bool back;
+		if (admitted && backFaceCertain(n[0], n[1], n[2], c, back)) ++fast;
+	}
+	if (bad) atomicAdd(&out[0], bad);
+	if (fast) atomicAdd(&out[1], fast);
+}
+
 // =======================================================================================
 extern "C" {
+
+// test hook (not part of include/b2r.h): the sign-only back-face test against the exact one on nCases pseudo-random
+// adversarial (normal, camera axis) pairs; counts[0] = disagreements, counts[1] = cases the short cut decided
+int b2r_selftest_cull(int device, unsigned long long nCases, uint32_t seed, unsigned long long counts[2])
+{
+	if (!counts) return B2R_E_INVALID;
+	if (cudaSetDevice(device) != cudaSuccess) return B2R_E_NO_DEVICE;
+	unsigned long long* d = nullptr;
+	if (cudaMalloc((void**)&d, 16) != cudaSuccess) return B2R_E_CUDA;
+	cudaMemset(d, 0, 16);
+	cull_selftest_kernel<<<148 * 8, 256>>>(nCases, seed, d);
+	cudaError_t e = cudaMemcpy(counts, d, 16, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return e == cudaSuccess ? B2R_OK : B2R_E_CUDA;
+}
 
 // test hook (not part of include/b2r.h): bit-compares the raster kernel's hoisted division with
 // __fdiv_rn on nPairs pseudo-random operand pairs; returns the number of mismatches

@@ -34,6 +34,56 @@ __device__ __forceinline__ void normalize3(float& x, float& y, float& z)
 	x = x * inv; y = y * inv; z = z * inv;
 }
 
+// Back-face test of TA_Kernel (CUDARenderer.cu:760-777): d = dot(normalize(n), camFwd), the triangle is culled when
+// d <= 0.  Only the SIGN of d is used, so the IEEE square root and reciprocal of the normalisation are skipped whenever
+// the sign is certain without them, and the reference's arithmetic (`exact` below) runs only for the rest.
+//
+// Why the short cut returns the same answer.  Write u = 2^-24, L = |n|, S = sum n_i c_i, T = sum |n_i c_i|,
+// M = sum |n_i|.  Under the guard (kCullFastOk: every |c_i| <= 2^20, set by the host; 2^-40 < M < 2^40):
+//  * the squared length lies in (2^-84, 2^82) - no overflow, squares that underflow change it by < 2^-65 relative - so the
+//    reference's m = sqrt_rn(len2) and inv = rcp_rn(m) carry relative errors <= 2u and <= 3.5u, and its normalised
+//    components are n_i / L * (1 + e_i), |e_i| <= 4.5u, or within 2^-150 of that when the product is subnormal;
+//  * its d is three roundings away from sum nhat_i c_i, so d_ref = (1 / L) * sum n_i c_i (1 + k_i) + E with |k_i| <= 8u
+//    and |E| <= 2^-127 (underflows, times |c_i| <= 2^20);
+//  * the S computed here differs from the exact S by <= 3u T + 2^-147.
+// With |S_computed| > 64u T (the 2^-18 below) the exact S has the sign of the computed one and |S| > 60u T, so the
+// reference's numerator sum n_i c_i (1 + k_i) has that sign too and magnitude > 52u T; and |S| >= 2^-60 M together with
+// L <= M puts |d_ref| above 2^-61, far above E and the subnormal range: d_ref is a non-zero number of the sign of S.
+// Anything else - zero-length or huge normals, NaN / Inf operands (every comparison below is false for them), a dot
+// product within rounding of 0 - takes the exact path.  tests/test_gpu_units.py::test_sign_only_cull_matches_the_exact_test
+// compares the two on 2^32 adversarial triangles per seed.
+constexpr uint32_t kCullFastOk = 0x100u;      // bit of FrameParams::cullMode
+#ifndef B2R_CULL_MARGIN
+#define B2R_CULL_MARGIN 3.814697265625e-6f      // 2^-18 = 64u (a build with 2^-25 fails the self test: the test does reach the boundary)
+#endif
+__device__ __forceinline__ bool backFaceExact(float nx, float ny, float nz, const float* c, uint32_t cull)
+{
+	normalize3(nx, ny, nz);
+	// the two culling branches of TA_Kernel were contracted differently (SASS @0x06f0 / @0x0aa0)
+	const float d = (cull == 0u) ? fmaf(nz, c[2], fmaf(nx, c[0], ny * c[1]))
+	                             : fmaf(nz, c[2], fmaf(ny, c[1], nx * c[0]));
+	return d <= 0.f;                // the live FrontFace branch uses the same test (CUDARenderer.cu:773)
+}
+// the short cut: true when the sign of the reference's d is certain (then `back` is the answer)
+__device__ __forceinline__ bool backFaceCertain(float nx, float ny, float nz, const float* c, bool& back)
+{
+	const float S = fmaf(nz, c[2], fmaf(nx, c[0], ny * c[1]));
+	const float T = fmaf(fabsf(nz), fabsf(c[2]), fmaf(fabsf(nx), fabsf(c[0]), fabsf(ny) * fabsf(c[1])));
+	const float M = fabsf(nx) + fabsf(ny) + fabsf(nz);
+	const float aS = fabsf(S);
+	back = S < 0.f;
+	return aS > T * B2R_CULL_MARGIN && aS >= M * 8.673617379884035e-19f /*2^-60*/ &&
+		M > 9.094947017729282e-13f /*2^-40*/ && M < 1.099511627776e12f /*2^40*/;
+}
+__device__ __forceinline__ bool backFace(float nx, float ny, float nz, const float* c, uint32_t cullMode)
+{
+#ifndef B2R_EXACT_CULL_ONLY
+	bool back;
+	if ((cullMode & kCullFastOk) != 0u && backFaceCertain(nx, ny, nz, c, back)) return back;
+#endif
+	return backFaceExact(nx, ny, nz, c, cullMode & 0xFFu);
+}
+
 // ---------------------------------------------------------------------------------------
 // upload-time: pull the positions out of the 56 B AoS records into a 16 B stream, so the per-frame
 // transform reads 16 B per vertex instead of dragging the whole record through the memory system

@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 	pdlPrologue();
 	__shared__ __align__(16) uint4 sRef[2][kChunk];              // vertex references of chunks i+1 / i+2
 	__shared__ __align__(16) float4 sPos[2][3][kChunk];          // positions of chunks i / i+1
-	__shared__ __align__(16) DirectRecord sRec[DIRECT ? kChunk : 1];      // 32 per warp
+	__shared__ __align__(16) DirectRecord sRec[DIRECT ? kChunk : 1];      // one slot per thread, written by the thread itself
+	__shared__ uint8_t sRecLane[DIRECT ? kChunk : 1];                      // per warp: the lanes that left a record, compacted
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t nChunks = (primHi - primLo + 31u) / 32u;        // ("chunk" = a warp's group of 32 primitives)
 	const uint32_t firstChunk = blockIdx.x * (kChunk / 32) + warp;
@@ -159,20 +160,35 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 	// pipeline fill (the step is gridDim.x chunks, and a chunk's buffers are chosen by the parity of its POSITION in this
 	// CTA's sequence, not of its index)
 	const uint32_t step = gridDim.x * (kChunk / 32);
+	const SmemAddr aRef = smemAddress(&sRef[0][tid]), aPos = smemAddress(&sPos[0][0][tid]);      // this thread's slots: + buffer / vertex strides
+	constexpr uint32_t kRefBuf = kChunk * (uint32_t)sizeof(uint4), kPosVtx = kChunk * (uint32_t)sizeof(float4), kPosBuf = 3u * kPosVtx;
 	{
 		const uint32_t c0 = firstChunk;
-		if (primOf(c0) < primHi) cpAsync16(&sRef[0][tid], triRefs + primOf(c0));
+		if (primOf(c0) < primHi) cpAsync16(aRef, triRefs + primOf(c0));
 		cpAsyncCommit(); cpAsyncWaitAll();
 		if (primOf(c0) < primHi)
 		{
 			const uint4 tr = sRef[0][tid];
-			cpAsync16(&sPos[0][0][tid], pos4 + tr.x); cpAsync16(&sPos[0][1][tid], pos4 + tr.y); cpAsync16(&sPos[0][2][tid], pos4 + tr.z);
+			cpAsync16(aPos, pos4 + tr.x); cpAsync16(aPos + kPosVtx, pos4 + tr.y); cpAsync16(aPos + 2u * kPosVtx, pos4 + tr.z);
 		}
-		if (c0 + step < nChunks && primOf(c0 + step) < primHi) cpAsync16(&sRef[1][tid], triRefs + primOf(c0 + step));
+		if (c0 + step < nChunks && primOf(c0 + step) < primHi) cpAsync16(aRef + kRefBuf, triRefs + primOf(c0 + step));
 		cpAsyncCommit();
 	}
-	uint32_t nFrags = 0, visAcc = 0;
-	unsigned long long directAcc = 0ull;
+	uint32_t nFrags = 0, visAcc = 0, directAcc = 0;
+	// statistics: a few atomics per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
+	auto flushStatistics = [&]()
+	{
+		uint32_t* slot = &counters[kVisBase + (firstChunk % kVisSlots) * 32];
+		if (lane == 0 && visAcc) atomicAdd(slot, visAcc);
+		if (DIRECT)
+		{
+			unsigned long long dt = directAcc;
+			#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) dt += __shfl_down_sync(0xFFFFFFFFu, dt, d);
+			if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, dt);
+		}
+		visAcc = 0; directAcc = 0;
+	};
 	uint32_t it = 0;
 	for (uint32_t chunk = firstChunk; chunk < nChunks; chunk += step, ++it)
 	{
@@ -190,9 +206,10 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 			if (c1 < nChunks && primOf(c1) < primHi)
 			{
 				const uint4 tr = sRef[nxt][tid];
-				cpAsync16(&sPos[nxt][0][tid], pos4 + tr.x); cpAsync16(&sPos[nxt][1][tid], pos4 + tr.y); cpAsync16(&sPos[nxt][2][tid], pos4 + tr.z);
+				const SmemAddr aNxt = aPos + nxt * kPosBuf;
+				cpAsync16(aNxt, pos4 + tr.x); cpAsync16(aNxt + kPosVtx, pos4 + tr.y); cpAsync16(aNxt + 2u * kPosVtx, pos4 + tr.z);
 			}
-			if (c2 < nChunks && primOf(c2) < primHi) cpAsync16(&sRef[cur][tid], triRefs + primOf(c2));
+			if (c2 < nChunks && primOf(c2) < primHi) cpAsync16(aRef + cur * kRefBuf, triRefs + primOf(c2));
 			cpAsyncCommit();
 
 			// ---- phase A: setup of primitive prim0
@@ -202,7 +219,6 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 			int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
 			uint32_t nTiles = 0, directTiles = 0;
 			bool record = false;
-			DirectRecord rec;
 			if (prim < primHi)
 			{
 				visible = true;
@@ -250,10 +266,13 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 								nTiles = 0;
 								if (area)
 								{
+									// the record goes straight into the thread's own slot (three 16-byte stores: a DirectRecord
+									// assembled in a local variable and copied after the vote lived in local memory)
 									record = true;
-									rec.x0 = r.x0; rec.y0 = r.y0; rec.x1 = r.x1; rec.y1 = r.y1; rec.x2 = r.x2; rec.y2 = r.y2;
-									rec.z0 = r.z0; rec.z1 = r.z1; rec.z2 = r.z2;
-									rec.prim = prim; rec.boxX = (uint32_t)x0 | ((uint32_t)x1 << 16); rec.boxY = (uint32_t)y0 | ((uint32_t)y1 << 16);
+									float4* q = reinterpret_cast<float4*>(&sRec[tid]);
+									q[0] = make_float4(r.x0, r.y0, r.x1, r.y1);
+									q[1] = make_float4(r.x2, r.y2, r.z0, r.z1);
+									q[2] = make_float4(r.z2, __uint_as_float(prim), __uint_as_float((uint32_t)x0 | ((uint32_t)x1 << 16)), __uint_as_float((uint32_t)y0 | ((uint32_t)y1 << 16)));
 								}
 							}
 						}
@@ -267,14 +286,16 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 			}
 			if (DIRECT)
 			{
-				// compaction into the warp's slice of the record buffer
+				// compaction of the lanes that left a record
 				const unsigned m = __ballot_sync(0xFFFFFFFFu, record);
 				nRec = (uint32_t)__popc(m);
-				if (record) sRec[warp * 32u + (uint32_t)__popc(m & ((1u << lane) - 1u))] = rec;
+				if (record) sRecLane[warp * 32u + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint8_t)lane;
 			}
-			// statistics of the group, accumulated per warp and flushed once when the warp is done
+			// statistics of the group, accumulated per warp and flushed when the warp is done (and every 64 groups, so that
+			// a lane's 32-bit sum of rectangles of at most 2^22 tiles cannot wrap)
 			visAcc += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, visible));
-			if (DIRECT) directAcc += min(directTiles, 0x00FFFFFFu);      // per lane (a rectangle has at most 2^22 tiles)
+			if (DIRECT) directAcc += min(directTiles, 0x00FFFFFFu);
+			if ((it & 63u) == 63u) flushStatistics();
 			// per-tile counts, warp-aggregated
 			if (nTiles > fp.bigRectTiles)
 			{
@@ -302,13 +323,13 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 		__syncwarp();
 		if (nRec)
 		{
-			// lanes per record: the largest power of two <= 32 / records
-			const uint32_t shareLog = 31u - (uint32_t)__clz(32u / nRec);
+			// lanes per record: the largest power of two <= 32 / records, 2^(5 - ceil(log2(records)))
+			const uint32_t shareLog = (uint32_t)__clz(nRec - 1u) - 27u;
 			const uint32_t share = 1u << shareLog;
 			const uint32_t recIdx = lane >> shareLog, first = lane & (share - 1u);
 			if (recIdx < nRec)
 			{
-				const DirectRecord& q = sRec[warp * 32u + recIdx];
+				const DirectRecord& q = sRec[warp * 32u + sRecLane[warp * 32u + recIdx]];
 				const int x0 = (int)(q.boxX & 0xFFFFu), x1 = (int)(q.boxX >> 16), y0 = (int)(q.boxY & 0xFFFFu), y1 = (int)(q.boxY >> 16);
 				const uint32_t w = (uint32_t)(x1 - x0), area = w * (uint32_t)(y1 - y0);
 				if (first < area)
@@ -326,6 +347,7 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 					t.prim = q.prim; t.zLow = 0; t.yExtent = 0;
 					const bool px = fp.binShiftX >= 0, py = fp.binShiftY >= 0;
 					const bool replicated = fp.ownerCount > 1u && !fp.shardGeometry;      // sort-first with a replicated front end: own tiles only
+					const bool tileIsBlock = fp.binShiftX == 4 && fp.binShiftY == 4 && fp.keyBlocksX == fp.binsX;
 					int y = y0, x = x0 + (int)first;
 					while (x >= x1) { x -= (int)w; ++y; }
 					for (uint32_t i = first; i < area; i += share)
@@ -333,10 +355,13 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 						Bary bc; int zi;
 						if (fragmentTest<TOPLEFT>(t, (float)x, (float)y, bc, zi))
 						{
-							const uint32_t tile = (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
+							const size_t key = keyIndex(fp.keyBlocksX, x, y);
+							// (16x16 bins on the key buffer's block grid: the tile is the key's block)
+							const uint32_t tile = tileIsBlock ? (uint32_t)(key >> 8)
+								: (uint32_t)(px ? x >> fp.binShiftX : x / (int)fp.binW) + (uint32_t)(py ? y >> fp.binShiftY : y / (int)fp.binH) * fp.binsX;
 							if (!replicated || tile % fp.ownerCount == fp.ownerRank)
 							{
-								atomicMin(keys + keyIndex(fp.keyBlocksX, x, y), ((unsigned long long)(uint32_t)zi << 32) | t.prim);
+								atomicMin(keys + key, ((unsigned long long)(uint32_t)zi << 32) | t.prim);
 								dirty[tile] = 1;
 								++nFrags;
 							}
@@ -349,18 +374,7 @@ __global__ void __launch_bounds__(kChunk, B2R_SETUP_CTAS) triangle_setup_kernel(
 		}
 		__syncwarp();                      // every lane is done with the records before the next group's are written
 	}
-	// statistics: a few atomics per warp, spread over kVisSlots padded slots (tile_scan_kernel sums them)
-	{
-		uint32_t* slot = &counters[kVisBase + (firstChunk % kVisSlots) * 32];
-		if (lane == 0 && visAcc) atomicAdd(slot, visAcc);
-		if (DIRECT)
-		{
-			unsigned long long dt = directAcc;
-			#pragma unroll
-			for (int d = 16; d > 0; d >>= 1) dt += __shfl_down_sync(0xFFFFFFFFu, dt, d);
-			if (lane == 0 && dt) atomicAdd(reinterpret_cast<unsigned long long*>(slot) + 1, dt);
-		}
-	}
+	flushStatistics();
 	if (DIRECT && fp.countFragments)
 	{
 		nFrags = __reduce_add_sync(0xFFFFFFFFu, nFrags);
@@ -488,7 +502,12 @@ __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefet
 #ifndef B2R_RASTER_FULL_CTAS
 #define B2R_RASTER_FULL_CTAS 4
 #endif
-constexpr int rasterCtasPerSM(bool textured) { return textured ? B2R_RASTER_FULL_CTAS : B2R_RASTER_LIGHT_CTAS; }
+// (the light instantiation that transforms vertices itself - sliced vertex stage of the sharded front end - spills
+// ~180 bytes at the light register budget: B2R_RASTER_OTF_CTAS lets a build trade occupancy for registers)
+#ifndef B2R_RASTER_OTF_CTAS
+#define B2R_RASTER_OTF_CTAS B2R_RASTER_LIGHT_CTAS
+#endif
+constexpr int rasterCtasPerSM(bool textured, bool otf) { return textured ? B2R_RASTER_FULL_CTAS : otf ? B2R_RASTER_OTF_CTAS : B2R_RASTER_LIGHT_CTAS; }
 
 // big triangles of the pixel-parallel path as they wait in shared memory (64 bytes; the edge vectors are rebuilt from
 // the vertices with the subtractions of expandRecord, hence the same bits)
@@ -575,7 +594,7 @@ __device__ __forceinline__ void fetchPositions(const RasterArgs& A, const uint4&
 }
 
 template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF>
-__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
+__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
 {
 	pdlPrologue();
 	__shared__ __align__(16) TriBig sBig[kListChunk];   // the pixel-parallel triangles of the block

@@ -15,6 +15,21 @@ def test_hoisted_division_is_bit_exact():
         assert bad.value == 0, f"{bad.value} of 2^30 quotients differ from div.rn (seed {seed})"
 
 
+def test_sign_only_cull_matches_the_exact_test():
+    """The setup kernel decides back faces from the sign of dot(n, camFwd) whenever that sign is certain and runs the
+    reference's arithmetic (normalise with IEEE sqrt + reciprocal, then the dot product: CUDARenderer.cu:760-777) only
+    for the rest (geometry_kernels.cuh backFace, proof in the comment there).  2^32 adversarial (normal, camera axis)
+    pairs per seed - dot products within a few ulp of zero, magnitudes on both sides of the guard, zero / subnormal /
+    NaN / Inf components - in both culling modes: no disagreement, and the short cut must decide most of them."""
+    from custom_gpgpu_rasterizer_b200._lib import lib
+    n = 1 << 32
+    for seed in (1, 2):
+        counts = (C.c_uint64 * 2)(123, 0)
+        assert lib.b2r_selftest_cull(0, n, seed, counts) == 0
+        assert counts[0] == 0, f"{counts[0]} of 2^33 back-face decisions differ from the exact test (seed {seed})"
+        assert counts[1] > n // 4, f"the short cut decided only {counts[1]} of 2^32 cases: the test does not exercise it"
+
+
 @pytest.mark.parametrize("res,grid,tess", [((640, 360), (3, 2), (101, 150)), ((320, 180), (1, 1), (201, 300)), ((1920, 1080), (6, 4), (61, 90))])
 def test_list_sort_tiers_give_canonical_lists(res, grid, tess):
     """Every sorter tier (the raster kernel's in-CTA run ordering / bitonic fallback for lists of up to 2048 entries, the long

@@ -64,6 +64,10 @@ def main(src_dir, dst_dir):
         s = s.replace('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = emuGlobalTimerNs();")
         # cp.async: a plain copy at issue time (the emulator has no asynchronous copies; commit / wait become no-ops below)
         s = s.replace('asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");', "memcpy(smemDst, gsrc, 16);")
+        # ... and its form with a converted shared-memory address: the "address" is the host pointer
+        s = s.replace('asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smemDst), "l"(gsrc) : "memory");', "memcpy((void*)smemDst, gsrc, 16);")
+        s = s.replace("typedef uint32_t SmemAddr;", "typedef uintptr_t SmemAddr;")
+        s = s.replace("return (SmemAddr)__cvta_generic_to_shared(p);", "return (SmemAddr)p;")
         s = s.replace("asm volatile(", "EMU_ASM(")
         s = s.replace("cudaFuncSetAttribute(", "emu::funcSetAttribute(")
         # MUFU.RCP: the correctly rounded reciprocal stands in for the hardware approximation; the refinement steps that follow
