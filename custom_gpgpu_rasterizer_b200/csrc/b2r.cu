@@ -467,7 +467,10 @@ cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, 
 {
 	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (otf ? 8 : 0);
 	const dim3 block(kTile * kTile);
-	const dim3 grid(blocks);
+	// measuring aid: B2R_DEBUG_RASTER_GRID clamps the grid (work items behind it are NOT rendered) - what do the CTAs cost
+	// that find no work item and leave at once?
+	static const int clamp = [] { const char* e = getenv("B2R_DEBUG_RASTER_GRID"); return e ? atoi(e) : 0; }();
+	const dim3 grid(clamp > 0 ? std::min<uint32_t>(blocks, (uint32_t)clamp) : blocks);
 #define B2R_RASTER_CASE(v, tl, cnt, tex) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, false>, grid, block, 0, s, A, fp); \
 	case v + 8: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, true>, grid, block, 0, s, A, fp);
 	switch (variant)
@@ -522,7 +525,7 @@ int enqueueKeyPush(b2r_context* c, b2r_context::BinSet& B, int set, cudaStream_t
 		P.dirtyInbox[p] = sh.dirtyInbox(sh.peerArena[p], set, sh.self);
 	}
 	const uint32_t tiles = nBins(c);
-	CU(c, launchFrameKernel(c, shard_push_keys_kernel, dim3((tiles + 7) / 8), dim3(256), 0, s, B.keys.ptr, B.dirty.ptr, P, tiles, (uint32_t)sh.self, (uint32_t)sh.n));
+	CU(c, launchFrameKernel(c, shard_push_keys_kernel, dim3(std::min<uint32_t>((tiles + 7) / 8, (uint32_t)c->numSMs * 2u)), dim3(256), 0, s, B.keys.ptr, B.dirty.ptr, P, tiles, (uint32_t)sh.self, (uint32_t)sh.n));
 	++c->kernelsLaunched;
 	return B2R_OK;
 }

@@ -604,7 +604,11 @@ constexpr uint32_t kTileClasses = 6;
 constexpr uint32_t kInfoClassBase = 8;       // frameInfo[8 .. 13]: tiles per class; frameInfo[14]: the raster kernel's work counter
 constexpr uint32_t kInfoWorkCounter = kInfoClassBase + kTileClasses;
 constexpr uint32_t kInfoDirectPairs = 5;     // frameInfo[5]: (triangle, tile) pairs of the triangles the setup kernel resolved itself (never binned)
-constexpr uint32_t kEmptyBatch = 4;          // empty tiles cleared per work item
+#ifndef B2R_EMPTY_BATCH
+#define B2R_EMPTY_BATCH 16
+#endif
+constexpr uint32_t kEmptyBatch = B2R_EMPTY_BATCH;      // empty 16x16 blocks cleared per work item (a multiple of 8: whole blocks per warp)
+static_assert(kEmptyBatch % 8u == 0u && kEmptyBatch >= 8u, "a warp of the raster kernel clears whole blocks");
 __device__ __forceinline__ uint32_t tileClass(uint32_t n)
 {
 	return n >= 1024u ? 0u : n >= 512u ? 1u : n >= 256u ? 2u : n >= 96u ? 3u : n >= 1u ? 4u : 5u;

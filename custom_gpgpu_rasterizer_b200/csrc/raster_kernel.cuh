@@ -505,7 +505,7 @@ __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefet
 // (the light instantiation that transforms vertices itself - sliced vertex stage of the sharded front end - spills
 // ~180 bytes at the light register budget: B2R_RASTER_OTF_CTAS lets a build trade occupancy for registers)
 #ifndef B2R_RASTER_OTF_CTAS
-#define B2R_RASTER_OTF_CTAS B2R_RASTER_LIGHT_CTAS
+#define B2R_RASTER_OTF_CTAS 4      // measured at 4 ranks (gpurun_out/s3_multi4): 7 429 frames/s at 4 CTAs (59 registers, no spills), 7 384 at 5, 7 151 at 6
 #endif
 constexpr int rasterCtasPerSM(bool textured, bool otf) { return textured ? B2R_RASTER_FULL_CTAS : otf ? B2R_RASTER_OTF_CTAS : B2R_RASTER_LIGHT_CTAS; }
 
@@ -643,9 +643,9 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 	};
 	// ROP write-back: row-major surface, or (sort-first) the rank's packed tile-major buffer that is
 	// gathered with one contiguous NCCL transfer / written straight into a peer's memory
-	auto storePixel = [&](uint32_t bin, uint32_t sub, size_t pix, uint32_t colour, int depthOut, float zOut, uint32_t prim)
+	auto storePixel = [&](uint32_t bin, uint32_t sub, uint32_t inBlock /*row * 16 + column*/, size_t pix, uint32_t colour, int depthOut, float zOut, uint32_t prim)
 	{
-		if (fp.packedOutput) A.framebuffer[((size_t)((bin - fp.ownerRank) / fp.ownerCount) * subs + sub) * (kTile * kTile) + tid] = colour;
+		if (fp.packedOutput) A.framebuffer[((size_t)((bin - fp.ownerRank) / fp.ownerCount) * subs + sub) * (kTile * kTile) + inBlock] = colour;
 		else A.framebuffer[pix] = colour;
 		A.depth[pix] = depthOut;
 		if (fp.debugSurfaces)
@@ -657,16 +657,33 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 	if (cls == kTileClasses - 1u)
 	{
 		// a batch of empty tiles: untouched fragments = zero-cleared PixelShade whose colour32 is the clear colour
-		// (Depth: (0-.985)/.015*255 < 0 -> 0 ; Normal: n = 0)
+		// (Depth: (0-.985)/.015*255 < 0 -> 0 ; Normal: n = 0).  A warp clears whole blocks, kEmptyBatch / 8 of them, and
+		// reads all their descriptors before the first store: the batch costs one memory round trip, not one per block
+		// (with one block after the other per CTA, a 4K frame's empty tiles took a third of this kernel's CTA-slot time)
 		const uint32_t clear = (fp.visState == 0u) ? packColour(fp.clearRGB[0], fp.clearRGB[1], fp.clearRGB[2]) : 0u;
-		for (uint32_t vb = v0; vb < v1; ++vb)
+		constexpr uint32_t kPerWarp = kEmptyBatch / (kTile * kTile / 32);
+		uint32_t bins[kPerWarp], subIdx[kPerWarp];
+		#pragma unroll
+		for (uint32_t k = 0; k < kPerWarp; ++k)
 		{
-			uint32_t sub;
-			const uint32_t bin = __ldg(&A.tileOrder[(size_t)cls * nTilesAll + divMagic(vb, subs, fp.subsMagic, sub)].x);
+			const uint32_t vb = v0 + warp + k * (kTile * kTile / 32);
+			bins[k] = kNoPrim; subIdx[k] = 0;
+			if (vb < v1) bins[k] = __ldg(&A.tileOrder[(size_t)cls * nTilesAll + divMagic(vb, subs, fp.subsMagic, subIdx[k])].x);
+		}
+		#pragma unroll
+		for (uint32_t k = 0; k < kPerWarp; ++k)
+		{
+			if (bins[k] == kNoPrim) continue;      // (warp-uniform)
 			int ox, oy, ex, ey;
-			blockRect(bin, sub, ox, oy, ex, ey);
-			const int px = ox + (tid & (kTile - 1)), py = oy + (tid >> 4);
-			if (px < ex && py < ey) storePixel(bin, sub, (size_t)px + (size_t)py * fp.width, clear, 0x7FFFFFFF, 0.f, kNoPrim);
+			blockRect(bins[k], subIdx[k], ox, oy, ex, ey);
+			const int px = ox + (int)(lane & (kTile - 1));
+			#pragma unroll
+			for (uint32_t j = 0; j < kTile / 2; ++j)
+			{
+				const uint32_t row = (lane >> 4) + 2u * j;
+				const int py = oy + (int)row;
+				if (px < ex && py < ey) storePixel(bins[k], subIdx[k], row * kTile + (lane & (kTile - 1)), (size_t)px + (size_t)py * fp.width, clear, 0x7FFFFFFF, 0.f, kNoPrim);
+			}
 		}
 		return;
 	}
@@ -977,7 +994,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 				}
 			}
 		}
-		storePixel(bin, sub, pix, colour, depthOut, zOut, prim);
+		storePixel(bin, sub, (uint32_t)tid, pix, colour, depthOut, zOut, prim);
 	}
 }
 
@@ -992,22 +1009,38 @@ __global__ void __launch_bounds__(256) shard_push_keys_kernel(unsigned long long
 	const __grid_constant__ ShardKeyPush P, uint32_t nTiles, uint32_t self, uint32_t nRanks)
 {
 	pdlPrologue();
-	const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
-	if (tile >= nTiles) return;
-	const uint32_t owner = tile % nRanks;
-	if (owner == self || dirty[tile] == 0) return;
-	uint4* src = reinterpret_cast<uint4*>(keys + ((size_t)tile << 8));
-	uint4* dst = reinterpret_cast<uint4*>(P.keyInbox[owner] + ((size_t)(tile / nRanks) << 8));
-	const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-	#pragma unroll
-	for (uint32_t i = 0; i < 4; ++i)
+	// A fixed grid of warps strides over the tiles (a CTA per 8 tiles was 4 050 short-lived CTAs on a 4K frame, ~25 us of
+	// CTA turnover for a few MB of traffic).  Warp w looks at tiles w, w + W, w + 2 W, ...: lane l reads the map byte of
+	// the l-th of them, so one load instruction covers 32 of the warp's tiles, and the touched ones - neighbours on the
+	// screen, hence spread over different warps by the stride - are pushed by the whole warp one after the other.
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t W = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	for (uint32_t k0 = 0; (unsigned long long)w + (unsigned long long)k0 * W < nTiles; k0 += 32u)
 	{
-		const uint4 v = src[i * 32u + lane];
-		dst[i * 32u + lane] = v;
-		src[i * 32u + lane] = empty;
+		const unsigned long long mine = (unsigned long long)w + (unsigned long long)(k0 + lane) * W;
+		const bool push = mine < nTiles && (uint32_t)mine % nRanks != self && dirty[mine] != 0;
+		unsigned m = __ballot_sync(0xFFFFFFFFu, push);
+		while (m)
+		{
+			const uint32_t bit = (uint32_t)__ffs((int)m) - 1u;
+			m &= m - 1u;
+			const uint32_t tile = w + (k0 + bit) * W;
+			const uint32_t owner = tile % nRanks;
+			uint4* src = reinterpret_cast<uint4*>(keys + ((size_t)tile << 8));
+			uint4* dst = reinterpret_cast<uint4*>(P.keyInbox[owner] + ((size_t)(tile / nRanks) << 8));
+			const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+			uint4 v[4];
+			#pragma unroll
+			for (uint32_t i = 0; i < 4; ++i) v[i] = src[i * 32u + lane];
+			#pragma unroll
+			for (uint32_t i = 0; i < 4; ++i)
+			{
+				dst[i * 32u + lane] = v[i];
+				src[i * 32u + lane] = empty;
+			}
+			if (lane == 0) { P.dirtyInbox[owner][tile] = 1; dirty[tile] = 0; }
+		}
 	}
-	__syncwarp();
-	if (lane == 0) { P.dirtyInbox[owner][tile] = 1; dirty[tile] = 0; }
 }
 
 // Sharded front end, after the "lists ready" barrier: the work order of this rank's raster kernel.  The length of a
