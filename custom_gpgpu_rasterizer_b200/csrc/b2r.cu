@@ -178,6 +178,7 @@ struct b2r_context
 		cudaEvent_t done = nullptr;
 		cudaEvent_t ev[10] = {};                    // 0..6 stage boundaries; sharded: 7 after pull, 8 after barrier A, 9 after raster
 		bool pending = false, timed = false, exchanged = false;
+		uint32_t rasterBlocks = 0;                  // worst-case grid of the frame's raster kernel (0: none launched)
 		bool longSkipped = false;                   // the frame was enqueued without the long-list sorter (see longLikely)
 	} slots[kRing];
 	uint64_t seq = 0;
@@ -187,6 +188,8 @@ struct b2r_context
 	// a frame that turns out to have them after all gets its long lists canonicalised when they are read.
 	bool longLikely = true, lastLongSkipped = false;
 	size_t overflowNeed = 0;
+	// raster grid (launchRaster): work items of the last harvested frame and the worst-case grid they were counted under
+	uint32_t rasterItemsHint = 0, rasterHintBlocks = 0, lastRasterBlocks = 0;
 	double stageAccum[B2R_NUM_STAGES] = {};
 	float stageLast[B2R_NUM_STAGES] = {};
 	uint64_t stageFrames = 0;
@@ -463,25 +466,49 @@ cudaError_t launchFrameKernel(const b2r_context* c, void (*kernel)(P...), dim3 g
 // the raster kernel instantiation of a frame: fill rule, fragment counter, light variant (the frame cannot reach the
 // texture / visualiser paths)
 // `blocks` = the 16x16 pixel blocks of the frame, an upper bound of the kernel's work items (CTAs behind the last item leave at once)
-cudaError_t launchRaster(const b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool otf = false)
+// The raster kernel + its tail (raster_kernel.cuh).  `blocks` = the worst case, every tile of this rank a work item; the
+// main grid follows the item count of the last finished frame of the same tile grid (rasterItemsHint, harvestSlot), the
+// tail's CTAs stride over the items behind it.  Without a hint - first frames, after a change of the tile grid - the
+// main grid is the worst case and there is no tail.
+cudaError_t launchRaster(b2r_context* c, uint32_t blocks, cudaStream_t s, const RasterArgs& A, const FrameParams& fp, bool textured, bool otf = false)
 {
 	const int variant = (c->fillTopLeft ? 1 : 0) | (c->countFragments ? 2 : 0) | (textured ? 4 : 0) | (otf ? 8 : 0);
 	const dim3 block(kTile * kTile);
-	// measuring aid: B2R_DEBUG_RASTER_GRID clamps the grid (work items behind it are NOT rendered) - what do the CTAs cost
-	// that find no work item and leave at once?
-	static const int clamp = [] { const char* e = getenv("B2R_DEBUG_RASTER_GRID"); return e ? atoi(e) : 0; }();
-	const dim3 grid(clamp > 0 ? std::min<uint32_t>(blocks, (uint32_t)clamp) : blocks);
-#define B2R_RASTER_CASE(v, tl, cnt, tex) case v: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, false>, grid, block, 0, s, A, fp); \
-	case v + 8: return launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, true>, grid, block, 0, s, A, fp);
+	uint32_t mainBlocks = blocks;
+	// B2R_RASTER_GRID_HINT=0 in the environment: always the worst-case grid (A/B and debugging aid)
+	static const bool useHint = [] { const char* e = getenv("B2R_RASTER_GRID_HINT"); return !e || atoi(e) != 0; }();
+	if (useHint && c->rasterHintBlocks == blocks && c->rasterItemsHint)
+		mainBlocks = std::min<uint32_t>(blocks, c->rasterItemsHint + c->rasterItemsHint / 4u + 256u);
+	const dim3 grid(mainBlocks);
+	c->lastRasterBlocks = blocks;
+	cudaError_t e = cudaErrorInvalidValue;
+#define B2R_RASTER_CASE(v, tl, cnt, tex) case v: e = launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, false>, grid, block, 0, s, A, fp); break; \
+	case v + 8: e = launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, true>, grid, block, 0, s, A, fp); break;
 	switch (variant)
 	{
 	B2R_RASTER_CASE(0, false, false, false) B2R_RASTER_CASE(1, true, false, false)
 	B2R_RASTER_CASE(2, false, true, false)  B2R_RASTER_CASE(3, true, true, false)
 	B2R_RASTER_CASE(4, false, false, true)  B2R_RASTER_CASE(5, true, false, true)
 	B2R_RASTER_CASE(6, false, true, true)   B2R_RASTER_CASE(7, true, true, true)
-	default: return cudaErrorInvalidValue;
+	default: break;
 	}
 #undef B2R_RASTER_CASE
+	++c->kernelsLaunched;
+	if (e != cudaSuccess || mainBlocks == blocks) return e;
+	const dim3 tailGrid(std::min<uint32_t>(blocks - mainBlocks, (uint32_t)c->numSMs * 2u));
+#define B2R_TAIL_CASE(v, tl, cnt, tex) case v: e = launchFrameKernel(c, raster_tail_kernel<tl, cnt, tex, false>, tailGrid, block, 0, s, A, fp, mainBlocks); break; \
+	case v + 8: e = launchFrameKernel(c, raster_tail_kernel<tl, cnt, tex, true>, tailGrid, block, 0, s, A, fp, mainBlocks); break;
+	switch (variant)
+	{
+	B2R_TAIL_CASE(0, false, false, false) B2R_TAIL_CASE(1, true, false, false)
+	B2R_TAIL_CASE(2, false, true, false)  B2R_TAIL_CASE(3, true, true, false)
+	B2R_TAIL_CASE(4, false, false, true)  B2R_TAIL_CASE(5, true, false, true)
+	B2R_TAIL_CASE(6, false, true, true)   B2R_TAIL_CASE(7, true, true, true)
+	default: break;
+	}
+#undef B2R_TAIL_CASE
+	++c->kernelsLaunched;
+	return e;
 }
 
 // persistent grid of the setup kernel: as many CTAs as are resident at once (each strides over the 256-primitive chunks)
@@ -541,6 +568,16 @@ int harvestSlot(b2r_context* c, b2r_context::Slot& slot)
 	c->lastLongSkipped = slot.longSkipped;
 	if (slot.hInfo->frameInfo[1])
 		c->overflowNeed = std::max(c->overflowNeed, (size_t)slot.hInfo->frameInfo[0]);
+	else if (slot.rasterBlocks)
+	{
+		// work items of that frame's raster kernel: the blocks of the non-empty classes + the batches of empty ones
+		const uint32_t subs = ((c->binW + kTile - 1) / kTile) * ((c->binH + kTile - 1) / kTile);
+		unsigned long long items = 0;
+		for (uint32_t k = 0; k + 1 < kTileClasses; ++k) items += slot.hInfo->frameInfo[kInfoClassBase + k] * subs;
+		items += (slot.hInfo->frameInfo[kInfoClassBase + kTileClasses - 1] * subs + kEmptyBatch - 1) / kEmptyBatch;
+		c->rasterItemsHint = (uint32_t)std::min<unsigned long long>(items, slot.rasterBlocks);
+		c->rasterHintBlocks = slot.rasterBlocks;
+	}
 	if (slot.hInfo->frameInfo[7])
 		return fail(c, B2R_E_STATE, "sharded front end: a peer rank did not reach the frame barrier within 4 s");
 	if (slot.timed)
@@ -687,6 +724,7 @@ int enqueueFrame(b2r_context* c)
 		int r = harvestSlot(c, slot); if (r) return r;
 	}
 	slot.timed = c->stageTimers != 0;
+	c->lastRasterBlocks = 0;
 	slot.exchanged = slot.timed && c->shard.bound;
 	memcpy(slot.hViewProj, rc.viewProj, 64);
 	if (c->meshStaticDirty) { int r = uploadMeshStatic(c, slot, s); if (r) return r; }
@@ -856,7 +894,6 @@ int enqueueFrame(b2r_context* c)
 		{
 			// light variant when the frame cannot reach the texture / visualiser paths
 			CU(c, launchRaster(c, owned * fp.subX * fp.subY, s, A, fp, rc.vis != 0 || c->anyDiffuse));
-			++c->kernelsLaunched;
 		}
 		// the vertex stage of frame f+2 may overwrite pos4 / constants of this parity once this raster is done
 		// (pipelined: the whole front end of frame f+2 re-uses this bin set, whose counters publish_info_kernel
@@ -890,6 +927,7 @@ int enqueueFrame(b2r_context* c)
 	CU(c, cudaEventRecord(slot.done, s));
 	CU(c, cudaGetLastError());
 	slot.pending = true;
+	slot.rasterBlocks = c->lastRasterBlocks;
 	++c->seq;
 	c->haveFrame = true;
 	return B2R_OK;
@@ -980,6 +1018,7 @@ int enqueueFrameRing(b2r_context* c)
 		int r = harvestSlot(c, slot); if (r) return r;
 	}
 	slot.timed = c->stageTimers != 0;
+	c->lastRasterBlocks = 0;
 	slot.exchanged = slot.timed && sh.bound;
 	memcpy(slot.hViewProj, rc.viewProj, 64);
 	// (the copy goes to the caller's stream, which has joined every frame enqueued so far - their constants kernels have
@@ -1138,7 +1177,6 @@ int enqueueFrameRing(b2r_context* c)
 			// sliced vertex stage: this rank has transformed the vertices of its own primitive slice only - the raster kernel
 			// transforms the vertices of its list entries and of its pixels' winners itself
 			CU(c, launchRaster(c, owned * fp.subX * fp.subY, rs, A, fp, rc.vis != 0 || c->anyDiffuse, sliced));
-			++c->kernelsLaunched;
 		}
 		if (sh.bound)
 		{
@@ -1164,6 +1202,7 @@ int enqueueFrameRing(b2r_context* c)
 	CU(c, cudaStreamWaitEvent(s, c->ringDone[k], 0));
 	CU(c, cudaGetLastError());
 	slot.pending = true;
+	slot.rasterBlocks = c->lastRasterBlocks;
 	++c->seq;
 	c->haveFrame = true;
 	return B2R_OK;

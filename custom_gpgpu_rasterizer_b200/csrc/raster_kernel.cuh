@@ -593,10 +593,10 @@ __device__ __forceinline__ void fetchPositions(const RasterArgs& A, const uint4&
 	}
 }
 
+// One work item of the raster kernel, by the whole CTA.  False: the frame has no item of that index (or is void).
 template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF>
-__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
+__device__ __forceinline__ bool rasterWorkItem(const RasterArgs& A, const FrameParams& fp, const uint32_t itemIdx)
 {
-	pdlPrologue();
 	__shared__ __align__(16) TriBig sBig[kListChunk];   // the pixel-parallel triangles of the block
 	__shared__ __align__(16) uint32_t sIds[kStage];    // the tile's list (primitive ids), staged for the sort and the sweep
 	__shared__ unsigned long long sKey[kTile * kTile]; // depth/winner of the triangle-parallel path
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 	__shared__ uint32_t sNumBig[2];                    // big-triangle count of the current / the next list chunk
 	__shared__ uint32_t sSortFallback;
 
-	if (A.frameInfo[1]) return;      // list-capacity overflow: frame is re-run by the host
+	if (A.frameInfo[1]) return false;      // list-capacity overflow: frame is re-run by the host
 	const int tid = threadIdx.x;
 	const uint32_t lane = (uint32_t)tid & 31u, warp = (uint32_t)tid >> 5;
 	const uint32_t nTilesAll = fp.binsX * fp.binsY;
@@ -617,12 +617,12 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 	for (uint32_t c = 0; c < kTileClasses; ++c)
 	{
 		const uint32_t blocks = (uint32_t)__ldg(A.frameInfo + kInfoClassBase + c) * subs;
-		if (blockIdx.x >= run) { cls = c; start = run; }
+		if (itemIdx >= run) { cls = c; start = run; }
 		if (c + 1 == kTileClasses) emptyBlocks = blocks;
 		run += (c + 1 < kTileClasses) ? blocks : (blocks + kEmptyBatch - 1u) / kEmptyBatch;
 	}
-	if (blockIdx.x >= run) return;
-	uint32_t v0 = blockIdx.x - start, v1 = v0 + 1;
+	if (itemIdx >= run) return false;
+	uint32_t v0 = itemIdx - start, v1 = v0 + 1;
 	if (cls == kTileClasses - 1u)
 	{
 		v0 *= kEmptyBatch;
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 				if (px < ex && py < ey) storePixel(bins[k], subIdx[k], row * kTile + (lane & (kTile - 1)), (size_t)px + (size_t)py * fp.width, clear, 0x7FFFFFFF, 0.f, kNoPrim);
 			}
 		}
-		return;
+		return true;
 	}
 	{
 		uint32_t sub;
@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 					}
 			}
 		}
-		if (!live) return;
+		if (!live) return true;
 
 		// ---- deferred shade of the winner (PS_Kernel, CUDARenderer.cu:833-897) + ROP write-back
 		const size_t pix = (size_t)px + (size_t)py * fp.width;
@@ -996,6 +996,27 @@ __global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF))
 		}
 		storePixel(bin, sub, (uint32_t)tid, pix, colour, depthOut, zOut, prim);
 	}
+	return true;
+}
+
+// The grid of the raster kernel.  The host cannot know how many work items a frame has (the scan kernel counts them on the
+// device) and a grid for the worst case - every tile a work item - is mostly CTAs that find nothing and leave: on a 4K
+// frame of BASELINE config 3 two thirds of 32 400, ~2 ns each = 40 of the kernel's 117 us (measured with a clamped grid).
+// So the library sizes the grid by the item count of the last frame it has seen finish (+ 25 % + 256) and launches a TAIL
+// behind it: a few CTAs that stride over whatever items lie beyond the main grid - normally none.  The tail is the same
+// code in a loop, compiled with its own register budget (the loop costs the one-item kernel ~100 bytes of spills).
+template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF>
+__global__ void __launch_bounds__(kTile * kTile, rasterCtasPerSM(TEXTURED, OTF)) raster_shade_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp)
+{
+	pdlPrologue();
+	rasterWorkItem<TOPLEFT, COUNT, TEXTURED, OTF>(A, fp, blockIdx.x);
+}
+template <bool TOPLEFT, bool COUNT, bool TEXTURED, bool OTF>
+__global__ void __launch_bounds__(kTile * kTile, 2) raster_tail_kernel(const __grid_constant__ RasterArgs A, const __grid_constant__ FrameParams fp, uint32_t firstItem)
+{
+	pdlPrologue();
+	for (uint32_t item = firstItem + blockIdx.x; rasterWorkItem<TOPLEFT, COUNT, TEXTURED, OTF>(A, fp, item); item += gridDim.x)
+		__syncthreads();      // (threads that left the item early must not touch the shared state of the next one yet)
 }
 
 // Sharded front end + direct path.  Every rank resolves the small triangles of ITS primitive slice into its own key

@@ -5,6 +5,8 @@ relative, 8-bit colour within +-1 LSB with at most 0.1 % of pixels beyond and on
 edges.  Because the kernels and the oracle follow the same arithmetic the tests assert the
 stronger property wherever it holds: bit-exact vertices, visibility, bins, depth and winners.
 """
+import copy
+
 import numpy as np
 import pytest
 
@@ -339,6 +341,46 @@ def test_moving_meshes_set_world_frames_in_flight():
             assert np.array_equal(counts, o["bin_counts"]) and np.array_equal(ids, o["bin_ids"])
             total, visible = r.stats()
             assert visible == o["visible_tris"]
+
+
+@pytest.mark.parametrize("ring", [0, 3])
+def test_raster_grid_follows_the_frame_and_the_tail_catches_the_rest(ring):
+    """The raster kernel's grid is sized by the work items of the last frame the library saw finish (+ 25 % + 256) and a tail
+    kernel strides over the items behind it (csrc/b2r.cu launchRaster).  Far away the sphere grid covers a few tiles; then
+    the camera jumps close and most tiles are work items - many more than the grid the far frames suggested: every frame,
+    the jump included, must still be the oracle's, in synchronous frames and with frames in flight."""
+    from custom_gpgpu_rasterizer_b200 import _lib
+    from custom_gpgpu_rasterizer_b200.renderer import Renderer, host_camera
+    sc = scenes.sphere_grid_scene(1280, 720, nx=6, ny=4, stacks=13, slices=16, cam_z=120.0)
+    far, near = (0.0, 0.0, 120.0), (0.0, 0.0, 9.0)
+    want = {}
+    for name, pos in (("far", far), ("near", near)):
+        s2 = copy.copy(sc)
+        s2.cam_pos = pos
+        want[name] = oracle_lib.render(s2, fill_rule=1)["framebuffer"]
+    tiles = (sc.width // 16) * (sc.height // 16)
+    clear = want["far"][0, 0]
+    cov_far, cov_near = (int(np.count_nonzero((want[k] != clear).reshape(sc.height // 16, 16, sc.width // 16, 16).any(axis=(1, 3)))) for k in ("far", "near"))
+    assert cov_far * 1.25 + (tiles - cov_far) / 16 + 256 < cov_near, f"the scene does not outgrow the hinted grid ({cov_far} -> {cov_near} covered tiles)"
+    with Renderer(sc.width, sc.height) as r:
+        if ring:
+            r.set_option(_lib.OPT_FRAME_RING, ring)
+        r.load_scene(sc)
+        cam = {k: host_camera(p, sc.fov_deg, sc.width, sc.height, sc.near, sc.far) for k, p in (("far", far), ("near", near))}
+        order = ["far"] * 6 + ["near"] * 6 + ["far"] * 3 + ["near"]
+        bufs = [np.zeros((sc.height, sc.width), np.uint32) for _ in order]
+        launches = []
+        for k, name in enumerate(order):
+            r.render(cam[name], sc.cull, sc.sample, sc.vis, sync=False)
+            r.present_async(bufs[k])
+            if not ring:
+                r.present_wait()
+                launches.append(r.counters()["kernels_launched"])
+        r.present_wait()
+        for k, name in enumerate(order):
+            assert np.array_equal(bufs[k], want[name]), f"ring {ring}: frame {k} ({name}) is not the oracle's frame"
+        # the first frame has no hint (one raster launch); a hinted frame has the tail behind the main grid
+        assert ring or (max(launches) == min(launches) + 1 and launches[0] == min(launches) and launches[1] == max(launches)), launches
 
 
 @pytest.mark.parametrize("ring", [2, 3, 4])

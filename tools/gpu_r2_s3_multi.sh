@@ -9,7 +9,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 port=29980
 for v in main "$@"; do
 	port=$((port + 1))
-	if [ $v = main ]; then unset B2R_LIBRARY; else export B2R_LIBRARY=$PWD/build/variants/libb2r_$v.so; fi
+	unset B2R_LIBRARY B2R_RASTER_GRID_HINT
+	if [ $v = nohint ]; then export B2R_RASTER_GRID_HINT=0; elif [ $v != main ]; then export B2R_LIBRARY=$PWD/build/variants/libb2r_$v.so; fi
 	timeout 120 $TR --master-port $port bench.py --gpus $N --steps 40 --warmup 5 --no-cpu-baseline --no-fill > $O/bench_$v.json 2> $O/bench_$v.err
 	python - "$O/bench_$v.json" "$v" <<'PY'
 import json,sys
