@@ -9,7 +9,7 @@ import sys
 
 STAGE_OF = {"build_constants_kernel": "vertex", "vertex_transform_kernel": "vertex", "frame_clear_kernel": "vertex",
             "triangle_setup_kernel": "setup", "bin_big_count_kernel": "binning", "tile_scan_kernel": "binning", "bin_scatter_kernel": "binning",
-            "bin_sort_long_kernel": "binning", "bin_sort_tiles_kernel": "binning", "raster_shade_kernel": "raster_shade", "publish_info_kernel": "raster_shade"}
+            "bin_sort_long_kernel": "binning", "bin_sort_tiles_kernel": "binning", "raster_shade_kernel": "raster_shade", "raster_tail_kernel": "raster_shade", "publish_info_kernel": "raster_shade"}
 
 
 def num(x):
