@@ -155,6 +155,15 @@ def test_gpu_unit_tests_on_the_emulation(emu_env):
             "assert lib.b2r_selftest_division(0, 1 << 22, 7, C.byref(bad)) == 0 and bad.value == 0, bad.value\nprint('division ok')")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=emu_env, cwd=ROOT)
     assert res.returncode == 0 and "division ok" in res.stdout, res.stdout + res.stderr[-2000:]
+    # the sign-only back-face test against the reference's normalise + dot on 2^23 adversarial decisions per seed (here with
+    # glibc's correctly rounded sqrtf / division standing in for sqrt.rn / rcp.rn; 2^33 per seed on hardware is a -m gpu test)
+    code = ("import ctypes as C\nfrom custom_gpgpu_rasterizer_b200._lib import lib\n"
+            "for seed in (1, 2, 3):\n"
+            "    counts = (C.c_uint64 * 2)(7, 0)\n"
+            "    assert lib.b2r_selftest_cull(0, 1 << 22, seed, counts) == 0 and counts[0] == 0 and counts[1] > (1 << 20), list(counts)\n"
+            "print('cull ok')")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=emu_env, cwd=ROOT)
+    assert res.returncode == 0 and "cull ok" in res.stdout, res.stdout + res.stderr[-2000:]
 
 
 def test_raster_grid_hint_and_tail_on_the_emulation(emu_env):
