@@ -190,6 +190,7 @@ struct b2r_context
 	size_t overflowNeed = 0;
 	// raster grid (launchRaster): work items of the last harvested frame and the worst-case grid they were counted under
 	uint32_t rasterItemsHint = 0, rasterHintBlocks = 0, lastRasterBlocks = 0;
+	uint32_t rasterHintMinSaving = 8192;      // CTAs the hinted grid must save before the tail launch is worth it (launchRaster)
 	double stageAccum[B2R_NUM_STAGES] = {};
 	float stageLast[B2R_NUM_STAGES] = {};
 	uint64_t stageFrames = 0;
@@ -478,7 +479,16 @@ cudaError_t launchRaster(b2r_context* c, uint32_t blocks, cudaStream_t s, const 
 	// B2R_RASTER_GRID_HINT=0 in the environment: always the worst-case grid (A/B and debugging aid)
 	static const bool useHint = [] { const char* e = getenv("B2R_RASTER_GRID_HINT"); return !e || atoi(e) != 0; }();
 	if (useHint && c->rasterHintBlocks == blocks && c->rasterItemsHint)
-		mainBlocks = std::min<uint32_t>(blocks, c->rasterItemsHint + c->rasterItemsHint / 4u + 256u);
+	{
+		// Only where it was measured to pay: the tail is one more launch in the frame's chain (~5 us by itself), so the
+		// smaller grid has to save more than that.  4K config 3 (8 927 CTAs fewer): raster 116 -> 109 us.  1080p vehicle
+		// (6 500 fewer): 50.3 -> 50.7 us, a wash.  640x480 vehicle (640 fewer, main grid below one wave): the stage took
+		// 80 us instead of 37 - not understood, and no GPU time left to look into it - hence the floor of 8 192 CTAs
+		// (b2r_context::rasterHintMinSaving; B2R_RASTER_HINT_MIN_SAVING in the environment of b2r_create overrides it: the tests
+		// exercise the tail on small frames).
+		const uint32_t hinted = std::min<uint32_t>(blocks, c->rasterItemsHint + c->rasterItemsHint / 4u + 256u);
+		if (blocks - hinted >= c->rasterHintMinSaving) mainBlocks = hinted;
+	}
 	const dim3 grid(mainBlocks);
 	c->lastRasterBlocks = blocks;
 	cudaError_t e = cudaErrorInvalidValue;
@@ -1414,6 +1424,7 @@ int b2r_create(int device, uint32_t width, uint32_t height, b2r_context** out)
 	b2r_context* c = new (std::nothrow) b2r_context;
 	if (!c) return fail(nullptr, B2R_E_INVALID, "out of host memory");
 	c->device = device; c->width = width; c->height = height;
+	if (const char* e = getenv("B2R_RASTER_HINT_MIN_SAVING")) c->rasterHintMinSaving = (uint32_t)std::max(0, atoi(e));      // testing aid (launchRaster)
 	if (const char* e = getenv("B2R_OVERLAP_VERTEX")) c->overlapVertex = atoi(e) != 0;
 	if (const char* e = getenv("B2R_PDL")) c->usePdl = atoi(e) != 0;                           // debugging aid: programmatic dependent launch
 	if (const char* e = getenv("B2R_OVERLAP_FRONT")) c->overlapFront = atoi(e) != 0;           // see B2R_OPT_OVERLAP_FRONT

@@ -6,6 +6,7 @@ edges.  Because the kernels and the oracle follow the same arithmetic the tests 
 stronger property wherever it holds: bit-exact vertices, visibility, bins, depth and winners.
 """
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -346,7 +347,7 @@ def test_moving_meshes_set_world_frames_in_flight():
 @pytest.mark.parametrize("ring", [0, 3])
 def test_raster_grid_follows_the_frame_and_the_tail_catches_the_rest(ring):
     """The raster kernel's grid is sized by the work items of the last frame the library saw finish (+ 25 % + 256) and a tail
-    kernel strides over the items behind it (csrc/b2r.cu launchRaster).  Far away the sphere grid covers a few tiles; then
+    kernel strides over the items behind it (csrc/b2r.cu launchRaster; used where it saves at least 8 192 CTAs).  Far away the sphere grid covers a few tiles; then
     the camera jumps close and most tiles are work items - many more than the grid the far frames suggested: every frame,
     the jump included, must still be the oracle's, in synchronous frames and with frames in flight."""
     from custom_gpgpu_rasterizer_b200 import _lib
@@ -362,7 +363,14 @@ def test_raster_grid_follows_the_frame_and_the_tail_catches_the_rest(ring):
     clear = want["far"][0, 0]
     cov_far, cov_near = (int(np.count_nonzero((want[k] != clear).reshape(sc.height // 16, 16, sc.width // 16, 16).any(axis=(1, 3)))) for k in ("far", "near"))
     assert cov_far * 1.25 + (tiles - cov_far) / 16 + 256 < cov_near, f"the scene does not outgrow the hinted grid ({cov_far} -> {cov_near} covered tiles)"
-    with Renderer(sc.width, sc.height) as r:
+    # (the library uses the hinted grid only where it saves at least 8 192 CTAs - 4K frames; the override makes this small
+    # frame take the same path.  Read by b2r_create.)
+    os.environ["B2R_RASTER_HINT_MIN_SAVING"] = "0"
+    try:
+        r = Renderer(sc.width, sc.height)
+    finally:
+        del os.environ["B2R_RASTER_HINT_MIN_SAVING"]
+    with r:
         if ring:
             r.set_option(_lib.OPT_FRAME_RING, ring)
         r.load_scene(sc)
