@@ -190,6 +190,7 @@ struct b2r_context
 	size_t overflowNeed = 0;
 	// raster grid (launchRaster): work items of the last harvested frame and the worst-case grid they were counted under
 	uint32_t rasterItemsHint = 0, rasterHintBlocks = 0, lastRasterBlocks = 0;
+	bool rasterTailTouched[16] = {};
 	uint32_t rasterHintMinSaving = 8192;      // CTAs the hinted grid must save before the tail launch is worth it (launchRaster)
 	double stageAccum[B2R_NUM_STAGES] = {};
 	float stageLast[B2R_NUM_STAGES] = {};
@@ -492,6 +493,26 @@ cudaError_t launchRaster(b2r_context* c, uint32_t blocks, cudaStream_t s, const 
 	const dim3 grid(mainBlocks);
 	c->lastRasterBlocks = blocks;
 	cudaError_t e = cudaErrorInvalidValue;
+	if (!c->rasterTailTouched[variant])
+	{
+		// First raster launch of this variant: query its tail kernel, so that CUDA's lazy loading brings the function in now
+		// and not with the first hinted frame - which comes a few frames later, possibly inside somebody's timed region
+		// (a load stalls the host for a millisecond or two).
+		int n = 0;
+#define B2R_TOUCH_CASE(v, tl, cnt, tex) case v: (void)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_tail_kernel<tl, cnt, tex, false>, (int)(kTile * kTile), 0); break; \
+	case v + 8: (void)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, raster_tail_kernel<tl, cnt, tex, true>, (int)(kTile * kTile), 0); break;
+		switch (variant)
+		{
+		B2R_TOUCH_CASE(0, false, false, false) B2R_TOUCH_CASE(1, true, false, false)
+		B2R_TOUCH_CASE(2, false, true, false)  B2R_TOUCH_CASE(3, true, true, false)
+		B2R_TOUCH_CASE(4, false, false, true)  B2R_TOUCH_CASE(5, true, false, true)
+		B2R_TOUCH_CASE(6, false, true, true)   B2R_TOUCH_CASE(7, true, true, true)
+		default: break;
+		}
+#undef B2R_TOUCH_CASE
+		(void)cudaGetLastError();
+		c->rasterTailTouched[variant] = true;
+	}
 #define B2R_RASTER_CASE(v, tl, cnt, tex) case v: e = launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, false>, grid, block, 0, s, A, fp); break; \
 	case v + 8: e = launchFrameKernel(c, raster_shade_kernel<tl, cnt, tex, true>, grid, block, 0, s, A, fp); break;
 	switch (variant)
